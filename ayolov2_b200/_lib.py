@@ -1,0 +1,118 @@
+"""ctypes binding of libay2.so (include/ay2.h). Plain pointers and sizes only; PyTorch owns all memory.
+
+There is no CPU fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+_LIB_PATH = Path(__file__).resolve().parent / "libay2.so"
+_lib: Optional[C.CDLL] = None
+
+ACT_NONE, ACT_SILU = 0, 1
+DT_U8, DT_F32 = 0, 1
+
+
+class ConvDesc(C.Structure):
+    """ay2_conv_desc (include/ay2.h)."""
+
+    _fields_ = [
+        ("batch", C.c_int32),
+        ("in_h", C.c_int32), ("in_w", C.c_int32),
+        ("cin", C.c_int32), ("in_cstride", C.c_int32),
+        ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("cout", C.c_int32), ("out_cstride", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32),
+        ("stride", C.c_int32), ("pad", C.c_int32),
+        ("act", C.c_int32), ("res_cstride", C.c_int32),
+        ("cout_pad", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class NmsParams(C.Structure):
+    """ay2_nms_params (include/ay2.h)."""
+
+    _fields_ = [
+        ("iou_thres", C.c_double),
+        ("conf_thres", C.c_float), ("max_wh", C.c_float),
+        ("batch", C.c_int32), ("n", C.c_int32), ("no", C.c_int32),
+        ("multi_label", C.c_int32), ("agnostic", C.c_int32),
+        ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_candidates", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/ay2.h
+_PROTOS = {
+    "ay2_version": (C.c_int, []),
+    "ay2_last_error_string": (C.c_char_p, []),
+    "ay2_launch_count": (C.c_int64, []),
+    "ay2_conv_block_n": (C.c_int, [C.c_int32]),
+    "ay2_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p)]),
+    "ay2_conv_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ay2_conv_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ay2_conv_plan_flops": (C.c_double, [C.c_void_p]),
+    "ay2_conv_reference_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "ay2_space_to_depth": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                     C.c_void_p]),
+    "ay2_sppf_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ay2_upsample2x": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                 C.c_int32, C.c_void_p]),
+    "ay2_head_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ay2_nms_workspace_bytes": (C.c_size_t, [C.POINTER(NmsParams)]),
+    "ay2_nms_batched": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load libay2.so (once). Raises if it has not been built (`python -m ayolov2_b200._build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "ayolov2_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list:
+    return sorted(_PROTOS)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ay2_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"libay2 {what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().ay2_launch_count())
+
+
+def ptr(t) -> int:
+    """Device address of a torch tensor (or 0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

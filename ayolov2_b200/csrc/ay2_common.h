@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: error string, CUDA checks, launch counter.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ay2.h"
+
+namespace ay2 {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define AY2_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::ay2::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return AY2_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define AY2_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::ay2::set_error(__VA_ARGS__);  \
+      return AY2_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+// Launch-error check that does not synchronise.
+#define AY2_CHECK_LAUNCH()                                                                    \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      ::ay2::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return AY2_ERR_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ay2

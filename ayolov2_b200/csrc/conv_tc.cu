@@ -1,0 +1,587 @@
+// Fused Conv2d + folded-BN bias + SiLU (+ residual) as an implicit GEMM on the sm_100a tensor cores.
+//
+//   out[b, oy, ox, n] = act( bias[n] + sum_{kh,kw,c} in[b, oy*s + kh - p, ox*s + kw - p, c] * w[n, kh, kw, c] ) (+ res)
+//
+// GEMM view: M = output pixels, N = Cout, K = KH*KW*Cin. One CTA tile is 128 output pixels x BLOCK_N
+// channels. The 128 pixels of a tile are NB spatial boxes of BH x BW pixels (BH*BW*NB = 128), so that the
+// A operand of one filter tap is NB *tiled* 4-D TMA boxes [CK ch][BW][BH][1] of the NHWC input, shifted by
+// the tap offset; TMA's out-of-bounds zero fill implements the convolution padding and every ragged edge
+// (partial boxes, M tail), and the same boxes written back with TMA stores implement the clipped output
+// write. Stride-2 convolutions read through four parity views of the input (one tensor map per (row,col)
+// parity, strides doubled), which makes every tap a stride-1 box again.
+//
+// Warp roles (256 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0 : TMA producer   (A boxes + B tile per K chunk into a NSTAGES ring, mbarrier full/empty)
+//   warp 1 : tcgen05.mma issuer (one lane), accumulators double-buffered in TMEM
+//   warp 2 : TMEM allocate / free
+//   warps 4-7 : epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem -> TMA store
+#include "ay2_common.h"
+#include "ay2_ptx.cuh"
+
+namespace ay2 {
+
+struct ConvKernelParams {
+  CUtensorMap tmA[4];  // input views: [0] for stride 1; [ph*2+pw] parity views for stride 2
+  CUtensorMap tmB;     // weights [Ktot][cout_pad] (K innermost)
+  CUtensorMap tmOut;   // output  [C][W][H][B]
+  CUtensorMap tmRes;   // residual (same geometry as output) if has_res
+  const float* bias;   // [cout_pad]
+  int num_m_tiles, num_n_tiles;
+  int boxes_x, boxes_per_img;
+  int BH, BW, NB;
+  int kh, kw, stride, pad;
+  int cin_chunks;  // Cin / CK
+  int cin;         // K extent per tap in the packed weights
+  int cout_pad;
+  int act, has_res;
+};
+
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kBiasFloats = 1024;
+
+template <int BLOCK_N, int CK>
+struct ConvCfg {
+  static constexpr int SWA = CK * 2;                 // operand row bytes == swizzle span
+  static constexpr int A_BYTES = 128 * SWA;
+  static constexpr int B_BYTES = BLOCK_N * SWA;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OC = BLOCK_N < 64 ? BLOCK_N : 64;  // channels per output slab
+  static constexpr int SWO = OC * 2;                       // output slab row bytes == swizzle span
+  static constexpr int SLAB_BYTES = 128 * SWO;
+  static constexpr int NSLAB = BLOCK_N / OC;
+  static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2;
+  static constexpr int TAIL_BYTES = kBiasFloats * 4 + 256;  // bias + barriers + tmem ptr
+  static constexpr int NSTAGES_RAW = (kSmemBudget - 1024 - STAGING_BYTES - TAIL_BYTES) / STAGE_BYTES;
+  static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
+  static constexpr int SMEM_BYTES = 1024 + NSTAGES * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 64..512, power of two
+  static_assert(NSTAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two");
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BLOCK_N, int CK>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N, CK>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: swizzle patterns repeat every 1024 B and UMMA descriptors assume base_offset 0
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* staging = smem + Cfg::NSTAGES * Cfg::STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kBiasFloats);
+  uint64_t* full_bar = bars;                      // [NSTAGES]
+  uint64_t* empty_bar = bars + Cfg::NSTAGES;      // [NSTAGES]
+  uint64_t* tmem_full = bars + 2 * Cfg::NSTAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint64_t* res_full = tmem_empty + 2;            // [1]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_k_chunks = p.kh * p.kw * p.cin_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::NSTAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    mbar_init(res_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+  for (int i = threadIdx.x; i < p.cout_pad && i < kBiasFloats; i += blockDim.x) bias_s[i] = p.bias[i];
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      const int box_rows = p.BH * p.BW;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / p.num_n_tiles;
+        const int n0 = (tile - m * p.num_n_tiles) * BLOCK_N;
+        int bx[8], by[8], bb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = m * p.NB + j;
+          const int b = q / p.boxes_per_img;
+          const int r = q - b * p.boxes_per_img;
+          const int py = r / p.boxes_x;
+          bb[j] = b;
+          by[j] = py * p.BH;
+          bx[j] = (r - py * p.boxes_x) * p.BW;
+        }
+        for (int kh = 0; kh < p.kh; ++kh) {
+          for (int kw = 0; kw < p.kw; ++kw) {
+            // input-box origin relative to the output-box origin for this tap
+            int dy, dx, view = 0;
+            if (p.stride == 1) {
+              dy = kh - p.pad;
+              dx = kw - p.pad;
+            } else {
+              const int uy = kh - p.pad, ux = kw - p.pad;
+              const int ph = uy & 1, pw = ux & 1;
+              dy = (uy - ph) >> 1;
+              dx = (ux - pw) >> 1;
+              view = ph * 2 + pw;
+            }
+            const CUtensorMap* tmA = &p.tmA[view];
+            const int kbase = (kh * p.kw + kw) * p.cin;
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
+              uint8_t* sb = sa + Cfg::A_BYTES;
+              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j < p.NB)
+                  tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, cc * CK, bx[j] + dx,
+                              by[j] + dy, bb[j]);
+              }
+              tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
+              if (++stage == Cfg::NSTAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const int acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kc = 0; kc < num_k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(stages + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < CK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_kmajor(a_addr + k * 32, Cfg::SWA);
+            const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
+            umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == Cfg::NSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int et = threadIdx.x - 128;  // 0..127 == accumulator row == TMEM lane
+    const int ewarp = warp - 4;        // == warp % 4 -> TMEM lane quadrant
+    const int box_rows = p.BH * p.BW;
+    int it = 0;
+    uint32_t res_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      const int m = tile / p.num_n_tiles;
+      const int n0 = (tile - m * p.num_n_tiles) * BLOCK_N;
+
+      if (et == 0) {
+        tma_store_wait_read<0>();  // previous tile's TMA stores have finished reading the staging buffer
+        if (p.has_res) {
+          mbar_expect_tx(res_full, Cfg::STAGING_BYTES);
+          for (int j = 0; j < p.NB; ++j) {
+            const int q = m * p.NB + j;
+            const int b = q / p.boxes_per_img;
+            const int r = q - b * p.boxes_per_img;
+            const int py = r / p.boxes_x;
+            const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
+#pragma unroll
+            for (int s = 0; s < Cfg::NSLAB; ++s)
+              tma_load_4d(&p.tmRes, res_full, staging + s * Cfg::SLAB_BYTES + j * box_rows * Cfg::SWO,
+                          n0 + s * Cfg::OC, ox, oy, b);
+          }
+        }
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      if (p.has_res) {
+        mbar_wait(res_full, res_phase);
+        res_phase ^= 1;
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        uint8_t* slab = staging + (c0 / Cfg::OC) * Cfg::SLAB_BYTES;
+        const int chunk0 = (c0 % Cfg::OC) / 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x = __uint_as_float(v[g * 8 + i]) + bias_s[n0 + c0 + g * 8 + i];
+            if (p.act == AY2_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+            f[i] = x;
+          }
+          uint4* dst = reinterpret_cast<uint4*>(slab + swizzled_offset<Cfg::SWO>(et, chunk0 + g));
+          if (p.has_res) {
+            const uint4 rv = *dst;
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 rf = __bfloat1622float2(r2[i]);
+              f[2 * i] += rf.x;
+              f[2 * i + 1] += rf.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+          *dst = o;
+        }
+      }
+      // accumulator drained -> hand the TMEM buffer back to the MMA warp
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      // staging complete -> TMA store
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int j = 0; j < p.NB; ++j) {
+          const int q = m * p.NB + j;
+          const int b = q / p.boxes_per_img;
+          const int r = q - b * p.boxes_per_img;
+          const int py = r / p.boxes_x;
+          const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
+#pragma unroll
+          for (int s = 0; s < Cfg::NSLAB; ++s)
+            tma_store_4d(&p.tmOut, staging + s * Cfg::SLAB_BYTES + j * box_rows * Cfg::SWO, n0 + s * Cfg::OC, ox,
+                         oy, b);
+        }
+        tma_store_commit();
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: plan = encoded tensor maps + launch configuration
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// NHWC bf16 activation view [C][W][H][B] with explicit element strides; box [boxc][bw][bh][1].
+static int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH,
+                          int64_t sB, int boxc, int bw, int bh) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AY2_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sB * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d box=%d,%d,%d strides=%lld,%lld,%lld) -> %d", C, W,
+              H, B, boxc, bw, bh, (long long)sW, (long long)sH, (long long)sB, (int)r);
+    return AY2_ERR_CUDA;
+  }
+  return AY2_OK;
+}
+
+static int encode_weight_map(CUtensorMap* tm, const void* base, int Ktot, int rows, int boxk, int boxn) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AY2_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)boxk, (cuuint32_t)boxn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights K=%d rows=%d box=%d,%d) -> %d", Ktot, rows, boxk, boxn, (int)r);
+    return AY2_ERR_CUDA;
+  }
+  return AY2_OK;
+}
+
+}  // namespace ay2
+
+using namespace ay2;
+
+struct ay2_conv_plan {
+  ConvKernelParams kp;
+  ay2_conv_desc desc;
+  int block_n, ck;
+  int grid;
+  size_t smem;
+  void (*kernel)(const ConvKernelParams);
+};
+
+extern "C" int ay2_conv_block_n(int32_t cout) {
+  if (cout <= 32) return 32;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  return 256;
+}
+
+template <int BN, int CK>
+static void bind_kernel(ay2_conv_plan* pl) {
+  pl->kernel = conv_tc_kernel<BN, CK>;
+  pl->smem = ConvCfg<BN, CK>::SMEM_BYTES;
+}
+
+static int pick_box(int H, int W, int* bh, int* bw) {
+  // candidate boxes (rows multiple of 8 keeps every box on a swizzle-pattern boundary; <= 8 boxes per tile)
+  static const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {8, 8},  {4, 16}, {16, 4},
+                                {2, 32}, {4, 8},  {8, 4},  {2, 16}, {4, 4},  {2, 8}, {1, 16}};
+  double best = 1e30;
+  int bi = -1;
+  for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
+    const int h = cand[i][0], w = cand[i][1];
+    const double cover = (double)ceil_div(H, h) * h * (double)ceil_div(W, w) * w;
+    // prefer less padding; break ties towards bigger boxes (fewer TMA ops)
+    const double cost = cover * (1.0 + 0.002 * (128 / (h * w)));
+    if (cost < best) {
+      best = cost;
+      bi = i;
+    }
+  }
+  *bh = cand[bi][0];
+  *bw = cand[bi][1];
+  return 0;
+}
+
+extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, const void* weight, const float* bias,
+                                    const void* residual, void* out, ay2_conv_plan** plan_out) {
+  AY2_REQUIRE(d && in && weight && bias && out && plan_out, "ay2_conv_plan_create: null argument");
+  AY2_REQUIRE(d->stride == 1 || d->stride == 2, "conv stride %d unsupported (1 or 2)", d->stride);
+  AY2_REQUIRE(d->cin % 16 == 0 && d->cin >= 16, "conv cin=%d must be a multiple of 16", d->cin);
+  AY2_REQUIRE(d->in_cstride % 8 == 0 && d->out_cstride % 8 == 0, "channel strides must be multiples of 8");
+  AY2_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh <= 7 && d->kw <= 7, "kernel %dx%d unsupported", d->kh, d->kw);
+  AY2_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(weight) & 15) == 0,
+              "conv buffers must be 16-byte aligned");
+  const int exp_oh = (d->in_h + 2 * d->pad - d->kh) / d->stride + 1;
+  const int exp_ow = (d->in_w + 2 * d->pad - d->kw) / d->stride + 1;
+  AY2_REQUIRE(exp_oh == d->out_h && exp_ow == d->out_w, "conv output size %dx%d does not match %dx%d", d->out_h,
+              d->out_w, exp_oh, exp_ow);
+  if (d->stride == 2) AY2_REQUIRE(d->in_h % 2 == 0 && d->in_w % 2 == 0, "stride-2 conv needs even input size");
+  const int bn = ay2_conv_block_n(d->cout);
+  AY2_REQUIRE(d->cout_pad >= d->cout && d->cout_pad % bn == 0, "cout_pad=%d must be a multiple of %d", d->cout_pad, bn);
+  AY2_REQUIRE(d->cout_pad <= kBiasFloats, "cout_pad=%d exceeds %d", d->cout_pad, kBiasFloats);
+  AY2_REQUIRE(d->res_cstride == 0 || residual, "residual stride given without a residual pointer");
+  AY2_REQUIRE(d->res_cstride % 8 == 0, "residual channel stride must be a multiple of 8");
+
+  ay2_conv_plan* pl = new ay2_conv_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->desc = *d;
+  const int ck = d->cin % 64 == 0 ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+  pl->block_n = bn;
+  pl->ck = ck;
+  ConvKernelParams& kp = pl->kp;
+  int bh, bw;
+  pick_box(d->out_h, d->out_w, &bh, &bw);
+  kp.BH = bh;
+  kp.BW = bw;
+  kp.NB = 128 / (bh * bw);
+  kp.boxes_x = ceil_div(d->out_w, bw);
+  const int boxes_y = ceil_div(d->out_h, bh);
+  kp.boxes_per_img = kp.boxes_x * boxes_y;
+  const long long total_boxes = (long long)kp.boxes_per_img * d->batch;
+  kp.num_m_tiles = (int)((total_boxes + kp.NB - 1) / kp.NB);
+  kp.num_n_tiles = d->cout_pad / bn;
+  kp.kh = d->kh;
+  kp.kw = d->kw;
+  kp.stride = d->stride;
+  kp.pad = d->pad;
+  kp.cin = d->cin;
+  kp.cin_chunks = d->cin / ck;
+  kp.cout_pad = d->cout_pad;
+  kp.act = d->act;
+  kp.has_res = d->res_cstride != 0;
+  kp.bias = bias;
+
+  int rc = AY2_OK;
+  const int64_t cs = d->in_cstride;
+  if (d->stride == 1) {
+    rc = encode_act_map(&kp.tmA[0], in, d->cin, d->in_w, d->in_h, d->batch, cs, cs * d->in_w,
+                        cs * d->in_w * d->in_h, ck, bw, bh);
+  } else {
+    for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
+      for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {
+        const uint8_t* base = static_cast<const uint8_t*>(in) + ((int64_t)ph * d->in_w + pw) * cs * 2;
+        rc = encode_act_map(&kp.tmA[ph * 2 + pw], base, d->cin, d->in_w / 2, d->in_h / 2, d->batch, 2 * cs,
+                            2 * cs * d->in_w, cs * d->in_w * d->in_h, ck, bw, bh);
+      }
+  }
+  if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn);
+  const int oc = bn < 64 ? bn : 64;
+  const int64_t os = d->out_cstride;
+  if (rc == AY2_OK)
+    rc = encode_act_map(&kp.tmOut, out, d->cout, d->out_w, d->out_h, d->batch, os, os * d->out_w,
+                        os * d->out_w * d->out_h, oc, bw, bh);
+  if (rc == AY2_OK && kp.has_res) {
+    const int64_t rs = d->res_cstride;
+    rc = encode_act_map(&kp.tmRes, residual, d->cout, d->out_w, d->out_h, d->batch, rs, rs * d->out_w,
+                        rs * d->out_w * d->out_h, oc, bw, bh);
+  }
+  if (rc != AY2_OK) {
+    delete pl;
+    return rc;
+  }
+
+#define AY2_BIND(BN, CKV)            \
+  if (bn == BN && ck == CKV) bind_kernel<BN, CKV>(pl);
+  AY2_BIND(32, 16) AY2_BIND(32, 32) AY2_BIND(32, 64)
+  AY2_BIND(64, 16) AY2_BIND(64, 32) AY2_BIND(64, 64)
+  AY2_BIND(128, 16) AY2_BIND(128, 32) AY2_BIND(128, 64)
+  AY2_BIND(256, 16) AY2_BIND(256, 32) AY2_BIND(256, 64)
+#undef AY2_BIND
+  if (!pl->kernel) {
+    delete pl;
+    set_error("no conv kernel for block_n=%d ck=%d", bn, ck);
+    return AY2_ERR_INVALID;
+  }
+  cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+  if (e != cudaSuccess) {
+    delete pl;
+    set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", pl->smem, cudaGetErrorString(e));
+    return AY2_ERR_CUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total_tiles = kp.num_m_tiles * kp.num_n_tiles;
+  pl->grid = total_tiles < sms ? total_tiles : sms;
+  *plan_out = pl;
+  return AY2_OK;
+}
+
+extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
+  AY2_REQUIRE(pl, "ay2_conv_plan_run: null plan");
+  pl->kernel<<<pl->grid, 256, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_conv_plan_destroy(ay2_conv_plan* pl) {
+  delete pl;
+  return AY2_OK;
+}
+
+extern "C" double ay2_conv_plan_flops(const ay2_conv_plan* pl) {
+  if (!pl) return 0.0;
+  const ay2_conv_desc& d = pl->desc;
+  return 2.0 * d.batch * d.out_h * d.out_w * (double)d.cout * d.kh * d.kw * d.cin;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference SIMT direct convolution (test infrastructure only)
+// ------------------------------------------------------------------------------------------------
+namespace ay2 {
+__global__ void conv_ref_simt_kernel(ay2_conv_desc d, const __nv_bfloat16* __restrict__ in,
+                                     const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)d.batch * d.out_h * d.out_w * d.cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % d.cout);
+    long long pix = idx / d.cout;
+    const int ox = (int)(pix % d.out_w);
+    const int oy = (int)((pix / d.out_w) % d.out_h);
+    const int b = (int)(pix / ((long long)d.out_w * d.out_h));
+    float acc = 0.f;
+    for (int kh = 0; kh < d.kh; ++kh) {
+      const int iy = oy * d.stride + kh - d.pad;
+      if (iy < 0 || iy >= d.in_h) continue;
+      for (int kw = 0; kw < d.kw; ++kw) {
+        const int ix = ox * d.stride + kw - d.pad;
+        if (ix < 0 || ix >= d.in_w) continue;
+        const __nv_bfloat16* ip = in + (((long long)b * d.in_h + iy) * d.in_w + ix) * d.in_cstride;
+        const __nv_bfloat16* wp = w + ((long long)n * d.kh * d.kw + kh * d.kw + kw) * d.cin;
+        for (int c = 0; c < d.cin; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+      }
+    }
+    acc += bias[n];
+    if (d.act == AY2_ACT_SILU) acc = acc / (1.0f + expf(-acc));
+    if (d.res_cstride) acc += __bfloat162float(res[pix * d.res_cstride + n]);
+    out[pix * d.out_cstride + n] = __float2bfloat16_rn(acc);
+  }
+}
+}  // namespace ay2
+
+extern "C" int ay2_conv_reference_simt(const ay2_conv_desc* d, const void* in, const void* weight, const float* bias,
+                                       const void* residual, void* out, void* stream) {
+  AY2_REQUIRE(d && in && weight && bias && out, "ay2_conv_reference_simt: null argument");
+  const long long total = (long long)d->batch * d->out_h * d->out_w * d->cout;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 32 ? (total + threads - 1) / threads : 148 * 32);
+  conv_ref_simt_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      *d, static_cast<const __nv_bfloat16*>(in), static_cast<const __nv_bfloat16*>(weight), bias,
+      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out));
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}

@@ -1,0 +1,354 @@
+// Batched non-max suppression for the whole batch in three launches, no host synchronisation.
+//
+// Reference: scripts/utils/metrics.py:285-443 (non_max_suppression, nms_type="nms") which loops over
+// images on the host and calls torchvision.ops.nms (:385). Semantics reproduced bit-for-bit on identical
+// fp32 inputs:
+//   candidates  : rows with obj > conf (:313,337); conf_c = cls_c * obj (:353, fp32 multiply);
+//                 best class = first arg-max (:363-364) or every class above conf when multi_label (:360-361)
+//   box         : xywh -> xyxy as x -/+ w/2 (scripts/utils/general.py:316-319), class offset cls*max_wh added
+//                 in fp32 (:383-384) for the suppression test only
+//   order       : descending score, ties by candidate order (torchvision's stable sort); cap max_nms (:378-379)
+//   suppression : greedy, IoU = inter / (area_i + area_j - inter) in fp32, suppressed iff IoU > iou_thres
+//   output      : first max_det kept rows [x1,y1,x2,y2,conf,cls] in kept order (:386-388)
+//
+// Kernel 1 (filter): one warp per 32 rows reads only the objectness column, then cooperatively scores the
+//   rows that pass and appends 64-bit keys  (~score_bits << 32 | row*nc + cls)  to a per-image list.
+// Kernel 2 (sort + scan): one CTA per image. Bitonic sort of the keys (shared memory up to 8192 keys, in
+//   global memory above), then the greedy scan in chunks of 256 sorted candidates: each chunk is first
+//   tested against the boxes kept so far, then a 256x256 bit matrix of within-chunk overlaps is built and
+//   resolved word by word by one warp. The scan stops as soon as max_det boxes are kept, which is what
+//   makes greedy NMS cheap: later candidates cannot change the first max_det decisions.
+#include "ay2_common.h"
+#include "ay2_ptx.cuh"
+
+namespace ay2 {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kSortSmemKeys = 8192;
+constexpr int kChunk = 256;
+constexpr int kChunkWords = kChunk / 32;
+constexpr int kMaxDetCap = 1024;
+
+__global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
+                                  unsigned long long* __restrict__ keys, long long key_stride, int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nc = p.no - 5;
+  const float* ip = pred + (long long)b * p.n * p.no;
+  unsigned long long* kb = keys + (long long)b * key_stride;
+  const int groups = (p.n + 31) / 32;
+  for (int g = warp_in_grid; g < groups; g += nwarps) {
+    const int row = g * 32 + lane;
+    const float obj = row < p.n ? ip[(long long)row * p.no + 4] : 0.f;
+    unsigned pass = __ballot_sync(0xffffffffu, row < p.n && obj > p.conf_thres);
+    while (pass) {
+      const int r = __ffs(pass) - 1;
+      pass &= pass - 1;
+      const int rrow = g * 32 + r;
+      const float robj = __shfl_sync(0xffffffffu, obj, r);
+      const float* cp = ip + (long long)rrow * p.no + 5;
+      if (p.multi_label) {
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int c = c0 + lane;
+          float conf = 0.f;
+          bool ok = false;
+          if (c < nc) {
+            conf = __fmul_rn(cp[c], robj);
+            ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&counts[b], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ok) {
+              const int slot = base + __popc(m & ((1u << lane) - 1));
+              if (slot < p.max_candidates)
+                kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) |
+                           static_cast<unsigned>(rrow * nc + c);
+            }
+          }
+        }
+      } else {
+        // first arg-max over classes (torch.max(1) keeps the first maximal index)
+        float best = -INFINITY;
+        int bidx = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+          const float conf = __fmul_rn(cp[c], robj);
+          if (conf > best) {
+            best = conf;
+            bidx = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ob > best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+          }
+        }
+        if (lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx])) {
+          const int slot = atomicAdd(&counts[b], 1);
+          if (slot < p.max_candidates)
+            kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) |
+                       static_cast<unsigned>(rrow * nc + bidx);
+        }
+      }
+    }
+  }
+}
+
+// IoU > thr exactly as torchvision's CPU kernel evaluates it (fp32 arithmetic, comparison against the
+// double threshold). The early-out is exact: a non-positive extent gives inter = 0 -> IoU 0 (or NaN) -> false
+// for any thr >= 0.
+__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const double thr) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  if (!(right > left) || !(bottom > top)) return false;
+  const float inter = __fmul_rn(__fsub_rn(right, left), __fsub_rn(bottom, top));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return static_cast<double>(iou) > thr;
+}
+
+template <typename Ptr>
+__device__ __forceinline__ void bitonic_sort(Ptr A, int N) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool asc = (i & k) == 0;
+        const unsigned long long a = A[i], b = A[l];
+        if ((a > b) == asc) {
+          A[i] = b;
+          A[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 1)
+    nms_sort_scan_kernel(const float* __restrict__ pred, ay2_nms_params p, unsigned long long* __restrict__ keys,
+                         long long key_stride, const int* __restrict__ counts, float* __restrict__ out_det,
+                         int* __restrict__ out_count, int* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);             // [kSortSmemKeys]
+  float4* cbo = reinterpret_cast<float4*>(skeys + kSortSmemKeys);                    // chunk boxes + class offset
+  float4* cbox = cbo + kChunk;                                                       // chunk boxes (output form)
+  float4* kbo = cbox + kChunk;                                                       // kept boxes + offset [kMaxDetCap]
+  float* carea = reinterpret_cast<float*>(kbo + kMaxDetCap);                         // [kChunk]
+  float* cconf = carea + kChunk;                                                     // [kChunk]
+  float* karea = cconf + kChunk;                                                     // [kMaxDetCap]
+  int* ccls = reinterpret_cast<int*>(karea + kMaxDetCap);                            // [kChunk]
+  int* alive = ccls + kChunk;                                                        // [kChunk]
+  int* kept_idx = alive + kChunk;                                                    // [kChunk]
+  unsigned* mask = reinterpret_cast<unsigned*>(kept_idx + kChunk);                   // [kChunk][kChunkWords]
+  __shared__ int s_kept, s_new;
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int nc = p.no - 5;
+  int n = counts[b];
+  if (n > p.max_candidates) {
+    n = p.max_candidates;
+    if (tid == 0) atomicExch(overflow, 1);
+  }
+  if (tid == 0) s_kept = 0;
+  if (n == 0) {
+    if (tid == 0) out_count[b] = 0;
+    return;
+  }
+  // ---------------------------------------------------------------- sort (ascending key == descending score)
+  int npow2 = 2;
+  while (npow2 < n) npow2 <<= 1;
+  unsigned long long* gk = keys + (long long)b * key_stride;
+  const unsigned long long* sorted;
+  if (npow2 <= kSortSmemKeys) {
+    for (int i = tid; i < npow2; i += blockDim.x) skeys[i] = i < n ? gk[i] : ~0ull;
+    __syncthreads();
+    bitonic_sort(skeys, npow2);
+    sorted = skeys;
+  } else {
+    for (int i = n + tid; i < npow2; i += blockDim.x) gk[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort(gk, npow2);
+    sorted = gk;
+  }
+  if (n > p.max_nms) n = p.max_nms;
+  const double thr = p.iou_thres;
+  const float* ip = pred + (long long)b * p.n * p.no;
+
+  // ---------------------------------------------------------------- greedy scan
+  for (int cs = 0; cs < n; cs += kChunk) {
+    const int kc = s_kept;
+    if (kc >= p.max_det) break;
+    const int cn = min(kChunk, n - cs);
+    if (tid < kChunk) {
+      int al = 0;
+      if (tid < cn) {
+        const unsigned long long key = sorted[cs + tid];
+        const unsigned idx = static_cast<unsigned>(key);
+        const float score = __uint_as_float(~static_cast<unsigned>(key >> 32));
+        const int row = idx / nc;
+        const int cls = idx - row * nc;
+        const float* rp = ip + (long long)row * p.no;
+        const float4 r = make_float4(rp[0], rp[1], rp[2], rp[3]);
+        // general.py:316-319 with ratio = wh = 1, pad = 0  (1*1*(x -+ w/2) + 0)
+        float4 bx;
+        bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+        bx.y = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+        bx.z = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+        bx.w = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+        const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(cls), p.max_wh);
+        float4 bo;
+        bo.x = __fadd_rn(bx.x, off);
+        bo.y = __fadd_rn(bx.y, off);
+        bo.z = __fadd_rn(bx.z, off);
+        bo.w = __fadd_rn(bx.w, off);
+        cbox[tid] = bx;
+        cbo[tid] = bo;
+        carea[tid] = __fmul_rn(__fsub_rn(bo.z, bo.x), __fsub_rn(bo.w, bo.y));
+        cconf[tid] = score;
+        ccls[tid] = cls;
+        al = 1;
+      }
+      alive[tid] = al;
+    }
+    __syncthreads();
+    // (1) chunk vs. boxes kept so far
+    for (int t = tid; t < cn * kc; t += blockDim.x) {
+      const int k = t / cn;
+      const int c = t - k * cn;
+      if (alive[c] && iou_gt(kbo[k], karea[k], cbo[c], carea[c], thr)) alive[c] = 0;
+    }
+    __syncthreads();
+    // (2) within-chunk overlap bit matrix: mask[i][w] bit jj <=> j = 32w+jj > i and IoU(i,j) > thr
+    for (int t = tid; t < kChunk * kChunkWords; t += blockDim.x) {
+      const int i = t / kChunkWords;
+      const int w = t - i * kChunkWords;
+      unsigned bits = 0;
+      if (i < cn && alive[i] && (w * 32 + 31) > i) {
+        const float4 bi = cbo[i];
+        const float ai = carea[i];
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = w * 32 + jj;
+          if (j > i && j < cn && alive[j] && iou_gt(bi, ai, cbo[j], carea[j], thr)) bits |= 1u << jj;
+        }
+      }
+      mask[t] = bits;
+    }
+    __syncthreads();
+    // (3) resolve the chunk, one 32-candidate word at a time
+    if (tid < 32) {
+      unsigned removed = 0xffffffffu;
+      if (lane < kChunkWords) {
+        unsigned a = 0;
+        for (int jj = 0; jj < 32; ++jj) a |= (alive[lane * 32 + jj] ? 1u : 0u) << jj;
+        removed = ~a;
+      }
+      int total = kc, nnew = 0;
+      for (int w = 0; w < kChunkWords && total < p.max_det; ++w) {
+        unsigned avail = ~__shfl_sync(0xffffffffu, removed, w);
+        while (avail && total < p.max_det) {
+          const int i = __ffs(avail) - 1;
+          const int gi = w * 32 + i;
+          avail &= ~(1u << i);
+          if (lane == 0) kept_idx[nnew] = gi;
+          ++nnew;
+          ++total;
+          const unsigned m = lane < kChunkWords ? mask[gi * kChunkWords + lane] : 0u;
+          removed |= m;
+          avail &= ~__shfl_sync(0xffffffffu, m, w);
+        }
+      }
+      if (lane == 0) s_new = nnew;
+    }
+    __syncthreads();
+    // (4) append the newly kept boxes and emit their output rows
+    const int nnew = s_new;
+    if (tid < nnew) {
+      const int gi = kept_idx[tid];
+      const int k = kc + tid;
+      kbo[k] = cbo[gi];
+      karea[k] = carea[gi];
+      float* o = out_det + ((long long)b * p.max_det + k) * 6;
+      const float4 bx = cbox[gi];
+      o[0] = bx.x;
+      o[1] = bx.y;
+      o[2] = bx.z;
+      o[3] = bx.w;
+      o[4] = cconf[gi];
+      o[5] = static_cast<float>(ccls[gi]);
+    }
+    __syncthreads();
+    if (tid == 0) s_kept = kc + nnew;
+    __syncthreads();
+  }
+  if (tid == 0) out_count[b] = s_kept;
+}
+
+constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys + sizeof(float4) * (2 * kChunk + kMaxDetCap) +
+                                 sizeof(float) * (2 * kChunk + kMaxDetCap) + sizeof(int) * 3 * kChunk +
+                                 sizeof(unsigned) * kChunk * kChunkWords;
+
+static long long key_stride_for(const ay2_nms_params* p) {
+  long long s = 2;
+  while (s < p->max_candidates) s <<= 1;
+  return s;
+}
+
+}  // namespace ay2
+
+using namespace ay2;
+
+// workspace layout: [counts int32 x B][overflow int32][pad to 256][keys u64 x B x key_stride]
+extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
+  if (!p) return 0;
+  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
+  return head + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p);
+}
+
+extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
+                               size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                               void* stream) {
+  AY2_REQUIRE(pred && p && workspace && out_det && out_count, "ay2_nms_batched: null pointer");
+  AY2_REQUIRE(p->no > 5 && p->n > 0 && p->batch > 0, "ay2_nms_batched: bad shape (batch=%d n=%d no=%d)", p->batch, p->n,
+              p->no);
+  AY2_REQUIRE(p->max_det >= 1 && p->max_det <= kMaxDetCap, "max_det=%d unsupported (1..%d)", p->max_det, kMaxDetCap);
+  AY2_REQUIRE(p->max_candidates >= 1, "max_candidates must be positive");
+  AY2_REQUIRE((long long)p->n * (p->no - 5) < (1LL << 32), "n*nc does not fit the 32-bit candidate index");
+  AY2_REQUIRE(workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace too small (%zu < %zu)", workspace_bytes,
+              ay2_nms_workspace_bytes(p));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
+  int* counts = static_cast<int*>(workspace);
+  int* overflow = counts + p->batch;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
+  const long long ks = key_stride_for(p);
+  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (p->batch + 1), st));
+  const int groups = (p->n + 31) / 32;
+  const int threads = 256;
+  int bx = (groups + (threads / 32) - 1) / (threads / 32);
+  if (bx > 64) bx = 64;
+  nms_filter_kernel<<<dim3(bx, p->batch), threads, 0, st>>>(pred, *p, class_mask, keys, ks, counts);
+  AY2_CHECK_LAUNCH();
+  static bool attr_set = false;
+  if (!attr_set) {
+    AY2_CHECK_CUDA(
+        cudaFuncSetAttribute(nms_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
+    attr_set = true;
+  }
+  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(pred, *p, keys, ks, counts, out_det, out_count,
+                                                                     overflow);
+  AY2_CHECK_LAUNCH();
+  if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  count_launch(2);
+  return AY2_OK;
+}

@@ -1,0 +1,191 @@
+"""Thin tensor-level wrappers over the C-ABI (one function / class per libay2 entry point).
+
+Everything here takes CUDA tensors that the caller owns; layouts are NHWC bf16 with explicit channel
+strides (a "view" of a wider buffer is expressed as (tensor, channel_offset, channels)).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, ConvDesc, NmsParams
+
+
+@dataclass
+class ActView:
+    """A channel slice [c0, c0+c) of an NHWC bf16 buffer of shape [B, H, W, Cs]."""
+
+    buf: torch.Tensor
+    c0: int
+    c: int
+
+    @property
+    def B(self) -> int:
+        return self.buf.shape[0]
+
+    @property
+    def H(self) -> int:
+        return self.buf.shape[1]
+
+    @property
+    def W(self) -> int:
+        return self.buf.shape[2]
+
+    @property
+    def cstride(self) -> int:
+        return self.buf.shape[3]
+
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + 2 * self.c0
+
+    def tensor(self) -> torch.Tensor:
+        return self.buf[..., self.c0:self.c0 + self.c]
+
+    def slice(self, c0: int, c: int) -> "ActView":
+        assert 0 <= c0 and c0 + c <= self.c
+        return ActView(self.buf, self.c0 + c0, c)
+
+
+def new_act(B: int, H: int, W: int, C_: int, device="cuda") -> ActView:
+    assert C_ % 8 == 0
+    return ActView(torch.empty((B, H, W, C_), dtype=torch.bfloat16, device=device), 0, C_)
+
+
+def conv_block_n(cout: int) -> int:
+    return int(_lib.load().ay2_conv_block_n(cout))
+
+
+def pack_conv_weight(w: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[Tuple[torch.Tensor, ...]] = None,
+                     eps: float = 1e-3) -> Tuple[torch.Tensor, torch.Tensor]:
+    """OIHW fp32 weight (+ optional BatchNorm (gamma, beta, mean, var)) -> K-major bf16 [Cout_pad, KH*KW*Cin]
+    and fp32 bias [Cout_pad] with the BN folded in (what kindle's YOLOModel.fuse() does, val.py:331)."""
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    if bn is not None:
+        gamma, beta, mean, var = [t.detach().float() for t in bn]
+        scale = gamma / torch.sqrt(var + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = beta - mean * scale
+        if bias is not None:
+            b = b + bias.detach().float() * scale
+    else:
+        b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    bn_tile = conv_block_n(cout)
+    cout_pad = (cout + bn_tile - 1) // bn_tile * bn_tile
+    wk = w.permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    wp = torch.zeros((cout_pad, kh * kw * cin), dtype=torch.bfloat16, device=w.device)
+    wp[:cout] = wk.to(torch.bfloat16)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp[:cout] = b
+    return wp.contiguous(), bp.contiguous()
+
+
+class ConvPlan:
+    """ay2_conv_plan: fused conv + bias + act (+ residual) between two ActViews. Keeps its tensors alive."""
+
+    def __init__(self, x: ActView, y: ActView, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int,
+                 stride: int, pad: int, act: int, residual: Optional[ActView] = None):
+        lib = _lib.load()
+        cout_pad, ktot = w_packed.shape
+        assert ktot == kh * kw * x.c, (ktot, kh, kw, x.c)
+        assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32 and bias.numel() == cout_pad
+        assert x.buf.is_cuda and y.buf.is_cuda and w_packed.is_cuda and bias.is_cuda
+        d = ConvDesc()
+        d.batch = x.B
+        d.in_h, d.in_w, d.cin, d.in_cstride = x.H, x.W, x.c, x.cstride
+        d.out_h, d.out_w, d.cout, d.out_cstride = y.H, y.W, y.c, y.cstride
+        d.kh, d.kw, d.stride, d.pad, d.act = kh, kw, stride, pad, act
+        d.res_cstride = residual.cstride if residual is not None else 0
+        d.cout_pad = cout_pad
+        self.desc = d
+        self.x, self.y, self.w, self.b, self.res = x, y, w_packed, bias, residual
+        h = C.c_void_p()
+        _lib.check(lib.ay2_conv_plan_create(C.byref(d), x.ptr(), w_packed.data_ptr(), bias.data_ptr(),
+                                            residual.ptr() if residual is not None else None, y.ptr(), C.byref(h)),
+                   "ay2_conv_plan_create")
+        self._h = h
+        self._lib = lib
+        self.flops = float(lib.ay2_conv_plan_flops(h))
+
+    def run(self, stream: Optional[int] = None) -> None:
+        _lib.check(self._lib.ay2_conv_plan_run(self._h, stream if stream is not None else _lib.current_stream_ptr()),
+                   "ay2_conv_plan_run")
+
+    def run_reference_simt(self) -> None:
+        """Same math on CUDA cores (test infrastructure)."""
+        _lib.check(self._lib.ay2_conv_reference_simt(C.byref(self.desc), self.x.ptr(), self.w.data_ptr(),
+                                                     self.b.data_ptr(), self.res.ptr() if self.res is not None else None,
+                                                     self.y.ptr(), _lib.current_stream_ptr()), "ay2_conv_reference_simt")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.ay2_conv_plan_destroy(h)
+            self._h = None
+
+
+def space_to_depth(img: torch.Tensor, out: ActView, scale: float) -> None:
+    """img: NCHW uint8/fp32 [B,3,H,W] -> out [B,H/2,W/2,16]."""
+    assert img.is_cuda and img.is_contiguous() and img.shape[1] == 3
+    B, _, H, W = img.shape
+    assert out.c0 == 0 and out.cstride == 16 and (out.B, out.H, out.W) == (B, H // 2, W // 2)
+    dt = {torch.uint8: _lib.DT_U8, torch.float32: _lib.DT_F32}[img.dtype]
+    _lib.check(_lib.load().ay2_space_to_depth(img.data_ptr(), dt, B, H, W, float(scale), out.ptr(),
+                                              _lib.current_stream_ptr()), "ay2_space_to_depth")
+
+
+def sppf_pool(x: ActView, o1: ActView, o2: ActView, o3: ActView, ks: Sequence[int]) -> None:
+    assert x.cstride == o1.cstride == o2.cstride == o3.cstride and x.buf is o1.buf
+    _lib.check(_lib.load().ay2_sppf_pool(x.ptr(), x.B, x.H, x.W, x.c, x.cstride, ks[0], ks[1], ks[2], o1.ptr(),
+                                         o2.ptr(), o3.ptr(), _lib.current_stream_ptr()), "ay2_sppf_pool")
+
+
+def upsample2x(x: ActView, y: ActView) -> None:
+    assert (y.H, y.W, y.c) == (2 * x.H, 2 * x.W, x.c)
+    _lib.check(_lib.load().ay2_upsample2x(x.ptr(), x.B, x.H, x.W, x.c, x.cstride, y.ptr(), y.cstride,
+                                          _lib.current_stream_ptr()), "ay2_upsample2x")
+
+
+def head_decode(logits: ActView, na: int, no: int, stride_px: float, anchor_wh_px: torch.Tensor, pred: torch.Tensor,
+                row_offset: int, raw: Optional[torch.Tensor]) -> None:
+    assert logits.c0 == 0 and pred.dtype == torch.float32 and pred.is_contiguous() and pred.shape[2] == no
+    assert anchor_wh_px.dtype == torch.float32 and anchor_wh_px.numel() == na * 2 and anchor_wh_px.is_cuda
+    _lib.check(_lib.load().ay2_head_decode(logits.ptr(), logits.B, logits.H, logits.W, logits.cstride, na, no,
+                                           float(stride_px), anchor_wh_px.data_ptr(), pred.data_ptr(), pred.shape[1],
+                                           row_offset, _lib.ptr(raw), _lib.current_stream_ptr()), "ay2_head_decode")
+
+
+class NmsWorkspace:
+    """Pre-allocated buffers for ay2_nms_batched on a fixed (batch, n, no) problem."""
+
+    def __init__(self, batch: int, n: int, no: int, max_det: int = 300, multi_label: bool = False,
+                 max_candidates: Optional[int] = None, device="cuda"):
+        nc = no - 5
+        if max_candidates is None:
+            max_candidates = n if not multi_label else min(n * nc, max(n, 131072))
+        self.p = NmsParams()
+        self.p.batch, self.p.n, self.p.no = batch, n, no
+        self.p.max_det = max_det
+        self.p.max_candidates = max_candidates
+        self.p.multi_label = int(multi_label)
+        lib = _lib.load()
+        nbytes = lib.ay2_nms_workspace_bytes(C.byref(self.p))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.out = torch.zeros((batch, max_det, 6), dtype=torch.float32, device=device)
+        self.count = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, agnostic: bool = False,
+            class_mask: Optional[torch.Tensor] = None, max_nms: int = 30000, max_wh: float = 4096.0) -> None:
+        p = self.p
+        assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous()
+        assert tuple(pred.shape) == (p.batch, p.n, p.no), (pred.shape, (p.batch, p.n, p.no))
+        p.conf_thres, p.iou_thres = float(conf_thres), float(iou_thres)
+        p.agnostic, p.max_nms, p.max_wh = int(agnostic), int(max_nms), float(max_wh)
+        _lib.check(_lib.load().ay2_nms_batched(pred.data_ptr(), C.byref(p), _lib.ptr(class_mask), self.ws.data_ptr(),
+                                               self.ws.numel(), self.out.data_ptr(), self.count.data_ptr(),
+                                               self.overflow.data_ptr(), _lib.current_stream_ptr()), "ay2_nms_batched")

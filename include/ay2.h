@@ -1,0 +1,148 @@
+/*
+ * ay2.h — C-ABI of libay2.so, the B200 (sm_100a) hot path of ayolov2_b200.
+ *
+ * The reference (j-marple-dev/AYolov2) has no FFI of its own for this path: the boundary is the Python
+ * operator API (kindle modules named in res/configs/model/*.yaml, ComputeLoss, non_max_suppression,
+ * batched_nms). This header declares what the replacement exports UNDER that Python boundary; every entry
+ * point cites the reference interface it replaces (file:line relative to the reference tree). The Python
+ * host (ayolov2_b200/_lib.py) binds these with ctypes; INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - Plain pointers + sizes only. All data pointers are DEVICE pointers owned by the caller (PyTorch);
+ *    the library never allocates, frees or retains tensor memory past a call, except that a *plan* keeps
+ *    the raw addresses it was created with (the caller keeps those buffers alive and at the same address;
+ *    this is what makes CUDA-graph capture of a step possible).
+ *  - Every function returns 0 on success, a negative ay2 error code otherwise, and never throws.
+ *    ay2_last_error_string() returns a thread-local description of the last failure.
+ *  - `stream` is a cudaStream_t passed as void*. All launches are asynchronous on that stream.
+ *  - Activations are NHWC bf16 with an explicit channel stride (so a tensor may be a channel slice of a
+ *    wider concat buffer); weights are bf16 [Cout_pad][KH*KW*Cin] (K-major) with the BatchNorm folded in.
+ */
+#ifndef AY2_H_
+#define AY2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AY2_OK 0
+#define AY2_ERR_INVALID -1   /* bad argument / unsupported shape */
+#define AY2_ERR_CUDA -2      /* a CUDA runtime / driver call failed */
+#define AY2_ERR_NO_DEVICE -3 /* no sm_100 device */
+
+#define AY2_ACT_NONE 0
+#define AY2_ACT_SILU 1
+
+int ay2_version(void);
+const char* ay2_last_error_string(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t ay2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Conv2d + folded BatchNorm + SiLU (+ residual add), NHWC bf16, implicit GEMM on tcgen05.
+ * Replaces kindle.modules.conv.Conv.forward (conv -> batch_norm -> activation; reference call sites
+ * train.py:137, scripts/train/yolo_trainer.py:322-323, scripts/utils/train_utils.py:436-444), the
+ * Bottleneck shortcut add, and — because input and output carry channel strides/offsets — the
+ * kindle Concat module (res/configs/model/yolov5s.yaml:37).
+ * Also runs each link of the Tucker-2 chain built by scripts/tensor_decomposition/decomposition.py:363-424.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ay2_conv_desc {
+  int32_t batch;
+  int32_t in_h, in_w;     /* input spatial size */
+  int32_t cin;            /* input channels consumed (multiple of 16) */
+  int32_t in_cstride;     /* channel stride (elements) of the input buffer, multiple of 8 */
+  int32_t out_h, out_w;   /* output spatial size */
+  int32_t cout;           /* output channels produced */
+  int32_t out_cstride;    /* channel stride (elements) of the output buffer, multiple of 8 */
+  int32_t kh, kw;         /* kernel size (1x1, 3x3; KxK stride 1 or 2) */
+  int32_t stride;         /* 1 or 2 */
+  int32_t pad;            /* symmetric zero padding */
+  int32_t act;            /* AY2_ACT_* */
+  int32_t res_cstride;    /* channel stride of the residual buffer (0 = no residual) */
+  int32_t cout_pad;       /* rows in the packed weight matrix (>= cout, multiple of the N tile) */
+  int32_t reserved;
+} ay2_conv_desc;
+
+typedef struct ay2_conv_plan ay2_conv_plan;
+
+/* N-tile (and therefore the cout_pad granularity) the library will use for `cout`. */
+int ay2_conv_block_n(int32_t cout);
+
+/* in/out/residual: bf16 NHWC (already offset to the first channel of the slice).
+ * weight: bf16 [cout_pad][kh*kw*cin]; bias: fp32 [cout_pad]. */
+int ay2_conv_plan_create(const ay2_conv_desc* desc, const void* in, const void* weight, const float* bias,
+                         const void* residual, void* out, ay2_conv_plan** plan);
+int ay2_conv_plan_run(const ay2_conv_plan* plan, void* stream);
+int ay2_conv_plan_destroy(ay2_conv_plan* plan);
+/* FLOPs (2*MAC, unpadded) one run of the plan performs — used for roofline accounting. */
+double ay2_conv_plan_flops(const ay2_conv_plan* plan);
+
+/* Reference SIMT direct convolution (same math, same layouts, no tensor cores). Test infrastructure
+ * for full-size parity checks on the GPU where the CPU oracle is too slow; never on the product path. */
+int ay2_conv_reference_simt(const ay2_conv_desc* desc, const void* in, const void* weight, const float* bias,
+                            const void* residual, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input side: NCHW image (uint8 or fp32) -> 2x2 space-to-depth NHWC bf16 with 16 channels
+ * (12 used: channel = (dy*2+dx)*3 + c for input pixel (2y+dy, 2x+dx); 4 zero), scaled by `scale`.
+ * Replaces YoloValidator.prepare_img / AbstractTrainer.prepare_img (scripts/utils/train_utils.py:255-260,
+ * scripts/train/abstract_trainer.py:252-261) and turns the 6x6/s2/p2 stem Conv
+ * (res/configs/model/yolov5s.yaml:21) and kindle Focus (res/configs/model/yolov5_v5.yaml:21) into a 3x3/s1 conv.
+ * ---------------------------------------------------------------------------------------------- */
+#define AY2_DT_U8 0
+#define AY2_DT_F32 1
+int ay2_space_to_depth(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float scale,
+                       void* out, void* stream);
+
+/* SPPF / SPP pooling: x1 = in slice; writes maxpool windows k1,k2,k3 (stride 1, same padding) into three
+ * channel slices. Replaces kindle.modules.poolings.SPPF / SPP (yolov5s.yaml:33, yolov5_v5.yaml:32). */
+int ay2_sppf_pool(const void* in, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t cstride, int32_t k1,
+                  int32_t k2, int32_t k3, void* out1, void* out2, void* out3, void* stream);
+
+/* Nearest 2x upsample into a channel slice: replaces nn.Upsample(scale_factor=2) + Concat
+ * (res/configs/model/yolov5s.yaml:36-37). */
+int ay2_upsample2x(const void* in, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t in_cstride, void* out,
+                   int32_t out_cstride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * YOLOHead decode (eval mode): per level, logits NHWC bf16 [B,ny,nx,cstride] (channel = a*no + o) ->
+ *   pred  fp32 [B, total_rows, no] rows [row_offset + a*ny*nx + y*nx + x]  (sigmoid, xy/wh decode)
+ *   raw   fp32 [B, na, ny, nx, no] (optional, may be NULL: the train-layout tensor)
+ * Replaces kindle.modules.yolo_head.YOLOHead.forward (consumers: scripts/utils/train_utils.py:441-444,
+ * scripts/loss/losses.py:245-255).
+ * ---------------------------------------------------------------------------------------------- */
+int ay2_head_decode(const void* logits, int32_t batch, int32_t ny, int32_t nx, int32_t cstride, int32_t na,
+                    int32_t no, float stride_px, const float* anchor_wh_px /* [na*2] device */, float* pred,
+                    int64_t total_rows, int64_t row_offset, float* raw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched NMS: replaces scripts/utils/metrics.py:285-443 non_max_suppression(nms_type="nms") and the
+ * torchvision.ops.nms call at :385 for the whole batch in a fixed number of launches.
+ *   pred: fp32 [B, n, no] (xywh, obj, cls...) ; out_det: fp32 [B, max_det, 6]; out_count: int32 [B].
+ * workspace: ay2_nms_workspace_bytes(...) bytes. Selection is bit-identical to the reference on identical
+ * inputs (stable descending score order, fp32 IoU, strict > iou_thres).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ay2_nms_params {
+  double iou_thres;     /* compared as (double)iou > iou_thres, like torchvision's CPU kernel */
+  float conf_thres;     /* compared in fp32, like `prediction[..., 4] > conf_thres` */
+  float max_wh;         /* metrics.py:326 (4096) */
+  int32_t batch, n, no;
+  int32_t multi_label;  /* metrics.py:330,359-364 */
+  int32_t agnostic;     /* metrics.py:383 */
+  int32_t max_det;      /* metrics.py:293 (300) */
+  int32_t max_nms;      /* metrics.py:327 (30000) */
+  int32_t max_candidates; /* per-image capacity of the candidate list (workspace sizing) */
+} ay2_nms_params;
+size_t ay2_nms_workspace_bytes(const ay2_nms_params* p);
+/* class_mask: optional device uint8[nc] (metrics.py:367-368 `classes` filter), NULL = keep all.
+ * overflow_flag: optional device int32, set to 1 if some image had more than max_candidates candidates. */
+int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
+                    size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AY2_H_ */

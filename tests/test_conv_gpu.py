@@ -1,0 +1,110 @@
+"""Parity of the tcgen05 implicit-GEMM conv (ay2_conv_plan_*) on the GPU.
+
+Checked against (a) a plain PyTorch fp32 conv2d of the same bf16-rounded operands and (b) the SIMT
+reference kernel ay2_conv_reference_simt. Tolerance: the kernel accumulates bf16 products in fp32 and rounds
+the result to bf16 once -> |err| <= 2^-8 * |ref| + small absolute slack for the accumulation order.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # (B, H, W, Cin, Cout, k, s, p, act, residual, in_slice, out_slice)
+    (2, 16, 16, 64, 64, 1, 1, 0, 1, False, False, False),
+    (2, 16, 16, 64, 64, 3, 1, 1, 1, False, False, False),
+    (2, 32, 32, 16, 32, 3, 1, 1, 1, False, False, False),   # stem-like: CK=16 / SW32, N=32
+    (2, 32, 32, 32, 64, 3, 2, 1, 1, False, False, False),   # CK=32 / SW64, stride 2
+    (3, 20, 20, 128, 128, 3, 1, 1, 1, True, False, False),  # 4x4 boxes, residual
+    (2, 40, 40, 64, 64, 3, 1, 1, 1, True, True, True),      # 8x8 boxes, slices of wider buffers, in-place style
+    (2, 40, 40, 128, 256, 3, 2, 1, 1, False, False, True),  # stride 2 -> 20x20
+    (1, 20, 20, 512, 512, 1, 1, 0, 1, False, True, False),  # two N tiles
+    (2, 20, 20, 256, 255, 1, 1, 0, 0, False, False, False), # head-like: cout 255, no act
+    (1, 24, 40, 64, 128, 3, 1, 1, 0, False, False, False),  # ragged boxes (24x40)
+    (5, 10, 10, 256, 128, 3, 1, 1, 1, False, False, False), # tiny maps, M tail
+    (1, 80, 80, 128, 128, 3, 2, 1, 1, False, True, True),
+    (2, 20, 20, 1024, 512, 1, 1, 0, 1, False, False, False),# SPPF conv2-like, long K
+]
+
+
+def _run_case(case, seed=0):
+    from ayolov2_b200 import ops
+
+    B, H, W, Cin, Cout, k, s, p, act, use_res, in_slice, out_slice = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    cs_in = Cin + 32 if in_slice else Cin
+    c0_in = 16 if in_slice else 0
+    cout8 = (Cout + 7) // 8 * 8
+    cs_out = cout8 + 64 if out_slice else cout8
+    c0_out = 24 if out_slice else 0
+    xbuf = torch.randn((B, H, W, cs_in), device=dev, generator=g).to(torch.bfloat16)
+    ybuf = torch.full((B, OH, OW, cs_out), 7.0, device=dev, dtype=torch.bfloat16)
+    x = ops.ActView(xbuf, c0_in, Cin)
+    y = ops.ActView(ybuf, c0_out, Cout)
+    w = torch.randn((Cout, Cin, k, k), device=dev, generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, device=dev, generator=g) * 0.5
+    wp, bp = ops.pack_conv_weight(w, b)
+    res = None
+    if use_res:
+        rbuf = torch.randn((B, OH, OW, cs_out), device=dev, generator=g).to(torch.bfloat16)
+        res = ops.ActView(rbuf, c0_out, Cout)
+    plan = ops.ConvPlan(x, y, wp, bp, k, k, s, p, act, residual=res)
+    plan.run()
+    torch.cuda.synchronize()
+    got = y.tensor().float().clone()
+    untouched = ybuf.clone()
+    untouched[..., c0_out:c0_out + Cout] = 7.0
+    assert torch.all(untouched == 7.0), "conv wrote outside its channel slice"
+
+    # (a) torch fp32 reference on the same rounded operands
+    xin = x.tensor().float().permute(0, 3, 1, 2)
+    wr = wp[:Cout].float().view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wr, bp[:Cout], stride=s, padding=p)
+    if act == 1:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    if use_res:
+        ref = ref + res.tensor().float()
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-2
+    bad = err > tol
+    assert not bad.any(), (f"case {case}: {int(bad.sum())} / {bad.numel()} mismatches, max err {float(err.max()):.4f}, "
+                           f"first bad index {bad.nonzero()[0].tolist()}")
+
+    # (b) SIMT reference kernel (same rounding points) -> at most 1 bf16 ulp apart
+    ybuf.fill_(7.0)
+    plan.run_reference_simt()
+    torch.cuda.synchronize()
+    simt = y.tensor().float()
+    err2 = (got - simt).abs()
+    assert float((err2 - (2.0 ** -7 * simt.abs() + 1e-2)).max()) <= 0, f"case {case}: SIMT mismatch {float(err2.max())}"
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv_parity(case):
+    _run_case(case)
+
+
+def test_conv_inplace_residual():
+    """Bottleneck shortcut: y1 <- y1 + conv3x3(t), residual and output are the same slice."""
+    from ayolov2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B, H, W, C_ = 2, 40, 40, 64
+    buf = torch.randn((B, H, W, 2 * C_), device="cuda", generator=g).to(torch.bfloat16)
+    t = torch.randn((B, H, W, C_), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((C_, C_, 3, 3), device="cuda", generator=g) * 0.05
+    wp, bp = ops.pack_conv_weight(w, None)
+    y1 = ops.ActView(buf, 0, C_)
+    before = buf.clone()
+    plan = ops.ConvPlan(ops.ActView(t, 0, C_), y1, wp, bp, 3, 3, 1, 1, 1, residual=y1)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.silu(F.conv2d(t.float().permute(0, 3, 1, 2), wp.float().view(C_, 3, 3, C_).permute(0, 3, 1, 2), bp, padding=1))
+    ref = ref.permute(0, 2, 3, 1) + before[..., :C_].float()
+    err = (buf[..., :C_].float() - ref).abs()
+    assert float((err - (2.0 ** -7 * ref.abs() + 2e-2)).max()) <= 0
+    assert torch.equal(buf[..., C_:], before[..., C_:])
