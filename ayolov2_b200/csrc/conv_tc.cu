@@ -15,6 +15,8 @@
 //   warp 1 : tcgen05.mma issuer (one lane), accumulators double-buffered in TMEM
 //   warp 2 : TMEM allocate / free
 //   warps 4-7 : epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem -> TMA store
+#include <string.h>
+
 #include "ay2_common.h"
 #include "ay2_ptx.cuh"
 
@@ -417,6 +419,8 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   AY2_REQUIRE(d && in && weight && bias && out && plan_out, "ay2_conv_plan_create: null argument");
   AY2_REQUIRE(d->stride == 1 || d->stride == 2, "conv stride %d unsupported (1 or 2)", d->stride);
   AY2_REQUIRE(d->cin % 16 == 0 && d->cin >= 16, "conv cin=%d must be a multiple of 16", d->cin);
+  // TMA clips the innermost dimension in 16-byte units, so a slice must own whole groups of 8 channels
+  AY2_REQUIRE(d->cout % 8 == 0 && d->cout >= 8, "conv cout=%d must be a multiple of 8 (pad with zero filters)", d->cout);
   AY2_REQUIRE(d->in_cstride % 8 == 0 && d->out_cstride % 8 == 0, "channel strides must be multiples of 8");
   AY2_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh <= 7 && d->kw <= 7, "kernel %dx%d unsupported", d->kh, d->kw);
   AY2_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&

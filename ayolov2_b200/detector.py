@@ -1,0 +1,115 @@
+"""Detector: model forward + batched NMS as ONE CUDA graph, plus the end-to-end host pipeline.
+
+This is the fused form of what scripts/utils/train_utils.py:403-472 (YoloValidator.validation_step) does per
+batch: prepare_img (uint8 -> float /255, :421,255-260) -> model(imgs) (:436-444) -> non_max_suppression
+(:461-469). `detect()` takes HOST images (pinned uint8 or float32 NCHW) and returns the reference's list of
+(n_i, 6) tensors; host->device copies, all kernels and the device->host read of the detections are part of
+every call. `submit()/collect()` expose the same pipeline asynchronously with two in-flight slots so that the
+PCIe copy of batch i+1 overlaps the kernels of batch i.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import Engine
+from .nms import nms_device
+
+
+class Detector:
+    def __init__(self, model: nn.Module, batch: int, height: int = 640, width: int = 640, conf_thres: float = 0.25,
+                 iou_thres: float = 0.45, multi_label: bool = False, agnostic: bool = False, max_det: int = 300,
+                 in_dtype: torch.dtype = torch.uint8, device: Optional[torch.device] = None, want_raw: bool = False) -> None:
+        scale = 1.0 / 255.0 if in_dtype == torch.uint8 else 1.0
+        self.engine = Engine(model, batch, height, width, in_dtype=in_dtype, scale=scale, want_raw=want_raw,
+                             device=device, use_graph=False)
+        self.device = self.engine.device
+        self.conf_thres, self.iou_thres = conf_thres, iou_thres
+        self.multi_label, self.agnostic, self.max_det = multi_label, agnostic, max_det
+        self.B, self.H, self.W = batch, height, width
+        self.in_dtype = in_dtype
+        pred = self.engine.pred
+        nc = pred.shape[2] - 5
+        self.nms_ws = ops.NmsWorkspace(batch, pred.shape[1], pred.shape[2], max_det=max_det,
+                                       multi_label=multi_label and nc > 1, device=self.device)
+        # two input / output slots for the host pipeline
+        self.dev_in = [torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) for _ in range(2)]
+        self.host_out = [torch.zeros((batch, max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.host_cnt = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        self.ev_consumed = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self._slot = 0
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._warm = False
+
+    # ---------------------------------------------------------------------------------------------
+    def _body(self) -> None:
+        """Everything after the space-to-depth kernel (which reads a per-slot input buffer): convs, head, NMS."""
+        eng = self.engine
+        for s in eng.b.steps:
+            if s is not eng.b.s2d_step:
+                s()
+        nms_device(eng.pred, self.conf_thres, self.iou_thres, agnostic=self.agnostic, multi_label=self.multi_label,
+                   max_det=self.max_det, workspace=self.nms_ws)
+
+    def launches_per_step(self) -> int:
+        return len(self.engine.b.steps) + 2  # + NMS filter and sort/scan kernels
+
+    def run_device(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """img: CUDA NCHW tensor of the detector's dtype. Asynchronous; returns (det [B,max_det,6], count [B])."""
+        eng = self.engine
+        eng._img = img
+        eng.b.s2d_step()
+        if not self._warm:
+            self._body()  # first call: plain launches (sets function attributes) ...
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()  # ... then capture the static part once
+            with torch.cuda.graph(g):
+                self._body()
+            self._graph = g
+            self._warm = True
+        else:
+            self._graph.replay()
+        return self.nms_ws.out, self.nms_ws.count
+
+    # ---------------------------------------------------------------------------------------------
+    def submit(self, host_img: torch.Tensor) -> int:
+        """Enqueue one batch from HOST memory (pinned for a truly asynchronous copy). Returns the slot id."""
+        k = self._slot
+        self._slot ^= 1
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_consumed[k])  # the s2d kernel that last read this slot has finished
+            self.dev_in[k].copy_(host_img, non_blocking=True)
+            self.ev_h2d[k].record(self.copy_stream)
+        cur.wait_event(self.ev_h2d[k])
+        det, cnt = self.run_device(self.dev_in[k])
+        self.ev_consumed[k].record(cur)
+        self.host_out[k].copy_(det, non_blocking=True)
+        self.host_cnt[k].copy_(cnt, non_blocking=True)
+        self.ev_done[k].record(cur)
+        return k
+
+    def collect(self, k: int) -> List[torch.Tensor]:
+        """Wait for slot k and return the reference-style list of (n_i, 6) tensors (host memory)."""
+        self.ev_done[k].synchronize()
+        counts = self.host_cnt[k].tolist()
+        out = self.host_out[k]
+        return [out[i, :c].clone() for i, c in enumerate(counts)]
+
+    def detect(self, host_img: torch.Tensor) -> List[torch.Tensor]:
+        """Synchronous end-to-end call: H2D, forward, NMS, D2H."""
+        return self.collect(self.submit(host_img))
+
+    @property
+    def flops_per_step(self) -> float:
+        return self.engine.b.flops
+
+    @property
+    def act_bytes_per_step(self) -> float:
+        return self.engine.b.act_bytes

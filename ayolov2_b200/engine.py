@@ -1,0 +1,472 @@
+"""Execution engine: compiles a kindle-style YOLOModel into a fixed sequence of libay2 kernel launches.
+
+What replaces what (reference call stack: scripts/utils/train_utils.py:403-472 validation_step ->
+`model(imgs)` -> kindle per-layer PyTorch dispatch):
+  * every `Conv` (conv + BN + SiLU)                 -> one fused tcgen05 implicit-GEMM launch (ay2_conv_plan_run)
+  * `C3`: conv1 & conv2 share their input           -> ONE 1x1 conv with concatenated weights writing both halves of
+                                                       the [.., 2c_] buffer conv3 reads (the torch.cat disappears);
+                                                       bottleneck shortcut add fused into the 3x3 epilogue (in place)
+  * `Concat` / the cat inside SPP(F)                -> addressing only: producers write channel slices
+  * `UpSample`                                      -> one copy kernel straight into the concat slice
+  * 6x6/s2 stem `Conv` and `Focus`                  -> space-to-depth kernel (also does uint8 -> /255 -> bf16) + 3x3 conv
+  * `YOLOHead`                                      -> 1x1 conv per level + fused sigmoid/grid/anchor decode kernel
+  * Tucker-2 decomposed convs (decomposition.py:363-424) -> three chained conv launches (ranks zero-padded to 16)
+Activations are NHWC bf16; BN is folded with running statistics (eval mode).
+
+The launch sequence is static, so a whole forward (+ NMS) is captured into one CUDA graph.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_NONE, ACT_SILU, ActView, ConvPlan
+
+
+def _act_code(m: nn.Module) -> int:
+    a = getattr(m, "activation", None)
+    if a is None or isinstance(a, nn.Identity):
+        return ACT_NONE
+    if isinstance(a, nn.SiLU):
+        return ACT_SILU
+    raise NotImplementedError(f"activation {type(a).__name__} is not implemented in the sm_100a conv epilogue (SiLU only)")
+
+
+def _bn_tuple(bn: Optional[nn.Module]):
+    if isinstance(bn, nn.BatchNorm2d):
+        return (bn.weight, bn.bias, bn.running_mean, bn.running_var), bn.eps
+    return None, 1e-3
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class Builder:
+    """Accumulates launches (`steps`) and owns every buffer of one compiled graph."""
+
+    def __init__(self, batch: int, device: torch.device) -> None:
+        self.B = batch
+        self.device = device
+        self.steps: List[Callable[[], None]] = []
+        self.plans: List[ConvPlan] = []
+        self.keep: List[Any] = []
+        self.flops = 0.0
+        self.act_bytes = 0.0  # algorithmic activation traffic (each conv reads its input once, writes its output once)
+
+    def new_act(self, H: int, W: int, C_: int) -> ActView:
+        v = ops.new_act(self.B, H, W, _round_up(C_, 8), device=self.device)
+        v.buf.zero_()
+        self.keep.append(v.buf)
+        return v
+
+    # ---------------------------------------------------------------------------------------------
+    def conv2d(self, x: ActView, y: ActView, weight: torch.Tensor, bias: Optional[torch.Tensor], bn, eps: float,
+               act: int, stride: int, pad: int, residual: Optional[ActView] = None) -> None:
+        """weight OIHW fp32 (Cin may be smaller than x.c: zero-padded), output channels may be padded up to y.c."""
+        w = weight.detach().float().to(self.device)
+        cout, cin, kh, kw = w.shape
+        if cin < x.c:
+            w = torch.cat((w, torch.zeros((cout, x.c - cin, kh, kw), device=self.device)), 1)
+        assert w.shape[1] == x.c, (w.shape, x.c)
+        assert cout <= y.c
+        if bn is not None:
+            bn = tuple(t.detach().float().to(self.device) for t in bn)
+        if bias is not None:
+            bias = bias.detach().float().to(self.device)
+        if cout < y.c:  # padded output channels produce act(0) = 0
+            w = torch.cat((w, torch.zeros((y.c - cout,) + tuple(w.shape[1:]), device=self.device)), 0)
+            if bn is not None:
+                g, b_, mu, var = bn
+                padn = y.c - cout
+                bn = (torch.cat((g, torch.ones(padn, device=self.device))), torch.cat((b_, torch.zeros(padn, device=self.device))),
+                      torch.cat((mu, torch.zeros(padn, device=self.device))), torch.cat((var, torch.ones(padn, device=self.device))))
+            if bias is not None:
+                bias = torch.cat((bias, torch.zeros(y.c - cout, device=self.device)))
+        wp, bp = ops.pack_conv_weight(w, bias, bn, eps)
+        plan = ConvPlan(x, y, wp, bp, kh, kw, stride, pad, act, residual=residual)
+        self.plans.append(plan)
+        self.steps.append(plan.run)
+        self.flops += 2.0 * self.B * y.H * y.W * cout * kh * kw * cin
+        self.act_bytes += 2.0 * self.B * (x.H * x.W * cin + y.H * y.W * cout)
+
+    @staticmethod
+    def _conv_geom(c: nn.Conv2d) -> Tuple[int, int]:
+        assert c.groups == 1 and c.dilation == (1, 1), "grouped / dilated convolutions are not on the YOLOv5 hot path"
+        assert c.stride[0] == c.stride[1] and c.padding[0] == c.padding[1] and c.kernel_size[0] == c.kernel_size[1]
+        return c.stride[0], c.padding[0]
+
+    def kindle_conv(self, m: nn.Module, x: ActView, y: Optional[ActView] = None, residual: Optional[ActView] = None) -> ActView:
+        """kindle Conv (conv -> BN -> act); `m.conv` may be a Tucker-2 nn.Sequential of three Conv2d."""
+        bn, eps = _bn_tuple(getattr(m, "batch_norm", None))
+        act = _act_code(m)
+        if isinstance(m.conv, nn.Sequential):  # decomposition.py:363-424: 1x1 (Cin->R1) -> kxk (R1->R0) -> 1x1 (R0->Cout, +bias)
+            first, core, last = m.conv[0], m.conv[1], m.conv[2]
+            s, p = self._conv_geom(core)
+            k = core.kernel_size[0]
+            oh, ow = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+            t1 = self.new_act(x.H, x.W, _round_up(first.out_channels, 16))
+            self.conv2d(x, t1, first.weight, first.bias, None, eps, ACT_NONE, 1, 0)
+            t2 = self.new_act(oh, ow, _round_up(core.out_channels, 16))
+            self.conv2d(t1, t2, core.weight, core.bias, None, eps, ACT_NONE, s, p)
+            if y is None:
+                y = self.new_act(oh, ow, last.out_channels)
+            self.conv2d(t2, y, last.weight, last.bias, bn, eps, act, 1, 0, residual)
+            return y
+        c = m.conv
+        s, p = self._conv_geom(c)
+        k = c.kernel_size[0]
+        if y is None:
+            y = self.new_act((x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1, c.out_channels)
+        self.conv2d(x, y, c.weight, c.bias, bn, eps, act, s, p, residual)
+        return y
+
+    # ---------------------------------------------------------------------------------------------
+    def stem(self, m: nn.Module, img_getter: Callable[[], torch.Tensor], H: int, W: int, scale: float,
+             y: Optional[ActView]) -> ActView:
+        """First layer fed by the NCHW image: 6x6/s2/p2 Conv or Focus(k, s=1) -> space-to-depth + k'xk' s1 conv."""
+        name = type(m).__name__
+        c = m.conv
+        assert isinstance(c, nn.Conv2d), "a decomposed stem is not supported"
+        s2d = ops.new_act(self.B, H // 2, W // 2, 16, device=self.device)
+        self.keep.append(s2d.buf)
+        self.steps.append(lambda: ops.space_to_depth(img_getter(), s2d, scale))
+        self.s2d_step = self.steps[-1]
+        w = c.weight.detach().float().to(self.device)
+        if name == "Focus":
+            s, p = self._conv_geom(c)
+            assert s == 1 and w.shape[1] == 12
+            # Focus channel = (dx*2+dy)*3 + c  ->  s2d channel = (dy*2+dx)*3 + c
+            w2 = torch.zeros_like(w)
+            for dy in range(2):
+                for dx in range(2):
+                    w2[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, (dx * 2 + dy) * 3:(dx * 2 + dy) * 3 + 3]
+            k2, p2 = c.kernel_size[0], p
+        elif name == "Conv" and c.kernel_size == (6, 6) and c.stride == (2, 2) and c.padding == (2, 2) and w.shape[1] == 3:
+            # W3[n, (dy*2+dx)*3 + c, a, b] = W6[n, c, 2a+dy, 2b+dx]
+            w2 = torch.zeros((w.shape[0], 12, 3, 3), device=self.device)
+            for dy in range(2):
+                for dx in range(2):
+                    w2[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = w[:, :, dy::2, dx::2]
+            k2, p2 = 3, 1
+        else:
+            raise NotImplementedError("first layer must be the 6x6/s2/p2 Conv stem or Focus (SURVEY.md §8a M1/M2)")
+        bn, eps = _bn_tuple(getattr(m, "batch_norm", None))
+        if y is None:
+            y = self.new_act(H // 2 + 2 * p2 - k2 + 1, W // 2 + 2 * p2 - k2 + 1, w.shape[0])
+        self.conv2d(s2d, y, w2, c.bias, bn, eps, _act_code(m), 1, p2)  # 9 taps x 12 ch == 36 taps x 3 ch: same FLOPs
+        return y
+
+    def bottleneck(self, m: nn.Module, y1: ActView) -> None:
+        """In place on y1: y1 <- (y1 +) conv2_3x3(conv1_1x1(y1))."""
+        t = self.kindle_conv(m.conv1, y1)
+        self.kindle_conv(m.conv2, t, y=y1, residual=y1 if m.shortcut else None)
+
+    def c3(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        c_ = m.conv1.conv.out_channels if isinstance(m.conv1.conv, nn.Conv2d) else m.conv1.conv[-1].out_channels
+        cat = self.new_act(x.H, x.W, 2 * c_)
+        fusable = (isinstance(m.conv1.conv, nn.Conv2d) and isinstance(m.conv2.conv, nn.Conv2d)
+                   and type(m.conv1.activation) is type(m.conv2.activation)
+                   and type(getattr(m.conv1, "batch_norm", None)) is type(getattr(m.conv2, "batch_norm", None)))
+        if fusable:
+            c1, c2 = m.conv1, m.conv2
+            w = torch.cat((c1.conv.weight.detach().float(), c2.conv.weight.detach().float()), 0)
+            bn1, eps = _bn_tuple(getattr(c1, "batch_norm", None))
+            bn2, _ = _bn_tuple(getattr(c2, "batch_norm", None))
+            bn = None if bn1 is None else tuple(torch.cat((a.detach().float(), b.detach().float())) for a, b in zip(bn1, bn2))
+            bias = None
+            if c1.conv.bias is not None:
+                bias = torch.cat((c1.conv.bias.detach().float(), c2.conv.bias.detach().float()))
+            self.conv2d(x, cat, w, bias, bn, eps, _act_code(c1), 1, 0)
+        else:
+            self.kindle_conv(m.conv1, x, y=cat.slice(0, c_))
+            self.kindle_conv(m.conv2, x, y=cat.slice(c_, c_))
+        y1 = cat.slice(0, c_)
+        for b in m.bottleneck_c3:
+            self.bottleneck(b, y1)
+        return self.kindle_conv(m.conv3, cat, y=y)
+
+    def bottleneck_csp(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        c_ = m.conv1.conv.out_channels
+        cat = self.new_act(x.H, x.W, 2 * c_)
+        t = self.kindle_conv(m.conv1, x)
+        for b in m.bottleneck_csp:
+            self.bottleneck(b, t)
+        # act(bn(cat[conv3(t), conv2(x)])) == cat[act(bn_a(conv3 t)), act(bn_b(conv2 x))]: fold each BN half
+        bn, eps = _bn_tuple(m.batch_norm)
+        act = _act_code(m)
+        halves = [tuple(p[:c_] for p in bn), tuple(p[c_:] for p in bn)]
+        self.conv2d(t, cat.slice(0, c_), m.conv3.weight, m.conv3.bias, halves[0], eps, act, 1, 0)
+        self.conv2d(x, cat.slice(c_, c_), m.conv2.weight, m.conv2.bias, halves[1], eps, act, 1, 0)
+        return self.kindle_conv(m.conv4, cat, y=y)
+
+    def spp(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        c_ = m.conv1.conv.out_channels if isinstance(m.conv1.conv, nn.Conv2d) else m.conv1.conv[-1].out_channels
+        if type(m).__name__ == "SPPF":
+            k = m.pooling.kernel_size
+            ks = (k, 2 * k - 1, 3 * k - 2)  # p(p(x)) == window 2k-1, p(p(p(x))) == 3k-2 (stride 1, -inf padding)
+        else:
+            ks = tuple(int(p.kernel_size) for p in m.pooling_modules)
+            assert len(ks) == 3, "SPP with other than 3 pooling windows is not implemented"
+        cat = self.new_act(x.H, x.W, 4 * c_)
+        self.kindle_conv(m.conv1, x, y=cat.slice(0, c_))
+        s0, s1, s2, s3 = (cat.slice(i * c_, c_) for i in range(4))
+        self.steps.append(lambda: ops.sppf_pool(s0, s1, s2, s3, ks))
+        return self.kindle_conv(m.conv2, cat, y=y)
+
+    def upsample(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        assert float(m.scale_factor) == 2.0 and m.mode == "nearest", "only nearest x2 UpSample is on the YOLOv5 path"
+        if y is None:
+            y = self.new_act(2 * x.H, 2 * x.W, x.c)
+        self.steps.append(lambda: ops.upsample2x(x, y))
+        return y
+
+
+class Engine:
+    """A compiled eval-mode forward of one YOLOModel for a fixed input shape.
+
+    run(img) -> (pred [B, sum(na*ny*nx), no] fp32, [raw_i (B, na, ny, nx, no) fp32]) ; all asynchronous.
+    """
+
+    def __init__(self, model: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float32,
+                 scale: float = 1.0, want_raw: bool = True, device: Optional[torch.device] = None,
+                 use_graph: bool = True) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ayolov2_b200.Engine needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.B, self.H, self.W = batch, height, width
+        self.in_dtype, self.scale = in_dtype, scale
+        self.input = torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) if use_graph else None
+        self._img = self.input
+        b = Builder(batch, self.device)
+        self.b = b
+        layers = list(model.model)
+        nL = len(layers)
+
+        def src_of(i: int) -> List[int]:
+            frm = getattr(layers[i], "from_idx", -1)
+            frm = list(frm) if isinstance(frm, (list, tuple)) else [frm]
+            return [i - 1 if f == -1 else f for f in frm]
+
+        # Concat planning: producers write straight into their slice of the concat buffer
+        dest: Dict[int, Tuple[int, int]] = {}
+        for j in range(nL):
+            if type(layers[j]).__name__ == "Concat":
+                assert getattr(layers[j], "dimension", 1) == 1
+                off = 0
+                for s in src_of(j):
+                    if s in dest or type(layers[s]).__name__ == "Concat":
+                        raise NotImplementedError("a tensor feeding two Concat layers / nested Concat needs a copy kernel")
+                    dest[s] = (j, off)
+                    off += self._out_channels(layers, s, src_of)
+        cat_bufs: Dict[int, ActView] = {}
+        outs: List[Optional[ActView]] = [None] * nL
+        self.pred: Optional[torch.Tensor] = None
+        self.raw: List[torch.Tensor] = []
+
+        def out_view(i: int, H: int, W: int, C_: int) -> Optional[ActView]:
+            if i not in dest:
+                return None
+            j, off = dest[i]
+            if j not in cat_bufs:
+                cat_bufs[j] = b.new_act(H, W, self._out_channels(layers, j, src_of))
+            cv = cat_bufs[j]
+            assert (cv.H, cv.W) == (H, W)
+            return cv.slice(off, C_)
+
+        for i, m in enumerate(layers):
+            name = type(m).__name__
+            srcs = src_of(i)
+            if name in ("Conv", "Focus") and srcs[0] < 0:
+                co = m.conv.out_channels
+                outs[i] = b.stem(m, lambda: self._img, height, width, scale, out_view(i, height // 2, width // 2, co))
+                continue
+            xin = [outs[s] for s in srcs]
+            if name == "Conv":
+                c = m.conv if isinstance(m.conv, nn.Conv2d) else m.conv[1]
+                s_, p_ = Builder._conv_geom(c)
+                k_ = c.kernel_size[0]
+                oh, ow = (xin[0].H + 2 * p_ - k_) // s_ + 1, (xin[0].W + 2 * p_ - k_) // s_ + 1
+                co = m.conv.out_channels if isinstance(m.conv, nn.Conv2d) else m.conv[-1].out_channels
+                outs[i] = b.kindle_conv(m, xin[0], y=out_view(i, oh, ow, co))
+            elif name == "C3":
+                co = m.conv3.conv.out_channels if isinstance(m.conv3.conv, nn.Conv2d) else m.conv3.conv[-1].out_channels
+                outs[i] = b.c3(m, xin[0], out_view(i, xin[0].H, xin[0].W, co))
+            elif name == "BottleneckCSP":
+                outs[i] = b.bottleneck_csp(m, xin[0], out_view(i, xin[0].H, xin[0].W, m.conv4.conv.out_channels))
+            elif name in ("SPP", "SPPF"):
+                co = m.conv2.conv.out_channels if isinstance(m.conv2.conv, nn.Conv2d) else m.conv2.conv[-1].out_channels
+                outs[i] = b.spp(m, xin[0], out_view(i, xin[0].H, xin[0].W, co))
+            elif name == "Upsample":
+                outs[i] = b.upsample(m, xin[0], out_view(i, 2 * xin[0].H, 2 * xin[0].W, xin[0].c))
+            elif name == "Concat":
+                outs[i] = cat_bufs[i]
+            elif name == "YOLOHead":
+                self._head(m, xin, want_raw)
+            else:
+                raise NotImplementedError(f"layer {i} ({name}) is not on the YOLOv5 detection hot path")
+        self.outs = outs
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        self.post_steps: List[Callable[[], None]] = []  # e.g. NMS appended by Detector
+
+    @staticmethod
+    def _out_channels(layers, i: int, src_of) -> int:
+        m = layers[i]
+        name = type(m).__name__
+        if name in ("Conv", "Focus"):
+            return m.conv.out_channels if isinstance(m.conv, nn.Conv2d) else m.conv[-1].out_channels
+        if name == "C3":
+            return m.conv3.conv.out_channels if isinstance(m.conv3.conv, nn.Conv2d) else m.conv3.conv[-1].out_channels
+        if name == "BottleneckCSP":
+            return m.conv4.conv.out_channels
+        if name in ("SPP", "SPPF"):
+            return m.conv2.conv.out_channels if isinstance(m.conv2.conv, nn.Conv2d) else m.conv2.conv[-1].out_channels
+        if name == "Upsample":
+            return Engine._out_channels(layers, src_of(i)[0], src_of)
+        if name == "Concat":
+            return sum(Engine._out_channels(layers, s, src_of) for s in src_of(i))
+        raise NotImplementedError(name)
+
+    def _head(self, m: nn.Module, xs: Sequence[ActView], want_raw: bool) -> None:
+        b = self.b
+        na, no = m.na, m.no
+        total = sum(na * x.H * x.W for x in xs)
+        self.pred = torch.zeros((self.B, total, no), dtype=torch.float32, device=self.device)
+        off = 0
+        self.na, self.no = na, no
+        for i, (conv, x) in enumerate(zip(m.conv, xs)):
+            logits = b.new_act(x.H, x.W, _round_up(na * no, 16))
+            b.conv2d(x, logits, conv.weight, conv.bias, None, 1e-3, ACT_NONE, 1, 0)
+            raw = torch.zeros((self.B, na, x.H, x.W, no), dtype=torch.float32, device=self.device) if want_raw else None
+            if raw is not None:
+                self.raw.append(raw)
+            anchors_px = m.anchor_grid[i].detach().float().reshape(-1).contiguous().to(self.device)
+            b.keep.append(anchors_px)
+            stride = float(m.stride[i])
+            b.steps.append(lambda l=logits, a=anchors_px, s=stride, o=off, r=raw: ops.head_decode(l, na, no, s, a, self.pred, o, r))
+            off += na * x.H * x.W
+
+    # ---------------------------------------------------------------------------------------------
+    def _launch_all(self) -> None:
+        for s in self.b.steps:
+            s()
+        for s in self.post_steps:
+            s()
+
+    @property
+    def n_launches(self) -> int:
+        return len(self.b.steps)
+
+    def run(self, img: Optional[torch.Tensor] = None):
+        """img: NCHW [B,3,H,W] of the engine's dtype on the engine's device, or None to use `self.input` as is."""
+        if self.use_graph:
+            if img is not None and img.data_ptr() != self.input.data_ptr():
+                self.input.copy_(img, non_blocking=True)
+            self._img = self.input
+            if self.graph is None:
+                self._launch_all()  # warm-up (sets function attributes, loads modules) before capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._img = self.input if img is None else img.contiguous()
+            self._launch_all()
+        return self.pred, self.raw
+
+
+# -------------------------------------------------------------------------------------------------
+# drop-in glue used by the kindle-compatible modules
+# -------------------------------------------------------------------------------------------------
+def _weights_signature(model: nn.Module) -> int:
+    sig = 0
+    for p in model.parameters():
+        sig += p._version + (p.data_ptr() & 0xFFFF)
+    for b_ in model.buffers():
+        sig += b_._version
+    return sig
+
+
+def forward_model(model: nn.Module, x: torch.Tensor):
+    """YOLOModel.forward for CUDA inputs (train.py / val.py call `model(imgs)`)."""
+    if model.training:
+        raise NotImplementedError(
+            "training-mode forward/backward (BN batch statistics, dgrad/wgrad kernels) is not built yet in this round; "
+            "call model.eval() — inference + NMS is the path implemented on sm_100a")
+    if x.dim() != 4:
+        raise ValueError("expected NCHW input")
+    in_dtype = x.dtype
+    scale = 1.0
+    if x.dtype in (torch.float16, torch.bfloat16, torch.float64):
+        x = x.float()
+        in_dtype = torch.float32
+    B, C_, H, W = x.shape
+    key = (B, H, W, in_dtype, x.device.index)
+    cache = model.__dict__.setdefault("_engine_cache", {})
+    sig = _weights_signature(model)
+    ent = cache.get(key)
+    if ent is None or ent[1] != sig:
+        cache.clear()
+        ent = (Engine(model, B, H, W, in_dtype=in_dtype, scale=scale, device=x.device, use_graph=False), sig)
+        cache[key] = ent
+    eng = ent[0]
+    pred, raw = eng.run(x)
+    pred, raw = pred.clone(), [r.clone() for r in raw]
+    if model.__dict__.get("_export", False):
+        return (pred,)
+    return pred, raw
+
+
+def run_single_module(module: nn.Module, x):
+    """`forward` of a bare kindle module on CUDA NCHW tensors: builds a one-layer plan (not cached; for the
+    reference's module-level uses such as profiling — the model-level path is forward_model)."""
+    name = type(module).__name__
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+    if not all(t.is_cuda for t in xs):
+        raise RuntimeError(f"ayolov2_b200 {name} runs on CUDA tensors only; there is no CPU fallback")
+    if module.training and any(isinstance(mm, nn.BatchNorm2d) for mm in module.modules()):
+        raise NotImplementedError("training-mode module forward is not built yet; call .eval()")
+    dev = xs[0].device
+    B = xs[0].shape[0]
+    b = Builder(B, dev)
+    views = []
+    for t in xs:
+        cpad = _round_up(t.shape[1], 16)
+        buf = torch.zeros((B, t.shape[2], t.shape[3], cpad), dtype=torch.bfloat16, device=dev)
+        buf[..., :t.shape[1]] = t.permute(0, 2, 3, 1)
+        views.append(ActView(buf, 0, cpad))
+    if name == "YOLOHead":
+        class _E:  # minimal host for Engine._head
+            pass
+        e = Engine.__new__(Engine)
+        e.b, e.B, e.device, e.raw, e.pred = b, B, dev, [], None
+        e._head(module, views, True)
+        for s in b.steps:
+            s()
+        return (e.pred, e.raw)
+    if name == "Conv":
+        y = b.kindle_conv(module, views[0])
+    elif name == "Focus":
+        raise NotImplementedError("Focus is compiled as part of a model (it consumes the NCHW image)")
+    elif name == "Bottleneck":
+        y = views[0]
+        b.bottleneck(module, y)
+    elif name == "C3":
+        y = b.c3(module, views[0], None)
+    elif name == "BottleneckCSP":
+        y = b.bottleneck_csp(module, views[0], None)
+    elif name in ("SPP", "SPPF"):
+        y = b.spp(module, views[0], None)
+    else:
+        raise NotImplementedError(name)
+    for s in b.steps:
+        s()
+    return y.tensor().permute(0, 3, 1, 2).float().contiguous()

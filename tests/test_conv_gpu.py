@@ -20,7 +20,7 @@ CASES = [
     (2, 40, 40, 64, 64, 3, 1, 1, 1, True, True, True),      # 8x8 boxes, slices of wider buffers, in-place style
     (2, 40, 40, 128, 256, 3, 2, 1, 1, False, False, True),  # stride 2 -> 20x20
     (1, 20, 20, 512, 512, 1, 1, 0, 1, False, True, False),  # two N tiles
-    (2, 20, 20, 256, 255, 1, 1, 0, 0, False, False, False), # head-like: cout 255, no act
+    (2, 20, 20, 256, 256, 1, 1, 0, 0, False, False, False), # head-like (255 padded to 256), no act
     (1, 24, 40, 64, 128, 3, 1, 1, 0, False, False, False),  # ragged boxes (24x40)
     (5, 10, 10, 256, 128, 3, 1, 1, 1, False, False, False), # tiny maps, M tail
     (1, 80, 80, 128, 128, 3, 2, 1, 1, False, True, True),

@@ -1,0 +1,75 @@
+"""End-to-end parity of the compiled CUDA forward (ayolov2_b200.engine) with the CPU fp32 oracle
+(oracle/yolo_oracle.py) on seeded random weights shared through the same module tree.
+
+Tolerance (BASELINE.json north_star): bf16 activations -> 1e-2 relative. Errors are normalised by the
+tensor's max magnitude; the head logits additionally by a mean-relative figure."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _norm_err(got, ref):
+    return float((got.float().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-6))
+
+
+@pytest.mark.parametrize("name,hw", [("yolov5s", (320, 320)), ("yolov5s", (256, 384)), ("yolov5_v5", (256, 256)), ("yolov5n", (192, 192))])
+def test_forward_matches_oracle(name, hw):
+    from ayolov2_b200 import synth as model_utils
+    from oracle import yolo_oracle
+
+    model = model_utils.build_model(name, seed=0)
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((B, 3, *hw), generator=g)
+    want_pred, want_raw = yolo_oracle.forward(model, x)
+    model_cuda = model.cuda()
+    got_pred, got_raw = model_cuda(x.cuda())
+    torch.cuda.synchronize()
+    assert got_pred.shape == want_pred.shape
+    for gr, wr in zip(got_raw, want_raw):
+        assert gr.shape == wr.shape
+        e = _norm_err(gr, wr)
+        assert e < 2e-2, f"raw logits normalised error {e}"
+    # decoded boxes / scores
+    gp = got_pred.float().cpu()
+    assert float((gp[..., 4:] - want_pred[..., 4:]).abs().max()) < 2e-2  # probabilities
+    rel_box = (gp[..., :4] - want_pred[..., :4]).abs() / (want_pred[..., :4].abs() + 8.0)
+    assert float(rel_box.max()) < 5e-2, float(rel_box.max())
+
+
+def test_uint8_detector_matches_float_path():
+    """Detector (uint8 input, /255 inside the space-to-depth kernel, CUDA graph, NMS) == Engine on float input."""
+    from ayolov2_b200.detector import Detector
+    from ayolov2_b200.nms import non_max_suppression
+    from ayolov2_b200 import synth as model_utils
+
+    model = model_utils.build_model("yolov5s", seed=1).cuda()
+    B, H, W = 2, 320, 320
+    g = torch.Generator().manual_seed(2)
+    img8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    det = Detector(model, B, H, W, conf_thres=0.001, iou_thres=0.6, in_dtype=torch.uint8)
+    out1 = det.detect(img8.pin_memory())
+    out2 = det.detect(img8.pin_memory())  # graph replay path
+    pred, _ = model(img8.cuda().float() / 255.0)
+    want = non_max_suppression(pred, 0.001, 0.6)
+    for a, b, c in zip(out1, out2, want):
+        assert torch.equal(a, b)
+        assert a.shape == c.shape and torch.allclose(a, c.cpu(), atol=1e-3, rtol=1e-3)
+
+
+def test_fuse_invariance():
+    """tests/test_model_convert.py:43-44 of the reference: model(x)[0] == model.fuse()(x)[0]."""
+    from copy import deepcopy
+
+    from ayolov2_b200 import synth as model_utils
+
+    model = model_utils.build_model("yolov5s", seed=3).cuda()
+    x = torch.rand((1, 3, 256, 256), device="cuda")
+    a = model(x)[0]
+    fused = deepcopy(model).fuse()
+    n0 = sum(p.numel() for p in model.parameters())
+    n1 = sum(p.numel() for p in fused.parameters())
+    assert n0 - n1 == sum(m.num_features for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    b = fused(x)[0]
+    assert torch.allclose(a, b, rtol=2e-2, atol=2e-2)
