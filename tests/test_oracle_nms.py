@@ -1,0 +1,49 @@
+"""Pins oracle/nms_oracle.py to the reference non_max_suppression / batched_nms: bit-exact on the committed
+golden fixture (tests/golden/nms_golden.npz, outputs of the unmodified reference) and, when /root/reference is
+present, against the reference itself on larger synthetic tensors."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nms_oracle, ref_import
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "nms_golden.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+
+
+def test_nms_oracle_matches_golden():
+    import make_golden as mg
+
+    z = np.load(GOLD)
+    pred = torch.from_numpy(z["pred"])
+    for si, kw in enumerate(mg.NMS_SETTINGS):
+        got = nms_oracle.non_max_suppression(pred, **kw)
+        for i, g in enumerate(got):
+            want = z[f"nms{si}_img{i}"]
+            assert g.shape == want.shape and np.array_equal(g.numpy(), want), (si, i)
+    got = nms_oracle.batched_nms(pred, 0.05, 0.65, 100, False)
+    for i, g in enumerate(got):
+        assert np.array_equal(g.numpy(), z[f"bnms_img{i}"])
+
+
+def test_xywh2xyxy_roundtrip_property():
+    """tests/test_utils_general.py:16-47 of the reference: xyxy2xywh(xywh2xyxy(x)) == x."""
+    x = torch.rand(100, 4).numpy() * 100 + 1
+    y = nms_oracle.xywh2xyxy(x)
+    back = np.stack(((y[:, 0] + y[:, 2]) / 2, (y[:, 1] + y[:, 3]) / 2, y[:, 2] - y[:, 0], y[:, 3] - y[:, 1]), 1)
+    assert np.allclose(back, x, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("kw", [dict(conf_thres=0.25, iou_thres=0.45), dict(conf_thres=0.25, iou_thres=0.45, multi_label=True),
+                                dict(conf_thres=0.3, iou_thres=0.65, agnostic=True), dict(conf_thres=0.01, iou_thres=0.6, nms_type="batched_nms")])
+def test_nms_oracle_matches_reference(kw):
+    ref = ref_import.load()
+    pred = nms_oracle.synth_predictions(2, n=3000, seed=4)
+    a = ref.non_max_suppression(pred.clone(), **kw)
+    b = nms_oracle.non_max_suppression(pred.clone(), **kw)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)
