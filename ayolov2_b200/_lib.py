@@ -27,7 +27,8 @@ class ConvDesc(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32),
         ("stride", C.c_int32), ("pad", C.c_int32),
         ("act", C.c_int32), ("res_cstride", C.c_int32),
-        ("cout_pad", C.c_int32), ("reserved", C.c_int32),
+        ("cout_pad", C.c_int32), ("pad_w", C.c_int32),
+        ("in_pix_stride", C.c_int32), ("in_row_pixels", C.c_int32),
     ]
 
 
@@ -40,6 +41,30 @@ class NmsParams(C.Structure):
         ("batch", C.c_int32), ("n", C.c_int32), ("no", C.c_int32),
         ("multi_label", C.c_int32), ("agnostic", C.c_int32),
         ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_candidates", C.c_int32),
+    ]
+
+
+class HeadLevels(C.Structure):
+    """ay2_head_levels (include/ay2.h)."""
+
+    _fields_ = [
+        ("nl", C.c_int32), ("na", C.c_int32),
+        ("logits", C.c_void_p * 5),
+        ("ny", C.c_int32 * 5), ("nx", C.c_int32 * 5), ("cstride", C.c_int32 * 5),
+        ("stride_px", C.c_float * 5),
+        ("anchor_px", (C.c_float * 2) * 8 * 5),
+    ]
+
+
+class LossParams(C.Structure):
+    """ay2_loss_params (include/ay2.h)."""
+
+    _fields_ = [
+        ("nl", C.c_int32), ("na", C.c_int32), ("nc", C.c_int32), ("bs", C.c_int32), ("nt", C.c_int32),
+        ("ny", C.c_int32 * 5), ("nx", C.c_int32 * 5),
+        ("balance", C.c_float * 5),
+        ("anchor_t", C.c_float), ("box", C.c_float), ("obj", C.c_float), ("cls", C.c_float),
+        ("cls_pw", C.c_float), ("obj_pw", C.c_float), ("cp", C.c_float), ("cn", C.c_float),
     ]
 
 
@@ -57,14 +82,19 @@ _PROTOS = {
     "ay2_conv_reference_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "ay2_space_to_depth": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
-                                     C.c_void_p]),
+                                     C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_sppf_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_upsample2x": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                  C.c_int32, C.c_void_p]),
     "ay2_head_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ay2_yolo_loss_workspace_bytes": (C.c_size_t, [C.POINTER(LossParams)]),
+    "ay2_yolo_loss": (C.c_int, [C.POINTER(LossParams), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ay2_nms_workspace_bytes": (C.c_size_t, [C.POINTER(NmsParams)]),
+    "ay2_nms_from_logits": (C.c_int, [C.POINTER(HeadLevels), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_nms_batched": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -31,15 +31,14 @@ struct ConvKernelParams {
   int num_m_tiles, num_n_tiles;
   int boxes_x, boxes_per_img;
   int BH, BW, NB;
-  int kh, kw, stride, pad;
+  int kh, kw, stride, pad, pad_w;
   int cin_chunks;  // Cin / CK
   int cin;         // K extent per tap in the packed weights
   int cout_pad;
   int act, has_res;
 };
 
-constexpr int kSmemBudget = 227 * 1024;
-constexpr int kBiasFloats = 1024;
+constexpr int kSmemPerSm = 227 * 1024;
 
 template <int BLOCK_N, int CK>
 struct ConvCfg {
@@ -52,8 +51,12 @@ struct ConvCfg {
   static constexpr int SLAB_BYTES = 128 * SWO;
   static constexpr int NSLAB = BLOCK_N / OC;
   static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2;
-  static constexpr int TAIL_BYTES = kBiasFloats * 4 + 256;  // bias + barriers + tmem ptr
-  static constexpr int NSTAGES_RAW = (kSmemBudget - 1024 - STAGING_BYTES - TAIL_BYTES) / STAGE_BYTES;
+  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256;  // bias slice + barriers + tmem ptr
+  // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
+  // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
+  static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
+  static constexpr int SMEM_BUDGET = kSmemPerSm / CTAS_PER_SM - 1024;  // 1 KB per CTA is reserved by the system
+  static constexpr int NSTAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - TAIL_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
   static constexpr int SMEM_BYTES = 1024 + NSTAGES * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 64..512, power of two
@@ -66,7 +69,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int BLOCK_N, int CK>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N, CK>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle patterns repeat every 1024 B and UMMA descriptors assume base_offset 0
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
   uint8_t* stages = smem;
   uint8_t* staging = smem + Cfg::NSTAGES * Cfg::STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + kBiasFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   uint64_t* full_bar = bars;                      // [NSTAGES]
   uint64_t* empty_bar = bars + Cfg::NSTAGES;      // [NSTAGES]
   uint64_t* tmem_full = bars + 2 * Cfg::NSTAGES;  // [2]
@@ -103,7 +106,6 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     tma_prefetch_desc(&p.tmOut);
   }
   if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
-  for (int i = threadIdx.x; i < p.cout_pad && i < kBiasFloats; i += blockDim.x) bias_s[i] = p.bias[i];
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -134,9 +136,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             int dy, dx, view = 0;
             if (p.stride == 1) {
               dy = kh - p.pad;
-              dx = kw - p.pad;
+              dx = kw - p.pad_w;
             } else {
-              const int uy = kh - p.pad, ux = kw - p.pad;
+              const int uy = kh - p.pad, ux = kw - p.pad_w;
               const int ph = uy & 1, pw = ux & 1;
               dy = (uy - ph) >> 1;
               dx = (ux - pw) >> 1;
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
           }
         }
       }
+      for (int i = et; i < BLOCK_N; i += 128) bias_s[i] = p.bias[n0 + i];
       named_bar_sync(1, 128);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(v[g * 8 + i]) + bias_s[n0 + c0 + g * 8 + i];
-            if (p.act == AY2_ACT_SILU) x = __fdividef(x, 1.0f + __expf(-x));
+            float x = __uint_as_float(v[g * 8 + i]) + bias_s[c0 + g * 8 + i];
+            if (p.act == AY2_ACT_SILU) x = silu_f(x);
             f[i] = x;
           }
           uint4* dst = reinterpret_cast<uint4*>(slab + swizzled_offset<Cfg::SWO>(et, chunk0 + g));
@@ -426,14 +429,18 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   AY2_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(weight) & 15) == 0,
               "conv buffers must be 16-byte aligned");
+  const int pad_w = d->pad_w < 0 ? d->pad : d->pad_w;
+  const int64_t pix_stride = d->in_pix_stride > 0 ? d->in_pix_stride : d->in_cstride;
+  const int64_t row_pixels = d->in_row_pixels > 0 ? d->in_row_pixels : d->in_w;
+  AY2_REQUIRE(pix_stride % 8 == 0, "in_pix_stride must be a multiple of 8 elements");
+  AY2_REQUIRE(d->stride == 1 || (d->in_pix_stride <= 0 && d->in_row_pixels <= 0), "custom input strides need stride 1");
   const int exp_oh = (d->in_h + 2 * d->pad - d->kh) / d->stride + 1;
-  const int exp_ow = (d->in_w + 2 * d->pad - d->kw) / d->stride + 1;
+  const int exp_ow = (d->in_w + 2 * pad_w - d->kw) / d->stride + 1;
   AY2_REQUIRE(exp_oh == d->out_h && exp_ow == d->out_w, "conv output size %dx%d does not match %dx%d", d->out_h,
               d->out_w, exp_oh, exp_ow);
   if (d->stride == 2) AY2_REQUIRE(d->in_h % 2 == 0 && d->in_w % 2 == 0, "stride-2 conv needs even input size");
   const int bn = ay2_conv_block_n(d->cout);
   AY2_REQUIRE(d->cout_pad >= d->cout && d->cout_pad % bn == 0, "cout_pad=%d must be a multiple of %d", d->cout_pad, bn);
-  AY2_REQUIRE(d->cout_pad <= kBiasFloats, "cout_pad=%d exceeds %d", d->cout_pad, kBiasFloats);
   AY2_REQUIRE(d->res_cstride == 0 || residual, "residual stride given without a residual pointer");
   AY2_REQUIRE(d->res_cstride % 8 == 0, "residual channel stride must be a multiple of 8");
 
@@ -459,6 +466,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   kp.kw = d->kw;
   kp.stride = d->stride;
   kp.pad = d->pad;
+  kp.pad_w = pad_w;
   kp.cin = d->cin;
   kp.cin_chunks = d->cin / ck;
   kp.cout_pad = d->cout_pad;
@@ -469,8 +477,9 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   int rc = AY2_OK;
   const int64_t cs = d->in_cstride;
   if (d->stride == 1) {
-    rc = encode_act_map(&kp.tmA[0], in, d->cin, d->in_w, d->in_h, d->batch, cs, cs * d->in_w,
-                        cs * d->in_w * d->in_h, ck, bw, bh);
+    // pix_stride < cin gives overlapping windows of neighbouring pixels (the packed 16-channel stem)
+    rc = encode_act_map(&kp.tmA[0], in, d->cin, d->in_w, d->in_h, d->batch, pix_stride, pix_stride * row_pixels,
+                        pix_stride * row_pixels * d->in_h, ck, bw, bh);
   } else {
     for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
       for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {
@@ -549,6 +558,9 @@ __global__ void conv_ref_simt_kernel(ay2_conv_desc d, const __nv_bfloat16* __res
                                      const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                                      const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)d.batch * d.out_h * d.out_w * d.cout;
+  const int pad_w = d.pad_w < 0 ? d.pad : d.pad_w;
+  const long long pixs = d.in_pix_stride > 0 ? d.in_pix_stride : d.in_cstride;
+  const long long rowp = d.in_row_pixels > 0 ? d.in_row_pixels : d.in_w;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx % d.cout);
@@ -561,9 +573,9 @@ __global__ void conv_ref_simt_kernel(ay2_conv_desc d, const __nv_bfloat16* __res
       const int iy = oy * d.stride + kh - d.pad;
       if (iy < 0 || iy >= d.in_h) continue;
       for (int kw = 0; kw < d.kw; ++kw) {
-        const int ix = ox * d.stride + kw - d.pad;
+        const int ix = ox * d.stride + kw - pad_w;
         if (ix < 0 || ix >= d.in_w) continue;
-        const __nv_bfloat16* ip = in + (((long long)b * d.in_h + iy) * d.in_w + ix) * d.in_cstride;
+        const __nv_bfloat16* ip = in + (((long long)b * d.in_h + iy) * rowp + ix) * pixs;
         const __nv_bfloat16* wp = w + ((long long)n * d.kh * d.kw + kh * d.kw + kw) * d.cin;
         for (int c = 0; c < d.cin; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
       }

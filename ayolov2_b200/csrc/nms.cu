@@ -18,8 +18,11 @@
 //   tested against the boxes kept so far, then a 256x256 bit matrix of within-chunk overlaps is built and
 //   resolved word by word by one warp. The scan stops as soon as max_det boxes are kept, which is what
 //   makes greedy NMS cheap: later candidates cannot change the first max_det decisions.
+#include <string.h>
+
 #include "ay2_common.h"
 #include "ay2_ptx.cuh"
+#include "head_math.cuh"
 
 namespace ay2 {
 
@@ -133,10 +136,127 @@ __device__ __forceinline__ void bitonic_sort(Ptr A, int N) {
   }
 }
 
+// Where a candidate's xywh box comes from: the dense fp32 prediction tensor, or (fused path) the bf16 head
+// logits of the pyramid level the row belongs to, decoded on the fly with the shared head arithmetic.
+struct BoxSource {
+  const float* pred;  // dense mode: (B, n, no); nullptr in logits mode
+  int n, no;
+  int nl, na;
+  const __nv_bfloat16* logits[AY2_NMS_MAX_LEVELS];
+  int ny[AY2_NMS_MAX_LEVELS], nx[AY2_NMS_MAX_LEVELS], cstride[AY2_NMS_MAX_LEVELS];
+  int row_off[AY2_NMS_MAX_LEVELS + 1];
+  float stride_px[AY2_NMS_MAX_LEVELS];
+  float anchor_px[AY2_NMS_MAX_LEVELS][AY2_NMS_MAX_ANCHORS][2];
+};
+
+__device__ __forceinline__ float4 load_xywh(const BoxSource& s, int b, int row) {
+  if (s.pred) {
+    const float* rp = s.pred + ((long long)b * s.n + row) * s.no;
+    return make_float4(rp[0], rp[1], rp[2], rp[3]);
+  }
+  int l = 0;
+  while (l + 1 < s.nl && row >= s.row_off[l + 1]) ++l;
+  const int r = row - s.row_off[l];
+  const int plane = s.ny[l] * s.nx[l];
+  const int a = r / plane;
+  const int pix = r - a * plane;
+  const int y = pix / s.nx[l], x = pix - y * s.nx[l];
+  const __nv_bfloat16* lp = s.logits[l] + ((long long)b * plane + pix) * s.cstride[l] + a * s.no;
+  float4 o;
+  o.x = head_xy(head_sigmoid(__bfloat162float(lp[0])), (float)x, s.stride_px[l]);
+  o.y = head_xy(head_sigmoid(__bfloat162float(lp[1])), (float)y, s.stride_px[l]);
+  o.z = head_wh(head_sigmoid(__bfloat162float(lp[2])), s.anchor_px[l][a][0]);
+  o.w = head_wh(head_sigmoid(__bfloat162float(lp[3])), s.anchor_px[l][a][1]);
+  return o;
+}
+
+// Fused filter: candidates straight from the head logits (no dense (B, 25200, 85) tensor is ever written).
+// One warp per 32 consecutive pixels of one level; lanes test the objectness logit of each anchor, then the
+// warp scores the passing (pixel, anchor) rows cooperatively. Scores are bit-identical to head_decode + filter.
+__global__ void nms_filter_logits_kernel(BoxSource src, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
+                                         unsigned long long* __restrict__ keys, long long key_stride,
+                                         int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nc = src.no - 5;
+  unsigned long long* kb = keys + (long long)b * key_stride;
+  for (int l = 0; l < src.nl; ++l) {
+    const int plane = src.ny[l] * src.nx[l];
+    const int groups = (plane + 31) / 32;
+    const __nv_bfloat16* base = src.logits[l] + (long long)b * plane * src.cstride[l];
+    for (int g = warp_in_grid; g < groups; g += nwarps) {
+      const int pix = g * 32 + lane;
+      for (int a = 0; a < src.na; ++a) {
+        float obj = 0.f;
+        if (pix < plane) obj = head_sigmoid(__bfloat162float(base[(long long)pix * src.cstride[l] + a * src.no + 4]));
+        unsigned pass = __ballot_sync(0xffffffffu, pix < plane && obj > p.conf_thres);
+        while (pass) {
+          const int r = __ffs(pass) - 1;
+          pass &= pass - 1;
+          const int rpix = g * 32 + r;
+          const int row = src.row_off[l] + a * plane + rpix;
+          const float robj = __shfl_sync(0xffffffffu, obj, r);
+          const __nv_bfloat16* cp = base + (long long)rpix * src.cstride[l] + a * src.no + 5;
+          if (p.multi_label) {
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+              const int c = c0 + lane;
+              float conf = 0.f;
+              bool ok = false;
+              if (c < nc) {
+                conf = __fmul_rn(head_sigmoid(__bfloat162float(cp[c])), robj);
+                ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, ok);
+              if (m) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&counts[b], __popc(m));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (ok) {
+                  const int slot = slot0 + __popc(m & ((1u << lane) - 1));
+                  if (slot < p.max_candidates)
+                    kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) |
+                               static_cast<unsigned>(row * nc + c);
+                }
+              }
+            }
+          } else {
+            float best = -INFINITY;
+            int bidx = 0x7fffffff;
+            for (int c = lane; c < nc; c += 32) {
+              const float conf = __fmul_rn(head_sigmoid(__bfloat162float(cp[c])), robj);
+              if (conf > best) {
+                best = conf;
+                bidx = c;
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+              if (ob > best || (ob == best && oi < bidx)) {
+                best = ob;
+                bidx = oi;
+              }
+            }
+            if (lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx])) {
+              const int slot = atomicAdd(&counts[b], 1);
+              if (slot < p.max_candidates)
+                kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) |
+                           static_cast<unsigned>(row * nc + bidx);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1)
-    nms_sort_scan_kernel(const float* __restrict__ pred, ay2_nms_params p, unsigned long long* __restrict__ keys,
-                         long long key_stride, const int* __restrict__ counts, float* __restrict__ out_det,
-                         int* __restrict__ out_count, int* __restrict__ overflow) {
+    nms_sort_scan_kernel(BoxSource src, ay2_nms_params p, unsigned long long* __restrict__ keys, long long key_stride,
+                         const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
+                         int* __restrict__ overflow) {
   extern __shared__ __align__(16) uint8_t sm[];
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);             // [kSortSmemKeys]
   float4* cbo = reinterpret_cast<float4*>(skeys + kSortSmemKeys);                    // chunk boxes + class offset
@@ -146,21 +266,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   float* cconf = carea + kChunk;                                                     // [kChunk]
   float* karea = cconf + kChunk;                                                     // [kMaxDetCap]
   int* ccls = reinterpret_cast<int*>(karea + kMaxDetCap);                            // [kChunk]
-  int* alive = ccls + kChunk;                                                        // [kChunk]
+  int* kcls = ccls + kChunk;                                                         // [kMaxDetCap]
+  int* alive = kcls + kMaxDetCap;                                                    // [kChunk]
   int* kept_idx = alive + kChunk;                                                    // [kChunk]
   unsigned* mask = reinterpret_cast<unsigned*>(kept_idx + kChunk);                   // [kChunk][kChunkWords]
-  __shared__ int s_kept, s_new;
+  __shared__ int s_kept, s_new, s_wide;
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int wid = tid >> 5;
+  const int nwarp = blockDim.x >> 5;
   const int nc = p.no - 5;
   int n = counts[b];
   if (n > p.max_candidates) {
     n = p.max_candidates;
     if (tid == 0) atomicExch(overflow, 1);
   }
-  if (tid == 0) s_kept = 0;
+  if (tid == 0) {
+    s_kept = 0;
+    s_wide = 0;
+  }
   if (n == 0) {
     if (tid == 0) out_count[b] = 0;
     return;
@@ -183,7 +309,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   }
   if (n > p.max_nms) n = p.max_nms;
   const double thr = p.iou_thres;
-  const float* ip = pred + (long long)b * p.n * p.no;
 
   // ---------------------------------------------------------------- greedy scan
   for (int cs = 0; cs < n; cs += kChunk) {
@@ -198,8 +323,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         const float score = __uint_as_float(~static_cast<unsigned>(key >> 32));
         const int row = idx / nc;
         const int cls = idx - row * nc;
-        const float* rp = ip + (long long)row * p.no;
-        const float4 r = make_float4(rp[0], rp[1], rp[2], rp[3]);
+        const float4 r = load_xywh(src, b, row);
         // general.py:316-319 with ratio = wh = 1, pad = 0  (1*1*(x -+ w/2) + 0)
         float4 bx;
         bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
@@ -218,15 +342,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
         cconf[tid] = score;
         ccls[tid] = cls;
         al = 1;
+        // Boxes of different classes are max_wh apart after the offset: they can only intersect if some box
+        // reaches outside the window [-max_wh/4, 3*max_wh/4 - 2] (2 px of slack for the rounding of the offset
+        // add). If none does, cross-class pairs are skipped without evaluating the IoU -- an exact shortcut.
+        const float lo = -0.25f * p.max_wh, hi = 0.75f * p.max_wh - 2.0f;
+        if (!(bx.x >= lo && bx.y >= lo && bx.z <= hi && bx.w <= hi)) s_wide = 1;
       }
       alive[tid] = al;
     }
     __syncthreads();
-    // (1) chunk vs. boxes kept so far
-    for (int t = tid; t < cn * kc; t += blockDim.x) {
-      const int k = t / cn;
-      const int c = t - k * cn;
-      if (alive[c] && iou_gt(kbo[k], karea[k], cbo[c], carea[c], thr)) alive[c] = 0;
+    const bool by_class = !p.agnostic && !s_wide;
+    // (1) chunk vs. boxes kept so far: warp per kept box, lanes over candidates
+    for (int k = wid; k < kc; k += nwarp) {
+      const float4 kb4 = kbo[k];
+      const float ka = karea[k];
+      const int kcl = kcls[k];
+      for (int c = lane; c < cn; c += 32) {
+        if (!alive[c]) continue;
+        if (by_class && ccls[c] != kcl) continue;
+        if (iou_gt(kb4, ka, cbo[c], carea[c], thr)) alive[c] = 0;
+      }
     }
     __syncthreads();
     // (2) within-chunk overlap bit matrix: mask[i][w] bit jj <=> j = 32w+jj > i and IoU(i,j) > thr
@@ -237,9 +372,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       if (i < cn && alive[i] && (w * 32 + 31) > i) {
         const float4 bi = cbo[i];
         const float ai = carea[i];
+        const int ci = ccls[i];
         for (int jj = 0; jj < 32; ++jj) {
           const int j = w * 32 + jj;
-          if (j > i && j < cn && alive[j] && iou_gt(bi, ai, cbo[j], carea[j], thr)) bits |= 1u << jj;
+          if (j <= i || j >= cn || !alive[j]) continue;
+          if (by_class && ccls[j] != ci) continue;
+          if (iou_gt(bi, ai, cbo[j], carea[j], thr)) bits |= 1u << jj;
         }
       }
       mask[t] = bits;
@@ -278,6 +416,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       const int k = kc + tid;
       kbo[k] = cbo[gi];
       karea[k] = carea[gi];
+      kcls[k] = ccls[gi];
       float* o = out_det + ((long long)b * p.max_det + k) * 6;
       const float4 bx = cbox[gi];
       o[0] = bx.x;
@@ -295,7 +434,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 }
 
 constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys + sizeof(float4) * (2 * kChunk + kMaxDetCap) +
-                                 sizeof(float) * (2 * kChunk + kMaxDetCap) + sizeof(int) * 3 * kChunk +
+                                 sizeof(float) * (2 * kChunk + kMaxDetCap) + sizeof(int) * (3 * kChunk + kMaxDetCap) +
                                  sizeof(unsigned) * kChunk * kChunkWords;
 
 static long long key_stride_for(const ay2_nms_params* p) {
@@ -315,17 +454,40 @@ extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
   return head + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p);
 }
 
-extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
-                               size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
-                               void* stream) {
-  AY2_REQUIRE(pred && p && workspace && out_det && out_count, "ay2_nms_batched: null pointer");
-  AY2_REQUIRE(p->no > 5 && p->n > 0 && p->batch > 0, "ay2_nms_batched: bad shape (batch=%d n=%d no=%d)", p->batch, p->n,
-              p->no);
+static int nms_common_checks(const ay2_nms_params* p, const void* workspace, size_t workspace_bytes, const void* out_det,
+                             const void* out_count) {
+  AY2_REQUIRE(p && workspace && out_det && out_count, "ay2_nms: null pointer");
+  AY2_REQUIRE(p->no > 5 && p->n > 0 && p->batch > 0, "ay2_nms: bad shape (batch=%d n=%d no=%d)", p->batch, p->n, p->no);
   AY2_REQUIRE(p->max_det >= 1 && p->max_det <= kMaxDetCap, "max_det=%d unsupported (1..%d)", p->max_det, kMaxDetCap);
   AY2_REQUIRE(p->max_candidates >= 1, "max_candidates must be positive");
   AY2_REQUIRE((long long)p->n * (p->no - 5) < (1LL << 32), "n*nc does not fit the 32-bit candidate index");
   AY2_REQUIRE(workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace too small (%zu < %zu)", workspace_bytes,
               ay2_nms_workspace_bytes(p));
+  return AY2_OK;
+}
+
+static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, unsigned long long* keys, long long ks,
+                                int* counts, int* overflow, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                                cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AY2_CHECK_CUDA(
+        cudaFuncSetAttribute(nms_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
+    attr_set = true;
+  }
+  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, keys, ks, counts, out_det, out_count,
+                                                                     overflow);
+  AY2_CHECK_LAUNCH();
+  if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return AY2_OK;
+}
+
+extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
+                               size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                               void* stream) {
+  AY2_REQUIRE(pred, "ay2_nms_batched: null prediction pointer");
+  int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
+  if (rc != AY2_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
   int* counts = static_cast<int*>(workspace);
@@ -339,16 +501,60 @@ extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const
   if (bx > 64) bx = 64;
   nms_filter_kernel<<<dim3(bx, p->batch), threads, 0, st>>>(pred, *p, class_mask, keys, ks, counts);
   AY2_CHECK_LAUNCH();
-  static bool attr_set = false;
-  if (!attr_set) {
-    AY2_CHECK_CUDA(
-        cudaFuncSetAttribute(nms_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
-    attr_set = true;
+  BoxSource src;
+  memset(&src, 0, sizeof(src));
+  src.pred = pred;
+  src.n = p->n;
+  src.no = p->no;
+  rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
+  if (rc != AY2_OK) return rc;
+  count_launch(2);
+  return AY2_OK;
+}
+
+extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_params* p, const uint8_t* class_mask,
+                                   void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
+                                   int32_t* overflow_flag, void* stream) {
+  AY2_REQUIRE(hl, "ay2_nms_from_logits: null level table");
+  int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
+  if (rc != AY2_OK) return rc;
+  AY2_REQUIRE(hl->nl >= 1 && hl->nl <= AY2_NMS_MAX_LEVELS && hl->na >= 1 && hl->na <= AY2_NMS_MAX_ANCHORS,
+              "ay2_nms_from_logits: nl=%d na=%d unsupported", hl->nl, hl->na);
+  BoxSource src;
+  memset(&src, 0, sizeof(src));
+  src.no = p->no;
+  src.nl = hl->nl;
+  src.na = hl->na;
+  int rows = 0;
+  for (int l = 0; l < hl->nl; ++l) {
+    AY2_REQUIRE(hl->logits[l] && hl->cstride[l] >= hl->na * p->no, "level %d: bad logits pointer / channel stride", l);
+    src.logits[l] = static_cast<const __nv_bfloat16*>(hl->logits[l]);
+    src.ny[l] = hl->ny[l];
+    src.nx[l] = hl->nx[l];
+    src.cstride[l] = hl->cstride[l];
+    src.stride_px[l] = hl->stride_px[l];
+    src.row_off[l] = rows;
+    rows += hl->na * hl->ny[l] * hl->nx[l];
+    for (int a = 0; a < hl->na; ++a) {
+      src.anchor_px[l][a][0] = hl->anchor_px[l][a][0];
+      src.anchor_px[l][a][1] = hl->anchor_px[l][a][1];
+    }
   }
-  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(pred, *p, keys, ks, counts, out_det, out_count,
-                                                                     overflow);
+  src.row_off[hl->nl] = rows;
+  src.n = rows;
+  AY2_REQUIRE(rows == p->n, "level table covers %d rows but params.n = %d", rows, p->n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
+  int* counts = static_cast<int*>(workspace);
+  int* overflow = counts + p->batch;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
+  const long long ks = key_stride_for(p);
+  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (p->batch + 1), st));
+  const int threads = 256;
+  nms_filter_logits_kernel<<<dim3(32, p->batch), threads, 0, st>>>(src, *p, class_mask, keys, ks, counts);
   AY2_CHECK_LAUNCH();
-  if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
+  if (rc != AY2_OK) return rc;
   count_launch(2);
   return AY2_OK;
 }

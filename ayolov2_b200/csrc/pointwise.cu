@@ -2,6 +2,7 @@
 // nearest 2x upsample into a concat slice, and the YOLOHead decode. All coalesced 16-byte accesses.
 #include "ay2_common.h"
 #include "ay2_ptx.cuh"
+#include "head_math.cuh"
 
 namespace ay2 {
 
@@ -12,7 +13,7 @@ namespace ay2 {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void space_to_depth_kernel(const T* __restrict__ img, int B, int H, int W, float scale,
-                                      uint4* __restrict__ out) {
+                                      uint4* __restrict__ out, int out_row_pixels, int out_x_offset) {
   const int OW = W >> 1, OH = H >> 1;
   const long long total = (long long)B * OH * OW;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -51,8 +52,9 @@ __global__ void space_to_depth_kernel(const T* __restrict__ img, int B, int H, i
     o1.y = pack_bf16x2(v[10], v[11]);
     o1.z = pack_bf16x2(v[12], v[13]);
     o1.w = pack_bf16x2(v[14], v[15]);
-    out[idx * 2] = o0;
-    out[idx * 2 + 1] = o1;
+    const long long opix = ((long long)b * OH + oy) * out_row_pixels + ox + out_x_offset;
+    out[opix * 2] = o0;
+    out[opix * 2 + 1] = o1;
   }
 }
 
@@ -159,32 +161,59 @@ __global__ void head_decode_kernel(const __nv_bfloat16* __restrict__ logits, int
                                    int na, int no, float stride_px, const float* __restrict__ anchor_wh,
                                    float* __restrict__ pred, long long total_rows, long long row_offset,
                                    float* __restrict__ raw) {
+  // One warp per pixel. Each lane loads 8 consecutive logits (one 16-byte read), decodes them and parks the
+  // results in shared memory; the warp then streams each anchor's `no` floats out with consecutive lanes.
+  extern __shared__ float dsm[];
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nch = na * no;
+  const int nch8 = (nch + 7) & ~7;
+  float* vbuf = dsm + (size_t)wib * 2 * nch8;  // decoded values
+  float* rbuf = vbuf + nch8;                   // raw logits (fp32)
   const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long npix = (long long)B * ny * nx;
-  const int nch = na * no;
   for (long long pix = warp_id; pix < npix; pix += nwarps) {
     const int x = (int)(pix % nx);
     const int y = (int)((pix / nx) % ny);
     const int b = (int)(pix / ((long long)nx * ny));
     const __nv_bfloat16* lp = logits + pix * cstride;
-    for (int ch = lane; ch < nch; ch += 32) {
-      const int a = ch / no;
-      const int o = ch - a * no;
-      const float t = __bfloat162float(lp[ch]);
-      const long long cell = (long long)a * ny * nx + (long long)y * nx + x;
-      if (raw) raw[(((long long)b * na) * ny * nx + cell) * no + o] = t;
-      const float s = 1.0f / (1.0f + __expf(-t));
-      float v = s;
-      if (o == 0) v = (s * 2.0f - 0.5f + (float)x) * stride_px;
-      else if (o == 1) v = (s * 2.0f - 0.5f + (float)y) * stride_px;
-      else if (o == 2 || o == 3) {
-        const float q = s * 2.0f;
-        v = q * q * anchor_wh[a * 2 + (o - 2)];
+    for (int c0 = lane * 8; c0 < nch8; c0 += 256) {
+      const uint4 q = *reinterpret_cast<const uint4*>(lp + c0);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+      int a = c0 / no;
+      int o = c0 - a * no;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 f = __bfloat1622float2(h2[j >> 1]);
+        const float t = (j & 1) ? f.y : f.x;
+        const float s = head_sigmoid(t);
+        float v = s;
+        if (a < na) {
+          if (o == 0) v = head_xy(s, (float)x, stride_px);
+          else if (o == 1) v = head_xy(s, (float)y, stride_px);
+          else if (o == 2) v = head_wh(s, anchor_wh[a * 2]);
+          else if (o == 3) v = head_wh(s, anchor_wh[a * 2 + 1]);
+        }
+        vbuf[c0 + j] = v;
+        rbuf[c0 + j] = t;
+        if (++o == no) {
+          o = 0;
+          ++a;
+        }
       }
-      pred[((long long)b * total_rows + row_offset + cell) * no + o] = v;
     }
+    __syncwarp();
+    for (int a = 0; a < na; ++a) {
+      const long long cell = (long long)a * ny * nx + (long long)y * nx + x;
+      float* dst = pred + ((long long)b * total_rows + row_offset + cell) * no;
+      for (int o = lane; o < no; o += 32) dst[o] = vbuf[a * no + o];
+      if (raw) {
+        float* rdst = raw + (((long long)b * na) * ny * nx + cell) * no;
+        for (int o = lane; o < no; o += 32) rdst[o] = rbuf[a * no + o];
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -199,20 +228,21 @@ static int grid_for(long long total, int threads, int per_sm) {
 }
 
 extern "C" int ay2_space_to_depth(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float scale,
-                                  void* out, void* stream) {
+                                  void* out, int32_t out_row_pixels, int32_t out_x_offset, void* stream) {
   AY2_REQUIRE(img && out, "ay2_space_to_depth: null pointer");
   AY2_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0, "space_to_depth needs even H,W (got %dx%d)", h, w);
   AY2_REQUIRE(dtype == AY2_DT_U8 || dtype == AY2_DT_F32, "space_to_depth dtype %d unsupported", dtype);
+  AY2_REQUIRE(out_x_offset >= 0 && out_row_pixels >= w / 2 + out_x_offset, "space_to_depth output row too short");
   const long long total = (long long)batch * (h / 2) * (w / 2);
   const int threads = 256;
   const int blocks = grid_for(total, threads, 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == AY2_DT_U8)
     space_to_depth_kernel<uint8_t><<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(img), batch, h, w, scale,
-                                                               static_cast<uint4*>(out));
+                                                               static_cast<uint4*>(out), out_row_pixels, out_x_offset);
   else
     space_to_depth_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(img), batch, h, w, scale,
-                                                             static_cast<uint4*>(out));
+                                                             static_cast<uint4*>(out), out_row_pixels, out_x_offset);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;
@@ -258,9 +288,12 @@ extern "C" int ay2_head_decode(const void* logits, int32_t batch, int32_t ny, in
                                int64_t row_offset, float* raw, void* stream) {
   AY2_REQUIRE(logits && anchor_wh_px && pred, "ay2_head_decode: null pointer");
   AY2_REQUIRE(na * no <= cstride, "head_decode: na*no=%d exceeds channel stride %d", na * no, cstride);
+  AY2_REQUIRE(cstride % 8 == 0 && ((na * no + 7) & ~7) <= cstride, "head_decode: channel stride %d too small", cstride);
   const long long npix = (long long)batch * ny * nx;
   const int threads = 256;
-  head_decode_kernel<<<grid_for(npix * 32, threads, 16), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const size_t smem = (size_t)(threads / 32) * 2 * ((na * no + 7) & ~7) * sizeof(float);
+  AY2_REQUIRE(smem <= 48 * 1024, "head_decode: na*no=%d too large", na * no);
+  head_decode_kernel<<<grid_for(npix * 32, threads, 8), threads, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(logits), batch, ny, nx, cstride, na, no, stride_px, anchor_wh_px, pred,
       total_rows, row_offset, raw);
   AY2_CHECK_LAUNCH();

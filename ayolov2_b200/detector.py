@@ -22,7 +22,8 @@ from .nms import nms_device
 class Detector:
     def __init__(self, model: nn.Module, batch: int, height: int = 640, width: int = 640, conf_thres: float = 0.25,
                  iou_thres: float = 0.45, multi_label: bool = False, agnostic: bool = False, max_det: int = 300,
-                 in_dtype: torch.dtype = torch.uint8, device: Optional[torch.device] = None, want_raw: bool = False) -> None:
+                 in_dtype: torch.dtype = torch.uint8, device: Optional[torch.device] = None, want_raw: bool = False,
+                 dense_pred: bool = False) -> None:
         scale = 1.0 / 255.0 if in_dtype == torch.uint8 else 1.0
         self.engine = Engine(model, batch, height, width, in_dtype=in_dtype, scale=scale, want_raw=want_raw,
                              device=device, use_graph=False)
@@ -35,6 +36,11 @@ class Detector:
         nc = pred.shape[2] - 5
         self.nms_ws = ops.NmsWorkspace(batch, pred.shape[1], pred.shape[2], max_det=max_det,
                                        multi_label=multi_label and nc > 1, device=self.device)
+        # fused head: NMS candidates and boxes are decoded straight from the bf16 head logits, the dense
+        # (B, 25200, 85) tensor is not written unless `dense_pred` is requested
+        self.dense_pred = dense_pred
+        eng = self.engine
+        self.levels = ops.make_head_levels(eng.head_logits, eng.na, eng.head_strides, eng.head_anchors_px)
         # two input / output slots for the host pipeline
         self.dev_in = [torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) for _ in range(2)]
         self.host_out = [torch.zeros((batch, max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -52,13 +58,19 @@ class Detector:
         """Everything after the space-to-depth kernel (which reads a per-slot input buffer): convs, head, NMS."""
         eng = self.engine
         for s in eng.b.steps:
-            if s is not eng.b.s2d_step:
-                s()
-        nms_device(eng.pred, self.conf_thres, self.iou_thres, agnostic=self.agnostic, multi_label=self.multi_label,
-                   max_det=self.max_det, workspace=self.nms_ws)
+            if s is eng.b.s2d_step or (not self.dense_pred and s in eng.decode_steps):
+                continue
+            s()
+        if self.dense_pred:
+            nms_device(eng.pred, self.conf_thres, self.iou_thres, agnostic=self.agnostic, multi_label=self.multi_label,
+                       max_det=self.max_det, workspace=self.nms_ws)
+        else:
+            self.nms_ws.p.multi_label = int(self.multi_label and eng.no - 5 > 1)
+            self.nms_ws.run_logits(self.levels, eng.head_logits, self.conf_thres, self.iou_thres, agnostic=self.agnostic)
 
     def launches_per_step(self) -> int:
-        return len(self.engine.b.steps) + 2  # + NMS filter and sort/scan kernels
+        n = len(self.engine.b.steps) + 2  # + NMS filter and sort/scan kernels
+        return n if self.dense_pred else n - len(self.engine.decode_steps)
 
     def run_device(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """img: CUDA NCHW tensor of the detector's dtype. Asynchronous; returns (det [B,max_det,6], count [B])."""

@@ -131,9 +131,14 @@ class Builder:
         name = type(m).__name__
         c = m.conv
         assert isinstance(c, nn.Conv2d), "a decomposed stem is not supported"
-        s2d = ops.new_act(self.B, H // 2, W // 2, 16, device=self.device)
+        # Space-to-depth output, horizontally padded: logical pixel x lives at physical column x + 1 and the row has
+        # 8 spare columns, all zero. A k x k conv over the 16-channel pixels is then run as k x 1 taps over 4-pixel
+        # WINDOWS (64 channels = one 128-byte TMA row) starting at physical column x: window = logical pixels x-1..x+2.
+        H2, W2 = H // 2, W // 2
+        Wp = W2 + 8
+        s2d = ActView(torch.zeros((self.B, H2, Wp, 16), dtype=torch.bfloat16, device=self.device), 0, 16)
         self.keep.append(s2d.buf)
-        self.steps.append(lambda: ops.space_to_depth(img_getter(), s2d, scale))
+        self.steps.append(lambda: ops.space_to_depth(img_getter(), s2d, scale, x_offset=1))
         self.s2d_step = self.steps[-1]
         w = c.weight.detach().float().to(self.device)
         if name == "Focus":
@@ -154,10 +159,24 @@ class Builder:
             k2, p2 = 3, 1
         else:
             raise NotImplementedError("first layer must be the 6x6/s2/p2 Conv stem or Focus (SURVEY.md §8a M1/M2)")
+        assert k2 == 3 and p2 == 1, "packed stem handles 3x3/p1 over the space-to-depth grid"
+        cout = w.shape[0]
         bn, eps = _bn_tuple(getattr(m, "batch_norm", None))
+        if bn is not None:
+            bn = tuple(t.detach().float().to(self.device) for t in bn)
         if y is None:
-            y = self.new_act(H // 2 + 2 * p2 - k2 + 1, W // 2 + 2 * p2 - k2 + 1, w.shape[0])
-        self.conv2d(s2d, y, w2, c.bias, bn, eps, _act_code(m), 1, p2)  # 9 taps x 12 ch == 36 taps x 3 ch: same FLOPs
+            y = self.new_act(H2, W2, cout)
+        # window weights: [cout, kh, (kwp in 0..3) * 16 + ch], kwp = 3 and ch >= 12 are zero
+        ww = torch.zeros((cout, 64, 3, 1), device=self.device)  # OIHW with I = 64 window channels, kernel 3x1
+        for kwp in range(3):
+            ww[:, kwp * 16:kwp * 16 + 12, :, 0] = w2[:, :, :, kwp]
+        bias = c.bias.detach().float().to(self.device) if c.bias is not None else None
+        wp, bp = ops.pack_conv_weight(ww, bias, bn, eps)
+        plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2, 16, Wp))
+        self.plans.append(plan)
+        self.steps.append(plan.run)
+        self.flops += 2.0 * self.B * H2 * W2 * cout * 9 * 12  # == 36 taps x 3 channels of the 6x6 stem
+        self.act_bytes += 2.0 * self.B * (H2 * W2 * 12 + H2 * W2 * cout)
         return y
 
     def bottleneck(self, m: nn.Module, y1: ActView) -> None:
@@ -340,6 +359,10 @@ class Engine:
         self.pred = torch.zeros((self.B, total, no), dtype=torch.float32, device=self.device)
         off = 0
         self.na, self.no = na, no
+        self.decode_steps: List[Callable[[], None]] = []
+        self.head_logits: List[ActView] = []
+        self.head_strides = [float(s) for s in m.stride]
+        self.head_anchors_px = [m.anchor_grid[i].detach().float().reshape(-1, 2).tolist() for i in range(len(xs))]
         for i, (conv, x) in enumerate(zip(m.conv, xs)):
             logits = b.new_act(x.H, x.W, _round_up(na * no, 16))
             b.conv2d(x, logits, conv.weight, conv.bias, None, 1e-3, ACT_NONE, 1, 0)
@@ -350,6 +373,8 @@ class Engine:
             b.keep.append(anchors_px)
             stride = float(m.stride[i])
             b.steps.append(lambda l=logits, a=anchors_px, s=stride, o=off, r=raw: ops.head_decode(l, na, no, s, a, self.pred, o, r))
+            self.decode_steps.append(b.steps[-1])
+            self.head_logits.append(logits)
             off += na * x.H * x.W
 
     # ---------------------------------------------------------------------------------------------

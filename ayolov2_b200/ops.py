@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SILU, ConvDesc, NmsParams
+from ._lib import ACT_NONE, ACT_SILU, ConvDesc, HeadLevels, NmsParams
 
 
 @dataclass
@@ -88,15 +88,22 @@ class ConvPlan:
     """ay2_conv_plan: fused conv + bias + act (+ residual) between two ActViews. Keeps its tensors alive."""
 
     def __init__(self, x: ActView, y: ActView, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int,
-                 stride: int, pad: int, act: int, residual: Optional[ActView] = None):
+                 stride: int, pad: int, act: int, residual: Optional[ActView] = None, pad_w: int = -1,
+                 window: Optional[Tuple[int, int, int, int]] = None):
+        """`window` = (cin, in_w, pix_stride, row_pixels): read `x.buf` as overlapping windows of `cin` channels
+        starting at every physical pixel (the packed 16-channel stem); otherwise the input is the ActView `x`."""
         lib = _lib.load()
         cout_pad, ktot = w_packed.shape
-        assert ktot == kh * kw * x.c, (ktot, kh, kw, x.c)
+        cin = window[0] if window else x.c
+        assert ktot == kh * kw * cin, (ktot, kh, kw, cin)
         assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32 and bias.numel() == cout_pad
         assert x.buf.is_cuda and y.buf.is_cuda and w_packed.is_cuda and bias.is_cuda
         d = ConvDesc()
         d.batch = x.B
         d.in_h, d.in_w, d.cin, d.in_cstride = x.H, x.W, x.c, x.cstride
+        d.pad_w = pad_w
+        if window:
+            d.cin, d.in_w, d.in_pix_stride, d.in_row_pixels = window
         d.out_h, d.out_w, d.cout, d.out_cstride = y.H, y.W, y.c, y.cstride
         d.kh, d.kw, d.stride, d.pad, d.act = kh, kw, stride, pad, act
         d.res_cstride = residual.cstride if residual is not None else 0
@@ -128,13 +135,14 @@ class ConvPlan:
             self._h = None
 
 
-def space_to_depth(img: torch.Tensor, out: ActView, scale: float) -> None:
-    """img: NCHW uint8/fp32 [B,3,H,W] -> out [B,H/2,W/2,16]."""
+def space_to_depth(img: torch.Tensor, out: ActView, scale: float, x_offset: int = 0) -> None:
+    """img: NCHW uint8/fp32 [B,3,H,W] -> out [B,H/2,Wp,16] with logical pixel x at physical column x + x_offset
+    (Wp >= W/2 + x_offset; untouched columns keep whatever the caller put there, i.e. zeros = conv padding)."""
     assert img.is_cuda and img.is_contiguous() and img.shape[1] == 3
     B, _, H, W = img.shape
-    assert out.c0 == 0 and out.cstride == 16 and (out.B, out.H, out.W) == (B, H // 2, W // 2)
+    assert out.c0 == 0 and out.cstride == 16 and (out.B, out.H) == (B, H // 2) and out.W >= W // 2 + x_offset
     dt = {torch.uint8: _lib.DT_U8, torch.float32: _lib.DT_F32}[img.dtype]
-    _lib.check(_lib.load().ay2_space_to_depth(img.data_ptr(), dt, B, H, W, float(scale), out.ptr(),
+    _lib.check(_lib.load().ay2_space_to_depth(img.data_ptr(), dt, B, H, W, float(scale), out.ptr(), out.W, x_offset,
                                               _lib.current_stream_ptr()), "ay2_space_to_depth")
 
 
@@ -189,3 +197,29 @@ class NmsWorkspace:
         _lib.check(_lib.load().ay2_nms_batched(pred.data_ptr(), C.byref(p), _lib.ptr(class_mask), self.ws.data_ptr(),
                                                self.ws.numel(), self.out.data_ptr(), self.count.data_ptr(),
                                                self.overflow.data_ptr(), _lib.current_stream_ptr()), "ay2_nms_batched")
+
+    def run_logits(self, levels: "HeadLevels", keep, conf_thres: float, iou_thres: float, agnostic: bool = False,
+                   class_mask: Optional[torch.Tensor] = None, max_nms: int = 30000, max_wh: float = 4096.0) -> None:
+        """Fused head: NMS straight from the bf16 head logits (ay2_nms_from_logits). `keep` = tensors to keep alive."""
+        p = self.p
+        p.conf_thres, p.iou_thres = float(conf_thres), float(iou_thres)
+        p.agnostic, p.max_nms, p.max_wh = int(agnostic), int(max_nms), float(max_wh)
+        self._keepalive = keep
+        _lib.check(_lib.load().ay2_nms_from_logits(C.byref(levels), C.byref(p), _lib.ptr(class_mask), self.ws.data_ptr(),
+                                                   self.ws.numel(), self.out.data_ptr(), self.count.data_ptr(),
+                                                   self.overflow.data_ptr(), _lib.current_stream_ptr()),
+                   "ay2_nms_from_logits")
+
+
+def make_head_levels(logits: Sequence[ActView], na: int, strides: Sequence[float], anchors_px: Sequence[Sequence[Sequence[float]]]) -> HeadLevels:
+    hl = HeadLevels()
+    hl.nl, hl.na = len(logits), na
+    for i, lv in enumerate(logits):
+        assert lv.c0 == 0
+        hl.logits[i] = lv.ptr()
+        hl.ny[i], hl.nx[i], hl.cstride[i] = lv.H, lv.W, lv.cstride
+        hl.stride_px[i] = float(strides[i])
+        for a in range(na):
+            hl.anchor_px[i][a][0] = float(anchors_px[i][a][0])
+            hl.anchor_px[i][a][1] = float(anchors_px[i][a][1])
+    return hl

@@ -215,7 +215,7 @@ def main() -> None:
     ms_per_step = ms / args.steps
     value = world * BATCH * args.steps / (ms / 1000.0)
     ndet = int(det.nms_ws.count.sum().item())
-    ncand = int((det.engine.pred[..., 4] > CONF).sum().item())
+    ncand = int(det.nms_ws.ws[:4 * BATCH].view(torch.int32).sum().item())  # per-image candidate counters
 
     # ------------------------------------------------------------------ end to end through the host API (`e2e`)
     for i in range(args.warmup):

@@ -63,7 +63,11 @@ typedef struct ay2_conv_desc {
   int32_t act;            /* AY2_ACT_* */
   int32_t res_cstride;    /* channel stride of the residual buffer (0 = no residual) */
   int32_t cout_pad;       /* rows in the packed weight matrix (>= cout, multiple of the N tile) */
-  int32_t reserved;
+  int32_t pad_w;          /* horizontal padding if different from `pad` (-1 = same) */
+  int32_t in_pix_stride;  /* elements between horizontally adjacent input pixels (0 = in_cstride). A value below
+                             `cin` makes each input "pixel" an overlapping window of neighbouring pixels: the
+                             16-channel space-to-depth stem is run as kh x 1 taps over 4-pixel windows (cin 64) */
+  int32_t in_row_pixels;  /* physical pixels per input row (0 = in_w); > in_w for a horizontally padded buffer */
 } ay2_conv_desc;
 
 typedef struct ay2_conv_plan ay2_conv_plan;
@@ -94,8 +98,10 @@ int ay2_conv_reference_simt(const ay2_conv_desc* desc, const void* in, const voi
  * ---------------------------------------------------------------------------------------------- */
 #define AY2_DT_U8 0
 #define AY2_DT_F32 1
+/* out: [batch, h/2, out_row_pixels, 16]; logical pixel x is written at physical column x + out_x_offset
+ * (columns outside are never touched: the caller zero-fills them once; they are the conv's horizontal padding). */
 int ay2_space_to_depth(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float scale,
-                       void* out, void* stream);
+                       void* out, int32_t out_row_pixels, int32_t out_x_offset, void* stream);
 
 /* SPPF / SPP pooling: x1 = in slice; writes maxpool windows k1,k2,k3 (stride 1, same padding) into three
  * channel slices. Replaces kindle.modules.poolings.SPPF / SPP (yolov5s.yaml:33, yolov5_v5.yaml:32). */
@@ -141,6 +147,49 @@ size_t ay2_nms_workspace_bytes(const ay2_nms_params* p);
  * overflow_flag: optional device int32, set to 1 if some image had more than max_candidates candidates. */
 int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
                     size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag, void* stream);
+
+/* Fused head: the same NMS fed straight from the bf16 YOLOHead logits (NHWC [B, ny, nx, cstride], channel = a*no + o)
+ * of every pyramid level. Candidate scores and boxes are decoded on the fly with the arithmetic of ay2_head_decode,
+ * so the result is bit-identical to ay2_head_decode followed by ay2_nms_batched, without materialising the
+ * (B, sum na*ny*nx, no) tensor. params.n must equal sum_l na*ny_l*nx_l (row order = the reference's cat order). */
+#define AY2_NMS_MAX_LEVELS 5
+#define AY2_NMS_MAX_ANCHORS 8
+typedef struct ay2_head_levels {
+  int32_t nl, na;
+  const void* logits[AY2_NMS_MAX_LEVELS];
+  int32_t ny[AY2_NMS_MAX_LEVELS], nx[AY2_NMS_MAX_LEVELS], cstride[AY2_NMS_MAX_LEVELS];
+  float stride_px[AY2_NMS_MAX_LEVELS];
+  float anchor_px[AY2_NMS_MAX_LEVELS][AY2_NMS_MAX_ANCHORS][2]; /* YOLOHead.anchor_grid */
+} ay2_head_levels;
+int ay2_nms_from_logits(const ay2_head_levels* levels, const ay2_nms_params* p, const uint8_t* class_mask,
+                        void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
+                        int32_t* overflow_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detection loss forward + analytic backward: replaces scripts/loss/losses.py:168-391 (ComputeLoss.__call__,
+ * build_targets) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU) for the default configuration
+ * (fl_gamma = 0, gr = 1, autobalance off).
+ *   preds[i]  : fp32 (bs, na, ny_i, nx_i, 5+nc) logits, contiguous        (losses.py:245)
+ *   grads[i]  : same shape, ZERO-INITIALISED by the caller, receives d(loss*bs)/d(preds[i]) * (*gscale);
+ *               pass grads = NULL for a forward-only evaluation
+ *   targets   : fp32 (nt, 6) [img, cls, x, y, w, h] normalised             (scripts/data_loader/data_loader.py:888-909)
+ *   anchors   : fp32 (nl, na, 2) in grid units (YOLOHead.anchors)
+ *   gscale    : optional device scalar multiplied into every gradient (autograd grad_output), NULL = 1
+ *   out5      : device fp32 [loss*bs, lbox, lobj, lcls, loss]               (losses.py:294-300)
+ * ---------------------------------------------------------------------------------------------- */
+#define AY2_LOSS_MAX_LEVELS 5
+typedef struct ay2_loss_params {
+  int32_t nl, na, nc, bs, nt;
+  int32_t ny[AY2_LOSS_MAX_LEVELS], nx[AY2_LOSS_MAX_LEVELS];
+  float balance[AY2_LOSS_MAX_LEVELS]; /* losses.py:204-206 */
+  float anchor_t, box, obj, cls;      /* hyp gains (res/configs/cfg/train_config.yaml:29-54) */
+  float cls_pw, obj_pw;               /* BCE pos_weight */
+  float cp, cn;                       /* smooth_BCE targets (losses.py:16-27) */
+} ay2_loss_params;
+size_t ay2_yolo_loss_workspace_bytes(const ay2_loss_params* p);
+int ay2_yolo_loss(const ay2_loss_params* p, const float* const* preds, float* const* grads, const float* targets,
+                  const float* anchors, const float* gscale, void* workspace, size_t workspace_bytes, float* out5,
+                  void* stream);
 
 #ifdef __cplusplus
 }

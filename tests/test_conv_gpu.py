@@ -108,3 +108,33 @@ def test_conv_inplace_residual():
     err = (buf[..., :C_].float() - ref).abs()
     assert float((err - (2.0 ** -7 * ref.abs() + 2e-2)).max()) <= 0
     assert torch.equal(buf[..., C_:], before[..., C_:])
+
+
+def test_conv_window_mode_packed_stem():
+    """16-channel 3x3 conv run as 3x1 taps over overlapping 4-pixel windows (in_pix_stride 16 < cin 64) of a
+    horizontally padded buffer == plain 3x3 conv of the 16-channel tensor."""
+    from ayolov2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    B, H, W, Cout = 2, 32, 48, 32
+    Wp = W + 8
+    buf = torch.zeros((B, H, Wp, 16), device="cuda", dtype=torch.bfloat16)
+    x = torch.randn((B, H, W, 16), device="cuda", generator=g).to(torch.bfloat16)
+    buf[:, :, 1:W + 1] = x
+    w = torch.randn((Cout, 16, 3, 3), device="cuda", generator=g) * 0.1
+    ww = torch.zeros((Cout, 64, 3, 1), device="cuda")
+    for kw in range(3):
+        ww[:, kw * 16:(kw + 1) * 16, :, 0] = w[:, :, :, kw]
+    wp, bp = ops.pack_conv_weight(ww, None)
+    y = ops.new_act(B, H, W, Cout)
+    plan = ops.ConvPlan(ops.ActView(buf, 0, 16), y, wp, bp, 3, 1, 1, 1, 1, pad_w=0, window=(64, W, 16, Wp))
+    plan.run()
+    torch.cuda.synchronize()
+    got = y.tensor().float().clone()
+    wr = w.to(torch.bfloat16).float()
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), wr, None, padding=1)).permute(0, 2, 3, 1)
+    err = (got - ref).abs()
+    assert float((err - (2.0 ** -7 * ref.abs() + 2e-2)).max()) <= 0, float(err.max())
+    plan.run_reference_simt()
+    torch.cuda.synchronize()
+    assert float((y.tensor().float() - got).abs().max()) < 3e-2

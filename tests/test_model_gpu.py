@@ -73,3 +73,27 @@ def test_fuse_invariance():
     assert n0 - n1 == sum(m.num_features for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d))
     b = fused(x)[0]
     assert torch.allclose(a, b, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("multi_label", [False, True])
+def test_fused_head_nms_equals_dense_path(multi_label):
+    """Detector's fused head (NMS straight from the bf16 logits, ay2_nms_from_logits) must select exactly what
+    ay2_head_decode + ay2_nms_batched select: same arithmetic, no dense (B, 25200, 85) tensor."""
+    from ayolov2_b200 import synth
+    from ayolov2_b200.detector import Detector
+
+    model = synth.build_model("yolov5s", seed=2).cuda()
+    B, H, W = 3, 320, 320
+    img = torch.randint(0, 256, (B, 3, H, W), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
+    with torch.no_grad():
+        _, raw = model(img.cuda().float() / 255.0)
+    synth.calibrate_head(model, raw, cand_frac=0.1)
+    model.invalidate_engine()
+    kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=multi_label, in_dtype=torch.uint8)
+    fused = Detector(model, B, H, W, **kw)
+    dense = Detector(model, B, H, W, dense_pred=True, **kw)
+    a = fused.detect(img.pin_memory())
+    b = dense.detect(img.pin_memory())
+    assert sum(x.shape[0] for x in a) > 50, "calibration should produce detections"
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and torch.equal(x, y)

@@ -1,0 +1,32 @@
+"""Runs N eager (non-graph) steps of the bs64 yolov5s detector for ncu: every kernel is a plain launch."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from ayolov2_b200 import synth  # noqa: E402
+from ayolov2_b200.detector import Detector  # noqa: E402
+from ayolov2_b200.nms import nms_device  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+torch.manual_seed(0)
+model = synth.build_model("yolov5s", seed=0).cuda()
+img = torch.randint(0, 256, (batch, 3, 640, 640), dtype=torch.uint8, device="cuda")
+with torch.no_grad():
+    _, raw = model(torch.randint(0, 256, (4, 3, 640, 640), dtype=torch.uint8, device="cuda").float() / 255.0)
+synth.calibrate_head(model, raw)
+model.invalidate_engine()
+det = Detector(model, batch, 640, 640, in_dtype=torch.uint8)
+eng = det.engine
+eng._img = img
+torch.cuda.synchronize()
+print("PROFILE_BEGIN", flush=True)
+for _ in range(steps):
+    for s in eng.b.steps:
+        s()
+    nms_device(eng.pred, det.conf_thres, det.iou_thres, workspace=det.nms_ws)
+torch.cuda.synchronize()
+print("PROFILE_END launches/step", len(eng.b.steps) + 2, "candidates", int((eng.pred[..., 4] > 0.25).sum()), "dets", int(det.nms_ws.count.sum()))
