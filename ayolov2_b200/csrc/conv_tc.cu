@@ -247,15 +247,19 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c0 + g * 8]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c0 + g * 8 + 4]);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(v[g * 8 + i]) + bias_s[c0 + g * 8 + i];
+            float x = __uint_as_float(v[g * 8 + i]) + bb[i];
             if (p.act == AY2_ACT_SILU) x = silu_f(x);
             f[i] = x;
           }
-          uint4* dst = reinterpret_cast<uint4*>(slab + swizzled_offset<Cfg::SWO>(et, chunk0 + g));
+          const uint32_t dst = smem_u32(slab) + swizzled_offset<Cfg::SWO>(et, chunk0 + g);
           if (p.has_res) {
-            const uint4 rv = *dst;
+            uint4 rv;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(dst));
             const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -264,12 +268,9 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
               f[2 * i + 1] += rf.y;
             }
           }
-          uint4 o;
-          o.x = pack_bf16x2(f[0], f[1]);
-          o.y = pack_bf16x2(f[2], f[3]);
-          o.z = pack_bf16x2(f[4], f[5]);
-          o.w = pack_bf16x2(f[6], f[7]);
-          *dst = o;
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(f[0], f[1])),
+                       "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+                       : "memory");
         }
       }
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
@@ -378,6 +379,7 @@ struct ay2_conv_plan {
   ConvKernelParams kp;
   ay2_conv_desc desc;
   int block_n, ck;
+  int ctas_per_sm;
   int grid;
   size_t smem;
   void (*kernel)(const ConvKernelParams);
@@ -394,6 +396,7 @@ template <int BN, int CK>
 static void bind_kernel(ay2_conv_plan* pl) {
   pl->kernel = conv_tc_kernel<BN, CK>;
   pl->smem = ConvCfg<BN, CK>::SMEM_BYTES;
+  pl->ctas_per_sm = ConvCfg<BN, CK>::CTAS_PER_SM;
 }
 
 static int pick_box(int H, int W, int* bh, int* bw) {
@@ -525,8 +528,10 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int total_tiles = kp.num_m_tiles * kp.num_n_tiles;
-  pl->grid = total_tiles < sms ? total_tiles : sms;
+  const int resident = sms * pl->ctas_per_sm;
+  pl->grid = total_tiles < resident ? total_tiles : resident;
   *plan_out = pl;
   return AY2_OK;
 }

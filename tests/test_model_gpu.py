@@ -97,3 +97,20 @@ def test_fused_head_nms_equals_dense_path(multi_label):
     assert sum(x.shape[0] for x in a) > 50, "calibration should produce detections"
     for x, y in zip(a, b):
         assert x.shape == y.shape and torch.equal(x, y)
+
+
+def test_tucker_decomposed_forward_matches_oracle():
+    """BASELINE.json configs[3]: Tucker-2 decomposed yolov5s (1x1 -> kxk -> 1x1 chains, decomposition.py:363-424) on the
+    CUDA engine vs the nn.Sequential oracle; ranks here are odd sizes to exercise the zero-padding to 16."""
+    from ayolov2_b200 import synth, tucker
+    from oracle import yolo_oracle
+
+    model = synth.build_model("yolov5s", seed=4)
+    names = tucker.decompose_model_fixed(model, ratio=0.45)
+    assert len(names) >= 15
+    x = torch.rand((2, 3, 256, 256), generator=torch.Generator().manual_seed(1))
+    want_pred, want_raw = yolo_oracle.forward(model, x)
+    got_pred, got_raw = model.cuda()(x.cuda())
+    torch.cuda.synchronize()
+    for g, w in zip(got_raw, want_raw):
+        assert _norm_err(g, w) < 3e-2, _norm_err(g, w)
