@@ -55,6 +55,12 @@ struct ConvCfg {
   // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
   // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
   static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
+  // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes; the 256-column tile (1 CTA/SM) uses two groups,
+  // each draining half of the columns, so that every scheduler has two epilogue warps to interleave.
+  static constexpr int EPI_GROUPS = BLOCK_N == 256 ? 2 : 1;
+  static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
+  static constexpr int THREADS = 128 + EPI_THREADS;
+  static constexpr int COLS_PER_GROUP = BLOCK_N / EPI_GROUPS;
   static constexpr int SMEM_BUDGET = kSmemPerSm / CTAS_PER_SM - 1024;  // 1 KB per CTA is reserved by the system
   static constexpr int NSTAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - TAIL_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGES = NSTAGES_RAW > 8 ? 8 : NSTAGES_RAW;
@@ -69,7 +75,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <int BLOCK_N, int CK>
-__global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N, CK>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle patterns repeat every 1024 B and UMMA descriptors assume base_offset 0
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
     }
     mbar_init(res_full, 1);
     fence_barrier_init();
@@ -200,8 +206,10 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
     }
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
-    const int et = threadIdx.x - 128;  // 0..127 == accumulator row == TMEM lane
-    const int ewarp = warp - 4;        // == warp % 4 -> TMEM lane quadrant
+    const int eall = threadIdx.x - 128;  // 0 .. EPI_THREADS-1
+    const int et = eall & 127;           // accumulator row == TMEM lane
+    const int egrp = eall >> 7;          // which column range of the tile this warp group drains
+    const int ewarp = warp & 3;          // TMEM lane quadrant a warp may read == warp id % 4
     const int box_rows = p.BH * p.BW;
     int it = 0;
     uint32_t res_phase = 0;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
       const int m = tile / p.num_n_tiles;
       const int n0 = (tile - m * p.num_n_tiles) * BLOCK_N;
 
-      if (et == 0) {
+      if (eall == 0) {
         tma_store_wait_read<0>();  // previous tile's TMA stores have finished reading the staging buffer
         if (p.has_res) {
           mbar_expect_tx(res_full, Cfg::STAGING_BYTES);
@@ -228,8 +236,8 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
           }
         }
       }
-      for (int i = et; i < BLOCK_N; i += 128) bias_s[i] = p.bias[n0 + i];
-      named_bar_sync(1, 128);
+      for (int i = eall; i < BLOCK_N; i += Cfg::EPI_THREADS) bias_s[i] = p.bias[n0 + i];
+      named_bar_sync(1, Cfg::EPI_THREADS);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       if (p.has_res) {
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = egrp * Cfg::COLS_PER_GROUP; c0 < (egrp + 1) * Cfg::COLS_PER_GROUP; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
@@ -278,8 +286,8 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
       mbar_arrive(&tmem_empty[acc]);
       // staging complete -> TMA store
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (et == 0) {
+      named_bar_sync(1, Cfg::EPI_THREADS);
+      if (eall == 0) {
         for (int j = 0; j < p.NB; ++j) {
           const int q = m * p.NB + j;
           const int b = q / p.boxes_per_img;
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(256, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_t
         tma_store_commit();
       }
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (eall == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
@@ -331,6 +339,12 @@ static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
 // NHWC bf16 activation view [C][W][H][B] with explicit element strides; box [boxc][bw][bh][1].
 static int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH,
                           int64_t sB, int boxc, int bw, int bh) {
+  // L2 promotion: fetch 256 B only when a pixel's channels are one dense run of >= 256 B that this conv consumes
+  // entirely; a channel slice of a wider concat buffer would otherwise drag its neighbour's bytes through HBM.
+  const bool dense = (int64_t)C == sW && C * 2 >= 256;
+  const CUtensorMapL2promotion promo = dense ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                             : (boxc * 2 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -341,8 +355,7 @@ static int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H
   cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(boxc * 2), promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d box=%d,%d,%d strides=%lld,%lld,%lld) -> %d", C, W,
               H, B, boxc, bw, bh, (long long)sW, (long long)sH, (long long)sB, (int)r);
@@ -379,7 +392,7 @@ struct ay2_conv_plan {
   ConvKernelParams kp;
   ay2_conv_desc desc;
   int block_n, ck;
-  int ctas_per_sm;
+  int ctas_per_sm, threads;
   int grid;
   size_t smem;
   void (*kernel)(const ConvKernelParams);
@@ -397,6 +410,7 @@ static void bind_kernel(ay2_conv_plan* pl) {
   pl->kernel = conv_tc_kernel<BN, CK>;
   pl->smem = ConvCfg<BN, CK>::SMEM_BYTES;
   pl->ctas_per_sm = ConvCfg<BN, CK>::CTAS_PER_SM;
+  pl->threads = ConvCfg<BN, CK>::THREADS;
 }
 
 static int pick_box(int H, int W, int* bh, int* bw) {
@@ -538,7 +552,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
 
 extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
   AY2_REQUIRE(pl, "ay2_conv_plan_run: null plan");
-  pl->kernel<<<pl->grid, 256, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+  pl->kernel<<<pl->grid, pl->threads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;
