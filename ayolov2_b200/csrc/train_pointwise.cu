@@ -1,0 +1,509 @@
+// Training-mode pointwise / reduction kernels over NHWC bf16 activations:
+//   * BatchNorm2d with batch statistics (+ SiLU): statistics, normalise+activate, and the backward pass
+//     (kindle Conv in train mode = conv -> nn.BatchNorm2d(eps 1e-3, momentum 0.03) -> SiLU; reference call site
+//     scripts/train/yolo_trainer.py:322-329: `pred = model(imgs)` ... `scaler.scale(loss).backward()`)
+//   * backward of the data-movement operators (nearest-2x upsample, SPPF/SPP max pools, residual / concat adds)
+//   * gradient layout conversion for the YOLOHead and the fused SGD-nesterov + EMA update
+// Every kernel is HBM-bound: one 16-byte access per 8 channels, fp32 math, per-channel sums reduced in registers,
+// then shared memory, then one double-precision atomic per (block, channel).
+#include "ay2_common.h"
+#include "ay2_ptx.cuh"
+
+namespace ay2 {
+
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __bfloat1622float2(h[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// Reduce `nval` per-thread partials (8 channels each) over the pixel lanes of a block and add them to `dst`
+// (double, [C]) with one atomic per channel per block. smem: [lanes][tpp*8] floats.
+template <int NVAL>
+__device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int tpp, int lanes, int cg, int pl, bool active,
+                                                     float* sm, double* const* dst, int C) {
+  for (int v = 0; v < NVAL; ++v) {
+    __syncthreads();
+    if (active)
+      for (int j = 0; j < 8; ++j) sm[(pl * tpp + cg) * 8 + j] = acc[v][j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < tpp * 8; ch += blockDim.x) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += sm[l * tpp * 8 + ch];
+      if (ch < C) atomicAdd(&dst[v][ch], (double)s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares of z [npix][cstride] (first C channels)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long npix, int C, int cs, double* sum,
+                                double* sumsq) {
+  extern __shared__ float sm[];
+  const int tpp = C >> 3;
+  const int lanes = blockDim.x / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const bool active = pl < lanes;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (active)
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + p * cs + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] += f[j] * f[j];
+      }
+    }
+  double* dst[2] = {sum, sumsq};
+  block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
+}
+
+// mean / invstd from the sums (biased variance for normalisation, unbiased for the running estimate,
+// exactly nn.BatchNorm2d in training mode) + running-statistics update with `momentum`.
+__global__ void bn_finalize_kernel(const double* sum, const double* sumsq, long long n, int C, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* mean, float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sum[c] / (double)n;
+  double var = sumsq[c] / (double)n - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// y = act(gamma * (z - mean) * invstd + beta) (+ residual)
+__global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long npix, int C, int zcs,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                  __nv_bfloat16* __restrict__ y, int ycs, const __nv_bfloat16* __restrict__ res, int rcs) {
+  const int tpp = C >> 3;
+  const long long total = npix * tpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % tpp);
+    const long long p = i / tpp;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
+    float r[8];
+    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * rcs + cg * 8), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      float u = gamma[c] * (f[j] - mean[c]) * invstd[c] + beta[c];
+      if (act == AY2_ACT_SILU) u = u * sigmoid_acc(u);
+      if (res) u += r[j];
+      f[j] = u;
+    }
+    *reinterpret_cast<uint4*>(y + p * ycs + cg * 8) = pack8(f);
+  }
+}
+
+// backward, pass 1: s1[c] = sum dyh, s2[c] = sum dyh * xhat, with dyh = dy * act'(u), u = gamma*xhat + beta
+__global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, const __nv_bfloat16* __restrict__ z,
+                                         int zcs, long long npix, int C, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int act, double* s1, double* s2) {
+  extern __shared__ float sm[];
+  const int tpp = C >> 3;
+  const int lanes = blockDim.x / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const bool active = pl < lanes;
+  float acc[2][8];
+  float mu[8], is[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = 0.f;
+    const int c = cg * 8 + j;
+    mu[j] = active ? mean[c] : 0.f;
+    is[j] = active ? invstd[c] : 0.f;
+    ga[j] = active ? gamma[c] : 0.f;
+    be[j] = active ? beta[c] : 0.f;
+  }
+  if (active)
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+      float g[8], f[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cg * 8), g);
+      unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (f[j] - mu[j]) * is[j];
+        float d = g[j];
+        if (act == AY2_ACT_SILU) {
+          const float u = ga[j] * xh + be[j];
+          const float s = sigmoid_acc(u);
+          d *= s * (1.0f + u * (1.0f - s));
+        }
+        acc[0][j] += d;
+        acc[1][j] += d * xh;
+      }
+    }
+  double* dst[2] = {s1, s2};
+  block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
+}
+
+// backward, pass 2: dz = gamma * invstd * (dyh - s1/N - xhat * s2/N)
+__global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, const __nv_bfloat16* __restrict__ z,
+                                        int zcs, long long npix, int C, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, int act, const double* __restrict__ s1,
+                                        const double* __restrict__ s2, __nv_bfloat16* __restrict__ dz, int zdcs) {
+  const int tpp = C >> 3;
+  const long long total = npix * tpp;
+  const float invn = 1.0f / (float)npix;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % tpp);
+    const long long p = i / tpp;
+    float g[8], f[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cg * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const float xh = (f[j] - mean[c]) * invstd[c];
+      float d = g[j];
+      if (act == AY2_ACT_SILU) {
+        const float u = gamma[c] * xh + beta[c];
+        const float s = sigmoid_acc(u);
+        d *= s * (1.0f + u * (1.0f - s));
+      }
+      g[j] = gamma[c] * invstd[c] * (d - (float)s1[c] * invn - xh * (float)s2[c] * invn);
+    }
+    *reinterpret_cast<uint4*>(dz + p * zdcs + cg * 8) = pack8(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dst (+)= src over a channel slice (residual / concat / fan-out gradient accumulation)
+// ------------------------------------------------------------------------------------------------
+__global__ void add_slices_kernel(const __nv_bfloat16* __restrict__ src, int scs, __nv_bfloat16* __restrict__ dst, int dcs,
+                                  long long npix, int C, int accumulate) {
+  const int tpp = C >> 3;
+  const long long total = npix * tpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % tpp);
+    const long long p = i / tpp;
+    float a[8];
+    unpack8(*reinterpret_cast<const uint4*>(src + p * scs + cg * 8), a);
+    if (accumulate) {
+      float b[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst + p * dcs + cg * 8), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += b[j];
+    }
+    *reinterpret_cast<uint4*>(dst + p * dcs + cg * 8) = pack8(a);
+  }
+}
+
+// nearest-2x upsample backward: dx[y][x] (+)= sum of the 2x2 block of dy
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int B, int H, int W, int C,
+                                      __nv_bfloat16* __restrict__ dx, int xcs, int accumulate) {
+  const int tpp = C >> 3;
+  const long long total = (long long)B * H * W * tpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % tpp);
+    long long p = i / tpp;
+    const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+    for (int dyy = 0; dyy < 2; ++dyy)
+#pragma unroll
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + ((((long long)b * 2 * H + 2 * y + dyy) * 2 * W) + 2 * x + dxx) * dcs + cg * 8), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += g[j];
+      }
+    if (accumulate) {
+      float o[8];
+      unpack8(*reinterpret_cast<const uint4*>(dx + p * xcs + cg * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += o[j];
+    }
+    *reinterpret_cast<uint4*>(dx + p * xcs + cg * 8) = pack8(a);
+  }
+}
+
+// MaxPool2d(k, stride 1, pad k/2) backward in gather form: dx[p] (+)= sum over the windows q that contain p of
+// dy[q] * [argmax(q) == p], with nn.MaxPool2d's tie rule (first maximum in row-major window order).
+// One thread per (pixel, channel); channels-last so neighbouring threads touch neighbouring bf16.
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const __nv_bfloat16* __restrict__ dy, int dcs,
+                                   int B, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, int gcs, int accumulate) {
+  const long long total = (long long)B * H * W * C;
+  const int r = k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int px = (int)(p % W), py = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+    const __nv_bfloat16* xb = x + (long long)b * H * W * xcs + c;
+    float acc = 0.f;
+    for (int qy = max(py - r, 0); qy <= min(py + r, H - 1); ++qy)
+      for (int qx = max(px - r, 0); qx <= min(px + r, W - 1); ++qx) {
+        // argmax of the window centred at (qy, qx)
+        float best = -INFINITY;
+        int by = -1, bx = -1;
+        for (int wy = max(qy - r, 0); wy <= min(qy + r, H - 1); ++wy)
+          for (int wx = max(qx - r, 0); wx <= min(qx + r, W - 1); ++wx) {
+            const float v = __bfloat162float(xb[((long long)wy * W + wx) * xcs]);
+            if (v > best) {
+              best = v;
+              by = wy;
+              bx = wx;
+            }
+          }
+        if (by == py && bx == px) acc += __bfloat162float(dy[(((long long)b * H + qy) * W + qx) * dcs + c]);
+      }
+    __nv_bfloat16* o = dx + p * gcs + c;
+    if (accumulate) acc += __bfloat162float(*o);
+    *o = __float2bfloat16_rn(acc);
+  }
+}
+
+// (bs, na, ny, nx, no) fp32 <-> NHWC bf16 [B, ny, nx, cstride] (channel = a*no + o): YOLOHead train layout
+__global__ void head_grad_to_nhwc_kernel(const float* __restrict__ g, int B, int na, int ny, int nx, int no,
+                                         __nv_bfloat16* __restrict__ out, int cs) {
+  const long long total = (long long)B * ny * nx * cs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % cs);
+    const long long pix = i / cs;
+    float v = 0.f;
+    if (ch < na * no) {
+      const int a = ch / no, o = ch - a * no;
+      const int x = (int)(pix % nx), y = (int)((pix / nx) % ny), b = (int)(pix / ((long long)nx * ny));
+      v = g[((((long long)b * na + a) * ny + y) * nx + x) * no + o];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void head_logits_to_train_kernel(const __nv_bfloat16* __restrict__ logits, int cs, int B, int na, int ny, int nx,
+                                            int no, float* __restrict__ out) {
+  const long long total = (long long)B * na * ny * nx * no;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % no);
+    long long r = i / no;
+    const int x = (int)(r % nx);
+    r /= nx;
+    const int y = (int)(r % ny);
+    r /= ny;
+    const int a = (int)(r % na);
+    const int b = (int)(r / na);
+    out[i] = __bfloat162float(logits[(((long long)b * ny + y) * nx + x) * cs + a * no + o]);
+  }
+}
+
+// per-channel sum over pixels of a bf16 NHWC tensor (bias gradient of the head convs)
+__global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ g, long long npix, int C, int cs, double* sum) {
+  extern __shared__ float sm[];
+  const int tpp = C >> 3;
+  const int lanes = blockDim.x / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const bool active = pl < lanes;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  if (active)
+    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(g + p * cs + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[0][j] += f[j];
+    }
+  double* dst[1] = {sum};
+  block_channel_reduce<1>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
+}
+
+// Fused SGD (nesterov momentum, weight decay) + EMA over one flat fp32 parameter range
+// (scripts/train/yolo_trainer.py:332-338 optimizer step + ema.update, scripts/utils/torch_utils.py:405-416).
+__global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, float* ema,
+                               long long n, float lr, float momentum, float wd, int nesterov, float ema_decay,
+                               const float* __restrict__ inv_scale) {
+  const float is = inv_scale ? *inv_scale : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = g[i] * is + wd * p[i];
+    const float b = momentum * mom[i] + d;  // torch.optim.SGD: buf = momentum*buf + d_p (dampening 0)
+    mom[i] = b;
+    d = nesterov ? d + momentum * b : b;
+    const float w = p[i] - lr * d;
+    p[i] = w;
+    if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * w;
+  }
+}
+
+static int ew_grid(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace ay2
+
+using namespace ay2;
+
+#define AY2_ST static_cast<cudaStream_t>(stream)
+#define AY2_BF(p) static_cast<__nv_bfloat16*>(p)
+#define AY2_CBF(p) static_cast<const __nv_bfloat16*>(p)
+
+static int red_cfg(int c, int* threads, int* lanes, size_t* smem) {
+  const int tpp = c / 8;
+  if (c % 8 != 0 || tpp < 1 || tpp > 256) return -1;
+  *threads = 256;
+  *lanes = 256 / tpp;
+  *smem = (size_t)(*lanes) * tpp * 8 * sizeof(float);
+  return 0;
+}
+
+extern "C" int ay2_bn_stats(const void* z, int64_t npix, int32_t c, int32_t cstride, double* sum, double* sumsq, void* stream) {
+  AY2_REQUIRE(z && sum && sumsq, "ay2_bn_stats: null pointer");
+  int threads, lanes;
+  size_t smem;
+  AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_stats: channels=%d unsupported", c);
+  long long blocks = (npix + lanes - 1) / lanes;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_stats_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(z), npix, c, cstride, sum, sumsq);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_bn_finalize(const double* sum, const double* sumsq, int64_t n, int32_t c, float eps, float momentum,
+                               float* running_mean, float* running_var, float* mean, float* invstd, void* stream) {
+  AY2_REQUIRE(sum && sumsq && mean && invstd, "ay2_bn_finalize: null pointer");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, AY2_ST>>>(sum, sumsq, n, c, eps, momentum, running_mean, running_var, mean,
+                                                          invstd);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_cstride, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, int32_t act, void* y,
+                              int32_t y_cstride, const void* residual, int32_t res_cstride, void* stream) {
+  AY2_REQUIRE(z && y && mean && invstd && gamma && beta, "ay2_bn_act_fwd: null pointer");
+  AY2_REQUIRE(c % 8 == 0, "ay2_bn_act_fwd: channels must be a multiple of 8");
+  bn_act_fwd_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, AY2_ST>>>(AY2_CBF(z), npix, c, z_cstride, mean, invstd, gamma,
+                                                                     beta, act, AY2_BF(y), y_cstride, AY2_CBF(residual),
+                                                                     res_cstride);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
+                              double* s1, double* s2, void* dz, int32_t dz_cstride, void* stream) {
+  AY2_REQUIRE(dy && z && mean && invstd && gamma && beta && s1 && s2 && dz, "ay2_bn_act_bwd: null pointer");
+  int threads, lanes;
+  size_t smem;
+  AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_bwd: channels=%d unsupported", c);
+  AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
+  AY2_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * c, AY2_ST));
+  long long blocks = (npix + lanes - 1) / lanes;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_act_bwd_reduce_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
+                                                                  mean, invstd, gamma, beta, act, s1, s2);
+  AY2_CHECK_LAUNCH();
+  bn_act_bwd_apply_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride,
+                                                                           npix, c, mean, invstd, gamma, beta, act, s1, s2,
+                                                                           AY2_BF(dz), dz_cstride);
+  AY2_CHECK_LAUNCH();
+  count_launch(2);
+  return AY2_OK;
+}
+
+extern "C" int ay2_add_slices(const void* src, int32_t src_cstride, void* dst, int32_t dst_cstride, int64_t npix, int32_t c,
+                              int32_t accumulate, void* stream) {
+  AY2_REQUIRE(src && dst && c % 8 == 0, "ay2_add_slices: bad arguments");
+  add_slices_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, AY2_ST>>>(AY2_CBF(src), src_cstride, AY2_BF(dst), dst_cstride,
+                                                                     npix, c, accumulate);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_upsample2x_bwd(const void* dy, int32_t dy_cstride, int32_t batch, int32_t h, int32_t w, int32_t c,
+                                  void* dx, int32_t dx_cstride, int32_t accumulate, void* stream) {
+  AY2_REQUIRE(dy && dx && c % 8 == 0, "ay2_upsample2x_bwd: bad arguments");
+  upsample2x_bwd_kernel<<<ew_grid((long long)batch * h * w * (c / 8), 256), 256, 0, AY2_ST>>>(
+      AY2_CBF(dy), dy_cstride, batch, h, w, c, AY2_BF(dx), dx_cstride, accumulate);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_maxpool_bwd(const void* x, int32_t x_cstride, const void* dy, int32_t dy_cstride, int32_t batch, int32_t h,
+                               int32_t w, int32_t c, int32_t k, void* dx, int32_t dx_cstride, int32_t accumulate,
+                               void* stream) {
+  AY2_REQUIRE(x && dy && dx && k % 2 == 1, "ay2_maxpool_bwd: bad arguments");
+  maxpool_bwd_kernel<<<ew_grid((long long)batch * h * w * c, 256), 256, 0, AY2_ST>>>(
+      AY2_CBF(x), x_cstride, AY2_CBF(dy), dy_cstride, batch, h, w, c, k, AY2_BF(dx), dx_cstride, accumulate);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_head_grad_to_nhwc(const float* grad, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t no,
+                                     void* out, int32_t out_cstride, void* stream) {
+  AY2_REQUIRE(grad && out && na * no <= out_cstride, "ay2_head_grad_to_nhwc: bad arguments");
+  head_grad_to_nhwc_kernel<<<ew_grid((long long)batch * ny * nx * out_cstride, 256), 256, 0, AY2_ST>>>(
+      grad, batch, na, ny, nx, no, AY2_BF(out), out_cstride);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_head_logits_to_train(const void* logits, int32_t cstride, int32_t batch, int32_t na, int32_t ny,
+                                        int32_t nx, int32_t no, float* out, void* stream) {
+  AY2_REQUIRE(logits && out && na * no <= cstride, "ay2_head_logits_to_train: bad arguments");
+  head_logits_to_train_kernel<<<ew_grid((long long)batch * na * ny * nx * no, 256), 256, 0, AY2_ST>>>(
+      AY2_CBF(logits), cstride, batch, na, ny, nx, no, out);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t cstride, double* sum, void* stream) {
+  AY2_REQUIRE(g && sum, "ay2_channel_sum: null pointer");
+  int threads, lanes;
+  size_t smem;
+  AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_channel_sum: channels=%d unsupported", c);
+  long long blocks = (npix + lanes - 1) / lanes;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  channel_sum_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(g), npix, c, cstride, sum);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_sgd_ema_step(float* param, const float* grad, float* momentum_buf, float* ema, int64_t n, float lr,
+                                float momentum, float weight_decay, int32_t nesterov, float ema_decay,
+                                const float* inv_scale, void* stream) {
+  AY2_REQUIRE(param && grad && momentum_buf && n >= 0, "ay2_sgd_ema_step: bad arguments");
+  if (n == 0) return AY2_OK;
+  sgd_ema_kernel<<<ew_grid(n, 256), 256, 0, AY2_ST>>>(param, grad, momentum_buf, ema, n, lr, momentum, weight_decay,
+                                                      nesterov, ema_decay, inv_scale);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}

@@ -223,3 +223,99 @@ def make_head_levels(logits: Sequence[ActView], na: int, strides: Sequence[float
             hl.anchor_px[i][a][0] = float(anchors_px[i][a][0])
             hl.anchor_px[i][a][1] = float(anchors_px[i][a][1])
     return hl
+
+
+# -------------------------------------------------------------------------------------------------
+# training-step wrappers (include/ay2.h "Training step pieces")
+# -------------------------------------------------------------------------------------------------
+def _npix(v: ActView) -> int:
+    return v.B * v.H * v.W
+
+
+def bn_batch_stats(z: ActView, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
+                   running_var: Optional[torch.Tensor], scratch: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor) -> None:
+    """scratch: double[2*c] (zeroed here); mean / invstd: fp32 [c] outputs; running stats updated in place."""
+    lib = _lib.load()
+    c = z.c
+    scratch.zero_()
+    st = _lib.current_stream_ptr()
+    _lib.check(lib.ay2_bn_stats(z.ptr(), _npix(z), c, z.cstride, scratch.data_ptr(), scratch.data_ptr() + 8 * c, st), "ay2_bn_stats")
+    _lib.check(lib.ay2_bn_finalize(scratch.data_ptr(), scratch.data_ptr() + 8 * c, _npix(z), c, float(eps), float(momentum),
+                                   _lib.ptr(running_mean), _lib.ptr(running_var), mean.data_ptr(), invstd.data_ptr(), st),
+               "ay2_bn_finalize")
+
+
+def bn_act_fwd(z: ActView, mean, invstd, gamma, beta, act: int, y: ActView, residual: Optional[ActView] = None) -> None:
+    _lib.check(_lib.load().ay2_bn_act_fwd(z.ptr(), _npix(z), z.c, z.cstride, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                          beta.data_ptr(), act, y.ptr(), y.cstride,
+                                          residual.ptr() if residual is not None else None,
+                                          residual.cstride if residual is not None else 0, _lib.current_stream_ptr()),
+               "ay2_bn_act_fwd")
+
+
+def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sums: torch.Tensor, dz: ActView) -> None:
+    """sums: double[2*c]; afterwards sums[:c] = d beta, sums[c:] = d gamma."""
+    c = z.c
+    _lib.check(_lib.load().ay2_bn_act_bwd(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(), invstd.data_ptr(),
+                                          gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(), sums.data_ptr() + 8 * c,
+                                          dz.ptr(), dz.cstride, _lib.current_stream_ptr()), "ay2_bn_act_bwd")
+
+
+def conv_wgrad(x: ActView, dz: ActView, dw: torch.Tensor, kh: int, kw: int, stride: int, pad: int,
+               in_row_pixels: int = 0, x_ptr: Optional[int] = None, in_w: Optional[int] = None) -> None:
+    """dw: fp32 [cout, kh*kw*cin] accumulated (+=)."""
+    d = ConvDesc()
+    d.batch = x.B
+    d.in_h, d.in_w, d.cin, d.in_cstride = x.H, (in_w if in_w is not None else x.W), x.c, x.cstride
+    d.out_h, d.out_w, d.cout, d.out_cstride = dz.H, dz.W, dz.c, dz.cstride
+    d.kh, d.kw, d.stride, d.pad = kh, kw, stride, pad
+    d.pad_w = -1
+    d.in_row_pixels = in_row_pixels
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == dz.c * kh * kw * x.c
+    _lib.check(_lib.load().ay2_conv_wgrad(C.byref(d), x_ptr if x_ptr is not None else x.ptr(), dz.ptr(), dw.data_ptr(),
+                                          _lib.current_stream_ptr()), "ay2_conv_wgrad")
+
+
+def add_slices(src: ActView, dst: ActView, accumulate: bool) -> None:
+    assert (src.B, src.H, src.W, src.c) == (dst.B, dst.H, dst.W, dst.c)
+    _lib.check(_lib.load().ay2_add_slices(src.ptr(), src.cstride, dst.ptr(), dst.cstride, _npix(src), src.c, int(accumulate),
+                                          _lib.current_stream_ptr()), "ay2_add_slices")
+
+
+def upsample2x_bwd(dy: ActView, dx: ActView, accumulate: bool) -> None:
+    assert (dy.H, dy.W, dy.c) == (2 * dx.H, 2 * dx.W, dx.c)
+    _lib.check(_lib.load().ay2_upsample2x_bwd(dy.ptr(), dy.cstride, dx.B, dx.H, dx.W, dx.c, dx.ptr(), dx.cstride,
+                                              int(accumulate), _lib.current_stream_ptr()), "ay2_upsample2x_bwd")
+
+
+def maxpool_bwd(x: ActView, dy: ActView, k: int, dx: ActView, accumulate: bool) -> None:
+    _lib.check(_lib.load().ay2_maxpool_bwd(x.ptr(), x.cstride, dy.ptr(), dy.cstride, x.B, x.H, x.W, x.c, k, dx.ptr(), dx.cstride,
+                                           int(accumulate), _lib.current_stream_ptr()), "ay2_maxpool_bwd")
+
+
+def head_grad_to_nhwc(grad: torch.Tensor, out: ActView) -> None:
+    B, na, ny, nx, no = grad.shape
+    assert grad.dtype == torch.float32 and grad.is_contiguous() and out.c0 == 0
+    _lib.check(_lib.load().ay2_head_grad_to_nhwc(grad.data_ptr(), B, na, ny, nx, no, out.ptr(), out.cstride,
+                                                 _lib.current_stream_ptr()), "ay2_head_grad_to_nhwc")
+
+
+def head_logits_to_train(logits: ActView, na: int, no: int, out: torch.Tensor) -> None:
+    assert out.dtype == torch.float32 and out.is_contiguous() and logits.c0 == 0
+    _lib.check(_lib.load().ay2_head_logits_to_train(logits.ptr(), logits.cstride, logits.B, na, logits.H, logits.W, no,
+                                                    out.data_ptr(), _lib.current_stream_ptr()), "ay2_head_logits_to_train")
+
+
+def channel_sum(g: ActView, out: torch.Tensor) -> None:
+    """out: double[c], accumulated."""
+    _lib.check(_lib.load().ay2_channel_sum(g.ptr(), _npix(g), g.c, g.cstride, out.data_ptr(), _lib.current_stream_ptr()),
+               "ay2_channel_sum")
+
+
+def sgd_ema_step(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema: Optional[torch.Tensor], lr: float,
+                 momentum: float, weight_decay: float, nesterov: bool, ema_decay: float,
+                 inv_scale: Optional[torch.Tensor] = None) -> None:
+    assert param.dtype == grad.dtype == mom.dtype == torch.float32 and param.is_contiguous() and grad.is_contiguous()
+    _lib.check(_lib.load().ay2_sgd_ema_step(param.data_ptr(), grad.data_ptr(), mom.data_ptr(), _lib.ptr(ema), param.numel(),
+                                            float(lr), float(momentum), float(weight_decay), int(nesterov), float(ema_decay),
+                                            _lib.ptr(inv_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step")

@@ -191,6 +191,49 @@ int ay2_yolo_loss(const ay2_loss_params* p, const float* const* preds, float* co
                   const float* anchors, const float* gscale, void* workspace, size_t workspace_bytes, float* out5,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step pieces (scripts/train/yolo_trainer.py:289-358: forward under autocast, ComputeLoss, backward, SGD step,
+ * EMA). In train mode a kindle Conv is conv -> BatchNorm2d(batch statistics, eps 1e-3, momentum 0.03) -> SiLU: the conv
+ * runs through ay2_conv_plan_* with act = NONE and zero bias (raw output z), then the kernels below.
+ * All activation tensors are NHWC bf16 channel slices (pointer to the first channel + channel stride).
+ * ---------------------------------------------------------------------------------------------- */
+/* per-channel sum / sum of squares of z over npix pixels, ACCUMULATED into double[c] buffers (zero them first) */
+int ay2_bn_stats(const void* z, int64_t npix, int32_t c, int32_t cstride, double* sum, double* sumsq, void* stream);
+/* mean / invstd (biased variance) + running-statistics update (unbiased variance), nn.BatchNorm2d semantics */
+int ay2_bn_finalize(const double* sum, const double* sumsq, int64_t n, int32_t c, float eps, float momentum,
+                    float* running_mean, float* running_var, float* mean, float* invstd, void* stream);
+/* y = act(gamma * (z - mean) * invstd + beta) (+ residual) */
+int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_cstride, const float* mean, const float* invstd,
+                   const float* gamma, const float* beta, int32_t act, void* y, int32_t y_cstride, const void* residual,
+                   int32_t res_cstride, void* stream);
+/* backward of the above w.r.t. z: s1 = sum dy*act'(u) (= d beta), s2 = sum dy*act'(u)*xhat (= d gamma) as double[c];
+ * dz = gamma*invstd*(dy*act' - s1/N - xhat*s2/N). dz may alias dy. */
+int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                   const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
+                   double* s2, void* dz, int32_t dz_cstride, void* stream);
+/* weight gradient of a conv: dw[cout][kh*kw][cin] (fp32, ACCUMULATED) += dz^T (*) x ; tcgen05, split-K */
+int ay2_conv_wgrad(const ay2_conv_desc* desc, const void* x, const void* dz, float* dw, void* stream);
+/* dst (+)= src over a channel slice: residual / concat / fan-out gradient accumulation */
+int ay2_add_slices(const void* src, int32_t src_cstride, void* dst, int32_t dst_cstride, int64_t npix, int32_t c,
+                   int32_t accumulate, void* stream);
+/* backward of nearest-2x upsample: dx[B,h,w,c] (+)= sum of the 2x2 blocks of dy[B,2h,2w,c] */
+int ay2_upsample2x_bwd(const void* dy, int32_t dy_cstride, int32_t batch, int32_t h, int32_t w, int32_t c, void* dx,
+                       int32_t dx_cstride, int32_t accumulate, void* stream);
+/* backward of MaxPool2d(k, 1, k/2) with nn.MaxPool2d's tie rule; x = the pool's input */
+int ay2_maxpool_bwd(const void* x, int32_t x_cstride, const void* dy, int32_t dy_cstride, int32_t batch, int32_t h, int32_t w,
+                    int32_t c, int32_t k, void* dx, int32_t dx_cstride, int32_t accumulate, void* stream);
+/* YOLOHead train layout: (bs, na, ny, nx, no) fp32 <-> NHWC bf16 [B, ny, nx, cstride] (channel = a*no + o) */
+int ay2_head_grad_to_nhwc(const float* grad, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t no, void* out,
+                          int32_t out_cstride, void* stream);
+int ay2_head_logits_to_train(const void* logits, int32_t cstride, int32_t batch, int32_t na, int32_t ny, int32_t nx,
+                             int32_t no, float* out, void* stream);
+/* per-channel sum over pixels (bias gradients), ACCUMULATED into double[c] */
+int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t cstride, double* sum, void* stream);
+/* fused SGD (nesterov, weight decay) + EMA over one flat fp32 range (yolo_trainer.py:332-338, torch_utils.py:405-416);
+ * inv_scale: optional device scalar multiplied into the gradient (GradScaler unscale), ema may be NULL */
+int ay2_sgd_ema_step(float* param, const float* grad, float* momentum_buf, float* ema, int64_t n, float lr, float momentum,
+                     float weight_decay, int32_t nesterov, float ema_decay, const float* inv_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
