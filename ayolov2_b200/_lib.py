@@ -29,6 +29,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32), ("res_cstride", C.c_int32),
         ("cout_pad", C.c_int32), ("pad_w", C.c_int32),
         ("in_pix_stride", C.c_int32), ("in_row_pixels", C.c_int32),
+        ("out_pix_stride", C.c_int32), ("out_row_pixels", C.c_int32),
     ]
 
 

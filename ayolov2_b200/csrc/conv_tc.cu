@@ -453,8 +453,9 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   AY2_REQUIRE(d->stride == 1 || (d->in_pix_stride <= 0 && d->in_row_pixels <= 0), "custom input strides need stride 1");
   const int exp_oh = (d->in_h + 2 * d->pad - d->kh) / d->stride + 1;
   const int exp_ow = (d->in_w + 2 * pad_w - d->kw) / d->stride + 1;
-  AY2_REQUIRE(exp_oh == d->out_h && exp_ow == d->out_w, "conv output size %dx%d does not match %dx%d", d->out_h,
-              d->out_w, exp_oh, exp_ow);
+  // (sub-grid outputs are the dgrad of a strided conv: asymmetric implicit padding, the caller fixes the size)
+  AY2_REQUIRE(d->out_pix_stride > 0 || (exp_oh == d->out_h && exp_ow == d->out_w),
+              "conv output size %dx%d does not match %dx%d", d->out_h, d->out_w, exp_oh, exp_ow);
   if (d->stride == 2) AY2_REQUIRE(d->in_h % 2 == 0 && d->in_w % 2 == 0, "stride-2 conv needs even input size");
   const int bn = ay2_conv_block_n(d->cout);
   AY2_REQUIRE(d->cout_pad >= d->cout && d->cout_pad % bn == 0, "cout_pad=%d must be a multiple of %d", d->cout_pad, bn);
@@ -507,14 +508,17 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   }
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn);
   const int oc = bn < 64 ? bn : 64;
-  const int64_t os = d->out_cstride;
-  if (rc == AY2_OK)
-    rc = encode_act_map(&kp.tmOut, out, d->cout, d->out_w, d->out_h, d->batch, os, os * d->out_w,
-                        os * d->out_w * d->out_h, oc, bw, bh);
+  // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)
+  const bool sub = d->out_pix_stride > 0;
+  const int64_t ops_ = sub ? d->out_pix_stride : d->out_cstride;
+  const int64_t orow = d->out_row_pixels > 0 ? (int64_t)d->out_row_pixels * ops_ : ops_ * d->out_w;
+  const int64_t oimg = sub ? orow * d->out_h : orow * d->out_h;
+  if (rc == AY2_OK) rc = encode_act_map(&kp.tmOut, out, d->cout, d->out_w, d->out_h, d->batch, ops_, orow, oimg, oc, bw, bh);
   if (rc == AY2_OK && kp.has_res) {
-    const int64_t rs = d->res_cstride;
-    rc = encode_act_map(&kp.tmRes, residual, d->cout, d->out_w, d->out_h, d->batch, rs, rs * d->out_w,
-                        rs * d->out_w * d->out_h, oc, bw, bh);
+    const int64_t rscale = sub ? d->out_pix_stride / d->out_cstride : 1;  // same sub-grid geometry for the residual
+    const int64_t rps = (int64_t)d->res_cstride * rscale;
+    const int64_t rrow = d->out_row_pixels > 0 ? (int64_t)d->out_row_pixels * rps : rps * d->out_w;
+    rc = encode_act_map(&kp.tmRes, residual, d->cout, d->out_w, d->out_h, d->batch, rps, rrow, rrow * d->out_h, oc, bw, bh);
   }
   if (rc != AY2_OK) {
     delete pl;

@@ -423,9 +423,9 @@ def _weights_signature(model: nn.Module) -> int:
 def forward_model(model: nn.Module, x: torch.Tensor):
     """YOLOModel.forward for CUDA inputs (train.py / val.py call `model(imgs)`)."""
     if model.training:
-        raise NotImplementedError(
-            "training-mode forward/backward (BN batch statistics, dgrad/wgrad kernels) is not built yet in this round; "
-            "call model.eval() — inference + NMS is the path implemented on sm_100a")
+        from .train_engine import forward_train
+
+        return forward_train(model, x)
     if x.dim() != 4:
         raise ValueError("expected NCHW input")
     in_dtype = x.dtype

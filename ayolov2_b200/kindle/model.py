@@ -149,15 +149,21 @@ class YOLOModel(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("ayolov2_b200 YOLOModel runs on CUDA (sm_100a) tensors only; there is no CPU fallback "
                                "(the CPU restatement lives in oracle/ and is test infrastructure)")
+        if self.training:
+            from ..train_engine import forward_train
+
+            return forward_train(self, x)
         from ..engine import forward_model
 
         return forward_model(self, x)
 
     def invalidate_engine(self) -> None:
         self._engine_cache.clear()
+        self.__dict__.pop("_train_engine_cache", None)
 
     def _apply(self, fn, *a, **k):  # .to()/.half()/.float()/.cuda() move or recast parameters
         self.__dict__.get("_engine_cache", {}).clear()
+        self.__dict__.pop("_train_engine_cache", None)
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
@@ -166,6 +172,7 @@ class YOLOModel(nn.Module):
 
     def __deepcopy__(self, memo):
         cache = self.__dict__.pop("_engine_cache", {})
+        tcache = self.__dict__.pop("_train_engine_cache", None)
         try:
             cls = self.__class__
             new = cls.__new__(cls)
@@ -175,11 +182,14 @@ class YOLOModel(nn.Module):
             new.__dict__["_engine_cache"] = {}
         finally:
             self.__dict__["_engine_cache"] = cache
+            if tcache is not None:
+                self.__dict__["_train_engine_cache"] = tcache
         return new
 
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_engine_cache"] = {}
+        d.pop("_train_engine_cache", None)
         return d
 
     def __setstate__(self, d):

@@ -89,9 +89,11 @@ class ConvPlan:
 
     def __init__(self, x: ActView, y: ActView, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int,
                  stride: int, pad: int, act: int, residual: Optional[ActView] = None, pad_w: int = -1,
-                 window: Optional[Tuple[int, int, int, int]] = None):
+                 window: Optional[Tuple[int, int, int, int]] = None, out_sub: Optional[Tuple[int, int]] = None):
         """`window` = (cin, in_w, pix_stride, row_pixels): read `x.buf` as overlapping windows of `cin` channels
-        starting at every physical pixel (the packed 16-channel stem); otherwise the input is the ActView `x`."""
+        starting at every physical pixel (the packed 16-channel stem); otherwise the input is the ActView `x`.
+        `out_sub` = (py, px): write (and read the residual from) the (row, column) parity sub-grid of `y` -- the
+        output is then y.H/2 x y.W/2 pixels (data gradient of a stride-2 convolution)."""
         lib = _lib.load()
         cout_pad, ktot = w_packed.shape
         cin = window[0] if window else x.c
@@ -105,15 +107,25 @@ class ConvPlan:
         if window:
             d.cin, d.in_w, d.in_pix_stride, d.in_row_pixels = window
         d.out_h, d.out_w, d.cout, d.out_cstride = y.H, y.W, y.c, y.cstride
+        y_ptr = y.ptr()
+        r_ptr = residual.ptr() if residual is not None else None
+        if out_sub is not None:
+            py, px = out_sub
+            assert y.H % 2 == 0 and y.W % 2 == 0
+            d.out_h, d.out_w = y.H // 2, y.W // 2
+            d.out_pix_stride, d.out_row_pixels = 2 * y.cstride, y.W
+            y_ptr += 2 * (py * y.W + px) * y.cstride
+            if residual is not None:
+                assert (residual.H, residual.W) == (y.H, y.W)
+                r_ptr += 2 * (py * residual.W + px) * residual.cstride
         d.kh, d.kw, d.stride, d.pad, d.act = kh, kw, stride, pad, act
         d.res_cstride = residual.cstride if residual is not None else 0
         d.cout_pad = cout_pad
         self.desc = d
         self.x, self.y, self.w, self.b, self.res = x, y, w_packed, bias, residual
         h = C.c_void_p()
-        _lib.check(lib.ay2_conv_plan_create(C.byref(d), x.ptr(), w_packed.data_ptr(), bias.data_ptr(),
-                                            residual.ptr() if residual is not None else None, y.ptr(), C.byref(h)),
-                   "ay2_conv_plan_create")
+        _lib.check(lib.ay2_conv_plan_create(C.byref(d), x.ptr(), w_packed.data_ptr(), bias.data_ptr(), r_ptr, y_ptr,
+                                            C.byref(h)), "ay2_conv_plan_create")
         self._h = h
         self._lib = lib
         self.flops = float(lib.ay2_conv_plan_flops(h))
@@ -319,3 +331,51 @@ def sgd_ema_step(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema
     _lib.check(_lib.load().ay2_sgd_ema_step(param.data_ptr(), grad.data_ptr(), mom.data_ptr(), _lib.ptr(ema), param.numel(),
                                             float(lr), float(momentum), float(weight_decay), int(nesterov), float(ema_decay),
                                             _lib.ptr(inv_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step")
+
+
+def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):
+    """[(sub-weight OIHW for the dgrad conv (out = cin, in = cout), kh, kw, pad_h, pad_w, out_sub)]."""
+    w = weight.detach().float()
+    cout, cin, kh, kw = w.shape
+    if stride == 1:
+        assert kh == kw
+        return [(w.permute(1, 0, 2, 3).flip(2, 3).contiguous(), kh, kw, kh - 1 - pad, kw - 1 - pad, None)]
+    assert stride == 2
+    specs = []
+    for py in range(2):
+        khs = sorted([k for k in range(kh) if (k - pad - py) % 2 == 0], key=lambda k: (py + pad - k) // 2)
+        offs_y = [(py + pad - k) // 2 for k in khs]
+        for px in range(2):
+            kws = sorted([k for k in range(kw) if (k - pad - px) % 2 == 0], key=lambda k: (px + pad - k) // 2)
+            offs_x = [(px + pad - k) // 2 for k in kws]
+            assert offs_y == list(range(offs_y[0], offs_y[0] + len(khs))) and offs_x == list(range(offs_x[0], offs_x[0] + len(kws)))
+            sub = w[:, :, khs][:, :, :, kws]  # (cout, cin, len(khs), len(kws)), taps ordered by input offset
+            specs.append((sub.permute(1, 0, 2, 3).contiguous(), len(khs), len(kws), -offs_y[0], -offs_x[0], (py, px)))
+    return specs
+
+
+def make_dgrad_weights(weight: torch.Tensor, stride: int, pad: int, dz_channels: int) -> List[torch.Tensor]:
+    """Packed bf16 weights of the dgrad launches, in the order make_dgrad_plans creates its plans."""
+    out = []
+    for wt, *_ in _dgrad_specs(weight, stride, pad):
+        if wt.shape[1] < dz_channels:
+            wt = torch.cat((wt, torch.zeros((wt.shape[0], dz_channels - wt.shape[1]) + tuple(wt.shape[2:]), device=wt.device)), 1)
+        out.append(pack_conv_weight(wt, None)[0])
+    return out
+
+
+def make_dgrad_plans(dz: ActView, dx: ActView, weight: torch.Tensor, stride: int, pad: int, accumulate: bool) -> List[ConvPlan]:
+    """Data gradient of `y = conv(x, weight, stride, pad)` as forward-conv launches of the same tcgen05 kernel:
+       stride 1: dx = conv(dz, flip(W)^T, pad = k-1-p);
+       stride 2: the four (row, column) parity sub-grids of dx are stride-1 convs of dz with the taps of matching
+                 parity (ix = 2*ox + kw - p), written through a strided output view.
+    weight: OIHW fp32 (the forward conv's). accumulate: dx += (fan-out), implemented with the residual input."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert dz.c >= cout and dx.c == cin, (dz.c, cout, dx.c, cin)
+    res = dx if accumulate else None
+    plans: List[ConvPlan] = []
+    packed = make_dgrad_weights(weight, stride, pad, dz.c)
+    for (wt, kh, kw, ph, pw, sub), wp in zip(_dgrad_specs(weight, stride, pad), packed):
+        bp = torch.zeros(wp.shape[0], dtype=torch.float32, device=wp.device)
+        plans.append(ConvPlan(dz, dx, wp, bp, kh, kw, 1, ph, ACT_NONE, residual=res, pad_w=pw, out_sub=sub))
+    return plans

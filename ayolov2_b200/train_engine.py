@@ -1,0 +1,474 @@
+"""Training-mode execution: forward with batch-statistics BatchNorm and the full analytic backward of a
+kindle-style YOLOModel, on the libay2 kernels.
+
+Replaces, for `model.train()`, what scripts/train/yolo_trainer.py:322-329 runs through PyTorch/cuDNN:
+`pred = model(imgs)` (per-layer conv -> BatchNorm2d(batch stats) -> SiLU) and the autograd backward that
+`scaler.scale(loss).backward()` triggers. Per kindle Conv:
+
+  forward   z  = conv(x, W)                        ay2_conv_plan_run (tcgen05 implicit GEMM, raw bf16 output)
+            mu, 1/sigma, running stats             ay2_bn_stats + ay2_bn_finalize
+            y  = SiLU(gamma*(z-mu)/sigma + beta)   ay2_bn_act_fwd (+ shortcut add)
+  backward  dz, dgamma, dbeta                      ay2_bn_act_bwd
+            dW += dz^T (*) x                       ay2_conv_wgrad (tcgen05, MN-major operands, split-K)
+            dx += dz (*) W^T                       the forward kernel again with flipped/transposed weights
+                                                   (stride 2: four parity sub-grids), accumulating via its residual input
+Concat / C3 cat / SPP cat are channel slices of one buffer in both directions; UpSample and the max pools have
+their own backward kernels; the YOLOHead is a 1x1 conv with bias whose gradient arrives as (bs, na, ny, nx, no).
+
+`TrainFunction` exposes this as ONE torch.autograd.Function over all parameters, so `loss.backward()`, GradScaler,
+DDP's gradient hooks and torch optimizers keep working unchanged (the drop-in contract of SURVEY.md §8b).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import _act_code, _round_up
+from .ops import ACT_NONE, ActView, ConvPlan
+
+
+class _ConvRec:
+    """One convolution (+ optional BN/act) of the network with everything its backward needs."""
+
+    def __init__(self) -> None:
+        self.conv: nn.Conv2d = None  # type: ignore
+        self.bn: Optional[nn.BatchNorm2d] = None
+        self.act = ACT_NONE
+        self.x: ActView = None  # type: ignore
+        self.z: ActView = None  # type: ignore   raw conv output
+        self.y: ActView = None  # type: ignore   bn/act output (== z when there is no BN)
+        self.residual: Optional[ActView] = None
+        self.stem = False
+
+
+class TrainEngine:
+    def __init__(self, model: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float32,
+                 scale: float = 1.0, device: Optional[torch.device] = None) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("ayolov2_b200.TrainEngine needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.B, self.H, self.W = batch, height, width
+        self.scale = scale
+        self.fwd: List[Callable[[], None]] = []
+        self.bwd: List[Callable[[], None]] = []   # appended in forward order, executed reversed
+        self.refresh: List[Callable[[], None]] = []  # weight re-packing (parameters change every optimizer step)
+        self.keep: List[Any] = []
+        self.grad_of: Dict[int, torch.Tensor] = {}   # id(activation buffer) -> gradient buffer
+        self.pgrads: Dict[int, torch.Tensor] = {}    # id(param) -> fp32 gradient (param shape), rebuilt per backward
+        self._img: Optional[torch.Tensor] = None
+        self.head_out: List[torch.Tensor] = []
+        self.head_gin: List[torch.Tensor] = []
+        self.flops_fwd = 0.0
+        self._build()
+
+    # ------------------------------------------------------------------------------------------------ buffers
+    def new_act(self, H: int, W: int, C_: int) -> ActView:
+        v = ops.new_act(self.B, H, W, _round_up(C_, 8), device=self.device)
+        v.buf.zero_()
+        self.keep.append(v.buf)
+        return v
+
+    def g(self, v: ActView) -> ActView:
+        """Gradient view mirroring an activation view."""
+        gb = self.grad_of.get(id(v.buf))
+        if gb is None:
+            gb = torch.zeros_like(v.buf)
+            self.grad_of[id(v.buf)] = gb
+        return ActView(gb, v.c0, v.c)
+
+    def _padd(self, p: nn.Parameter, t: torch.Tensor) -> None:
+        cur = self.pgrads.get(id(p))
+        if cur is None:
+            self.pgrads[id(p)] = t.to(p.dtype).reshape(p.shape).clone()
+        else:
+            cur.add_(t.to(p.dtype).reshape(p.shape))
+
+    # ------------------------------------------------------------------------------------------------ conv + bn + act
+    def conv_bn_act(self, conv: nn.Conv2d, bn: Optional[nn.Module], act: int, x: ActView, y: Optional[ActView] = None,
+                    residual: Optional[ActView] = None, need_dx: bool = True) -> ActView:
+        assert conv.groups == 1 and conv.dilation == (1, 1) and conv.kernel_size[0] == conv.kernel_size[1]
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        cout, cin = conv.out_channels, conv.in_channels
+        assert x.c == cin, (x.c, cin)
+        oh, ow = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+        has_bn = isinstance(bn, nn.BatchNorm2d)
+        if y is None:
+            y = self.new_act(oh, ow, cout)
+        z = self.new_act(oh, ow, cout) if has_bn else y
+        dev = self.device
+        bn_tile = ops.conv_block_n(cout)
+        cout_pad = _round_up(cout, bn_tile)
+        wp = torch.zeros((cout_pad, k * k * cin), dtype=torch.bfloat16, device=dev)
+        bp = torch.zeros(cout_pad, dtype=torch.float32, device=dev)
+        plan = ConvPlan(x, z, wp, bp, k, k, s, p, ACT_NONE if has_bn else act)
+        self.keep += [wp, bp, plan]
+        self.flops_fwd += plan.flops
+
+        def refresh() -> None:
+            wp[:cout].copy_(conv.weight.detach().permute(0, 2, 3, 1).reshape(cout, -1))
+            if conv.bias is not None:
+                bp[:cout].copy_(conv.bias.detach())
+        self.refresh.append(refresh)
+        self.fwd.append(plan.run)
+        if has_bn:
+            mean = torch.empty(cout, device=dev)
+            invstd = torch.empty(cout, device=dev)
+            scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+            self.keep += [mean, invstd, scratch]
+
+            def f_bn() -> None:
+                ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd)
+                bn.num_batches_tracked += 1
+                ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, residual)
+            self.fwd.append(f_bn)
+        else:
+            assert residual is None and act == ACT_NONE, "conv without BN is only used by the head"
+        # ---------------- backward
+        gy, gz = self.g(y), (self.g(z) if has_bn else self.g(y))
+        gx = self.g(x) if need_dx else None
+        dw = torch.zeros((cout, k * k * cin), dtype=torch.float32, device=dev)
+        dplans: List[ConvPlan] = []
+        if need_dx:
+            dplans = ops.make_dgrad_plans(gz, gx, conv.weight, s, p, accumulate=True)
+            self.keep += dplans
+            wsrc = conv.weight
+
+            def refresh_d() -> None:
+                fresh = ops.make_dgrad_weights(wsrc, s, p, gz.c)
+                for pl, wnew in zip(dplans, fresh):
+                    pl.w.copy_(wnew)
+            self.refresh.append(refresh_d)
+        gres = self.g(residual) if residual is not None else None
+
+        def b() -> None:
+            if has_bn:
+                if gres is not None:
+                    ops.add_slices(gy, gres, accumulate=True)  # shortcut branch: d(residual) += dy
+                ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz)
+                self._padd(bn.bias, scratch[:cout].float())
+                self._padd(bn.weight, scratch[cout:].float())
+            dw.zero_()
+            ops.conv_wgrad(x, gz, dw, k, k, s, p)
+            self._padd(conv.weight, dw.view(cout, k, k, cin).permute(0, 3, 1, 2))
+            if conv.bias is not None:
+                bs = torch.zeros(_round_up(cout, 8), dtype=torch.float64, device=dev)
+                ops.channel_sum(ActView(gz.buf, gz.c0, _round_up(cout, 8)), bs)
+                self._padd(conv.bias, bs[:cout].float())
+            for pl in dplans:
+                pl.run()
+        self.bwd.append(b)
+        return y
+
+    def kindle_conv(self, m: nn.Module, x: ActView, y: Optional[ActView] = None, residual: Optional[ActView] = None) -> ActView:
+        if isinstance(m.conv, nn.Sequential):
+            raise NotImplementedError("training a Tucker-decomposed model is not implemented (the reference fine-tunes "
+                                      "decomposed models rarely; eval-mode execution is supported)")
+        return self.conv_bn_act(m.conv, getattr(m, "batch_norm", None), _act_code(m), x, y, residual)
+
+    # ------------------------------------------------------------------------------------------------ stem
+    def stem(self, m: nn.Module, y: Optional[ActView]) -> ActView:
+        """6x6/s2/p2 Conv or Focus fed by the image: space-to-depth + packed 3x1-tap window conv (see engine.Builder.stem).
+        Backward: weight gradient over the 16-channel space-to-depth image (3x3 taps), mapped back to the 6x6 / Focus
+        layout on the host; no data gradient (the input is the image)."""
+        name = type(m).__name__
+        c = m.conv
+        bn = getattr(m, "batch_norm", None)
+        assert isinstance(c, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d)
+        H2, W2 = self.H // 2, self.W // 2
+        Wp = W2 + 8
+        dev = self.device
+        s2d = ActView(torch.zeros((self.B, H2, Wp, 16), dtype=torch.bfloat16, device=dev), 0, 16)
+        self.keep.append(s2d.buf)
+        self.fwd.append(lambda: ops.space_to_depth(self._img, s2d, self.scale, x_offset=1))
+        cout = c.out_channels
+        is_focus = name == "Focus"
+        if is_focus:
+            assert c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1) and c.in_channels == 12
+        else:
+            assert c.kernel_size == (6, 6) and c.stride == (2, 2) and c.padding == (2, 2) and c.in_channels == 3
+
+        def to_s2d_weight(w: torch.Tensor) -> torch.Tensor:  # -> (cout, 12, 3, 3) over s2d channels (dy*2+dx)*3+c
+            w2 = torch.zeros((cout, 12, 3, 3), device=dev)
+            for dy in range(2):
+                for dx in range(2):
+                    blk = slice((dy * 2 + dx) * 3, (dy * 2 + dx) * 3 + 3)
+                    if is_focus:
+                        w2[:, blk] = w[:, (dx * 2 + dy) * 3:(dx * 2 + dy) * 3 + 3]
+                    else:
+                        w2[:, blk] = w[:, :, dy::2, dx::2]
+            return w2
+
+        def from_s2d_grad(g2: torch.Tensor) -> torch.Tensor:  # inverse mapping for the gradient
+            gw = torch.zeros_like(c.weight, dtype=torch.float32)
+            for dy in range(2):
+                for dx in range(2):
+                    blk = slice((dy * 2 + dx) * 3, (dy * 2 + dx) * 3 + 3)
+                    if is_focus:
+                        gw[:, (dx * 2 + dy) * 3:(dx * 2 + dy) * 3 + 3] = g2[:, blk]
+                    else:
+                        gw[:, :, dy::2, dx::2] = g2[:, blk]
+            return gw
+
+        if y is None:
+            y = self.new_act(H2, W2, cout)
+        z = self.new_act(H2, W2, cout)
+        bn_tile = ops.conv_block_n(cout)
+        wp = torch.zeros((_round_up(cout, bn_tile), 3 * 64), dtype=torch.bfloat16, device=dev)
+        bp = torch.zeros(_round_up(cout, bn_tile), dtype=torch.float32, device=dev)
+        plan = ConvPlan(s2d, z, wp, bp, 3, 1, 1, 1, ACT_NONE, pad_w=0, window=(64, W2, 16, Wp))
+        self.keep += [wp, bp, plan]
+        self.flops_fwd += 2.0 * self.B * H2 * W2 * cout * 108
+
+        def refresh() -> None:
+            w2 = to_s2d_weight(c.weight.detach().float())
+            ww = torch.zeros((cout, 3, 64), device=dev)  # [cout][kh][kwp*16 + ch]
+            for kwp in range(3):
+                ww[:, :, kwp * 16:kwp * 16 + 12] = w2[:, :, :, kwp].permute(0, 2, 1)
+            wp[:cout].copy_(ww.reshape(cout, -1))
+        self.refresh.append(refresh)
+        self.fwd.append(plan.run)
+        mean, invstd = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+        scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+        act = _act_code(m)
+
+        def f_bn() -> None:
+            ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd)
+            bn.num_batches_tracked += 1
+            ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, None)
+        self.fwd.append(f_bn)
+        gy, gz = self.g(y), self.g(z)
+        dw = torch.zeros((cout, 9 * 16), dtype=torch.float32, device=dev)
+        x_ptr = s2d.ptr() + 2 * 16  # logical pixel 0 lives at physical column 1
+
+        def b() -> None:
+            ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz)
+            self._padd(bn.bias, scratch[:cout].float())
+            self._padd(bn.weight, scratch[cout:].float())
+            dw.zero_()
+            ops.conv_wgrad(s2d, gz, dw, 3, 3, 1, 1, in_row_pixels=Wp, x_ptr=x_ptr, in_w=W2)
+            g2 = dw.view(cout, 3, 3, 16)[..., :12].permute(0, 3, 1, 2)  # (cout, 12, 3, 3)
+            self._padd(c.weight, from_s2d_grad(g2))
+        self.bwd.append(b)
+        return y
+
+    # ------------------------------------------------------------------------------------------------ composite modules
+    def bottleneck(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        t = self.kindle_conv(m.conv1, x)
+        return self.kindle_conv(m.conv2, t, y=y, residual=x if m.shortcut else None)
+
+    def c3(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        c_ = m.conv1.conv.out_channels
+        cat = self.new_act(x.H, x.W, 2 * c_)
+        n = len(m.bottleneck_c3)
+        cur = self.kindle_conv(m.conv1, x, y=cat.slice(0, c_) if n == 0 else None)
+        for i, b in enumerate(m.bottleneck_c3):
+            cur = self.bottleneck(b, cur, cat.slice(0, c_) if i == n - 1 else None)
+        self.kindle_conv(m.conv2, x, y=cat.slice(c_, c_))
+        return self.kindle_conv(m.conv3, cat, y=y)
+
+    def spp(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        c_ = m.conv1.conv.out_channels
+        cascade = type(m).__name__ == "SPPF"
+        if cascade:
+            k = m.pooling.kernel_size
+            ks = (k, 2 * k - 1, 3 * k - 2)
+        else:
+            ks = tuple(int(p.kernel_size) for p in m.pooling_modules)
+        cat = self.new_act(x.H, x.W, 4 * c_)
+        sl = [cat.slice(i * c_, c_) for i in range(4)]
+        self.kindle_conv(m.conv1, x, y=sl[0])
+        self.fwd.append(lambda: ops.sppf_pool(sl[0], sl[1], sl[2], sl[3], ks))
+        out = self.kindle_conv(m.conv2, cat, y=y)
+        gs = [self.g(s) for s in sl]
+
+        def b() -> None:  # runs after conv2's backward filled d(cat)
+            if cascade:  # p3 = pool(p2), p2 = pool(p1), p1 = pool(x1): route through the cascade like the reference
+                ops.maxpool_bwd(sl[2], gs[3], ks[0], gs[2], accumulate=True)
+                ops.maxpool_bwd(sl[1], gs[2], ks[0], gs[1], accumulate=True)
+                ops.maxpool_bwd(sl[0], gs[1], ks[0], gs[0], accumulate=True)
+            else:
+                for i in (1, 2, 3):
+                    ops.maxpool_bwd(sl[0], gs[i], ks[i - 1], gs[0], accumulate=True)
+        # order: this must run BEFORE conv1's backward and AFTER conv2's: conv2's b() was appended last, so insert
+        # the pool backward just before it in list order (lists are executed reversed)
+        self.bwd.insert(len(self.bwd) - 1, b)
+        return out
+
+    def upsample(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
+        assert float(m.scale_factor) == 2.0 and m.mode == "nearest"
+        if y is None:
+            y = self.new_act(2 * x.H, 2 * x.W, x.c)
+        self.fwd.append(lambda: ops.upsample2x(x, y))
+        gy, gx = self.g(y), self.g(x)
+        self.bwd.append(lambda: ops.upsample2x_bwd(gy, gx, accumulate=True))
+        return y
+
+    def head(self, m: nn.Module, xs: Sequence[ActView]) -> None:
+        na, no = m.na, m.no
+        for i, (conv, x) in enumerate(zip(m.conv, xs)):
+            cpad = _round_up(na * no, 16)
+            logits = self.new_act(x.H, x.W, cpad)
+            out = torch.zeros((self.B, na, x.H, x.W, no), dtype=torch.float32, device=self.device)
+            gin = torch.zeros_like(out)
+            self.head_out.append(out)
+            self.head_gin.append(gin)
+            gl = self.g(logits)
+            # gradient arrives as (bs, na, ny, nx, no) fp32 -> NHWC bf16 before the conv's backward (executed reversed:
+            # append the conversion AFTER the conv record so that it runs first)
+            self._head_conv(conv, x, logits, na * no)
+            self.fwd.append(lambda l=logits, o=out: ops.head_logits_to_train(l, na, no, o))
+            self.bwd.append(lambda g_=gin, gl_=gl: ops.head_grad_to_nhwc(g_, gl_))
+
+    def _head_conv(self, conv: nn.Conv2d, x: ActView, logits: ActView, nch: int) -> None:
+        """1x1 conv with bias, Cout = na*no padded to the logits buffer width."""
+        dev = self.device
+        cin = conv.in_channels
+        cpad = logits.c
+        bn_tile = ops.conv_block_n(cpad)
+        wp = torch.zeros((_round_up(cpad, bn_tile), cin), dtype=torch.bfloat16, device=dev)
+        bp = torch.zeros(_round_up(cpad, bn_tile), dtype=torch.float32, device=dev)
+        plan = ConvPlan(x, logits, wp, bp, 1, 1, 1, 0, ACT_NONE)
+        self.keep += [wp, bp, plan]
+        self.flops_fwd += 2.0 * self.B * x.H * x.W * nch * cin
+
+        def refresh() -> None:
+            wp[:nch].copy_(conv.weight.detach().reshape(nch, cin))
+            bp[:nch].copy_(conv.bias.detach())
+        self.refresh.append(refresh)
+        self.fwd.append(plan.run)
+        gl, gx = self.g(logits), self.g(x)
+        dw = torch.zeros((cpad, cin), dtype=torch.float32, device=dev)
+        wfull = torch.zeros((cpad, cin, 1, 1), device=dev)
+        dplans = ops.make_dgrad_plans(gl, gx, wfull, 1, 0, accumulate=True)
+        self.keep += dplans
+
+        def refresh_d() -> None:
+            wfull[:nch].copy_(conv.weight.detach())
+            for pl, wnew in zip(dplans, ops.make_dgrad_weights(wfull, 1, 0, gl.c)):
+                pl.w.copy_(wnew)
+        self.refresh.append(refresh_d)
+
+        def b() -> None:
+            dw.zero_()
+            ops.conv_wgrad(x, gl, dw, 1, 1, 1, 0)
+            self._padd(conv.weight, dw[:nch].view(nch, cin, 1, 1))
+            bs = torch.zeros(cpad, dtype=torch.float64, device=dev)
+            ops.channel_sum(gl, bs)
+            self._padd(conv.bias, bs[:nch].float())
+            for pl in dplans:
+                pl.run()
+        self.bwd.append(b)
+
+    # ------------------------------------------------------------------------------------------------ graph walk
+    def _build(self) -> None:
+        from .engine import Engine
+
+        layers = list(self.model.model)
+        nL = len(layers)
+
+        def src_of(i: int) -> List[int]:
+            frm = getattr(layers[i], "from_idx", -1)
+            frm = list(frm) if isinstance(frm, (list, tuple)) else [frm]
+            return [i - 1 if f == -1 else f for f in frm]
+
+        dest: Dict[int, Tuple[int, int]] = {}
+        for j in range(nL):
+            if type(layers[j]).__name__ == "Concat":
+                off = 0
+                for s in src_of(j):
+                    if s in dest or type(layers[s]).__name__ == "Concat":
+                        raise NotImplementedError("a tensor feeding two Concat layers / nested Concat needs a copy kernel")
+                    dest[s] = (j, off)
+                    off += Engine._out_channels(layers, s, src_of)
+        cat_bufs: Dict[int, ActView] = {}
+        outs: List[Optional[ActView]] = [None] * nL
+
+        def out_view(i: int, H: int, W: int, C_: int) -> Optional[ActView]:
+            if i not in dest:
+                return None
+            j, off = dest[i]
+            if j not in cat_bufs:
+                cat_bufs[j] = self.new_act(H, W, Engine._out_channels(layers, j, src_of))
+            return cat_bufs[j].slice(off, C_)
+
+        for i, m in enumerate(layers):
+            name = type(m).__name__
+            srcs = src_of(i)
+            if name in ("Conv", "Focus") and srcs[0] < 0:
+                outs[i] = self.stem(m, out_view(i, self.H // 2, self.W // 2, m.conv.out_channels))
+                continue
+            xin = [outs[s] for s in srcs]
+            if name == "Conv":
+                c = m.conv
+                k_, s_, p_ = c.kernel_size[0], c.stride[0], c.padding[0]
+                oh, ow = (xin[0].H + 2 * p_ - k_) // s_ + 1, (xin[0].W + 2 * p_ - k_) // s_ + 1
+                outs[i] = self.kindle_conv(m, xin[0], y=out_view(i, oh, ow, c.out_channels))
+            elif name == "C3":
+                outs[i] = self.c3(m, xin[0], out_view(i, xin[0].H, xin[0].W, m.conv3.conv.out_channels))
+            elif name in ("SPP", "SPPF"):
+                outs[i] = self.spp(m, xin[0], out_view(i, xin[0].H, xin[0].W, m.conv2.conv.out_channels))
+            elif name == "Upsample":
+                outs[i] = self.upsample(m, xin[0], out_view(i, 2 * xin[0].H, 2 * xin[0].W, xin[0].c))
+            elif name == "Concat":
+                outs[i] = cat_bufs[i]
+            elif name == "YOLOHead":
+                self.head(m, xin)
+            else:
+                raise NotImplementedError(f"layer {i} ({name}) has no training path")
+
+    # ------------------------------------------------------------------------------------------------ run
+    def forward(self, img: torch.Tensor) -> List[torch.Tensor]:
+        self._img = img.contiguous()
+        for r in self.refresh:
+            r()
+        for f in self.fwd:
+            f()
+        return [o.clone() for o in self.head_out]
+
+    def backward(self, grads: Sequence[torch.Tensor]) -> Dict[int, torch.Tensor]:
+        for gb in self.grad_of.values():
+            gb.zero_()
+        self.pgrads = {}
+        for gin, g_ in zip(self.head_gin, grads):
+            gin.copy_(g_)
+        for b in reversed(self.bwd):
+            b()
+        return self.pgrads
+
+
+class TrainFunction(torch.autograd.Function):
+    """model(x) in training mode: one autograd node over every parameter of the model."""
+
+    @staticmethod
+    def forward(ctx, engine: TrainEngine, x: torch.Tensor, *params: torch.Tensor):
+        ctx.engine = engine
+        ctx.params = params
+        outs = engine.forward(x)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts: torch.Tensor):
+        eng: TrainEngine = ctx.engine
+        pg = eng.backward([g if g is not None else torch.zeros_like(o) for g, o in zip(gouts, eng.head_out)])
+        grads = tuple(pg.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        return (None, None) + grads
+
+
+def forward_train(model: nn.Module, x: torch.Tensor) -> List[torch.Tensor]:
+    """YOLOModel.forward in training mode (returns the list of (bs, na, ny, nx, no) head outputs)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    B, _, H, W = x.shape
+    cache = model.__dict__.setdefault("_train_engine_cache", {})
+    key = (B, H, W, x.device.index)
+    eng = cache.get(key)
+    if eng is None:
+        cache.clear()
+        eng = TrainEngine(model, B, H, W, device=x.device)
+        cache[key] = eng
+    params = tuple(model.parameters())
+    return list(TrainFunction.apply(eng, x, *params))

@@ -68,6 +68,10 @@ typedef struct ay2_conv_desc {
                              `cin` makes each input "pixel" an overlapping window of neighbouring pixels: the
                              16-channel space-to-depth stem is run as kh x 1 taps over 4-pixel windows (cin 64) */
   int32_t in_row_pixels;  /* physical pixels per input row (0 = in_w); > in_w for a horizontally padded buffer */
+  int32_t out_pix_stride; /* elements between horizontally adjacent OUTPUT pixels (0 = out_cstride) ... */
+  int32_t out_row_pixels; /* ... and output pixels per physical row (0 = out_w). With pix stride 2*cstride and row pixels
+                             = full width, the output (and the residual) is one (row, column) parity sub-grid of a
+                             twice-as-large tensor: how the data gradient of a stride-2 conv is written (4 launches) */
 } ay2_conv_desc;
 
 typedef struct ay2_conv_plan ay2_conv_plan;

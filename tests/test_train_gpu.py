@@ -141,3 +141,26 @@ def test_sgd_nesterov_ema_matches_torch():
     torch.cuda.synchronize()
     assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
     assert torch.allclose(ema, ema_ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 64, 3, 1, 1), (2, 20, 20, 128, 64, 1, 1, 0), (2, 32, 32, 32, 64, 3, 2, 1),
+                                  (2, 40, 40, 64, 128, 3, 2, 1)], ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_conv_dgrad_via_forward_kernel(case, accumulate):
+    from ayolov2_b200 import ops
+
+    B, H, W, Cin, Cout, k, s, p = case
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    g = torch.Generator(device="cuda").manual_seed(11)
+    w = torch.randn((Cout, Cin, k, k), device="cuda", generator=g) * 0.1
+    dz = _rand_act(B, OH, OW, Cout, seed=12)
+    dx = _rand_act(B, H, W, Cin, seed=13)
+    before = dx.tensor().float().clone()
+    for plan in ops.make_dgrad_plans(dz, dx, w, s, p, accumulate):
+        plan.run()
+    torch.cuda.synchronize()
+    xt = torch.zeros((B, Cin, H, W), device="cuda", requires_grad=True)
+    F.conv2d(xt, w.to(torch.bfloat16).float(), None, stride=s, padding=p).backward(dz.tensor().float().permute(0, 3, 1, 2))
+    ref = xt.grad.permute(0, 2, 3, 1) + (before if accumulate else 0.0)
+    err = (dx.tensor().float() - ref).abs().max() / ref.abs().max()
+    assert float(err) < 2e-2, float(err)

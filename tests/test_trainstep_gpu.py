@@ -1,0 +1,67 @@
+"""End-to-end parity of one training step (BASELINE.json configs[2] at a small size): train-mode forward with batch
+statistics -> ComputeLoss -> backward through every layer, CUDA path vs the CPU fp32 oracle (restated operators +
+loss oracle + autograd). bf16 activations/gradients: tolerances are relative L2 per tensor and a global cosine."""
+from copy import deepcopy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HYP = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
+
+
+def _targets(bs, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.zeros(n, 6)
+    t[:, 0] = torch.randint(0, bs, (n,), generator=g).float()
+    t[:, 1] = torch.randint(0, 80, (n,), generator=g).float()
+    t[:, 2:4] = 0.1 + 0.8 * torch.rand(n, 2, generator=g)
+    t[:, 4:6] = 0.05 + 0.4 * torch.rand(n, 2, generator=g)
+    return t
+
+
+@pytest.mark.parametrize("name,hw,bs", [("yolov5n", (128, 128), 4), ("yolov5s", (160, 192), 2), ("yolov5_v5", (128, 128), 2)])
+def test_train_step_matches_oracle(name, hw, bs):
+    from ayolov2_b200 import synth
+    from ayolov2_b200.loss import ComputeLoss
+    from oracle import loss_oracle, yolo_oracle
+
+    base = synth.build_model(name, seed=0)
+    base.hyp = dict(HYP)
+    x = torch.rand((bs, 3, *hw), generator=torch.Generator().manual_seed(3))
+    targets = _targets(bs, 12, 4)
+    # ---- oracle (CPU fp32, autograd)
+    ref = deepcopy(base).train()
+    preds_ref = yolo_oracle.forward_with_grad(ref, x)
+    head = ref.model[-1]
+    loss_ref, items_ref = loss_oracle.compute_loss(preds_ref, targets, head.anchors, HYP, head.nc)
+    loss_ref.backward()
+    # ---- CUDA
+    m = deepcopy(base).cuda().train()
+    preds = m(x.cuda())
+    loss, items = ComputeLoss(m)(preds, targets.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    for a, b in zip(preds, preds_ref):
+        err = float((a.detach().cpu() - b.detach()).abs().max() / b.detach().abs().max())
+        assert err < 4e-2, f"train-mode logits {err}"
+    assert abs(float(loss) - float(loss_ref)) / abs(float(loss_ref)) < 3e-2, (float(loss), float(loss_ref))
+    # BatchNorm running statistics were updated with batch statistics (momentum 0.03)
+    for (n1, b1), (n2, b2) in zip(m.named_buffers(), ref.named_buffers()):
+        if n1.endswith("running_mean") or n1.endswith("running_var"):
+            assert torch.allclose(b1.cpu(), b2, rtol=5e-2, atol=5e-3), n1
+    dots = n1s = n2s = 0.0
+    worst = (0.0, "")
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None, n
+        g1, g2 = p.grad.detach().cpu().double(), q.grad.detach().double()
+        dots += float((g1 * g2).sum())
+        n1s += float((g1 * g1).sum())
+        n2s += float((g2 * g2).sum())
+        rel = float((g1 - g2).norm() / (g2.norm() + 1e-12))
+        if g2.norm() > 1e-6 and rel > worst[0]:
+            worst = (rel, n)
+    cos = dots / (n1s ** 0.5 * n2s ** 0.5)
+    assert cos > 0.99, f"global gradient cosine {cos}, worst tensor {worst}"
+    assert worst[0] < 0.35, f"worst per-tensor relative L2 gradient error {worst}"
