@@ -6,7 +6,8 @@
 
 namespace ay2 {
 
-__device__ __forceinline__ float head_sigmoid(float t) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, __expf(-t))); }
+// ex2.approx + rcp.approx: 2 MUFU ops, ~2 ulp; the SAME function feeds the dense decode and the fused NMS filter
+__device__ __forceinline__ float head_sigmoid(float t) { return __fdividef(1.0f, __fadd_rn(1.0f, __expf(-t))); }
 __device__ __forceinline__ float head_xy(float s, float g, float stride) {
   return __fmul_rn(__fadd_rn(__fmaf_rn(s, 2.0f, -0.5f), g), stride);  // s*2 is exact, so the fma == mul, sub
 }

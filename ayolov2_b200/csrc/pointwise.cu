@@ -181,27 +181,32 @@ __global__ void head_decode_kernel(const __nv_bfloat16* __restrict__ logits, int
     for (int c0 = lane * 8; c0 < nch8; c0 += 256) {
       const uint4 q = *reinterpret_cast<const uint4*>(lp + c0);
       const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
-      int a = c0 / no;
-      int o = c0 - a * no;
+      float t[8], sg[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 f = __bfloat1622float2(h2[j >> 1]);
-        const float t = (j & 1) ? f.y : f.x;
-        const float s = head_sigmoid(t);
-        float v = s;
-        if (a < na) {
-          if (o == 0) v = head_xy(s, (float)x, stride_px);
-          else if (o == 1) v = head_xy(s, (float)y, stride_px);
-          else if (o == 2) v = head_wh(s, anchor_wh[a * 2]);
-          else if (o == 3) v = head_wh(s, anchor_wh[a * 2 + 1]);
-        }
-        vbuf[c0 + j] = v;
-        rbuf[c0 + j] = t;
-        if (++o == no) {
-          o = 0;
-          ++a;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        t[2 * j] = f.x;
+        t[2 * j + 1] = f.y;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sg[j] = head_sigmoid(t[j]);
+      *reinterpret_cast<float4*>(vbuf + c0) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      *reinterpret_cast<float4*>(vbuf + c0 + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+      if (raw) {
+        *reinterpret_cast<float4*>(rbuf + c0) = make_float4(t[0], t[1], t[2], t[3]);
+        *reinterpret_cast<float4*>(rbuf + c0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+      }
+    }
+    __syncwarp();
+    // box channels: 4 per anchor, fixed up by the first 4*na lanes (xy grid/stride, wh anchor)
+    if (lane < 4 * na) {
+      const int a = lane >> 2, o = lane & 3;
+      const float sgm = vbuf[a * no + o];
+      float v;
+      if (o == 0) v = head_xy(sgm, (float)x, stride_px);
+      else if (o == 1) v = head_xy(sgm, (float)y, stride_px);
+      else v = head_wh(sgm, anchor_wh[a * 2 + (o - 2)]);
+      vbuf[a * no + o] = v;
     }
     __syncwarp();
     for (int a = 0; a < na; ++a) {

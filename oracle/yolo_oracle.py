@@ -27,6 +27,20 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# When set, the forward rounds to bfloat16 (straight-through: gradients pass unchanged) at exactly the points where the
+# CUDA path stores bf16: conv weights, conv inputs, the raw conv output, and each layer output. Train-mode BatchNorm
+# re-normalises with batch statistics at every layer, which makes a random-init network chaotic w.r.t. such rounding
+# (the rounded and the exact fp32 forward give parameter gradients with cosine ~0.78 on the small test inputs), so
+# training-step parity is measured against this rounding-matched oracle, and the rounding noise itself is reported.
+SIMULATE_BF16 = False
+
+
+def _r(t: torch.Tensor) -> torch.Tensor:
+    if not SIMULATE_BF16:
+        return t
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
 def _act(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
     a = getattr(m, "activation", None)
     if a is None or isinstance(a, nn.Identity):
@@ -37,7 +51,11 @@ def _act(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
 def conv_bn_act(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """kindle Conv: activation(batch_norm(conv(x))); `conv` may be a Tucker nn.Sequential
     (scripts/tensor_decomposition/decomposition.py:325-335); `batch_norm` is Identity after fuse()."""
-    y = m.conv(x)
+    if SIMULATE_BF16 and isinstance(m.conv, nn.Conv2d):
+        c = m.conv
+        y = _r(F.conv2d(_r(x), _r(c.weight), c.bias, c.stride, c.padding, c.dilation, c.groups))
+    else:
+        y = m.conv(x)
     bn = getattr(m, "batch_norm", None)
     if isinstance(bn, nn.BatchNorm2d):
         y = bn(y)
@@ -47,19 +65,20 @@ def conv_bn_act(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
 def focus(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """Slice order verified by the detection pin."""
     x = torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1)
-    return conv_bn_act(m, x)
+    return _r(conv_bn_act(m, x))
 
 
 def bottleneck(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    y = conv_bn_act(m.conv2, conv_bn_act(m.conv1, x))
-    return x + y if m.shortcut else y
+    t = _r(conv_bn_act(m.conv1, x))
+    y = conv_bn_act(m.conv2, t)
+    return _r(x + y) if m.shortcut else _r(y)
 
 
 def c3(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    y1 = conv_bn_act(m.conv1, x)
+    y1 = _r(conv_bn_act(m.conv1, x))
     for b in m.bottleneck_c3:
         y1 = bottleneck(b, y1)
-    return conv_bn_act(m.conv3, torch.cat((y1, conv_bn_act(m.conv2, x)), 1))
+    return _r(conv_bn_act(m.conv3, torch.cat((y1, _r(conv_bn_act(m.conv2, x))), 1)))
 
 
 def bottleneck_csp(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -72,23 +91,23 @@ def bottleneck_csp(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
 
 
 def spp(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    x1 = conv_bn_act(m.conv1, x)
-    return conv_bn_act(m.conv2, torch.cat([x1] + [p(x1) for p in m.pooling_modules], 1))
+    x1 = _r(conv_bn_act(m.conv1, x))
+    return _r(conv_bn_act(m.conv2, torch.cat([x1] + [p(x1) for p in m.pooling_modules], 1)))
 
 
 def sppf(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
-    x1 = conv_bn_act(m.conv1, x)
+    x1 = _r(conv_bn_act(m.conv1, x))
     p1 = m.pooling(x1)
     p2 = m.pooling(p1)
     p3 = m.pooling(p2)
-    return conv_bn_act(m.conv2, torch.cat((x1, p1, p2, p3), 1))
+    return _r(conv_bn_act(m.conv2, torch.cat((x1, p1, p2, p3), 1)))
 
 
 def yolo_head(m: nn.Module, xs: Sequence[torch.Tensor], training: bool):
     """Train: [(bs, na, ny, nx, no)] logits. Eval: (cat over levels of (bs, na*ny*nx, no), [logits...])."""
     raw, dec = [], []
     for i, (conv, x) in enumerate(zip(m.conv, xs)):
-        t = conv(x)
+        t = _r(F.conv2d(_r(x), _r(conv.weight), conv.bias)) if SIMULATE_BF16 else conv(x)
         bs, _, ny, nx = t.shape
         t = t.view(bs, m.na, m.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         raw.append(t)
@@ -105,8 +124,12 @@ def yolo_head(m: nn.Module, xs: Sequence[torch.Tensor], training: bool):
     return raw if training else (torch.cat(dec, 1), raw)
 
 
+def _conv_layer(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    return _r(conv_bn_act(m, x))
+
+
 _DISPATCH = {
-    "Conv": conv_bn_act, "Focus": focus, "Bottleneck": bottleneck, "C3": c3, "BottleneckCSP": bottleneck_csp,
+    "Conv": _conv_layer, "Focus": focus, "Bottleneck": bottleneck, "C3": c3, "BottleneckCSP": bottleneck_csp,
     "SPP": spp, "SPPF": sppf,
 }
 

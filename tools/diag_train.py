@@ -15,16 +15,18 @@ base = synth.build_model(name, seed=0); base.hyp = dict(HYP)
 x = torch.rand((bs, 3, *hw), generator=torch.Generator().manual_seed(3))
 targets = _targets(bs, 12, 4)
 ref = deepcopy(base).train()
+yolo_oracle.SIMULATE_BF16 = True
 preds_ref = yolo_oracle.forward_with_grad(ref, x)
+yolo_oracle.SIMULATE_BF16 = False
 for p_ in preds_ref: p_.retain_grad()
 head = ref.model[-1]
-loss_ref, _ = loss_oracle.compute_loss(preds_ref, targets, head.anchors, HYP, head.nc)
-loss_ref.backward()
+g = torch.Generator().manual_seed(7)
+G = [torch.randn(p_.shape, generator=g) / p_.numel() ** 0.5 for p_ in preds_ref]
+sum((p_ * gg).sum() for p_, gg in zip(preds_ref, G)).backward()
 m = deepcopy(base).cuda().train()
 preds = m(x.cuda())
 for p_ in preds: p_.retain_grad()
-loss, _ = ComputeLoss(m)(preds, targets.cuda())
-loss.backward()
+sum((p_ * gg.cuda()).sum() for p_, gg in zip(preds, G)).backward()
 torch.cuda.synchronize()
 for i, (a, b) in enumerate(zip(preds, preds_ref)):
     print("dL/dpred level", i, "rel", float((a.grad.cpu() - b.grad).norm() / b.grad.norm()))
