@@ -304,8 +304,14 @@ def main() -> None:
         achieved = flops / (conv_ms / 1000.0) / 1e12
         peak = peaks["tflops_sustained"]
         abytes = ACT_MB_PER_IMG * 1e6 * BATCH
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (60 launches = one step)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_src": peaks["src"] + " (sustained)",
+        traffic = None  # DRAM bytes of the same 52 launches from the committed ncu capture (profiles/*_conv_traffic.json)
+        tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_traffic.json")) \
+            if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+        if tfiles:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))["dram_bytes"]
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (52 launches / 60 convolutions = one step)", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_src": peaks["src"] + " (sustained)",
                 "conv_ms_per_step": conv_ms, "hbm_view": {"achieved_gbs": abytes / (conv_ms / 1000.0) / 1e9,
                                                           "peak_gbs": peaks["hbm_gbs"],
                                                           "frac": abytes / (conv_ms / 1000.0) / 1e9 / peaks["hbm_gbs"]}}

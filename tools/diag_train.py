@@ -10,8 +10,10 @@ from oracle import loss_oracle, yolo_oracle
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_trainstep_gpu import HYP, _targets
 
-name, hw, bs = (sys.argv[1] if len(sys.argv) > 1 else "yolov5n"), (128, 128), 4
-base = synth.build_model(name, seed=0); base.hyp = dict(HYP)
+from test_trainstep_gpu import _build
+name = sys.argv[1] if len(sys.argv) > 1 else "mini_v6"
+hw, bs = ((256, 256), 4) if name.startswith("mini") else ((128, 128), 4)
+base = _build(name); base.hyp = dict(HYP)
 x = torch.rand((bs, 3, *hw), generator=torch.Generator().manual_seed(3))
 targets = _targets(bs, 12, 4)
 ref = deepcopy(base).train()
