@@ -46,7 +46,7 @@ class _ConvRec:
 
 class TrainEngine:
     def __init__(self, model: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float32,
-                 scale: float = 1.0, device: Optional[torch.device] = None) -> None:
+                 scale: float = 1.0, device: Optional[torch.device] = None, use_graph: bool = True) -> None:
         if not torch.cuda.is_available():
             raise RuntimeError("ayolov2_b200.TrainEngine needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.model = model
@@ -58,12 +58,19 @@ class TrainEngine:
         self.refresh: List[Callable[[], None]] = []  # weight re-packing (parameters change every optimizer step)
         self.keep: List[Any] = []
         self.grad_of: Dict[int, torch.Tensor] = {}   # id(activation buffer) -> gradient buffer
-        self.pgrads: Dict[int, torch.Tensor] = {}    # id(param) -> fp32 gradient (param shape), rebuilt per backward
         self._img: Optional[torch.Tensor] = None
         self.head_out: List[torch.Tensor] = []
         self.head_gin: List[torch.Tensor] = []
         self.flops_fwd = 0.0
+        # The launch sequence of a step is static (fixed shapes, static buffers, parameters updated in place), so the
+        # forward and the backward are each captured into a CUDA graph after one eager warm-up call: ~2000 small
+        # launches (weight re-packing, per-layer kernels, gradient scatter) become two graph replays.
+        self.use_graph = use_graph
+        self._gstate: Dict[str, int] = {}
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.static_in = torch.zeros((batch, 3, height, width), dtype=torch.float32, device=self.device)
         self._build()
+        self.pg: Dict[int, torch.Tensor] = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in model.parameters()}
 
     # ------------------------------------------------------------------------------------------------ buffers
     def new_act(self, H: int, W: int, C_: int) -> ActView:
@@ -81,11 +88,7 @@ class TrainEngine:
         return ActView(gb, v.c0, v.c)
 
     def _padd(self, p: nn.Parameter, t: torch.Tensor) -> None:
-        cur = self.pgrads.get(id(p))
-        if cur is None:
-            self.pgrads[id(p)] = t.to(p.dtype).reshape(p.shape).clone()
-        else:
-            cur.add_(t.to(p.dtype).reshape(p.shape))
+        self.pg[id(p)].add_(t.reshape(p.shape))
 
     # ------------------------------------------------------------------------------------------------ conv + bn + act
     def conv_bn_act(self, conv: nn.Conv2d, bn: Optional[nn.Module], act: int, x: ActView, y: Optional[ActView] = None,
@@ -421,23 +424,46 @@ class TrainEngine:
                 raise NotImplementedError(f"layer {i} ({name}) has no training path")
 
     # ------------------------------------------------------------------------------------------------ run
-    def forward(self, img: torch.Tensor) -> List[torch.Tensor]:
-        self._img = img.contiguous()
+    def _run_or_replay(self, key: str, body: Callable[[], None]) -> None:
+        st = self._gstate.get(key, 0)
+        if not self.use_graph or st == 0:
+            body()  # eager (also the warm-up that sets kernel attributes before any capture)
+            self._gstate[key] = 1
+            return
+        if st == 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self._graphs[key] = g
+            self._gstate[key] = 2
+        self._graphs[key].replay()
+
+    def _forward_body(self) -> None:
         for r in self.refresh:
             r()
         for f in self.fwd:
             f()
+
+    def _backward_body(self) -> None:
+        for gb in self.grad_of.values():
+            gb.zero_()
+        for t in self.pg.values():
+            t.zero_()
+        for b in reversed(self.bwd):
+            b()
+
+    def forward(self, img: torch.Tensor) -> List[torch.Tensor]:
+        self.static_in.copy_(img)
+        self._img = self.static_in
+        self._run_or_replay("fwd", self._forward_body)
         return [o.clone() for o in self.head_out]
 
     def backward(self, grads: Sequence[torch.Tensor]) -> Dict[int, torch.Tensor]:
-        for gb in self.grad_of.values():
-            gb.zero_()
-        self.pgrads = {}
         for gin, g_ in zip(self.head_gin, grads):
             gin.copy_(g_)
-        for b in reversed(self.bwd):
-            b()
-        return self.pgrads
+        self._run_or_replay("bwd", self._backward_body)
+        return {k: v.clone() for k, v in self.pg.items()}
 
 
 class TrainFunction(torch.autograd.Function):
