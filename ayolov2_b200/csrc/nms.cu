@@ -31,6 +31,37 @@ constexpr int kSortSmemKeys = 8192;
 constexpr int kChunk = 256;
 constexpr int kChunkWords = kChunk / 32;
 constexpr int kMaxDetCap = 1024;
+constexpr int kFastN = 4096;   // class-partitioned fast path: at most this many candidates per image ...
+constexpr int kMaxSeg = 256;   // ... and this many per class
+
+// Per-warp staging of candidate keys in shared memory: one global atomicAdd per flush instead of one per candidate
+// (2,800 same-address atomics per image serialise in L2 at ~70 ns each: 0.2 ms; staged: ~30 per image).
+constexpr int kStage = 96;
+struct WarpStage {
+  unsigned long long* buf;  // [kStage] shared memory, private to the warp
+  int n;                    // warp-uniform fill count
+};
+__device__ __forceinline__ void stage_flush(WarpStage& s, unsigned long long* kb, int* cnt, int cap, int lane) {
+  if (s.n == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(cnt, s.n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < s.n; i += 32)
+    if (base + i < cap) kb[base + i] = s.buf[i];
+  __syncwarp();
+  s.n = 0;
+}
+// all lanes call; lanes with ok contribute `key`
+__device__ __forceinline__ void stage_push(WarpStage& s, bool ok, unsigned long long key, unsigned long long* kb, int* cnt,
+                                           int cap, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (!m) return;
+  const int c = __popc(m);
+  if (s.n + c > kStage) stage_flush(s, kb, cnt, cap, lane);
+  if (ok) s.buf[s.n + __popc(m & ((1u << lane) - 1))] = key;
+  s.n += c;
+  __syncwarp();
+}
 
 __global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
                                   unsigned long long* __restrict__ keys, long long key_stride, int* __restrict__ counts) {
@@ -41,6 +72,8 @@ __global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params
   const int nc = p.no - 5;
   const float* ip = pred + (long long)b * p.n * p.no;
   unsigned long long* kb = keys + (long long)b * key_stride;
+  __shared__ unsigned long long stage_mem[8][kStage];
+  WarpStage st{stage_mem[threadIdx.x >> 5], 0};
   const int groups = (p.n + 31) / 32;
   for (int g = warp_in_grid; g < groups; g += nwarps) {
     const int row = g * 32 + lane;
@@ -61,18 +94,8 @@ __global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params
             conf = __fmul_rn(cp[c], robj);
             ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
           }
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&counts[b], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (ok) {
-              const int slot = base + __popc(m & ((1u << lane) - 1));
-              if (slot < p.max_candidates)
-                kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) |
-                           static_cast<unsigned>(rrow * nc + c);
-            }
-          }
+          stage_push(st, ok, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | static_cast<unsigned>(rrow * nc + c),
+                     kb, &counts[b], p.max_candidates, lane);
         }
       } else {
         // first arg-max over classes (torch.max(1) keeps the first maximal index)
@@ -94,15 +117,13 @@ __global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params
             bidx = oi;
           }
         }
-        if (lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx])) {
-          const int slot = atomicAdd(&counts[b], 1);
-          if (slot < p.max_candidates)
-            kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) |
-                       static_cast<unsigned>(rrow * nc + bidx);
-        }
+        stage_push(st, lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx]),
+                   (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | static_cast<unsigned>(rrow * nc + bidx), kb,
+                   &counts[b], p.max_candidates, lane);
       }
     }
   }
+  stage_flush(st, kb, &counts[b], p.max_candidates, lane);
 }
 
 // IoU > thr exactly as torchvision's CPU kernel evaluates it (fp32 arithmetic, comparison against the
@@ -182,6 +203,8 @@ __global__ void nms_filter_logits_kernel(BoxSource src, ay2_nms_params p, const 
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nc = src.no - 5;
   unsigned long long* kb = keys + (long long)b * key_stride;
+  __shared__ unsigned long long stage_mem[8][kStage];
+  WarpStage st{stage_mem[threadIdx.x >> 5], 0};
   for (int l = 0; l < src.nl; ++l) {
     const int plane = src.ny[l] * src.nx[l];
     const int groups = (plane + 31) / 32;
@@ -208,18 +231,8 @@ __global__ void nms_filter_logits_kernel(BoxSource src, ay2_nms_params p, const 
                 conf = __fmul_rn(head_sigmoid(__bfloat162float(cp[c])), robj);
                 ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
               }
-              const unsigned m = __ballot_sync(0xffffffffu, ok);
-              if (m) {
-                int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&counts[b], __popc(m));
-                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (ok) {
-                  const int slot = slot0 + __popc(m & ((1u << lane) - 1));
-                  if (slot < p.max_candidates)
-                    kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) |
-                               static_cast<unsigned>(row * nc + c);
-                }
-              }
+              stage_push(st, ok, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | static_cast<unsigned>(row * nc + c),
+                         kb, &counts[b], p.max_candidates, lane);
             }
           } else {
             float best = -INFINITY;
@@ -240,17 +253,15 @@ __global__ void nms_filter_logits_kernel(BoxSource src, ay2_nms_params p, const 
                 bidx = oi;
               }
             }
-            if (lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx])) {
-              const int slot = atomicAdd(&counts[b], 1);
-              if (slot < p.max_candidates)
-                kb[slot] = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) |
-                           static_cast<unsigned>(row * nc + bidx);
-            }
+            stage_push(st, lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx]),
+                       (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | static_cast<unsigned>(row * nc + bidx), kb,
+                       &counts[b], p.max_candidates, lane);
           }
         }
       }
     }
   }
+  stage_flush(st, kb, &counts[b], p.max_candidates, lane);
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1)
@@ -310,7 +321,141 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   if (n > p.max_nms) n = p.max_nms;
   const double thr = p.iou_thres;
 
-  // ---------------------------------------------------------------- greedy scan
+  // ---------------------------------------------------------------- class-partitioned fast path
+  // With per-class box offsets (metrics.py:383-384) boxes of different classes cannot intersect as long as every
+  // box lies inside a max_wh-wide window (checked below; exact, not an approximation), so greedy NMS decomposes
+  // into independent per-class greedy scans. Candidates are re-sorted by (class, score rank); one warp resolves one
+  // class segment; the kept flags are then compacted in global score order and the first max_det are emitted --
+  // exactly the rows, in exactly the order, of the sequential reference.
+  bool fast = !p.agnostic && n <= kFastN && sorted == skeys;
+  float4* fbo = reinterpret_cast<float4*>(skeys + kSortSmemKeys);   // [kFastN] offset boxes
+  float* farea = reinterpret_cast<float*>(fbo + kFastN);            // [kFastN]
+  int* fcls = reinterpret_cast<int*>(farea + kFastN);               // [kFastN]
+  unsigned char* fsupp = reinterpret_cast<unsigned char*>(fcls + kFastN);  // [kFastN]
+  int* fseg = reinterpret_cast<int*>(fsupp + kFastN);               // [kFastN] segment starts
+  unsigned long long* key2 = skeys + kFastN;                        // [kFastN] (upper half of the key buffer)
+  __shared__ int s_nseg, s_maxseg, s_scan[kNmsThreads / 32];
+  if (fast) {
+    if (tid == 0) {
+      s_nseg = 0;
+      s_maxseg = 0;
+    }
+    const float lo = -0.25f * p.max_wh, hi = 0.75f * p.max_wh - 2.0f;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned idx = static_cast<unsigned>(sorted[i]);
+      const int row = idx / nc;
+      const int cls = idx - row * nc;
+      const float4 r = load_xywh(src, b, row);
+      float4 bx;
+      bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+      bx.y = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+      bx.z = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+      bx.w = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+      if (!(bx.x >= lo && bx.y >= lo && bx.z <= hi && bx.w <= hi)) s_wide = 1;
+      const float off = __fmul_rn(static_cast<float>(cls), p.max_wh);
+      float4 bo;
+      bo.x = __fadd_rn(bx.x, off);
+      bo.y = __fadd_rn(bx.y, off);
+      bo.z = __fadd_rn(bx.z, off);
+      bo.w = __fadd_rn(bx.w, off);
+      fbo[i] = bo;
+      farea[i] = __fmul_rn(__fsub_rn(bo.z, bo.x), __fsub_rn(bo.w, bo.y));
+      fcls[i] = cls;
+      fsupp[i] = 0;
+    }
+    int n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (int i = tid; i < n2; i += blockDim.x)
+      key2[i] = i < n ? ((static_cast<unsigned long long>(static_cast<unsigned>(sorted[i]) % nc) << 32) | static_cast<unsigned>(i)) : ~0ull;
+    __syncthreads();
+    if (s_wide) fast = false;
+    if (fast) {
+      bitonic_sort(key2, n2);  // (class, score rank) ascending
+      for (int t = tid; t < n; t += blockDim.x) {
+        const unsigned c = static_cast<unsigned>(key2[t] >> 32);
+        if (t == 0 || static_cast<unsigned>(key2[t - 1] >> 32) != c) {
+          int a = t + 1, z = n;  // first index whose class differs (binary search on the sorted class field)
+          while (a < z) {
+            const int mid = (a + z) >> 1;
+            if (static_cast<unsigned>(key2[mid] >> 32) == c) a = mid + 1;
+            else z = mid;
+          }
+          atomicMax(&s_maxseg, a - t);
+          fseg[atomicAdd(&s_nseg, 1)] = t;
+        }
+      }
+      __syncthreads();
+      if (s_maxseg > kMaxSeg) fast = false;
+    }
+  }
+  if (fast) {
+    const int nseg = s_nseg;
+    for (int sgi = wid; sgi < nseg; sgi += nwarp) {
+      const int t0 = fseg[sgi];
+      const unsigned c = static_cast<unsigned>(key2[t0] >> 32);
+      int t1 = t0 + 1;
+      while (t1 < n && static_cast<unsigned>(key2[t1] >> 32) == c) ++t1;  // segments are short (<= kMaxSeg)
+      for (int a = t0; a < t1; ++a) {
+        const int ia = static_cast<int>(static_cast<unsigned>(key2[a]));
+        if (fsupp[ia]) continue;  // warp-uniform: every lane reads the same byte
+        const float4 ba = fbo[ia];
+        const float aa = farea[ia];
+        for (int bb = a + 1 + lane; bb < t1; bb += 32) {
+          const int ib = static_cast<int>(static_cast<unsigned>(key2[bb]));
+          if (!fsupp[ib] && iou_gt(ba, aa, fbo[ib], farea[ib], thr)) fsupp[ib] = 1;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // compaction in score order: exclusive prefix count of kept flags
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += fsupp[i] ? 0 : 1;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int v = lane < nwarp ? s_scan[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      if (lane < nwarp) s_scan[lane] = v;
+    }
+    __syncthreads();
+    int k = incl - cnt + (wid > 0 ? s_scan[wid - 1] : 0);
+    for (int i = i0; i < i1 && k < p.max_det; ++i) {
+      if (fsupp[i]) continue;
+      const unsigned long long key = sorted[i];
+      const unsigned idx = static_cast<unsigned>(key);
+      const int row = idx / nc;
+      const float4 r = load_xywh(src, b, row);
+      float* o = out_det + ((long long)b * p.max_det + k) * 6;
+      o[0] = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+      o[1] = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+      o[2] = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+      o[3] = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+      o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
+      o[5] = static_cast<float>(idx - row * nc);
+      ++k;
+    }
+    __syncthreads();
+    if (tid == 0) out_count[b] = min(s_scan[nwarp - 1], p.max_det);
+    return;
+  }
+  __syncthreads();
+  if (tid == 0) s_wide = 0;  // the chunk path recomputes it
+  __syncthreads();
+
+  // ---------------------------------------------------------------- greedy scan (general path)
   for (int cs = 0; cs < n; cs += kChunk) {
     const int kc = s_kept;
     if (kc >= p.max_det) break;
@@ -433,9 +578,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   if (tid == 0) out_count[b] = s_kept;
 }
 
-constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys + sizeof(float4) * (2 * kChunk + kMaxDetCap) +
-                                 sizeof(float) * (2 * kChunk + kMaxDetCap) + sizeof(int) * (3 * kChunk + kMaxDetCap) +
-                                 sizeof(unsigned) * kChunk * kChunkWords;
+constexpr size_t kNmsChunkBytes = sizeof(float4) * (2 * kChunk + kMaxDetCap) + sizeof(float) * (2 * kChunk + kMaxDetCap) +
+                                  sizeof(int) * (3 * kChunk + kMaxDetCap) + sizeof(unsigned) * kChunk * kChunkWords;
+constexpr size_t kNmsFastBytes = (sizeof(float4) + sizeof(float) + sizeof(int) + 1 + sizeof(int)) * kFastN;
+constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys +
+                                 (kNmsChunkBytes > kNmsFastBytes ? kNmsChunkBytes : kNmsFastBytes);
 
 static long long key_stride_for(const ay2_nms_params* p) {
   long long s = 2;

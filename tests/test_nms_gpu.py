@@ -49,3 +49,17 @@ def test_nms_ties_documented():
     pred[0, :, 5] = 0.8
     pred[0, 4:, 0] += 200.0
     _cmp(pred, conf_thres=0.25, iou_thres=0.45)
+
+
+def test_nms_paths_agree_wide_boxes_and_single_class():
+    """The class-partitioned fast path must hand over to the general chunked scan when a box leaves the max_wh window
+    (cross-class overlap possible) or when one class dominates; both must equal the oracle."""
+    from oracle import nms_oracle
+
+    pred = nms_oracle.synth_predictions(2, n=3000, seed=5)
+    pred[0, :50, 2:4] = 6000.0  # huge boxes: classes overlap despite the offset
+    _cmp(pred, conf_thres=0.25, iou_thres=0.45)
+    one = nms_oracle.synth_predictions(2, n=3000, nc=1, seed=6)
+    _cmp(one, conf_thres=0.25, iou_thres=0.45)
+    many = nms_oracle.synth_predictions(1, n=6000, seed=7, cand_frac=0.9)  # > 4096 candidates: general path
+    _cmp(many, conf_thres=0.25, iou_thres=0.45)
