@@ -36,6 +36,8 @@ struct ConvKernelParams {
   int cin;         // K extent per tap in the packed weights
   int cout_pad;
   int act, has_res;
+  int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
+              // CTA fetches half of every weight (B) tile, multicast into both CTAs' shared memory
 };
 
 constexpr int kSmemPerSm = 227 * 1024;
@@ -93,13 +95,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_k_chunks = p.kh * p.kw * p.cin_chunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::NSTAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.csize);  // every CTA sharing the multicast B tile must release the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -113,18 +114,26 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   }
   if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
+  if (p.csize > 1) cluster_sync_all();  // peer barriers must be initialised before any multicast can land
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // work items: (group of csize neighbouring M tiles, N tile); a cluster walks the item list, CTA `crank` takes its M tile
+  const int crank = p.csize > 1 ? (int)cluster_ctarank() : 0;
+  const int item0 = blockIdx.x / p.csize;
+  const int item_step = gridDim.x / p.csize;
+  const int total_items = ((p.num_m_tiles + p.csize - 1) / p.csize) * p.num_n_tiles;
+  const uint16_t cmask = (uint16_t)((1u << p.csize) - 1);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0, phase = 0;
       const int box_rows = p.BH * p.BW;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m = tile / p.num_n_tiles;
-        const int n0 = (tile - m * p.num_n_tiles) * BLOCK_N;
+      for (int item = item0; item < total_items; item += item_step) {
+        const int mg = item / p.num_n_tiles;
+        const int m = mg * p.csize + crank;
+        const int n0 = (item - mg * p.num_n_tiles) * BLOCK_N;
         int bx[8], by[8], bb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -163,7 +172,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
                   tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, cc * CK, bx[j] + dx,
                               by[j] + dy, bb[j]);
               }
-              tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
+              if (p.csize > 1) {
+                constexpr int HALF_ROWS = BLOCK_N / 2;
+                tma_load_2d_mc(&p.tmB, &full_bar[stage], sb + crank * HALF_ROWS * Cfg::SWA, kbase + cc * CK,
+                               n0 + crank * HALF_ROWS, cmask);
+              } else {
+                tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
+              }
               if (++stage == Cfg::NSTAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
       int stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int item = item0; item < total_items; item += item_step, ++it) {
         const int acc = it & 1;
         const int acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -195,7 +210,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
             const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
             umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (p.csize > 1) umma_commit_mc(&empty_bar[stage], cmask);  // release the stage in every CTA of the cluster
+          else umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
           if (++stage == Cfg::NSTAGES) {
             stage = 0;
             phase ^= 1;
@@ -213,11 +229,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
     const int box_rows = p.BH * p.BW;
     int it = 0;
     uint32_t res_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int item = item0; item < total_items; item += item_step, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
-      const int m = tile / p.num_n_tiles;
-      const int n0 = (tile - m * p.num_n_tiles) * BLOCK_N;
+      const int mg = item / p.num_n_tiles;
+      const int m = mg * p.csize + crank;
+      const int n0 = (item - mg * p.num_n_tiles) * BLOCK_N;
 
       if (eall == 0) {
         tma_store_wait_read<0>();  // previous tile's TMA stores have finished reading the staging buffer
@@ -306,7 +323,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (p.csize > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on it
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -506,7 +524,9 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
                             2 * cs * d->in_w, cs * d->in_w * d->in_h, ck, bw, bh);
       }
   }
-  if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn);
+  // cluster of 2 when there is more than one M tile: halves the weight (B) traffic out of L2
+  kp.csize = kp.num_m_tiles >= 2 ? 2 : 1;
+  if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);
   const int oc = bn < 64 ? bn : 64;
   // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)
   const bool sub = d->out_pix_stride > 0;
@@ -547,16 +567,32 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  const int total_tiles = kp.num_m_tiles * kp.num_n_tiles;
-  const int resident = sms * pl->ctas_per_sm;
-  pl->grid = total_tiles < resident ? total_tiles : resident;
+  const int items = ((kp.num_m_tiles + kp.csize - 1) / kp.csize) * kp.num_n_tiles;
+  const int resident = sms * pl->ctas_per_sm / kp.csize;  // clusters that fit at once
+  pl->grid = (items < resident ? items : resident) * kp.csize;
   *plan_out = pl;
   return AY2_OK;
 }
 
 extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
   AY2_REQUIRE(pl, "ay2_conv_plan_run: null plan");
-  pl->kernel<<<pl->grid, pl->threads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+  if (pl->kp.csize > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl->grid);
+    cfg.blockDim = dim3(pl->threads);
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = pl->kp.csize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    AY2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pl->kernel, pl->kp));
+  } else {
+    pl->kernel<<<pl->grid, pl->threads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+  }
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -315,6 +315,16 @@ def main() -> None:
                 "conv_ms_per_step": conv_ms, "hbm_view": {"achieved_gbs": abytes / (conv_ms / 1000.0) / 1e9,
                                                           "peak_gbs": peaks["hbm_gbs"],
                                                           "frac": abytes / (conv_ms / 1000.0) / 1e9 / peaks["hbm_gbs"]}}
+        # NMS share (north_star: NMS < 2 % of the step): the two NMS launches timed alone on the last step's logits
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            det.nms_ws.run_logits(det.levels, eng.head_logits, det.conf_thres, det.iou_thres, agnostic=det.agnostic)
+        b_.record()
+        torch.cuda.synchronize()
+        nms_ms = a.elapsed_time(b_) / 20
+        roof["nms_ms_per_step"] = nms_ms
+        roof["nms_share_of_step"] = nms_ms / ms_per_step
         layers = []
         for plan, tot, n in per_plan.values():
             d = plan.desc
