@@ -15,6 +15,7 @@
 //   warp 1 : tcgen05.mma issuer (one lane), accumulators double-buffered in TMEM
 //   warp 2 : TMEM allocate / free
 //   warps 4-7 : epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> swizzled smem -> TMA store
+#include <stdlib.h>
 #include <string.h>
 
 #include "ay2_common.h"
@@ -524,8 +525,11 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
                             2 * cs * d->in_w, cs * d->in_w * d->in_h, ck, bw, bh);
       }
   }
-  // cluster of 2 when there is more than one M tile: halves the weight (B) traffic out of L2
-  kp.csize = kp.num_m_tiles >= 2 ? 2 : 1;
+  // Weight-tile multicast across a 2-CTA cluster is implemented and parity-tested (AY2_CONV_CLUSTER=2), but measured
+  // 5 % SLOWER on every yolov5s layer (r01: 2.81 vs 2.65 ms per step): at cluster sizes <= 4 the L2 already dedups
+  // neighbouring unicast requests, so multicast saves no LTS bandwidth and only adds lock-step. Off by default.
+  static const int env_cluster = getenv("AY2_CONV_CLUSTER") ? atoi(getenv("AY2_CONV_CLUSTER")) : 1;
+  kp.csize = (env_cluster == 2 && kp.num_m_tiles >= 2) ? 2 : 1;
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);
   const int oc = bn < 64 ? bn : 64;
   // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)

@@ -63,69 +63,6 @@ __device__ __forceinline__ void stage_push(WarpStage& s, bool ok, unsigned long 
   __syncwarp();
 }
 
-__global__ void nms_filter_kernel(const float* __restrict__ pred, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
-                                  unsigned long long* __restrict__ keys, long long key_stride, int* __restrict__ counts) {
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nc = p.no - 5;
-  const float* ip = pred + (long long)b * p.n * p.no;
-  unsigned long long* kb = keys + (long long)b * key_stride;
-  __shared__ unsigned long long stage_mem[8][kStage];
-  WarpStage st{stage_mem[threadIdx.x >> 5], 0};
-  const int groups = (p.n + 31) / 32;
-  for (int g = warp_in_grid; g < groups; g += nwarps) {
-    const int row = g * 32 + lane;
-    const float obj = row < p.n ? ip[(long long)row * p.no + 4] : 0.f;
-    unsigned pass = __ballot_sync(0xffffffffu, row < p.n && obj > p.conf_thres);
-    while (pass) {
-      const int r = __ffs(pass) - 1;
-      pass &= pass - 1;
-      const int rrow = g * 32 + r;
-      const float robj = __shfl_sync(0xffffffffu, obj, r);
-      const float* cp = ip + (long long)rrow * p.no + 5;
-      if (p.multi_label) {
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-          const int c = c0 + lane;
-          float conf = 0.f;
-          bool ok = false;
-          if (c < nc) {
-            conf = __fmul_rn(cp[c], robj);
-            ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
-          }
-          stage_push(st, ok, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | static_cast<unsigned>(rrow * nc + c),
-                     kb, &counts[b], p.max_candidates, lane);
-        }
-      } else {
-        // first arg-max over classes (torch.max(1) keeps the first maximal index)
-        float best = -INFINITY;
-        int bidx = 0x7fffffff;
-        for (int c = lane; c < nc; c += 32) {
-          const float conf = __fmul_rn(cp[c], robj);
-          if (conf > best) {
-            best = conf;
-            bidx = c;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-          if (ob > best || (ob == best && oi < bidx)) {
-            best = ob;
-            bidx = oi;
-          }
-        }
-        stage_push(st, lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx]),
-                   (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | static_cast<unsigned>(rrow * nc + bidx), kb,
-                   &counts[b], p.max_candidates, lane);
-      }
-    }
-  }
-  stage_flush(st, kb, &counts[b], p.max_candidates, lane);
-}
-
 // IoU > thr exactly as torchvision's CPU kernel evaluates it (fp32 arithmetic, comparison against the
 // double threshold). The early-out is exact: a non-positive extent gives inter = 0 -> IoU 0 (or NaN) -> false
 // for any thr >= 0.
@@ -191,74 +128,145 @@ __device__ __forceinline__ float4 load_xywh(const BoxSource& s, int b, int row) 
   return o;
 }
 
-// Fused filter: candidates straight from the head logits (no dense (B, 25200, 85) tensor is ever written).
-// One warp per 32 consecutive pixels of one level; lanes test the objectness logit of each anchor, then the
-// warp scores the passing (pixel, anchor) rows cooperatively. Scores are bit-identical to head_decode + filter.
-__global__ void nms_filter_logits_kernel(BoxSource src, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
-                                         unsigned long long* __restrict__ keys, long long key_stride,
-                                         int* __restrict__ counts) {
+// ---------------------------------------------------------------------------------------------------------------
+// Candidate generation in two balanced phases.
+//   phase A (rows)  : every row's objectness is tested once (coalesced over rows / pixels); passing row indices are
+//                     appended to a per-image list. Objectness is spatially clustered, so scoring the rows inside this
+//                     loop would leave a few warps with ~100 serial row visits (measured: 0.2 ms of tail).
+//   phase B (score) : one warp per listed row, grid-strided over the list -> every warp gets the same amount of work.
+//                     conf_c = cls_c * obj, best class (first arg-max) or every class above conf (multi_label).
+// Dense mode reads the fp32 prediction tensor; logits mode decodes the bf16 head logits with the shared head arithmetic
+// (bit-identical scores, no dense (B, 25200, 85) tensor).
+// ---------------------------------------------------------------------------------------------------------------
+struct U32Stage {
+  unsigned* buf;
+  int n;
+};
+__device__ __forceinline__ void rows_flush(U32Stage& s, unsigned* list, int* cnt, int cap, int lane) {
+  if (s.n == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(cnt, s.n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < s.n; i += 32)
+    if (base + i < cap) list[base + i] = s.buf[i];
+  __syncwarp();
+  s.n = 0;
+}
+__device__ __forceinline__ void rows_push(U32Stage& s, bool ok, unsigned v, unsigned* list, int* cnt, int cap, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (!m) return;
+  const int c = __popc(m);
+  if (s.n + c > kStage) rows_flush(s, list, cnt, cap, lane);
+  if (ok) s.buf[s.n + __popc(m & ((1u << lane) - 1))] = v;
+  s.n += c;
+  __syncwarp();
+}
+
+__global__ void nms_rows_kernel(BoxSource src, ay2_nms_params p, unsigned* __restrict__ rows, int* __restrict__ row_counts) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nc = src.no - 5;
-  unsigned long long* kb = keys + (long long)b * key_stride;
-  __shared__ unsigned long long stage_mem[8][kStage];
-  WarpStage st{stage_mem[threadIdx.x >> 5], 0};
-  for (int l = 0; l < src.nl; ++l) {
-    const int plane = src.ny[l] * src.nx[l];
-    const int groups = (plane + 31) / 32;
-    const __nv_bfloat16* base = src.logits[l] + (long long)b * plane * src.cstride[l];
+  unsigned* list = rows + (long long)b * p.n;
+  __shared__ unsigned stage_mem[8][kStage];
+  U32Stage st{stage_mem[threadIdx.x >> 5], 0};
+  if (src.pred) {
+    const float* ip = src.pred + (long long)b * p.n * p.no;
+    const int groups = (p.n + 31) / 32;
     for (int g = warp_in_grid; g < groups; g += nwarps) {
-      const int pix = g * 32 + lane;
-      for (int a = 0; a < src.na; ++a) {
-        float obj = 0.f;
-        if (pix < plane) obj = head_sigmoid(__bfloat162float(base[(long long)pix * src.cstride[l] + a * src.no + 4]));
-        unsigned pass = __ballot_sync(0xffffffffu, pix < plane && obj > p.conf_thres);
-        while (pass) {
-          const int r = __ffs(pass) - 1;
-          pass &= pass - 1;
-          const int rpix = g * 32 + r;
-          const int row = src.row_off[l] + a * plane + rpix;
-          const float robj = __shfl_sync(0xffffffffu, obj, r);
-          const __nv_bfloat16* cp = base + (long long)rpix * src.cstride[l] + a * src.no + 5;
-          if (p.multi_label) {
-            for (int c0 = 0; c0 < nc; c0 += 32) {
-              const int c = c0 + lane;
-              float conf = 0.f;
-              bool ok = false;
-              if (c < nc) {
-                conf = __fmul_rn(head_sigmoid(__bfloat162float(cp[c])), robj);
-                ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
-              }
-              stage_push(st, ok, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | static_cast<unsigned>(row * nc + c),
-                         kb, &counts[b], p.max_candidates, lane);
-            }
-          } else {
-            float best = -INFINITY;
-            int bidx = 0x7fffffff;
-            for (int c = lane; c < nc; c += 32) {
-              const float conf = __fmul_rn(head_sigmoid(__bfloat162float(cp[c])), robj);
-              if (conf > best) {
-                best = conf;
-                bidx = c;
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-              if (ob > best || (ob == best && oi < bidx)) {
-                best = ob;
-                bidx = oi;
-              }
-            }
-            stage_push(st, lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx]),
-                       (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | static_cast<unsigned>(row * nc + bidx), kb,
-                       &counts[b], p.max_candidates, lane);
-          }
+      const int row = g * 32 + lane;
+      const bool ok = row < p.n && ip[(long long)row * p.no + 4] > p.conf_thres;
+      rows_push(st, ok, (unsigned)row, list, &row_counts[b], p.n, lane);
+    }
+  } else {
+    for (int l = 0; l < src.nl; ++l) {
+      const int plane = src.ny[l] * src.nx[l];
+      const int groups = (plane + 31) / 32;
+      const __nv_bfloat16* base = src.logits[l] + (long long)b * plane * src.cstride[l];
+      for (int g = warp_in_grid; g < groups; g += nwarps) {
+        const int pix = g * 32 + lane;
+        for (int a = 0; a < src.na; ++a) {
+          bool ok = false;
+          if (pix < plane)
+            ok = head_sigmoid(__bfloat162float(base[(long long)pix * src.cstride[l] + a * src.no + 4])) > p.conf_thres;
+          rows_push(st, ok, (unsigned)(src.row_off[l] + a * plane + pix), list, &row_counts[b], p.n, lane);
         }
       }
+    }
+  }
+  rows_flush(st, list, &row_counts[b], p.n, lane);
+}
+
+__global__ void nms_score_rows_kernel(BoxSource src, ay2_nms_params p, const uint8_t* __restrict__ class_mask,
+                                      const unsigned* __restrict__ rows, const int* __restrict__ row_counts,
+                                      unsigned long long* __restrict__ keys, long long key_stride, int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_grid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nc = p.no - 5;
+  const unsigned* list = rows + (long long)b * p.n;
+  unsigned long long* kb = keys + (long long)b * key_stride;
+  const int nrows = min(row_counts[b], p.n);
+  __shared__ unsigned long long stage_mem[8][kStage];
+  WarpStage st{stage_mem[threadIdx.x >> 5], 0};
+  for (int e = warp_in_grid; e < nrows; e += nwarps) {
+    const int row = (int)list[e];
+    float robj;
+    float cv[4];  // class scores of this lane: classes lane, lane+32, lane+64, lane+96 (more classes: extra passes below)
+    const float* fp = nullptr;
+    const __nv_bfloat16* hp = nullptr;
+    if (src.pred) {
+      fp = src.pred + ((long long)b * p.n + row) * p.no;
+      robj = fp[4];
+    } else {
+      int l = 0;
+      while (l + 1 < src.nl && row >= src.row_off[l + 1]) ++l;
+      const int r = row - src.row_off[l];
+      const int plane = src.ny[l] * src.nx[l];
+      const int a = r / plane;
+      const int pix = r - a * plane;
+      hp = src.logits[l] + ((long long)b * plane + pix) * src.cstride[l] + a * src.no;
+      robj = head_sigmoid(__bfloat162float(hp[4]));
+    }
+    (void)cv;
+    if (p.multi_label) {
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        float conf = 0.f;
+        bool ok = false;
+        if (c < nc) {
+          const float cs = fp ? fp[5 + c] : head_sigmoid(__bfloat162float(hp[5 + c]));
+          conf = __fmul_rn(cs, robj);
+          ok = conf > p.conf_thres && (!class_mask || class_mask[c]);
+        }
+        stage_push(st, ok, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | static_cast<unsigned>(row * nc + c),
+                   kb, &counts[b], p.max_candidates, lane);
+      }
+    } else {
+      // first arg-max over classes (torch.max(1) keeps the first maximal index)
+      float best = -INFINITY;
+      int bidx = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {
+        const float cs = fp ? fp[5 + c] : head_sigmoid(__bfloat162float(hp[5 + c]));
+        const float conf = __fmul_rn(cs, robj);
+        if (conf > best) {
+          best = conf;
+          bidx = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) {
+          best = ob;
+          bidx = oi;
+        }
+      }
+      stage_push(st, lane == 0 && best > p.conf_thres && (!class_mask || class_mask[bidx]),
+                 (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | static_cast<unsigned>(row * nc + bidx), kb,
+                 &counts[b], p.max_candidates, lane);
     }
   }
   stage_flush(st, kb, &counts[b], p.max_candidates, lane);
@@ -594,11 +602,33 @@ static long long key_stride_for(const ay2_nms_params* p) {
 
 using namespace ay2;
 
-// workspace layout: [counts int32 x B][overflow int32][pad to 256][keys u64 x B x key_stride]
+// workspace layout: [counts int32 x B][overflow int32][row_counts int32 x B][pad to 256]
+//                   [keys u64 x B x key_stride][rows u32 x B x n]
+static size_t nms_head_bytes(const ay2_nms_params* p) { return ((sizeof(int) * (2 * p->batch + 1) + 255) / 256) * 256; }
 extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
   if (!p) return 0;
-  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
-  return head + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p);
+  return nms_head_bytes(p) + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p) +
+         sizeof(unsigned) * (size_t)p->batch * (size_t)p->n;
+}
+
+static int nms_generate_candidates(const BoxSource& src, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
+                                   unsigned long long** keys_out, int** counts_out, int** overflow_out, cudaStream_t st) {
+  const size_t head = nms_head_bytes(p);
+  int* counts = static_cast<int*>(workspace);
+  int* overflow = counts + p->batch;
+  int* row_counts = overflow + 1;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
+  const long long ks = key_stride_for(p);
+  unsigned* rows = reinterpret_cast<unsigned*>(keys + (size_t)p->batch * ks);
+  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (2 * p->batch + 1), st));
+  nms_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, rows, row_counts);
+  AY2_CHECK_LAUNCH();
+  nms_score_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, class_mask, rows, row_counts, keys, ks, counts);
+  AY2_CHECK_LAUNCH();
+  *keys_out = keys;
+  *counts_out = counts;
+  *overflow_out = overflow;
+  return AY2_OK;
 }
 
 static int nms_common_checks(const ay2_nms_params* p, const void* workspace, size_t workspace_bytes, const void* out_det,
@@ -636,26 +666,19 @@ extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const
   int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
   if (rc != AY2_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
-  int* counts = static_cast<int*>(workspace);
-  int* overflow = counts + p->batch;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
-  const long long ks = key_stride_for(p);
-  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (p->batch + 1), st));
-  const int groups = (p->n + 31) / 32;
-  const int threads = 256;
-  int bx = (groups + (threads / 32) - 1) / (threads / 32);
-  if (bx > 64) bx = 64;
-  nms_filter_kernel<<<dim3(bx, p->batch), threads, 0, st>>>(pred, *p, class_mask, keys, ks, counts);
-  AY2_CHECK_LAUNCH();
   BoxSource src;
   memset(&src, 0, sizeof(src));
   src.pred = pred;
   src.n = p->n;
   src.no = p->no;
+  unsigned long long* keys;
+  int *counts, *overflow;
+  rc = nms_generate_candidates(src, p, class_mask, workspace, &keys, &counts, &overflow, st);
+  if (rc != AY2_OK) return rc;
+  const long long ks = key_stride_for(p);
   rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
   if (rc != AY2_OK) return rc;
-  count_launch(2);
+  count_launch(3);
   return AY2_OK;
 }
 
@@ -691,17 +714,13 @@ extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_para
   src.n = rows;
   AY2_REQUIRE(rows == p->n, "level table covers %d rows but params.n = %d", rows, p->n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t head = ((sizeof(int) * (p->batch + 1) + 255) / 256) * 256;
-  int* counts = static_cast<int*>(workspace);
-  int* overflow = counts + p->batch;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
+  unsigned long long* keys;
+  int *counts, *overflow;
+  rc = nms_generate_candidates(src, p, class_mask, workspace, &keys, &counts, &overflow, st);
+  if (rc != AY2_OK) return rc;
   const long long ks = key_stride_for(p);
-  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (p->batch + 1), st));
-  const int threads = 256;
-  nms_filter_logits_kernel<<<dim3(32, p->batch), threads, 0, st>>>(src, *p, class_mask, keys, ks, counts);
-  AY2_CHECK_LAUNCH();
   rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
   if (rc != AY2_OK) return rc;
-  count_launch(2);
+  count_launch(3);
   return AY2_OK;
 }

@@ -69,7 +69,7 @@ class Detector:
             self.nms_ws.run_logits(self.levels, eng.head_logits, self.conf_thres, self.iou_thres, agnostic=self.agnostic)
 
     def launches_per_step(self) -> int:
-        n = len(self.engine.b.steps) + 2  # + NMS filter and sort/scan kernels
+        n = len(self.engine.b.steps) + 3  # + NMS row filter, row scoring and sort/scan kernels
         return n if self.dense_pred else n - len(self.engine.decode_steps)
 
     def run_device(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

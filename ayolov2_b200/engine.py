@@ -166,13 +166,29 @@ class Builder:
             bn = tuple(t.detach().float().to(self.device) for t in bn)
         if y is None:
             y = self.new_act(H2, W2, cout)
-        # window weights: [cout, kh, (kwp in 0..3) * 16 + ch], kwp = 3 and ch >= 12 are zero
-        ww = torch.zeros((cout, 64, 3, 1), device=self.device)  # OIHW with I = 64 window channels, kernel 3x1
-        for kwp in range(3):
-            ww[:, kwp * 16:kwp * 16 + 12, :, 0] = w2[:, :, :, kwp]
         bias = c.bias.detach().float().to(self.device) if c.bias is not None else None
-        wp, bp = ops.pack_conv_weight(ww, bias, bn, eps)
-        plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2, 16, Wp))
+        pair = (y.c0 == 0 and y.cstride == cout and W2 % 2 == 0 and Wp % 2 == 0 and 2 * cout <= 256)
+        if pair:
+            # Two horizontally adjacent output pixels share one 4-pixel window (logical pixels 2x-1 .. 2x+2 are exactly
+            # the union of their receptive fields): run the stem as M = pixel pairs, N = 2*cout. The window tile is
+            # fetched once per pair, halving the L2->SM traffic of this L2-bound layer, and the 2*cout output channels
+            # of a pair are the NHWC bytes of the two pixels, so the same buffer is simply viewed as [B,H,W/2,2*cout].
+            ww = torch.zeros((2 * cout, 64, 3, 1), device=self.device)
+            for px in range(2):
+                for kw_ in range(3):
+                    ww[px * cout:(px + 1) * cout, (kw_ + px) * 16:(kw_ + px) * 16 + 12, :, 0] = w2[:, :, :, kw_]
+            bn2 = None if bn is None else tuple(torch.cat((t, t)) for t in bn)
+            bias2 = None if bias is None else torch.cat((bias, bias))
+            wp, bp = ops.pack_conv_weight(ww, bias2, bn2, eps)
+            y2 = ActView(y.buf.view(self.B, H2, W2 // 2, 2 * cout), 0, 2 * cout)
+            plan = ConvPlan(s2d, y2, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2 // 2, 32, Wp // 2))
+        else:
+            # window weights: [cout, kh, (kwp in 0..3) * 16 + ch], kwp = 3 and ch >= 12 are zero
+            ww = torch.zeros((cout, 64, 3, 1), device=self.device)  # OIHW with I = 64 window channels, kernel 3x1
+            for kwp in range(3):
+                ww[:, kwp * 16:kwp * 16 + 12, :, 0] = w2[:, :, :, kwp]
+            wp, bp = ops.pack_conv_weight(ww, bias, bn, eps)
+            plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2, 16, Wp))
         self.plans.append(plan)
         self.steps.append(plan.run)
         self.flops += 2.0 * self.B * H2 * W2 * cout * 9 * 12  # == 36 taps x 3 channels of the 6x6 stem
