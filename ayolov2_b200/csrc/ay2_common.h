@@ -42,4 +42,25 @@ void count_launch(int n = 1);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// NMS workspace layout (nms.cu), shared with the head convolution whose epilogue appends candidates to it (conv_tc.cu)
+struct NmsWorkspaceView {
+  int* counts;               // [batch] candidates per image
+  int* overflow;             // [1]
+  int* row_counts;           // [batch] rows that passed the objectness test (two-phase generation only)
+  unsigned long long* keys;  // [batch][key_stride]
+  long long key_stride;
+  unsigned* rows;            // [batch][n]
+};
+NmsWorkspaceView nms_workspace_view(const ay2_nms_params* p, void* workspace);
+
+// Candidate generation fused into the detect-head convolution epilogue (conv_tc.cu); keys == nullptr: off.
+struct HeadCandParams {
+  unsigned long long* keys;
+  int* counts;
+  const uint8_t* class_mask;
+  long long key_stride;
+  float conf_thres;
+  int max_candidates, na, no, row_off, multi_label, batch, out_h, out_w;
+};
+
 }  // namespace ay2

@@ -20,6 +20,7 @@
 
 #include "ay2_common.h"
 #include "ay2_ptx.cuh"
+#include "head_math.cuh"
 
 namespace ay2 {
 
@@ -39,6 +40,7 @@ struct ConvKernelParams {
   int act, has_res;
   int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
               // CTA fetches half of every weight (B) tile, multicast into both CTAs' shared memory
+  HeadCandParams hc;  // detect head only: NMS candidates are scored and appended from the staged output tile
 };
 
 constexpr int kSmemPerSm = 227 * 1024;
@@ -75,6 +77,89 @@ struct ConvCfg {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Detect-head epilogue: NMS candidate generation from the staged bf16 output tile (metrics.py:313-364).
+// The tile holds all na*no logits of 128 pixels; epilogue thread `et` owns one pixel, the epilogue groups split the
+// anchors. A row passes when obj > conf (:313,337); its score is conf_c = cls_c * obj (:353) with the first arg-max
+// class (:363-364) or every class above conf (multi_label, :360-361) -- the same arithmetic (head_math.cuh) on the
+// same stored bf16 logits as the stand-alone kernels in nms.cu, so the keys are bit-identical to theirs. Keys are
+// appended to the per-image list with one atomicAdd per warp and image.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok, int b, unsigned long long key, int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  while (m) {  // one round per distinct image among the passing lanes (a warp's 32 pixels rarely span two images)
+    const int leader = __ffs(m) - 1;
+    const int bl = __shfl_sync(0xffffffffu, b, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, ok && b == bl);
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&h.counts[bl], __popc(same));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok && b == bl) {
+      const int pos = base + __popc(same & ((1u << lane) - 1u));
+      if (pos < h.max_candidates) h.keys[(long long)bl * h.key_stride + pos] = key;
+    }
+    m &= ~same;
+  }
+}
+
+template <class Cfg>
+__device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
+                                                int lane) {
+  const HeadCandParams& h = p.hc;
+  const int box_rows = p.BH * p.BW;
+  const int j = et / box_rows, rr = et - j * box_rows;
+  const int q = m * p.NB + j;
+  const int b = q / p.boxes_per_img;
+  const int r = q - b * p.boxes_per_img;
+  const int py = r / p.boxes_x;
+  const int ry = rr / p.BW;
+  const int oy = py * p.BH + ry, ox = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
+  const bool inside = b < h.batch && oy < h.out_h && ox < h.out_w;
+  const int plane = h.out_h * h.out_w;
+  const int nc = h.no - 5;
+  auto logit = [&](int ch) -> float {  // channel ch of this thread's pixel in the swizzled staging slabs
+    const uint8_t* slab = staging + (ch / Cfg::OC) * Cfg::SLAB_BYTES;
+    const int cc = ch % Cfg::OC;
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(et, cc >> 3) + (cc & 7) * 2));
+  };
+  for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
+    const int c0 = a * h.no;
+    float obj = 0.0f;
+    bool pass = false;
+    if (inside) {
+      obj = head_sigmoid(logit(c0 + 4));
+      pass = obj > h.conf_thres;
+    }
+    if (!__ballot_sync(0xffffffffu, pass)) continue;  // warp-uniform
+    const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy * h.out_w + ox);
+    if (h.multi_label) {
+      for (int c = 0; c < nc; ++c) {
+        float conf = 0.0f;
+        bool ok = false;
+        if (pass) {
+          conf = __fmul_rn(head_sigmoid(logit(c0 + 5 + c)), obj);
+          ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
+        }
+        head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
+      }
+    } else {
+      float best = -INFINITY;
+      int bidx = 0;
+      if (pass) {
+        for (int c = 0; c < nc; ++c) {  // first arg-max: strict > keeps the lowest index among equal scores
+          const float conf = __fmul_rn(head_sigmoid(logit(c0 + 5 + c)), obj);
+          if (conf > best) {
+            best = conf;
+            bidx = c;
+          }
+        }
+      }
+      const bool ok = pass && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+      head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx), lane);
+    }
+  }
 }
 
 template <int BLOCK_N, int CK>
@@ -319,6 +404,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
         }
         tma_store_commit();
       }
+      // detect head: score NMS candidates from the staged tile while the TMA store drains it (both only read);
+      // nobody rewrites the staging buffer before every epilogue thread has passed the next iteration's barrier
+      if (p.hc.keys) head_candidates<Cfg>(p, staging, m, et, egrp, lane);
     }
     if (eall == 0) tma_store_wait_all<0>();
   }
@@ -575,6 +663,40 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   const int resident = sms * pl->ctas_per_sm / kp.csize;  // clusters that fit at once
   pl->grid = (items < resident ? items : resident) * kp.csize;
   *plan_out = pl;
+  return AY2_OK;
+}
+
+extern "C" int ay2_conv_plan_set_head_candidates(ay2_conv_plan* pl, const ay2_nms_params* p, int32_t na, int32_t row_off,
+                                                 const uint8_t* class_mask, void* nms_workspace, size_t workspace_bytes) {
+  AY2_REQUIRE(pl, "ay2_conv_plan_set_head_candidates: null plan");
+  if (!p) {  // switch the fused candidate generation off again
+    memset(&pl->kp.hc, 0, sizeof(pl->kp.hc));
+    return AY2_OK;
+  }
+  const ay2_conv_desc& d = pl->desc;
+  AY2_REQUIRE(nms_workspace && workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace missing or too small");
+  AY2_REQUIRE(pl->kp.num_n_tiles == 1, "head candidates need all %d output channels in one N tile (block_n=%d)", d.cout,
+              pl->block_n);
+  AY2_REQUIRE(na >= 1 && p->no > 5 && na * p->no <= d.cout, "head layout na=%d no=%d does not fit cout=%d", na, p->no, d.cout);
+  AY2_REQUIRE(p->batch == d.batch, "NMS batch %d != conv batch %d", p->batch, d.batch);
+  AY2_REQUIRE(d.out_pix_stride <= 0, "head candidates are not defined for sub-grid outputs");
+  AY2_REQUIRE(row_off >= 0 && row_off + na * d.out_h * d.out_w <= p->n, "level rows [%d, %d) exceed params.n = %d", row_off,
+              row_off + na * d.out_h * d.out_w, p->n);
+  const NmsWorkspaceView v = nms_workspace_view(p, nms_workspace);
+  HeadCandParams& h = pl->kp.hc;
+  h.keys = v.keys;
+  h.counts = v.counts;
+  h.class_mask = class_mask;
+  h.key_stride = v.key_stride;
+  h.conf_thres = p->conf_thres;
+  h.max_candidates = p->max_candidates;
+  h.na = na;
+  h.no = p->no;
+  h.row_off = row_off;
+  h.multi_label = p->multi_label;
+  h.batch = d.batch;
+  h.out_h = d.out_h;
+  h.out_w = d.out_w;
   return AY2_OK;
 }
 

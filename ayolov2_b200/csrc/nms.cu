@@ -18,6 +18,7 @@
 //   tested against the boxes kept so far, then a 256x256 bit matrix of within-chunk overlaps is built and
 //   resolved word by word by one warp. The scan stops as soon as max_det boxes are kept, which is what
 //   makes greedy NMS cheap: later candidates cannot change the first max_det decisions.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ay2_common.h"
@@ -31,8 +32,9 @@ constexpr int kSortSmemKeys = 8192;
 constexpr int kChunk = 256;
 constexpr int kChunkWords = kChunk / 32;
 constexpr int kMaxDetCap = 1024;
-constexpr int kFastN = 4096;   // class-partitioned fast path: at most this many candidates per image ...
-constexpr int kMaxSeg = 256;   // ... and this many per class
+constexpr int kFastN = 2048;         // segmented bit-matrix path: at most this many candidates per image ...
+constexpr int kMaskWords = 16384;    // ... and this many 32-bit words of upper-triangular overlap masks (64 KB)
+constexpr int kRound = 64;           // candidates of a segment resolved per round (multiple of 32)
 
 // Per-warp staging of candidate keys in shared memory: one global atomicAdd per flush instead of one per candidate
 // (2,800 same-address atomics per image serialise in L2 at ~70 ns each: 0.2 ms; staged: ~30 per image).
@@ -63,16 +65,33 @@ __device__ __forceinline__ void stage_push(WarpStage& s, bool ok, unsigned long 
   __syncwarp();
 }
 
-// IoU > thr exactly as torchvision's CPU kernel evaluates it (fp32 arithmetic, comparison against the
-// double threshold). The early-out is exact: a non-positive extent gives inter = 0 -> IoU 0 (or NaN) -> false
-// for any thr >= 0.
-__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const double thr) {
-  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
-  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
-  if (!(right > left) || !(bottom > top)) return false;
-  const float inter = __fmul_rn(__fsub_rn(right, left), __fsub_rn(bottom, top));
-  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
-  return static_cast<double>(iou) > thr;
+// IoU > iou_thres exactly as torchvision's CPU kernel evaluates it: fp32 arithmetic, w/h clamped at 0, RN division,
+// comparison against the double threshold. The double comparison is folded into `thr` = the largest float <= iou_thres
+// ((double)x > T  <=>  x > thr for every float x). The division is avoided for all but a sliver of pairs:
+// with q = inter/uni (real), inter > uni*thr*(1+2^-20) => q > thr + ulp(thr) => RN(q) > thr, and
+// inter < uni*thr*(1-2^-20) => q < thr => RN(q) <= thr (RN is monotone, thr is a float); the roundings of hi/lo are
+// < 2^-22 relative as long as uni is a normal positive number far from overflow (`fin`). Branch-free up to that sliver.
+struct IouThr {
+  float thr, hi, lo;
+};
+__device__ __forceinline__ IouThr make_iou_thr(double iou_thres) {
+  IouThr t;
+  t.thr = static_cast<float>(iou_thres);
+  if (static_cast<double>(t.thr) > iou_thres) t.thr = nextafterf(t.thr, -INFINITY);
+  const bool filt = t.thr > 1e-30f && t.thr < 1e30f;
+  t.hi = filt ? __fmul_rn(t.thr, 1.000001f) : INFINITY;
+  t.lo = filt ? __fmul_rn(t.thr, 0.999999f) : -INFINITY;
+  return t;
+}
+__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const IouThr t) {
+  const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+  const bool fin = (__float_as_uint(uni) - 0x0D800000u) < 0x64000000u;  // 2^-100 <= uni < 2^100 (positive, finite)
+  if (fin && inter > __fmul_rn(uni, t.hi)) return true;
+  if (fin && inter < __fmul_rn(uni, t.lo)) return false;
+  return __fdiv_rn(inter, uni) > t.thr;
 }
 
 template <typename Ptr>
@@ -92,6 +111,54 @@ __device__ __forceinline__ void bitonic_sort(Ptr A, int N) {
       __syncthreads();
     }
   }
+}
+
+// Bitonic sort of N <= 2 * blockDim.x keys with two keys per thread held in registers: the j = 1 stages are in-thread,
+// j = 2..32 are warp shuffles, only j >= 64 exchange through shared memory. (A pure shared-memory bitonic sort moves
+// 32 KB per stage for 2048 keys -- 66 stages at the 128 B/clk of one SM are 9 us before any barrier cost; measured 18 us.)
+// N is a power of two >= 2; A holds the keys on entry and the sorted keys on return.
+__device__ __forceinline__ void bitonic_cmpx(unsigned long long& a, const unsigned long long o, const bool keep_min) {
+  const bool lt = a < o;
+  a = (lt == keep_min) ? a : o;
+}
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long* A, const int N) {
+  const int t = threadIdx.x;
+  const bool act = 2 * t < N;
+  unsigned long long a0 = ~0ull, a1 = ~0ull;
+  if (act) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&A[2 * t]);
+    a0 = v.x;
+    a1 = v.y;
+  }
+  for (int k = 2; k <= N; k <<= 1) {
+    const bool up = ((2 * t) & k) == 0;
+    for (int j = k >> 1; j >= 64; j >>= 1) {
+      __syncthreads();
+      if (act) *reinterpret_cast<ulonglong2*>(&A[2 * t]) = make_ulonglong2(a0, a1);
+      __syncthreads();
+      if (act) {
+        const int m = j >> 1;
+        const ulonglong2 o = *reinterpret_cast<const ulonglong2*>(&A[2 * (t ^ m)]);
+        const bool keep_min = ((t & m) == 0) == up;
+        bitonic_cmpx(a0, o.x, keep_min);
+        bitonic_cmpx(a1, o.y, keep_min);
+      }
+    }
+    for (int j = (k >> 1) < 32 ? (k >> 1) : 32; j >= 2; j >>= 1) {
+      const int m = j >> 1;
+      const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, a0, m);
+      const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, a1, m);
+      const bool keep_min = ((t & m) == 0) == up;
+      bitonic_cmpx(a0, o0, keep_min);
+      bitonic_cmpx(a1, o1, keep_min);
+    }
+    const unsigned long long lo = a0 < a1 ? a0 : a1, hi = a0 < a1 ? a1 : a0;
+    a0 = up ? lo : hi;
+    a1 = up ? hi : lo;
+  }
+  __syncthreads();
+  if (act) *reinterpret_cast<ulonglong2*>(&A[2 * t]) = make_ulonglong2(a0, a1);
+  __syncthreads();
 }
 
 // Where a candidate's xywh box comes from: the dense fp32 prediction tensor, or (fused path) the bf16 head
@@ -275,7 +342,12 @@ __global__ void nms_score_rows_kernel(BoxSource src, ay2_nms_params p, const uin
 __global__ void __launch_bounds__(kNmsThreads, 1)
     nms_sort_scan_kernel(BoxSource src, ay2_nms_params p, unsigned long long* __restrict__ keys, long long key_stride,
                          const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
-                         int* __restrict__ overflow) {
+                         int* __restrict__ overflow, long long* __restrict__ trace) {
+#define AY2_NMS_MARK(k)                                                    \
+  do {                                                                     \
+    if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); \
+  } while (0)
+  AY2_NMS_MARK(0);
   extern __shared__ __align__(16) uint8_t sm[];
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);             // [kSortSmemKeys]
   float4* cbo = reinterpret_cast<float4*>(skeys + kSortSmemKeys);                    // chunk boxes + class offset
@@ -318,7 +390,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   if (npow2 <= kSortSmemKeys) {
     for (int i = tid; i < npow2; i += blockDim.x) skeys[i] = i < n ? gk[i] : ~0ull;
     __syncthreads();
-    bitonic_sort(skeys, npow2);
+    if (npow2 <= 2 * kNmsThreads) bitonic_sort_regs(skeys, npow2);
+    else bitonic_sort(skeys, npow2);
     sorted = skeys;
   } else {
     for (int i = n + tid; i < npow2; i += blockDim.x) gk[i] = ~0ull;
@@ -326,23 +399,36 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     bitonic_sort(gk, npow2);
     sorted = gk;
   }
+  AY2_NMS_MARK(1);
+  const bool fits_fast = npow2 <= kFastN;  // judged on the unclamped count: the key buffer's upper half must be free
   if (n > p.max_nms) n = p.max_nms;
-  const double thr = p.iou_thres;
+  const IouThr thr = make_iou_thr(p.iou_thres);
 
-  // ---------------------------------------------------------------- class-partitioned fast path
+  // ---------------------------------------------------------------- segmented bit-matrix path (n <= kFastN)
   // With per-class box offsets (metrics.py:383-384) boxes of different classes cannot intersect as long as every
   // box lies inside a max_wh-wide window (checked below; exact, not an approximation), so greedy NMS decomposes
-  // into independent per-class greedy scans. Candidates are re-sorted by (class, score rank); one warp resolves one
-  // class segment; the kept flags are then compacted in global score order and the first max_det are emitted --
-  // exactly the rows, in exactly the order, of the sequential reference.
-  bool fast = !p.agnostic && n <= kFastN && sorted == skeys;
-  float4* fbo = reinterpret_cast<float4*>(skeys + kSortSmemKeys);   // [kFastN] offset boxes
-  float* farea = reinterpret_cast<float*>(fbo + kFastN);            // [kFastN]
-  int* fcls = reinterpret_cast<int*>(farea + kFastN);               // [kFastN]
-  unsigned char* fsupp = reinterpret_cast<unsigned char*>(fcls + kFastN);  // [kFastN]
-  int* fseg = reinterpret_cast<int*>(fsupp + kFastN);               // [kFastN] segment starts
-  unsigned long long* key2 = skeys + kFastN;                        // [kFastN] (upper half of the key buffer)
+  // into independent per-class greedy scans. Candidates are re-sorted by (class, score rank) into segments (one
+  // segment for everything when agnostic or when a box leaves the window). Each segment is resolved in rounds of
+  // kRound candidates: all warps build the upper-triangular overlap words of the round's rows that are still alive
+  // (32 IoU tests + a ballot per word; words whose 32 columns are already suppressed are skipped), then one warp per
+  // segment resolves the round's greedy order 32 candidates at a time and ORs the kept rows into the segment's
+  // suppressed bits. Survivors are compacted in global score order -- exactly the rows, in exactly the order, of the
+  // sequential reference; the laziness only skips tests whose outcome cannot matter.
+  unsigned long long* key2 = skeys + kFastN;                                    // [kFastN]  (class, rank) keys
+  float4* sbo = reinterpret_cast<float4*>(skeys + 2 * kFastN);                  // [kFastN]  offset boxes, segment order
+  uint8_t* fr = reinterpret_cast<uint8_t*>(skeys + kSortSmemKeys);              // overlay of the chunk-path region
+  float4* rbox = reinterpret_cast<float4*>(fr);                                 // [kFastN] output boxes, score order
+  float* sarea = reinterpret_cast<float*>(rbox + kFastN);                       // [kFastN]
+  int* soff = reinterpret_cast<int*>(sarea + kFastN);                           // [kFastN + 4] mask row offsets
+  int* st0 = soff + kFastN + 4;                                                 // [kFastN] segment start of row t
+  int* segend = st0 + kFastN;                                                   // [kFastN] indexed by segment start
+  int* fseg = segend + kFastN;                                                  // [kFastN] list of segment starts
+  unsigned* srem = reinterpret_cast<unsigned*>(fseg + kFastN);                  // [kFastN] suppressed bits of a 32-block,
+                                                                                //          indexed by the block's first row
+  unsigned* masks = srem + kFastN;                                              // [kMaskWords]
+  unsigned char* ssupp = reinterpret_cast<unsigned char*>(masks + kMaskWords);  // [kFastN] by score rank
   __shared__ int s_nseg, s_maxseg, s_scan[kNmsThreads / 32];
+  bool fast = fits_fast;
   if (fast) {
     if (tid == 0) {
       s_nseg = 0;
@@ -351,76 +437,171 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     const float lo = -0.25f * p.max_wh, hi = 0.75f * p.max_wh - 2.0f;
     for (int i = tid; i < n; i += blockDim.x) {
       const unsigned idx = static_cast<unsigned>(sorted[i]);
-      const int row = idx / nc;
-      const int cls = idx - row * nc;
-      const float4 r = load_xywh(src, b, row);
+      const float4 r = load_xywh(src, b, idx / nc);
+      // general.py:316-319 with ratio = wh = 1, pad = 0  (1*1*(x -+ w/2) + 0)
       float4 bx;
       bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
       bx.y = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
       bx.z = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
       bx.w = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
       if (!(bx.x >= lo && bx.y >= lo && bx.z <= hi && bx.w <= hi)) s_wide = 1;
-      const float off = __fmul_rn(static_cast<float>(cls), p.max_wh);
+      rbox[i] = bx;
+      ssupp[i] = 0;
+      srem[i] = 0;
+    }
+    __syncthreads();
+    AY2_NMS_MARK(2);
+    const bool partition = !p.agnostic && !s_wide;
+    int n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (int i = tid; i < n2; i += blockDim.x) {
+      const unsigned cls = partition && i < n ? static_cast<unsigned>(sorted[i]) % nc : 0u;
+      key2[i] = i < n ? ((static_cast<unsigned long long>(cls) << 32) | static_cast<unsigned>(i)) : ~0ull;
+    }
+    __syncthreads();
+    if (partition) bitonic_sort_regs(key2, n2);  // (class, score rank) ascending
+    AY2_NMS_MARK(3);
+    // per row: its segment, offset box, and the length of its mask row (words from its own 32-block to the segment end)
+    for (int t = tid; t < n; t += blockDim.x) {
+      const unsigned c = static_cast<unsigned>(key2[t] >> 32);
+      const int i = static_cast<int>(static_cast<unsigned>(key2[t]));
+      int a = 0, z = t;  // first index of class c
+      while (a < z) {
+        const int mid = (a + z) >> 1;
+        if (static_cast<unsigned>(key2[mid] >> 32) < c) a = mid + 1;
+        else z = mid;
+      }
+      const int t0 = a;
+      a = t + 1, z = n;  // first index whose class differs
+      while (a < z) {
+        const int mid = (a + z) >> 1;
+        if (static_cast<unsigned>(key2[mid] >> 32) == c) a = mid + 1;
+        else z = mid;
+      }
+      const int t1 = a;
+      if (t == t0) {
+        segend[t0] = t1;
+        fseg[atomicAdd(&s_nseg, 1)] = t0;
+        atomicMax(&s_maxseg, t1 - t0);
+      }
+      st0[t] = t0;
+      soff[t] = ((t1 - t0 + 31) >> 5) - ((t - t0) >> 5);
+      const float4 bx = rbox[i];
+      const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(static_cast<unsigned>(sorted[i]) % nc), p.max_wh);
       float4 bo;
       bo.x = __fadd_rn(bx.x, off);
       bo.y = __fadd_rn(bx.y, off);
       bo.z = __fadd_rn(bx.z, off);
       bo.w = __fadd_rn(bx.w, off);
-      fbo[i] = bo;
-      farea[i] = __fmul_rn(__fsub_rn(bo.z, bo.x), __fsub_rn(bo.w, bo.y));
-      fcls[i] = cls;
-      fsupp[i] = 0;
+      sbo[t] = bo;
+      sarea[t] = __fmul_rn(__fsub_rn(bo.z, bo.x), __fsub_rn(bo.w, bo.y));
     }
-    int n2 = 2;
-    while (n2 < n) n2 <<= 1;
-    for (int i = tid; i < n2; i += blockDim.x)
-      key2[i] = i < n ? ((static_cast<unsigned long long>(static_cast<unsigned>(sorted[i]) % nc) << 32) | static_cast<unsigned>(i)) : ~0ull;
     __syncthreads();
-    if (s_wide) fast = false;
-    if (fast) {
-      bitonic_sort(key2, n2);  // (class, score rank) ascending
-      for (int t = tid; t < n; t += blockDim.x) {
-        const unsigned c = static_cast<unsigned>(key2[t] >> 32);
-        if (t == 0 || static_cast<unsigned>(key2[t - 1] >> 32) != c) {
-          int a = t + 1, z = n;  // first index whose class differs (binary search on the sorted class field)
-          while (a < z) {
-            const int mid = (a + z) >> 1;
-            if (static_cast<unsigned>(key2[mid] >> 32) == c) a = mid + 1;
-            else z = mid;
+    {  // exclusive scan of the row lengths (two rows per thread)
+      const int e0 = 2 * tid, e1 = 2 * tid + 1;
+      const int v0 = e0 < n ? soff[e0] : 0, v1 = e1 < n ? soff[e1] : 0;
+      const int sum = v0 + v1;
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_scan[wid] = incl;
+      __syncthreads();
+      if (wid == 0) {
+        int v = lane < nwarp ? s_scan[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, v, o);
+          if (lane >= o) v += u;
+        }
+        if (lane < nwarp) s_scan[lane] = v;
+      }
+      __syncthreads();
+      const int base = incl - sum + (wid > 0 ? s_scan[wid - 1] : 0);
+      if (e0 < n) soff[e0] = base;
+      if (e1 < n) soff[e1] = base + v0;
+      if (tid == 0) soff[n] = s_scan[nwarp - 1];
+      __syncthreads();
+    }
+    if (soff[n] > kMaskWords) fast = false;  // block-uniform
+  }
+  if (fast) {
+    AY2_NMS_MARK(4);
+    const int nseg = s_nseg;
+    const int rounds = (s_maxseg + kRound - 1) / kRound;
+    for (int rd = 0; rd < rounds; ++rd) {
+      // (a) overlap words of this round's rows that are still alive: row t, word k covers the segment's 32-block
+      //     (q/32 + k), bits at or below q cleared
+      for (int t = wid; t < n; t += nwarp) {
+        const int t0 = st0[t];
+        const int q = t - t0;
+        if (q / kRound != rd) continue;
+        const int w0 = q >> 5;
+        if ((srem[t0 + (w0 << 5)] >> (q & 31)) & 1u) continue;  // suppressed in an earlier round: its row is never read
+        const int t1 = segend[t0];
+        const int o0 = soff[t], len = soff[t + 1] - o0;
+        const float4 ba = sbo[t];
+        const float aa = sarea[t];
+        for (int k = 0; k < len; ++k) {
+          const int cb = t0 + ((w0 + k) << 5);  // first row of the column block
+          unsigned word = 0;
+          if (srem[cb] != 0xffffffffu) {  // warp-uniform: some column of the block may still be alive
+            const int u = cb + lane;
+            const bool hit = u > t && u < t1 && iou_gt(ba, aa, sbo[u], sarea[u], thr);
+            word = __ballot_sync(0xffffffffu, hit);
           }
-          atomicMax(&s_maxseg, a - t);
-          fseg[atomicAdd(&s_nseg, 1)] = t;
+          if (lane == 0) masks[o0 + k] = word;
         }
       }
       __syncthreads();
-      if (s_maxseg > kMaxSeg) fast = false;
-    }
-  }
-  if (fast) {
-    const int nseg = s_nseg;
-    for (int sgi = wid; sgi < nseg; sgi += nwarp) {
-      const int t0 = fseg[sgi];
-      const unsigned c = static_cast<unsigned>(key2[t0] >> 32);
-      int t1 = t0 + 1;
-      while (t1 < n && static_cast<unsigned>(key2[t1] >> 32) == c) ++t1;  // segments are short (<= kMaxSeg)
-      for (int a = t0; a < t1; ++a) {
-        const int ia = static_cast<int>(static_cast<unsigned>(key2[a]));
-        if (fsupp[ia]) continue;  // warp-uniform: every lane reads the same byte
-        const float4 ba = fbo[ia];
-        const float aa = farea[ia];
-        for (int bb = a + 1 + lane; bb < t1; bb += 32) {
-          const int ib = static_cast<int>(static_cast<unsigned>(key2[bb]));
-          if (!fsupp[ib] && iou_gt(ba, aa, fbo[ib], farea[ib], thr)) fsupp[ib] = 1;
+      // (b) greedy resolution of the round, one warp per segment, 32 candidates per step
+      for (int sgi = wid; sgi < nseg; sgi += nwarp) {
+        const int t0 = fseg[sgi], t1 = segend[t0];
+        const int sl = t1 - t0, nw = (sl + 31) >> 5;
+        for (int wb = rd * (kRound / 32); wb < (rd + 1) * (kRound / 32) && wb < nw; ++wb) {
+          const int q = (wb << 5) + lane;
+          const bool valid = q < sl;
+          const unsigned remw = srem[t0 + (wb << 5)];
+          const int left = sl - (wb << 5);
+          unsigned avail = ~remw & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
+          const int myoff = valid ? soff[t0 + q] : 0;
+          // first word of a row == the word of its own block (rows skipped in (a) are not in `avail`)
+          const unsigned diag = (avail >> lane) & 1u ? masks[myoff] : 0u;
+          unsigned keep = 0;
+          while (avail) {  // warp-uniform
+            const int i = __ffs(avail) - 1;
+            keep |= 1u << i;
+            avail &= ~(1u << i);
+            avail &= ~__shfl_sync(0xffffffffu, diag, i);
+          }
+          if (valid && !((keep >> lane) & 1u)) ssupp[static_cast<unsigned>(key2[t0 + q])] = 1;
+          // OR the kept rows into the later blocks' suppressed bits: lane l owns words l and l + 32 of the segment
+          const bool own0 = lane > wb && lane < nw, own1 = lane + 32 > wb && lane + 32 < nw;
+          unsigned acc0 = 0, acc1 = 0;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const int base = __shfl_sync(0xffffffffu, myoff, i) - wb;  // masks[base + w] = word w of row i of the block
+            if ((keep >> i) & 1u) {                                      // warp-uniform
+              if (own0) acc0 |= masks[base + lane];
+              if (own1) acc1 |= masks[base + lane + 32];
+            }
+          }
+          if (own0 && acc0) srem[t0 + (lane << 5)] |= acc0;
+          if (own1 && acc1) srem[t0 + ((lane + 32) << 5)] |= acc1;
+          __syncwarp();
         }
-        __syncwarp();
       }
+      __syncthreads();
     }
-    __syncthreads();
+    AY2_NMS_MARK(5);
+    AY2_NMS_MARK(6);
     // compaction in score order: exclusive prefix count of kept flags
     const int per = (n + blockDim.x - 1) / blockDim.x;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     int cnt = 0;
-    for (int i = i0; i < i1; ++i) cnt += fsupp[i] ? 0 : 1;
+    for (int i = i0; i < i1; ++i) cnt += ssupp[i] ? 0 : 1;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -441,22 +622,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     __syncthreads();
     int k = incl - cnt + (wid > 0 ? s_scan[wid - 1] : 0);
     for (int i = i0; i < i1 && k < p.max_det; ++i) {
-      if (fsupp[i]) continue;
+      if (ssupp[i]) continue;
       const unsigned long long key = sorted[i];
       const unsigned idx = static_cast<unsigned>(key);
-      const int row = idx / nc;
-      const float4 r = load_xywh(src, b, row);
+      const float4 bx = rbox[i];
       float* o = out_det + ((long long)b * p.max_det + k) * 6;
-      o[0] = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
-      o[1] = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
-      o[2] = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
-      o[3] = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+      o[0] = bx.x;
+      o[1] = bx.y;
+      o[2] = bx.z;
+      o[3] = bx.w;
       o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
-      o[5] = static_cast<float>(idx - row * nc);
+      o[5] = static_cast<float>(idx % nc);
       ++k;
     }
     __syncthreads();
     if (tid == 0) out_count[b] = min(s_scan[nwarp - 1], p.max_det);
+    AY2_NMS_MARK(7);
+    if (trace && b == 0 && tid == 0) {
+      trace[8] = n;
+      trace[9] = s_nseg;
+      trace[10] = soff[n];
+    }
     return;
   }
   __syncthreads();
@@ -588,7 +774,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 
 constexpr size_t kNmsChunkBytes = sizeof(float4) * (2 * kChunk + kMaxDetCap) + sizeof(float) * (2 * kChunk + kMaxDetCap) +
                                   sizeof(int) * (3 * kChunk + kMaxDetCap) + sizeof(unsigned) * kChunk * kChunkWords;
-constexpr size_t kNmsFastBytes = (sizeof(float4) + sizeof(float) + sizeof(int) + 1 + sizeof(int)) * kFastN;
+constexpr size_t kNmsFastBytes = sizeof(float4) * kFastN + sizeof(float) * kFastN + sizeof(int) * (kFastN + 4) +
+                                 4 * sizeof(int) * kFastN + sizeof(unsigned) * kMaskWords + kFastN;
+static_assert(sizeof(unsigned long long) * kSortSmemKeys >= sizeof(unsigned long long) * 2 * kFastN + sizeof(float4) * kFastN,
+              "the key buffer holds the sorted keys, the (class, rank) keys and the segment-ordered boxes");
+static_assert(kFastN <= 2 * kNmsThreads && kRound % 32 == 0, "register bitonic sort: two keys per thread");
 constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys +
                                  (kNmsChunkBytes > kNmsFastBytes ? kNmsChunkBytes : kNmsFastBytes);
 
@@ -611,23 +801,27 @@ extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
          sizeof(unsigned) * (size_t)p->batch * (size_t)p->n;
 }
 
-static int nms_generate_candidates(const BoxSource& src, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
-                                   unsigned long long** keys_out, int** counts_out, int** overflow_out, cudaStream_t st) {
-  const size_t head = nms_head_bytes(p);
-  int* counts = static_cast<int*>(workspace);
-  int* overflow = counts + p->batch;
-  int* row_counts = overflow + 1;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + head);
-  const long long ks = key_stride_for(p);
-  unsigned* rows = reinterpret_cast<unsigned*>(keys + (size_t)p->batch * ks);
-  AY2_CHECK_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (2 * p->batch + 1), st));
-  nms_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, rows, row_counts);
+namespace ay2 {
+NmsWorkspaceView nms_workspace_view(const ay2_nms_params* p, void* workspace) {
+  NmsWorkspaceView v;
+  v.counts = static_cast<int*>(workspace);
+  v.overflow = v.counts + p->batch;
+  v.row_counts = v.overflow + 1;
+  v.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + nms_head_bytes(p));
+  v.key_stride = key_stride_for(p);
+  v.rows = reinterpret_cast<unsigned*>(v.keys + (size_t)p->batch * v.key_stride);
+  return v;
+}
+}  // namespace ay2
+
+static int nms_generate_candidates(const BoxSource& src, const ay2_nms_params* p, const uint8_t* class_mask,
+                                   const NmsWorkspaceView& v, cudaStream_t st) {
+  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * (2 * p->batch + 1), st));
+  nms_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, v.rows, v.row_counts);
   AY2_CHECK_LAUNCH();
-  nms_score_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, class_mask, rows, row_counts, keys, ks, counts);
+  nms_score_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, class_mask, v.rows, v.row_counts, v.keys, v.key_stride,
+                                                            v.counts);
   AY2_CHECK_LAUNCH();
-  *keys_out = keys;
-  *counts_out = counts;
-  *overflow_out = overflow;
   return AY2_OK;
 }
 
@@ -643,19 +837,37 @@ static int nms_common_checks(const ay2_nms_params* p, const void* workspace, siz
   return AY2_OK;
 }
 
-static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, unsigned long long* keys, long long ks,
-                                int* counts, int* overflow, float* out_det, int32_t* out_count, int32_t* overflow_flag,
-                                cudaStream_t st) {
+static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, const NmsWorkspaceView& v, float* out_det,
+                                int32_t* out_count, int32_t* overflow_flag, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     AY2_CHECK_CUDA(
         cudaFuncSetAttribute(nms_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
     attr_set = true;
   }
-  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, keys, ks, counts, out_det, out_count,
-                                                                     overflow);
+  // AY2_NMS_TRACE=1: clock64 stamps of image 0's phases (debugging aid; synchronises, never set in production)
+  static const bool want_trace = getenv("AY2_NMS_TRACE") != nullptr;
+  static long long* trace = nullptr;
+  if (want_trace && !trace) {
+    AY2_CHECK_CUDA(cudaMalloc(&trace, 16 * sizeof(long long)));
+    AY2_CHECK_CUDA(cudaMemset(trace, 0, 16 * sizeof(long long)));
+  }
+  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, v.keys, v.key_stride, v.counts, out_det,
+                                                                     out_count, v.overflow, trace);
   AY2_CHECK_LAUNCH();
-  if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (trace) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      long long h[16];
+      AY2_CHECK_CUDA(cudaStreamSynchronize(st));
+      AY2_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[ay2 nms trace] img0 n=%lld nseg=%lld mask_words=%lld | clocks: sort %lld, boxes %lld, class sort %lld, "
+              "segments+scan %lld, masks %lld, resolve %lld, emit %lld\n", h[8], h[9], h[10], h[1] - h[0], h[2] - h[1],
+              h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+    }
+  }
+  if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, v.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
   return AY2_OK;
 }
 
@@ -671,26 +883,20 @@ extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const
   src.pred = pred;
   src.n = p->n;
   src.no = p->no;
-  unsigned long long* keys;
-  int *counts, *overflow;
-  rc = nms_generate_candidates(src, p, class_mask, workspace, &keys, &counts, &overflow, st);
+  const NmsWorkspaceView v = nms_workspace_view(p, workspace);
+  rc = nms_generate_candidates(src, p, class_mask, v, st);
   if (rc != AY2_OK) return rc;
-  const long long ks = key_stride_for(p);
-  rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
+  rc = nms_sort_scan_launch(src, p, v, out_det, out_count, overflow_flag, st);
   if (rc != AY2_OK) return rc;
   count_launch(3);
   return AY2_OK;
 }
 
-extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_params* p, const uint8_t* class_mask,
-                                   void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
-                                   int32_t* overflow_flag, void* stream) {
-  AY2_REQUIRE(hl, "ay2_nms_from_logits: null level table");
-  int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
-  if (rc != AY2_OK) return rc;
+static int box_source_from_levels(const ay2_head_levels* hl, const ay2_nms_params* p, BoxSource* out) {
+  AY2_REQUIRE(hl, "ay2_nms: null level table");
   AY2_REQUIRE(hl->nl >= 1 && hl->nl <= AY2_NMS_MAX_LEVELS && hl->na >= 1 && hl->na <= AY2_NMS_MAX_ANCHORS,
-              "ay2_nms_from_logits: nl=%d na=%d unsupported", hl->nl, hl->na);
-  BoxSource src;
+              "ay2_nms: nl=%d na=%d unsupported", hl->nl, hl->na);
+  BoxSource& src = *out;
   memset(&src, 0, sizeof(src));
   src.no = p->no;
   src.nl = hl->nl;
@@ -713,13 +919,46 @@ extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_para
   src.row_off[hl->nl] = rows;
   src.n = rows;
   AY2_REQUIRE(rows == p->n, "level table covers %d rows but params.n = %d", rows, p->n);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned long long* keys;
-  int *counts, *overflow;
-  rc = nms_generate_candidates(src, p, class_mask, workspace, &keys, &counts, &overflow, st);
+  return AY2_OK;
+}
+
+extern "C" int ay2_nms_candidates_begin(const ay2_nms_params* p, void* workspace, size_t workspace_bytes, void* stream) {
+  AY2_REQUIRE(p && workspace, "ay2_nms_candidates_begin: null pointer");
+  AY2_REQUIRE(workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace too small (%zu < %zu)", workspace_bytes,
+              ay2_nms_workspace_bytes(p));
+  const NmsWorkspaceView v = nms_workspace_view(p, workspace);
+  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * (2 * p->batch + 1), static_cast<cudaStream_t>(stream)));
+  return AY2_OK;
+}
+
+extern "C" int ay2_nms_from_candidates(const ay2_head_levels* hl, const ay2_nms_params* p, void* workspace,
+                                       size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                                       void* stream) {
+  int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
   if (rc != AY2_OK) return rc;
-  const long long ks = key_stride_for(p);
-  rc = nms_sort_scan_launch(src, p, keys, ks, counts, overflow, out_det, out_count, overflow_flag, st);
+  BoxSource src;
+  rc = box_source_from_levels(hl, p, &src);
+  if (rc != AY2_OK) return rc;
+  rc = nms_sort_scan_launch(src, p, nms_workspace_view(p, workspace), out_det, out_count, overflow_flag,
+                            static_cast<cudaStream_t>(stream));
+  if (rc != AY2_OK) return rc;
+  count_launch(1);
+  return AY2_OK;
+}
+
+extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_params* p, const uint8_t* class_mask,
+                                   void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
+                                   int32_t* overflow_flag, void* stream) {
+  int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
+  if (rc != AY2_OK) return rc;
+  BoxSource src;
+  rc = box_source_from_levels(hl, p, &src);
+  if (rc != AY2_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const NmsWorkspaceView v = nms_workspace_view(p, workspace);
+  rc = nms_generate_candidates(src, p, class_mask, v, st);
+  if (rc != AY2_OK) return rc;
+  rc = nms_sort_scan_launch(src, p, v, out_det, out_count, overflow_flag, st);
   if (rc != AY2_OK) return rc;
   count_launch(3);
   return AY2_OK;

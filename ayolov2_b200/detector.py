@@ -23,7 +23,7 @@ class Detector:
     def __init__(self, model: nn.Module, batch: int, height: int = 640, width: int = 640, conf_thres: float = 0.25,
                  iou_thres: float = 0.45, multi_label: bool = False, agnostic: bool = False, max_det: int = 300,
                  in_dtype: torch.dtype = torch.uint8, device: Optional[torch.device] = None, want_raw: bool = False,
-                 dense_pred: bool = False) -> None:
+                 dense_pred: bool = False, fuse_candidates: bool = True) -> None:
         scale = 1.0 / 255.0 if in_dtype == torch.uint8 else 1.0
         self.engine = Engine(model, batch, height, width, in_dtype=in_dtype, scale=scale, want_raw=want_raw,
                              device=device, use_graph=False)
@@ -41,6 +41,15 @@ class Detector:
         self.dense_pred = dense_pred
         eng = self.engine
         self.levels = ops.make_head_levels(eng.head_logits, eng.na, eng.head_strides, eng.head_anchors_px)
+        # ... and the candidates themselves are scored by the detect convolutions' epilogues, from the output tile they
+        # hold in shared memory (ay2_conv_plan_set_head_candidates): the NMS kernel only sorts and suppresses
+        self.fused_candidates = fuse_candidates and not dense_pred and all(pl.desc.cout_pad <= 256 for pl in eng.head_plans)
+        if self.fused_candidates:
+            p = self.nms_ws.p
+            p.conf_thres = float(conf_thres)
+            p.multi_label = int(self.multi_label and nc > 1)
+            for pl, off in zip(eng.head_plans, eng.head_row_off):
+                pl.set_head_candidates(self.nms_ws, eng.na, off)
         # two input / output slots for the host pipeline
         self.dev_in = [torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) for _ in range(2)]
         self.host_out = [torch.zeros((batch, max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -57,11 +66,15 @@ class Detector:
     def _body(self) -> None:
         """Everything after the space-to-depth kernel (which reads a per-slot input buffer): convs, head, NMS."""
         eng = self.engine
+        if self.fused_candidates:
+            self.nms_ws.begin_candidates()
         for s in eng.b.steps:
             if s is eng.b.s2d_step or (not self.dense_pred and s in eng.decode_steps):
                 continue
             s()
-        if self.dense_pred:
+        if self.fused_candidates:
+            self.nms_ws.run_candidates(self.levels, eng.head_logits, self.iou_thres, agnostic=self.agnostic)
+        elif self.dense_pred:
             nms_device(eng.pred, self.conf_thres, self.iou_thres, agnostic=self.agnostic, multi_label=self.multi_label,
                        max_det=self.max_det, workspace=self.nms_ws)
         else:
@@ -69,8 +82,11 @@ class Detector:
             self.nms_ws.run_logits(self.levels, eng.head_logits, self.conf_thres, self.iou_thres, agnostic=self.agnostic)
 
     def launches_per_step(self) -> int:
-        n = len(self.engine.b.steps) + 3  # + NMS row filter, row scoring and sort/scan kernels
-        return n if self.dense_pred else n - len(self.engine.decode_steps)
+        n = len(self.engine.b.steps) - len(self.engine.decode_steps)
+        if self.fused_candidates:
+            return n + 1  # + the NMS sort/suppress kernel (candidates come from the detect convolutions)
+        # + NMS row filter, row scoring and sort/scan kernels (+ the dense decode kernels)
+        return n + 3 + (len(self.engine.decode_steps) if self.dense_pred else 0)
 
     def run_device(self, img: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """img: CUDA NCHW tensor of the detector's dtype. Asynchronous; returns (det [B,max_det,6], count [B])."""

@@ -377,11 +377,15 @@ class Engine:
         self.na, self.no = na, no
         self.decode_steps: List[Callable[[], None]] = []
         self.head_logits: List[ActView] = []
+        self.head_plans: List[ConvPlan] = []  # the detect convolutions (Detector arms their candidate epilogue)
+        self.head_row_off: List[int] = []
         self.head_strides = [float(s) for s in m.stride]
         self.head_anchors_px = [m.anchor_grid[i].detach().float().reshape(-1, 2).tolist() for i in range(len(xs))]
         for i, (conv, x) in enumerate(zip(m.conv, xs)):
             logits = b.new_act(x.H, x.W, _round_up(na * no, 16))
             b.conv2d(x, logits, conv.weight, conv.bias, None, 1e-3, ACT_NONE, 1, 0)
+            self.head_plans.append(b.plans[-1])
+            self.head_row_off.append(off)
             raw = torch.zeros((self.B, na, x.H, x.W, no), dtype=torch.float32, device=self.device) if want_raw else None
             if raw is not None:
                 self.raw.append(raw)

@@ -134,6 +134,20 @@ class ConvPlan:
         _lib.check(self._lib.ay2_conv_plan_run(self._h, stream if stream is not None else _lib.current_stream_ptr()),
                    "ay2_conv_plan_run")
 
+    def set_head_candidates(self, ws: Optional["NmsWorkspace"], na: int = 0, row_off: int = 0,
+                            class_mask: Optional[torch.Tensor] = None) -> None:
+        """Detect-head plan: also append this level's NMS candidates to `ws` on every run (ws.p carries conf_thres,
+        multi_label, max_candidates). ws=None switches it off."""
+        if ws is None:
+            _lib.check(self._lib.ay2_conv_plan_set_head_candidates(self._h, None, 0, 0, None, None, 0),
+                       "ay2_conv_plan_set_head_candidates")
+            self._cand_keep = None
+            return
+        self._cand_keep = (ws, class_mask)
+        _lib.check(self._lib.ay2_conv_plan_set_head_candidates(self._h, C.byref(ws.p), na, row_off, _lib.ptr(class_mask),
+                                                               ws.ws.data_ptr(), ws.ws.numel()),
+                   "ay2_conv_plan_set_head_candidates")
+
     def run_reference_simt(self) -> None:
         """Same math on CUDA cores (test infrastructure)."""
         _lib.check(self._lib.ay2_conv_reference_simt(C.byref(self.desc), self.x.ptr(), self.w.data_ptr(),
@@ -221,6 +235,25 @@ class NmsWorkspace:
                                                    self.ws.numel(), self.out.data_ptr(), self.count.data_ptr(),
                                                    self.overflow.data_ptr(), _lib.current_stream_ptr()),
                    "ay2_nms_from_logits")
+
+
+    def begin_candidates(self) -> None:
+        """Zero the per-image candidate counters; the detect-head convolutions that follow append candidates
+        (ConvPlan.set_head_candidates), run_candidates() finishes the step."""
+        _lib.check(_lib.load().ay2_nms_candidates_begin(C.byref(self.p), self.ws.data_ptr(), self.ws.numel(),
+                                                        _lib.current_stream_ptr()), "ay2_nms_candidates_begin")
+
+    def run_candidates(self, levels: "HeadLevels", keep, iou_thres: float, agnostic: bool = False, max_nms: int = 30000,
+                       max_wh: float = 4096.0) -> None:
+        """Sort + suppression + output over the candidates the head convolutions produced (ay2_nms_from_candidates).
+        conf_thres / multi_label are the ones in self.p when the plans were armed."""
+        p = self.p
+        p.iou_thres = float(iou_thres)
+        p.agnostic, p.max_nms, p.max_wh = int(agnostic), int(max_nms), float(max_wh)
+        self._keepalive = keep
+        _lib.check(_lib.load().ay2_nms_from_candidates(C.byref(levels), C.byref(p), self.ws.data_ptr(), self.ws.numel(),
+                                                       self.out.data_ptr(), self.count.data_ptr(), self.overflow.data_ptr(),
+                                                       _lib.current_stream_ptr()), "ay2_nms_from_candidates")
 
 
 def make_head_levels(logits: Sequence[ActView], na: int, strides: Sequence[float], anchors_px: Sequence[Sequence[Sequence[float]]]) -> HeadLevels:
@@ -349,7 +382,10 @@ def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):
             kws = sorted([k for k in range(kw) if (k - pad - px) % 2 == 0], key=lambda k: (px + pad - k) // 2)
             offs_x = [(px + pad - k) // 2 for k in kws]
             assert offs_y == list(range(offs_y[0], offs_y[0] + len(khs))) and offs_x == list(range(offs_x[0], offs_x[0] + len(kws)))
-            sub = w[:, :, khs][:, :, :, kws]  # (cout, cin, len(khs), len(kws)), taps ordered by input offset
+            # taps ordered by input offset == kernel index descending in steps of 2; slices + flip only (no index tensors:
+            # this runs inside CUDA-graph capture, where a host->device index copy is illegal)
+            assert khs == list(range(khs[0], khs[-1] - 1, -2)) and kws == list(range(kws[0], kws[-1] - 1, -2))
+            sub = w[:, :, khs[-1]:khs[0] + 1:2, kws[-1]:kws[0] + 1:2].flip(2, 3)  # (cout, cin, len(khs), len(kws))
             specs.append((sub.permute(1, 0, 2, 3).contiguous(), len(khs), len(kws), -offs_y[0], -offs_x[0], (py, px)))
     return specs
 

@@ -433,8 +433,17 @@ class TrainEngine:
         if st == 1:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            try:
+                with torch.cuda.graph(g):
+                    body()
+            except Exception as e:  # capture is an optimisation of the launch path only: keep training, say so loudly
+                import warnings
+
+                warnings.warn(f"TrainEngine: CUDA-graph capture of '{key}' failed ({e}); running the kernels eagerly")
+                torch.cuda.synchronize()
+                self.use_graph = False
                 body()
+                return
             self._graphs[key] = g
             self._gstate[key] = 2
         self._graphs[key].replay()

@@ -169,6 +169,22 @@ int ay2_nms_from_logits(const ay2_head_levels* levels, const ay2_nms_params* p, 
                         void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
                         int32_t* overflow_flag, void* stream);
 
+/* Candidate generation fused into the detect-head convolutions (the producing kernel): after
+ * ay2_conv_plan_set_head_candidates, every run of that plan also scores its output tile for NMS candidates
+ * (metrics.py:313-364: obj > conf, conf_c = cls_c * obj, best class or multi_label) and appends the 64-bit keys to
+ * the NMS workspace, so no kernel re-reads the logits to find candidates. One step is then
+ *   ay2_nms_candidates_begin (zeroes the per-image counters)  ->  the head convolutions of every level, any order
+ *   ->  ay2_nms_from_candidates (sort + greedy suppression + output; reads boxes of the survivors from the logits).
+ * `p` carries conf_thres / multi_label / max_candidates / batch / n / no (the values the NMS call will use);
+ * `row_off` is the level's first row in the reference's cat order (sum over earlier levels of na*ny*nx). The plan
+ * must produce all na*no channels in one N tile (cout <= 256). Pass p = NULL to switch the fusion off.
+ * Results are bit-identical to ay2_nms_from_logits on the same logits. */
+int ay2_conv_plan_set_head_candidates(ay2_conv_plan* plan, const ay2_nms_params* p, int32_t na, int32_t row_off,
+                                      const uint8_t* class_mask, void* nms_workspace, size_t workspace_bytes);
+int ay2_nms_candidates_begin(const ay2_nms_params* p, void* workspace, size_t workspace_bytes, void* stream);
+int ay2_nms_from_candidates(const ay2_head_levels* levels, const ay2_nms_params* p, void* workspace, size_t workspace_bytes,
+                            float* out_det, int32_t* out_count, int32_t* overflow_flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Detection loss forward + analytic backward: replaces scripts/loss/losses.py:168-391 (ComputeLoss.__call__,
  * build_targets) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU) for the default configuration

@@ -76,14 +76,17 @@ def test_fuse_invariance():
 
 
 @pytest.mark.parametrize("multi_label", [False, True])
-def test_fused_head_nms_equals_dense_path(multi_label):
-    """Detector's fused head (NMS straight from the bf16 logits, ay2_nms_from_logits) must select exactly what
-    ay2_head_decode + ay2_nms_batched select: same arithmetic, no dense (B, 25200, 85) tensor."""
+@pytest.mark.parametrize("hw", [(320, 320), (352, 288)])
+def test_fused_head_nms_equals_dense_path(multi_label, hw):
+    """Detector's fused head must select exactly what ay2_head_decode + ay2_nms_batched select (same arithmetic, no
+    dense (B, 25200, 85) tensor), both with the candidates scored by the detect convolutions' epilogues
+    (ay2_conv_plan_set_head_candidates + ay2_nms_from_candidates) and by the stand-alone kernels
+    (ay2_nms_from_logits). 352x288 gives 11x9 / 22x18 / 44x36 maps: output tiles overhang the image."""
     from ayolov2_b200 import synth
     from ayolov2_b200.detector import Detector
 
     model = synth.build_model("yolov5s", seed=2).cuda()
-    B, H, W = 3, 320, 320
+    B, (H, W) = 3, hw
     img = torch.randint(0, 256, (B, 3, H, W), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
     with torch.no_grad():
         _, raw = model(img.cuda().float() / 255.0)
@@ -91,12 +94,22 @@ def test_fused_head_nms_equals_dense_path(multi_label):
     model.invalidate_engine()
     kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=multi_label, in_dtype=torch.uint8)
     fused = Detector(model, B, H, W, **kw)
+    logits = Detector(model, B, H, W, fuse_candidates=False, **kw)
     dense = Detector(model, B, H, W, dense_pred=True, **kw)
+    assert fused.fused_candidates and not logits.fused_candidates
     a = fused.detect(img.pin_memory())
+    a2 = fused.detect(img.pin_memory())  # graph replay: the counters are re-zeroed inside the graph
+    l = logits.detect(img.pin_memory())
     b = dense.detect(img.pin_memory())
     assert sum(x.shape[0] for x in a) > 50, "calibration should produce detections"
-    for x, y in zip(a, b):
+    for x, x2, y, z in zip(a, a2, b, l):
         assert x.shape == y.shape and torch.equal(x, y)
+        assert torch.equal(x, x2) and torch.equal(z, y)
+    # the candidate sets themselves (unordered) are identical, not just the survivors
+    nb = fused.nms_ws.p.batch
+    ca = fused.nms_ws.ws[: 4 * nb].view(torch.int32).cpu()
+    cl = logits.nms_ws.ws[: 4 * nb].view(torch.int32).cpu()
+    assert torch.equal(ca, cl) and int(ca.sum()) > 0
 
 
 def test_tucker_decomposed_forward_matches_oracle():

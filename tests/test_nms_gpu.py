@@ -63,3 +63,41 @@ def test_nms_paths_agree_wide_boxes_and_single_class():
     _cmp(one, conf_thres=0.25, iou_thres=0.45)
     many = nms_oracle.synth_predictions(1, n=6000, seed=7, cand_frac=0.9)  # > 4096 candidates: general path
     _cmp(many, conf_thres=0.25, iou_thres=0.45)
+
+
+def test_nms_segmented_rounds_and_fallbacks():
+    """The segmented bit-matrix path: few classes -> long segments resolved over several lazy rounds; agnostic ->
+    one segment; a segment whose triangular masks exceed the shared-memory budget hands over to the chunked scan."""
+    from oracle import nms_oracle
+
+    few = nms_oracle.synth_predictions(3, n=2400, nc=3, seed=11, cand_frac=0.7, clusters=12)  # ~1700 candidates, 3 classes
+    _cmp(few, conf_thres=0.25, iou_thres=0.45)
+    _cmp(few, conf_thres=0.25, iou_thres=0.6, max_det=50)
+    agn = nms_oracle.synth_predictions(2, n=1200, seed=12, cand_frac=0.75, clusters=30)  # ~900 candidates, one segment
+    _cmp(agn, conf_thres=0.25, iou_thres=0.45, agnostic=True)
+    big = nms_oracle.synth_predictions(2, n=2400, nc=1, seed=13, cand_frac=0.8, clusters=40)  # one ~1900-row segment
+    _cmp(big, conf_thres=0.25, iou_thres=0.45)
+
+
+def test_nms_iou_threshold_sliver():
+    """Pairs whose IoU sits within a few ulp of the threshold take the exact-division branch of the division-free
+    filter: nested boxes with IoU = area ratio ~ iou_thres, swept in 1-ulp steps around it."""
+    import numpy as np
+
+    thr = 0.45
+    n = 384  # 768 boxes, one segment (positions leave the max_wh window): 9.6k mask words, the bit-matrix path
+    pred = torch.zeros(1, 2 * n, 6)
+    base = torch.tensor([320.0, 320.0])
+    w = 200.0
+    for i in range(n):
+        # outer box (score high) and an inner box whose area ratio is thr * (1 + (i - n/2) * 2^-24)
+        ratio = np.float64(thr) * (1.0 + (i - n // 2) * 2.0 ** -24)
+        iw = np.float32(w * np.sqrt(ratio))
+        c = base + torch.tensor([float(i % 32) * 1300.0, float(i // 32) * 1300.0])  # far apart: pairs do not interact
+        pred[0, 2 * i, :4] = torch.tensor([c[0], c[1], w, w])
+        pred[0, 2 * i + 1, :4] = torch.tensor([c[0], c[1], float(iw), float(iw)])
+        pred[0, 2 * i, 4], pred[0, 2 * i + 1, 4] = 0.9, 0.8
+    pred[0, :, 5] = 1.0
+    _cmp(pred, max_det=1000, conf_thres=0.25, iou_thres=thr)
+    _cmp(pred, max_det=1000, conf_thres=0.25, iou_thres=float(np.float32(thr)))
+    _cmp(pred[:, :256], conf_thres=0.25, iou_thres=thr, agnostic=True)
