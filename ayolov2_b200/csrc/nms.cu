@@ -32,9 +32,10 @@ constexpr int kSortSmemKeys = 8192;
 constexpr int kChunk = 256;
 constexpr int kChunkWords = kChunk / 32;
 constexpr int kMaxDetCap = 1024;
-constexpr int kFastN = 2048;         // segmented bit-matrix path: at most this many candidates per image ...
-constexpr int kMaskWords = 16384;    // ... and this many 32-bit words of upper-triangular overlap masks (64 KB)
-constexpr int kRound = 64;           // candidates of a segment resolved per round (multiple of 32)
+constexpr int kFastN = 2048;         // segmented path: at most this many candidates per image
+constexpr int kCountNc = 128;        // counting sort by class up to this many classes (bitonic sort above)
+constexpr int kGroups = 4;           // warp groups that resolve multi-block segments concurrently ...
+constexpr int kGroupWarps = 8;       // ... of this many warps each (kGroups * kGroupWarps * 32 == kNmsThreads)
 
 // Per-warp staging of candidate keys in shared memory: one global atomicAdd per flush instead of one per candidate
 // (2,800 same-address atomics per image serialise in L2 at ~70 ns each: 0.2 ms; staged: ~30 per image).
@@ -92,6 +93,10 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const flo
   if (fin && inter > __fmul_rn(uni, t.hi)) return true;
   if (fin && inter < __fmul_rn(uni, t.lo)) return false;
   return __fdiv_rn(inter, uni) > t.thr;
+}
+
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 template <typename Ptr>
@@ -404,88 +409,187 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   if (n > p.max_nms) n = p.max_nms;
   const IouThr thr = make_iou_thr(p.iou_thres);
 
-  // ---------------------------------------------------------------- segmented bit-matrix path (n <= kFastN)
+  // ---------------------------------------------------------------- segmented path (n <= kFastN)
   // With per-class box offsets (metrics.py:383-384) boxes of different classes cannot intersect as long as every
   // box lies inside a max_wh-wide window (checked below; exact, not an approximation), so greedy NMS decomposes
-  // into independent per-class greedy scans. Candidates are re-sorted by (class, score rank) into segments (one
-  // segment for everything when agnostic or when a box leaves the window). Each segment is resolved in rounds of
-  // kRound candidates: all warps build the upper-triangular overlap words of the round's rows that are still alive
-  // (32 IoU tests + a ballot per word; words whose 32 columns are already suppressed are skipped), then one warp per
-  // segment resolves the round's greedy order 32 candidates at a time and ORs the kept rows into the segment's
-  // suppressed bits. Survivors are compacted in global score order -- exactly the rows, in exactly the order, of the
-  // sequential reference; the laziness only skips tests whose outcome cannot matter.
+  // into independent per-class greedy scans. Candidates are re-ordered by (class, score rank) into segments (one
+  // segment for everything when agnostic or when a box leaves the window) and each segment is resolved 32
+  // candidates (one block) at a time:
+  //   D. all warps: for every block, which earlier candidates of the same block overlap each candidate (<= 31 tests);
+  //   S. per block, in order: every candidate is tested against the segment's kept list so far (the only tests
+  //      whose outcome can matter), then one warp resolves the block's internal greedy order from D's bits and
+  //      appends the survivors to the kept list. One-block segments need one warp; longer ones are shared out to
+  //      four 8-warp groups (the kept list is split over the group's warps).
+  // Survivors are compacted in global score order -- exactly the rows, in exactly the order, of the sequential
+  // reference. A segment stops once it holds max_det survivors: its later rows cannot reach the output.
   unsigned long long* key2 = skeys + kFastN;                                    // [kFastN]  (class, rank) keys
   float4* sbo = reinterpret_cast<float4*>(skeys + 2 * kFastN);                  // [kFastN]  offset boxes, segment order
   uint8_t* fr = reinterpret_cast<uint8_t*>(skeys + kSortSmemKeys);              // overlay of the chunk-path region
   float4* rbox = reinterpret_cast<float4*>(fr);                                 // [kFastN] output boxes, score order
   float* sarea = reinterpret_cast<float*>(rbox + kFastN);                       // [kFastN]
-  int* soff = reinterpret_cast<int*>(sarea + kFastN);                           // [kFastN + 4] mask row offsets
-  int* st0 = soff + kFastN + 4;                                                 // [kFastN] segment start of row t
+  int* st0 = reinterpret_cast<int*>(sarea + kFastN);                            // [kFastN] segment start of row t
   int* segend = st0 + kFastN;                                                   // [kFastN] indexed by segment start
-  int* fseg = segend + kFastN;                                                  // [kFastN] list of segment starts
-  unsigned* srem = reinterpret_cast<unsigned*>(fseg + kFastN);                  // [kFastN] suppressed bits of a 32-block,
-                                                                                //          indexed by the block's first row
-  unsigned* masks = srem + kFastN;                                              // [kMaskWords]
-  unsigned char* ssupp = reinterpret_cast<unsigned char*>(masks + kMaskWords);  // [kFastN] by score rank
-  __shared__ int s_nseg, s_maxseg, s_scan[kNmsThreads / 32];
+  int* fseg = segend + kFastN;                                                  // [kFastN] one-block segments from the
+                                                                                //   front, longer ones from the back
+  int* klist = fseg + kFastN;                                                   // [kFastN] kept rows, per segment at t0
+  unsigned* sdin = reinterpret_cast<unsigned*>(klist + kFastN);                 // [kFastN] in-block overlap bits
+  int* blist = reinterpret_cast<int*>(sdin + kFastN);                           // [kFastN] first rows of all blocks
+  unsigned char* ssupp = reinterpret_cast<unsigned char*>(blist + kFastN);      // [kFastN] by score rank
+  unsigned short* ccnt = reinterpret_cast<unsigned short*>(klist);              // [64][kCountNc] counting-sort table
+                                                                                //   (klist + sdin, before they are used)
+  __shared__ int s_nsmall, s_nbig, s_nblk, s_bignext, s_scan[kNmsThreads / 32], s_cstart[kCountNc], s_ctot[kCountNc];
+  __shared__ int s_gseg[kGroups], s_gk[kGroups];
+  __shared__ unsigned s_gsup[kGroups];
   bool fast = fits_fast;
   if (fast) {
     if (tid == 0) {
-      s_nseg = 0;
-      s_maxseg = 0;
+      s_nsmall = 0;
+      s_nbig = 0;
+      s_nblk = 0;
+      s_bignext = 0;
     }
+    if (tid < kGroups) s_gsup[tid] = 0;
     const float lo = -0.25f * p.max_wh, hi = 0.75f * p.max_wh - 2.0f;
-    for (int i = tid; i < n; i += blockDim.x) {
-      const unsigned idx = static_cast<unsigned>(sorted[i]);
-      const float4 r = load_xywh(src, b, idx / nc);
-      // general.py:316-319 with ratio = wh = 1, pad = 0  (1*1*(x -+ w/2) + 0)
-      float4 bx;
-      bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
-      bx.y = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
-      bx.z = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
-      bx.w = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
-      if (!(bx.x >= lo && bx.y >= lo && bx.z <= hi && bx.w <= hi)) s_wide = 1;
-      rbox[i] = bx;
-      ssupp[i] = 0;
-      srem[i] = 0;
+    {  // both rows of a thread are fetched before either is used: the gather is pure latency
+      float4 rr[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tid + h * kNmsThreads;
+        if (i < n) rr[h] = load_xywh(src, b, static_cast<unsigned>(sorted[i]) / nc);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tid + h * kNmsThreads;
+        if (i < n) {
+          const float4 r = rr[h];
+          // general.py:316-319 with ratio = wh = 1, pad = 0  (1*1*(x -+ w/2) + 0)
+          float4 bx;
+          bx.x = __fadd_rn(__fsub_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+          bx.y = __fadd_rn(__fsub_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+          bx.z = __fadd_rn(__fadd_rn(r.x, __fmul_rn(r.z, 0.5f)), 0.0f);
+          bx.w = __fadd_rn(__fadd_rn(r.y, __fmul_rn(r.w, 0.5f)), 0.0f);
+          if (!(bx.x >= lo && bx.y >= lo && bx.z <= hi && bx.w <= hi)) s_wide = 1;
+          rbox[i] = bx;
+          ssupp[i] = 0;
+        }
+      }
     }
     __syncthreads();
     AY2_NMS_MARK(2);
     const bool partition = !p.agnostic && !s_wide;
-    int n2 = 2;
-    while (n2 < n) n2 <<= 1;
-    for (int i = tid; i < n2; i += blockDim.x) {
-      const unsigned cls = partition && i < n ? static_cast<unsigned>(sorted[i]) % nc : 0u;
-      key2[i] = i < n ? ((static_cast<unsigned long long>(cls) << 32) | static_cast<unsigned>(i)) : ~0ull;
+    // ---- (class, rank) order -> key2[t] (low word = score rank), st0[t], segend[], segment lists
+    auto add_segment = [&](int t0, int t1) {
+      segend[t0] = t1;
+      if (t1 - t0 <= 32) fseg[atomicAdd(&s_nsmall, 1)] = t0;
+      else fseg[kFastN - 1 - atomicAdd(&s_nbig, 1)] = t0;
+    };
+    if (!partition) {
+      for (int t = tid; t < n; t += blockDim.x) {
+        key2[t] = static_cast<unsigned>(t);
+        st0[t] = 0;
+      }
+      if (tid == 0) add_segment(0, n);
+      __syncthreads();
+    } else if (nc <= kCountNc) {
+      // stable counting sort by class: rank inside a 32-candidate chunk by __match_any_sync, chunk totals per class in
+      // a [chunk][class] table, running sum over chunks per class, exclusive scan over classes
+      const int chunks = (n + 31) >> 5;
+      for (int i = tid; i < chunks * kCountNc / 2; i += blockDim.x) reinterpret_cast<unsigned*>(ccnt)[i] = 0u;
+      __syncthreads();
+      unsigned mycls[2];
+      int myrank[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tid + h * kNmsThreads;
+        const bool valid = i < n;
+        mycls[h] = valid ? static_cast<unsigned>(sorted[i]) % nc : 0xffffffffu;
+        if ((i & ~31) < n) {  // warp-uniform: the chunk exists
+          const unsigned peers = __match_any_sync(0xffffffffu, mycls[h]);
+          myrank[h] = __popc(peers & ((1u << lane) - 1u));
+          if (valid && lane == __ffs(peers) - 1) ccnt[(i >> 5) * kCountNc + mycls[h]] = static_cast<unsigned short>(__popc(peers));
+        }
+      }
+      __syncthreads();
+      if (tid < nc) {
+        int run = 0;
+        for (int w = 0; w < chunks; ++w) {
+          const int v = ccnt[w * kCountNc + tid];
+          ccnt[w * kCountNc + tid] = static_cast<unsigned short>(run);
+          run += v;
+        }
+        s_ctot[tid] = run;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        constexpr int per = kCountNc / 32;
+        int v[per], sum = 0;
+#pragma unroll
+        for (int e = 0; e < per; ++e) {
+          const int c = lane * per + e;
+          v[e] = c < nc ? s_ctot[c] : 0;
+          sum += v[e];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += u;
+        }
+        int base = incl - sum;
+#pragma unroll
+        for (int e = 0; e < per; ++e) {
+          const int c = lane * per + e;
+          if (c < nc) {
+            s_cstart[c] = base;
+            if (v[e] > 0) add_segment(base, base + v[e]);
+          }
+          base += v[e];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tid + h * kNmsThreads;
+        if (i < n) {
+          const int t0 = s_cstart[mycls[h]];
+          const int pos = t0 + ccnt[(i >> 5) * kCountNc + mycls[h]] + myrank[h];
+          key2[pos] = (static_cast<unsigned long long>(mycls[h]) << 32) | static_cast<unsigned>(i);
+          st0[pos] = t0;
+        }
+      }
+      __syncthreads();
+    } else {
+      int n2 = 2;
+      while (n2 < n) n2 <<= 1;
+      for (int i = tid; i < n2; i += blockDim.x)
+        key2[i] = i < n ? ((static_cast<unsigned long long>(static_cast<unsigned>(sorted[i]) % nc) << 32) | static_cast<unsigned>(i)) : ~0ull;
+      __syncthreads();
+      bitonic_sort_regs(key2, n2);  // (class, score rank) ascending
+      for (int t = tid; t < n; t += blockDim.x) {
+        const unsigned c = static_cast<unsigned>(key2[t] >> 32);
+        int a = 0, z = t;  // first index of class c
+        while (a < z) {
+          const int mid = (a + z) >> 1;
+          if (static_cast<unsigned>(key2[mid] >> 32) < c) a = mid + 1;
+          else z = mid;
+        }
+        st0[t] = a;
+        if (t == a) {
+          int a2 = t + 1, z2 = n;  // first index whose class differs
+          while (a2 < z2) {
+            const int mid = (a2 + z2) >> 1;
+            if (static_cast<unsigned>(key2[mid] >> 32) == c) a2 = mid + 1;
+            else z2 = mid;
+          }
+          add_segment(t, a2);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (partition) bitonic_sort_regs(key2, n2);  // (class, score rank) ascending
     AY2_NMS_MARK(3);
-    // per row: its segment, offset box, and the length of its mask row (words from its own 32-block to the segment end)
+    // ---- segment-ordered offset boxes, block list
     for (int t = tid; t < n; t += blockDim.x) {
-      const unsigned c = static_cast<unsigned>(key2[t] >> 32);
       const int i = static_cast<int>(static_cast<unsigned>(key2[t]));
-      int a = 0, z = t;  // first index of class c
-      while (a < z) {
-        const int mid = (a + z) >> 1;
-        if (static_cast<unsigned>(key2[mid] >> 32) < c) a = mid + 1;
-        else z = mid;
-      }
-      const int t0 = a;
-      a = t + 1, z = n;  // first index whose class differs
-      while (a < z) {
-        const int mid = (a + z) >> 1;
-        if (static_cast<unsigned>(key2[mid] >> 32) == c) a = mid + 1;
-        else z = mid;
-      }
-      const int t1 = a;
-      if (t == t0) {
-        segend[t0] = t1;
-        fseg[atomicAdd(&s_nseg, 1)] = t0;
-        atomicMax(&s_maxseg, t1 - t0);
-      }
-      st0[t] = t0;
-      soff[t] = ((t1 - t0 + 31) >> 5) - ((t - t0) >> 5);
       const float4 bx = rbox[i];
       const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(static_cast<unsigned>(sorted[i]) % nc), p.max_wh);
       float4 bo;
@@ -495,107 +599,107 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       bo.w = __fadd_rn(bx.w, off);
       sbo[t] = bo;
       sarea[t] = __fmul_rn(__fsub_rn(bo.z, bo.x), __fsub_rn(bo.w, bo.y));
+      if (((t - st0[t]) & 31) == 0) blist[atomicAdd(&s_nblk, 1)] = t;
     }
     __syncthreads();
-    {  // exclusive scan of the row lengths (two rows per thread)
-      const int e0 = 2 * tid, e1 = 2 * tid + 1;
-      const int v0 = e0 < n ? soff[e0] : 0, v1 = e1 < n ? soff[e1] : 0;
-      const int sum = v0 + v1;
-      int incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s_scan[wid] = incl;
-      __syncthreads();
-      if (wid == 0) {
-        int v = lane < nwarp ? s_scan[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int u = __shfl_up_sync(0xffffffffu, v, o);
-          if (lane >= o) v += u;
-        }
-        if (lane < nwarp) s_scan[lane] = v;
-      }
-      __syncthreads();
-      const int base = incl - sum + (wid > 0 ? s_scan[wid - 1] : 0);
-      if (e0 < n) soff[e0] = base;
-      if (e1 < n) soff[e1] = base + v0;
-      if (tid == 0) soff[n] = s_scan[nwarp - 1];
-      __syncthreads();
-    }
-    if (soff[n] > kMaskWords) fast = false;  // block-uniform
-  }
-  if (fast) {
     AY2_NMS_MARK(4);
-    const int nseg = s_nseg;
-    const int rounds = (s_maxseg + kRound - 1) / kRound;
-    for (int rd = 0; rd < rounds; ++rd) {
-      // (a) overlap words of this round's rows that are still alive: row t, word k covers the segment's 32-block
-      //     (q/32 + k), bits at or below q cleared
-      for (int t = wid; t < n; t += nwarp) {
-        const int t0 = st0[t];
-        const int q = t - t0;
-        if (q / kRound != rd) continue;
-        const int w0 = q >> 5;
-        if ((srem[t0 + (w0 << 5)] >> (q & 31)) & 1u) continue;  // suppressed in an earlier round: its row is never read
-        const int t1 = segend[t0];
-        const int o0 = soff[t], len = soff[t + 1] - o0;
-        const float4 ba = sbo[t];
-        const float aa = sarea[t];
-        for (int k = 0; k < len; ++k) {
-          const int cb = t0 + ((w0 + k) << 5);  // first row of the column block
-          unsigned word = 0;
-          if (srem[cb] != 0xffffffffu) {  // warp-uniform: some column of the block may still be alive
-            const int u = cb + lane;
-            const bool hit = u > t && u < t1 && iou_gt(ba, aa, sbo[u], sarea[u], thr);
-            word = __ballot_sync(0xffffffffu, hit);
-          }
-          if (lane == 0) masks[o0 + k] = word;
-        }
+    // ---- D: in-block overlaps. sdin[c] bit r <=> row (block start + r) precedes c in its block and IoU > thr
+    const int nblk = s_nblk;
+    for (int bi = wid; bi < nblk; bi += nwarp) {
+      const int tb = blist[bi];
+      const int t1 = segend[st0[tb]];
+      const int c = tb + lane;
+      const bool valid = c < t1;
+      const float4 bc = valid ? sbo[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float ac = valid ? sarea[c] : 0.f;
+      const int rows = min(31, t1 - tb - 1);
+      unsigned din = 0;
+      for (int r = 0; r < rows; ++r) {
+        const bool hit = valid && lane > r && iou_gt(sbo[tb + r], sarea[tb + r], bc, ac, thr);
+        din |= (hit ? 1u : 0u) << r;
       }
-      __syncthreads();
-      // (b) greedy resolution of the round, one warp per segment, 32 candidates per step
-      for (int sgi = wid; sgi < nseg; sgi += nwarp) {
-        const int t0 = fseg[sgi], t1 = segend[t0];
-        const int sl = t1 - t0, nw = (sl + 31) >> 5;
-        for (int wb = rd * (kRound / 32); wb < (rd + 1) * (kRound / 32) && wb < nw; ++wb) {
-          const int q = (wb << 5) + lane;
-          const bool valid = q < sl;
-          const unsigned remw = srem[t0 + (wb << 5)];
-          const int left = sl - (wb << 5);
-          unsigned avail = ~remw & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
-          const int myoff = valid ? soff[t0 + q] : 0;
-          // first word of a row == the word of its own block (rows skipped in (a) are not in `avail`)
-          const unsigned diag = (avail >> lane) & 1u ? masks[myoff] : 0u;
+      if (valid) sdin[c] = din;
+    }
+    __syncthreads();
+    AY2_NMS_MARK(5);
+    // ---- S (one-block segments): one warp each
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int nsmall = s_nsmall, nbig = s_nbig;
+    for (int si = wid; si < nsmall; si += nwarp) {
+      const int t0 = fseg[si];
+      const int sl = segend[t0] - t0;
+      const bool valid = lane < sl;
+      const unsigned din = valid ? sdin[t0 + lane] : 0u;
+      unsigned avail = sl >= 32 ? 0xffffffffu : ((1u << sl) - 1u);
+      unsigned keep = 0;
+      while (avail) {  // warp-uniform
+        const int i = __ffs(avail) - 1;
+        keep |= 1u << i;
+        avail &= ~(1u << i);
+        avail &= ~__ballot_sync(0xffffffffu, (din >> i) & 1u);
+      }
+      if (valid && !((keep >> lane) & 1u)) ssupp[static_cast<unsigned>(key2[t0 + lane])] = 1;
+    }
+    // ---- S (longer segments): 8-warp groups take segments from the list; per block: test against the kept list
+    //      (split over the group's warps), then warp 0 of the group resolves the block and extends the list
+    const int grp = wid / kGroupWarps, gw = wid % kGroupWarps;
+    for (;;) {
+      if (gw == 0 && lane == 0) {
+        s_gseg[grp] = atomicAdd(&s_bignext, 1);
+        s_gk[grp] = 0;
+      }
+      group_bar_sync(1 + grp, kGroupWarps * 32);
+      const int sgi = s_gseg[grp];
+      if (sgi >= nbig) break;  // group-uniform
+      const int t0 = fseg[kFastN - 1 - sgi], t1 = segend[t0];
+      const int nw = (t1 - t0 + 31) >> 5;
+      for (int wb = 0; wb < nw; ++wb) {
+        const int c = t0 + (wb << 5) + lane;
+        const bool valid = c < t1;
+        const int kc = s_gk[grp];
+        if (kc >= p.max_det) {  // group-uniform: the rest of the segment cannot reach the output
+          if (valid && gw == 0) ssupp[static_cast<unsigned>(key2[c])] = 1;
+          continue;
+        }
+        const float4 bc = valid ? sbo[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float ac = valid ? sarea[c] : 0.f;
+        bool sup = false;
+        for (int i = gw; i < kc; i += 2 * kGroupWarps) {  // two independent tests per trip
+          const int i2 = i + kGroupWarps;
+          const bool has2 = i2 < kc;
+          const int r0 = klist[t0 + i], r1 = klist[t0 + (has2 ? i2 : i)];
+          const bool h0 = iou_gt(sbo[r0], sarea[r0], bc, ac, thr);
+          const bool h1 = iou_gt(sbo[r1], sarea[r1], bc, ac, thr);
+          sup |= h0 | (has2 & h1);
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, valid && sup);
+        if (lane == 0 && word) atomicOr(&s_gsup[grp], word);
+        group_bar_sync(1 + grp, kGroupWarps * 32);
+        if (gw == 0) {
+          const unsigned supw = s_gsup[grp];
+          const int left = t1 - t0 - (wb << 5);
+          const unsigned din = valid ? sdin[c] : 0u;
+          unsigned avail = ~supw & (left >= 32 ? 0xffffffffu : ((1u << left) - 1u));
           unsigned keep = 0;
           while (avail) {  // warp-uniform
             const int i = __ffs(avail) - 1;
             keep |= 1u << i;
             avail &= ~(1u << i);
-            avail &= ~__shfl_sync(0xffffffffu, diag, i);
+            avail &= ~__ballot_sync(0xffffffffu, (din >> i) & 1u);
           }
-          if (valid && !((keep >> lane) & 1u)) ssupp[static_cast<unsigned>(key2[t0 + q])] = 1;
-          // OR the kept rows into the later blocks' suppressed bits: lane l owns words l and l + 32 of the segment
-          const bool own0 = lane > wb && lane < nw, own1 = lane + 32 > wb && lane + 32 < nw;
-          unsigned acc0 = 0, acc1 = 0;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const int base = __shfl_sync(0xffffffffu, myoff, i) - wb;  // masks[base + w] = word w of row i of the block
-            if ((keep >> i) & 1u) {                                      // warp-uniform
-              if (own0) acc0 |= masks[base + lane];
-              if (own1) acc1 |= masks[base + lane + 32];
-            }
+          if (valid) {
+            if ((keep >> lane) & 1u) klist[t0 + kc + __popc(keep & lt_mask)] = c;
+            else ssupp[static_cast<unsigned>(key2[c])] = 1;
           }
-          if (own0 && acc0) srem[t0 + (lane << 5)] |= acc0;
-          if (own1 && acc1) srem[t0 + ((lane + 32) << 5)] |= acc1;
-          __syncwarp();
+          if (lane == 0) {
+            s_gk[grp] = kc + __popc(keep);
+            s_gsup[grp] = 0;
+          }
         }
+        group_bar_sync(1 + grp, kGroupWarps * 32);
       }
-      __syncthreads();
     }
-    AY2_NMS_MARK(5);
+    __syncthreads();
     AY2_NMS_MARK(6);
     // compaction in score order: exclusive prefix count of kept flags
     const int per = (n + blockDim.x - 1) / blockDim.x;
@@ -640,8 +744,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     AY2_NMS_MARK(7);
     if (trace && b == 0 && tid == 0) {
       trace[8] = n;
-      trace[9] = s_nseg;
-      trace[10] = soff[n];
+      trace[9] = nsmall;
+      trace[10] = nbig;
+      trace[11] = nblk;
     }
     return;
   }
@@ -774,11 +879,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 
 constexpr size_t kNmsChunkBytes = sizeof(float4) * (2 * kChunk + kMaxDetCap) + sizeof(float) * (2 * kChunk + kMaxDetCap) +
                                   sizeof(int) * (3 * kChunk + kMaxDetCap) + sizeof(unsigned) * kChunk * kChunkWords;
-constexpr size_t kNmsFastBytes = sizeof(float4) * kFastN + sizeof(float) * kFastN + sizeof(int) * (kFastN + 4) +
-                                 4 * sizeof(int) * kFastN + sizeof(unsigned) * kMaskWords + kFastN;
+constexpr size_t kNmsFastBytes = sizeof(float4) * kFastN + sizeof(float) * kFastN + 6 * sizeof(int) * kFastN + kFastN;
 static_assert(sizeof(unsigned long long) * kSortSmemKeys >= sizeof(unsigned long long) * 2 * kFastN + sizeof(float4) * kFastN,
               "the key buffer holds the sorted keys, the (class, rank) keys and the segment-ordered boxes");
-static_assert(kFastN <= 2 * kNmsThreads && kRound % 32 == 0, "register bitonic sort: two keys per thread");
+static_assert(kFastN <= 2 * kNmsThreads && kGroups * kGroupWarps * 32 == kNmsThreads, "two keys per thread; warp groups");
+static_assert(2 * sizeof(int) * kFastN >= sizeof(unsigned short) * (kFastN / 32) * kCountNc && kCountNc % 32 == 0,
+              "the counting-sort table overlays klist + sdin");
 constexpr size_t kNmsSmemBytes = sizeof(unsigned long long) * kSortSmemKeys +
                                  (kNmsChunkBytes > kNmsFastBytes ? kNmsChunkBytes : kNmsFastBytes);
 
@@ -862,9 +968,9 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
       long long h[16];
       AY2_CHECK_CUDA(cudaStreamSynchronize(st));
       AY2_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
-      fprintf(stderr, "[ay2 nms trace] img0 n=%lld nseg=%lld mask_words=%lld | clocks: sort %lld, boxes %lld, class sort %lld, "
-              "segments+scan %lld, masks %lld, resolve %lld, emit %lld\n", h[8], h[9], h[10], h[1] - h[0], h[2] - h[1],
-              h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+      fprintf(stderr, "[ay2 nms trace] img0 n=%lld segments %lld one-block + %lld longer, %lld blocks | clocks: sort %lld, boxes %lld, "
+              "class order %lld, offset boxes %lld, in-block tests %lld, resolve %lld, emit %lld\n", h[8], h[9], h[10], h[11],
+              h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
     }
   }
   if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, v.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));

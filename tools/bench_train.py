@@ -49,6 +49,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--model", default="yolov5s")
+    ap.add_argument("--profile", action="store_true", help="print a per-kernel table (torch profiler) of 2 extra steps")
     args = ap.parse_args()
     rank, local_rank, world = du.env_ranks()
     torch.cuda.set_device(local_rank)
@@ -93,6 +94,14 @@ def main() -> None:
     du.barrier()
     ms = du.max_over_ranks(e0.elapsed_time(e1), dev)
     eng = next(iter(model.__dict__["_train_engine_cache"].values()))
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(2):
+                step(i)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70), file=sys.stderr)
     if rank == 0:
         ips = world * bs * args.steps / (ms / 1000.0)
         line = {"metric": "images/sec train step (fwd + ComputeLoss + bwd + SGD/EMA)", "value": ips, "unit": "images/s",
