@@ -28,7 +28,16 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   o.w = pack_bf16x2(f[6], f[7]);
   return o;
 }
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// sigmoid(x) = 0.5 + 0.5 * tanh(x/2): ONE MUFU op (tanh.approx, |rel err| <= 2^-11, below the bf16 storage of every
+// tensor it feeds). exp2 + rcp would be two, and these kernels are MUFU-bound: 2 passes x 5e9 elements per step.
+__device__ __forceinline__ float sigmoid_acc(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+// forward activations keep the 2-MUFU form (~2 ulp): a random-init train-mode network amplifies forward perturbations
+// chaotically (DESIGN.md §training parity), the forward kernel is not MUFU-bound, the two backward passes are
+__device__ __forceinline__ float sigmoid_fwd(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 // Reduce `nval` per-thread partials (8 channels each) over the pixel lanes of a block and add them to `dst`
 // (double, [C]) with one atomic per channel per block. smem: [lanes][tpp*8] floats.
@@ -94,24 +103,32 @@ __global__ void bn_finalize_kernel(const double* sum, const double* sumsq, long 
 }
 
 // y = act(gamma * (z - mean) * invstd + beta) (+ residual)
+// Thread (cg, pl) owns channel group cg for the pixels pl, pl + lanes*grid, ...: u = z*A + B with A, B in registers.
 __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long npix, int C, int zcs,
                                   const float* __restrict__ mean, const float* __restrict__ invstd,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                   __nv_bfloat16* __restrict__ y, int ycs, const __nv_bfloat16* __restrict__ res, int rcs) {
   const int tpp = C >> 3;
-  const long long total = npix * tpp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % tpp);
-    const long long p = i / tpp;
+  const int lanes = blockDim.x / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  if (pl >= lanes) return;
+  float A[8], Bc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    A[j] = gamma[c] * invstd[c];
+    Bc[j] = beta[c] - A[j] * mean[c];
+  }
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += step) {
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
     float r[8];
     if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * rcs + cg * 8), r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      float u = gamma[c] * (f[j] - mean[c]) * invstd[c] + beta[c];
-      if (act == AY2_ACT_SILU) u = u * sigmoid_acc(u);
+      float u = fmaf(f[j], A[j], Bc[j]);
+      if (act == AY2_ACT_SILU) u = u * sigmoid_fwd(u);
       if (res) u += r[j];
       f[j] = u;
     }
@@ -130,13 +147,13 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const bool active = pl < lanes;
   float acc[2][8];
-  float mu[8], is[8], ga[8], be[8];
+  float is[8], ms[8], ga[8], be[8];  // xhat = z*is - ms ; u = ga*xhat + be
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     acc[0][j] = acc[1][j] = 0.f;
     const int c = cg * 8 + j;
-    mu[j] = active ? mean[c] : 0.f;
     is[j] = active ? invstd[c] : 0.f;
+    ms[j] = active ? mean[c] * invstd[c] : 0.f;
     ga[j] = active ? gamma[c] : 0.f;
     be[j] = active ? beta[c] : 0.f;
   }
@@ -147,15 +164,15 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
       unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (f[j] - mu[j]) * is[j];
+        const float xh = fmaf(f[j], is[j], -ms[j]);
         float d = g[j];
         if (act == AY2_ACT_SILU) {
-          const float u = ga[j] * xh + be[j];
-          const float s = sigmoid_acc(u);
-          d *= s * (1.0f + u * (1.0f - s));
+          const float u = fmaf(ga[j], xh, be[j]);
+          const float sg = sigmoid_acc(u);
+          d *= sg * fmaf(u, 1.0f - sg, 1.0f);
         }
         acc[0][j] += d;
-        acc[1][j] += d * xh;
+        acc[1][j] = fmaf(d, xh, acc[1][j]);
       }
     }
   double* dst[2] = {s1, s2};
@@ -169,25 +186,37 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
                                         const float* __restrict__ beta, int act, const double* __restrict__ s1,
                                         const double* __restrict__ s2, __nv_bfloat16* __restrict__ dz, int zdcs) {
   const int tpp = C >> 3;
-  const long long total = npix * tpp;
+  const int lanes = blockDim.x / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  if (pl >= lanes) return;
   const float invn = 1.0f / (float)npix;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % tpp);
-    const long long p = i / tpp;
+  float is[8], ms[8], ga[8], be[8], k0[8], k1[8], k2[8];  // dz = k0*dyh - k1 - xhat*k2
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    is[j] = invstd[c];
+    ms[j] = mean[c] * is[j];
+    ga[j] = gamma[c];
+    be[j] = beta[c];
+    k0[j] = ga[j] * is[j];
+    k1[j] = k0[j] * (float)s1[c] * invn;
+    k2[j] = k0[j] * (float)s2[c] * invn;
+  }
+  const long long step = (long long)gridDim.x * lanes;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += step) {
     float g[8], f[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cg * 8), g);
     unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      const float xh = (f[j] - mean[c]) * invstd[c];
+      const float xh = fmaf(f[j], is[j], -ms[j]);
       float d = g[j];
       if (act == AY2_ACT_SILU) {
-        const float u = gamma[c] * xh + beta[c];
-        const float s = sigmoid_acc(u);
-        d *= s * (1.0f + u * (1.0f - s));
+        const float u = fmaf(ga[j], xh, be[j]);
+        const float sg = sigmoid_acc(u);
+        d *= sg * fmaf(u, 1.0f - sg, 1.0f);
       }
-      g[j] = gamma[c] * invstd[c] * (d - (float)s1[c] * invn - xh * (float)s2[c] * invn);
+      g[j] = fmaf(d, k0[j], -fmaf(xh, k2[j], k1[j]));
     }
     *reinterpret_cast<uint4*>(dz + p * zdcs + cg * 8) = pack8(g);
   }
@@ -278,6 +307,67 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int xcs,
     __nv_bfloat16* o = dx + p * gcs + c;
     if (accumulate) acc += __bfloat162float(*o);
     *o = __float2bfloat16_rn(acc);
+  }
+}
+
+// The same, for planes that fit shared memory (the SPP/SPPF maps: 20x20 at 640 px): one block per (image, group of 8
+// channels) stages x and dy, finds every window's argmax ONCE (k*k reads instead of k^4 per output element), then
+// gathers. Identical tie rule and summation order to the kernel above.
+__global__ void maxpool_bwd_tile_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const __nv_bfloat16* __restrict__ dy,
+                                        int dcs, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, int gcs,
+                                        int accumulate) {
+  extern __shared__ __align__(16) uint8_t tile_sm[];
+  const int HW = H * W;
+  uint4* xs = reinterpret_cast<uint4*>(tile_sm);                       // [HW] 8 channels of x
+  uint4* ds = xs + HW;                                                 // [HW] 8 channels of dy
+  unsigned short* arg = reinterpret_cast<unsigned short*>(ds + HW);    // [HW][8] flat index of the window argmax
+  const int groups = C >> 3;
+  const int b = blockIdx.x / groups, cg = blockIdx.x - b * groups;
+  const long long pix0 = (long long)b * HW;
+  for (int q = threadIdx.x; q < HW; q += blockDim.x) {
+    xs[q] = *reinterpret_cast<const uint4*>(x + (pix0 + q) * xcs + cg * 8);
+    ds[q] = *reinterpret_cast<const uint4*>(dy + (pix0 + q) * dcs + cg * 8);
+  }
+  __syncthreads();
+  const int r = k / 2;
+  const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(xs);
+  const __nv_bfloat16* de = reinterpret_cast<const __nv_bfloat16*>(ds);
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+    const int j = i & 7, q = i >> 3;
+    const int qy = q / W, qx = q - qy * W;
+    float best = -INFINITY;
+    int bi = 0xffff;
+    for (int wy = max(qy - r, 0); wy <= min(qy + r, H - 1); ++wy)
+      for (int wx = max(qx - r, 0); wx <= min(qx + r, W - 1); ++wx) {
+        const float v = __bfloat162float(xe[(wy * W + wx) * 8 + j]);
+        if (v > best) {
+          best = v;
+          bi = wy * W + wx;
+        }
+      }
+    arg[i] = static_cast<unsigned short>(bi);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < HW; q += blockDim.x) {
+    const int py = q / W, px = q - py * W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int qy = max(py - r, 0); qy <= min(py + r, H - 1); ++qy)
+      for (int qx = max(px - r, 0); qx <= min(px + r, W - 1); ++qx) {
+        const int w = qy * W + qx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (arg[w * 8 + j] == q) acc[j] += __bfloat162float(de[w * 8 + j]);
+      }
+    __nv_bfloat16* o = dx + (pix0 + q) * gcs + cg * 8;
+    if (accumulate) {
+      float old[8];
+      unpack8(*reinterpret_cast<const uint4*>(o), old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+    }
+    *reinterpret_cast<uint4*>(o) = pack8(acc);
   }
 }
 
@@ -401,8 +491,10 @@ extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_
                               const float* invstd, const float* gamma, const float* beta, int32_t act, void* y,
                               int32_t y_cstride, const void* residual, int32_t res_cstride, void* stream) {
   AY2_REQUIRE(z && y && mean && invstd && gamma && beta, "ay2_bn_act_fwd: null pointer");
-  AY2_REQUIRE(c % 8 == 0, "ay2_bn_act_fwd: channels must be a multiple of 8");
-  bn_act_fwd_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, AY2_ST>>>(AY2_CBF(z), npix, c, z_cstride, mean, invstd, gamma,
+  int threads, lanes;
+  size_t smem;
+  AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_fwd: channels=%d unsupported", c);
+  bn_act_fwd_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(AY2_CBF(z), npix, c, z_cstride, mean, invstd, gamma,
                                                                      beta, act, AY2_BF(y), y_cstride, AY2_CBF(residual),
                                                                      res_cstride);
   AY2_CHECK_LAUNCH();
@@ -424,7 +516,7 @@ extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z,
   bn_act_bwd_reduce_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
                                                                   mean, invstd, gamma, beta, act, s1, s2);
   AY2_CHECK_LAUNCH();
-  bn_act_bwd_apply_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride,
+  bn_act_bwd_apply_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride,
                                                                            npix, c, mean, invstd, gamma, beta, act, s1, s2,
                                                                            AY2_BF(dz), dz_cstride);
   AY2_CHECK_LAUNCH();
@@ -456,6 +548,21 @@ extern "C" int ay2_maxpool_bwd(const void* x, int32_t x_cstride, const void* dy,
                                int32_t w, int32_t c, int32_t k, void* dx, int32_t dx_cstride, int32_t accumulate,
                                void* stream) {
   AY2_REQUIRE(x && dy && dx && k % 2 == 1, "ay2_maxpool_bwd: bad arguments");
+  const size_t tile_bytes = (size_t)h * w * (16 + 16 + 16);
+  if (c % 8 == 0 && x_cstride % 8 == 0 && dy_cstride % 8 == 0 && dx_cstride % 8 == 0 && h * w < 0xffff &&
+      tile_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
+    static size_t attr_bytes = 0;
+    if (tile_bytes > 48 * 1024 && tile_bytes > attr_bytes) {
+      AY2_CHECK_CUDA(cudaFuncSetAttribute(maxpool_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_bytes = 200 * 1024;
+    }
+    maxpool_bwd_tile_kernel<<<batch * (c / 8), 256, tile_bytes, AY2_ST>>>(AY2_CBF(x), x_cstride, AY2_CBF(dy), dy_cstride, h, w, c,
+                                                                         k, AY2_BF(dx), dx_cstride, accumulate);
+    AY2_CHECK_LAUNCH();
+    count_launch();
+    return AY2_OK;
+  }
   maxpool_bwd_kernel<<<ew_grid((long long)batch * h * w * c, 256), 256, 0, AY2_ST>>>(
       AY2_CBF(x), x_cstride, AY2_CBF(dy), dy_cstride, batch, h, w, c, k, AY2_BF(dx), dx_cstride, accumulate);
   AY2_CHECK_LAUNCH();

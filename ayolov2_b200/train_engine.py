@@ -58,6 +58,7 @@ class TrainEngine:
         self.refresh: List[Callable[[], None]] = []  # weight re-packing (parameters change every optimizer step)
         self.keep: List[Any] = []
         self.grad_of: Dict[int, torch.Tensor] = {}   # id(activation buffer) -> gradient buffer
+        self.overwritten: set = set()                 # activation buffers whose gradient needs no zero-fill per step
         self._img: Optional[torch.Tensor] = None
         self.head_out: List[torch.Tensor] = []
         self.head_gin: List[torch.Tensor] = []
@@ -132,6 +133,8 @@ class TrainEngine:
             assert residual is None and act == ACT_NONE, "conv without BN is only used by the head"
         # ---------------- backward
         gy, gz = self.g(y), (self.g(z) if has_bn else self.g(y))
+        if has_bn:
+            self.overwritten.add(id(z.buf))
         gx = self.g(x) if need_dx else None
         dw = torch.zeros((cout, k * k * cin), dtype=torch.float32, device=dev)
         dplans: List[ConvPlan] = []
@@ -244,6 +247,7 @@ class TrainEngine:
             ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, None)
         self.fwd.append(f_bn)
         gy, gz = self.g(y), self.g(z)
+        self.overwritten.add(id(z.buf))
         dw = torch.zeros((cout, 9 * 16), dtype=torch.float32, device=dev)
         x_ptr = s2d.ptr() + 2 * 16  # logical pixel 0 lives at physical column 1
 
@@ -455,8 +459,9 @@ class TrainEngine:
             f()
 
     def _backward_body(self) -> None:
-        for gb in self.grad_of.values():
-            gb.zero_()
+        for key, gb in self.grad_of.items():
+            if key not in self.overwritten:  # pre-BN gradients are written whole by bn_act_bwd, never accumulated
+                gb.zero_()
         for t in self.pg.values():
             t.zero_()
         for b in reversed(self.bwd):
