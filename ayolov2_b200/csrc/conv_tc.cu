@@ -204,6 +204,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+  // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.
+  // The next kernel may start its own prologue as soon as every CTA of this grid is resident (all are: persistent grid).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // work items: (group of csize neighbouring M tiles, N tile); a cluster walks the item list, CTA `crank` takes its M tile
   const int crank = p.csize > 1 ? (int)cluster_ctarank() : 0;
   const int item0 = blockIdx.x / p.csize;
@@ -702,23 +707,29 @@ extern "C" int ay2_conv_plan_set_head_candidates(ay2_conv_plan* pl, const ay2_nm
 
 extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
   AY2_REQUIRE(pl, "ay2_conv_plan_run: null plan");
+  static const bool use_pdl = getenv("AY2_CONV_PDL") && atoi(getenv("AY2_CONV_PDL")) == 1;  // measured: no gain inside a CUDA graph (2.72 vs 2.70 ms/step), off by default
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->grid);
+  cfg.blockDim = dim3(pl->threads);
+  cfg.dynamicSmemBytes = pl->smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
   if (pl->kp.csize > 1) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pl->grid);
-    cfg.blockDim = dim3(pl->threads);
-    cfg.dynamicSmemBytes = pl->smem;
-    cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = pl->kp.csize;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    AY2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pl->kernel, pl->kp));
-  } else {
-    pl->kernel<<<pl->grid, pl->threads, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = pl->kp.csize;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (use_pdl) {  // the kernel's prologue may overlap the previous kernel's tail (griddepcontrol.wait guards the data)
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  AY2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pl->kernel, pl->kp));
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;
