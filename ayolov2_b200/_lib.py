@@ -33,6 +33,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ChainDesc(C.Structure):
+    """ay2_chain_desc (include/ay2.h)."""
+
+    _fields_ = [
+        ("batch", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32),
+        ("cin", C.c_int32), ("in_cstride", C.c_int32),
+        ("c1", C.c_int32), ("act1", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("c2", C.c_int32), ("act2", C.c_int32),
+        ("c3", C.c_int32), ("act3", C.c_int32),
+        ("out_cstride", C.c_int32), ("res_cstride", C.c_int32),
+    ]
+
+
 class NmsParams(C.Structure):
     """ay2_nms_params (include/ay2.h)."""
 
@@ -82,6 +96,12 @@ _PROTOS = {
     "ay2_conv_plan_flops": (C.c_double, [C.c_void_p]),
     "ay2_conv_reference_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "ay2_chain_supported": (C.c_int, [C.POINTER(ChainDesc)]),
+    "ay2_chain_plan_create": (C.c_int, [C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ay2_chain_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ay2_chain_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ay2_chain_plan_flops": (C.c_double, [C.c_void_p]),
     "ay2_space_to_depth": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_sppf_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

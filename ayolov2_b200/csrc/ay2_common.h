@@ -42,6 +42,12 @@ void count_launch(int n = 1);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// TMA tensor maps (conv_tc.cu). Activation: NHWC bf16 view [C][W][H][B] with element strides, box [boxc][bw][bh][1],
+// swizzle span = boxc*2 bytes. Weights: bf16 [rows][Ktot] (K innermost), box [boxk][boxn].
+int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB,
+                   int boxc, int bw, int bh);
+int encode_weight_map(CUtensorMap* tm, const void* base, int Ktot, int rows, int boxk, int boxn);
+
 // NMS workspace layout (nms.cu), shared with the head convolution whose epilogue appends candidates to it (conv_tc.cu)
 struct NmsWorkspaceView {
   int* counts;               // [batch] candidates per image

@@ -1,0 +1,607 @@
+// Fused convolution CHAIN on the sm_100a tensor cores: 1x1 -> 3x3 (-> 1x1), intermediates never leave the SM.
+//
+//   t   = act1(bias1 + W1 * x)                 1x1, Cin -> C1      (computed on the 18x10 halo of a 16x8 output tile)
+//   u   = act2(bias2 + W2 (*) t)               3x3 / stride 1 / pad 1, C1 -> C2
+//   out = act3(bias3 + W3 * u)  (+ residual)   1x1, C2 -> C3        (optional; without it `u` (+ residual) is the output)
+//
+// Two users:
+//   * the Tucker-2 chain emitted by scripts/tensor_decomposition/decomposition.py:363-424 (first 1x1 without bias,
+//     core kxk without bias, last 1x1 carrying the bias; the enclosing kindle Conv's BN + SiLU fold into stage 3);
+//   * kindle Bottleneck  x + conv2_3x3(conv1_1x1(x))  (stage 3 absent, residual = x).
+//
+// Data flow per tile (one CTA, persistent over tiles):
+//   TMA   : x halo tile [18][10][CK1 ch] per 64-channel chunk (OOB zero fill = image border) + the matching W1 chunk
+//   MMA 1 : D1[256 halo rows (2 x M128)][C1]  in TMEM                      (tcgen05.mma kind::f16, fp32 accumulate)
+//   EPI 1 : TMEM -> +bias1 -> act1 -> zero outside the image (the 3x3's padding applies to t, not to x) -> bf16 ->
+//           shared memory T in the UMMA *no-swizzle* K-major core-matrix layout: 8 channels x 16 B per pixel, pixels
+//           contiguous inside a plane of 8 channels. A 3x3 tap is then just a shifted START ADDRESS of the same tile:
+//           8-row groups (= 8 horizontally adjacent pixels) are 128 contiguous bytes for every shift, the group stride
+//           (SBO) is one halo row (160 B), the K stride (LBO) one 8-channel plane.
+//   MMA 2 : D2[128 pixels][C2] += T(shifted by tap) x W2[tap]   (9 x C1/16 instructions; W2 streamed by TMA)
+//   EPI 2 : either the final epilogue (bias2, act2, + residual, bf16, swizzled staging, TMA store) or
+//           TMEM -> bias2 -> act2 -> bf16 -> shared memory U (same no-swizzle layout), then
+//   MMA 3 : D3[128][N3 tile] = U x W3, EPI 3 = final epilogue, per N3 tile (D3 re-uses the TMEM columns of D1).
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM alloc, warps 4-7 epilogues.
+#include <stdlib.h>
+#include <string.h>
+
+#include "ay2_common.h"
+#include "ay2_ptx.cuh"
+
+namespace ay2 {
+
+constexpr int CH_TH = 16, CH_TW = 8;   // output tile (TW = 8: one UMMA 8-row group == 8 horizontally adjacent pixels)
+constexpr int CH_HH = CH_TH + 2, CH_HW = CH_TW + 2;
+constexpr int CH_NH = CH_HH * CH_HW;   // 180 halo pixels == rows of the stage-1 GEMM (two M=128 instructions)
+constexpr int CH_THREADS = 256;
+constexpr int CH_EPI_THREADS = 128;
+constexpr int CH_MAX_STAGES = 8;
+constexpr int CH_U_PLANE = 128 * 16;   // bytes of one 8-channel plane of U (128 pixels x 16 B)
+
+struct ChainParams {
+  CUtensorMap tmX;    // input  [C][W][H][B], box [ck1][10][18][1]
+  CUtensorMap tmW1;   // [cin][c1],    box [ck1][c1]
+  CUtensorMap tmW2;   // [9*c1][c2],   box [ck2][c2]
+  CUtensorMap tmW3;   // [c2][c3],     box [ck3][n3]
+  CUtensorMap tmOut;  // output [C][W][H][B], box [oc][8][16][1]
+  CUtensorMap tmRes;  // residual, same geometry as the output
+  const float* bias;  // [c1 + c2 + c3] fp32 (zeros where the reference has no bias)
+  int tiles_x, tiles_y, num_tiles;
+  int in_h, in_w;
+  int cin_chunks, ck1, c1, act1;
+  int c1_chunks, ck2, c2, act2;
+  int c3, n3, n3_tiles, c2_chunks, ck3, act3;  // c3 == 0: no stage 3
+  int has_res;
+  int oc;            // channels per output slab (64 / 32 / 16); swizzle span = 2*oc bytes
+  int nstages, slot_bytes;
+  int t_plane;       // bytes of one 8-channel plane of T (CH_NH * 16)
+  int tmem_cols, d2_col;
+  int off_T, off_U, off_staging, off_bias, off_bars;  // byte offsets from the 1024-aligned shared-memory base
+};
+
+__device__ __forceinline__ void ch_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major operand WITHOUT swizzle (canonical layout ((8,m),(8,2)) : ((16 B, SBO), (2 B, LBO))): a core matrix is 8 rows
+// x 16 bytes stored contiguously (128 B); LBO = byte distance between the two core matrices of one K=16 step,
+// SBO = byte distance between consecutive 8-row groups. The start address only needs 16-byte alignment.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;  // layout type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ uint32_t swizzled_offset_rt(uint32_t row, uint32_t chunk16, uint32_t row_bytes) {
+  uint32_t off = row * row_bytes + chunk16 * 16;
+  const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
+__device__ __forceinline__ float ch_act(float x, int act) { return act == AY2_ACT_SILU ? silu_f(x) : x; }
+
+// Final epilogue of one accumulator tile: TMEM -> +bias -> act (-> + residual) -> bf16 -> swizzled staging -> TMA store.
+// All 128 epilogue threads call it; `acc_full` is the MMA->epilogue barrier of this accumulator.
+__device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* staging, const float* bias_s, uint32_t taddr,
+                                                 int ncols, int act, int n0, int x0, int y0, int b, int et,
+                                                 uint64_t* acc_full, uint32_t acc_phase, uint64_t* acc_empty,
+                                                 uint64_t* res_full, uint32_t& res_phase) {
+  const int swo = p.oc * 2;
+  const int slab_bytes = 128 * swo;
+  const int nslab = ncols / p.oc;
+  if (et == 0) {
+    tma_store_wait_read<0>();  // the previous tile's stores have finished reading the staging buffer
+    if (p.has_res) {
+      mbar_expect_tx(res_full, 128 * ncols * 2);
+      for (int s = 0; s < nslab; ++s) tma_load_4d(&p.tmRes, res_full, staging + s * slab_bytes, n0 + s * p.oc, x0, y0, b);
+    }
+  }
+  ch_bar_sync(1, CH_EPI_THREADS);
+  mbar_wait(acc_full, acc_phase);
+  tcgen05_fence_after();
+  if (p.has_res) {
+    mbar_wait(res_full, res_phase);
+    res_phase ^= 1;
+  }
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(taddr + c0, v);
+    tmem_ld_wait();
+    uint8_t* slab = staging + (c0 / p.oc) * slab_bytes;
+    const int chunk0 = (c0 % p.oc) / 8;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = ch_act(__uint_as_float(v[g * 8 + i]) + bias_s[n0 + c0 + g * 8 + i], act);
+      const uint32_t dst = smem_u32(slab) + swizzled_offset_rt(et, chunk0 + g, swo);
+      if (p.has_res) {
+        uint4 rv;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(dst));
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 rf = __bfloat1622float2(r2[i]);
+          f[2 * i] += rf.x;
+          f[2 * i + 1] += rf.y;
+        }
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(f[0], f[1])),
+                   "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+                   : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  if (acc_empty) mbar_arrive(acc_empty);  // accumulator drained
+  fence_proxy_async_smem();
+  ch_bar_sync(1, CH_EPI_THREADS);
+  if (et == 0) {
+    for (int s = 0; s < nslab; ++s) tma_store_4d(&p.tmOut, staging + s * slab_bytes, n0 + s * p.oc, x0, y0, b);
+    tma_store_commit();
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* T = smem + p.off_T;
+  uint8_t* U = smem + p.off_U;
+  uint8_t* staging = smem + p.off_staging;
+  float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+  uint64_t* full_bar = bars;                        // [CH_MAX_STAGES]
+  uint64_t* empty_bar = bars + CH_MAX_STAGES;       // [CH_MAX_STAGES]
+  uint64_t* d1_full = bars + 2 * CH_MAX_STAGES;     // MMA -> epilogue 1
+  uint64_t* t_ready = d1_full + 1;                  // epilogue 1 -> MMA (T written, D1 drained)
+  uint64_t* d2_full = d1_full + 2;
+  uint64_t* u_ready = d1_full + 3;
+  uint64_t* d3_full = d1_full + 4;
+  uint64_t* d3_empty = d1_full + 5;
+  uint64_t* res_full = d1_full + 6;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(d1_full + 7);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int swa1 = p.ck1 * 2, swa2 = p.ck2 * 2, swa3 = p.ck3 * 2;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(d1_full, 1);
+    mbar_init(t_ready, CH_EPI_THREADS);
+    mbar_init(d2_full, 1);
+    mbar_init(u_ready, CH_EPI_THREADS);
+    mbar_init(d3_full, 1);
+    mbar_init(d3_empty, CH_EPI_THREADS);
+    mbar_init(res_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW1);
+    tma_prefetch_desc(&p.tmW2);
+    tma_prefetch_desc(&p.tmOut);
+  }
+  for (int i = threadIdx.x; i < p.c1 + p.c2 + p.c3; i += CH_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 2) tmem_alloc(tmem_ptr_s, p.tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img;
+        const int r = tile - b * tiles_per_img;
+        const int ty = r / p.tiles_x;
+        const int y0 = ty * CH_TH, x0 = (r - ty * p.tiles_x) * CH_TW;
+        for (int kc = 0; kc < p.cin_chunks; ++kc) {  // stage 1: halo chunk of x + W1 chunk
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* slot = ring + stage * p.slot_bytes;
+          mbar_expect_tx(&full_bar[stage], (CH_NH + p.c1) * swa1);
+          tma_load_4d(&p.tmX, &full_bar[stage], slot, kc * p.ck1, x0 - 1, y0 - 1, b);
+          tma_load_2d(&p.tmW1, &full_bar[stage], slot + 256 * swa1, kc * p.ck1, 0);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+        for (int tap = 0; tap < 9; ++tap) {          // stage 2: W2 per tap and channel chunk
+          for (int cc = 0; cc < p.c1_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], p.c2 * swa2);
+            tma_load_2d(&p.tmW2, &full_bar[stage], ring + stage * p.slot_bytes, tap * p.c1 + cc * p.ck2, 0);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+        for (int n = 0; n < p.n3_tiles; ++n) {       // stage 3: W3 per N tile and channel chunk
+          for (int cc = 0; cc < p.c2_chunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], p.n3 * swa3);
+            tma_load_2d(&p.tmW3, &full_bar[stage], ring + stage * p.slot_bytes, cc * p.ck3, n * p.n3);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16_f32(128, p.c1);
+      const uint32_t idesc2 = make_idesc_bf16_f32(128, p.c2);
+      const uint32_t idesc3 = make_idesc_bf16_f32(128, p.n3 > 0 ? p.n3 : 16);
+      const uint32_t t_addr = smem_u32(T), u_addr = smem_u32(U);
+      int stage = 0, phase = 0;
+      uint32_t t_phase = 0, u_phase = 0, d3e_phase = 0;
+      bool d3_pending = false;  // an accumulator in the D1/D3 column range has been handed to the epilogue
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (d3_pending) {  // D3 shares its TMEM columns with D1
+          mbar_wait(d3_empty, d3e_phase);
+          d3e_phase ^= 1;
+          d3_pending = false;
+          tcgen05_fence_after();
+        }
+        // ---- stage 1: D1[half] = Xhalo[half*128 .. +128) x W1^T
+        for (int kc = 0; kc < p.cin_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(ring + stage * p.slot_bytes);
+          const uint32_t b_addr = a_addr + 256 * swa1;
+          for (int half = 0; half < 2; ++half) {
+            for (int k = 0; k < p.ck1 / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_kmajor(a_addr + half * 128 * swa1 + k * 32, swa1);
+              const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa1);
+              umma_f16_ss(tmem_base + half * p.c1, adesc, bdesc, idesc1, (kc | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(d1_full);
+        // ---- stage 2: D2 += T(shifted by tap) x W2[tap]^T
+        mbar_wait(t_ready, t_phase);
+        t_phase ^= 1;
+        tcgen05_fence_after();
+        uint32_t accum = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const uint32_t a_tap = t_addr + (ky * CH_HW + kx) * 16;
+          for (int cc = 0; cc < p.c1_chunks; ++cc) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t b_addr = smem_u32(ring + stage * p.slot_bytes);
+            for (int k = 0; k < p.ck2 / 16; ++k) {
+              const int c16 = cc * (p.ck2 / 16) + k;
+              const uint64_t adesc = make_smem_desc_nosw(a_tap + c16 * 2 * p.t_plane, p.t_plane, CH_HW * 16);
+              const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa2);
+              umma_f16_ss(tmem_base + p.d2_col, adesc, bdesc, idesc2, accum);
+              accum = 1;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(d2_full);
+        // ---- stage 3: D3[n] = U x W3[n]^T
+        if (p.c3) {
+          mbar_wait(u_ready, u_phase);
+          u_phase ^= 1;
+          tcgen05_fence_after();
+          for (int n = 0; n < p.n3_tiles; ++n) {
+            if (d3_pending) {
+              mbar_wait(d3_empty, d3e_phase);
+              d3e_phase ^= 1;
+              d3_pending = false;
+              tcgen05_fence_after();
+            }
+            for (int cc = 0; cc < p.c2_chunks; ++cc) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t b_addr = smem_u32(ring + stage * p.slot_bytes);
+              for (int k = 0; k < p.ck3 / 16; ++k) {
+                const int c16 = cc * (p.ck3 / 16) + k;
+                const uint64_t adesc = make_smem_desc_nosw(u_addr + c16 * 2 * CH_U_PLANE, CH_U_PLANE, 128);
+                const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa3);
+                umma_f16_ss(tmem_base, adesc, bdesc, idesc3, (cc | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(d3_full);
+            d3_pending = true;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogues ===============================
+    const int et = threadIdx.x - 128;  // accumulator row == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t d1_phase = 0, d2_phase = 0, d3_phase = 0, res_phase = 0;
+    const float* bias1 = bias_s;
+    const float* bias2 = bias_s + p.c1;
+    const float* bias3 = bias_s + p.c1 + p.c2;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_img;
+      const int r = tile - b * tiles_per_img;
+      const int ty = r / p.tiles_x;
+      const int y0 = ty * CH_TH, x0 = (r - ty * p.tiles_x) * CH_TW;
+      // ---- epilogue 1: D1 -> T
+      mbar_wait(d1_full, d1_phase);
+      d1_phase ^= 1;
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half * 128 + (et & ~31) >= CH_NH) continue;  // warp-uniform: this warp's rows are all beyond the halo
+        const int h = half * 128 + et;
+        bool inb = false;
+        if (h < CH_NH) {
+          const int hy = h / CH_HW, hx = h - hy * CH_HW;
+          const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
+          inb = iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
+        }
+        const uint32_t tbase = tmem_base + lane_off + half * p.c1;
+        const uint32_t trow = smem_u32(T) + h * 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.c1; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tbase + c0, v);
+          tmem_ld_wait();
+          if (h < CH_NH) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              float f[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                f[i] = inb ? ch_act(__uint_as_float(v[g * 8 + i]) + bias1[c0 + g * 8 + i], p.act1) : 0.0f;
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(trow + (c0 / 8 + g) * p.t_plane),
+                           "r"(pack_bf16x2(f[0], f[1])), "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])),
+                           "r"(pack_bf16x2(f[6], f[7]))
+                           : "memory");
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();  // generic-proxy writes of T -> visible to the tensor core's async-proxy reads
+      mbar_arrive(t_ready);
+      if (p.c3 == 0) {
+        // ---- epilogue 2 = final
+        chain_store_tile(p, staging, bias2, tmem_base + lane_off + p.d2_col, p.c2, p.act2, 0, x0, y0, b, et, d2_full,
+                         d2_phase, nullptr, res_full, res_phase);
+        d2_phase ^= 1;
+      } else {
+        // ---- epilogue 2: D2 -> U
+        mbar_wait(d2_full, d2_phase);
+        d2_phase ^= 1;
+        tcgen05_fence_after();
+        const uint32_t urow = smem_u32(U) + et * 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.c2; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + lane_off + p.d2_col + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = ch_act(__uint_as_float(v[g * 8 + i]) + bias2[c0 + g * 8 + i], p.act2);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(urow + (c0 / 8 + g) * CH_U_PLANE),
+                         "r"(pack_bf16x2(f[0], f[1])), "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])),
+                         "r"(pack_bf16x2(f[6], f[7]))
+                         : "memory");
+          }
+        }
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(u_ready);
+        // ---- epilogue 3 per N tile
+        for (int n = 0; n < p.n3_tiles; ++n) {
+          chain_store_tile(p, staging, bias3, tmem_base + lane_off, p.n3, p.act3, n * p.n3, x0, y0, b, et, d3_full, d3_phase,
+                           d3_empty, res_full, res_phase);
+          d3_phase ^= 1;
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace ay2
+
+using namespace ay2;
+
+struct ay2_chain_plan {
+  ChainParams kp;
+  ay2_chain_desc desc;
+  int grid, ctas_per_sm;
+  size_t smem;
+};
+
+static int chunk_for(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+static int round_up_i(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" int ay2_chain_supported(const ay2_chain_desc* d) {
+  if (!d) return 0;
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1) return 0;
+  if (d->cin % 16 || d->c1 % 16 || d->c2 % 16 || d->c3 % 16) return 0;
+  if (d->cin < 16 || d->c1 < 16 || d->c1 > 128 || d->c2 < 16 || d->c2 > 256) return 0;
+  if (d->c3 == 0 && d->c2 % 16) return 0;
+  if (d->in_cstride % 8 || d->out_cstride % 8 || d->res_cstride % 8) return 0;
+  return 1;
+}
+
+extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, const void* w1, const void* w2, const void* w3,
+                                     const float* bias, const void* residual, void* out, ay2_chain_plan** plan_out) {
+  AY2_REQUIRE(d && in && w1 && w2 && bias && out && plan_out, "ay2_chain_plan_create: null argument");
+  AY2_REQUIRE(ay2_chain_supported(d),
+              "chain cin=%d c1=%d c2=%d c3=%d k=%dx%d s=%d p=%d is outside the fused kernel's envelope (3x3/s1/p1, channels "
+              "multiples of 16, c1 <= 128, c2 <= 256)",
+              d->cin, d->c1, d->c2, d->c3, d->kh, d->kw, d->stride, d->pad);
+  AY2_REQUIRE(d->c3 == 0 || w3, "stage 3 needs its weights");
+  AY2_REQUIRE(d->res_cstride == 0 || residual, "residual stride given without a residual pointer");
+  AY2_REQUIRE(out != in, "the fused chain cannot run in place (tiles read their neighbours' halo)");
+  ay2_chain_plan* pl = new ay2_chain_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->desc = *d;
+  ChainParams& kp = pl->kp;
+  const int H = d->in_h, W = d->in_w;
+  kp.in_h = H;
+  kp.in_w = W;
+  kp.tiles_x = ceil_div(W, CH_TW);
+  kp.tiles_y = ceil_div(H, CH_TH);
+  kp.num_tiles = kp.tiles_x * kp.tiles_y * d->batch;
+  kp.ck1 = chunk_for(d->cin);
+  kp.cin_chunks = d->cin / kp.ck1;
+  kp.c1 = d->c1;
+  kp.act1 = d->act1;
+  kp.ck2 = chunk_for(d->c1);
+  kp.c1_chunks = d->c1 / kp.ck2;
+  kp.c2 = d->c2;
+  kp.act2 = d->act2;
+  kp.c3 = d->c3;
+  kp.act3 = d->act3;
+  if (d->c3) {
+    kp.ck3 = chunk_for(d->c2);
+    kp.c2_chunks = d->c2 / kp.ck3;
+    // N tile of stage 3: the largest divisor of c3 that is a multiple of 16 and <= 256
+    int n3 = 0;
+    for (int cand = 256; cand >= 16; cand -= 16)
+      if (d->c3 % cand == 0) {
+        n3 = cand;
+        break;
+      }
+    kp.n3 = n3;
+    kp.n3_tiles = d->c3 / n3;
+  } else {
+    kp.ck3 = 16;
+  }
+  kp.has_res = d->res_cstride != 0;
+  const int cout = d->c3 ? d->c3 : d->c2;
+  const int ntile = d->c3 ? kp.n3 : d->c2;  // channels per final accumulator tile
+  kp.oc = ntile % 64 == 0 ? 64 : (ntile % 32 == 0 ? 32 : 16);
+  kp.t_plane = CH_NH * 16;
+  kp.bias = bias;
+  // TMEM: [0, max(2*c1, n3)) = D1 halves / D3 tile, then D2
+  const int regA = 2 * d->c1 > kp.n3 ? 2 * d->c1 : kp.n3;
+  kp.d2_col = regA;
+  int cols = regA + d->c2, pow2 = 32;
+  while (pow2 < cols) pow2 *= 2;
+  AY2_REQUIRE(pow2 <= 512, "chain needs %d TMEM columns", cols);
+  kp.tmem_cols = pow2;
+  // shared memory
+  const int swa1 = kp.ck1 * 2, swa2 = kp.ck2 * 2, swa3 = kp.ck3 * 2;
+  int slot = (256 + d->c1) * swa1;
+  if (d->c2 * swa2 > slot) slot = d->c2 * swa2;
+  if (d->c3 && kp.n3 * swa3 > slot) slot = kp.n3 * swa3;
+  slot = round_up_i(slot, 1024);
+  const int t_bytes = round_up_i(d->c1 / 8 * kp.t_plane, 1024);
+  const int u_bytes = d->c3 ? d->c2 / 8 * CH_U_PLANE : 0;
+  const int staging_bytes = 128 * ntile * 2;
+  const int bias_bytes = round_up_i((d->c1 + d->c2 + d->c3) * 4, 128);
+  const int bars_bytes = (2 * CH_MAX_STAGES + 8) * 8;
+  const int fixed = t_bytes + u_bytes + staging_bytes + bias_bytes + bars_bytes + 1024 /* alignment slack */;
+  int ctas = 0, nst = 0;
+  for (int c = 3; c >= 1 && !ctas; --c) {  // 68 registers x 256 threads: at most 3 CTAs per SM
+    if (kp.tmem_cols * c > 512) continue;
+    const int budget = 227 * 1024 / c - 1024;
+    int n = (budget - fixed) / slot;
+    if (n > CH_MAX_STAGES) n = CH_MAX_STAGES;
+    if (n >= (c == 1 ? 2 : 3)) {
+      ctas = c;
+      nst = n;
+    }
+  }
+  if (!ctas) {
+    delete pl;
+    set_error("chain cin=%d c1=%d c2=%d c3=%d does not fit in shared memory (fixed %d B + 2 x %d B)", d->cin, d->c1, d->c2,
+              d->c3, fixed, slot);
+    return AY2_ERR_INVALID;
+  }
+  // a deeper ring than one tile's worth of slots buys nothing
+  const int slots_per_tile = kp.cin_chunks + 9 * kp.c1_chunks + kp.n3_tiles * kp.c2_chunks;
+  if (nst > slots_per_tile + 2) nst = slots_per_tile + 2;
+  kp.nstages = nst;
+  kp.slot_bytes = slot;
+  kp.off_T = nst * slot;
+  kp.off_U = kp.off_T + t_bytes;
+  kp.off_staging = round_up_i(kp.off_U + u_bytes, 1024);
+  kp.off_bias = kp.off_staging + staging_bytes;
+  kp.off_bars = kp.off_bias + bias_bytes;
+  pl->smem = (size_t)kp.off_bars + bars_bytes + 1024;
+  pl->ctas_per_sm = ctas;
+
+  int rc = encode_act_map(&kp.tmX, in, d->cin, W, H, d->batch, d->in_cstride, (int64_t)d->in_cstride * W,
+                          (int64_t)d->in_cstride * W * H, kp.ck1, CH_HW, CH_HH);
+  if (rc == AY2_OK) rc = encode_weight_map(&kp.tmW1, w1, d->cin, d->c1, kp.ck1, d->c1);
+  if (rc == AY2_OK) rc = encode_weight_map(&kp.tmW2, w2, 9 * d->c1, d->c2, kp.ck2, d->c2);
+  if (rc == AY2_OK && d->c3) rc = encode_weight_map(&kp.tmW3, w3, d->c2, d->c3, kp.ck3, kp.n3);
+  if (rc == AY2_OK)
+    rc = encode_act_map(&kp.tmOut, out, cout, W, H, d->batch, d->out_cstride, (int64_t)d->out_cstride * W,
+                        (int64_t)d->out_cstride * W * H, kp.oc, CH_TW, CH_TH);
+  if (rc == AY2_OK && kp.has_res)
+    rc = encode_act_map(&kp.tmRes, residual, cout, W, H, d->batch, d->res_cstride, (int64_t)d->res_cstride * W,
+                        (int64_t)d->res_cstride * W * H, kp.oc, CH_TW, CH_TH);
+  if (rc != AY2_OK) {
+    delete pl;
+    return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    delete pl;
+    set_error("cudaFuncSetAttribute(chain smem) failed: %s", cudaGetErrorString(e));
+    return AY2_ERR_CUDA;
+  }
+  cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int resident = sms * ctas;
+  pl->grid = kp.num_tiles < resident ? kp.num_tiles : resident;
+  *plan_out = pl;
+  return AY2_OK;
+}
+
+extern "C" int ay2_chain_plan_run(const ay2_chain_plan* pl, void* stream) {
+  AY2_REQUIRE(pl, "ay2_chain_plan_run: null plan");
+  conv_chain_kernel<<<pl->grid, CH_THREADS, pl->smem, static_cast<cudaStream_t>(stream)>>>(pl->kp);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_chain_plan_destroy(ay2_chain_plan* pl) {
+  delete pl;
+  return AY2_OK;
+}
+
+extern "C" double ay2_chain_plan_flops(const ay2_chain_plan* pl) {
+  if (!pl) return 0.0;
+  const ay2_chain_desc& d = pl->desc;
+  const double px = (double)d.batch * d.in_h * d.in_w;
+  return 2.0 * px * ((double)d.cin * d.c1 + 9.0 * d.c1 * d.c2 + (double)d.c2 * d.c3);
+}

@@ -449,7 +449,7 @@ static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
 }
 
 // NHWC bf16 activation view [C][W][H][B] with explicit element strides; box [boxc][bw][bh][1].
-static int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH,
+int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH,
                           int64_t sB, int boxc, int bw, int bh) {
   // L2 promotion: fetch 256 B only when a pixel's channels are one dense run of >= 256 B that this conv consumes
   // entirely; a channel slice of a wider concat buffer would otherwise drag its neighbour's bytes through HBM.
@@ -476,7 +476,7 @@ static int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H
   return AY2_OK;
 }
 
-static int encode_weight_map(CUtensorMap* tm, const void* base, int Ktot, int rows, int boxk, int boxn) {
+int encode_weight_map(CUtensorMap* tm, const void* base, int Ktot, int rows, int boxk, int boxn) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");

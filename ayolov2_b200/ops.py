@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SILU, ConvDesc, HeadLevels, NmsParams
+from ._lib import ACT_NONE, ACT_SILU, ChainDesc, ConvDesc, HeadLevels, NmsParams
 
 
 @dataclass
@@ -158,6 +158,82 @@ class ConvPlan:
         h = getattr(self, "_h", None)
         if h:
             self._lib.ay2_conv_plan_destroy(h)
+            self._h = None
+
+
+def pack_chain_weight(w: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[Tuple[torch.Tensor, ...]] = None,
+                      eps: float = 1e-3, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None):
+    """One link of a fused chain: OIHW fp32 (+ optional BN fold) -> bf16 K-major [cout_pad][kh*kw*cin_pad] and fp32 bias
+    [cout_pad]; input / output channels are zero-padded to multiples of 16 (a padded output channel is act(0) = 0 and
+    meets zero weights in the next link)."""
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    if bn is not None:
+        gamma, beta, mean, var = [t.detach().float() for t in bn]
+        scale = gamma / torch.sqrt(var + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = beta - mean * scale
+        if bias is not None:
+            b = b + bias.detach().float() * scale
+    else:
+        b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    cin_pad = cin_pad or (cin + 15) // 16 * 16
+    cout_pad = cout_pad or (cout + 15) // 16 * 16
+    wp = torch.zeros((cout_pad, kh, kw, cin_pad), dtype=torch.float32, device=w.device)
+    wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp[:cout] = b
+    return wp.reshape(cout_pad, kh * kw * cin_pad).to(torch.bfloat16).contiguous(), bp
+
+
+def chain_desc(x: ActView, c1: int, c2: int, c3: int, act1: int, act2: int, act3: int, out_cstride: int,
+               res_cstride: int, k: int = 3, stride: int = 1, pad: int = 1) -> ChainDesc:
+    d = ChainDesc()
+    d.batch, d.in_h, d.in_w, d.cin, d.in_cstride = x.B, x.H, x.W, x.c, x.cstride
+    d.c1, d.act1, d.c2, d.act2, d.c3, d.act3 = c1, act1, c2, act2, c3, act3
+    d.kh = d.kw = k
+    d.stride, d.pad = stride, pad
+    d.out_cstride, d.res_cstride = out_cstride, res_cstride
+    return d
+
+
+def chain_supported(d: ChainDesc) -> bool:
+    return bool(_lib.load().ay2_chain_supported(C.byref(d)))
+
+
+class ChainPlan:
+    """ay2_chain_plan: 1x1 -> 3x3 (-> 1x1) fused in one kernel (Tucker-2 chain / Bottleneck). Keeps its tensors alive.
+    links = [(w_packed, bias)] * 2 or 3 from pack_chain_weight; acts = activation code per link."""
+
+    def __init__(self, x: ActView, y: ActView, links, acts, residual: Optional[ActView] = None):
+        lib = _lib.load()
+        assert len(links) in (2, 3) and len(acts) == len(links)
+        (w1, b1), (w2, b2) = links[0], links[1]
+        w3, b3 = links[2] if len(links) == 3 else (None, None)
+        c1, c2 = w1.shape[0], w2.shape[0]
+        c3 = w3.shape[0] if w3 is not None else 0
+        assert w1.shape[1] == x.c and w2.shape[1] == 9 * c1 and (w3 is None or w3.shape[1] == c2)
+        assert y.c == (c3 or c2) and (y.H, y.W) == (x.H, x.W)
+        d = chain_desc(x, c1, c2, c3, acts[0], acts[1], acts[2] if c3 else ACT_NONE, y.cstride,
+                       residual.cstride if residual is not None else 0)
+        bias = torch.cat([b1, b2] + ([b3] if b3 is not None else [])).float().contiguous()
+        self.desc = d
+        self.keep = (x, y, w1, w2, w3, bias, residual)
+        h = C.c_void_p()
+        _lib.check(lib.ay2_chain_plan_create(C.byref(d), x.ptr(), w1.data_ptr(), w2.data_ptr(), _lib.ptr(w3), bias.data_ptr(),
+                                             residual.ptr() if residual is not None else None, y.ptr(), C.byref(h)),
+                   "ay2_chain_plan_create")
+        self._h, self._lib = h, lib
+        self.flops = float(lib.ay2_chain_plan_flops(h))
+
+    def run(self, stream: Optional[int] = None) -> None:
+        _lib.check(self._lib.ay2_chain_plan_run(self._h, stream if stream is not None else _lib.current_stream_ptr()),
+                   "ay2_chain_plan_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.ay2_chain_plan_destroy(h)
             self._h = None
 
 

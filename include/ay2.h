@@ -94,6 +94,35 @@ int ay2_conv_reference_simt(const ay2_conv_desc* desc, const void* in, const voi
                             const void* residual, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused convolution chain: 1x1 (cin -> c1) -> 3x3/s1/p1 (c1 -> c2) [-> 1x1 (c2 -> c3)] in ONE kernel; the c1- and
+ * c2-channel intermediates live in shared memory / TMEM only. Replaces
+ *   - the nn.Sequential(Conv2d 1x1, Conv2d kxk, Conv2d 1x1) that tucker_decomposition_conv_layer builds
+ *     (scripts/tensor_decomposition/decomposition.py:363-424) inside a kindle Conv (its BN + SiLU fold into stage 3), and
+ *   - kindle.modules.bottleneck.Bottleneck.forward, x + conv2(conv1(x)) (c3 = 0, residual = x).
+ * Every stage is y = act(bias + W * x); the optional residual is added after the last activation.
+ * Weights: bf16 K-major w1 [c1][cin], w2 [c2][9*c1] (tap-major: (ky*3+kx)*c1 + c), w3 [c3][c2];
+ * bias: fp32 [c1 + c2 + c3] (zeros where the reference has no bias). `out` must not alias `in`.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ay2_chain_desc {
+  int32_t batch, in_h, in_w;  /* stride 1: output size == input size */
+  int32_t cin, in_cstride;
+  int32_t c1, act1;
+  int32_t kh, kw, stride, pad; /* stage 2: 3, 3, 1, 1 */
+  int32_t c2, act2;
+  int32_t c3, act3;            /* c3 == 0: no third stage */
+  int32_t out_cstride;
+  int32_t res_cstride;         /* 0 = no residual */
+} ay2_chain_desc;
+typedef struct ay2_chain_plan ay2_chain_plan;
+/* 1 if the fused kernel covers this chain (otherwise run the links as separate ay2_conv_plan launches). */
+int ay2_chain_supported(const ay2_chain_desc* desc);
+int ay2_chain_plan_create(const ay2_chain_desc* desc, const void* in, const void* w1, const void* w2, const void* w3,
+                          const float* bias, const void* residual, void* out, ay2_chain_plan** plan);
+int ay2_chain_plan_run(const ay2_chain_plan* plan, void* stream);
+int ay2_chain_plan_destroy(ay2_chain_plan* plan);
+double ay2_chain_plan_flops(const ay2_chain_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
  * Input side: NCHW image (uint8 or fp32) -> 2x2 space-to-depth NHWC bf16 with 16 channels
  * (12 used: channel = (dy*2+dx)*3 + c for input pixel (2y+dy, 2x+dx); 4 zero), scaled by `scale`.
  * Replaces YoloValidator.prepare_img / AbstractTrainer.prepare_img (scripts/utils/train_utils.py:255-260,
