@@ -30,6 +30,8 @@ class ConvDesc(C.Structure):
         ("cout_pad", C.c_int32), ("pad_w", C.c_int32),
         ("in_pix_stride", C.c_int32), ("in_row_pixels", C.c_int32),
         ("out_pix_stride", C.c_int32), ("out_row_pixels", C.c_int32),
+        ("cin_split", C.c_int32), ("in2_cstride", C.c_int32),
+        ("in2", C.c_void_p),
     ]
 
 
@@ -102,6 +104,8 @@ _PROTOS = {
     "ay2_chain_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ay2_chain_plan_destroy": (C.c_int, [C.c_void_p]),
     "ay2_chain_plan_flops": (C.c_double, [C.c_void_p]),
+    "ay2_chain_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "ay2_chain_plan_set_debug": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ay2_space_to_depth": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_sppf_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

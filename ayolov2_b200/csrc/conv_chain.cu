@@ -47,6 +47,7 @@ struct ChainParams {
   CUtensorMap tmOut;  // output [C][W][H][B], box [oc][8][16][1]
   CUtensorMap tmRes;  // residual, same geometry as the output
   const float* bias;  // [c1 + c2 + c3] fp32 (zeros where the reference has no bias)
+  unsigned long long* dbg;  // optional timeline buffer (tools/chain_timeline.py): block 0 records %globaltimer per phase
   int tiles_x, tiles_y, num_tiles;
   int in_h, in_w;
   int cin_chunks, ck1, c1, act1;
@@ -54,10 +55,12 @@ struct ChainParams {
   int c3, n3, n3_tiles, c2_chunks, ck3, act3;  // c3 == 0: no stage 3
   int has_res;
   int oc;            // channels per output slab (64 / 32 / 16); swizzle span = 2*oc bytes
-  int nstages, slot_bytes;
+  int nx, x_slot, xw_off;  // X ring: slots of [x halo chunk | W1 chunk]; W1 chunk at byte offset xw_off inside a slot
+  int nw, w_slot;          // W ring: W2 / W3 chunks
+  int alias_staging;       // the output staging buffer re-uses T's bytes (T is dead once stage 2 has finished)
   int t_plane;       // bytes of one 8-channel plane of T (CH_NH * 16)
-  int tmem_cols, d2_col;
-  int off_T, off_U, off_staging, off_bias, off_bars;  // byte offsets from the 1024-aligned shared-memory base
+  int tmem_cols, d2_col;   // TMEM: [0, d2_col) = D1 rows 0..127 / D3 tile; [d2_col, ..) = D1 rows 128..255 / D2
+  int off_W, off_T, off_U, off_staging, off_bias, off_bars;  // byte offsets from the 1024-aligned shared-memory base
 };
 
 __device__ __forceinline__ void ch_bar_sync(int id, int nthreads) {
@@ -92,6 +95,16 @@ __device__ __forceinline__ uint32_t swizzled_offset_rt(uint32_t row, uint32_t ch
   return off ^ (((off >> 7) & mask) << 4);
 }
 
+__device__ __forceinline__ unsigned long long ch_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CH_DBG(it, slot)                                                            \
+  do {                                                                              \
+    if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = ch_now(); \
+  } while (0)
+
 __device__ __forceinline__ float ch_act(float x, int act) { return act == AY2_ACT_SILU ? silu_f(x) : x; }
 
 // Final epilogue of one accumulator tile: TMEM -> +bias -> act (-> + residual) -> bf16 -> swizzled staging -> TMA store.
@@ -106,6 +119,8 @@ __device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* 
   if (et == 0) {
     tma_store_wait_read<0>();  // the previous tile's stores have finished reading the staging buffer
     if (p.has_res) {
+      // staging aliased onto T: the tensor core may still be reading T until this accumulator is complete
+      if (p.alias_staging) mbar_wait(acc_full, acc_phase);
       mbar_expect_tx(res_full, 128 * ncols * 2);
       for (int s = 0; s < nslab; ++s) tma_load_4d(&p.tmRes, res_full, staging + s * slab_bytes, n0 + s * p.oc, x0, y0, b);
     }
@@ -113,6 +128,7 @@ __device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* 
   ch_bar_sync(1, CH_EPI_THREADS);
   mbar_wait(acc_full, acc_phase);
   tcgen05_fence_after();
+  if (et == 0 && p.dbg && blockIdx.x == 0) p.dbg[15] = ch_now();  // last accumulator-complete time (see CH_DBG)
   if (p.has_res) {
     mbar_wait(res_full, res_phase);
     res_phase ^= 1;
@@ -159,39 +175,46 @@ __device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* 
 __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;
+  uint8_t* xring = smem;
+  uint8_t* wring = smem + p.off_W;
   uint8_t* T = smem + p.off_T;
   uint8_t* U = smem + p.off_U;
   uint8_t* staging = smem + p.off_staging;
   float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
-  uint64_t* full_bar = bars;                        // [CH_MAX_STAGES]
-  uint64_t* empty_bar = bars + CH_MAX_STAGES;       // [CH_MAX_STAGES]
-  uint64_t* d1_full = bars + 2 * CH_MAX_STAGES;     // MMA -> epilogue 1
+  uint64_t* wfull = bars;                           // [CH_MAX_STAGES] W ring
+  uint64_t* wempty = bars + CH_MAX_STAGES;          // [CH_MAX_STAGES]
+  uint64_t* xfull = bars + 2 * CH_MAX_STAGES;       // [2] X ring
+  uint64_t* xempty = xfull + 2;                     // [2]
+  uint64_t* d1_full = xfull + 4;                    // MMA -> epilogue 1
   uint64_t* t_ready = d1_full + 1;                  // epilogue 1 -> MMA (T written, D1 drained)
   uint64_t* d2_full = d1_full + 2;
   uint64_t* u_ready = d1_full + 3;
   uint64_t* d3_full = d1_full + 4;
-  uint64_t* d3_empty = d1_full + 5;
+  uint64_t* acc_empty = d1_full + 5;                // final epilogue -> MMA: last accumulator drained
   uint64_t* res_full = d1_full + 6;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(d1_full + 7);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int swa1 = p.ck1 * 2, swa2 = p.ck2 * 2, swa3 = p.ck3 * 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nstages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < p.nw; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], 1);
+    }
+    for (int i = 0; i < p.nx; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
     }
     mbar_init(d1_full, 1);
     mbar_init(t_ready, CH_EPI_THREADS);
     mbar_init(d2_full, 1);
     mbar_init(u_ready, CH_EPI_THREADS);
     mbar_init(d3_full, 1);
-    mbar_init(d3_empty, CH_EPI_THREADS);
+    mbar_init(acc_empty, CH_EPI_THREADS);
     mbar_init(res_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmX);
@@ -208,124 +231,169 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0, phase = 0;
+    // All 32 lanes run the loop (warp-uniform control flow keeps addresses / coordinates in uniform registers);
+    // one elected lane issues the copies.
+    {
+      int ws = 0, wph = 0, xs = 0, xph = 0;
+      const int nx = p.nx, nw = p.nw, x_slot = p.x_slot, w_slot = p.w_slot, xw_off = p.xw_off;
+      const int cin_chunks = p.cin_chunks, c1_chunks = p.c1_chunks, c2_chunks = p.c2_chunks, n3_tiles = p.n3_tiles;
+      const int ck1 = p.ck1, ck2 = p.ck2, ck3 = p.ck3, c1 = p.c1, n3 = p.n3;
+      const uint32_t xbytes = (CH_NH + p.c1) * swa1, w2bytes = p.c2 * swa2, w3bytes = p.n3 * swa3;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img;
         const int r = tile - b * tiles_per_img;
         const int ty = r / p.tiles_x;
         const int y0 = ty * CH_TH, x0 = (r - ty * p.tiles_x) * CH_TW;
-        for (int kc = 0; kc < p.cin_chunks; ++kc) {  // stage 1: halo chunk of x + W1 chunk
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* slot = ring + stage * p.slot_bytes;
-          mbar_expect_tx(&full_bar[stage], (CH_NH + p.c1) * swa1);
-          tma_load_4d(&p.tmX, &full_bar[stage], slot, kc * p.ck1, x0 - 1, y0 - 1, b);
-          tma_load_2d(&p.tmW1, &full_bar[stage], slot + 256 * swa1, kc * p.ck1, 0);
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        for (int kc = 0; kc < cin_chunks; ++kc) {  // stage 1: halo chunk of x + W1 chunk
+          mbar_wait(&xempty[xs], xph ^ 1);
+          if (elect_one()) {
+            uint8_t* slot = xring + xs * x_slot;
+            mbar_expect_tx(&xfull[xs], xbytes);
+            tma_load_4d(&p.tmX, &xfull[xs], slot, kc * ck1, x0 - 1, y0 - 1, b);
+            tma_load_2d(&p.tmW1, &xfull[xs], slot + xw_off, kc * ck1, 0);
+          }
+          __syncwarp();
+          if (++xs == nx) { xs = 0; xph ^= 1; }
         }
         for (int tap = 0; tap < 9; ++tap) {          // stage 2: W2 per tap and channel chunk
-          for (int cc = 0; cc < p.c1_chunks; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], p.c2 * swa2);
-            tma_load_2d(&p.tmW2, &full_bar[stage], ring + stage * p.slot_bytes, tap * p.c1 + cc * p.ck2, 0);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          for (int cc = 0; cc < c1_chunks; ++cc) {
+            mbar_wait(&wempty[ws], wph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&wfull[ws], w2bytes);
+              tma_load_2d(&p.tmW2, &wfull[ws], wring + ws * w_slot, tap * c1 + cc * ck2, 0);
+            }
+            __syncwarp();
+            if (++ws == nw) { ws = 0; wph ^= 1; }
           }
         }
-        for (int n = 0; n < p.n3_tiles; ++n) {       // stage 3: W3 per N tile and channel chunk
-          for (int cc = 0; cc < p.c2_chunks; ++cc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], p.n3 * swa3);
-            tma_load_2d(&p.tmW3, &full_bar[stage], ring + stage * p.slot_bytes, cc * p.ck3, n * p.n3);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        for (int n = 0; n < n3_tiles; ++n) {         // stage 3: W3 per N tile and channel chunk
+          for (int cc = 0; cc < c2_chunks; ++cc) {
+            mbar_wait(&wempty[ws], wph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&wfull[ws], w3bytes);
+              tma_load_2d(&p.tmW3, &wfull[ws], wring + ws * w_slot, cc * ck3, n * n3);
+            }
+            __syncwarp();
+            if (++ws == nw) { ws = 0; wph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // Warp-uniform loop, one elected lane issues tcgen05.mma / commit (see the producer).
+    {
       const uint32_t idesc1 = make_idesc_bf16_f32(128, p.c1);
       const uint32_t idesc2 = make_idesc_bf16_f32(128, p.c2);
       const uint32_t idesc3 = make_idesc_bf16_f32(128, p.n3 > 0 ? p.n3 : 16);
       const uint32_t t_addr = smem_u32(T), u_addr = smem_u32(U);
-      int stage = 0, phase = 0;
-      uint32_t t_phase = 0, u_phase = 0, d3e_phase = 0;
-      bool d3_pending = false;  // an accumulator in the D1/D3 column range has been handed to the epilogue
+      const uint32_t xring_a = smem_u32(xring), wring_a = smem_u32(wring);
+      const int nx = p.nx, nw = p.nw, x_slot = p.x_slot, w_slot = p.w_slot, xw_off = p.xw_off;
+      const int cin_chunks = p.cin_chunks, c1_chunks = p.c1_chunks, c2_chunks = p.c2_chunks, n3_tiles = p.n3_tiles;
+      const int ks1 = p.ck1 / 16, ks2 = p.ck2 / 16, ks3 = p.ck3 / 16;
+      const uint32_t t_plane = p.t_plane;
+      const uint32_t d2_t = tmem_base + p.d2_col;
+      const bool has3 = p.c3 != 0;
+      int ws = 0, wph = 0, xs = 0, xph = 0;
+      uint32_t t_phase = 0, u_phase = 0, ae_phase = 0;
+      bool acc_pending = false;  // the last accumulator handed to the final epilogue has not been drained yet
+      int it = -1;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        if (d3_pending) {  // D3 shares its TMEM columns with D1
-          mbar_wait(d3_empty, d3e_phase);
-          d3e_phase ^= 1;
-          d3_pending = false;
-          tcgen05_fence_after();
+        ++it;
+        if (lane == 0) CH_DBG(it, 0);  // tile start (MMA warp)
+        if (acc_pending) {  // D1 shares its TMEM columns with D2 / D3 of the previous tile
+          mbar_wait(acc_empty, ae_phase);
+          ae_phase ^= 1;
+          acc_pending = false;
         }
         // ---- stage 1: D1[half] = Xhalo[half*128 .. +128) x W1^T
-        for (int kc = 0; kc < p.cin_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kc = 0; kc < cin_chunks; ++kc) {
+          mbar_wait(&xfull[xs], xph);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(ring + stage * p.slot_bytes);
-          const uint32_t b_addr = a_addr + 256 * swa1;
-          for (int half = 0; half < 2; ++half) {
-            for (int k = 0; k < p.ck1 / 16; ++k) {
-              const uint64_t adesc = make_smem_desc_kmajor(a_addr + half * 128 * swa1 + k * 32, swa1);
-              const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa1);
-              umma_f16_ss(tmem_base + half * p.c1, adesc, bdesc, idesc1, (kc | k) != 0 ? 1u : 0u);
+          if (kc == 0 && lane == 0) CH_DBG(it, 1);  // previous accumulator drained and first x chunk landed
+          const uint32_t a_addr = xring_a + xs * x_slot;
+          const uint32_t b_addr = a_addr + xw_off;
+          if (elect_one()) {
+            for (int half = 0; half < 2; ++half) {
+              for (int k = 0; k < ks1; ++k) {
+                const uint64_t adesc = make_smem_desc_kmajor(a_addr + half * 128 * swa1 + k * 32, swa1);
+                const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa1);
+                umma_f16_ss(half ? d2_t : tmem_base, adesc, bdesc, idesc1, (kc | k) != 0 ? 1u : 0u);
+              }
             }
+            umma_commit(&xempty[xs]);
+            if (kc == cin_chunks - 1) umma_commit(d1_full);
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (++xs == nx) { xs = 0; xph ^= 1; }
         }
-        umma_commit(d1_full);
+        if (lane == 0) CH_DBG(it, 2);  // stage-1 MMAs issued
         // ---- stage 2: D2 += T(shifted by tap) x W2[tap]^T
         mbar_wait(t_ready, t_phase);
         t_phase ^= 1;
         tcgen05_fence_after();
-        uint32_t accum = 0;
+        if (lane == 0) CH_DBG(it, 3);  // T ready
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3;
           const uint32_t a_tap = t_addr + (ky * CH_HW + kx) * 16;
-          for (int cc = 0; cc < p.c1_chunks; ++cc) {
-            mbar_wait(&full_bar[stage], phase);
+          for (int cc = 0; cc < c1_chunks; ++cc) {
+            const bool rec = p.dbg && blockIdx.x == 0 && it == 1 && tap < 4 && cc == 0 && lane == 0;
+            long long k0 = 0, k1 = 0, k2 = 0;
+            if (rec) k0 = clock64();
+            mbar_wait(&wfull[ws], wph);
             tcgen05_fence_after();
-            const uint32_t b_addr = smem_u32(ring + stage * p.slot_bytes);
-            for (int k = 0; k < p.ck2 / 16; ++k) {
-              const int c16 = cc * (p.ck2 / 16) + k;
-              const uint64_t adesc = make_smem_desc_nosw(a_tap + c16 * 2 * p.t_plane, p.t_plane, CH_HW * 16);
-              const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa2);
-              umma_f16_ss(tmem_base + p.d2_col, adesc, bdesc, idesc2, accum);
-              accum = 1;
+            if (rec) k1 = clock64();
+            const uint32_t b_addr = wring_a + ws * w_slot;
+            if (elect_one()) {
+              for (int k = 0; k < ks2; ++k) {
+                const uint32_t c16 = cc * ks2 + k;
+                const uint64_t adesc = make_smem_desc_nosw(a_tap + c16 * 2 * t_plane, t_plane, CH_HW * 16);
+                const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa2);
+                umma_f16_ss(d2_t, adesc, bdesc, idesc2, (tap | cc | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(&wempty[ws]);
+              if (tap == 8 && cc == c1_chunks - 1) umma_commit(d2_full);
             }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            __syncwarp();
+            if (rec) {
+              k2 = clock64();
+              p.dbg[128 + tap * 4 + 0] = k0, p.dbg[128 + tap * 4 + 1] = k1, p.dbg[128 + tap * 4 + 2] = k2, p.dbg[128 + tap * 4 + 3] = k2;
+            }
+            if (++ws == nw) { ws = 0; wph ^= 1; }
           }
         }
-        umma_commit(d2_full);
+        if (lane == 0) CH_DBG(it, 4);  // stage-2 MMAs issued (all W2 chunks had landed)
+        if (!has3) acc_pending = true;
         // ---- stage 3: D3[n] = U x W3[n]^T
-        if (p.c3) {
+        if (has3) {
           mbar_wait(u_ready, u_phase);
           u_phase ^= 1;
           tcgen05_fence_after();
-          for (int n = 0; n < p.n3_tiles; ++n) {
-            if (d3_pending) {
-              mbar_wait(d3_empty, d3e_phase);
-              d3e_phase ^= 1;
-              d3_pending = false;
+          for (int n = 0; n < n3_tiles; ++n) {
+            if (acc_pending) {
+              mbar_wait(acc_empty, ae_phase);
+              ae_phase ^= 1;
+              acc_pending = false;
               tcgen05_fence_after();
             }
-            for (int cc = 0; cc < p.c2_chunks; ++cc) {
-              mbar_wait(&full_bar[stage], phase);
+            for (int cc = 0; cc < c2_chunks; ++cc) {
+              mbar_wait(&wfull[ws], wph);
               tcgen05_fence_after();
-              const uint32_t b_addr = smem_u32(ring + stage * p.slot_bytes);
-              for (int k = 0; k < p.ck3 / 16; ++k) {
-                const int c16 = cc * (p.ck3 / 16) + k;
-                const uint64_t adesc = make_smem_desc_nosw(u_addr + c16 * 2 * CH_U_PLANE, CH_U_PLANE, 128);
-                const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa3);
-                umma_f16_ss(tmem_base, adesc, bdesc, idesc3, (cc | k) != 0 ? 1u : 0u);
+              const uint32_t b_addr = wring_a + ws * w_slot;
+              if (elect_one()) {
+                for (int k = 0; k < ks3; ++k) {
+                  const uint32_t c16 = cc * ks3 + k;
+                  const uint64_t adesc = make_smem_desc_nosw(u_addr + c16 * 2 * CH_U_PLANE, CH_U_PLANE, 128);
+                  const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, swa3);
+                  umma_f16_ss(tmem_base, adesc, bdesc, idesc3, (cc | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&wempty[ws]);
+                if (cc == c2_chunks - 1) umma_commit(d3_full);
               }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+              __syncwarp();
+              if (++ws == nw) { ws = 0; wph ^= 1; }
             }
-            umma_commit(d3_full);
-            d3_pending = true;
+            acc_pending = true;
           }
         }
       }
@@ -338,15 +406,22 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
     const float* bias1 = bias_s;
     const float* bias2 = bias_s + p.c1;
     const float* bias3 = bias_s + p.c1 + p.c2;
+    int it = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      ++it;
       const int b = tile / tiles_per_img;
       const int r = tile - b * tiles_per_img;
       const int ty = r / p.tiles_x;
       const int y0 = ty * CH_TH, x0 = (r - ty * p.tiles_x) * CH_TW;
       // ---- epilogue 1: D1 -> T
+      if (p.alias_staging) {  // T is about to be rewritten: the previous tile's TMA store must have read it out
+        if (et == 0) tma_store_wait_read<0>();
+        ch_bar_sync(1, CH_EPI_THREADS);
+      }
       mbar_wait(d1_full, d1_phase);
       d1_phase ^= 1;
       tcgen05_fence_after();
+      if (et == 0) CH_DBG(it, 8);  // D1 complete
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         if (half * 128 + (et & ~31) >= CH_NH) continue;  // warp-uniform: this warp's rows are all beyond the halo
@@ -357,7 +432,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
           const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
           inb = iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
         }
-        const uint32_t tbase = tmem_base + lane_off + half * p.c1;
+        const uint32_t tbase = tmem_base + lane_off + half * p.d2_col;
         const uint32_t trow = smem_u32(T) + h * 16;
 #pragma unroll 1
         for (int c0 = 0; c0 < p.c1; c0 += 16) {
@@ -382,11 +457,13 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
       tcgen05_fence_before();
       fence_proxy_async_smem();  // generic-proxy writes of T -> visible to the tensor core's async-proxy reads
       mbar_arrive(t_ready);
+      if (et == 0) CH_DBG(it, 9);  // epilogue 1 done
       if (p.c3 == 0) {
         // ---- epilogue 2 = final
         chain_store_tile(p, staging, bias2, tmem_base + lane_off + p.d2_col, p.c2, p.act2, 0, x0, y0, b, et, d2_full,
-                         d2_phase, nullptr, res_full, res_phase);
+                         d2_phase, acc_empty, res_full, res_phase);
         d2_phase ^= 1;
+        if (et == 0) CH_DBG(it, 11);  // final epilogue done (store issued)
       } else {
         // ---- epilogue 2: D2 -> U
         mbar_wait(d2_full, d2_phase);
@@ -415,7 +492,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
         // ---- epilogue 3 per N tile
         for (int n = 0; n < p.n3_tiles; ++n) {
           chain_store_tile(p, staging, bias3, tmem_base + lane_off, p.n3, p.act3, n * p.n3, x0, y0, b, et, d3_full, d3_phase,
-                           d3_empty, res_full, res_phase);
+                           acc_empty, res_full, res_phase);
           d3_phase ^= 1;
         }
       }
@@ -475,30 +552,22 @@ extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, co
   kp.tiles_x = ceil_div(W, CH_TW);
   kp.tiles_y = ceil_div(H, CH_TH);
   kp.num_tiles = kp.tiles_x * kp.tiles_y * d->batch;
-  kp.ck1 = chunk_for(d->cin);
-  kp.cin_chunks = d->cin / kp.ck1;
   kp.c1 = d->c1;
   kp.act1 = d->act1;
-  kp.ck2 = chunk_for(d->c1);
-  kp.c1_chunks = d->c1 / kp.ck2;
   kp.c2 = d->c2;
   kp.act2 = d->act2;
   kp.c3 = d->c3;
   kp.act3 = d->act3;
   if (d->c3) {
-    kp.ck3 = chunk_for(d->c2);
-    kp.c2_chunks = d->c2 / kp.ck3;
-    // N tile of stage 3: the largest divisor of c3 that is a multiple of 16 and <= 256
+    // N tile of stage 3: the largest divisor of c3 that is a multiple of 16 and <= 128 (staging and W3 slots stay small)
     int n3 = 0;
-    for (int cand = 256; cand >= 16; cand -= 16)
+    for (int cand = 128; cand >= 16; cand -= 16)
       if (d->c3 % cand == 0) {
         n3 = cand;
         break;
       }
     kp.n3 = n3;
     kp.n3_tiles = d->c3 / n3;
-  } else {
-    kp.ck3 = 16;
   }
   kp.has_res = d->res_cstride != 0;
   const int cout = d->c3 ? d->c3 : d->c2;
@@ -506,52 +575,72 @@ extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, co
   kp.oc = ntile % 64 == 0 ? 64 : (ntile % 32 == 0 ? 32 : 16);
   kp.t_plane = CH_NH * 16;
   kp.bias = bias;
-  // TMEM: [0, max(2*c1, n3)) = D1 halves / D3 tile, then D2
-  const int regA = 2 * d->c1 > kp.n3 ? 2 * d->c1 : kp.n3;
+  // TMEM: region A [0, max(c1, n3)) = D1 rows 0..127, later the D3 tile; region B = D1 rows 128..255, later D2
+  const int regA = d->c1 > kp.n3 ? d->c1 : kp.n3;
+  const int regB = d->c1 > d->c2 ? d->c1 : d->c2;
   kp.d2_col = regA;
-  int cols = regA + d->c2, pow2 = 32;
+  int cols = regA + regB, pow2 = 32;
   while (pow2 < cols) pow2 *= 2;
   AY2_REQUIRE(pow2 <= 512, "chain needs %d TMEM columns", cols);
   kp.tmem_cols = pow2;
-  // shared memory
-  const int swa1 = kp.ck1 * 2, swa2 = kp.ck2 * 2, swa3 = kp.ck3 * 2;
-  int slot = (256 + d->c1) * swa1;
-  if (d->c2 * swa2 > slot) slot = d->c2 * swa2;
-  if (d->c3 && kp.n3 * swa3 > slot) slot = kp.n3 * swa3;
-  slot = round_up_i(slot, 1024);
+  // Shared memory: [X ring | W ring | T | U | staging | bias | barriers]. Pick the layout that lets most CTAs share an
+  // SM (the stages of one tile are serialised inside a CTA; co-resident CTAs are what overlaps tensor, epilogue and TMA
+  // work): first fewer X slots, then staging aliased onto T, then 32-channel instead of 64-channel operand chunks.
   const int t_bytes = round_up_i(d->c1 / 8 * kp.t_plane, 1024);
   const int u_bytes = d->c3 ? d->c2 / 8 * CH_U_PLANE : 0;
   const int staging_bytes = 128 * ntile * 2;
   const int bias_bytes = round_up_i((d->c1 + d->c2 + d->c3) * 4, 128);
-  const int bars_bytes = (2 * CH_MAX_STAGES + 8) * 8;
-  const int fixed = t_bytes + u_bytes + staging_bytes + bias_bytes + bars_bytes + 1024 /* alignment slack */;
-  int ctas = 0, nst = 0;
-  for (int c = 3; c >= 1 && !ctas; --c) {  // 68 registers x 256 threads: at most 3 CTAs per SM
+  const int bars_bytes = (2 * CH_MAX_STAGES + 4 + 8) * 8;
+  int ctas = 0;
+  static const int env_ctas = getenv("AY2_CHAIN_MAX_CTAS") ? atoi(getenv("AY2_CHAIN_MAX_CTAS")) : 3;
+  for (int c = env_ctas < 3 ? (env_ctas < 1 ? 1 : env_ctas) : 3; c >= 1 && !ctas; --c) {  // 75 registers x 256 threads: <= 3 CTAs / SM
     if (kp.tmem_cols * c > 512) continue;
     const int budget = 227 * 1024 / c - 1024;
-    int n = (budget - fixed) / slot;
-    if (n > CH_MAX_STAGES) n = CH_MAX_STAGES;
-    if (n >= (c == 1 ? 2 : 3)) {
-      ctas = c;
-      nst = n;
+    for (int small = 0; small < 2 && !ctas; ++small) {
+      const int cap = small ? 32 : 64;
+      const int ck1 = chunk_for(d->cin) > cap ? cap : chunk_for(d->cin);
+      const int ck2 = chunk_for(d->c1) > cap ? cap : chunk_for(d->c1);
+      const int ck3 = d->c3 ? (chunk_for(d->c2) > cap ? cap : chunk_for(d->c2)) : 16;
+      const int swa1 = ck1 * 2, swa2 = ck2 * 2, swa3 = ck3 * 2;
+      const int xw_off = round_up_i(CH_NH * swa1, 1024);
+      const int x_slot = round_up_i(xw_off + d->c1 * swa1, 1024);
+      int w_slot = d->c2 * swa2;
+      if (d->c3 && kp.n3 * swa3 > w_slot) w_slot = kp.n3 * swa3;
+      w_slot = round_up_i(w_slot, 1024);
+      const int cin_chunks = d->cin / ck1;
+      const int w_slots_per_tile = 9 * (d->c1 / ck2) + (d->c3 ? kp.n3_tiles * (d->c2 / ck3) : 0);
+      static const int opts[4][2] = {{2, 0}, {1, 0}, {2, 1}, {1, 1}};  // (X slots, staging aliased onto T)
+      for (int o = 0; o < 4 && !ctas; ++o) {
+        const int nx = opts[o][0] < cin_chunks + 1 ? opts[o][0] : cin_chunks + 1, alias = opts[o][1];
+        const int t_region = alias && staging_bytes > t_bytes ? staging_bytes : t_bytes;
+        const int fixed = nx * x_slot + t_region + u_bytes + (alias ? 0 : staging_bytes) + bias_bytes + bars_bytes + 2048;
+        int nw = (budget - fixed) / w_slot;
+        if (nw > CH_MAX_STAGES) nw = CH_MAX_STAGES;
+        if (nw > w_slots_per_tile + 2) nw = w_slots_per_tile + 2;  // a deeper ring than one tile's worth buys nothing
+        const int need = w_slots_per_tile < 4 ? w_slots_per_tile : 4;
+        if (nw >= need || (c == 1 && small && o == 3 && nw >= 2)) {
+          ctas = c;
+          kp.ck1 = ck1, kp.ck2 = ck2, kp.ck3 = ck3;
+          kp.cin_chunks = cin_chunks;
+          kp.c1_chunks = d->c1 / ck2;
+          kp.c2_chunks = d->c3 ? d->c2 / ck3 : 0;
+          kp.nx = nx, kp.nw = nw, kp.alias_staging = alias;
+          kp.xw_off = xw_off, kp.x_slot = x_slot, kp.w_slot = w_slot;
+          kp.off_W = nx * x_slot;
+          kp.off_T = kp.off_W + nw * w_slot;
+          kp.off_U = kp.off_T + t_region;
+          kp.off_staging = alias ? kp.off_T : round_up_i(kp.off_U + u_bytes, 1024);
+          kp.off_bias = alias ? round_up_i(kp.off_U + u_bytes, 128) : kp.off_staging + staging_bytes;
+          kp.off_bars = kp.off_bias + bias_bytes;
+        }
+      }
     }
   }
   if (!ctas) {
     delete pl;
-    set_error("chain cin=%d c1=%d c2=%d c3=%d does not fit in shared memory (fixed %d B + 2 x %d B)", d->cin, d->c1, d->c2,
-              d->c3, fixed, slot);
+    set_error("chain cin=%d c1=%d c2=%d c3=%d does not fit in shared memory", d->cin, d->c1, d->c2, d->c3);
     return AY2_ERR_INVALID;
   }
-  // a deeper ring than one tile's worth of slots buys nothing
-  const int slots_per_tile = kp.cin_chunks + 9 * kp.c1_chunks + kp.n3_tiles * kp.c2_chunks;
-  if (nst > slots_per_tile + 2) nst = slots_per_tile + 2;
-  kp.nstages = nst;
-  kp.slot_bytes = slot;
-  kp.off_T = nst * slot;
-  kp.off_U = kp.off_T + t_bytes;
-  kp.off_staging = round_up_i(kp.off_U + u_bytes, 1024);
-  kp.off_bias = kp.off_staging + staging_bytes;
-  kp.off_bars = kp.off_bias + bias_bytes;
   pl->smem = (size_t)kp.off_bars + bars_bytes + 1024;
   pl->ctas_per_sm = ctas;
 
@@ -583,6 +672,19 @@ extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, co
   const int resident = sms * ctas;
   pl->grid = kp.num_tiles < resident ? kp.num_tiles : resident;
   *plan_out = pl;
+  return AY2_OK;
+}
+
+extern "C" int ay2_chain_plan_set_debug(ay2_chain_plan* pl, unsigned long long* dbg) {
+  AY2_REQUIRE(pl, "ay2_chain_plan_set_debug: null plan");
+  pl->kp.dbg = dbg;  // device buffer of (16 x 16 + 64) uint64 (block 0's per-phase %globaltimer for its first 16 tiles), or NULL
+  return AY2_OK;
+}
+
+extern "C" int ay2_chain_plan_info(const ay2_chain_plan* pl, int32_t* out8) {
+  AY2_REQUIRE(pl && out8, "ay2_chain_plan_info: null argument");
+  out8[0] = pl->ctas_per_sm, out8[1] = pl->grid, out8[2] = (int)pl->smem, out8[3] = pl->kp.nx, out8[4] = pl->kp.nw;
+  out8[5] = pl->kp.alias_staging, out8[6] = pl->kp.tmem_cols, out8[7] = pl->kp.ck2;
   return AY2_OK;
 }
 

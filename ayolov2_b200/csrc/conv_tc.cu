@@ -36,6 +36,8 @@ struct ConvKernelParams {
   int kh, kw, stride, pad, pad_w;
   int cin_chunks;  // Cin / CK
   int cin;         // K extent per tap in the packed weights
+  int split_chunks;  // > 0: channel chunks >= split_chunks come from the second input view tmA[3] (stride-1 convs only):
+                     // the consumer-side form of torch.cat([a, b], 1) when a and b live in different buffers
   int cout_pad;
   int act, has_res;
   int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   uint64_t* res_full = tmem_empty + 2;            // [1]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_k_chunks = p.kh * p.kw * p.cin_chunks;
 
@@ -218,7 +220,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // All 32 lanes run the loop: warp-uniform control flow lets the compiler keep coordinates and addresses in uniform
+    // registers; one elected lane issues the copies (no per-instruction uniformisation loops in the SASS).
+    {
       int stage = 0, phase = 0;
       const int box_rows = p.BH * p.BW;
       for (int item = item0; item < total_items; item += item_step) {
@@ -250,26 +254,31 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
               dx = (ux - pw) >> 1;
               view = ph * 2 + pw;
             }
-            const CUtensorMap* tmA = &p.tmA[view];
             const int kbase = (kh * p.kw + kw) * p.cin;
             for (int cc = 0; cc < p.cin_chunks; ++cc) {
+              const bool second = p.split_chunks > 0 && cc >= p.split_chunks;
+              const CUtensorMap* tmA = second ? &p.tmA[3] : &p.tmA[view];
+              const int ccoord = (second ? cc - p.split_chunks : cc) * CK;
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
-              uint8_t* sb = sa + Cfg::A_BYTES;
-              mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (elect_one()) {
+                uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
+                uint8_t* sb = sa + Cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (j < p.NB)
-                  tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, cc * CK, bx[j] + dx,
-                              by[j] + dy, bb[j]);
+                for (int j = 0; j < 8; ++j) {
+                  if (j < p.NB)
+                    tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx,
+                                by[j] + dy, bb[j]);
+                }
+                if (p.csize > 1) {
+                  constexpr int HALF_ROWS = BLOCK_N / 2;
+                  tma_load_2d_mc(&p.tmB, &full_bar[stage], sb + crank * HALF_ROWS * Cfg::SWA, kbase + cc * CK,
+                                 n0 + crank * HALF_ROWS, cmask);
+                } else {
+                  tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
+                }
               }
-              if (p.csize > 1) {
-                constexpr int HALF_ROWS = BLOCK_N / 2;
-                tma_load_2d_mc(&p.tmB, &full_bar[stage], sb + crank * HALF_ROWS * Cfg::SWA, kbase + cc * CK,
-                               n0 + crank * HALF_ROWS, cmask);
-              } else {
-                tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
-              }
+              __syncwarp();
               if (++stage == Cfg::NSTAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -281,7 +290,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    {  // warp-uniform loop, one elected lane issues (see the producer)
       constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
       int stage = 0, phase = 0, it = 0;
       for (int item = item0; item < total_items; item += item_step, ++it) {
@@ -295,20 +304,23 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(stages + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < CK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc_kmajor(a_addr + k * 32, Cfg::SWA);
-            const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
-            umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_kmajor(a_addr + k * 32, Cfg::SWA);
+              const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
+              umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+            }
+            if (p.csize > 1) umma_commit_mc(&empty_bar[stage], cmask);  // release the stage in every CTA of the cluster
+            else umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+            if (kc == num_k_chunks - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
           }
-          if (p.csize > 1) umma_commit_mc(&empty_bar[stage], cmask);  // release the stage in every CTA of the cluster
-          else umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          __syncwarp();
           if (++stage == Cfg::NSTAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
       }
     }
   } else if (warp >= 4) {
@@ -577,7 +589,11 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   ay2_conv_plan* pl = new ay2_conv_plan();
   memset(pl, 0, sizeof(*pl));
   pl->desc = *d;
-  const int ck = d->cin % 64 == 0 ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+  const int split = d->cin_split;
+  AY2_REQUIRE(split == 0 || (d->stride == 1 && d->in2 && split > 0 && split < d->cin && split % 16 == 0 && d->in2_cstride % 8 == 0 &&
+                             d->in_pix_stride <= 0 && d->in_row_pixels <= 0),
+              "two-source input needs stride 1, a second pointer, and cin_split a multiple of 16 inside (0, cin)");
+  const int ck = (d->cin % 64 == 0 && split % 64 == 0) ? 64 : ((d->cin % 32 == 0 && split % 32 == 0) ? 32 : 16);
   pl->block_n = bn;
   pl->ck = ck;
   ConvKernelParams& kp = pl->kp;
@@ -599,6 +615,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   kp.pad_w = pad_w;
   kp.cin = d->cin;
   kp.cin_chunks = d->cin / ck;
+  kp.split_chunks = split / ck;
   kp.cout_pad = d->cout_pad;
   kp.act = d->act;
   kp.has_res = d->res_cstride != 0;
@@ -608,8 +625,11 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   const int64_t cs = d->in_cstride;
   if (d->stride == 1) {
     // pix_stride < cin gives overlapping windows of neighbouring pixels (the packed 16-channel stem)
-    rc = encode_act_map(&kp.tmA[0], in, d->cin, d->in_w, d->in_h, d->batch, pix_stride, pix_stride * row_pixels,
+    rc = encode_act_map(&kp.tmA[0], in, split ? split : d->cin, d->in_w, d->in_h, d->batch, pix_stride, pix_stride * row_pixels,
                         pix_stride * row_pixels * d->in_h, ck, bw, bh);
+    if (rc == AY2_OK && split)
+      rc = encode_act_map(&kp.tmA[3], d->in2, d->cin - split, d->in_w, d->in_h, d->batch, d->in2_cstride,
+                          (int64_t)d->in2_cstride * d->in_w, (int64_t)d->in2_cstride * d->in_w * d->in_h, ck, bw, bh);
   } else {
     for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
       for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {
@@ -773,7 +793,13 @@ __global__ void conv_ref_simt_kernel(ay2_conv_desc d, const __nv_bfloat16* __res
         if (ix < 0 || ix >= d.in_w) continue;
         const __nv_bfloat16* ip = in + (((long long)b * d.in_h + iy) * rowp + ix) * pixs;
         const __nv_bfloat16* wp = w + ((long long)n * d.kh * d.kw + kh * d.kw + kw) * d.cin;
-        for (int c = 0; c < d.cin; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+        const int c_first = d.cin_split > 0 ? d.cin_split : d.cin;
+        for (int c = 0; c < c_first; ++c) acc += __bfloat162float(ip[c]) * __bfloat162float(wp[c]);
+        if (d.cin_split > 0) {
+          const __nv_bfloat16* ip2 =
+              static_cast<const __nv_bfloat16*>(d.in2) + (((long long)b * d.in_h + iy) * d.in_w + ix) * d.in2_cstride;
+          for (int c = c_first; c < d.cin; ++c) acc += __bfloat162float(ip2[c - c_first]) * __bfloat162float(wp[c]);
+        }
       }
     }
     acc += bias[n];

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ACT_NONE, ACT_SILU, ActView, ConvPlan
+from .ops import ACT_NONE, ACT_SILU, ActView, ChainPlan, ConvPlan
 
 
 def _act_code(m: nn.Module) -> int:
@@ -65,13 +65,16 @@ class Builder:
 
     # ---------------------------------------------------------------------------------------------
     def conv2d(self, x: ActView, y: ActView, weight: torch.Tensor, bias: Optional[torch.Tensor], bn, eps: float,
-               act: int, stride: int, pad: int, residual: Optional[ActView] = None) -> None:
-        """weight OIHW fp32 (Cin may be smaller than x.c: zero-padded), output channels may be padded up to y.c."""
+               act: int, stride: int, pad: int, residual: Optional[ActView] = None, x2: Optional[ActView] = None) -> None:
+        """weight OIHW fp32 (Cin may be smaller than x.c: zero-padded), output channels may be padded up to y.c.
+        x2: the conv reads torch.cat([x, x2], 1) (two-source input, no concatenated tensor)."""
         w = weight.detach().float().to(self.device)
         cout, cin, kh, kw = w.shape
-        if cin < x.c:
-            w = torch.cat((w, torch.zeros((cout, x.c - cin, kh, kw), device=self.device)), 1)
-        assert w.shape[1] == x.c, (w.shape, x.c)
+        xc = x.c + (x2.c if x2 is not None else 0)
+        if cin < xc:
+            assert x2 is None
+            w = torch.cat((w, torch.zeros((cout, xc - cin, kh, kw), device=self.device)), 1)
+        assert w.shape[1] == xc, (w.shape, xc)
         assert cout <= y.c
         if bn is not None:
             bn = tuple(t.detach().float().to(self.device) for t in bn)
@@ -87,11 +90,33 @@ class Builder:
             if bias is not None:
                 bias = torch.cat((bias, torch.zeros(y.c - cout, device=self.device)))
         wp, bp = ops.pack_conv_weight(w, bias, bn, eps)
-        plan = ConvPlan(x, y, wp, bp, kh, kw, stride, pad, act, residual=residual)
+        plan = ConvPlan(x, y, wp, bp, kh, kw, stride, pad, act, residual=residual, x2=x2)
         self.plans.append(plan)
         self.steps.append(plan.run)
         self.flops += 2.0 * self.B * y.H * y.W * cout * kh * kw * cin
         self.act_bytes += 2.0 * self.B * (x.H * x.W * cin + y.H * y.W * cout)
+
+    # ---------------------------------------------------------------------------------------------
+    # fused chains (csrc/conv_chain.cu): 1x1 -> 3x3 (-> 1x1) in one launch
+    FUSE_CHAINS = True      # class-level switch (tests / A-B measurements)
+    CHAIN_MIN_TILE_EFF = 0.7  # 16x8 output tiles: below this coverage (20x20 maps: 0.52) separate launches win
+
+    @staticmethod
+    def _tile_eff(H: int, W: int) -> float:
+        return (H * W) / float(((H + 15) // 16 * 16) * ((W + 7) // 8 * 8))
+
+    def _chain_ok(self, x: ActView, c1: int, c2: int, c3: int, k: int, s: int, p: int) -> bool:
+        if not self.FUSE_CHAINS or self._tile_eff(x.H, x.W) < self.CHAIN_MIN_TILE_EFF or x.c % 16:
+            return False
+        return ops.chain_supported(ops.chain_desc(x, c1, c2, c3, 0, 0, 0, 16, 0, k=k, stride=s, pad=p))
+
+    def chain(self, x: ActView, y: ActView, links, acts, residual: Optional[ActView], flops: float, act_elems: float) -> None:
+        """links: [(OIHW weight, bias, bn)] for the 2 or 3 convolutions; eps fixed by the caller's fold."""
+        plan = ChainPlan(x, y, links, acts, residual=residual)
+        self.plans.append(plan)
+        self.steps.append(plan.run)
+        self.flops += flops
+        self.act_bytes += 2.0 * act_elems
 
     @staticmethod
     def _conv_geom(c: nn.Conv2d) -> Tuple[int, int]:
@@ -108,6 +133,24 @@ class Builder:
             s, p = self._conv_geom(core)
             k = core.kernel_size[0]
             oh, ow = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+            r1p, r0p = _round_up(first.out_channels, 16), _round_up(core.out_channels, 16)
+            cout = last.out_channels
+            if (first.bias is None and core.bias is None and cout % 16 == 0 and (y is None or y.c == cout)
+                    and self._chain_ok(x, r1p, r0p, cout, k, s, p)):
+                # ONE launch: the rank-R1 / rank-R0 intermediates stay in shared memory / TMEM
+                if y is None:
+                    y = self.new_act(oh, ow, cout)
+                dev = self.device
+                bn_d = None if bn is None else tuple(t.detach().float().to(dev) for t in bn)
+                links = [ops.pack_chain_weight(first.weight.to(dev), None, cin_pad=x.c, cout_pad=r1p),
+                         ops.pack_chain_weight(core.weight.to(dev), None, cin_pad=r1p, cout_pad=r0p),
+                         ops.pack_chain_weight(last.weight.to(dev), None if last.bias is None else last.bias.to(dev), bn_d, eps,
+                                               cin_pad=r0p, cout_pad=cout)]
+                npx = self.B * x.H * x.W
+                fl = 2.0 * npx * (first.in_channels * first.out_channels + k * k * core.in_channels * core.out_channels
+                                  + last.in_channels * cout)
+                self.chain(x, y, links, (ACT_NONE, ACT_NONE, act), residual, fl, npx * (first.in_channels + cout))
+                return y
             t1 = self.new_act(x.H, x.W, _round_up(first.out_channels, 16))
             self.conv2d(x, t1, first.weight, first.bias, None, eps, ACT_NONE, 1, 0)
             t2 = self.new_act(oh, ow, _round_up(core.out_channels, 16))
@@ -200,6 +243,50 @@ class Builder:
         t = self.kindle_conv(m.conv1, y1)
         self.kindle_conv(m.conv2, t, y=y1, residual=y1 if m.shortcut else None)
 
+    def _bottleneck_fusable(self, m: nn.Module, x: ActView) -> bool:
+        c1, c2 = m.conv1.conv, m.conv2.conv
+        if not (isinstance(c1, nn.Conv2d) and isinstance(c2, nn.Conv2d)):
+            return False
+        if c1.kernel_size != (1, 1) or c1.stride != (1, 1) or c1.padding != (0, 0) or c1.groups != 1:
+            return False
+        if c2.kernel_size != (3, 3) or c2.stride != (1, 1) or c2.padding != (1, 1) or c2.groups != 1 or c2.dilation != (1, 1):
+            return False
+        if c1.in_channels != x.c or c2.out_channels != x.c:
+            return False
+        return self._chain_ok(x, c1.out_channels, c2.out_channels, 0, 3, 1, 1)
+
+    def bottleneck_fused(self, m: nn.Module, x: ActView, y: ActView) -> None:
+        """y <- (x +) conv2_3x3(conv1_1x1(x)) in ONE launch (y must be a different buffer: tiles read halos of x)."""
+        dev = self.device
+        links = []
+        for cm in (m.conv1, m.conv2):
+            bn, eps = _bn_tuple(getattr(cm, "batch_norm", None))
+            bn = None if bn is None else tuple(t.detach().float().to(dev) for t in bn)
+            bias = None if cm.conv.bias is None else cm.conv.bias.to(dev)
+            links.append(ops.pack_chain_weight(cm.conv.weight.to(dev), bias, bn, eps))
+        c_, ch = x.c, m.conv1.conv.out_channels
+        npx = self.B * x.H * x.W
+        self.chain(x, y, links, (_act_code(m.conv1), _act_code(m.conv2)), x if m.shortcut else None,
+                   2.0 * npx * (c_ * ch + 9 * ch * c_), npx * (c_ + ch + ch + c_))
+
+    def bottleneck_seq(self, blocks, cur: ActView) -> ActView:
+        """Runs the bottlenecks of a C3 / BottleneckCSP starting from `cur`; fused ones ping-pong between `cur`'s slice
+        and one temporary (they cannot run in place). Returns the view holding the result."""
+        home, tmp = cur, None
+        for b in blocks:
+            if self._bottleneck_fusable(b, cur):
+                if cur is home:
+                    if tmp is None:
+                        tmp = self.new_act(cur.H, cur.W, cur.c)
+                    dst = tmp
+                else:
+                    dst = home
+                self.bottleneck_fused(b, cur, dst)
+                cur = dst
+            else:
+                self.bottleneck(b, cur)
+        return cur
+
     def c3(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
         c_ = m.conv1.conv.out_channels if isinstance(m.conv1.conv, nn.Conv2d) else m.conv1.conv[-1].out_channels
         cat = self.new_act(x.H, x.W, 2 * c_)
@@ -220,16 +307,27 @@ class Builder:
             self.kindle_conv(m.conv1, x, y=cat.slice(0, c_))
             self.kindle_conv(m.conv2, x, y=cat.slice(c_, c_))
         y1 = cat.slice(0, c_)
-        for b in m.bottleneck_c3:
-            self.bottleneck(b, y1)
-        return self.kindle_conv(m.conv3, cat, y=y)
+        cur = self.bottleneck_seq(m.bottleneck_c3, y1)
+        if cur is y1:
+            return self.kindle_conv(m.conv3, cat, y=y)
+        # odd number of fused bottlenecks: the result sits in the temporary -> conv3 reads [tmp | cat[c_:]] as two sources
+        c3 = m.conv3
+        if not isinstance(c3.conv, nn.Conv2d) or c_ % 16:
+            ops_copy = cur  # rare: copy back and take the ordinary path
+            self.steps.append(lambda: y1.tensor().copy_(ops_copy.tensor()))
+            return self.kindle_conv(m.conv3, cat, y=y)
+        bn, eps = _bn_tuple(getattr(c3, "batch_norm", None))
+        s_, p_ = self._conv_geom(c3.conv)
+        if y is None:
+            y = self.new_act(x.H, x.W, c3.conv.out_channels)
+        self.conv2d(cur, y, c3.conv.weight, c3.conv.bias, bn, eps, _act_code(c3), s_, p_, x2=cat.slice(c_, c_))
+        return y
 
     def bottleneck_csp(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
         c_ = m.conv1.conv.out_channels
         cat = self.new_act(x.H, x.W, 2 * c_)
         t = self.kindle_conv(m.conv1, x)
-        for b in m.bottleneck_csp:
-            self.bottleneck(b, t)
+        t = self.bottleneck_seq(m.bottleneck_csp, t)
         # act(bn(cat[conv3(t), conv2(x)])) == cat[act(bn_a(conv3 t)), act(bn_b(conv2 x))]: fold each BN half
         bn, eps = _bn_tuple(m.batch_norm)
         act = _act_code(m)

@@ -89,21 +89,26 @@ class ConvPlan:
 
     def __init__(self, x: ActView, y: ActView, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int,
                  stride: int, pad: int, act: int, residual: Optional[ActView] = None, pad_w: int = -1,
-                 window: Optional[Tuple[int, int, int, int]] = None, out_sub: Optional[Tuple[int, int]] = None):
+                 window: Optional[Tuple[int, int, int, int]] = None, out_sub: Optional[Tuple[int, int]] = None,
+                 x2: Optional[ActView] = None):
         """`window` = (cin, in_w, pix_stride, row_pixels): read `x.buf` as overlapping windows of `cin` channels
         starting at every physical pixel (the packed 16-channel stem); otherwise the input is the ActView `x`.
         `out_sub` = (py, px): write (and read the residual from) the (row, column) parity sub-grid of `y` -- the
-        output is then y.H/2 x y.W/2 pixels (data gradient of a stride-2 convolution)."""
+        output is then y.H/2 x y.W/2 pixels (data gradient of a stride-2 convolution).
+        `x2`: second input view; the conv consumes torch.cat([x, x2], channel) without the concatenation existing."""
         lib = _lib.load()
         cout_pad, ktot = w_packed.shape
-        cin = window[0] if window else x.c
+        cin = window[0] if window else x.c + (x2.c if x2 is not None else 0)
         assert ktot == kh * kw * cin, (ktot, kh, kw, cin)
         assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32 and bias.numel() == cout_pad
         assert x.buf.is_cuda and y.buf.is_cuda and w_packed.is_cuda and bias.is_cuda
         d = ConvDesc()
         d.batch = x.B
-        d.in_h, d.in_w, d.cin, d.in_cstride = x.H, x.W, x.c, x.cstride
+        d.in_h, d.in_w, d.cin, d.in_cstride = x.H, x.W, cin, x.cstride
         d.pad_w = pad_w
+        if x2 is not None:
+            assert window is None and (x2.B, x2.H, x2.W) == (x.B, x.H, x.W) and x2.buf.is_cuda
+            d.cin_split, d.in2_cstride, d.in2 = x.c, x2.cstride, x2.ptr()
         if window:
             d.cin, d.in_w, d.in_pix_stride, d.in_row_pixels = window
         d.out_h, d.out_w, d.cout, d.out_cstride = y.H, y.W, y.c, y.cstride
@@ -122,7 +127,7 @@ class ConvPlan:
         d.res_cstride = residual.cstride if residual is not None else 0
         d.cout_pad = cout_pad
         self.desc = d
-        self.x, self.y, self.w, self.b, self.res = x, y, w_packed, bias, residual
+        self.x, self.y, self.w, self.b, self.res, self.x2 = x, y, w_packed, bias, residual, x2
         h = C.c_void_p()
         _lib.check(lib.ay2_conv_plan_create(C.byref(d), x.ptr(), w_packed.data_ptr(), bias.data_ptr(), r_ptr, y_ptr,
                                             C.byref(h)), "ay2_conv_plan_create")

@@ -285,7 +285,7 @@ def main() -> None:
             if det.fused_candidates:
                 det.nms_ws.begin_candidates()  # the detect convolutions below append this step's NMS candidates
             for s in eng.b.steps:
-                is_conv = getattr(s, "__self__", None) is not None and s.__self__.__class__.__name__ == "ConvPlan"
+                is_conv = getattr(s, "__self__", None) is not None and s.__self__.__class__.__name__ in ("ConvPlan", "ChainPlan")
                 if is_conv:
                     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()
@@ -311,7 +311,10 @@ def main() -> None:
             if os.path.isdir(os.path.join(ROOT, "profiles")) else []
         if tfiles:
             traffic = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))["dram_bytes"]
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (52 launches / 60 convolutions = one step)", "achieved": achieved,
+        n_chain = sum(1 for v in per_plan.values() if v[0].__class__.__name__ == "ChainPlan")
+        roof = {"bound": "tensor",
+                "kernel": f"conv family: {len(per_plan) - n_chain} conv_tc_kernel + {n_chain} conv_chain_kernel launches "
+                          "(60 convolutions) = one step", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_src": peaks["src"] + " (sustained)",
                 "conv_ms_per_step": conv_ms, "hbm_view": {"achieved_gbs": abytes / (conv_ms / 1000.0) / 1e9,
@@ -335,6 +338,10 @@ def main() -> None:
         layers = []
         for plan, tot, n in per_plan.values():
             d = plan.desc
+            if plan.__class__.__name__ == "ChainPlan":
+                layers.append({"chain": [d.cin, d.c1, d.c2, d.c3], "k": d.kh, "s": d.stride, "hw": [d.in_h, d.in_w],
+                               "ms": tot / n, "tflops": plan.flops / (tot / n / 1000.0) / 1e12})
+                continue
             layers.append({"cin": d.cin, "cout": d.cout, "k": d.kh, "s": d.stride, "hw": [d.out_h, d.out_w],
                            "ms": tot / n, "tflops": plan.flops / (tot / n / 1000.0) / 1e12})
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -72,6 +72,11 @@ typedef struct ay2_conv_desc {
   int32_t out_row_pixels; /* ... and output pixels per physical row (0 = out_w). With pix stride 2*cstride and row pixels
                              = full width, the output (and the residual) is one (row, column) parity sub-grid of a
                              twice-as-large tensor: how the data gradient of a stride-2 conv is written (4 launches) */
+  int32_t cin_split;      /* > 0 (stride-1 convs): input channels [0, cin_split) come from `in`, channels [cin_split, cin)
+                             from `in2` -- torch.cat([a, b], 1) resolved by the consumer when a and b live in different
+                             buffers (kindle C3 conv3 after out-of-place fused bottlenecks) */
+  int32_t in2_cstride;    /* channel stride of the second input buffer */
+  const void* in2;        /* second input (device pointer, same batch / height / width), NULL when cin_split == 0 */
 } ay2_conv_desc;
 
 typedef struct ay2_conv_plan ay2_conv_plan;
@@ -121,6 +126,10 @@ int ay2_chain_plan_create(const ay2_chain_desc* desc, const void* in, const void
 int ay2_chain_plan_run(const ay2_chain_plan* plan, void* stream);
 int ay2_chain_plan_destroy(ay2_chain_plan* plan);
 double ay2_chain_plan_flops(const ay2_chain_plan* plan);
+/* Diagnostics: chosen launch configuration {CTAs/SM, grid, smem bytes, X slots, W slots, staging aliased, TMEM columns,
+ * stage-2 K chunk}, and an optional device buffer (16 x 16 uint64) into which CTA 0 records %globaltimer per phase. */
+int ay2_chain_plan_info(const ay2_chain_plan* plan, int32_t* out8);
+int ay2_chain_plan_set_debug(ay2_chain_plan* plan, unsigned long long* dbg);
 
 /* ------------------------------------------------------------------------------------------------
  * Input side: NCHW image (uint8 or fp32) -> 2x2 space-to-depth NHWC bf16 with 16 channels

@@ -127,3 +127,36 @@ def test_tucker_decomposed_forward_matches_oracle():
     torch.cuda.synchronize()
     for g, w in zip(got_raw, want_raw):
         assert _norm_err(g, w) < 3e-2, _norm_err(g, w)
+
+
+@pytest.mark.parametrize("name,decomposed", [("yolov5s", False), ("yolov5s", True), ("yolov5m", False)])
+def test_fused_chains_match_separate_launches(name, decomposed):
+    """The fused chain kernel (Bottleneck = 1 launch, Tucker chain = 1 launch, C3 conv3 reading two sources) against the
+    same engine with every link as its own launch: identical bf16 rounding points, so the logits agree to accumulation
+    order. 640x640 so that the 160x160 / 80x80 / 40x40 maps (the fused ones) are all exercised."""
+    from ayolov2_b200 import engine as eng_mod, synth, tucker
+
+    model = synth.build_model(name, seed=3)
+    if decomposed:
+        tucker.decompose_model_fixed(model, ratio=0.5)
+    model = model.cuda().eval()
+    x = torch.rand((2, 3, 640, 640), generator=torch.Generator().manual_seed(9)).cuda()
+
+    def run(fuse):
+        eng_mod.Builder.FUSE_CHAINS = fuse
+        try:
+            e = eng_mod.Engine(model, 2, 640, 640, use_graph=False)
+            pred, raw = e.run(x)
+            torch.cuda.synchronize()
+            nchain = sum(1 for p in e.b.plans if type(p).__name__ == "ChainPlan")
+            return pred.clone(), [r.clone() for r in raw], nchain, len(e.b.steps)
+        finally:
+            eng_mod.Builder.FUSE_CHAINS = True
+
+    p1, r1, n1, s1 = run(True)
+    p0, r0, n0, s0 = run(False)
+    assert n0 == 0 and n1 >= 8, (n0, n1)
+    assert s1 < s0
+    for a, b in zip(r1, r0):
+        e = float((a - b).abs().max() / b.abs().max())
+        assert e < 1e-2, e
