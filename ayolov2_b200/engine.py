@@ -99,11 +99,11 @@ class Builder:
     # ---------------------------------------------------------------------------------------------
     # fused chains (csrc/conv_chain.cu): 1x1 -> 3x3 (-> 1x1) in one launch
     FUSE_CHAINS = True      # class-level switch (tests / A-B measurements)
-    CHAIN_MIN_TILE_EFF = 0.7  # 16x8 output tiles: below this coverage (20x20 maps: 0.52) separate launches win
+    CHAIN_MIN_TILE_EFF = 0.65  # 16x16 output tiles: below this coverage (20x20 maps: 0.39) separate launches win
 
     @staticmethod
     def _tile_eff(H: int, W: int) -> float:
-        return (H * W) / float(((H + 15) // 16 * 16) * ((W + 7) // 8 * 8))
+        return (H * W) / float(((H + 15) // 16 * 16) * ((W + 15) // 16 * 16))
 
     def _chain_ok(self, x: ActView, c1: int, c2: int, c3: int, k: int, s: int, p: int) -> bool:
         if not self.FUSE_CHAINS or self._tile_eff(x.H, x.W) < self.CHAIN_MIN_TILE_EFF or x.c % 16:

@@ -30,7 +30,7 @@ torch.cuda.synchronize()
 _lib.load().ay2_chain_plan_set_debug(plan._h, dbg.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); plan.run(); e1.record(); torch.cuda.synchronize()
-print("kernel ms", e0.elapsed_time(e1), "tiles", B * ((hw + 15) // 16) * ((hw + 7) // 8), "tiles/CTA", B * ((hw + 15) // 16) * ((hw + 7) // 8) / info[1])
+print("kernel ms", e0.elapsed_time(e1), "tiles", B * ((hw + 15) // 16) ** 2, "tiles/CTA", B * ((hw + 15) // 16) ** 2 / info[1])
 dall = dbg.cpu()
 d = dall[:256].view(16, 16)
 ck = dall[128:144].view(4, 4)
