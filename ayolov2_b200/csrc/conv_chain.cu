@@ -130,13 +130,16 @@ __device__ __forceinline__ float ch_act(float x, int act) { return act == AY2_AC
 
 // 16 accumulator columns of one row: +bias -> act (-> zero) -> bf16 -> two 16-byte stores `plane` bytes apart
 // (no-swizzle core-matrix layout of T / U: 8 channels x 16 B per pixel, one plane per 8 channels).
-__device__ __forceinline__ void ch_store_planes(const uint32_t* v, const float* bias, int act, bool keep, uint32_t dst,
+__device__ __forceinline__ void ch_store_planes(const uint32_t* v, uint32_t bias_addr, int act, bool keep, uint32_t dst,
                                                 uint32_t plane) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
+    float bb[8];
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(bias_addr + g * 32));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(bias_addr + g * 32 + 16));
     float f[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = keep ? ch_act(__uint_as_float(v[g * 8 + i]) + bias[g * 8 + i], act) : 0.0f;
+    for (int i = 0; i < 8; ++i) f[i] = keep ? ch_act(__uint_as_float(v[g * 8 + i]) + bb[i], act) : 0.0f;
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + g * plane), "r"(pack_bf16x2(f[0], f[1])),
                  "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
                  : "memory");
@@ -147,14 +150,15 @@ __device__ __forceinline__ void ch_store_planes(const uint32_t* v, const float* 
 // swizzled staging [256 pixels][oc] per slab (pixel = y*16 + x, the order a [oc][16][16] TMA box uses) -> TMA store.
 // All 256 epilogue threads call it (group `eg` drains the 16-column blocks [blk_lo, blk_hi)); `acc_full` is the
 // MMA->epilogue barrier of this pair, `acc_empty` the way back. taddr0 / taddr1: TMEM addresses of the two halves.
-__device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* staging, const float* bias_s, uint32_t taddr0,
+__device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* staging, uint32_t bias_addr, uint32_t taddr0,
                                                  uint32_t taddr1, int ncols, int act, int n0, int x0, int y0, int b, int et,
                                                  int eall, int blk_lo, int blk_hi, uint64_t* acc_full, uint32_t acc_phase,
                                                  uint64_t* acc_empty, uint64_t* res_full, uint32_t& res_phase,
                                                  const uint8_t* xring, int xslot0) {
   const int swo = p.oc * 2;
   const int slab_bytes = 256 * swo;
-  const int nslab = ncols / p.oc;
+  const int oc_shift = p.oc == 64 ? 6 : (p.oc == 32 ? 5 : 4);
+  const int nslab = ncols >> oc_shift;
   const bool tma_res = p.has_res && !p.res_from_x;
   if (eall == 0) {
     tma_store_wait_read<0>();  // the previous tile's stores have finished reading the staging buffer
@@ -185,13 +189,17 @@ __device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* 
       uint32_t v[16];
       tmem_ld_32x32b_x16(taddr + c0, v);
       tmem_ld_wait();
-      uint8_t* slab = staging + (c0 / p.oc) * slab_bytes;
-      const int chunk0 = (c0 % p.oc) / 8;
+      uint8_t* slab = staging + (c0 >> oc_shift) * slab_bytes;
+      const int chunk0 = (c0 & (p.oc - 1)) >> 3;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
+        float bb[8];
+        const uint32_t ba = bias_addr + (n0 + c0 + g * 8) * 4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + 16));
         float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = ch_act(__uint_as_float(v[g * 8 + i]) + bias_s[n0 + c0 + g * 8 + i], act);
+        for (int i = 0; i < 8; ++i) f[i] = ch_act(__uint_as_float(v[g * 8 + i]) + bb[i], act);
         const uint32_t dst = smem_u32(slab) + swizzled_offset_rt(row, chunk0 + g, swo);
         if (p.has_res) {
           uint32_t src = dst;
@@ -479,9 +487,9 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
     const int eg = eall >> 7;            // epilogue group
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     uint32_t d1_phase = 0, d2_phase = 0, d3_phase = 0, res_phase = 0;
-    const float* bias1 = bias_s;
-    const float* bias2 = bias_s + p.c1;
-    const float* bias3 = bias_s + p.c1 + p.c2;
+    const uint32_t bias1 = smem_u32(bias_s);
+    const uint32_t bias2 = bias1 + p.c1 * 4;
+    const uint32_t bias3 = bias2 + p.c2 * 4;
     auto split = [&](int ncols, int& lo, int& hi) {  // this group's share of the 16-column blocks
       const int nblk = ncols / 16, mid = (nblk + 1) / 2;
       lo = eg ? mid : 0;
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
           uint32_t v[16];
           tmem_ld_32x32b_x16(tbase + blk * 16, v);
           tmem_ld_wait();
-          if (h < CH_NH) ch_store_planes(v, bias1 + blk * 16, p.act1, inb, trow + blk * 2 * t_plane, t_plane);
+          if (h < CH_NH) ch_store_planes(v, bias1 + blk * 64, p.act1, inb, trow + blk * 2 * t_plane, t_plane);
         }
       }
       tcgen05_fence_before();
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
             uint32_t v[16];
             tmem_ld_32x32b_x16(tsrc + blk * 16, v);
             tmem_ld_wait();
-            ch_store_planes(v, bias2 + blk * 16, p.act2, true, urow + blk * 2 * CH_U_PLANE, CH_U_PLANE);
+            ch_store_planes(v, bias2 + blk * 64, p.act2, true, urow + blk * 2 * CH_U_PLANE, CH_U_PLANE);
           }
         }
         tcgen05_fence_before();
@@ -696,7 +704,10 @@ extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, co
         int nx = opts[o][0] * cin_chunks;
         if (nx > 4) nx = cin_chunks <= 4 ? cin_chunks : 4;
         const int alias = opts[o][1];
-        const int rfx = res_is_input && nx % cin_chunks == 0 ? 1 : 0;  // whole tiles in the X ring
+        // measured (r01): reading the shortcut from the halo slot is slower than a residual TMA load (bank conflicts on the
+        // 64/128-byte rows and the slot is held until the last epilogue) -> opt-in only
+        static const int env_rfx = getenv("AY2_CHAIN_RES_FROM_X") ? atoi(getenv("AY2_CHAIN_RES_FROM_X")) : 0;
+        const int rfx = env_rfx && res_is_input && nx % cin_chunks == 0 ? 1 : 0;  // whole tiles in the X ring
         const int t_region = alias && staging_bytes > t_bytes ? staging_bytes : t_bytes;
         const int fixed = nx * x_slot + t_region + u_bytes + (alias ? 0 : staging_bytes) + bias_bytes + bars_bytes + 2048;
         int nw = (budget - fixed) / w_slot;

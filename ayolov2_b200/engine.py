@@ -17,6 +17,7 @@ The launch sequence is static, so a whole forward (+ NMS) is captured into one C
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -99,6 +100,10 @@ class Builder:
     # ---------------------------------------------------------------------------------------------
     # fused chains (csrc/conv_chain.cu): 1x1 -> 3x3 (-> 1x1) in one launch
     FUSE_CHAINS = True      # class-level switch (tests / A-B measurements)
+    # Bottlenecks wider than this stay two launches: measured on B200 (r01, bs 64): c = 32 @160x160 fused 0.165 ms vs
+    # 0.240 ms, c = 64 @80x80 0.097 vs 0.084 ms, c = 128 @40x40 0.105 vs 0.066 ms (the serialised stages of the fused
+    # kernel lose to two pipelined launches once the 3x3 is tensor-bound). Tucker chains are always fused when supported.
+    FUSE_BOTTLENECK_MAX_C = int(os.environ.get("AY2_FUSE_BOTTLENECK_MAX_C", "32"))
     CHAIN_MIN_TILE_EFF = 0.65  # 16x16 output tiles: below this coverage (20x20 maps: 0.39) separate launches win
 
     @staticmethod
@@ -251,7 +256,7 @@ class Builder:
             return False
         if c2.kernel_size != (3, 3) or c2.stride != (1, 1) or c2.padding != (1, 1) or c2.groups != 1 or c2.dilation != (1, 1):
             return False
-        if c1.in_channels != x.c or c2.out_channels != x.c:
+        if c1.in_channels != x.c or c2.out_channels != x.c or x.c > self.FUSE_BOTTLENECK_MAX_C:
             return False
         return self._chain_ok(x, c1.out_channels, c2.out_channels, 0, 3, 1, 1)
 

@@ -144,6 +144,8 @@ def test_fused_chains_match_separate_launches(name, decomposed):
 
     def run(fuse):
         eng_mod.Builder.FUSE_CHAINS = fuse
+        keep = eng_mod.Builder.FUSE_BOTTLENECK_MAX_C
+        eng_mod.Builder.FUSE_BOTTLENECK_MAX_C = 128  # exercise every fusable Bottleneck, not only the ones the policy picks
         try:
             e = eng_mod.Engine(model, 2, 640, 640, use_graph=False)
             pred, raw = e.run(x)
@@ -152,6 +154,7 @@ def test_fused_chains_match_separate_launches(name, decomposed):
             return pred.clone(), [r.clone() for r in raw], nchain, len(e.b.steps)
         finally:
             eng_mod.Builder.FUSE_CHAINS = True
+            eng_mod.Builder.FUSE_BOTTLENECK_MAX_C = keep
 
     p1, r1, n1, s1 = run(True)
     p0, r0, n0, s0 = run(False)
