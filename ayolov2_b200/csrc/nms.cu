@@ -1069,3 +1069,41 @@ extern "C" int ay2_nms_from_logits(const ay2_head_levels* hl, const ay2_nms_para
   count_launch(3);
   return AY2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Pairwise IoU matrix (scripts/utils/metrics.py:138-164 box_iou): out[i][j] = inter / (area1[i] + area2[j] - inter),
+// inter = clamp(min(rb) - max(lt), 0).prod(). Same fp32 operation order as the reference expression (explicit
+// round-to-nearest intrinsics, IEEE division), so the matrix is bit-identical to torch's on identical inputs.
+// ------------------------------------------------------------------------------------------------
+namespace ay2 {
+__global__ void box_iou_kernel(const float4* __restrict__ b1, int n, const float4* __restrict__ b2, int m,
+                               float* __restrict__ out) {
+  const long long total = (long long)n * m;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / m), j = (int)(idx - (long long)i * m);
+    const float4 a = b1[i], b = b2[j];
+    const float area1 = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float area2 = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+    const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+    const float inter = __fmul_rn(w, h);
+    out[idx] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area1, area2), inter));
+  }
+}
+}  // namespace ay2
+
+extern "C" int ay2_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float* out, void* stream) {
+  AY2_REQUIRE(n >= 0 && m >= 0, "ay2_box_iou: negative size");
+  if (n == 0 || m == 0) return AY2_OK;
+  AY2_REQUIRE(box1 && box2 && out, "ay2_box_iou: null pointer");
+  AY2_REQUIRE(((reinterpret_cast<uintptr_t>(box1) | reinterpret_cast<uintptr_t>(box2)) & 15) == 0, "ay2_box_iou: boxes must be 16-byte aligned");
+  const long long total = (long long)n * m;
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  box_iou_kernel<<<(int)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(box1), n,
+                                                                                   reinterpret_cast<const float4*>(box2), m, out);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}

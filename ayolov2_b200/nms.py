@@ -88,3 +88,48 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
         counts = ws.count.tolist()
     out = ws.out
     return [out[i, :c].clone() for i, c in enumerate(counts)]
+
+
+def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
+    """(N, M) pairwise IoU of xyxy boxes (reference signature, metrics.py:138-164), one CUDA launch."""
+    from . import _lib
+
+    if not (box1.is_cuda and box2.is_cuda):
+        raise RuntimeError("ayolov2_b200.nms.box_iou runs on CUDA tensors only (no CPU fallback)")
+    b1, b2 = box1.float().contiguous(), box2.float().contiguous()
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    _lib.check(_lib.load().ay2_box_iou(b1.data_ptr(), b1.shape[0], b2.data_ptr(), b2.shape[0], out.data_ptr(),
+                                       _lib.current_stream_ptr()), "ay2_box_iou")
+    return out
+
+
+def batched_nms(prediction: torch.Tensor, conf_thres: float = 0.001, iou_thres: float = 0.65, nms_box: int = 500,
+                agnostic: bool = False, nms_type: str = "nms") -> List[torch.Tensor]:
+    """Reference signature of scripts/utils/nms.py:15-116 (the val2.py path), nms_type "nms".
+
+    The reference keeps the `nms_box` rows of highest objectness per image (:41-42), scores every (row, class) pair
+    conf = cls * obj > conf_thres (:45-47) and runs torchvision NMS per image -- class-separated (offset 4096 * class) only
+    when `agnostic` is True, plain otherwise (:58-62; the flag is inverted relative to non_max_suppression). That is the
+    multi-label candidate generation + greedy suppression of ay2_nms_batched on the gathered (B, nms_box, no) rows with
+    the agnostic flag flipped and no max_det / max_nms cut, so the batch runs in the same fixed number of launches.
+    Candidate order (row in objectness order, then class) is the reference's, which fixes torchvision's stable tie order.
+    """
+    if nms_type != "nms":
+        raise NotImplementedError(f"nms_type={nms_type!r}: only 'nms' runs on the B200 kernels (box_iou is available for the others)")
+    if not prediction.is_cuda:
+        raise RuntimeError("ayolov2_b200.nms runs on CUDA tensors only (no CPU fallback)")
+    pred = prediction.float()
+    B, n, no = pred.shape
+    nc = no - 5
+    k = min(nms_box, n)
+    idx = pred[:, :, 4].argsort(descending=True)[:, :k]                      # nms.py:41 (same call, same tie behaviour)
+    top = torch.gather(pred, 1, idx[:, :, None].expand(B, k, no)).contiguous()  # nms.py:42
+    cap = 1024  # kMaxDetCap of the kernel
+    ws = _workspace(B, k, no, cap, True, pred.device, max_candidates=k * nc)
+    ws.p.multi_label = 1
+    ws.run(top, conf_thres, iou_thres, agnostic=not agnostic, max_nms=k * nc)
+    ws._keepalive = (top,)
+    counts = ws.count.tolist()
+    if max(counts, default=0) >= cap:
+        raise NotImplementedError(f"an image kept >= {cap} boxes; raise conf_thres (the kernel's survivor list holds {cap})")
+    return [ws.out[i, :c].clone() for i, c in enumerate(counts)]

@@ -223,6 +223,11 @@ int ay2_nms_candidates_begin(const ay2_nms_params* p, void* workspace, size_t wo
 int ay2_nms_from_candidates(const ay2_head_levels* levels, const ay2_nms_params* p, void* workspace, size_t workspace_bytes,
                             float* out_det, int32_t* out_count, int32_t* overflow_flag, void* stream);
 
+/* Pairwise IoU matrix: replaces scripts/utils/metrics.py:138-164 box_iou (fast/matrix/merge NMS in scripts/utils/nms.py:74-110,
+ * mAP matching in scripts/utils/train_utils.py:294-401). box1: fp32 (n, 4) xyxy, box2: fp32 (m, 4) xyxy, out: fp32 (n, m);
+ * bit-identical to the reference expression on identical inputs. */
+int ay2_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Detection loss forward + analytic backward: replaces scripts/loss/losses.py:168-391 (ComputeLoss.__call__,
  * build_targets) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU) for the default configuration

@@ -30,7 +30,8 @@ def test_build_and_symbols():
 def test_struct_layouts_match_header():
     from ayolov2_b200 import _lib
 
-    assert ctypes.sizeof(_lib.ConvDesc) == 21 * 4
+    assert ctypes.sizeof(_lib.ConvDesc) == 104 and _lib.ConvDesc.in2.offset == 96  # 23 int32, 4 bytes padding, pointer
+    assert ctypes.sizeof(_lib.ChainDesc) == 17 * 4
     assert ctypes.sizeof(_lib.NmsParams) == 48
     assert _lib.NmsParams.iou_thres.offset == 0 and _lib.NmsParams.batch.offset == 16
 

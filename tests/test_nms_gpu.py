@@ -101,3 +101,40 @@ def test_nms_iou_threshold_sliver():
     _cmp(pred, max_det=1000, conf_thres=0.25, iou_thres=thr)
     _cmp(pred, max_det=1000, conf_thres=0.25, iou_thres=float(np.float32(thr)))
     _cmp(pred[:, :256], conf_thres=0.25, iou_thres=thr, agnostic=True)
+
+
+@pytest.mark.parametrize("agnostic,conf", [(False, 0.3), (True, 0.93), (False, 0.6)])
+def test_batched_nms_val2_path(agnostic, conf):
+    """scripts/utils/nms.py:15-116 (val2.py): top-nms_box rows by objectness, every (row, class) above conf, torchvision NMS
+    with the (inverted) agnostic flag -- bit-exact against the oracle restatement pinned to the reference."""
+    from ayolov2_b200.nms import batched_nms
+    from oracle import nms_oracle
+
+    pred = nms_oracle.synth_predictions(3, n=6000, nc=80, seed=11, cand_frac=0.15)
+    want = nms_oracle.batched_nms(pred, conf_thres=conf, iou_thres=0.65, nms_box=500, agnostic=agnostic)
+    got = batched_nms(pred.cuda(), conf_thres=conf, iou_thres=0.65, nms_box=500, agnostic=agnostic)
+    assert sum(w.shape[0] for w in want) > 100 and max(w.shape[0] for w in want) < 1024
+    for g, w in zip(got, want):
+        assert g.shape == w.shape, (g.shape, w.shape)
+        assert torch.equal(g.cpu(), w)
+
+
+def test_box_iou_bit_exact():
+    """scripts/utils/metrics.py:138-164 on identical fp32 inputs (the expression below is the reference's)."""
+    from ayolov2_b200.nms import box_iou
+
+    g = torch.Generator().manual_seed(4)
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * 600
+        wh = torch.rand(n, 2, generator=g) * 200 + 1
+        return torch.cat((xy, xy + wh), 1)
+
+    b1, b2 = boxes(333), boxes(1025)
+    area1 = (b1.T[2] - b1.T[0]) * (b1.T[3] - b1.T[1])
+    area2 = (b2.T[2] - b2.T[0]) * (b2.T[3] - b2.T[1])
+    inter = (torch.min(b1[:, None, 2:], b2[:, 2:]) - torch.max(b1[:, None, :2], b2[:, :2])).clamp(0).prod(2)
+    want = inter / (area1[:, None] + area2 - inter)
+    got = box_iou(b1.cuda(), b2.cuda()).cpu()
+    assert torch.equal(got, want)
+    assert box_iou(b1[:0].cuda(), b2.cuda()).shape == (0, 1025)
