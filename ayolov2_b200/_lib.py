@@ -106,6 +106,7 @@ _PROTOS = {
     "ay2_chain_plan_flops": (C.c_double, [C.c_void_p]),
     "ay2_chain_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ay2_chain_plan_set_debug": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ay2_conv_plan_set_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
     "ay2_space_to_depth": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_sppf_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -43,7 +43,18 @@ struct ConvKernelParams {
   int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
               // CTA fetches half of every weight (B) tile, multicast into both CTAs' shared memory
   HeadCandParams hc;  // detect head only: NMS candidates are scored and appended from the staged output tile
+  unsigned long long* dbg;  // optional timeline buffer (tools/conv_timeline.py): every CTA records %globaltimer per phase
 };
+
+__device__ __forceinline__ unsigned long long cv_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define CV_DBG(slot)                                                \
+  do {                                                              \
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + (slot)] = cv_now();  \
+  } while (0)
 
 constexpr int kSmemPerSm = 227 * 1024;
 
@@ -64,7 +75,7 @@ struct ConvCfg {
   static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
   // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes; the 256-column tile (1 CTA/SM) uses two groups,
   // each draining half of the columns, so that every scheduler has two epilogue warps to interleave.
-  static constexpr int EPI_GROUPS = BLOCK_N == 256 ? 2 : 1;
+  static constexpr int EPI_GROUPS = BLOCK_N >= 128 ? 2 : 1;
   static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
   static constexpr int COLS_PER_GROUP = BLOCK_N / EPI_GROUPS;
@@ -164,6 +175,48 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
   }
 }
 
+// Drain this warp group's column range of one accumulator: TMEM -> +bias -> act (-> + residual already staged in the
+// output slab) -> bf16 -> swizzled staging slab. Bias comes from shared memory with explicit ld.shared (a pointer derived
+// from the aligned dynamic-smem base loses its address space and compiles to generic loads).
+template <class Cfg, bool SILU, bool RES>
+__device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint32_t staging_u32, uint32_t bias_u32, int et) {
+#pragma unroll 1
+  for (int c0 = egrp * Cfg::COLS_PER_GROUP; c0 < (egrp + 1) * Cfg::COLS_PER_GROUP; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c0, v);
+    tmem_ld_wait();
+    const uint32_t slab = staging_u32 + (c0 / Cfg::OC) * Cfg::SLAB_BYTES;
+    const int chunk0 = (c0 % Cfg::OC) / 8;
+    const uint32_t ba = bias_u32 + c0 * 4;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float bb[8], f[8];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba + g * 32));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + g * 32 + 16));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = __uint_as_float(v[g * 8 + i]) + bb[i];
+        f[i] = SILU ? silu_f(x) : x;
+      }
+      const uint32_t dst = slab + swizzled_offset<Cfg::SWO>(et, chunk0 + g);
+      if (RES) {
+        uint4 rv;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(dst));
+        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 rf = __bfloat1622float2(r2[i]);
+          f[2 * i] += rf.x;
+          f[2 * i + 1] += rf.y;
+        }
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(f[0], f[1])),
+                   "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+                   : "memory");
+    }
+  }
+}
+
 template <int BLOCK_N, int CK>
 __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N, CK>;
@@ -186,6 +239,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   const int num_k_chunks = p.kh * p.kw * p.cin_chunks;
 
   if (threadIdx.x == 0) {
+    CV_DBG(0);  // CTA entry
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 9] = clock64();
     for (int i = 0; i < Cfg::NSTAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], p.csize);  // every CTA sharing the multicast B tile must release the stage
@@ -206,6 +261,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) CV_DBG(1);  // prologue done (barriers, TMEM)
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
   // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.
   // The next kernel may start its own prologue as soon as every CTA of this grid is resident (all are: persistent grid).
@@ -302,6 +358,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
         for (int kc = 0; kc < num_k_chunks; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if (it == 0 && kc == 0 && lane == 0) CV_DBG(2);  // first operands landed
           const uint32_t a_addr = smem_u32(stages + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
           if (elect_one()) {
@@ -360,53 +417,29 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
       named_bar_sync(1, Cfg::EPI_THREADS);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
+      if (eall == 0) CV_DBG(it == 0 ? 3 : 5);  // first / last accumulator complete
       if (p.has_res) {
         mbar_wait(res_full, res_phase);
         res_phase ^= 1;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = egrp * Cfg::COLS_PER_GROUP; c0 < (egrp + 1) * Cfg::COLS_PER_GROUP; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c0, v);
-        tmem_ld_wait();
-        uint8_t* slab = staging + (c0 / Cfg::OC) * Cfg::SLAB_BYTES;
-        const int chunk0 = (c0 % Cfg::OC) / 8;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[c0 + g * 8]);
-          const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[c0 + g * 8 + 4]);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x = __uint_as_float(v[g * 8 + i]) + bb[i];
-            if (p.act == AY2_ACT_SILU) x = silu_f(x);
-            f[i] = x;
-          }
-          const uint32_t dst = smem_u32(slab) + swizzled_offset<Cfg::SWO>(et, chunk0 + g);
-          if (p.has_res) {
-            uint4 rv;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(dst));
-            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 rf = __bfloat1622float2(r2[i]);
-              f[2 * i] += rf.x;
-              f[2 * i + 1] += rf.y;
-            }
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(f[0], f[1])),
-                       "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
-                       : "memory");
-        }
+      // activation / residual are compile-time inside the drain loop: no predicated-off residual code, no branch per group
+      if (p.act == AY2_ACT_SILU) {
+        if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
+        else drain_accumulator<Cfg, true, false>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
+      } else {
+        if (p.has_res) drain_accumulator<Cfg, false, true>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
+        else drain_accumulator<Cfg, false, false>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
       }
+      if (eall == 0 && it == 0) CV_DBG(12);  // first tile drained by this thread
       // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       // staging complete -> TMA store
       fence_proxy_async_smem();
+      if (eall == 0 && it == 0) CV_DBG(13);  // fences done
       named_bar_sync(1, Cfg::EPI_THREADS);
+      if (eall == 0 && it == 0) CV_DBG(14);  // all epilogue warps done
       if (eall == 0) {
         for (int j = 0; j < p.NB; ++j) {
           const int q = m * p.NB + j;
@@ -420,17 +453,25 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
                          oy, b);
         }
         tma_store_commit();
+        CV_DBG(it == 0 ? 4 : 6);  // first / last tile's store issued
       }
       // detect head: score NMS candidates from the staged tile while the TMA store drains it (both only read);
       // nobody rewrites the staging buffer before every epilogue thread has passed the next iteration's barrier
       if (p.hc.keys) head_candidates<Cfg>(p, staging, m, et, egrp, lane);
     }
-    if (eall == 0) tma_store_wait_all<0>();
+    if (eall == 0) {
+      tma_store_wait_all<0>();
+      CV_DBG(7);  // stores drained
+    }
   }
 
   tcgen05_fence_before();
   if (p.csize > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on it
   else __syncthreads();
+  if (threadIdx.x == 0) {
+    CV_DBG(8);  // all roles finished
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 15] = clock64();
+  }
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -752,6 +793,13 @@ extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
   AY2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pl->kernel, pl->kp));
   AY2_CHECK_LAUNCH();
   count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_conv_plan_set_debug(ay2_conv_plan* pl, unsigned long long* dbg, int32_t* info4) {
+  AY2_REQUIRE(pl, "ay2_conv_plan_set_debug: null plan");
+  pl->kp.dbg = dbg;  // device buffer of grid x 16 uint64, or NULL
+  if (info4) info4[0] = pl->grid, info4[1] = pl->ctas_per_sm, info4[2] = pl->block_n, info4[3] = pl->kp.num_m_tiles * pl->kp.num_n_tiles;
   return AY2_OK;
 }
 

@@ -130,6 +130,9 @@ double ay2_chain_plan_flops(const ay2_chain_plan* plan);
  * stage-2 K chunk}, and an optional device buffer (16 x 16 uint64) into which CTA 0 records %globaltimer per phase. */
 int ay2_chain_plan_info(const ay2_chain_plan* plan, int32_t* out8);
 int ay2_chain_plan_set_debug(ay2_chain_plan* plan, unsigned long long* dbg);
+/* Diagnostics for the single-conv plan: info4 = {grid, CTAs/SM, N tile, tiles}; dbg = device buffer of grid x 16 uint64
+ * into which every CTA records %globaltimer per phase (tools/conv_timeline.py), or NULL to switch it off. */
+int ay2_conv_plan_set_debug(ay2_conv_plan* plan, unsigned long long* dbg, int32_t* info4);
 
 /* ------------------------------------------------------------------------------------------------
  * Input side: NCHW image (uint8 or fp32) -> 2x2 space-to-depth NHWC bf16 with 16 channels
