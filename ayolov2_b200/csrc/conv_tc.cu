@@ -43,6 +43,7 @@ struct ConvKernelParams {
   int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
               // CTA fetches half of every weight (B) tile, multicast into both CTAs' shared memory
   HeadCandParams hc;  // detect head only: NMS candidates are scored and appended from the staged output tile
+  int experiment;           // diagnostics only (AY2_CONV_EXPERIMENT): bit 0 = the MMA warp skips the tcgen05.mma instructions
   unsigned long long* dbg;  // optional timeline buffer (tools/conv_timeline.py): every CTA records %globaltimer per phase
 };
 
@@ -69,13 +70,14 @@ struct ConvCfg {
   static constexpr int SLAB_BYTES = 128 * SWO;
   static constexpr int NSLAB = BLOCK_N / OC;
   static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2;
-  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256;  // bias slice + barriers + tmem ptr
+  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256;  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr
   // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
   // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
   static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
-  // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes; the 256-column tile (1 CTA/SM) uses two groups,
-  // each draining half of the columns, so that every scheduler has two epilogue warps to interleave.
-  static constexpr int EPI_GROUPS = BLOCK_N >= 128 ? 2 : 1;
+  // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes and owns ONE output slab (<= 64 columns): it drains
+  // it, stores it with TMA and waits for its own store only -- groups never synchronise with each other, and every
+  // scheduler has EPI_GROUPS x CTAS_PER_SM epilogue warps to interleave (the drain is latency-bound per warp).
+  static constexpr int EPI_GROUPS = NSLAB;
   static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
   static constexpr int COLS_PER_GROUP = BLOCK_N / EPI_GROUPS;
@@ -175,21 +177,23 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
   }
 }
 
-// Drain this warp group's column range of one accumulator: TMEM -> +bias -> act (-> + residual already staged in the
-// output slab) -> bf16 -> swizzled staging slab. Bias comes from shared memory with explicit ld.shared (a pointer derived
-// from the aligned dynamic-smem base loses its address space and compiles to generic loads).
+// Drain this warp group's slab of one accumulator: TMEM -> +bias -> act (-> + residual already staged in the output
+// slab) -> bf16 -> swizzled staging slab. Bias comes from shared memory with explicit ld.shared (a pointer derived from
+// the aligned dynamic-smem base loses its address space and compiles to generic loads). Activation / residual are
+// compile-time: no predicated-off residual code, no branch per column group.
 template <class Cfg, bool SILU, bool RES>
 __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint32_t staging_u32, uint32_t bias_u32, int et) {
+  constexpr int BLK = Cfg::OC < 32 ? Cfg::OC : 32;  // columns per tcgen05.ld
+  const uint32_t slab = staging_u32 + egrp * Cfg::SLAB_BYTES;
 #pragma unroll 1
-  for (int c0 = egrp * Cfg::COLS_PER_GROUP; c0 < (egrp + 1) * Cfg::COLS_PER_GROUP; c0 += 32) {
+  for (int cc = 0; cc < Cfg::OC; cc += BLK) {
+    const int c0 = egrp * Cfg::OC + cc;
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr + c0, v);
     tmem_ld_wait();
-    const uint32_t slab = staging_u32 + (c0 / Cfg::OC) * Cfg::SLAB_BYTES;
-    const int chunk0 = (c0 % Cfg::OC) / 8;
     const uint32_t ba = bias_u32 + c0 * 4;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < BLK / 8; ++g) {
       float bb[8], f[8];
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba + g * 32));
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + g * 32 + 16));
@@ -198,7 +202,7 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint
         const float x = __uint_as_float(v[g * 8 + i]) + bb[i];
         f[i] = SILU ? silu_f(x) : x;
       }
-      const uint32_t dst = slab + swizzled_offset<Cfg::SWO>(et, chunk0 + g);
+      const uint32_t dst = slab + swizzled_offset<Cfg::SWO>(et, cc / 8 + g);
       if (RES) {
         uint4 rv;
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(dst));
@@ -217,6 +221,18 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint
   }
 }
 
+template <class Cfg>
+__device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32_t taddr, int egrp, uint32_t staging_u32,
+                                               uint32_t bias_u32, int et) {
+  if (p.act == AY2_ACT_SILU) {
+    if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, egrp, staging_u32, bias_u32, et);
+    else drain_accumulator<Cfg, true, false>(taddr, egrp, staging_u32, bias_u32, et);
+  } else {
+    if (p.has_res) drain_accumulator<Cfg, false, true>(taddr, egrp, staging_u32, bias_u32, et);
+    else drain_accumulator<Cfg, false, false>(taddr, egrp, staging_u32, bias_u32, et);
+  }
+}
+
 template <int BLOCK_N, int CK>
 __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = ConvCfg<BLOCK_N, CK>;
@@ -231,8 +247,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   uint64_t* empty_bar = bars + Cfg::NSTAGES;      // [NSTAGES]
   uint64_t* tmem_full = bars + 2 * Cfg::NSTAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
-  uint64_t* res_full = tmem_empty + 2;            // [1]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 1);
+  uint64_t* res_full = tmem_empty + 2;            // [EPI_GROUPS <= 4]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 4);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
     }
-    mbar_init(res_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -363,7 +379,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k) {
+            for (int k = 0; k < CK / 16 && !(p.experiment & 1); ++k) {
               const uint64_t adesc = make_smem_desc_kmajor(a_addr + k * 32, Cfg::SWA);
               const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
               umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
@@ -389,79 +405,73 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
     const int box_rows = p.BH * p.BW;
     int it = 0;
     uint32_t res_phase = 0;
+    const bool leader = ewarp == 0;  // first warp of the group: lanes < NB own one box each (residual load, store, bulk group)
+    uint8_t* slab = staging + egrp * Cfg::SLAB_BYTES;
+    const int gbar = 2 + egrp;       // named barrier of this group
+    // one N tile: the bias slice never changes -> staged once
+    const bool bias_once = p.num_n_tiles == 1;
+    if (bias_once) {
+      for (int i = eall; i < BLOCK_N; i += Cfg::EPI_THREADS) bias_s[i] = p.bias[i];
+      named_bar_sync(1, Cfg::EPI_THREADS);
+    }
     for (int item = item0; item < total_items; item += item_step, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
       const int mg = item / p.num_n_tiles;
       const int m = mg * p.csize + crank;
       const int n0 = (item - mg * p.num_n_tiles) * BLOCK_N;
+      const int nc0 = n0 + egrp * Cfg::OC;  // first output channel of this group's slab
 
-      if (eall == 0) {
-        tma_store_wait_read<0>();  // previous tile's TMA stores have finished reading the staging buffer
-        if (p.has_res) {
-          mbar_expect_tx(res_full, Cfg::STAGING_BYTES);
-          for (int j = 0; j < p.NB; ++j) {
-            const int q = m * p.NB + j;
-            const int b = q / p.boxes_per_img;
-            const int r = q - b * p.boxes_per_img;
-            const int py = r / p.boxes_x;
-            const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
-#pragma unroll
-            for (int s = 0; s < Cfg::NSLAB; ++s)
-              tma_load_4d(&p.tmRes, res_full, staging + s * Cfg::SLAB_BYTES + j * box_rows * Cfg::SWO,
-                          n0 + s * Cfg::OC, ox, oy, b);
-          }
+      int cb = 0, cy = 0, cx = 0;
+      if (leader) {
+        {  // box j of this tile: lane j does the index arithmetic
+          const int q = m * p.NB + (lane & 7);
+          cb = q / p.boxes_per_img;
+          const int r = q - cb * p.boxes_per_img;
+          const int py = r / p.boxes_x;
+          cy = py * p.BH;
+          cx = (r - py * p.boxes_x) * p.BW;
         }
+        tma_store_wait_read<0>();  // the previous tile's store of this slab has finished reading it
+        if (p.has_res) {
+          if (lane == 0) mbar_expect_tx(&res_full[egrp], Cfg::SLAB_BYTES);
+          __syncwarp();
+          if (lane < p.NB) tma_load_4d(&p.tmRes, &res_full[egrp], slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+        }
+        if (!bias_once)
+          for (int i = lane; i < Cfg::OC; i += 32) bias_s[egrp * Cfg::OC + i] = p.bias[nc0 + i];
       }
-      for (int i = eall; i < BLOCK_N; i += Cfg::EPI_THREADS) bias_s[i] = p.bias[n0 + i];
-      named_bar_sync(1, Cfg::EPI_THREADS);
+      named_bar_sync(gbar, 128);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       if (eall == 0) CV_DBG(it == 0 ? 3 : 5);  // first / last accumulator complete
-      if (p.has_res) {
-        mbar_wait(res_full, res_phase);
-        res_phase ^= 1;
-      }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N;
-      // activation / residual are compile-time inside the drain loop: no predicated-off residual code, no branch per group
-      if (p.act == AY2_ACT_SILU) {
-        if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
-        else drain_accumulator<Cfg, true, false>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
-      } else {
-        if (p.has_res) drain_accumulator<Cfg, false, true>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
-        else drain_accumulator<Cfg, false, false>(taddr, egrp, smem_u32(staging), smem_u32(bias_s), et);
-      }
+      if (p.has_res) mbar_wait(&res_full[egrp], res_phase);
+      drain_dispatch<Cfg>(p, tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N, egrp, smem_u32(staging),
+                          smem_u32(bias_s), et);
       if (eall == 0 && it == 0) CV_DBG(12);  // first tile drained by this thread
-      // accumulator drained -> hand the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
-      // staging complete -> TMA store
-      fence_proxy_async_smem();
-      if (eall == 0 && it == 0) CV_DBG(13);  // fences done
-      named_bar_sync(1, Cfg::EPI_THREADS);
-      if (eall == 0 && it == 0) CV_DBG(14);  // all epilogue warps done
-      if (eall == 0) {
-        for (int j = 0; j < p.NB; ++j) {
-          const int q = m * p.NB + j;
-          const int b = q / p.boxes_per_img;
-          const int r = q - b * p.boxes_per_img;
-          const int py = r / p.boxes_x;
-          const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
-#pragma unroll
-          for (int s = 0; s < Cfg::NSLAB; ++s)
-            tma_store_4d(&p.tmOut, staging + s * Cfg::SLAB_BYTES + j * box_rows * Cfg::SWO, n0 + s * Cfg::OC, ox,
-                         oy, b);
+      mbar_arrive(&tmem_empty[acc]);  // accumulator drained -> back to the MMA warp
+      fence_proxy_async_smem();       // staging complete -> visible to the TMA store
+      named_bar_sync(gbar, 128);
+      if (leader) {
+        if (lane < p.NB) {
+          tma_store_4d(&p.tmOut, slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+          tma_store_commit();
         }
-        tma_store_commit();
-        CV_DBG(it == 0 ? 4 : 6);  // first / last tile's store issued
+        if (eall == 0) CV_DBG(it == 0 ? 4 : 6);  // first / last tile's store issued
       }
-      // detect head: score NMS candidates from the staged tile while the TMA store drains it (both only read);
-      // nobody rewrites the staging buffer before every epilogue thread has passed the next iteration's barrier
-      if (p.hc.keys) head_candidates<Cfg>(p, staging, m, et, egrp, lane);
+      res_phase ^= 1;
+      if (p.hc.keys) {
+        // detect head: score NMS candidates from the whole staged tile (all slabs) while the TMA stores drain it (both
+        // only read); no group may start rewriting its slab before every group has finished reading
+        named_bar_sync(1, Cfg::EPI_THREADS);
+        head_candidates<Cfg>(p, staging, m, et, egrp, lane);
+        named_bar_sync(1, Cfg::EPI_THREADS);
+      }
     }
-    if (eall == 0) {
+    if (leader) {
       tma_store_wait_all<0>();
-      CV_DBG(7);  // stores drained
+      if (eall == 0) CV_DBG(7);  // stores drained
     }
   }
 
@@ -684,6 +694,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   // neighbouring unicast requests, so multicast saves no LTS bandwidth and only adds lock-step. Off by default.
   static const int env_cluster = getenv("AY2_CONV_CLUSTER") ? atoi(getenv("AY2_CONV_CLUSTER")) : 1;
   kp.csize = (env_cluster == 2 && kp.num_m_tiles >= 2) ? 2 : 1;
+  kp.experiment = getenv("AY2_CONV_EXPERIMENT") ? atoi(getenv("AY2_CONV_EXPERIMENT")) : 0;
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);
   const int oc = bn < 64 ? bn : 64;
   // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)
