@@ -31,8 +31,7 @@ p = os.path.join(OUT, "launches.csv")
 if os.path.exists(p):
     rows = [(r["Kernel Name"], float(r["Metric Value"].replace(",", ""))) for r in rows_of(p) if r.get("Metric Name") == "gpu__time_duration.sum"]
     starts = [i for i, r in enumerate(rows) if "space_to_depth" in r[0]]
-    ends = [i for i, r in enumerate(rows) if "nms_sort_scan" in r[0] and i > starts[-1]]
-    step = rows[starts[-1]:ends[0] + 1]
+    step = rows[starts[-1]:]
     agg = collections.OrderedDict()
     for n, v in step:
         agg.setdefault(short(n), [0, 0.0])
@@ -40,7 +39,7 @@ if os.path.exists(p):
         agg[short(n)][1] += v
     tot = sum(v for _, v in step)
     with open(os.path.join(PROF, f"{tag}_launches_step.csv"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none over `python tools/profile_step.py 2` (eager replay of the\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none over `python tools/profile_step.py 3` (eager replay of the\n")
         f.write("# benchmarked launch sequence: bs64 yolov5s 640x640, uint8 in, fused head -> NMS). Cold-cache serialised times: compare SHARES.\n")
         f.write(f"# launches in one step: {len(step)}; sum of durations {tot / 1e3:.1f} us\n")
         f.write("kernel,launches,total_us,share_pct\n")
@@ -66,7 +65,7 @@ if os.path.exists(p):
         return val * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
     tot_rd = tot_wr = tot_us = tot_l2 = 0.0
     with open(os.path.join(PROF, f"{tag}_conv_launches_metrics.csv"), "w") as f:
-        f.write("# ncu metrics (clock-control none) for the 52 conv_tc_kernel launches of ONE bs64 yolov5s step, in launch order\n")
+        f.write(f"# ncu metrics (clock-control none) for the {len(per)} conv_tc_kernel / conv_chain_kernel launches of ONE bs64 yolov5s step, in launch order\n")
         f.write("idx,kernel,dur_us,dram_read_MB,dram_write_MB,l2_MB,tensor_pipe_pct,xu_pipe_pct,dram_pct\n")
         for i, (k, m) in enumerate(per.items()):
             rd, wr = to_bytes(m["dram__bytes_read.sum"]), to_bytes(m["dram__bytes_write.sum"])
@@ -84,7 +83,7 @@ if os.path.exists(p):
     print(json.dumps(summary, indent=1))
 
 # 3. full captures -> raw metric CSV (small) for whatever .ncu-rep files exist
-for rep in ("prof_conv3", "prof_nms"):
+for rep in ("prof_conv3", "prof_chain", "prof_nms"):
     rp = os.path.join(OUT, rep + ".ncu-rep")
     if not os.path.exists(rp):
         continue
