@@ -43,6 +43,8 @@ struct ConvKernelParams {
   int csize;  // CTAs per cluster (1 or 2): with 2, the pair works on neighbouring M tiles of the same N tile and each
               // CTA fetches half of every weight (B) tile, multicast into both CTAs' shared memory
   HeadCandParams hc;  // detect head only: NMS candidates are scored and appended from the staged output tile
+  // halo kernel (conv_halo_kernel): work items are 16-row bands x pairs of 8-pixel-wide half tiles
+  int hl_pairs_x, hl_bands_y, hl_w_halves;
   int experiment;           // diagnostics only (AY2_CONV_EXPERIMENT): bit 0 = the MMA warp skips the tcgen05.mma instructions
   unsigned long long* dbg;  // optional timeline buffer (tools/conv_timeline.py): every CTA records %globaltimer per phase
 };
@@ -182,16 +184,14 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
 // the aligned dynamic-smem base loses its address space and compiles to generic loads). Activation / residual are
 // compile-time: no predicated-off residual code, no branch per column group.
 template <class Cfg, bool SILU, bool RES>
-__device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint32_t staging_u32, uint32_t bias_u32, int et) {
+__device__ __forceinline__ void drain_accumulator(uint32_t taddr, uint32_t slab, uint32_t bias_u32, int et) {
   constexpr int BLK = Cfg::OC < 32 ? Cfg::OC : 32;  // columns per tcgen05.ld
-  const uint32_t slab = staging_u32 + egrp * Cfg::SLAB_BYTES;
 #pragma unroll 1
   for (int cc = 0; cc < Cfg::OC; cc += BLK) {
-    const int c0 = egrp * Cfg::OC + cc;
     uint32_t v[32];
-    tmem_ld_32x32b_x32(taddr + c0, v);
+    tmem_ld_32x32b_x32(taddr + cc, v);
     tmem_ld_wait();
-    const uint32_t ba = bias_u32 + c0 * 4;
+    const uint32_t ba = bias_u32 + cc * 4;
 #pragma unroll
     for (int g = 0; g < BLK / 8; ++g) {
       float bb[8], f[8];
@@ -221,15 +221,15 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, int egrp, uint
   }
 }
 
+// taddr: TMEM address (lane quadrant + first column) of the slab; slab: its staging bytes; bias_u32: its bias slice
 template <class Cfg>
-__device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32_t taddr, int egrp, uint32_t staging_u32,
-                                               uint32_t bias_u32, int et) {
+__device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32_t taddr, uint32_t slab, uint32_t bias_u32, int et) {
   if (p.act == AY2_ACT_SILU) {
-    if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, egrp, staging_u32, bias_u32, et);
-    else drain_accumulator<Cfg, true, false>(taddr, egrp, staging_u32, bias_u32, et);
+    if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, slab, bias_u32, et);
+    else drain_accumulator<Cfg, true, false>(taddr, slab, bias_u32, et);
   } else {
-    if (p.has_res) drain_accumulator<Cfg, false, true>(taddr, egrp, staging_u32, bias_u32, et);
-    else drain_accumulator<Cfg, false, false>(taddr, egrp, staging_u32, bias_u32, et);
+    if (p.has_res) drain_accumulator<Cfg, false, true>(taddr, slab, bias_u32, et);
+    else drain_accumulator<Cfg, false, false>(taddr, slab, bias_u32, et);
   }
 }
 
@@ -446,8 +446,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
       tcgen05_fence_after();
       if (eall == 0) CV_DBG(it == 0 ? 3 : 5);  // first / last accumulator complete
       if (p.has_res) mbar_wait(&res_full[egrp], res_phase);
-      drain_dispatch<Cfg>(p, tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N, egrp, smem_u32(staging),
-                          smem_u32(bias_s), et);
+      drain_dispatch<Cfg>(p, tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * BLOCK_N + egrp * Cfg::OC,
+                          smem_u32(slab), smem_u32(bias_s) + egrp * Cfg::OC * 4, et);
       if (eall == 0 && it == 0) CV_DBG(12);  // first tile drained by this thread
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);  // accumulator drained -> back to the MMA warp
@@ -480,6 +480,254 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   else __syncthreads();
   if (threadIdx.x == 0) {
     CV_DBG(8);  // all roles finished
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 15] = clock64();
+  }
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution from a HALO tile: the nine taps are nine shifted views of ONE input tile.
+//
+// conv_tc_kernel fetches a 128-pixel A tile per tap (9x the input through L2 -> shared memory) and a weight tile per
+// 128 pixels; measured, the 3x3 layers sit at the SM's ingest limit (~45 B/clk) at half the tensor rate. Here one work
+// item is a 16 x 16 output tile (two 16 x 8 halves, each one M = 128 accumulator): per 64-channel chunk the
+// 18 x 18 x 64 input halo is loaded ONCE (TMA, SWIZZLE_128B: one pixel = one 128-byte row) and every weight tile is
+// shared by both halves: 3.1x fewer bytes per FLOP.
+//   A operand of tap (ky, kx), half h: the UMMA descriptor's start address is the halo row (ky * HW + kx + 8 h) --
+//   an 8-row group is 8 horizontally adjacent pixels = 8 consecutive 128-byte rows, the group stride (SBO) one halo
+//   line (HW rows). The 128-byte swizzle is a function of the shared-memory ADDRESS bits [7,10) for TMA writes and
+//   UMMA reads alike, so a start address shifted by whole rows addresses the same bytes TMA wrote.
+// Tiles at the right edge have one half (HW = 10 instead of 18). Epilogue groups own one (half, 64-column slab).
+// ------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct HaloCfg {
+  static constexpr int CK = 64, SWA = 128;
+  static constexpr int TH = 16, TW = 8;                   // one half tile
+  static constexpr int HH = TH + 2;                       // halo lines
+  static constexpr int X_SLOT = (HH * (2 * TW + 2) * SWA + 1023) / 1024 * 1024;  // 18 x 18 pixels x 128 B
+  static constexpr int NX = 2;
+  static constexpr int W_STAGE = BLOCK_N * SWA;
+  static constexpr int OC = BLOCK_N < 64 ? BLOCK_N : 64;
+  static constexpr int SWO = OC * 2;
+  static constexpr int SLAB_BYTES = 128 * SWO;
+  static constexpr int NSLAB = BLOCK_N / OC;
+  static constexpr int EPI_GROUPS = 2 * NSLAB;            // (half, slab)
+  static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
+  static constexpr int THREADS = 128 + EPI_THREADS;
+  static constexpr int STAGING_BYTES = EPI_GROUPS * SLAB_BYTES;
+  static constexpr int TAIL_BYTES = EPI_GROUPS * OC * 4 + 256;  // per-group bias slice + barriers + tmem ptr
+  static constexpr int NW_RAW = (kSmemPerSm - 2048 - NX * X_SLOT - STAGING_BYTES - TAIL_BYTES) / W_STAGE;
+  static constexpr int NW = NW_RAW > 8 ? 8 : NW_RAW;
+  static constexpr int SMEM_BYTES = 1024 + NX * X_SLOT + NW * W_STAGE + STAGING_BYTES + TAIL_BYTES;
+  static constexpr int TMEM_COLS = 4 * BLOCK_N;           // two halves, double-buffered: 128 / 256 / 512
+  static_assert(NW >= 3, "not enough shared memory for the weight ring");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = HaloCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xring = smem;
+  uint8_t* wring = xring + Cfg::NX * Cfg::X_SLOT;
+  uint8_t* staging = wring + Cfg::NW * Cfg::W_STAGE;
+  float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);  // [EPI_GROUPS][OC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + Cfg::EPI_GROUPS * Cfg::OC);
+  uint64_t* xfull = bars;                // [2]
+  uint64_t* xempty = bars + 2;           // [2]
+  uint64_t* wfull = bars + 4;            // [8]
+  uint64_t* wempty = bars + 12;          // [8]
+  uint64_t* tmem_full = bars + 20;       // [2]
+  uint64_t* tmem_empty = bars + 22;      // [2]
+  uint64_t* res_full = bars + 24;        // [EPI_GROUPS <= 4]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    CV_DBG(0);
+    if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 9] = clock64();
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&xfull[i], 1);
+      mbar_init(&xempty[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmOut);
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) CV_DBG(1);
+
+  const int tiles_per_img = p.hl_pairs_x * p.hl_bands_y;
+  const int total_items = tiles_per_img * p.num_m_tiles * p.num_n_tiles;  // num_m_tiles == batch here
+  const int cin_chunks = p.cin_chunks;
+  // item -> (N tile fastest: the second N tile finds the halo in L2, tile, image)
+  auto decode = [&](int item, int& n0, int& b, int& y0, int& x0, int& nh) {
+    const int t = item / p.num_n_tiles;
+    n0 = (item - t * p.num_n_tiles) * BLOCK_N;
+    b = t / tiles_per_img;
+    const int r = t - b * tiles_per_img;
+    const int band = r / p.hl_pairs_x;
+    const int pair = r - band * p.hl_pairs_x;
+    y0 = band * Cfg::TH;
+    x0 = pair * 2 * Cfg::TW;
+    nh = p.hl_w_halves - 2 * pair >= 2 ? 2 : 1;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    int xs = 0, xph = 0, ws = 0, wph = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int n0, b, y0, x0, nh;
+      decode(item, n0, b, y0, x0, nh);
+      const CUtensorMap* tmX = nh == 2 ? &p.tmA[0] : &p.tmA[1];
+      const uint32_t xbytes = Cfg::HH * (nh * Cfg::TW + 2) * Cfg::SWA;
+      for (int c = 0; c < cin_chunks; ++c) {
+        mbar_wait(&xempty[xs], xph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&xfull[xs], xbytes);
+          tma_load_4d(tmX, &xfull[xs], xring + xs * Cfg::X_SLOT, c * Cfg::CK, x0 - 1, y0 - 1, b);
+        }
+        __syncwarp();
+        if (++xs == Cfg::NX) { xs = 0; xph ^= 1; }
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&wempty[ws], wph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&wfull[ws], Cfg::W_STAGE);
+            tma_load_2d(&p.tmB, &wfull[ws], wring + ws * Cfg::W_STAGE, tap * p.cin + c * Cfg::CK, n0);
+          }
+          __syncwarp();
+          if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+    // descriptor halves: lo = start address >> 4 | LBO (unused for swizzled K-major: 1) << 16;
+    //                    hi = SBO >> 4 | version 1 << 14 | base offset << 17 | SWIZZLE_128B (2) << 29
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t x_lo0 = ((smem_u32(xring) & 0x3FFFF) >> 4) | (1u << 16);
+    const uint32_t w_lo0 = ((smem_u32(wring) & 0x3FFFF) >> 4) | (1u << 16);
+    int xs = 0, xph = 0, ws = 0, wph = 0, it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int n0, b, y0, x0, nh;
+      decode(item, n0, b, y0, x0, nh);
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d0 = tmem_base + acc * 2 * BLOCK_N;
+      const int hw = nh * Cfg::TW + 2;                       // halo line in pixels == rows
+      const uint32_t a_hi0 = (static_cast<uint32_t>(hw * Cfg::SWA) >> 4) | (1u << 14) | (2u << 29);
+      for (int c = 0; c < cin_chunks; ++c) {
+        mbar_wait(&xfull[xs], xph);
+        const uint32_t a_slot = x_lo0 + xs * (Cfg::X_SLOT >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          mbar_wait(&wfull[ws], wph);
+          tcgen05_fence_after();
+          if (c == 0 && tap == 0 && it == 0 && lane == 0) CV_DBG(2);
+          const uint32_t a_tap = a_slot + (ky * hw + kx) * (Cfg::SWA >> 4);  // whole rows: 8 address units each
+          const uint32_t b_lo = w_lo0 + ws * (Cfg::W_STAGE >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < Cfg::CK / 16; ++k) {
+              const uint32_t accum = (c | tap | k) != 0 ? 1u : 0u;
+              for (int h = 0; h < nh; ++h) {
+                const uint32_t a_lo = a_tap + h * (Cfg::TW * Cfg::SWA >> 4) + 2 * k;
+                // experiment bit 1: descriptor base offset = row phase of the start address inside the 1024-byte pattern
+                const uint32_t a_hi = (p.experiment & 2) ? (a_hi0 | (((a_lo >> 3) & 7u) << 17)) : a_hi0;
+                umma_f16_lohi(d0 + h * BLOCK_N, a_lo, a_hi, b_lo + 2 * k, b_hi, idesc, accum);
+              }
+            }
+            umma_commit(&wempty[ws]);
+            if (tap == 8) umma_commit(&xempty[xs]);
+            if (tap == 8 && c == cin_chunks - 1) umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
+        }
+        if (++xs == Cfg::NX) { xs = 0; xph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue ===============================
+    const int eall = threadIdx.x - 128;
+    const int et = eall & 127;          // accumulator row == TMEM lane == pixel (y = et / 8, x = et % 8) of the half
+    const int egrp = eall >> 7;
+    const int half = egrp / Cfg::NSLAB, slabi = egrp - half * Cfg::NSLAB;
+    const int ewarp = warp & 3;
+    const bool leader = ewarp == 0;
+    uint8_t* slab = staging + egrp * Cfg::SLAB_BYTES;
+    float* bias_g = bias_s + egrp * Cfg::OC;
+    const int gbar = 2 + egrp;
+    const bool bias_once = p.num_n_tiles == 1;
+    if (bias_once && et < Cfg::OC) bias_g[et] = p.bias[slabi * Cfg::OC + et];
+    uint32_t res_phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int n0, b, y0, x0, nh;
+      decode(item, n0, b, y0, x0, nh);
+      const int acc = it & 1;
+      const bool active = half < nh;
+      const int nc0 = n0 + slabi * Cfg::OC;
+      const int xh = x0 + half * Cfg::TW;
+      if (leader && active) {
+        tma_store_wait_read<0>();  // the previous store of this slab has been read out
+        if (p.has_res && lane == 0) {
+          mbar_expect_tx(&res_full[egrp], Cfg::SLAB_BYTES);
+          tma_load_4d(&p.tmRes, &res_full[egrp], slab, nc0, xh, y0, b);
+        }
+      }
+      if (!bias_once && et < Cfg::OC) bias_g[et] = p.bias[nc0 + et];
+      named_bar_sync(gbar, 128);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tcgen05_fence_after();
+      if (eall == 0) CV_DBG(it == 0 ? 3 : 5);
+      if (active) {
+        if (p.has_res) {
+          mbar_wait(&res_full[egrp], res_phase);
+          res_phase ^= 1;
+        }
+        drain_dispatch<Cfg>(p, tmem_base + (static_cast<uint32_t>(ewarp * 32) << 16) + acc * 2 * BLOCK_N + half * BLOCK_N + slabi * Cfg::OC,
+                            smem_u32(slab), smem_u32(bias_g), et);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      fence_proxy_async_smem();
+      named_bar_sync(gbar, 128);
+      if (leader && active && lane == 0) {
+        tma_store_4d(&p.tmOut, slab, nc0, xh, y0, b);
+        tma_store_commit();
+      }
+      if (eall == 0) CV_DBG(it == 0 ? 4 : 6);
+    }
+    if (leader) {
+      tma_store_wait_all<0>();
+      if (eall == 0) CV_DBG(7);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CV_DBG(8);
     if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 15] = clock64();
   }
   if (warp == 2) {
@@ -568,7 +816,7 @@ struct ay2_conv_plan {
   ay2_conv_desc desc;
   int block_n, ck;
   int ctas_per_sm, threads;
-  int grid;
+  int grid, halo;
   size_t smem;
   void (*kernel)(const ConvKernelParams);
 };
@@ -648,6 +896,65 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   pl->block_n = bn;
   pl->ck = ck;
   ConvKernelParams& kp = pl->kp;
+  kp.experiment = getenv("AY2_CONV_EXPERIMENT") ? atoi(getenv("AY2_CONV_EXPERIMENT")) : 0;
+  {
+    // 3x3 / s1 / p1 over whole 64-channel chunks: the halo kernel (unless the 16 x 8 half tiles would waste > 30 % of
+    // the MMA rows on this feature-map size, e.g. 20 x 20)
+    static const int env_halo = getenv("AY2_CONV_HALO") ? atoi(getenv("AY2_CONV_HALO")) : 1;
+    const int bands = ceil_div(d->out_h, 16), halves = ceil_div(d->out_w, 8);
+    const bool shape_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->cin % 64 == 0 &&
+                          split == 0 && d->in_pix_stride <= 0 && d->in_row_pixels <= 0 && d->out_pix_stride <= 0 &&
+                          d->out_row_pixels <= 0;
+    const bool fill_ok = (double)bands * 16 * halves * 8 <= 1.3 * d->out_h * d->out_w;
+    if (env_halo && shape_ok && (fill_ok || env_halo == 2)) {
+      const int nt = bn < 128 ? bn : 128;
+      pl->block_n = nt;
+      pl->ck = 64;
+      kp.num_m_tiles = d->batch;
+      kp.num_n_tiles = d->cout_pad / nt;
+      kp.hl_bands_y = bands;
+      kp.hl_w_halves = halves;
+      kp.hl_pairs_x = ceil_div(halves, 2);
+      kp.cin = d->cin;
+      kp.cin_chunks = d->cin / 64;
+      kp.cout_pad = d->cout_pad;
+      kp.act = d->act;
+      kp.has_res = d->res_cstride != 0;
+      kp.bias = bias;
+      kp.csize = 1;
+      const int64_t cs = d->in_cstride, os = d->out_cstride, rs = d->res_cstride;
+      const int W = d->in_w, H = d->in_h;
+      const int oc = nt < 64 ? nt : 64;
+      int rc = encode_act_map(&kp.tmA[0], in, d->cin, W, H, d->batch, cs, cs * W, cs * W * H, 64, 18, 18);
+      if (rc == AY2_OK) rc = encode_act_map(&kp.tmA[1], in, d->cin, W, H, d->batch, cs, cs * W, cs * W * H, 64, 10, 18);
+      if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, 9 * d->cin, d->cout_pad, 64, nt);
+      if (rc == AY2_OK) rc = encode_act_map(&kp.tmOut, out, d->cout, W, H, d->batch, os, os * W, os * W * H, oc, 8, 16);
+      if (rc == AY2_OK && kp.has_res) rc = encode_act_map(&kp.tmRes, residual, d->cout, W, H, d->batch, rs, rs * W, rs * W * H, oc, 8, 16);
+      if (rc != AY2_OK) {
+        delete pl;
+        return rc;
+      }
+      if (nt == 32) pl->kernel = conv_halo_kernel<32>, pl->smem = HaloCfg<32>::SMEM_BYTES, pl->threads = HaloCfg<32>::THREADS;
+      else if (nt == 64) pl->kernel = conv_halo_kernel<64>, pl->smem = HaloCfg<64>::SMEM_BYTES, pl->threads = HaloCfg<64>::THREADS;
+      else pl->kernel = conv_halo_kernel<128>, pl->smem = HaloCfg<128>::SMEM_BYTES, pl->threads = HaloCfg<128>::THREADS;
+      pl->ctas_per_sm = 1;
+      pl->halo = 1;
+      cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);
+      if (e != cudaSuccess) {
+        delete pl;
+        set_error("cudaFuncSetAttribute(halo smem=%zu) failed: %s", pl->smem, cudaGetErrorString(e));
+        return AY2_ERR_CUDA;
+      }
+      cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int items = kp.hl_pairs_x * kp.hl_bands_y * d->batch * kp.num_n_tiles;
+      pl->grid = items < sms ? items : sms;
+      *plan_out = pl;
+      return AY2_OK;
+    }
+  }
   int bh, bw;
   pick_box(d->out_h, d->out_w, &bh, &bw);
   kp.BH = bh;
@@ -694,7 +1001,6 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   // neighbouring unicast requests, so multicast saves no LTS bandwidth and only adds lock-step. Off by default.
   static const int env_cluster = getenv("AY2_CONV_CLUSTER") ? atoi(getenv("AY2_CONV_CLUSTER")) : 1;
   kp.csize = (env_cluster == 2 && kp.num_m_tiles >= 2) ? 2 : 1;
-  kp.experiment = getenv("AY2_CONV_EXPERIMENT") ? atoi(getenv("AY2_CONV_EXPERIMENT")) : 0;
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);
   const int oc = bn < 64 ? bn : 64;
   // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)
@@ -752,6 +1058,7 @@ extern "C" int ay2_conv_plan_set_head_candidates(ay2_conv_plan* pl, const ay2_nm
   }
   const ay2_conv_desc& d = pl->desc;
   AY2_REQUIRE(nms_workspace && workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace missing or too small");
+  AY2_REQUIRE(!pl->halo, "head candidates are scored by the 1x1 detect convolutions, not by a 3x3 halo plan");
   AY2_REQUIRE(pl->kp.num_n_tiles == 1, "head candidates need all %d output channels in one N tile (block_n=%d)", d.cout,
               pl->block_n);
   AY2_REQUIRE(na >= 1 && p->no > 5 && na * p->no <= d.cout, "head layout na=%d no=%d does not fit cout=%d", na, p->no, d.cout);
@@ -810,7 +1117,9 @@ extern "C" int ay2_conv_plan_run(const ay2_conv_plan* pl, void* stream) {
 extern "C" int ay2_conv_plan_set_debug(ay2_conv_plan* pl, unsigned long long* dbg, int32_t* info4) {
   AY2_REQUIRE(pl, "ay2_conv_plan_set_debug: null plan");
   pl->kp.dbg = dbg;  // device buffer of grid x 16 uint64, or NULL
-  if (info4) info4[0] = pl->grid, info4[1] = pl->ctas_per_sm, info4[2] = pl->block_n, info4[3] = pl->kp.num_m_tiles * pl->kp.num_n_tiles;
+  if (info4)
+    info4[0] = pl->grid, info4[1] = pl->ctas_per_sm, info4[2] = pl->halo ? -pl->block_n : pl->block_n,
+    info4[3] = (pl->halo ? pl->kp.hl_pairs_x * pl->kp.hl_bands_y : 1) * pl->kp.num_m_tiles * pl->kp.num_n_tiles;
   return AY2_OK;
 }
 

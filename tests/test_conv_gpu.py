@@ -25,6 +25,12 @@ CASES = [
     (5, 10, 10, 256, 128, 3, 1, 1, 1, False, False, False), # tiny maps, M tail
     (1, 80, 80, 128, 128, 3, 2, 1, 1, False, True, True),
     (2, 20, 20, 1024, 512, 1, 1, 0, 1, False, False, False),# SPPF conv2-like, long K
+    # 3x3 / s1 / p1 with Cin % 64 == 0 -> halo kernel (16 x 8 half tiles, shifted-descriptor taps)
+    (2, 40, 40, 128, 128, 3, 1, 1, 1, True, False, False),  # two K chunks, residual, ragged bands (40 = 16 + 16 + 8)
+    (1, 80, 80, 64, 64, 3, 1, 1, 1, False, True, True),     # exact tiling, slices of wider buffers
+    (1, 48, 24, 64, 32, 3, 1, 1, 0, False, False, False),   # odd number of halves (2 + 1), N = 32
+    (1, 32, 32, 128, 256, 3, 1, 1, 1, False, False, False), # two N tiles of 128
+    (2, 16, 40, 320, 64, 3, 1, 1, 1, True, False, True),    # five K chunks
 ]
 
 
