@@ -82,6 +82,7 @@ class LossParams(C.Structure):
         ("balance", C.c_float * 5),
         ("anchor_t", C.c_float), ("box", C.c_float), ("obj", C.c_float), ("cls", C.c_float),
         ("cls_pw", C.c_float), ("obj_pw", C.c_float), ("cp", C.c_float), ("cn", C.c_float),
+        ("fl_gamma", C.c_float), ("fl_alpha", C.c_float),
     ]
 
 
@@ -146,6 +147,7 @@ _PROTOS = {
     "ay2_conv_plan_set_head_candidates": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_int32, C.c_int32, C.c_void_p,
                                                     C.c_void_p, C.c_size_t]),
     "ay2_box_iou": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ay2_nms_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_nms_candidates_begin": (C.c_int, [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ay2_nms_from_candidates": (C.c_int, [C.POINTER(HeadLevels), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -36,7 +36,7 @@ struct LossKernelParams {
   const float* anchors;  // (nl, na, 2) grid units
   const float* gscale;   // device scalar or nullptr (= 1)
   int nl, na, nc, no, bs, nt;
-  float anchor_t, hbox, hobj, hcls, cls_pw, obj_pw, cp, cn;
+  float anchor_t, hbox, hobj, hcls, cls_pw, obj_pw, cp, cn, fl_gamma, fl_alpha;
   double* acc;  // [nl][3] : sum(1 - ciou), sum(cls bce), sum(obj bce)
   int* count;   // [nl]
 };
@@ -121,6 +121,26 @@ __global__ void loss_assign_kernel(LossKernelParams p) {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+// One element of BCEWithLogits(pos_weight) and its derivative; with gamma > 0 the FocalLoss wrapper (losses.py:64-114):
+// el * alpha_t * (1 - p_t)^gamma, p_t = t p + (1 - t)(1 - p), alpha_t = t a + (1 - t)(1 - a); d/dx by the product rule,
+// d p_t / dx = (2t - 1) p (1 - p).
+__device__ __forceinline__ float bce_elem(float x, float t, float pw, float gamma, float alpha, bool want_grad, float* grad) {
+  const float bce = pw * t * softplusf_(-x) + (1.0f - t) * softplusf_(x);
+  if (gamma <= 0.0f) {
+    if (want_grad) *grad = sigmoidf_(x) * (1.0f - t + pw * t) - pw * t;
+    return bce;
+  }
+  const float s = sigmoidf_(x);
+  const float q = 1.0f - (t * s + (1.0f - t) * (1.0f - s));
+  const float af = t * alpha + (1.0f - t) * (1.0f - alpha);
+  const float m = powf(q, gamma);
+  if (want_grad) {
+    const float dbce = s * (1.0f - t + pw * t) - pw * t;
+    const float dm = q > 0.0f ? -gamma * powf(q, gamma - 1.0f) * (2.0f * t - 1.0f) * s * (1.0f - s) : 0.0f;
+    *grad = af * (dbce * m + bce * dm);
+  }
+  return bce * af * m;
+}
 // d min(a,b)/da and d max(a,b)/da with torch's even split on ties
 __device__ __forceinline__ float dmin_a(float a, float b) { return a < b ? 1.f : (a == b ? 0.5f : 0.f); }
 __device__ __forceinline__ float dmax_a(float a, float b) { return a > b ? 1.f : (a == b ? 0.5f : 0.f); }
@@ -208,11 +228,9 @@ __global__ void loss_match_kernel(LossKernelParams p) {
       for (int k = lane; k < p.nc; k += 32) {
         const float x = ps[5 + k];
         const float t = k == m.cls ? p.cp : p.cn;
-        sum += p.cls_pw * t * softplusf_(-x) + (1.0f - t) * softplusf_(x);
-        if (gp) {
-          const float s = sigmoidf_(x);
-          atomicAdd(gp + 5 + k, gsc * (s * (1.0f - t + p.cls_pw * t) - p.cls_pw * t));
-        }
+        float g = 0.f;
+        sum += bce_elem(x, t, p.cls_pw, p.fl_gamma, p.fl_alpha, gp != nullptr, &g);
+        if (gp) atomicAdd(gp + 5 + k, gsc * g);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -230,12 +248,10 @@ __global__ void loss_obj_kernel(LossKernelParams p, int level) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
     const float x = L.pred[i * p.no + 4];
     const float t = L.tobj[i];
-    sum += p.obj_pw * t * softplusf_(-x) + (1.0f - t) * softplusf_(x);
-    if (L.grad) {
-      const float s = sigmoidf_(x);
-      // the matched cells already hold box/cls gradients in other channels; channel 4 is written only here
-      L.grad[i * p.no + 4] = gsc * (s * (1.0f - t + p.obj_pw * t) - p.obj_pw * t);
-    }
+    float g = 0.f;
+    sum += bce_elem(x, t, p.obj_pw, p.fl_gamma, p.fl_alpha, L.grad != nullptr, &g);
+    // the matched cells already hold box/cls gradients in other channels; channel 4 is written only here
+    if (L.grad) L.grad[i * p.no + 4] = gsc * g;
   }
   __shared__ float red[32];
 #pragma unroll
@@ -340,6 +356,8 @@ extern "C" int ay2_yolo_loss(const ay2_loss_params* hp, const float* const* pred
   kp.obj_pw = hp->obj_pw;
   kp.cp = hp->cp;
   kp.cn = hp->cn;
+  kp.fl_gamma = hp->fl_gamma;
+  kp.fl_alpha = hp->fl_alpha;
   // accumulators, counts, tobj <- 0 ; owner <- -1 (0xFF bytes)
   AY2_CHECK_CUDA(cudaMemsetAsync(ws, 0, head + tobj_bytes, st));
   AY2_CHECK_CUDA(cudaMemsetAsync(ws + owner_off, 0xFF, off - owner_off, st));

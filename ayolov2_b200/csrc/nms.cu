@@ -1107,3 +1107,80 @@ extern "C" int ay2_box_iou(const float* box1, int32_t n, const float* box2, int3
   count_launch();
   return AY2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// torchvision.ops.nms on an arbitrary box list (metrics.py:385 and the "batched_nms" / "merge_nms" nms_type branches,
+// :391-431): `order` = indices by descending score (stable), greedy suppression IoU > thr with the same exact test as
+// the batched kernel (iou_gt). Phase 1 fills the upper-triangular suppression bit matrix over sorted positions,
+// phase 2 walks it once (one CTA; the walk is inherently sequential) and emits the kept ORIGINAL indices in score order.
+// ------------------------------------------------------------------------------------------------
+namespace ay2 {
+__global__ void nms_boxes_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, int n, double iou_thres,
+                                      unsigned long long* __restrict__ mask) {
+  const int words = (n + 63) / 64;
+  const IouThr t = make_iou_thr(iou_thres);
+  const long long total = (long long)n * words;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / words), w = (int)(idx - (long long)i * words);
+    unsigned long long bits = 0;
+    if (w * 64 + 63 > i) {
+      const float4 a = boxes[order[i]];
+      const float aa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+      for (int k = 0; k < 64; ++k) {
+        const int j = w * 64 + k;
+        if (j <= i || j >= n) continue;
+        const float4 b = boxes[order[j]];
+        const float ab = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+        if (iou_gt(a, aa, b, ab, t)) bits |= 1ull << k;
+      }
+    }
+    mask[idx] = bits;
+  }
+}
+
+__global__ void nms_boxes_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
+                                      int* __restrict__ keep, int* __restrict__ count) {
+  extern __shared__ unsigned long long remv[];
+  const int words = (n + 63) / 64;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) remv[w] = 0;
+  __shared__ int nkeep;
+  if (threadIdx.x == 0) nkeep = 0;
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    const bool dead = (remv[i >> 6] >> (i & 63)) & 1ull;  // uniform: every thread reads the same word
+    __syncthreads();
+    if (!dead) {
+      if (threadIdx.x == 0) keep[nkeep++] = order[i];
+      for (int w = (i >> 6) + threadIdx.x; w < words; w += blockDim.x) remv[w] |= mask[(long long)i * words + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = nkeep;
+}
+}  // namespace ay2
+
+extern "C" int ay2_nms_boxes(const float* boxes, const int32_t* order, int32_t n, double iou_thres, unsigned long long* mask_ws,
+                             int32_t* keep, int32_t* count, void* stream) {
+  AY2_REQUIRE(n >= 0 && count, "ay2_nms_boxes: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    AY2_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+    return AY2_OK;
+  }
+  AY2_REQUIRE(boxes && order && mask_ws && keep, "ay2_nms_boxes: null pointer");
+  AY2_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "ay2_nms_boxes: boxes must be 16-byte aligned");
+  const int words = (n + 63) / 64;
+  AY2_REQUIRE((size_t)words * 8 <= 96 * 1024, "ay2_nms_boxes: n = %d exceeds the scan kernel's shared-memory bit vector", n);
+  const long long total = (long long)n * words;
+  long long blocks = (total + 127) / 128;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  nms_boxes_mask_kernel<<<(int)blocks, 128, 0, st>>>(reinterpret_cast<const float4*>(boxes), order, n, iou_thres, mask_ws);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  if ((size_t)words * 8 > 48 * 1024)
+    AY2_CHECK_CUDA(cudaFuncSetAttribute(nms_boxes_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 8));
+  nms_boxes_scan_kernel<<<1, 256, words * 8, st>>>(mask_ws, order, n, keep, count);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}

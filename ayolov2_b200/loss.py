@@ -4,7 +4,7 @@ Same constructor contract (`ComputeLoss(model)` reads model.hyp and the YOLOHead
 stride, losses.py:171-221) and same call contract: `loss_fn(preds, targets) -> (loss * bs, cat(lbox, lobj, lcls,
 loss).detach())` with `preds` the list of (bs, na, ny, nx, 5+nc) head outputs and `targets` (nt, 6). The returned
 loss is differentiable w.r.t. `preds` (torch.autograd.Function whose backward is the analytic gradient kernel).
-Supported configuration = the reference default: fl_gamma == 0, autobalance off; others raise.
+Supported configuration: plain BCE (fl_gamma == 0, the reference default) or the FocalLoss wrapper (fl_gamma > 0); autobalance raises.
 """
 from __future__ import annotations
 
@@ -50,8 +50,6 @@ class ComputeLoss:
         if autobalance:
             raise NotImplementedError("autobalance is not implemented on the sm_100a loss path (reference default: off)")
         hyp: Dict[str, Any] = model.hyp  # type: ignore
-        if hyp.get("fl_gamma", 0.0) > 0:
-            raise NotImplementedError("focal loss (fl_gamma > 0) is not implemented on the sm_100a loss path")
         head = model.module.model[-1] if is_parallel(model) else model.model[-1]  # type: ignore
         self.hyp = hyp
         self.cp, self.cn = smooth_BCE(eps=hyp.get("label_smoothing", 0.0))
@@ -71,6 +69,7 @@ class ComputeLoss:
         h = self.hyp
         p.anchor_t, p.box, p.obj, p.cls = h["anchor_t"], h["box"], h["obj"], h["cls"]
         p.cls_pw, p.obj_pw, p.cp, p.cn = h["cls_pw"], h["obj_pw"], self.cp, self.cn
+        p.fl_gamma, p.fl_alpha = float(h.get("fl_gamma", 0.0)), 0.25  # FocalLoss(BCE, gamma) keeps its default alpha (losses.py:71,196)
         return p
 
     def _launch(self, preds, targets, grads, gscale) -> torch.Tensor:

@@ -61,8 +61,8 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
     """Run NMS on inference results (reference signature, metrics.py:285-295)."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
-    if nms_type != "nms":
-        raise NotImplementedError(f"nms_type={nms_type!r}: only the default 'nms' path runs on the B200 kernels")
+    if nms_type not in ("nms", "batched_nms", "fast_nms", "matrix_nms", "merge_nms"):
+        raise AssertionError("Wrong NMS type!!")  # metrics.py:433
     if labels:
         # metrics.py:340-346: a-priori labels are appended as rows with obj = 1 and a one-hot class
         nc = prediction.shape[2] - 5
@@ -75,6 +75,8 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
                     pad[xi, :len(lab), 4] = 1.0
                     pad[xi, range(len(lab)), lab[:, 0].long() + 5] = 1.0
             prediction = torch.cat((prediction, pad), 1)
+    if nms_type != "nms":
+        return _nms_other_types(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nms_type)
     ws = nms_device(prediction, conf_thres, iou_thres, agnostic=agnostic, multi_label=multi_label, max_det=max_det,
                     classes=classes)
     counts = ws.count.tolist()  # the one host sync
@@ -88,6 +90,92 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
         counts = ws.count.tolist()
     out = ws.out
     return [out[i, :c].clone() for i, c in enumerate(counts)]
+
+
+def nms_boxes(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float) -> torch.Tensor:
+    """torchvision.ops.nms(boxes, scores, iou_thres) on the ay2_nms_boxes kernels: kept indices in descending score order
+    (stable for ties), greedy suppression IoU > iou_thres. One host sync (the count)."""
+    from . import _lib
+
+    if not boxes.is_cuda:
+        raise RuntimeError("ayolov2_b200.nms.nms_boxes runs on CUDA tensors only (no CPU fallback)")
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.long, device=boxes.device)
+    b = boxes.float().contiguous()
+    order = torch.sort(scores.float(), descending=True, stable=True).indices.to(torch.int32)
+    mask = torch.empty((n * ((n + 63) // 64),), dtype=torch.int64, device=b.device)
+    keep = torch.empty((n,), dtype=torch.int32, device=b.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=b.device)
+    _lib.check(_lib.load().ay2_nms_boxes(b.data_ptr(), order.data_ptr(), n, float(iou_thres), mask.data_ptr(), keep.data_ptr(),
+                                         count.data_ptr(), _lib.current_stream_ptr()), "ay2_nms_boxes")
+    return keep[:int(count.item())].long()
+
+
+def _xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
+    """general.py:316-319 with the default ratio / wh / pad, same fp32 operation order."""
+    y = torch.empty_like(x)
+    hw, hh = x[:, 2] / 2, x[:, 3] / 2
+    y[:, 0], y[:, 1], y[:, 2], y[:, 3] = x[:, 0] - hw, x[:, 1] - hh, x[:, 0] + hw, x[:, 1] + hh
+    return y
+
+
+def _nms_other_types(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nms_type) -> list:
+    """The non-default nms_type branches of metrics.py:388-431 ("batched_nms", "fast_nms", "matrix_nms", "merge_nms"):
+    per image, candidate rows in the reference's order (metrics.py:337-379), then the branch's matrix arithmetic on the
+    CUDA IoU matrix (ay2_box_iou) / box-list NMS (ay2_nms_boxes). Device tensors throughout; these are diagnostic
+    variants in the reference (the validator and val.py use "nms"), so they are not batched across images."""
+    if not prediction.is_cuda:
+        raise RuntimeError("ayolov2_b200.nms runs on CUDA tensors only (no CPU fallback)")
+    pred = prediction.float()
+    nc = pred.shape[2] - 5
+    max_wh, max_nms = 4096.0, 30000  # metrics.py:326-327
+    multi_label = bool(multi_label) and nc > 1
+    out = [torch.zeros((0, 6), device=pred.device)] * pred.shape[0]
+    for xi in range(pred.shape[0]):
+        x = pred[xi]
+        x = x[x[:, 4] > conf_thres].clone()                                       # :313,337
+        if not x.shape[0]:
+            continue
+        x[:, 5:] *= x[:, 4:5]                                                     # :353
+        box = _xywh2xyxy(x[:, :4])                                                # :356
+        if multi_label:                                                           # :359-361
+            i, j = (x[:, 5:] > conf_thres).nonzero(as_tuple=False).T
+            x = torch.cat((box[i], x[i, j + 5, None], j[:, None].float()), 1)
+        else:                                                                     # :362-364
+            conf, j = x[:, 5:].max(1, keepdim=True)
+            x = torch.cat((box, conf, j.float()), 1)[conf.view(-1) > conf_thres]
+        if classes is not None:                                                   # :367-368
+            x = x[(x[:, 5:6] == torch.tensor(classes, device=x.device)).any(1)]
+        n = x.shape[0]
+        if not n:
+            continue
+        if n > max_nms:                                                           # :378-379
+            x = x[x[:, 4].argsort(descending=True)[:max_nms]]
+        if nms_type == "batched_nms":      # :391-394 (torchvision's coordinate trick: offset = class * (max coordinate + 1))
+            c = x[:, 5] * 0 if agnostic else x[:, 5]
+            boxes = x[:, :4] + (c * (x[:, :4].max() + 1))[:, None]
+            out[xi] = x[nms_boxes(boxes, x[:, 4], iou_thres)[:max_det]]
+        elif nms_type == "fast_nms":       # :397-401
+            c = x[:, 5] * 0 if agnostic else x[:, 5]
+            boxes = x[:, :4] + c.view(-1, 1) * max_wh
+            iou = box_iou(boxes, boxes).triu_(diagonal=1)
+            out[xi] = x[iou.max(0)[0] < iou_thres][:max_det]
+        elif nms_type == "matrix_nms":     # :404-413
+            iou = box_iou(x[:, :4], x[:, :4]).triu_(diagonal=1)
+            m = iou.max(0)[0].view(-1, 1)
+            x[:, 4] *= torch.exp(-(iou ** 2 - m ** 2) / 0.5).min(0)[0]
+            out[xi] = x[:max_det]
+        else:                              # merge_nms, :414-431
+            boxes, scores = x[:, :4] + x[:, 5:6] * (0 if agnostic else max_wh), x[:, 4]
+            i = nms_boxes(boxes, scores, iou_thres)[:max_det]
+            if 1 < n < 3e3:
+                hit = box_iou(boxes[i], boxes) > iou_thres
+                weights = hit * scores[None]
+                x[i, :4] = torch.mm(weights, x[:, :4]).float() / weights.sum(1, keepdim=True)
+                i = i[hit.sum(1) > 1]      # redundant = True (:326)
+            out[xi] = x[i]
+    return out
 
 
 def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:

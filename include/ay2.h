@@ -231,6 +231,13 @@ int ay2_nms_from_candidates(const ay2_head_levels* levels, const ay2_nms_params*
  * bit-identical to the reference expression on identical inputs. */
 int ay2_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float* out, void* stream);
 
+/* torchvision.ops.nms on a plain box list -- the call inside non_max_suppression (metrics.py:385) and its "batched_nms" /
+ * "merge_nms" nms_type branches (:391-431). boxes: fp32 [n][4] xyxy; order: indices by descending score (stable);
+ * mask_ws: n * ceil(n / 64) uint64 of scratch; keep: [n] kept ORIGINAL indices in score order; count: their number.
+ * Greedy suppression IoU > iou_thres with the reference's fp32 IoU and its comparison against the double threshold. */
+int ay2_nms_boxes(const float* boxes, const int32_t* order, int32_t n, double iou_thres, unsigned long long* mask_ws,
+                  int32_t* keep, int32_t* count, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Detection loss forward + analytic backward: replaces scripts/loss/losses.py:168-391 (ComputeLoss.__call__,
  * build_targets) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU) for the default configuration
@@ -251,6 +258,7 @@ typedef struct ay2_loss_params {
   float anchor_t, box, obj, cls;      /* hyp gains (res/configs/cfg/train_config.yaml:29-54) */
   float cls_pw, obj_pw;               /* BCE pos_weight */
   float cp, cn;                       /* smooth_BCE targets (losses.py:16-27) */
+  float fl_gamma, fl_alpha;           /* > 0: FocalLoss wrapper around both BCE criteria (losses.py:64-114,193-196; alpha 0.25) */
 } ay2_loss_params;
 size_t ay2_yolo_loss_workspace_bytes(const ay2_loss_params* p);
 int ay2_yolo_loss(const ay2_loss_params* p, const float* const* preds, float* const* grads, const float* targets,

@@ -1,7 +1,7 @@
 """CPU oracle for the detection loss. TEST INFRASTRUCTURE ONLY (see oracle/nms_oracle.py header).
 
 Restates scripts/loss/losses.py:168-391 (ComputeLoss.__call__ / build_targets, default configuration:
-fl_gamma = 0, autobalance off, gr = 1, sort_obj_iou off) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU
+fl_gamma >= 0 i.e. plain BCE or the FocalLoss wrapper, autobalance off, gr = 1, sort_obj_iou off) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU
 branch) in plain PyTorch so that autograd supplies the reference gradients. Pinned by tests/test_oracle_loss.py
 against tests/golden/loss_golden.npz (generated from the unmodified reference) and, in the build container,
 against the reference itself.
@@ -83,10 +83,23 @@ def build_targets(shapes: Sequence[Tuple[int, int]], targets: torch.Tensor, anch
     return out
 
 
+def bce_logits(x: torch.Tensor, t: torch.Tensor, pos_weight: torch.Tensor, gamma: float, alpha: float = 0.25) -> torch.Tensor:
+    """Mean BCEWithLogits(pos_weight); with gamma > 0 the FocalLoss wrapper of losses.py:64-114 (the criterion ComputeLoss
+    installs when hyp["fl_gamma"] > 0, :193-196): every element is scaled by alpha_t * (1 - p_t) ** gamma before the mean."""
+    if gamma <= 0:
+        return F.binary_cross_entropy_with_logits(x, t, pos_weight=pos_weight)
+    el = F.binary_cross_entropy_with_logits(x, t, pos_weight=pos_weight, reduction="none")
+    prob = torch.sigmoid(x)
+    p_t = t * prob + (1 - t) * (1 - prob)
+    alpha_t = t * alpha + (1 - t) * (1 - alpha)
+    return (el * alpha_t * (1.0 - p_t) ** gamma).mean()
+
+
 def compute_loss(preds: List[torch.Tensor], targets: torch.Tensor, anchors: torch.Tensor, hyp: Dict[str, float],
                  nc: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """losses.py:223-300. preds: list of (bs, na, ny, nx, 5+nc) logits (requires_grad for the backward oracle)."""
     cp, cn = smooth_bce(hyp.get("label_smoothing", 0.0))
+    gamma = float(hyp.get("fl_gamma", 0.0))
     balance = {3: [4.0, 1.0, 0.4]}.get(len(preds), [4.0, 1.0, 0.25, 0.06, 0.02])
     cls_pw = torch.tensor([hyp["cls_pw"]])
     obj_pw = torch.tensor([hyp["obj_pw"]])
@@ -106,8 +119,8 @@ def compute_loss(preds: List[torch.Tensor], targets: torch.Tensor, anchors: torc
             if nc > 1:
                 t = torch.full_like(ps[:, 5:], cn)
                 t[range(n), tcls] = cp
-                lcls = lcls + F.binary_cross_entropy_with_logits(ps[:, 5:], t, pos_weight=cls_pw)
-        lobj = lobj + F.binary_cross_entropy_with_logits(pi[..., 4], tobj, pos_weight=obj_pw) * balance[i]
+                lcls = lcls + bce_logits(ps[:, 5:], t, cls_pw, gamma)
+        lobj = lobj + bce_logits(pi[..., 4], tobj, obj_pw, gamma) * balance[i]
     lbox = lbox * hyp["box"]
     lobj = lobj * hyp["obj"]
     lcls = lcls * hyp["cls"]

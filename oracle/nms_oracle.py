@@ -4,7 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 module; the product path (ayolov2_b200/) never does.
 
 A plain numpy/torch-CPU restatement of
-  * scripts/utils/metrics.py:285-443   non_max_suppression (nms_type "nms" and "batched_nms")
+  * scripts/utils/metrics.py:285-443   non_max_suppression (every nms_type: "nms", "batched_nms", "fast_nms",
+                                       "matrix_nms", "merge_nms")
+  * scripts/utils/metrics.py:138-164   box_iou
   * scripts/utils/general.py:297-321   xywh2xyxy
   * scripts/utils/nms.py:15-116        batched_nms (val2 path, nms_type "nms")
   * torchvision.ops.nms (torchvision 0.10.1 pinned by environment.yml:28; 0.26 behaves the same): stable
@@ -72,10 +74,22 @@ def greedy_nms(boxes: np.ndarray, scores: np.ndarray, iou_thres: float, limit: O
     return np.asarray(keep, dtype=np.int64)
 
 
+def box_iou(box1: np.ndarray, box2: np.ndarray) -> np.ndarray:
+    """metrics.py:138-164: (N, M) IoU of xyxy boxes, fp32, inter / (area1 + area2 - inter) (0/0 -> nan like the reference)."""
+    b1, b2 = box1.astype(np.float32, copy=False), box2.astype(np.float32, copy=False)
+    a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    wh = np.minimum(b1[:, None, 2:], b2[None, :, 2:]) - np.maximum(b1[:, None, :2], b2[None, :, :2])
+    wh = np.maximum(wh, np.float32(0))
+    inter = wh[..., 0] * wh[..., 1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (inter / (a1[:, None] + a2[None, :] - inter)).astype(np.float32)
+
+
 def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_thres: float = 0.45,
                         classes: Optional[Sequence[int]] = None, agnostic: bool = False, multi_label: bool = False,
                         max_det: int = 300, nms_type: str = "nms") -> List[torch.Tensor]:
-    """metrics.py:285-443 restated (nms_type "nms" / "batched_nms"); prediction fp32 [B, n, 5+nc] on CPU."""
+    """metrics.py:285-443 restated (all five nms_type values); prediction fp32 [B, n, 5+nc] on CPU."""
     pred = prediction.detach().cpu().float().numpy()
     nc = pred.shape[2] - 5
     max_wh = np.float32(4096)  # metrics.py:326
@@ -113,6 +127,33 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
             cls = x[:, 5] * 0 if agnostic else x[:, 5]
             max_coord = x[:, :4].max()
             boxes = x[:, :4] + (cls * (max_coord + np.float32(1)))[:, None]
+        elif nms_type == "fast_nms":  # :397-401 (yolact): a box survives when no EARLIER row overlaps it (rows keep x's order)
+            cls = x[:, 5] * 0 if agnostic else x[:, 5]
+            boxes = x[:, :4] + cls[:, None] * max_wh
+            iou = np.triu(box_iou(boxes, boxes), k=1)
+            keep = np.nonzero(iou.max(0) < np.float32(iou_thres))[0]
+            out.append(torch.from_numpy(x[keep][:max_det].astype(np.float32)))
+            continue
+        elif nms_type == "matrix_nms":  # :404-413: gaussian score decay (sigma 0.5), nothing is removed, scores change in place
+            iou = np.triu(box_iou(x[:, :4], x[:, :4]), k=1)
+            m = iou.max(0)[:, None]
+            decay = torch.exp(torch.from_numpy(-(iou ** 2 - m ** 2) / np.float32(0.5))).numpy().min(0)
+            x = x.copy()
+            x[:, 4] *= decay
+            out.append(torch.from_numpy(x[:max_det].astype(np.float32)))
+            continue
+        elif nms_type == "merge_nms":  # :414-431: greedy NMS, then every kept box <- score-weighted mean of its overlaps
+            c = x[:, 5:6] * (np.float32(0) if agnostic else max_wh)
+            boxes = (x[:, :4] + c).astype(np.float32)
+            keep = greedy_nms(boxes, x[:, 4], iou_thres)[:max_det]
+            if 1 < n < 3e3:
+                hit = box_iou(boxes[keep], boxes) > np.float32(iou_thres)
+                weights = hit * x[None, :, 4]
+                x = x.copy()
+                x[keep, :4] = (weights @ x[:, :4]).astype(np.float32) / weights.sum(1, keepdims=True)
+                keep = keep[hit.sum(1) > 1]  # redundant=True (:326): require at least one other overlapping box
+            out.append(torch.from_numpy(x[keep].astype(np.float32)))
+            continue
         else:
             raise NotImplementedError(nms_type)
         keep = greedy_nms(boxes.astype(np.float32), x[:, 4], iou_thres, limit=max_det)

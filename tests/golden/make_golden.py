@@ -25,6 +25,11 @@ NMS_SETTINGS = [
     dict(conf_thres=0.1, iou_thres=0.65, agnostic=True),
     dict(conf_thres=0.25, iou_thres=0.45, classes=[1, 3]),
     dict(conf_thres=0.25, iou_thres=0.45, max_det=10),
+    # non-default nms_type values (metrics.py:388-431); index selection exact, merged boxes / decayed scores to fp32 rounding
+    dict(conf_thres=0.05, iou_thres=0.6, nms_type="batched_nms"),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="fast_nms"),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="matrix_nms"),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="merge_nms", multi_label=True),
 ]
 
 
@@ -75,7 +80,8 @@ def loss_inputs(seed=0, bs=3, nc=6, img=128, nt=14):
 
 def make_loss(ref):
     out = {}
-    for case, (hyp_over, nt) in enumerate([({}, 14), ({"label_smoothing": 0.1, "cls_pw": 0.7, "obj_pw": 1.3}, 9), ({}, 0)]):
+    for case, (hyp_over, nt) in enumerate([({}, 14), ({"label_smoothing": 0.1, "cls_pw": 0.7, "obj_pw": 1.3}, 9), ({}, 0),
+                                            ({"fl_gamma": 1.5, "label_smoothing": 0.05, "obj_pw": 1.2}, 11)]):
         hyp = dict(HYP, **hyp_over)
         nc = 6
         preds, targets = loss_inputs(seed=case, nc=nc, nt=nt)

@@ -50,7 +50,7 @@ def _check(preds_cpu, targets, hyp, nc, scale=1.0):
     return l_gpu, it_gpu
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_loss_golden(case):
     z = np.load(GOLD)
     hyp = dict(zip(HYP_KEYS, z[f"c{case}_hyp"].tolist()))
@@ -74,6 +74,22 @@ def test_loss_random(seed, bs, nt, scale):
     t[:, 4:6] = torch.exp(np.log(0.02) + (np.log(0.8) - np.log(0.02)) * torch.rand(nt, 2, generator=g))
     hyp = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
     _check(preds, t, hyp, nc, scale)
+
+
+@pytest.mark.parametrize("gamma", [1.5, 2.0])
+def test_loss_focal(gamma):
+    """hyp["fl_gamma"] > 0: both BCE criteria become FocalLoss(BCE, gamma) (losses.py:193-196); forward and gradient vs the
+    pinned oracle, same tolerances as the plain path."""
+    g = torch.Generator().manual_seed(11)
+    nc, bs, nt = 80, 4, 50
+    preds = [torch.randn(bs, 3, 160 // s, 160 // s, nc + 5, generator=g) * 2 for s in (8, 16, 32)]
+    t = torch.zeros(nt, 6)
+    t[:, 0] = torch.randint(0, bs, (nt,), generator=g).float()
+    t[:, 1] = torch.randint(0, nc, (nt,), generator=g).float()
+    t[:, 2:4] = 0.05 + 0.9 * torch.rand(nt, 2, generator=g)
+    t[:, 4:6] = torch.exp(np.log(0.03) + (np.log(0.7) - np.log(0.03)) * torch.rand(nt, 2, generator=g))
+    hyp = dict(box=0.05, cls=0.5, cls_pw=0.9, obj=1.0, obj_pw=1.1, anchor_t=4.0, fl_gamma=gamma, label_smoothing=0.05)
+    _check(preds, t, hyp, nc)
 
 
 def test_loss_duplicate_cells_last_wins():

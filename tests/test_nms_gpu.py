@@ -138,3 +138,50 @@ def test_box_iou_bit_exact():
     got = box_iou(b1.cuda(), b2.cuda()).cpu()
     assert torch.equal(got, want)
     assert box_iou(b1[:0].cuda(), b2.cuda()).shape == (0, 1025)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(conf_thres=0.05, iou_thres=0.6, nms_type="batched_nms"),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="batched_nms", agnostic=True, multi_label=True),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="fast_nms"),
+    dict(conf_thres=0.3, iou_thres=0.5, nms_type="fast_nms", agnostic=True, multi_label=True),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="matrix_nms"),
+    dict(conf_thres=0.25, iou_thres=0.45, nms_type="merge_nms"),
+    dict(conf_thres=0.25, iou_thres=0.6, nms_type="merge_nms", multi_label=True, max_det=20),
+], ids=["batched", "batched-agnostic-ml", "fast", "fast-agnostic-ml", "matrix", "merge", "merge-ml"])
+def test_other_nms_types(kw):
+    """metrics.py:388-431: index selection (which rows, which order, which class) identical to the pinned oracle; the
+    decayed scores (exp) and merged boxes (mm) within fp32 rounding, tolerance 1e-5 relative / 1e-4 absolute pixels."""
+    from ayolov2_b200.nms import non_max_suppression
+    from oracle import nms_oracle
+
+    pred = nms_oracle.synth_predictions(2, n=2500, seed=7)
+    pred[1, :, 4] *= 0.5
+    want = nms_oracle.non_max_suppression(pred, **kw)
+    got = non_max_suppression(pred.cuda(), **kw)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and w.shape[0] > 0
+        assert torch.equal(g[:, 5].cpu(), w[:, 5])
+        if kw["nms_type"] in ("batched_nms", "fast_nms"):
+            assert torch.equal(g.cpu(), w)
+        else:
+            assert torch.allclose(g.cpu(), w, rtol=1e-5, atol=1e-4)
+
+
+def test_nms_boxes_matches_torchvision_semantics():
+    """ay2_nms_boxes == the oracle's greedy_nms (torchvision.ops.nms restatement) on clustered boxes incl. exact ties."""
+    from ayolov2_b200.nms import nms_boxes
+    from oracle import nms_oracle
+
+    g = torch.Generator().manual_seed(3)
+    c = torch.rand(40, 2, generator=g) * 600
+    xy = c[torch.randint(0, 40, (3000,), generator=g)] + torch.randn(3000, 2, generator=g) * 6
+    wh = torch.rand(3000, 2, generator=g) * 80 + 8
+    boxes = torch.cat((xy - wh / 2, xy + wh / 2), 1)
+    scores = torch.rand(3000, generator=g)
+    scores[100:120] = scores[100]  # ties keep their original order (stable sort)
+    for thr in (0.3, 0.45, 0.7):
+        want = nms_oracle.greedy_nms(boxes.numpy(), scores.numpy(), thr)
+        got = nms_boxes(boxes.cuda(), scores.cuda(), thr).cpu().numpy()
+        assert (want == got).all() and len(want) == len(got)
+    assert nms_boxes(boxes[:0].cuda(), scores[:0].cuda(), 0.5).numel() == 0
