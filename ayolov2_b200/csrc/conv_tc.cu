@@ -72,7 +72,7 @@ struct ConvCfg {
   static constexpr int SLAB_BYTES = 128 * SWO;
   static constexpr int NSLAB = BLOCK_N / OC;
   static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2;
-  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256;  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr
+  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256 + 1024;  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr + head-candidate list
   // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
   // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
   static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
@@ -121,59 +121,129 @@ __device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok,
   }
 }
 
+constexpr int kHeadDenseMax = 48;  // (pixel, anchor) pairs per tile (of 384) up to which the warp-per-entry walk wins
+
+// Two phases per tile. (1) Every epilogue thread owns one pixel and tests the objectness of its group's anchors; passing
+// (pixel, anchor) pairs are appended to a small shared-memory list (warp-aggregated). (2) After a barrier the warps walk
+// that DENSE list: one entry per warp at a time, the 32 lanes split the classes and reduce to the first arg-max -- with
+// sparse candidates (a few % of the rows) this is ~10x less issue work than looping the classes for whole warps of
+// mostly failing pixels. Tiles with more than kHeadDenseMax passing pairs fall back to one thread per pixel.
 template <class Cfg>
 __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
-                                                int lane) {
+                                                int lane, int ewarp_all, unsigned short* list, int* cnt) {
   const HeadCandParams& h = p.hc;
   const int box_rows = p.BH * p.BW;
-  const int j = et / box_rows, rr = et - j * box_rows;
-  const int q = m * p.NB + j;
-  const int b = q / p.boxes_per_img;
-  const int r = q - b * p.boxes_per_img;
-  const int py = r / p.boxes_x;
-  const int ry = rr / p.BW;
-  const int oy = py * p.BH + ry, ox = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
-  const bool inside = b < h.batch && oy < h.out_h && ox < h.out_w;
   const int plane = h.out_h * h.out_w;
   const int nc = h.no - 5;
-  auto logit = [&](int ch) -> float {  // channel ch of this thread's pixel in the swizzled staging slabs
+  auto locate = [&](int px, int& b, int& oy, int& ox) -> bool {  // pixel `px` of tile m -> image, row, column
+    const int j = px / box_rows, rr = px - j * box_rows;
+    const int q = m * p.NB + j;
+    b = q / p.boxes_per_img;
+    const int r = q - b * p.boxes_per_img;
+    const int py = r / p.boxes_x;
+    const int ry = rr / p.BW;
+    oy = py * p.BH + ry;
+    ox = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
+    return b < h.batch && oy < h.out_h && ox < h.out_w;
+  };
+  auto logit = [&](int px, int ch) -> float {  // channel ch of pixel px in the swizzled staging slabs
     const uint8_t* slab = staging + (ch / Cfg::OC) * Cfg::SLAB_BYTES;
     const int cc = ch % Cfg::OC;
-    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(et, cc >> 3) + (cc & 7) * 2));
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(px, cc >> 3) + (cc & 7) * 2));
   };
+  // ---- phase 1: objectness test, dense list of passing (pixel, anchor) pairs
+  int b0, oy0, ox0;
+  const bool inside = locate(et, b0, oy0, ox0);
+  unsigned pass_bits = 0;  // bit a: this thread's pixel passes for anchor a (only this group's anchors)
   for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
-    const int c0 = a * h.no;
-    float obj = 0.0f;
-    bool pass = false;
-    if (inside) {
-      obj = head_sigmoid(logit(c0 + 4));
-      pass = obj > h.conf_thres;
+    const bool pass = inside && head_sigmoid(logit(et, a * h.no + 4)) > h.conf_thres;
+    pass_bits |= pass ? 1u << a : 0u;
+    const unsigned mk = __ballot_sync(0xffffffffu, pass);
+    if (mk) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(cnt, __popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) list[base + __popc(mk & ((1u << lane) - 1u))] = static_cast<unsigned short>(et | (a << 8));
     }
-    if (!__ballot_sync(0xffffffffu, pass)) continue;  // warp-uniform
+  }
+  named_bar_sync(1, Cfg::EPI_THREADS);
+  const int n = *reinterpret_cast<volatile int*>(cnt);
+  if (n > kHeadDenseMax) {
+    // dense tile (synthetic / untrained heads): most warps have passing pixels, so every thread scores its own pixel
+    for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
+      const bool pass = (pass_bits >> a) & 1u;
+      if (!__ballot_sync(0xffffffffu, pass)) continue;  // warp-uniform
+      const int c0 = a * h.no;
+      const float obj = pass ? head_sigmoid(logit(et, c0 + 4)) : 0.0f;
+      const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy0 * h.out_w + ox0);
+      if (h.multi_label) {
+        for (int c = 0; c < nc; ++c) {
+          float conf = 0.0f;
+          bool ok = false;
+          if (pass) {
+            conf = __fmul_rn(head_sigmoid(logit(et, c0 + 5 + c)), obj);
+            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
+          }
+          head_cand_push(h, ok, b0, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
+        }
+      } else {
+        float best = -INFINITY;
+        int bidx = 0;
+        if (pass) {
+          for (int c = 0; c < nc; ++c) {  // first arg-max: strict > keeps the lowest index among equal scores
+            const float conf = __fmul_rn(head_sigmoid(logit(et, c0 + 5 + c)), obj);
+            if (conf > best) {
+              best = conf;
+              bidx = c;
+            }
+          }
+        }
+        const bool ok = pass && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+        head_cand_push(h, ok, b0, (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx), lane);
+      }
+    }
+    return;
+  }
+  // ---- phase 2: one list entry per warp, classes over lanes
+  for (int e = ewarp_all; e < n; e += Cfg::EPI_THREADS / 32) {
+    const int ent = list[e];
+    const int px = ent & 0xff, a = ent >> 8;
+    int b, oy, ox;
+    locate(px, b, oy, ox);
+    const int c0 = a * h.no;
+    const float obj = head_sigmoid(logit(px, c0 + 4));
     const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy * h.out_w + ox);
     if (h.multi_label) {
-      for (int c = 0; c < nc; ++c) {
+      for (int cb = 0; cb < nc; cb += 32) {  // every class above conf (metrics.py:360-361)
+        const int c = cb + lane;
         float conf = 0.0f;
         bool ok = false;
-        if (pass) {
-          conf = __fmul_rn(head_sigmoid(logit(c0 + 5 + c)), obj);
+        if (c < nc) {
+          conf = __fmul_rn(head_sigmoid(logit(px, c0 + 5 + c)), obj);
           ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
         }
         head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
       }
     } else {
       float best = -INFINITY;
-      int bidx = 0;
-      if (pass) {
-        for (int c = 0; c < nc; ++c) {  // first arg-max: strict > keeps the lowest index among equal scores
-          const float conf = __fmul_rn(head_sigmoid(logit(c0 + 5 + c)), obj);
-          if (conf > best) {
-            best = conf;
-            bidx = c;
-          }
+      int bidx = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {  // ascending per lane: strict > keeps the lowest index among equal scores
+        const float conf = __fmul_rn(head_sigmoid(logit(px, c0 + 5 + c)), obj);
+        if (conf > best) {
+          best = conf;
+          bidx = c;
         }
       }
-      const bool ok = pass && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {  // first arg-max over the warp (metrics.py:363-364): larger score, then lower class
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) {
+          best = ob;
+          bidx = oi;
+        }
+      }
+      const bool ok = lane == 0 && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
       head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx), lane);
     }
   }
@@ -249,6 +319,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint64_t* res_full = tmem_empty + 2;            // [EPI_GROUPS <= 4]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 4);
+  int* cand_cnt = reinterpret_cast<int*>(tmem_ptr_s + 2);                               // [2], one per tile parity
+  unsigned short* cand_list = reinterpret_cast<unsigned short*>(bars) + 128;           // 256 B past the barriers: 128 x 3 entries
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -257,6 +329,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   if (threadIdx.x == 0) {
     CV_DBG(0);  // CTA entry
     if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 9] = clock64();
+    cand_cnt[0] = cand_cnt[1] = 0;
     for (int i = 0; i < Cfg::NSTAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], p.csize);  // every CTA sharing the multicast B tile must release the stage
@@ -465,7 +538,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
         // detect head: score NMS candidates from the whole staged tile (all slabs) while the TMA stores drain it (both
         // only read); no group may start rewriting its slab before every group has finished reading
         named_bar_sync(1, Cfg::EPI_THREADS);
-        head_candidates<Cfg>(p, staging, m, et, egrp, lane);
+        if (eall == 0) cand_cnt[(it + 1) & 1] = 0;  // the other counter was last read before the barrier above
+        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall >> 5, cand_list, &cand_cnt[it & 1]);
         named_bar_sync(1, Cfg::EPI_THREADS);
       }
     }

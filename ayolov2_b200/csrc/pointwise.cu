@@ -136,19 +136,21 @@ __global__ void sppf_pool_kernel(const __nv_bfloat16* __restrict__ in, int H, in
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, int B, int H, int W, int C, int ics,
                                   __nv_bfloat16* __restrict__ out, int ocs) {
-  const int chunks = C >> 3;
-  const int OW = W * 2, OH = H * 2;
-  const long long total = (long long)B * OH * OW * chunks;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % chunks) << 3;
-    long long pix = idx / chunks;
-    const int ox = (int)(pix % OW);
-    const int oy = (int)((pix / OW) % OH);
-    const int b = (int)(pix / ((long long)OW * OH));
-    const uint4 v =
-        *reinterpret_cast<const uint4*>(in + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * ics + c);
-    *reinterpret_cast<uint4*>(out + pix * ocs + c) = v;
+  // one thread per 16-byte chunk of an INPUT pixel: one load, four stores (the 2x2 output pixels), 32-bit index math
+  const unsigned chunks = C >> 3;
+  const unsigned total = (unsigned)B * H * W * chunks;  // < 2^31 for every supported shape (checked by the launcher)
+  const unsigned OW = W * 2;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned c = (idx % chunks) << 3;
+    const unsigned pix = idx / chunks;          // (b * H + y) * W + x
+    const unsigned x = pix % W;
+    const unsigned row = pix / W;               // b * H + y
+    const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)pix * ics + c);
+    __nv_bfloat16* o = out + ((size_t)(2 * row) * OW + 2 * x) * ocs + c;  // output row 2 * (b * H + y) == b * 2H + 2y
+    *reinterpret_cast<uint4*>(o) = v;
+    *reinterpret_cast<uint4*>(o + ocs) = v;
+    *reinterpret_cast<uint4*>(o + (size_t)OW * ocs) = v;
+    *reinterpret_cast<uint4*>(o + (size_t)OW * ocs + ocs) = v;
   }
 }
 
@@ -279,7 +281,8 @@ extern "C" int ay2_upsample2x(const void* in, int32_t batch, int32_t h, int32_t 
                               void* out, int32_t out_cstride, void* stream) {
   AY2_REQUIRE(in && out, "ay2_upsample2x: null pointer");
   AY2_REQUIRE(c % 8 == 0 && in_cstride % 8 == 0 && out_cstride % 8 == 0, "upsample2x channels must be multiples of 8");
-  const long long total = (long long)batch * h * 2 * w * 2 * (c / 8);
+  const long long total = (long long)batch * h * w * (c / 8);
+  AY2_REQUIRE(total < (1ll << 31), "upsample2x: tensor too large for 32-bit indexing");
   const int threads = 256;
   upsample2x_kernel<<<grid_for(total, threads, 16), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), batch, h, w, c, in_cstride, static_cast<__nv_bfloat16*>(out), out_cstride);
