@@ -16,7 +16,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libay2.so"
 STAMP_PATH = PKG_DIR / "csrc" / ".build_stamp"
 
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "train_pointwise.cu", "nms.cu", "loss.cu"]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "train_pointwise.cu", "nms.cu", "loss.cu", "val_match.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

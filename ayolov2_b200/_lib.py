@@ -147,6 +147,8 @@ _PROTOS = {
     "ay2_conv_plan_set_head_candidates": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_int32, C.c_int32, C.c_void_p,
                                                     C.c_void_p, C.c_size_t]),
     "ay2_box_iou": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ay2_match_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ay2_nms_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_nms_candidates_begin": (C.c_int, [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ay2_nms_from_candidates": (C.c_int, [C.POINTER(HeadLevels), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,

@@ -238,6 +238,17 @@ int ay2_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, floa
 int ay2_nms_boxes(const float* boxes, const int32_t* order, int32_t n, double iou_thres, unsigned long long* mask_ws,
                   int32_t* keep, int32_t* count, void* stream);
 
+/* Validation statistics: replaces the per-image host loop of YoloValidator.statistics_per_image / process_batch
+ * (scripts/utils/train_utils.py:294-401) for a whole batch. det / counts: the NMS output ([batch][max_det][6], [batch]);
+ * labels: fp32 [nt][6] = image, class, box; meta == NULL: boxes are xyxy in the detections' coordinates (the plain
+ * process_batch contract); meta = fp32 [batch][5] {gain, pad_x, pad_y, native_w, native_h}: label boxes are xywh pixels of
+ * the network input and both sides are mapped to the native image first (xywh2xyxy + scale_coords + clip_coords,
+ * scripts/utils/general.py:203-230,316-358). labels_cap: upper bound of labels per image (shared-memory sizing).
+ * correct: uint8 [batch][max_det][niou], 1 where the detection is matched with IoU >= iouv[k]. */
+int ay2_match_detections(const float* det, const int32_t* counts, int32_t batch, int32_t max_det, const float* labels,
+                         int32_t nt, int32_t labels_cap, const float* meta, const float* iouv, int32_t niou,
+                         uint8_t* correct, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Detection loss forward + analytic backward: replaces scripts/loss/losses.py:168-391 (ComputeLoss.__call__,
  * build_targets) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU) for the default configuration
