@@ -134,6 +134,9 @@ class ConvPlan:
         self._h = h
         self._lib = lib
         self.flops = float(lib.ay2_conv_plan_flops(h))
+        info = (C.c_int32 * 4)()
+        lib.ay2_conv_plan_set_debug(h, None, info)
+        self.halo = info[2] < 0  # 3x3 / s1 halo kernel (conv_halo_kernel) instead of conv_tc_kernel
 
     def run(self, stream: Optional[int] = None) -> None:
         _lib.check(self._lib.ay2_conv_plan_run(self._h, stream if stream is not None else _lib.current_stream_ptr()),
