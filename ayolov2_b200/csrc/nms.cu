@@ -713,7 +713,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       if (lane >= o) incl += v;
     }
     if (lane == 31) s_scan[wid] = incl;
+    AY2_NMS_MARK(14);
     __syncthreads();
+    AY2_NMS_MARK(15);
     if (wid == 0) {
       int v = lane < nwarp ? s_scan[lane] : 0;
 #pragma unroll
@@ -725,6 +727,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     }
     __syncthreads();
     int k = incl - cnt + (wid > 0 ? s_scan[wid - 1] : 0);
+    AY2_NMS_MARK(12);
     for (int i = i0; i < i1 && k < p.max_det; ++i) {
       if (ssupp[i]) continue;
       const unsigned long long key = sorted[i];
@@ -739,6 +742,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       o[5] = static_cast<float>(idx % nc);
       ++k;
     }
+    AY2_NMS_MARK(13);
     __syncthreads();
     if (tid == 0) out_count[b] = min(s_scan[nwarp - 1], p.max_det);
     AY2_NMS_MARK(7);
@@ -969,8 +973,9 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
       AY2_CHECK_CUDA(cudaStreamSynchronize(st));
       AY2_CHECK_CUDA(cudaMemcpy(h, trace, sizeof(h), cudaMemcpyDeviceToHost));
       fprintf(stderr, "[ay2 nms trace] img0 n=%lld segments %lld one-block + %lld longer, %lld blocks | clocks: sort %lld, boxes %lld, "
-              "class order %lld, offset boxes %lld, in-block tests %lld, resolve %lld, emit %lld\n", h[8], h[9], h[10], h[11],
-              h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6]);
+              "class order %lld, offset boxes %lld, in-block tests %lld, resolve %lld, emit %lld (scan %lld = count %lld + barrier %lld + rest, write %lld, tail %lld)\n",
+              h[8], h[9], h[10], h[11], h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6],
+              h[12] - h[6], h[14] - h[6], h[15] - h[14], h[13] - h[12], h[7] - h[13]);
     }
   }
   if (overflow_flag) AY2_CHECK_CUDA(cudaMemcpyAsync(overflow_flag, v.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));

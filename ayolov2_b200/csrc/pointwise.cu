@@ -73,58 +73,60 @@ __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
   return r;
 }
 
+// CPC: 16-byte channel chunks per CTA. With 2, neighbouring threads read / write the two halves of a 32-byte sector, so
+// every DRAM sector the strided NHWC plane touches is used whole (with 1 half of each sector was wasted both ways).
+template <int CPC>
 __global__ void sppf_pool_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int cstride, int r1,
                                  int r2, int r3, __nv_bfloat16* __restrict__ o1, __nv_bfloat16* __restrict__ o2,
                                  __nv_bfloat16* __restrict__ o3) {
   extern __shared__ uint4 sp[];
-  const int chunks = C >> 3;
-  const int b = blockIdx.x / chunks;
-  const int ch = (blockIdx.x - b * chunks) << 3;
-  const int HW = H * W;
-  uint4* X = sp;           // [H][W]
-  uint4* R1 = X + HW;      // row-max with radius r1
-  uint4* R2 = R1 + HW;
-  uint4* R3 = R2 + HW;
+  const int groups = C / (8 * CPC);
+  const int b = blockIdx.x / groups;
+  const int ch = (blockIdx.x - b * groups) * 8 * CPC;
+  const int HW = H * W, N = HW * CPC;
+  uint4* X = sp;          // [H][W][CPC]
+  uint4* R1 = X + N;      // row-max with radius r1
+  uint4* R2 = R1 + N;
+  uint4* R3 = R2 + N;
   const uint32_t ninf2 = 0xFF80FF80u;  // bf16 -inf pair
   const uint4 NINF = make_uint4(ninf2, ninf2, ninf2, ninf2);
   const long long base = (long long)b * HW * cstride + ch;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x)
-    X[i] = *reinterpret_cast<const uint4*>(in + base + (long long)i * cstride);
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    X[i] = *reinterpret_cast<const uint4*>(in + base + (long long)(i / CPC) * cstride + (i % CPC) * 8);
   __syncthreads();
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int y = i / W, x = i - y * W;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int x = (i / CPC) % W;
     uint4 m = X[i];
     int d = 1;
     for (; d <= r1; ++d) {
-      if (x - d >= 0) m = bf16x8_max(m, X[i - d]);
-      if (x + d < W) m = bf16x8_max(m, X[i + d]);
+      if (x - d >= 0) m = bf16x8_max(m, X[i - d * CPC]);
+      if (x + d < W) m = bf16x8_max(m, X[i + d * CPC]);
     }
     R1[i] = m;
     for (; d <= r2; ++d) {
-      if (x - d >= 0) m = bf16x8_max(m, X[i - d]);
-      if (x + d < W) m = bf16x8_max(m, X[i + d]);
+      if (x - d >= 0) m = bf16x8_max(m, X[i - d * CPC]);
+      if (x + d < W) m = bf16x8_max(m, X[i + d * CPC]);
     }
     R2[i] = m;
     for (; d <= r3; ++d) {
-      if (x - d >= 0) m = bf16x8_max(m, X[i - d]);
-      if (x + d < W) m = bf16x8_max(m, X[i + d]);
+      if (x - d >= 0) m = bf16x8_max(m, X[i - d * CPC]);
+      if (x + d < W) m = bf16x8_max(m, X[i + d * CPC]);
     }
     R3[i] = m;
-    (void)y;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const int y = i / W;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const int y = (i / CPC) / W;
     uint4 m1 = NINF, m2 = NINF, m3 = NINF;
     for (int d = -r3; d <= r3; ++d) {
       const int yy = y + d;
       if (yy < 0 || yy >= H) continue;
-      const int j = i + d * W;
+      const int j = i + d * W * CPC;
       m3 = bf16x8_max(m3, R3[j]);
       if (d >= -r2 && d <= r2) m2 = bf16x8_max(m2, R2[j]);
       if (d >= -r1 && d <= r1) m1 = bf16x8_max(m1, R1[j]);
     }
-    const long long o = base + (long long)i * cstride;
+    const long long o = base + (long long)(i / CPC) * cstride + (i % CPC) * 8;
     *reinterpret_cast<uint4*>(o1 + o) = m1;
     *reinterpret_cast<uint4*>(o2 + o) = m2;
     *reinterpret_cast<uint4*>(o3 + o) = m3;
@@ -261,15 +263,19 @@ extern "C" int ay2_sppf_pool(const void* in, int32_t batch, int32_t h, int32_t w
   AY2_REQUIRE(c % 8 == 0 && cstride % 8 == 0, "sppf_pool channels must be multiples of 8");
   AY2_REQUIRE(k1 % 2 == 1 && k2 % 2 == 1 && k3 % 2 == 1 && k1 <= k2 && k2 <= k3, "sppf_pool windows %d,%d,%d invalid",
               k1, k2, k3);
-  const size_t smem = (size_t)4 * h * w * sizeof(uint4);
+  const int cpc = (c % 16 == 0 && (size_t)8 * h * w * sizeof(uint4) <= 100 * 1024) ? 2 : 1;
+  const size_t smem = (size_t)4 * cpc * h * w * sizeof(uint4);
   AY2_REQUIRE(smem <= 200 * 1024, "sppf_pool plane %dx%d too large for shared memory", h, w);
   static bool attr_set = false;
   if (!attr_set) {
-    AY2_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AY2_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AY2_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const int threads = h * w >= 512 ? 512 : ((h * w + 31) / 32) * 32;
-  sppf_pool_kernel<<<batch * (c / 8), threads, smem, static_cast<cudaStream_t>(stream)>>>(
+  const int n = h * w * cpc;
+  const int threads = n >= 512 ? 512 : ((n + 31) / 32) * 32;
+  auto kern = cpc == 2 ? sppf_pool_kernel<2> : sppf_pool_kernel<1>;
+  kern<<<batch * (c / (8 * cpc)), threads, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), h, w, c, cstride, k1 / 2, k2 / 2, k3 / 2,
       static_cast<__nv_bfloat16*>(out1), static_cast<__nv_bfloat16*>(out2), static_cast<__nv_bfloat16*>(out3));
   AY2_CHECK_LAUNCH();
