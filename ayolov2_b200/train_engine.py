@@ -71,7 +71,17 @@ class TrainEngine:
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.static_in = torch.zeros((batch, 3, height, width), dtype=torch.float32, device=self.device)
         self._build()
-        self.pg: Dict[int, torch.Tensor] = {id(p): torch.zeros_like(p, dtype=torch.float32) for p in model.parameters()}
+        # parameter gradients: views (in model.parameters() order) of ONE flat fp32 buffer, so that a step zeroes, copies,
+        # all-reduces and applies them with a handful of launches instead of one per parameter
+        params = list(model.parameters())
+        self.pg_offsets: List[int] = []
+        off = 0
+        for p in params:
+            self.pg_offsets.append(off)
+            off += _round_up(p.numel(), 4)  # 16-byte aligned slices
+        self.pg_flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.pg: Dict[int, torch.Tensor] = {id(p): self.pg_flat[o:o + p.numel()].view(p.shape) for p, o in zip(params, self.pg_offsets)}
+        self.last_grad_flat: Optional[torch.Tensor] = None  # the flat gradient of the latest backward (same layout)
 
     # ------------------------------------------------------------------------------------------------ buffers
     def new_act(self, H: int, W: int, C_: int) -> ActView:
@@ -462,8 +472,7 @@ class TrainEngine:
         for key, gb in self.grad_of.items():
             if key not in self.overwritten:  # pre-BN gradients are written whole by bn_act_bwd, never accumulated
                 gb.zero_()
-        for t in self.pg.values():
-            t.zero_()
+        self.pg_flat.zero_()
         for b in reversed(self.bwd):
             b()
 
@@ -477,7 +486,9 @@ class TrainEngine:
         for gin, g_ in zip(self.head_gin, grads):
             gin.copy_(g_)
         self._run_or_replay("bwd", self._backward_body)
-        return {k: v.clone() for k, v in self.pg.items()}
+        flat = self.pg_flat.clone()  # one copy out of the graph's static buffer; the per-parameter gradients are views of it
+        self.last_grad_flat = flat
+        return {k: flat[v.storage_offset():v.storage_offset() + v.numel()].view(v.shape) for k, v in self.pg.items()}
 
 
 class TrainFunction(torch.autograd.Function):

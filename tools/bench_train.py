@@ -60,14 +60,25 @@ def main() -> None:
     model.hyp = dict(HYP)
     loss_fn = ComputeLoss(model)
     params = [p for p in model.parameters()]
-    mom = [torch.zeros_like(p) for p in params]
-    ema = [p.detach().clone() for p in params] if rank == 0 else [None] * len(params)
-    # the reference's three parameter groups (yolo_trainer.py:149-168): BN weights (no decay), other weights (decay), biases
-    wd = 5e-4 * args.batch / 64
-    decay = [p.dim() > 1 for p in params]
     imgs = [torch.randint(0, 256, (bs, 3, args.size, args.size), dtype=torch.uint8, device=dev) for _ in range(2)]
     tgts = [synth_targets(bs, 10 * rank + i).to(dev) for i in range(2)]
     lr, momentum, ema_decay = 0.01, 0.937, 0.9999
+    wd = 5e-4 * args.batch / 64
+    # Flat optimizer state in the engine's gradient layout (model.parameters() order, 16-byte aligned slices): the
+    # parameters become views of one fp32 buffer, so SGD-nesterov + EMA is ONE fused launch and the DDP exchange ONE
+    # all-reduce. The reference's three parameter groups (yolo_trainer.py:149-168: BN weights / biases without decay,
+    # other weights with decay) become a 0/1 mask on the decay term.
+    model(imgs[0].float() / 255.0)  # builds the train engine (fixes the flat layout)
+    eng = next(iter(model.__dict__["_train_engine_cache"].values()))
+    flat_p = torch.zeros_like(eng.pg_flat)
+    decay_mask = torch.zeros_like(eng.pg_flat)
+    for p, o in zip(params, eng.pg_offsets):
+        flat_p[o:o + p.numel()].copy_(p.data.reshape(-1))
+        p.data = flat_p[o:o + p.numel()].view(p.shape)
+        if p.dim() > 1:
+            decay_mask[o:o + p.numel()] = 1.0
+    flat_m = torch.zeros_like(flat_p)
+    flat_e = flat_p.clone() if rank == 0 else None
 
     def step(i: int) -> float:
         x = imgs[i % 2].float() / 255.0  # prepare_img (abstract_trainer.py:252-261)
@@ -76,10 +87,13 @@ def main() -> None:
         if world > 1:
             loss = loss * world  # yolo_trainer.py:325-326
         loss.backward()
-        grads = [p.grad for p in params]
-        du.allreduce_mean_(grads)
-        for p, g, m, e, d in zip(params, grads, mom, ema, decay):
-            ops.sgd_ema_step(p.data, g, m, e, lr, momentum, wd if d else 0.0, True, ema_decay)
+        g = eng.last_grad_flat  # d(loss)/d(parameters), flat; the per-parameter .grad tensors are views of it
+        if world > 1:
+            torch.distributed.all_reduce(g)
+            g.div_(world)
+        g.addcmul_(decay_mask, flat_p, value=wd)  # weight decay of the decayed group (torch.optim.SGD adds wd * p to the gradient)
+        ops.sgd_ema_step(flat_p, g, flat_m, flat_e, lr, momentum, 0.0, True, ema_decay)
+        for p in params:
             p.grad = None
         return items
 
