@@ -130,8 +130,15 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
-    // instruction descriptor: bf16 x bf16 -> f32, A and B both MN-major (bits 15, 16), M = 128, N = N_T
-    constexpr uint32_t idesc = make_idesc_bf16_f32(128, N_T) | (1u << 15) | (1u << 16);
+    // instruction descriptor: bf16 x bf16 -> f32, A and B both MN-major (bits 15, 16), M = 128.
+    // The taps' x tiles sit TAP_BYTES apart in shared memory and their accumulators N_T columns apart in TMEM, i.e. they
+    // are consecutive N blocks of ONE MN-major operand (block stride LBO = XBLK_BYTES = TAP_BYTES / NXB): up to 256 / N_T
+    // taps go into one instruction. For the 3x3 kernel (N_T = 32) that is N = 256 + N = 32 per K step instead of nine
+    // N = 32 instructions, whose (128 + 32) x 32 B of operand reads per 16 tensor clocks made them shared-memory bound.
+    constexpr int TAPS_PER_MMA = TAPS * N_T <= 256 ? TAPS : (256 / N_T >= 1 ? 256 / N_T : 1);
+    constexpr int N_BIG = TAPS_PER_MMA * N_T;
+    constexpr uint32_t idesc_big = make_idesc_bf16_f32(128, N_BIG) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc_one = make_idesc_bf16_f32(128, N_T) | (1u << 15) | (1u << 16);
     int stage = 0, phase = 0;
     for (int i = 0; i < nchunks; ++i) {
       mbar_wait(&full_bar[stage], phase);
@@ -139,7 +146,8 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES);
       const uint32_t x_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll 1
-      for (int t = 0; t < TAPS; ++t) {
+      for (int t = 0; t < TAPS; t += (TAPS - t >= TAPS_PER_MMA ? TAPS_PER_MMA : 1)) {
+        const bool big = TAPS - t >= TAPS_PER_MMA;
 #pragma unroll
         for (int k = 0; k < Cfg::P / 16; ++k) {
           // MN-major descriptors: LBO = distance between channel blocks, SBO = 8 pixel rows
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
                     (static_cast<uint64_t>((8 * Cfg::XROW) >> 4) << 32) | (1ull << 46) |
                     ((Cfg::XROW == 128 ? 2ull : 4ull) << 61);
           }
-          umma_f16_ss(tmem_base + t * N_T, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + t * N_T, adesc, bdesc, big ? idesc_big : idesc_one, (i | k) != 0 ? 1u : 0u);
         }
       }
       umma_commit(&empty_bar[stage]);
