@@ -1,7 +1,7 @@
 """CPU oracle for the detection loss. TEST INFRASTRUCTURE ONLY (see oracle/nms_oracle.py header).
 
 Restates scripts/loss/losses.py:168-391 (ComputeLoss.__call__ / build_targets, default configuration:
-fl_gamma >= 0 i.e. plain BCE or the FocalLoss wrapper, autobalance off, gr = 1, sort_obj_iou off) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU
+fl_gamma >= 0 i.e. plain BCE or the FocalLoss wrapper, autobalance on or off, gr = 1, sort_obj_iou off) and scripts/utils/metrics.py:60-135 (bbox_iou, CIoU
 branch) in plain PyTorch so that autograd supplies the reference gradients. Pinned by tests/test_oracle_loss.py
 against tests/golden/loss_golden.npz (generated from the unmodified reference) and, in the build container,
 against the reference itself.
@@ -96,11 +96,16 @@ def bce_logits(x: torch.Tensor, t: torch.Tensor, pos_weight: torch.Tensor, gamma
 
 
 def compute_loss(preds: List[torch.Tensor], targets: torch.Tensor, anchors: torch.Tensor, hyp: Dict[str, float],
-                 nc: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """losses.py:223-300. preds: list of (bs, na, ny, nx, 5+nc) logits (requires_grad for the backward oracle)."""
+                 nc: int, balance: "List[float] | None" = None, ssi: "int | None" = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """losses.py:223-300. preds: list of (bs, na, ny, nx, 5+nc) logits (requires_grad for the backward oracle).
+    `balance` (a list, updated IN PLACE) + `ssi` (index of the stride-16 level) switch autobalance on (losses.py:286-292):
+    the loss of this call uses the incoming weights, then balance[i] <- 0.9999 balance[i] + 1e-4 / obj_loss_i and the
+    list is renormalised by balance[ssi]."""
     cp, cn = smooth_bce(hyp.get("label_smoothing", 0.0))
     gamma = float(hyp.get("fl_gamma", 0.0))
-    balance = {3: [4.0, 1.0, 0.4]}.get(len(preds), [4.0, 1.0, 0.25, 0.06, 0.02])
+    auto = balance is not None
+    if balance is None:
+        balance = {3: [4.0, 1.0, 0.4]}.get(len(preds), [4.0, 1.0, 0.25, 0.06, 0.02])
     cls_pw = torch.tensor([hyp["cls_pw"]])
     obj_pw = torch.tensor([hyp["obj_pw"]])
     lcls, lbox, lobj = torch.zeros(1), torch.zeros(1), torch.zeros(1)
@@ -120,7 +125,13 @@ def compute_loss(preds: List[torch.Tensor], targets: torch.Tensor, anchors: torc
                 t = torch.full_like(ps[:, 5:], cn)
                 t[range(n), tcls] = cp
                 lcls = lcls + bce_logits(ps[:, 5:], t, cls_pw, gamma)
-        lobj = lobj + bce_logits(pi[..., 4], tobj, obj_pw, gamma) * balance[i]
+        obji = bce_logits(pi[..., 4], tobj, obj_pw, gamma)
+        lobj = lobj + obji * balance[i]
+        if auto:
+            balance[i] = balance[i] * 0.9999 + 0.0001 / obji.detach().item()
+    if auto:
+        norm = balance[ssi]
+        balance[:] = [x / norm for x in balance]
     lbox = lbox * hyp["box"]
     lobj = lobj * hyp["obj"]
     lcls = lcls * hyp["cls"]

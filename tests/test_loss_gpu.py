@@ -92,6 +92,39 @@ def test_loss_focal(gamma):
     _check(preds, t, hyp, nc)
 
 
+def test_loss_autobalance():
+    """autobalance=True (losses.py:209,286-292): the level weights evolve like the oracle's over three calls, every loss
+    and the gradient of the LAST call (taken after its weights were already updated) match the oracle."""
+    from ayolov2_b200.loss import ComputeLoss
+    from oracle import loss_oracle
+
+    nc, bs, nt = 80, 2, 12
+    hyp = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
+    head = _Head(nc)
+    fn = ComputeLoss(_Model(nc, hyp), autobalance=True)
+    assert fn.ssi == 1
+    bal = [4.0, 1.0, 0.4]
+    for seed in (7, 8, 9):
+        g = torch.Generator().manual_seed(seed)
+        preds = [torch.randn(bs, 3, 160 // s, 160 // s, nc + 5, generator=g) for s in (8, 16, 32)]
+        t = torch.zeros(nt, 6)
+        t[:, 0] = torch.randint(0, bs, (nt,), generator=g).float()
+        t[:, 1] = torch.randint(0, nc, (nt,), generator=g).float()
+        t[:, 2:4] = 0.05 + 0.9 * torch.rand(nt, 2, generator=g)
+        t[:, 4:6] = torch.exp(np.log(0.03) + (np.log(0.7) - np.log(0.03)) * torch.rand(nt, 2, generator=g))
+        p_ref = [p.clone().requires_grad_(True) for p in preds]
+        l_ref, it_ref = loss_oracle.compute_loss(p_ref, t, head.anchors, hyp, nc, balance=bal, ssi=1)
+        p_gpu = [p.clone().cuda().requires_grad_(True) for p in preds]
+        l_gpu, it_gpu = fn(p_gpu, t.cuda())
+        assert torch.allclose(l_gpu.cpu(), l_ref.detach(), rtol=1e-4) and torch.allclose(it_gpu.cpu(), it_ref, rtol=1e-4, atol=1e-6)
+        assert np.allclose(fn.balance, bal, rtol=1e-5)
+    l_ref.backward()
+    l_gpu.backward()
+    for a, b in zip(p_gpu, p_ref):
+        denom = b.grad.abs().max().clamp_min(1e-12)
+        assert float((a.grad.cpu() - b.grad).abs().max() / denom) < 1e-3
+
+
 def test_loss_duplicate_cells_last_wins():
     """Two identical targets hit the same cells: tobj takes the later candidate's IoU, gradients accumulate."""
     g = torch.Generator().manual_seed(3)
