@@ -346,11 +346,21 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
   }
   if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
   tcgen05_fence_before();
-  if (p.csize > 1) cluster_sync_all();  // peer barriers must be initialised before any multicast can land
-  else __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
-  if (threadIdx.x == 0) CV_DBG(1);  // prologue done (barriers, TMEM)
+  uint32_t tmem_base = 0;
+  if (p.csize > 1) {
+    cluster_sync_all();  // peer barriers must be initialised before any multicast can land
+    tcgen05_fence_after();
+    tmem_base = *tmem_ptr_s;
+  } else if (warp == 0) {
+    // The TMA producer never touches TMEM: it only ARRIVES on the prologue barrier (its own thread 0 has initialised the
+    // mbarriers above) and starts filling the ring while the other warps still wait for the TMEM allocation.
+    asm volatile("bar.arrive 0, %0;" ::"r"(Cfg::THREADS) : "memory");
+  } else {
+    asm volatile("bar.sync 0, %0;" ::"r"(Cfg::THREADS) : "memory");
+    tcgen05_fence_after();
+    tmem_base = *tmem_ptr_s;
+  }
+  if (threadIdx.x == 32) CV_DBG(1);  // prologue done (barriers, TMEM)
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the
   // tail of the previous kernel in the stream; nothing below touches global memory before that kernel has completed.
   // The next kernel may start its own prologue as soon as every CTA of this grid is resident (all are: persistent grid).
@@ -643,25 +653,44 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
   }
   if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
-  if (threadIdx.x == 0) CV_DBG(1);
+  uint32_t tmem_base = 0;
+  if (warp == 0) {  // the producer only arrives (see conv_tc_kernel)
+    asm volatile("bar.arrive 0, %0;" ::"r"(Cfg::THREADS) : "memory");
+  } else {
+    asm volatile("bar.sync 0, %0;" ::"r"(Cfg::THREADS) : "memory");
+    tcgen05_fence_after();
+    tmem_base = *tmem_ptr_s;
+  }
+  if (threadIdx.x == 32) CV_DBG(1);
 
   const int tiles_per_img = p.hl_pairs_x * p.hl_bands_y;
   const int total_items = tiles_per_img * p.num_m_tiles * p.num_n_tiles;  // num_m_tiles == batch here
   const int cin_chunks = p.cin_chunks;
   // item -> (N tile fastest: the second N tile finds the halo in L2, tile, image)
+  // Longest work first: all two-half tiles, then the one-half tiles of the right edge (odd number of halves per row), so
+  // that the short items fill the tail of the static round-robin schedule.
+  const int full_pairs = p.hl_w_halves >> 1;
+  const int tiles2 = p.num_m_tiles * p.hl_bands_y * full_pairs;
   auto decode = [&](int item, int& n0, int& b, int& y0, int& x0, int& nh) {
-    const int t = item / p.num_n_tiles;
+    int t = item / p.num_n_tiles;
     n0 = (item - t * p.num_n_tiles) * BLOCK_N;
-    b = t / tiles_per_img;
-    const int r = t - b * tiles_per_img;
-    const int band = r / p.hl_pairs_x;
-    const int pair = r - band * p.hl_pairs_x;
+    int band, pair;
+    if (t < tiles2) {
+      const int per_img = p.hl_bands_y * full_pairs;
+      b = t / per_img;
+      const int r = t - b * per_img;
+      band = r / full_pairs;
+      pair = r - band * full_pairs;
+      nh = 2;
+    } else {
+      t -= tiles2;
+      b = t / p.hl_bands_y;
+      band = t - b * p.hl_bands_y;
+      pair = full_pairs;
+      nh = 1;
+    }
     y0 = band * Cfg::TH;
     x0 = pair * 2 * Cfg::TW;
-    nh = p.hl_w_halves - 2 * pair >= 2 ? 2 : 1;
   };
 
   if (warp == 0) {
