@@ -163,3 +163,31 @@ def test_fused_chains_match_separate_launches(name, decomposed):
     for a, b in zip(r1, r0):
         e = float((a - b).abs().max() / b.abs().max())
         assert e < 1e-2, e
+
+
+def test_tta_matches_oracle_views():
+    """inference_with_tta (tta_utils.py:62-86; the reference's val.py scales 1 / 0.83 / 0.67 with a left-right flip on the
+    second view): every augmented view runs through the CUDA engine; the concatenated, de-augmented prediction equals the
+    same orchestration over the fp32 CPU oracle forward within the bf16 tolerance."""
+    from ayolov2_b200 import synth as model_utils, tta
+    from oracle import yolo_oracle
+
+    model = model_utils.build_model("yolov5s", seed=3)
+    x = torch.rand((2, 3, 256, 320), generator=torch.Generator().manual_seed(8))
+    s, f = [1, 0.83, 0.67], [None, 3, None]
+
+    class _Oracle(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m, self.model, self.stride = m, m.model, m.stride
+
+        def forward(self, xi):
+            return yolo_oracle.forward(self.m, xi)
+
+    want, _ = tta.inference_with_tta(_Oracle(model), x, s, f)
+    got, _ = tta.inference_with_tta(model.cuda(), x.cuda(), s, f)
+    got = got.float().cpu()
+    assert got.shape == want.shape
+    assert float((got[..., 4:] - want[..., 4:]).abs().max()) < 2e-2
+    rel_box = (got[..., :4] - want[..., :4]).abs() / (want[..., :4].abs() + 8.0)
+    assert float(rel_box.max()) < 5e-2
