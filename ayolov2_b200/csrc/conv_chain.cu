@@ -62,6 +62,8 @@ struct ChainParams {
   int w_resident;    // all weight chunks stay in shared memory (loaded once per CTA): the "ring" has one slot per chunk
   int alias_staging; // the output staging buffer re-uses T's bytes (T is dead once stage 2 has finished)
   int t_plane;       // bytes of one 8-channel plane of T (CH_NH * 16)
+  int d2_split;            // stage 2 accumulates in regions R3 / R4 of its own (no stage 3, 5 regions fit): stage 1 of the
+                           // NEXT tile then overlaps the final epilogue of this one instead of waiting for it to drain
   int tmem_cols, d2_col;   // TMEM: three regions of d2_col columns: R0 = D1 rows 0..127 / D3 left half, R1 = D1 rows
                            // 128..255 / D2 left / D3 right, R2 = D1 rows 256..383 / D2 right
   int off_W, off_T, off_U, off_staging, off_bias, off_bars;  // byte offsets from the 1024-aligned shared-memory base
@@ -372,6 +374,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
     const uint32_t t_lo0 = desc_lo(smem_u32(T), p.t_plane), t_kstep = (2 * p.t_plane) >> 4;
     const uint32_t u_lo0 = desc_lo(smem_u32(U), CH_U_PLANE), u_kstep = (2 * CH_U_PLANE) >> 4;
     const uint32_t r1_t = tmem_base + p.d2_col, r2_t = tmem_base + 2 * p.d2_col;
+    const bool split = p.d2_split != 0;
+    const uint32_t d2l_t = split ? tmem_base + 3 * p.d2_col : r1_t, d2r_t = split ? tmem_base + 4 * p.d2_col : r2_t;
     const bool has3 = p.c3 != 0;
     int ws = 0, wph = 0, xs = 0, xph = 0;
     uint32_t t_phase = 0, u_phase = 0, ae_phase = 0;
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
       ++it;
       if (lane == 0) CH_DBG(it, 0);  // tile start (MMA warp)
       if (resident) ws = 0;
-      if (acc_pending) {  // D1 shares its TMEM columns with D2 / D3 of the previous tile
+      if (acc_pending && !split) {  // D1 shares its TMEM columns with D2 / D3 of the previous tile
         mbar_wait(acc_empty, ae_phase);
         ae_phase ^= 1;
         acc_pending = false;
@@ -416,6 +420,11 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
       // ---- stage 2: D2[left|right] += T(shifted by tap) x W2[tap]^T
       mbar_wait(t_ready, t_phase);
       t_phase ^= 1;
+      if (acc_pending) {  // split regions: only D2 waits for the previous tile's final epilogue (already true in practice:
+        mbar_wait(acc_empty, ae_phase);  // the epilogue warps wrote this tile's T after draining the previous D2)
+        ae_phase ^= 1;
+        acc_pending = false;
+      }
       tcgen05_fence_after();
       if (lane == 0) CH_DBG(it, 3);  // T ready
       for (int tap = 0; tap < 9; ++tap) {
@@ -431,8 +440,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
           if (elect_one()) {
             for (int k = 0; k < ks2; ++k) {  // left / right half: independent accumulators sharing the weight tile
               const uint32_t acc = (tap | cc | k) != 0 ? 1u : 0u;
-              umma_ss(r1_t, a_lo + k * t_kstep, hiT, b_lo + 2 * k, hi2, idesc2, acc);
-              umma_ss(r2_t, a_lo + 8 + k * t_kstep, hiT, b_lo + 2 * k, hi2, idesc2, acc);
+              umma_ss(d2l_t, a_lo + k * t_kstep, hiT, b_lo + 2 * k, hi2, idesc2, acc);
+              umma_ss(d2r_t, a_lo + 8 + k * t_kstep, hiT, b_lo + 2 * k, hi2, idesc2, acc);
             }
             if (!resident) umma_commit(&wempty[ws]);
             if (tap == 8 && cc == c1_chunks - 1) umma_commit(d2_full);
@@ -545,7 +554,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) conv_chain_kernel(const __grid_
       if (eall == 0) CH_DBG(it, 9);  // epilogue 1 done
       if (p.c3 == 0) {
         // ---- epilogue 2 = final
-        chain_store_tile(p, staging, bias2, tmem_base + lane_off + p.d2_col, tmem_base + lane_off + 2 * p.d2_col, p.c2, p.act2, 0,
+        const int d2reg = p.d2_split ? 3 : 1;
+        chain_store_tile(p, staging, bias2, tmem_base + lane_off + d2reg * p.d2_col, tmem_base + lane_off + (d2reg + 1) * p.d2_col, p.c2, p.act2, 0,
                          x0, y0, b, et, eall, b2_lo, b2_hi, d2_full, d2_phase, acc_empty, res_full, res_phase, xring, xslot0);
         d2_phase ^= 1;
         if (p.res_from_x) {  // the shortcut has been read: hand this tile's halo slots back to the producer
@@ -666,7 +676,12 @@ extern "C" int ay2_chain_plan_create(const ay2_chain_desc* d, const void* in, co
   int regW = d->c1 > d->c2 ? d->c1 : d->c2;
   if (kp.n3 > regW) regW = kp.n3;
   kp.d2_col = regW;
-  int cols = 3 * regW, pow2 = 32;
+  // Without a stage 3, five regions (D1 x 3, D2 x 2) decouple consecutive tiles if they still leave room for two CTAs.
+  // Implemented and parity-tested (AY2_CHAIN_SPLIT=1) but measured NEUTRAL (r01: 0.147 ms either way for the 32-channel
+  // Bottleneck @160x160): a tile's E1 -> stage 2 -> E2 chain (1.4 + 2.3 + 1.45 us) is the period, and the epilogue warps
+  // that would consume the early D1 are still draining the previous tile. Off by default.
+  kp.d2_split = (d->c3 == 0 && 5 * regW <= 256 && getenv("AY2_CHAIN_SPLIT") && atoi(getenv("AY2_CHAIN_SPLIT")) == 1) ? 1 : 0;
+  int cols = (kp.d2_split ? 5 : 3) * regW, pow2 = 32;
   while (pow2 < cols) pow2 *= 2;
   AY2_REQUIRE(pow2 <= 512, "chain needs %d TMEM columns", cols);
   kp.tmem_cols = pow2;
