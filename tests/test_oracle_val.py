@@ -53,3 +53,22 @@ def test_val_oracle_matches_reference_fresh_seeds():
     rb = val_oracle.ap_per_class(np.concatenate(tps), np.concatenate(confs), np.concatenate(pcls), np.concatenate(tcls))
     for x, y in zip(ra, rb):
         assert np.allclose(x, y, rtol=1e-12, atol=1e-15)
+
+
+def test_product_host_reductions_match_oracle():
+    """ayolov2_b200.val_stats (host side, no GPU): ap_per_class / compute_ap / scale_meta against the pinned oracle."""
+    from ayolov2_b200 import val_stats
+
+    tps, confs, pcls, tcls = [], [], [], []
+    for seed in range(30, 35):
+        det, lab = val_oracle.synth_case(seed, n_det=250, n_lab=35, nc=9)
+        tps.append(val_oracle.process_batch(det, lab)); confs.append(det[:, 4]); pcls.append(det[:, 5]); tcls.append(lab[:, 0])
+    args = (np.concatenate(tps), np.concatenate(confs), np.concatenate(pcls), np.concatenate(tcls))
+    for x, y in zip(val_stats.ap_per_class(*args), val_oracle.ap_per_class(*args)):
+        assert np.allclose(x, y, rtol=1e-12, atol=1e-15)
+    meta = val_stats.scale_meta((640, 640), [((480, 600), ((0.8, 0.8), (16.0, 24.0))), (480, 600)], device="cpu").numpy()
+    assert np.allclose(meta[0], [0.8, 16.0, 24.0, 600.0, 480.0])
+    gain = min(640 / 480, 640 / 600)  # general.py:343-349
+    assert np.allclose(meta[1], [gain, (640 - 600 * gain) / 2, (640 - 480 * gain) / 2, 600.0, 480.0])
+    with pytest.raises(RuntimeError):
+        val_stats.match_batch(torch.zeros((1, 4, 6)), torch.zeros(1, dtype=torch.int32), torch.zeros((0, 6)), torch.linspace(0.5, 0.95, 10))
