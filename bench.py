@@ -206,7 +206,8 @@ def main() -> None:
     from ayolov2_b200.detector import Detector
     from ayolov2_b200 import synth as model_utils
 
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    args.warmup = max(args.warmup, 3)  # timing rules: at least 3 warm-up steps (the line reports the count actually run)
+    args.steps = max(args.steps, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
