@@ -662,6 +662,9 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
     tmem_base = *tmem_ptr_s;
   }
   if (threadIdx.x == 32) CV_DBG(1);
+  // programmatic dependent launch (opt-in, see ay2_conv_plan_run): no global memory access before the previous kernel is done
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tiles_per_img = p.hl_pairs_x * p.hl_bands_y;
   const int total_items = tiles_per_img * p.num_m_tiles * p.num_n_tiles;  // num_m_tiles == batch here
