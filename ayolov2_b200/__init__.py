@@ -5,3 +5,10 @@ library of hand-written CUDA kernels (include/ay2.h). No CPU fallback: the ops r
 CUDA device is missing.
 """
 __version__ = "0.1.0"
+
+
+def set_precision(model, precision: str = "bf16"):
+    """See ayolov2_b200.engine.set_precision."""
+    from .engine import set_precision as _sp
+
+    return _sp(model, precision)

@@ -14,9 +14,9 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libay2.so"
-STAMP_PATH = PKG_DIR / "csrc" / ".build_stamp"
+HASH_MARK = b"AY2_SOURCE_HASH="
 
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "train_pointwise.cu", "nms.cu", "loss.cu", "val_match.cu"]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "precise.cu", "train_pointwise.cu", "nms.cu", "nms_variants.cu", "loss.cu", "val_match.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -44,10 +44,27 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+def embedded_hash(path: Path = LIB_PATH) -> str:
+    """The source hash compiled into libay2.so (csrc/capi.cu, `ay2_source_hash()`), read from the file's bytes so that
+    the check needs neither a loadable CUDA runtime nor a side file that could travel separately from the binary."""
+    if not path.exists():
+        return ""
+    data = path.read_bytes()
+    i = data.find(HASH_MARK)
+    if i < 0:
+        return ""
+    return data[i + len(HASH_MARK):i + len(HASH_MARK) + 64].decode("ascii", "replace")
+
+
+def is_current() -> bool:
+    return embedded_hash() == _source_hash()
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every translation unit to an object and link libay2.so. Rebuilds only when sources changed."""
+    """Compile every translation unit to an object and link libay2.so. Rebuilds only when the hash embedded in the
+    existing binary differs from the hash of the sources (a stale .so after a checkout is rebuilt, never silently bound)."""
     want = _source_hash()
-    if not force and LIB_PATH.exists() and STAMP_PATH.exists() and STAMP_PATH.read_text().strip() == want:
+    if not force and embedded_hash() == want:
         return LIB_PATH
     nvcc = _nvcc()
     objdir = PKG_DIR / "build"
@@ -60,6 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             continue
         obj = objdir / (src + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(sp), "-o", str(obj)]
+        if src == "capi.cu":
+            cmd.insert(1, f"-DAY2_SOURCE_HASH_STR=\"{want}\"")
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     log = []
@@ -74,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     (objdir / "build.log").write_text("\n".join(log))
-    STAMP_PATH.write_text(want)
+    assert embedded_hash() == want, "libay2.so does not carry the source hash it was built from"
     if verbose:
         print("\n".join(log))
     return LIB_PATH

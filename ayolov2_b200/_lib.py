@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
         ("cout_pad", C.c_int32), ("pad_w", C.c_int32),
         ("in_pix_stride", C.c_int32), ("in_row_pixels", C.c_int32),
         ("out_pix_stride", C.c_int32), ("out_row_pixels", C.c_int32),
-        ("cin_split", C.c_int32), ("in2_cstride", C.c_int32),
+        ("cin_split", C.c_int32), ("in2_cstride", C.c_int32), ("x3", C.c_int32),
         ("in2", C.c_void_p),
     ]
 
@@ -90,6 +90,7 @@ class LossParams(C.Structure):
 _PROTOS = {
     "ay2_version": (C.c_int, []),
     "ay2_last_error_string": (C.c_char_p, []),
+    "ay2_source_hash": (C.c_char_p, []),
     "ay2_launch_count": (C.c_int64, []),
     "ay2_conv_block_n": (C.c_int, [C.c_int32]),
     "ay2_conv_plan_create": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -116,6 +117,12 @@ _PROTOS = {
                                  C.c_int32, C.c_void_p]),
     "ay2_head_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ay2_space_to_depth_x3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_int32, C.c_int32, C.c_void_p]),
+    "ay2_sppf_pool_x3": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ay2_head_decode2": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_float, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ay2_yolo_loss_workspace_bytes": (C.c_size_t, [C.POINTER(LossParams)]),
     "ay2_yolo_loss": (C.c_int, [C.POINTER(LossParams), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
@@ -150,6 +157,16 @@ _PROTOS = {
     "ay2_match_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "ay2_nms_boxes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ay2_nms_candidate_table": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ay2_nms_fast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                               C.c_int32, C.c_void_p, C.c_void_p]),
+    "ay2_nms_matrix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_void_p, C.c_void_p]),
+    "ay2_nms_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ay2_nms_batched_scaled": (C.c_int, [C.c_void_p, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_nms_candidates_begin": (C.c_int, [C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ay2_nms_from_candidates": (C.c_int, [C.POINTER(HeadLevels), C.POINTER(NmsParams), C.c_void_p, C.c_size_t, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -175,6 +192,14 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    # A binary built from other sources than the ones next to it (stale after a checkout) must not be bound silently:
+    # struct layouts and kernel semantics are only guaranteed for the matching include/ay2.h + csrc/.
+    from . import _build
+
+    have, want = lib.ay2_source_hash().decode(), _build._source_hash()
+    if have != want:
+        raise RuntimeError(f"{_LIB_PATH} was built from different sources (embedded {have[:12]}, tree {want[:12]}): rebuild it "
+                           "with `python -c 'import __graft_entry__ as g; g.build()'`")
     _lib = lib
     return lib
 

@@ -42,6 +42,19 @@ void count_launch(int n = 1);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute (e.g. the opt-in to > 48 KB of dynamic shared memory) is per (function, DEVICE): call sites keep one
+// flag per device, `static DeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)`, not one flag per process.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const bool f = !done[dev];
+    done[dev] = true;
+    return f;
+  }
+};
+
 // TMA tensor maps (conv_tc.cu). Activation: NHWC bf16 view [C][W][H][B] with element strides, box [boxc][bw][bh][1],
 // swizzle span = boxc*2 bytes. Weights: bf16 [rows][Ktot] (K innermost), box [boxk][boxn].
 int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB,

@@ -29,6 +29,10 @@ struct ConvKernelParams {
   CUtensorMap tmB;     // weights [Ktot][cout_pad] (K innermost)
   CUtensorMap tmOut;   // output  [C][W][H][B]
   CUtensorMap tmRes;   // residual (same geometry as output) if has_res
+  // split-precision mode (x3, see ConvCfg): the output segment is three planes of `cout` channels [hi | lo | hi]; tmOut is
+  // plane 0, tmOutX[0..1] planes 1 and 2; the residual is read as hi (tmRes) + lo (tmResLo)
+  CUtensorMap tmOutX[2];
+  CUtensorMap tmResLo;
   const float* bias;   // [cout_pad]
   int num_m_tiles, num_n_tiles;
   int boxes_x, boxes_per_img;
@@ -61,8 +65,14 @@ __device__ __forceinline__ unsigned long long cv_now() {
 
 constexpr int kSmemPerSm = 227 * 1024;
 
-template <int BLOCK_N, int CK>
+// X3 = split-precision verification mode ("bf16x3"): every activation v is stored as hi = bf16(v), lo = bf16(v - hi) in three
+// channel planes [hi | lo | hi] and every weight as [w_hi | w_hi | w_lo] along K, so the unchanged main loop accumulates
+// x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32: fp32-equivalent products (the dropped x_lo w_lo term is 2^-16 relative) on
+// the same TMA / tcgen05 pipeline. Only the epilogue differs: exact SiLU, hi/lo split, three plane stores.
+template <int BLOCK_N, int CK, bool X3 = false>
 struct ConvCfg {
+  static constexpr bool kX3 = X3;
+  static constexpr int BN = BLOCK_N;
   static constexpr int SWA = CK * 2;                 // operand row bytes == swizzle span
   static constexpr int A_BYTES = 128 * SWA;
   static constexpr int B_BYTES = BLOCK_N * SWA;
@@ -71,11 +81,11 @@ struct ConvCfg {
   static constexpr int SWO = OC * 2;                       // output slab row bytes == swizzle span
   static constexpr int SLAB_BYTES = 128 * SWO;
   static constexpr int NSLAB = BLOCK_N / OC;
-  static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2;
+  static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2 * (X3 ? 2 : 1);  // x3: hi slabs, then lo slabs
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256 + 1024;  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr + head-candidate list
   // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
   // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
-  static constexpr int CTAS_PER_SM = BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1);
+  static constexpr int CTAS_PER_SM = X3 ? 1 : (BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1));
   // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes and owns ONE output slab (<= 64 columns): it drains
   // it, stores it with TMA and waits for its own store only -- groups never synchronise with each other, and every
   // scheduler has EPI_GROUPS x CTAS_PER_SM epilogue warps to interleave (the drain is latency-bound per warp).
@@ -291,9 +301,69 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, uint32_t slab,
   }
 }
 
+// Split-precision drain: TMEM -> +bias -> exact SiLU (-> + residual hi + lo already staged) -> hi = bf16(v), lo = bf16(v - hi)
+// -> the hi slab and the lo slab (same swizzled layout, `lo_delta` bytes apart).
+template <class Cfg, bool SILU, bool RES>
+__device__ __forceinline__ void drain_accumulator_x3(uint32_t taddr, uint32_t slab, uint32_t lo_delta, uint32_t bias_u32, int et) {
+  constexpr int BLK = Cfg::OC < 32 ? Cfg::OC : 32;
+#pragma unroll 1
+  for (int cc = 0; cc < Cfg::OC; cc += BLK) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + cc, v);
+    tmem_ld_wait();
+    const uint32_t ba = bias_u32 + cc * 4;
+#pragma unroll
+    for (int g = 0; g < BLK / 8; ++g) {
+      float bb[8], f[8];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba + g * 32));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + g * 32 + 16));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = __uint_as_float(v[g * 8 + i]) + bb[i];
+        f[i] = SILU ? __fdividef(x, 1.0f + __expf(-x)) : x;
+      }
+      const uint32_t dst = slab + swizzled_offset<Cfg::SWO>(et, cc / 8 + g);
+      if (RES) {
+        uint4 rh, rl;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(dst));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(dst + lo_delta));
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rh);
+        const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&rl);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __bfloat1622float2(h2[i]), b = __bfloat1622float2(l2[i]);
+          f[2 * i] += a.x + b.x;  // hi + lo is exact in fp32 (at most 17 significant bits)
+          f[2 * i + 1] += a.y + b.y;
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        const float2 hf = __bfloat1622float2(h);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = pack_bf16x2(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + lo_delta), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    }
+  }
+}
+
 // taddr: TMEM address (lane quadrant + first column) of the slab; slab: its staging bytes; bias_u32: its bias slice
 template <class Cfg>
 __device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32_t taddr, uint32_t slab, uint32_t bias_u32, int et) {
+  if constexpr (Cfg::kX3) {
+    constexpr uint32_t lo_delta = 128 * Cfg::BN * 2;  // the lo slabs follow all hi slabs
+    if (p.act == AY2_ACT_SILU) {
+      if (p.has_res) drain_accumulator_x3<Cfg, true, true>(taddr, slab, lo_delta, bias_u32, et);
+      else drain_accumulator_x3<Cfg, true, false>(taddr, slab, lo_delta, bias_u32, et);
+    } else {
+      if (p.has_res) drain_accumulator_x3<Cfg, false, true>(taddr, slab, lo_delta, bias_u32, et);
+      else drain_accumulator_x3<Cfg, false, false>(taddr, slab, lo_delta, bias_u32, et);
+    }
+    return;
+  }
   if (p.act == AY2_ACT_SILU) {
     if (p.has_res) drain_accumulator<Cfg, true, true>(taddr, slab, bias_u32, et);
     else drain_accumulator<Cfg, true, false>(taddr, slab, bias_u32, et);
@@ -303,9 +373,9 @@ __device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32
   }
 }
 
-template <int BLOCK_N, int CK>
-__global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N, CK>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, CK>;
+template <int BLOCK_N, int CK, bool X3>
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLOCK_N, CK, X3>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N, CK, X3>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle patterns repeat every 1024 B and UMMA descriptors assume base_offset 0
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -517,9 +587,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
         }
         tma_store_wait_read<0>();  // the previous tile's store of this slab has finished reading it
         if (p.has_res) {
-          if (lane == 0) mbar_expect_tx(&res_full[egrp], Cfg::SLAB_BYTES);
+          if (lane == 0) mbar_expect_tx(&res_full[egrp], Cfg::SLAB_BYTES * (X3 ? 2 : 1));
           __syncwarp();
-          if (lane < p.NB) tma_load_4d(&p.tmRes, &res_full[egrp], slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+          if (lane < p.NB) {
+            tma_load_4d(&p.tmRes, &res_full[egrp], slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+            if constexpr (X3)
+              tma_load_4d(&p.tmResLo, &res_full[egrp], slab + 128 * BLOCK_N * 2 + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+          }
         }
         if (!bias_once)
           for (int i = lane; i < Cfg::OC; i += 32) bias_s[egrp * Cfg::OC + i] = p.bias[nc0 + i];
@@ -539,12 +613,16 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
       if (leader) {
         if (lane < p.NB) {
           tma_store_4d(&p.tmOut, slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+          if constexpr (X3) {  // planes [hi | lo | hi] of the output segment
+            tma_store_4d(&p.tmOutX[0], slab + 128 * BLOCK_N * 2 + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+            tma_store_4d(&p.tmOutX[1], slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
+          }
           tma_store_commit();
         }
         if (eall == 0) CV_DBG(it == 0 ? 4 : 6);  // first / last tile's store issued
       }
       res_phase ^= 1;
-      if (p.hc.keys) {
+      if (!X3 && p.hc.keys) {
         // detect head: score NMS candidates from the whole staged tile (all slabs) while the TMA stores drain it (both
         // only read); no group may start rewriting its slab before every group has finished reading
         named_bar_sync(1, Cfg::EPI_THREADS);
@@ -588,6 +666,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK>::THREADS, ConvCfg<BLOCK_N
 // ------------------------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
 struct HaloCfg {
+  static constexpr bool kX3 = false;
+  static constexpr int BN = BLOCK_N;
   static constexpr int CK = 64, SWA = 128;
   static constexpr int TH = 16, TW = 8;                   // one half tile
   static constexpr int HH = TH + 2;                       // halo lines
@@ -934,12 +1014,12 @@ extern "C" int ay2_conv_block_n(int32_t cout) {
   return 256;
 }
 
-template <int BN, int CK>
+template <int BN, int CK, bool X3>
 static void bind_kernel(ay2_conv_plan* pl) {
-  pl->kernel = conv_tc_kernel<BN, CK>;
-  pl->smem = ConvCfg<BN, CK>::SMEM_BYTES;
-  pl->ctas_per_sm = ConvCfg<BN, CK>::CTAS_PER_SM;
-  pl->threads = ConvCfg<BN, CK>::THREADS;
+  pl->kernel = conv_tc_kernel<BN, CK, X3>;
+  pl->smem = ConvCfg<BN, CK, X3>::SMEM_BYTES;
+  pl->ctas_per_sm = ConvCfg<BN, CK, X3>::CTAS_PER_SM;
+  pl->threads = ConvCfg<BN, CK, X3>::THREADS;
 }
 
 static int pick_box(int H, int W, int* bh, int* bw) {
@@ -990,6 +1070,8 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   AY2_REQUIRE(d->cout_pad >= d->cout && d->cout_pad % bn == 0, "cout_pad=%d must be a multiple of %d", d->cout_pad, bn);
   AY2_REQUIRE(d->res_cstride == 0 || residual, "residual stride given without a residual pointer");
   AY2_REQUIRE(d->res_cstride % 8 == 0, "residual channel stride must be a multiple of 8");
+  AY2_REQUIRE(!d->x3 || (d->out_pix_stride <= 0 && d->out_cstride >= 3 * d->cout && (d->res_cstride == 0 || d->res_cstride >= 3 * d->cout)),
+              "split-precision output needs three planes of cout channels inside the channel stride");
 
   ay2_conv_plan* pl = new ay2_conv_plan();
   memset(pl, 0, sizeof(*pl));
@@ -998,7 +1080,8 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   AY2_REQUIRE(split == 0 || (d->stride == 1 && d->in2 && split > 0 && split < d->cin && split % 16 == 0 && d->in2_cstride % 8 == 0 &&
                              d->in_pix_stride <= 0 && d->in_row_pixels <= 0),
               "two-source input needs stride 1, a second pointer, and cin_split a multiple of 16 inside (0, cin)");
-  const int ck = (d->cin % 64 == 0 && split % 64 == 0) ? 64 : ((d->cin % 32 == 0 && split % 32 == 0) ? 32 : 16);
+  int ck = (d->cin % 64 == 0 && split % 64 == 0) ? 64 : ((d->cin % 32 == 0 && split % 32 == 0) ? 32 : 16);
+  if (d->x3 && bn == 256 && ck == 64) ck = 32;  // the doubled (hi + lo) staging of a 256-column tile leaves room for 32-channel stages only
   pl->block_n = bn;
   pl->ck = ck;
   ConvKernelParams& kp = pl->kp;
@@ -1008,7 +1091,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
     // the MMA rows on this feature-map size, e.g. 20 x 20)
     static const int env_halo = getenv("AY2_CONV_HALO") ? atoi(getenv("AY2_CONV_HALO")) : 1;
     const int bands = ceil_div(d->out_h, 16), halves = ceil_div(d->out_w, 8);
-    const bool shape_ok = d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->cin % 64 == 0 &&
+    const bool shape_ok = !d->x3 && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->cin % 64 == 0 &&
                           split == 0 && d->in_pix_stride <= 0 && d->in_row_pixels <= 0 && d->out_pix_stride <= 0 &&
                           d->out_row_pixels <= 0;
     const bool fill_ok = (double)bands * 16 * halves * 8 <= 1.3 * d->out_h * d->out_w;
@@ -1115,19 +1198,30 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   const int64_t orow = d->out_row_pixels > 0 ? (int64_t)d->out_row_pixels * ops_ : ops_ * d->out_w;
   const int64_t oimg = sub ? orow * d->out_h : orow * d->out_h;
   if (rc == AY2_OK) rc = encode_act_map(&kp.tmOut, out, d->cout, d->out_w, d->out_h, d->batch, ops_, orow, oimg, oc, bw, bh);
+  for (int pl_i = 0; pl_i < 2 && rc == AY2_OK && d->x3; ++pl_i)  // planes 1 (lo) and 2 (hi again) of the output segment
+    rc = encode_act_map(&kp.tmOutX[pl_i], static_cast<uint8_t*>(out) + (size_t)(pl_i + 1) * d->cout * 2, d->cout, d->out_w,
+                        d->out_h, d->batch, ops_, orow, oimg, oc, bw, bh);
   if (rc == AY2_OK && kp.has_res) {
     const int64_t rscale = sub ? d->out_pix_stride / d->out_cstride : 1;  // same sub-grid geometry for the residual
     const int64_t rps = (int64_t)d->res_cstride * rscale;
     const int64_t rrow = d->out_row_pixels > 0 ? (int64_t)d->out_row_pixels * rps : rps * d->out_w;
     rc = encode_act_map(&kp.tmRes, residual, d->cout, d->out_w, d->out_h, d->batch, rps, rrow, rrow * d->out_h, oc, bw, bh);
+    if (rc == AY2_OK && d->x3)
+      rc = encode_act_map(&kp.tmResLo, static_cast<const uint8_t*>(residual) + (size_t)d->cout * 2, d->cout, d->out_w, d->out_h,
+                          d->batch, rps, rrow, rrow * d->out_h, oc, bw, bh);
   }
   if (rc != AY2_OK) {
     delete pl;
     return rc;
   }
 
-#define AY2_BIND(BN, CKV)            \
-  if (bn == BN && ck == CKV) bind_kernel<BN, CKV>(pl);
+#define AY2_BIND(BN, CKV)                                         \
+  if (bn == BN && ck == CKV) {                                    \
+    if constexpr (BN * CKV < 256 * 64) {                          \
+      if (d->x3) bind_kernel<BN, CKV, true>(pl);                  \
+    }                                                             \
+    if (!d->x3) bind_kernel<BN, CKV, false>(pl);                  \
+  }
   AY2_BIND(32, 16) AY2_BIND(32, 32) AY2_BIND(32, 64)
   AY2_BIND(64, 16) AY2_BIND(64, 32) AY2_BIND(64, 64)
   AY2_BIND(128, 16) AY2_BIND(128, 32) AY2_BIND(128, 64)

@@ -243,11 +243,9 @@ static int launch_wgrad(const WgradParams& kp, int grid, cudaStream_t st) {
   constexpr int STAGE_BYTES = Cfg::A_BYTES + TAPS * Cfg::TAP_BYTES;
   constexpr int NSTAGES = (220 * 1024) / STAGE_BYTES >= 3 ? 3 : 2;
   constexpr size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 256;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce once;
+  if (once.first())
     AY2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<N_T, XB, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   conv_wgrad_kernel<N_T, XB, TAPS><<<grid, 256, smem, st>>>(kp);
   AY2_CHECK_LAUNCH();
   return AY2_OK;

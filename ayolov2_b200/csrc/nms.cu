@@ -24,6 +24,7 @@
 #include "ay2_common.h"
 #include "ay2_ptx.cuh"
 #include "head_math.cuh"
+#include "nms_common.cuh"
 
 namespace ay2 {
 
@@ -64,35 +65,6 @@ __device__ __forceinline__ void stage_push(WarpStage& s, bool ok, unsigned long 
   if (ok) s.buf[s.n + __popc(m & ((1u << lane) - 1))] = key;
   s.n += c;
   __syncwarp();
-}
-
-// IoU > iou_thres exactly as torchvision's CPU kernel evaluates it: fp32 arithmetic, w/h clamped at 0, RN division,
-// comparison against the double threshold. The double comparison is folded into `thr` = the largest float <= iou_thres
-// ((double)x > T  <=>  x > thr for every float x). The division is avoided for all but a sliver of pairs:
-// with q = inter/uni (real), inter > uni*thr*(1+2^-20) => q > thr + ulp(thr) => RN(q) > thr, and
-// inter < uni*thr*(1-2^-20) => q < thr => RN(q) <= thr (RN is monotone, thr is a float); the roundings of hi/lo are
-// < 2^-22 relative as long as uni is a normal positive number far from overflow (`fin`). Branch-free up to that sliver.
-struct IouThr {
-  float thr, hi, lo;
-};
-__device__ __forceinline__ IouThr make_iou_thr(double iou_thres) {
-  IouThr t;
-  t.thr = static_cast<float>(iou_thres);
-  if (static_cast<double>(t.thr) > iou_thres) t.thr = nextafterf(t.thr, -INFINITY);
-  const bool filt = t.thr > 1e-30f && t.thr < 1e30f;
-  t.hi = filt ? __fmul_rn(t.thr, 1.000001f) : INFINITY;
-  t.lo = filt ? __fmul_rn(t.thr, 0.999999f) : -INFINITY;
-  return t;
-}
-__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const IouThr t) {
-  const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-  const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-  const float inter = __fmul_rn(w, h);
-  const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
-  const bool fin = (__float_as_uint(uni) - 0x0D800000u) < 0x64000000u;  // 2^-100 <= uni < 2^100 (positive, finite)
-  if (fin && inter > __fmul_rn(uni, t.hi)) return true;
-  if (fin && inter < __fmul_rn(uni, t.lo)) return false;
-  return __fdiv_rn(inter, uni) > t.thr;
 }
 
 __device__ __forceinline__ void group_bar_sync(int id, int nthreads) {
@@ -347,7 +319,7 @@ __global__ void nms_score_rows_kernel(BoxSource src, ay2_nms_params p, const uin
 __global__ void __launch_bounds__(kNmsThreads, 1)
     nms_sort_scan_kernel(BoxSource src, ay2_nms_params p, unsigned long long* __restrict__ keys, long long key_stride,
                          const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
-                         int* __restrict__ overflow, long long* __restrict__ trace) {
+                         int* __restrict__ overflow, long long* __restrict__ trace, const float* __restrict__ wh_scale) {
 #define AY2_NMS_MARK(k)                                                    \
   do {                                                                     \
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); \
@@ -374,6 +346,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   const int wid = tid >> 5;
   const int nwarp = blockDim.x >> 5;
   const int nc = p.no - 5;
+  // per-image class-offset scale (torchvision's batched_nms coordinate trick: max coordinate of the image + 1). A scale
+  // that small fails the disjoint-window test below, so such images take the single-segment (exact, all-pairs) route.
+  if (wh_scale) p.max_wh = __fadd_rn(wh_scale[b], 1.0f);
   int n = counts[b];
   if (n > p.max_candidates) {
     n = p.max_candidates;
@@ -948,13 +923,12 @@ static int nms_common_checks(const ay2_nms_params* p, const void* workspace, siz
 }
 
 static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, const NmsWorkspaceView& v, float* out_det,
-                                int32_t* out_count, int32_t* overflow_flag, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+                                int32_t* out_count, int32_t* overflow_flag, cudaStream_t st, const float* wh_scale = nullptr) {
+  // the opt-in to > 48 KB of dynamic shared memory is per (function, device): one flag per device, not per process
+  static DeviceOnce once;
+  if (once.first())
     AY2_CHECK_CUDA(
         cudaFuncSetAttribute(nms_sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
-    attr_set = true;
-  }
   // AY2_NMS_TRACE=1: clock64 stamps of image 0's phases (debugging aid; synchronises, never set in production)
   static const bool want_trace = getenv("AY2_NMS_TRACE") != nullptr;
   static long long* trace = nullptr;
@@ -963,7 +937,7 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
     AY2_CHECK_CUDA(cudaMemset(trace, 0, 16 * sizeof(long long)));
   }
   nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, v.keys, v.key_stride, v.counts, out_det,
-                                                                     out_count, v.overflow, trace);
+                                                                     out_count, v.overflow, trace, wh_scale);
   AY2_CHECK_LAUNCH();
   if (trace) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -982,9 +956,9 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
   return AY2_OK;
 }
 
-extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
-                               size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
-                               void* stream) {
+static int nms_batched_impl(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, const float* max_coord,
+                            void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                            void* stream) {
   AY2_REQUIRE(pred, "ay2_nms_batched: null prediction pointer");
   int rc = nms_common_checks(p, workspace, workspace_bytes, out_det, out_count);
   if (rc != AY2_OK) return rc;
@@ -997,10 +971,23 @@ extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const
   const NmsWorkspaceView v = nms_workspace_view(p, workspace);
   rc = nms_generate_candidates(src, p, class_mask, v, st);
   if (rc != AY2_OK) return rc;
-  rc = nms_sort_scan_launch(src, p, v, out_det, out_count, overflow_flag, st);
+  rc = nms_sort_scan_launch(src, p, v, out_det, out_count, overflow_flag, st, max_coord);
   if (rc != AY2_OK) return rc;
   count_launch(3);
   return AY2_OK;
+}
+
+extern "C" int ay2_nms_batched(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, void* workspace,
+                               size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                               void* stream) {
+  return nms_batched_impl(pred, p, class_mask, nullptr, workspace, workspace_bytes, out_det, out_count, overflow_flag, stream);
+}
+
+extern "C" int ay2_nms_batched_scaled(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, const float* max_coord,
+                                      void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count,
+                                      int32_t* overflow_flag, void* stream) {
+  AY2_REQUIRE(max_coord, "ay2_nms_batched_scaled: null per-image coordinate maxima");
+  return nms_batched_impl(pred, p, class_mask, max_coord, workspace, workspace_bytes, out_det, out_count, overflow_flag, stream);
 }
 
 static int box_source_from_levels(const ay2_head_levels* hl, const ay2_nms_params* p, BoxSource* out) {

@@ -266,11 +266,10 @@ extern "C" int ay2_sppf_pool(const void* in, int32_t batch, int32_t h, int32_t w
   const int cpc = (c % 16 == 0 && (size_t)8 * h * w * sizeof(uint4) <= 100 * 1024) ? 2 : 1;
   const size_t smem = (size_t)4 * cpc * h * w * sizeof(uint4);
   AY2_REQUIRE(smem <= 200 * 1024, "sppf_pool plane %dx%d too large for shared memory", h, w);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     AY2_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AY2_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const int n = h * w * cpc;
   const int threads = n >= 512 ? 512 : ((n + 31) / 32) * 32;

@@ -49,9 +49,14 @@ def _round_up(v: int, m: int) -> int:
 class Builder:
     """Accumulates launches (`steps`) and owns every buffer of one compiled graph."""
 
-    def __init__(self, batch: int, device: torch.device) -> None:
+    def __init__(self, batch: int, device: torch.device, x3: bool = False) -> None:
         self.B = batch
         self.device = device
+        # split-precision verification mode ("bf16x3", ops.ActView): same tcgen05 conv kernel, fp32-equivalent arithmetic.
+        # Every producer writes ONE segment [hi | lo | hi]; `segments` remembers them per buffer so that a consumer can lay
+        # its weights out as [w_hi | w_hi | w_lo] per input segment.
+        self.x3 = x3
+        self.segments: Dict[int, Dict[int, int]] = {}
         self.steps: List[Callable[[], None]] = []
         self.plans: List[ConvPlan] = []
         self.keep: List[Any] = []
@@ -59,10 +64,25 @@ class Builder:
         self.act_bytes = 0.0  # algorithmic activation traffic (each conv reads its input once, writes its output once)
 
     def new_act(self, H: int, W: int, C_: int) -> ActView:
-        v = ops.new_act(self.B, H, W, _round_up(C_, 8), device=self.device)
+        v = ops.new_act(self.B, H, W, _round_up(C_, 8), device=self.device, x3=self.x3)
         v.buf.zero_()
         self.keep.append(v.buf)
         return v
+
+    def mark_segment(self, v: ActView) -> None:
+        if self.x3:
+            self.segments.setdefault(v.buf.data_ptr(), {})[v.c0] = v.c
+
+    def segments_of(self, v: ActView) -> List[Tuple[int, int]]:
+        """[(offset inside the view, width)] of the producer segments that tile the split-precision view `v`."""
+        table = self.segments.get(v.buf.data_ptr(), {})
+        out, at = [], v.c0
+        while at < v.c0 + v.c:
+            assert at in table, f"split-precision view [{v.c0}, {v.c0 + v.c}) is not cut at producer segments {sorted(table.items())}"
+            out.append((at - v.c0, table[at]))
+            at += table[at]
+        assert at == v.c0 + v.c, "split-precision view ends inside a producer segment"
+        return out
 
     # ---------------------------------------------------------------------------------------------
     def conv2d(self, x: ActView, y: ActView, weight: torch.Tensor, bias: Optional[torch.Tensor], bn, eps: float,
@@ -90,7 +110,14 @@ class Builder:
                       torch.cat((mu, torch.zeros(padn, device=self.device))), torch.cat((var, torch.ones(padn, device=self.device))))
             if bias is not None:
                 bias = torch.cat((bias, torch.zeros(y.c - cout, device=self.device)))
-        wp, bp = ops.pack_conv_weight(w, bias, bn, eps)
+        if self.x3:
+            segs = self.segments_of(x)
+            if x2 is not None:
+                segs = segs + [(x.c + o, wd) for o, wd in self.segments_of(x2)]
+            wp, bp = ops.pack_conv_weight_x3(w, bias, bn, eps, segs)
+            self.mark_segment(y)
+        else:
+            wp, bp = ops.pack_conv_weight(w, bias, bn, eps)
         plan = ConvPlan(x, y, wp, bp, kh, kw, stride, pad, act, residual=residual, x2=x2)
         self.plans.append(plan)
         self.steps.append(plan.run)
@@ -111,7 +138,7 @@ class Builder:
         return (H * W) / float(((H + 15) // 16 * 16) * ((W + 15) // 16 * 16))
 
     def _chain_ok(self, x: ActView, c1: int, c2: int, c3: int, k: int, s: int, p: int) -> bool:
-        if not self.FUSE_CHAINS or self._tile_eff(x.H, x.W) < self.CHAIN_MIN_TILE_EFF or x.c % 16:
+        if self.x3 or not self.FUSE_CHAINS or self._tile_eff(x.H, x.W) < self.CHAIN_MIN_TILE_EFF or x.c % 16:
             return False
         return ops.chain_supported(ops.chain_desc(x, c1, c2, c3, 0, 0, 0, 16, 0, k=k, stride=s, pad=p))
 
@@ -184,9 +211,14 @@ class Builder:
         # WINDOWS (64 channels = one 128-byte TMA row) starting at physical column x: window = logical pixels x-1..x+2.
         H2, W2 = H // 2, W // 2
         Wp = W2 + 8
-        s2d = ActView(torch.zeros((self.B, H2, Wp, 16), dtype=torch.bfloat16, device=self.device), 0, 16)
+        s2d = ActView(torch.zeros((self.B, H2, Wp, 48 if self.x3 else 16), dtype=torch.bfloat16, device=self.device), 0, 16, self.x3)
         self.keep.append(s2d.buf)
-        self.steps.append(lambda: ops.space_to_depth(img_getter(), s2d, scale, x_offset=1))
+        if self.x3:
+            inv = 1.0 / scale
+            divisor = float(round(inv)) if abs(inv - round(inv)) < 1e-6 * inv else inv  # 1/255 -> exactly 255
+            self.steps.append(lambda: ops.space_to_depth_x3(img_getter(), s2d, divisor, x_offset=1))
+        else:
+            self.steps.append(lambda: ops.space_to_depth(img_getter(), s2d, scale, x_offset=1))
         self.s2d_step = self.steps[-1]
         w = c.weight.detach().float().to(self.device)
         if name == "Focus":
@@ -215,7 +247,7 @@ class Builder:
         if y is None:
             y = self.new_act(H2, W2, cout)
         bias = c.bias.detach().float().to(self.device) if c.bias is not None else None
-        pair = (y.c0 == 0 and y.cstride == cout and W2 % 2 == 0 and Wp % 2 == 0 and 2 * cout <= 256)
+        pair = (not self.x3 and y.c0 == 0 and y.cstride == cout and W2 % 2 == 0 and Wp % 2 == 0 and 2 * cout <= 256)
         if pair:
             # Two horizontally adjacent output pixels share one 4-pixel window (logical pixels 2x-1 .. 2x+2 are exactly
             # the union of their receptive fields): run the stem as M = pixel pairs, N = 2*cout. The window tile is
@@ -235,8 +267,13 @@ class Builder:
             ww = torch.zeros((cout, 64, 3, 1), device=self.device)  # OIHW with I = 64 window channels, kernel 3x1
             for kwp in range(3):
                 ww[:, kwp * 16:kwp * 16 + 12, :, 0] = w2[:, :, :, kwp]
-            wp, bp = ops.pack_conv_weight(ww, bias, bn, eps)
-            plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2, 16, Wp))
+            if self.x3:  # the window's four pixels are four split-precision segments of 16 channels
+                wp, bp = ops.pack_conv_weight_x3(ww, bias, bn, eps, [(0, 16), (16, 16), (32, 16), (48, 16)])
+                self.mark_segment(y)
+                plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(192, W2, 48, Wp))
+            else:
+                wp, bp = ops.pack_conv_weight(ww, bias, bn, eps)
+                plan = ConvPlan(s2d, y, wp, bp, 3, 1, 1, 1, _act_code(m), pad_w=0, window=(64, W2, 16, Wp))
         self.plans.append(plan)
         self.steps.append(plan.run)
         self.flops += 2.0 * self.B * H2 * W2 * cout * 9 * 12  # == 36 taps x 3 channels of the 6x6 stem
@@ -294,6 +331,21 @@ class Builder:
 
     def c3(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
         c_ = m.conv1.conv.out_channels if isinstance(m.conv1.conv, nn.Conv2d) else m.conv1.conv[-1].out_channels
+        if self.x3:
+            # split precision: a view must be whole producer segments, so the two branches live in their own buffers
+            # (no merged conv1 || conv2 launch) and conv3 reads them as two sources
+            y1 = self.kindle_conv(m.conv1, x)
+            y2 = self.kindle_conv(m.conv2, x)
+            cur = self.bottleneck_seq(m.bottleneck_c3, y1)
+            c3 = m.conv3
+            if not isinstance(c3.conv, nn.Conv2d):
+                raise NotImplementedError("split-precision mode: a decomposed C3.conv3 is not supported")
+            bn, eps = _bn_tuple(getattr(c3, "batch_norm", None))
+            s_, p_ = self._conv_geom(c3.conv)
+            if y is None:
+                y = self.new_act(x.H, x.W, c3.conv.out_channels)
+            self.conv2d(cur, y, c3.conv.weight, c3.conv.bias, bn, eps, _act_code(c3), s_, p_, x2=y2)
+            return y
         cat = self.new_act(x.H, x.W, 2 * c_)
         fusable = (isinstance(m.conv1.conv, nn.Conv2d) and isinstance(m.conv2.conv, nn.Conv2d)
                    and type(m.conv1.activation) is type(m.conv2.activation)
@@ -352,13 +404,21 @@ class Builder:
         cat = self.new_act(x.H, x.W, 4 * c_)
         self.kindle_conv(m.conv1, x, y=cat.slice(0, c_))
         s0, s1, s2, s3 = (cat.slice(i * c_, c_) for i in range(4))
-        self.steps.append(lambda: ops.sppf_pool(s0, s1, s2, s3, ks))
+        if self.x3:
+            for sl in (s1, s2, s3):
+                self.mark_segment(sl)
+            self.steps.append(lambda: ops.sppf_pool_x3(s0, s1, s2, s3, ks))
+        else:
+            self.steps.append(lambda: ops.sppf_pool(s0, s1, s2, s3, ks))
         return self.kindle_conv(m.conv2, cat, y=y)
 
     def upsample(self, m: nn.Module, x: ActView, y: Optional[ActView]) -> ActView:
         assert float(m.scale_factor) == 2.0 and m.mode == "nearest", "only nearest x2 UpSample is on the YOLOv5 path"
         if y is None:
             y = self.new_act(2 * x.H, 2 * x.W, x.c)
+        if self.x3:  # a segment is copied whole: the destination has the source's segment structure
+            for off, wd in self.segments_of(x):
+                self.mark_segment(y.slice(off, wd))
         self.steps.append(lambda: ops.upsample2x(x, y))
         return y
 
@@ -371,7 +431,7 @@ class Engine:
 
     def __init__(self, model: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float32,
                  scale: float = 1.0, want_raw: bool = True, device: Optional[torch.device] = None,
-                 use_graph: bool = True) -> None:
+                 use_graph: bool = True, precision: str = "bf16") -> None:
         if not torch.cuda.is_available():
             raise RuntimeError("ayolov2_b200.Engine needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
@@ -381,7 +441,10 @@ class Engine:
         self.in_dtype, self.scale = in_dtype, scale
         self.input = torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) if use_graph else None
         self._img = self.input
-        b = Builder(batch, self.device)
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"precision {precision!r}: 'bf16' (the product path) or 'bf16x3' (split-precision verification mode)")
+        self.precision = precision
+        b = Builder(batch, self.device, x3=precision == "bf16x3")
         self.b = b
         layers = list(model.model)
         nL = len(layers)
@@ -495,7 +558,11 @@ class Engine:
             anchors_px = m.anchor_grid[i].detach().float().reshape(-1).contiguous().to(self.device)
             b.keep.append(anchors_px)
             stride = float(m.stride[i])
-            b.steps.append(lambda l=logits, a=anchors_px, s=stride, o=off, r=raw: ops.head_decode(l, na, no, s, a, self.pred, o, r))
+            xyxy = bool(getattr(m, "out_xyxy", False))
+            if b.x3 or xyxy:
+                b.steps.append(lambda l=logits, a=anchors_px, s=stride, o=off, r=raw: ops.head_decode2(l, na, no, s, a, self.pred, o, r, xyxy=xyxy))
+            else:
+                b.steps.append(lambda l=logits, a=anchors_px, s=stride, o=off, r=raw: ops.head_decode(l, na, no, s, a, self.pred, o, r))
             self.decode_steps.append(b.steps[-1])
             self.head_logits.append(logits)
             off += na * x.H * x.W
@@ -535,12 +602,20 @@ class Engine:
 # drop-in glue used by the kindle-compatible modules
 # -------------------------------------------------------------------------------------------------
 def _weights_signature(model: nn.Module) -> int:
-    sig = 0
-    for p in model.parameters():
-        sig += p._version + (p.data_ptr() & 0xFFFF)
-    for b_ in model.buffers():
-        sig += b_._version
-    return sig
+    """Hash of (storage address, version counter) of every parameter and buffer: any in-place update, reallocation or
+    re-binding of a tensor changes it (a sum of the fields would let two changes cancel)."""
+    return hash(tuple((t.data_ptr(), t._version) for t in list(model.parameters()) + list(model.buffers())))
+
+
+def set_precision(model: nn.Module, precision: str = "bf16") -> nn.Module:
+    """Arithmetic of `model(x)` in eval mode: "bf16" (product path: bf16 storage, fp32 accumulation) or "bf16x3" (split-
+    precision verification mode: every activation and weight carried as hi + lo bf16 pairs through the same tcgen05
+    kernels, fp32-equivalent results at ~4x the cost; tests/test_precise_gpu.py)."""
+    if precision not in ("bf16", "bf16x3"):
+        raise ValueError(precision)
+    model.__dict__["_ay2_precision"] = precision
+    model.__dict__.get("_engine_cache", {}).clear()
+    return model
 
 
 def forward_model(model: nn.Module, x: torch.Tensor):
@@ -557,13 +632,14 @@ def forward_model(model: nn.Module, x: torch.Tensor):
         x = x.float()
         in_dtype = torch.float32
     B, C_, H, W = x.shape
-    key = (B, H, W, in_dtype, x.device.index)
+    precision = model.__dict__.get("_ay2_precision", "bf16")
+    key = (B, H, W, in_dtype, x.device.index, precision)
     cache = model.__dict__.setdefault("_engine_cache", {})
     sig = _weights_signature(model)
     ent = cache.get(key)
     if ent is None or ent[1] != sig:
         cache.clear()
-        ent = (Engine(model, B, H, W, in_dtype=in_dtype, scale=scale, device=x.device, use_graph=False), sig)
+        ent = (Engine(model, B, H, W, in_dtype=in_dtype, scale=scale, device=x.device, use_graph=False, precision=precision), sig)
         cache[key] = ent
     eng = ent[0]
     pred, raw = eng.run(x)

@@ -41,10 +41,13 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss: torch.Tensor, _g_items):
         preds = ctx.saved_tensors
-        grads = [torch.zeros_like(p) for p in preds]
+        # The kernel writes fp32 at contiguous (cell * no) offsets whatever the dtype / strides of the saved predictions
+        # (fp16 / bf16 heads under autocast, permuted views): launch on contiguous fp32 buffers, hand autograd tensors of
+        # the predictions' own dtype back.
+        grads = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in preds]
         gscale = g_loss.reshape(-1)[:1].float().contiguous()
         ctx.owner._launch(preds, ctx.targets, grads, gscale, balance=ctx.balance)
-        return (None, None, *grads)
+        return (None, None, *[g if g.dtype == p.dtype else g.to(p.dtype) for g, p in zip(grads, preds)])
 
 
 class ComputeLoss:

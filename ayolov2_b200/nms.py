@@ -112,70 +112,148 @@ def nms_boxes(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float) -> to
     return keep[:int(count.item())].long()
 
 
-def _xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
-    """general.py:316-319 with the default ratio / wh / pad, same fp32 operation order."""
-    y = torch.empty_like(x)
-    hw, hh = x[:, 2] / 2, x[:, 3] / 2
-    y[:, 0], y[:, 1], y[:, 2], y[:, 3] = x[:, 0] - hw, x[:, 1] - hh, x[:, 0] + hw, x[:, 1] + hh
-    return y
+class CandidateTable:
+    """The candidate rows of a whole batch in the reference's order (ay2_nms_candidate_table): `rows` fp32 [B, cap, 8] =
+    {x1, y1, x2, y2, conf, cls, 0, 0}, `counts` int32 [B], `max_coord` fp32 [B]. Built with one launch, no host sync; the
+    capacity grows (and the max_nms re-ranking of metrics.py:378-379 is applied) only when the device flags ask for it,
+    which the caller learns at the one synchronisation it needs anyway to size its output list."""
+
+    def __init__(self, pred: torch.Tensor, conf_thres: float, multi_label: bool, classes: Optional[Sequence[int]],
+                 max_nms: int, cap: Optional[int] = None):
+        from . import _lib
+
+        if not pred.is_cuda:
+            raise RuntimeError("ayolov2_b200.nms runs on CUDA tensors only (no CPU fallback)")
+        self.pred = pred.float().contiguous()
+        B, n, no = self.pred.shape
+        nc = no - 5
+        self.B, self.n, self.no = B, n, no
+        self.multi_label = bool(multi_label) and nc > 1
+        self.max_nms = max_nms
+        self.cmask = None
+        if classes is not None:
+            self.cmask = torch.zeros(nc, dtype=torch.uint8, device=pred.device)
+            self.cmask[torch.as_tensor(list(classes), dtype=torch.long, device=pred.device)] = 1
+        self.p = _lib.NmsParams()
+        self.p.batch, self.p.n, self.p.no = B, n, no
+        self.p.conf_thres, self.p.multi_label, self.p.max_nms = float(conf_thres), int(self.multi_label), int(max_nms)
+        full = n * nc if self.multi_label else n
+        self._build(min(full, cap if cap is not None else max(n, 4096)))
+        self._full = full
+
+    def _build(self, cap: int) -> None:
+        from . import _lib
+
+        dev = self.pred.device
+        self.cap = max(int(cap), 1)
+        self.rows = torch.empty((self.B, self.cap, 8), dtype=torch.float32, device=dev)
+        self.counts = torch.empty(self.B, dtype=torch.int32, device=dev)
+        self.max_coord = torch.empty(self.B, dtype=torch.float32, device=dev)
+        self.flags = torch.empty(1, dtype=torch.int32, device=dev)
+        _lib.check(_lib.load().ay2_nms_candidate_table(self.pred.data_ptr(), C_byref(self.p), _lib.ptr(self.cmask),
+                                                       self.rows.data_ptr(), self.cap, self.counts.data_ptr(),
+                                                       self.max_coord.data_ptr(), self.flags.data_ptr(),
+                                                       _lib.current_stream_ptr()), "ay2_nms_candidate_table")
+
+    def settle(self) -> bool:
+        """One host read of the flags. Returns True when the table had to be rebuilt (the caller re-runs its rule)."""
+        f = int(self.flags.item())
+        if not f:
+            return False
+        if f & 1:  # truncated: room for every (row, class) pair
+            self._build(self._full)
+            f = int(self.flags.item())
+        if f & 2:  # more than max_nms candidates somewhere: keep each image's max_nms best, best first (stable)
+            conf = self.rows[:, :, 4].clone()
+            idx = torch.arange(self.cap, device=conf.device)[None, :]
+            conf[idx >= self.counts[:, None]] = -float("inf")
+            order = torch.sort(conf, dim=1, descending=True, stable=True).indices
+            ranked = torch.gather(self.rows, 1, order[:, :, None].expand(-1, -1, 8))
+            over = (self.counts > self.max_nms)[:, None, None]
+            self.rows = torch.where(over, ranked, self.rows).contiguous()
+            self.counts = torch.clamp(self.counts, max=self.max_nms)
+            live = (idx < self.counts[:, None])[:, :, None]
+            self.max_coord = torch.where(live, self.rows[:, :, :4], torch.full_like(self.rows[:, :, :4], -float("inf"))).amax((1, 2))
+            self.flags.zero_()
+        return True
+
+
+def C_byref(x):
+    import ctypes
+
+    return ctypes.byref(x)
+
+
+def _emit(out: torch.Tensor, count: torch.Tensor) -> List[torch.Tensor]:
+    counts = count.tolist()
+    return [out[i, :c].clone() for i, c in enumerate(counts)]
+
+
+def _fast_or_matrix(tab: CandidateTable, rule: str, class_offset: float, iou_thres: float, out_cap: int) -> List[torch.Tensor]:
+    from . import _lib
+
+    lib = _lib.load()
+    while True:
+        dev = tab.rows.device
+        ws = torch.empty((tab.B, tab.cap), dtype=torch.float32, device=dev)
+        cap = max(1, min(out_cap, tab.cap))
+        out = torch.zeros((tab.B, cap, 6), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(tab.B, dtype=torch.int32, device=dev)
+        st = _lib.current_stream_ptr()
+        if rule == "fast_nms":
+            _lib.check(lib.ay2_nms_fast(tab.rows.data_ptr(), tab.counts.data_ptr(), tab.B, tab.cap, float(class_offset),
+                                        float(iou_thres), ws.data_ptr(), out.data_ptr(), cap, cnt.data_ptr(), st), "ay2_nms_fast")
+        else:
+            _lib.check(lib.ay2_nms_matrix(tab.rows.data_ptr(), tab.counts.data_ptr(), tab.B, tab.cap, float(class_offset),
+                                          ws.data_ptr(), out.data_ptr(), cap, cnt.data_ptr(), st), "ay2_nms_matrix")
+        if not tab.settle():
+            return _emit(out, cnt)
+
+
+def _greedy(tab: CandidateTable, conf_thres: float, iou_thres: float, class_separated: bool, max_det: int,
+            coordinate_trick: bool = False) -> ops.NmsWorkspace:
+    """Greedy NMS of the table's batch on the batched kernel (ay2_nms_batched / ay2_nms_batched_scaled): survivors in kept
+    order in `ws.out` / `ws.count`. The kernel draws the same candidates from the prediction tensor as the table holds."""
+    from . import _lib
+
+    B, n, no = tab.B, tab.n, tab.no
+    ws = _workspace(B, n, no, max_det, tab.multi_label, tab.pred.device, max_candidates=tab._full if tab.multi_label else None)
+    p = ws.p
+    p.multi_label = int(tab.multi_label)
+    p.conf_thres, p.iou_thres = float(conf_thres), float(iou_thres)
+    p.agnostic, p.max_nms, p.max_wh = int(not class_separated), int(tab.max_nms), 4096.0
+    fn, extra = ("ay2_nms_batched_scaled", (tab.max_coord.data_ptr(),)) if coordinate_trick else ("ay2_nms_batched", ())
+    _lib.check(getattr(_lib.load(), fn)(tab.pred.data_ptr(), C_byref(p), _lib.ptr(tab.cmask), *extra, ws.ws.data_ptr(),
+                                        ws.ws.numel(), ws.out.data_ptr(), ws.count.data_ptr(), ws.overflow.data_ptr(),
+                                        _lib.current_stream_ptr()), fn)
+    ws._keepalive = (tab,)
+    return ws
+
+
+def _merge(tab: CandidateTable, ws: ops.NmsWorkspace, class_offset: float, iou_thres: float, n_min_excl: int, n_max_excl: int) -> None:
+    from . import _lib
+
+    _lib.check(_lib.load().ay2_nms_merge(tab.rows.data_ptr(), tab.counts.data_ptr(), tab.B, tab.cap, float(class_offset),
+                                         float(iou_thres), n_min_excl, n_max_excl, ws.out.data_ptr(), ws.out.shape[1],
+                                         ws.count.data_ptr(), _lib.current_stream_ptr()), "ay2_nms_merge")
 
 
 def _nms_other_types(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nms_type) -> list:
-    """The non-default nms_type branches of metrics.py:388-431 ("batched_nms", "fast_nms", "matrix_nms", "merge_nms"):
-    per image, candidate rows in the reference's order (metrics.py:337-379), then the branch's matrix arithmetic on the
-    CUDA IoU matrix (ay2_box_iou) / box-list NMS (ay2_nms_boxes). Device tensors throughout; these are diagnostic
-    variants in the reference (the validator and val.py use "nms"), so they are not batched across images."""
-    if not prediction.is_cuda:
-        raise RuntimeError("ayolov2_b200.nms runs on CUDA tensors only (no CPU fallback)")
-    pred = prediction.float()
-    nc = pred.shape[2] - 5
-    max_wh, max_nms = 4096.0, 30000  # metrics.py:326-327
-    multi_label = bool(multi_label) and nc > 1
-    out = [torch.zeros((0, 6), device=pred.device)] * pred.shape[0]
-    for xi in range(pred.shape[0]):
-        x = pred[xi]
-        x = x[x[:, 4] > conf_thres].clone()                                       # :313,337
-        if not x.shape[0]:
-            continue
-        x[:, 5:] *= x[:, 4:5]                                                     # :353
-        box = _xywh2xyxy(x[:, :4])                                                # :356
-        if multi_label:                                                           # :359-361
-            i, j = (x[:, 5:] > conf_thres).nonzero(as_tuple=False).T
-            x = torch.cat((box[i], x[i, j + 5, None], j[:, None].float()), 1)
-        else:                                                                     # :362-364
-            conf, j = x[:, 5:].max(1, keepdim=True)
-            x = torch.cat((box, conf, j.float()), 1)[conf.view(-1) > conf_thres]
-        if classes is not None:                                                   # :367-368
-            x = x[(x[:, 5:6] == torch.tensor(classes, device=x.device)).any(1)]
-        n = x.shape[0]
-        if not n:
-            continue
-        if n > max_nms:                                                           # :378-379
-            x = x[x[:, 4].argsort(descending=True)[:max_nms]]
-        if nms_type == "batched_nms":      # :391-394 (torchvision's coordinate trick: offset = class * (max coordinate + 1))
-            c = x[:, 5] * 0 if agnostic else x[:, 5]
-            boxes = x[:, :4] + (c * (x[:, :4].max() + 1))[:, None]
-            out[xi] = x[nms_boxes(boxes, x[:, 4], iou_thres)[:max_det]]
-        elif nms_type == "fast_nms":       # :397-401
-            c = x[:, 5] * 0 if agnostic else x[:, 5]
-            boxes = x[:, :4] + c.view(-1, 1) * max_wh
-            iou = box_iou(boxes, boxes).triu_(diagonal=1)
-            out[xi] = x[iou.max(0)[0] < iou_thres][:max_det]
-        elif nms_type == "matrix_nms":     # :404-413
-            iou = box_iou(x[:, :4], x[:, :4]).triu_(diagonal=1)
-            m = iou.max(0)[0].view(-1, 1)
-            x[:, 4] *= torch.exp(-(iou ** 2 - m ** 2) / 0.5).min(0)[0]
-            out[xi] = x[:max_det]
-        else:                              # merge_nms, :414-431
-            boxes, scores = x[:, :4] + x[:, 5:6] * (0 if agnostic else max_wh), x[:, 4]
-            i = nms_boxes(boxes, scores, iou_thres)[:max_det]
-            if 1 < n < 3e3:
-                hit = box_iou(boxes[i], boxes) > iou_thres
-                weights = hit * scores[None]
-                x[i, :4] = torch.mm(weights, x[:, :4]).float() / weights.sum(1, keepdim=True)
-                i = i[hit.sum(1) > 1]      # redundant = True (:326)
-            out[xi] = x[i]
-    return out
+    """nms_type "batched_nms" / "fast_nms" / "matrix_nms" / "merge_nms" of non_max_suppression (metrics.py:388-431), the
+    whole batch per launch (csrc/nms_variants.cu); the single host synchronisation is the read of the per-image counts."""
+    tab = CandidateTable(prediction, conf_thres, multi_label, classes, max_nms=30000)
+    sep = 0.0 if agnostic else 4096.0  # metrics.py:326 max_wh
+    if nms_type == "fast_nms":
+        return _fast_or_matrix(tab, nms_type, sep, iou_thres, max_det)
+    if nms_type == "matrix_nms":
+        return _fast_or_matrix(tab, nms_type, 0.0, iou_thres, max_det)  # metrics.py:405: the boxes are not class-separated
+    while True:
+        ws = _greedy(tab, conf_thres, iou_thres, class_separated=not agnostic, max_det=max_det,
+                     coordinate_trick=nms_type == "batched_nms")
+        if nms_type == "merge_nms":
+            _merge(tab, ws, sep, iou_thres, 1, 3000)
+        if not tab.settle():
+            return _emit(ws.out, ws.count)
 
 
 def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
@@ -193,31 +271,54 @@ def box_iou(box1: torch.Tensor, box2: torch.Tensor) -> torch.Tensor:
 
 def batched_nms(prediction: torch.Tensor, conf_thres: float = 0.001, iou_thres: float = 0.65, nms_box: int = 500,
                 agnostic: bool = False, nms_type: str = "nms") -> List[torch.Tensor]:
-    """Reference signature of scripts/utils/nms.py:15-116 (the val2.py path), nms_type "nms".
+    """Reference signature of scripts/utils/nms.py:15-116 (the val2 path), every nms_type.
 
     The reference keeps the `nms_box` rows of highest objectness per image (:41-42), scores every (row, class) pair
-    conf = cls * obj > conf_thres (:45-47) and runs torchvision NMS per image -- class-separated (offset 4096 * class) only
-    when `agnostic` is True, plain otherwise (:58-62; the flag is inverted relative to non_max_suppression). That is the
-    multi-label candidate generation + greedy suppression of ay2_nms_batched on the gathered (B, nms_box, no) rows with
-    the agnostic flag flipped and no max_det / max_nms cut, so the batch runs in the same fixed number of launches.
-    Candidate order (row in objectness order, then class) is the reference's, which fixes torchvision's stable tie order.
-    """
-    if nms_type != "nms":
-        raise NotImplementedError(f"nms_type={nms_type!r}: only 'nms' runs on the B200 kernels (box_iou is available for the others)")
+    conf = cls * obj > conf_thres (:45-47) and then applies the chosen rule per image -- for "nms" / "merge_nms" class-
+    separated (offset 4096 * class) only when `agnostic` is True (:58-62; the flag is inverted relative to
+    non_max_suppression), for "fast_nms" / "matrix_nms" always class-separated (:75,84), for "batched_nms" through
+    torchvision's coordinate trick. Here the gathered (B, nms_box, no) rows go through the same batched kernels as
+    non_max_suppression (multi-label candidate rule, no max_det / max_nms cut). The reference has no bound on the number
+    of survivors; images that fill the batched kernel's 1024-entry kept list are finished by the unbounded box-list NMS
+    (ay2_nms_boxes), so nothing is truncated."""
+    if nms_type not in ("nms", "batched_nms", "fast_nms", "matrix_nms", "merge_nms"):
+        raise AssertionError("Wrong NMS type!!")
     if not prediction.is_cuda:
         raise RuntimeError("ayolov2_b200.nms runs on CUDA tensors only (no CPU fallback)")
     pred = prediction.float()
     B, n, no = pred.shape
     nc = no - 5
     k = min(nms_box, n)
-    idx = pred[:, :, 4].argsort(descending=True)[:, :k]                      # nms.py:41 (same call, same tie behaviour)
+    idx = pred[:, :, 4].argsort(descending=True)[:, :k]                         # nms.py:41 (same call, same tie behaviour)
     top = torch.gather(pred, 1, idx[:, :, None].expand(B, k, no)).contiguous()  # nms.py:42
-    cap = 1024  # kMaxDetCap of the kernel
-    ws = _workspace(B, k, no, cap, True, pred.device, max_candidates=k * nc)
-    ws.p.multi_label = 1
-    ws.run(top, conf_thres, iou_thres, agnostic=not agnostic, max_nms=k * nc)
-    ws._keepalive = (top,)
+    tab = CandidateTable(top, conf_thres, True, None, max_nms=k * max(nc, 1), cap=k * max(nc, 1))
+    if nms_type in ("fast_nms", "matrix_nms"):
+        return _fast_or_matrix(tab, nms_type, 4096.0, iou_thres, tab.cap)
+    cap = 1024  # kept-list capacity of the batched kernel
+    ws = _greedy(tab, conf_thres, iou_thres, class_separated=(agnostic or nms_type == "batched_nms"), max_det=cap,
+                 coordinate_trick=nms_type == "batched_nms")
+    full = (ws.count >= cap)
+    if nms_type == "merge_nms":
+        _merge(tab, ws, 4096.0 if agnostic else 0.0, iou_thres, -1, 1 << 30)
     counts = ws.count.tolist()
-    if max(counts, default=0) >= cap:
-        raise NotImplementedError(f"an image kept >= {cap} boxes; raise conf_thres (the kernel's survivor list holds {cap})")
-    return [ws.out[i, :c].clone() for i, c in enumerate(counts)]
+    out = [ws.out[i, :c].clone() for i, c in enumerate(counts)]
+    for i in torch.nonzero(full).flatten().tolist():  # more than 1024 survivors: unbounded route for this image
+        out[i] = _unbounded_image(tab, i, iou_thres, agnostic, nms_type)
+    return out
+
+
+def _unbounded_image(tab: CandidateTable, i: int, iou_thres: float, agnostic: bool, nms_type: str) -> torch.Tensor:
+    """One image of the val2 path whose survivors exceed the batched kernel's kept list: box-list NMS without a bound."""
+    n = int(tab.counts[i])
+    x = tab.rows[i, :n, :6].clone()
+    if nms_type == "batched_nms":
+        boxes = x[:, :4] + (x[:, 5] * (x[:, :4].max() + 1))[:, None]
+    else:
+        boxes = x[:, :4] + x[:, 5:6] * 4096.0 if agnostic else x[:, :4]
+    keep = nms_boxes(boxes.contiguous(), x[:, 4], iou_thres)
+    if nms_type == "merge_nms":
+        hit = box_iou(boxes[keep], boxes) > iou_thres
+        w = hit * x[None, :, 4]
+        x[keep, :4] = (w @ x[:, :4]) / w.sum(1, keepdim=True)
+        keep = keep[hit.sum(1) > 1]
+    return x[keep]

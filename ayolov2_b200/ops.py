@@ -17,11 +17,16 @@ from ._lib import ACT_NONE, ACT_SILU, ChainDesc, ConvDesc, HeadLevels, NmsParams
 
 @dataclass
 class ActView:
-    """A channel slice [c0, c0+c) of an NHWC bf16 buffer of shape [B, H, W, Cs]."""
+    """A channel slice [c0, c0+c) of an NHWC bf16 buffer of shape [B, H, W, Cs].
+
+    x3 = split-precision layout (include/ay2.h, ay2_conv_desc::x3): c0 / c stay LOGICAL channel numbers; every producer's
+    output segment of w channels occupies 3 w physical channels [hi | lo | hi], so logical offset c0 sits at physical 3 c0
+    (views are only ever cut at segment boundaries) and the buffer's last dimension is 3x the logical width."""
 
     buf: torch.Tensor
     c0: int
     c: int
+    x3: bool = False
 
     @property
     def B(self) -> int:
@@ -39,20 +44,32 @@ class ActView:
     def cstride(self) -> int:
         return self.buf.shape[3]
 
+    @property
+    def pc(self) -> int:
+        """physical channels of the view"""
+        return 3 * self.c if self.x3 else self.c
+
     def ptr(self) -> int:
-        return self.buf.data_ptr() + 2 * self.c0
+        return self.buf.data_ptr() + 2 * (3 * self.c0 if self.x3 else self.c0)
 
     def tensor(self) -> torch.Tensor:
+        assert not self.x3, "a split-precision view has no plain tensor form (use value_f32 on a single segment)"
         return self.buf[..., self.c0:self.c0 + self.c]
+
+    def value_f32(self) -> torch.Tensor:
+        """fp32 [B, H, W, c] of a view that is ONE split-precision segment: hi + lo."""
+        assert self.x3
+        p0 = 3 * self.c0
+        return self.buf[..., p0:p0 + self.c].float() + self.buf[..., p0 + self.c:p0 + 2 * self.c].float()
 
     def slice(self, c0: int, c: int) -> "ActView":
         assert 0 <= c0 and c0 + c <= self.c
-        return ActView(self.buf, self.c0 + c0, c)
+        return ActView(self.buf, self.c0 + c0, c, self.x3)
 
 
-def new_act(B: int, H: int, W: int, C_: int, device="cuda") -> ActView:
+def new_act(B: int, H: int, W: int, C_: int, device="cuda", x3: bool = False) -> ActView:
     assert C_ % 8 == 0
-    return ActView(torch.empty((B, H, W, C_), dtype=torch.bfloat16, device=device), 0, C_)
+    return ActView(torch.empty((B, H, W, 3 * C_ if x3 else C_), dtype=torch.bfloat16, device=device), 0, C_, x3)
 
 
 def conv_block_n(cout: int) -> int:
@@ -84,6 +101,37 @@ def pack_conv_weight(w: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional
     return wp.contiguous(), bp.contiguous()
 
 
+def pack_conv_weight_x3(w: torch.Tensor, bias: Optional[torch.Tensor], bn: Optional[Tuple[torch.Tensor, ...]], eps: float,
+                        segs: Sequence[Tuple[int, int]]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Split-precision weights: the BN-folded fp32 weight w = w_hi + w_lo (both bf16) laid out along K to meet the input's
+    segment planes: for every input segment (offset, width): [w_hi | w_hi | w_lo] of its channels. segs must tile cin."""
+    w = w.detach().float()
+    cout, cin, kh, kw = w.shape
+    if bn is not None:
+        gamma, beta, mean, var = [t.detach().float() for t in bn]
+        scale = gamma / torch.sqrt(var + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = beta - mean * scale
+        if bias is not None:
+            b = b + bias.detach().float() * scale
+    else:
+        b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    assert sum(wd for _, wd in segs) == cin and [o for o, _ in segs] == [sum(wd for _, wd in segs[:i]) for i in range(len(segs))], segs
+    hi = w.to(torch.bfloat16).float()
+    lo = (w - hi).to(torch.bfloat16).float()
+    parts = []
+    for off, wd in segs:
+        parts += [hi[:, off:off + wd], hi[:, off:off + wd], lo[:, off:off + wd]]
+    w3 = torch.cat(parts, 1)
+    bn_tile = conv_block_n(cout)
+    cout_pad = (cout + bn_tile - 1) // bn_tile * bn_tile
+    wp = torch.zeros((cout_pad, kh * kw * 3 * cin), dtype=torch.bfloat16, device=w.device)
+    wp[:cout] = w3.permute(0, 2, 3, 1).reshape(cout, -1).to(torch.bfloat16)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    bp[:cout] = b
+    return wp.contiguous(), bp.contiguous()
+
+
 class ConvPlan:
     """ay2_conv_plan: fused conv + bias + act (+ residual) between two ActViews. Keeps its tensors alive."""
 
@@ -98,8 +146,10 @@ class ConvPlan:
         `x2`: second input view; the conv consumes torch.cat([x, x2], channel) without the concatenation existing."""
         lib = _lib.load()
         cout_pad, ktot = w_packed.shape
-        cin = window[0] if window else x.c + (x2.c if x2 is not None else 0)
+        cin = window[0] if window else x.pc + (x2.pc if x2 is not None else 0)
         assert ktot == kh * kw * cin, (ktot, kh, kw, cin)
+        x3 = y.x3
+        assert x.x3 == x3 and (x2 is None or x2.x3 == x3) and (residual is None or residual.x3 == x3)
         assert w_packed.dtype == torch.bfloat16 and bias.dtype == torch.float32 and bias.numel() == cout_pad
         assert x.buf.is_cuda and y.buf.is_cuda and w_packed.is_cuda and bias.is_cuda
         d = ConvDesc()
@@ -108,7 +158,7 @@ class ConvPlan:
         d.pad_w = pad_w
         if x2 is not None:
             assert window is None and (x2.B, x2.H, x2.W) == (x.B, x.H, x.W) and x2.buf.is_cuda
-            d.cin_split, d.in2_cstride, d.in2 = x.c, x2.cstride, x2.ptr()
+            d.cin_split, d.in2_cstride, d.in2 = x.pc, x2.cstride, x2.ptr()
         if window:
             d.cin, d.in_w, d.in_pix_stride, d.in_row_pixels = window
         d.out_h, d.out_w, d.cout, d.out_cstride = y.H, y.W, y.c, y.cstride
@@ -126,6 +176,8 @@ class ConvPlan:
         d.kh, d.kw, d.stride, d.pad, d.act = kh, kw, stride, pad, act
         d.res_cstride = residual.cstride if residual is not None else 0
         d.cout_pad = cout_pad
+        d.x3 = int(x3)
+        assert not (x3 and out_sub is not None)
         self.desc = d
         self.x, self.y, self.w, self.b, self.res, self.x2 = x, y, w_packed, bias, residual, x2
         h = C.c_void_p()
@@ -263,9 +315,35 @@ def sppf_pool(x: ActView, o1: ActView, o2: ActView, o3: ActView, ks: Sequence[in
 
 
 def upsample2x(x: ActView, y: ActView) -> None:
-    assert (y.H, y.W, y.c) == (2 * x.H, 2 * x.W, x.c)
-    _lib.check(_lib.load().ay2_upsample2x(x.ptr(), x.B, x.H, x.W, x.c, x.cstride, y.ptr(), y.cstride,
+    assert (y.H, y.W, y.c) == (2 * x.H, 2 * x.W, x.c) and x.x3 == y.x3
+    _lib.check(_lib.load().ay2_upsample2x(x.ptr(), x.B, x.H, x.W, x.pc, x.cstride, y.ptr(), y.cstride,
                                           _lib.current_stream_ptr()), "ay2_upsample2x")
+
+
+def space_to_depth_x3(img: torch.Tensor, out: ActView, divisor: float, x_offset: int = 0) -> None:
+    """Split-precision space-to-depth: out.buf [B, H/2, Wp, 48] = planes [hi16 | lo16 | hi16] of img / divisor."""
+    assert img.is_cuda and img.is_contiguous() and img.shape[1] == 3 and out.x3 and out.buf.shape[3] == 48
+    B, _, H, W = img.shape
+    dt = {torch.uint8: _lib.DT_U8, torch.float32: _lib.DT_F32}[img.dtype]
+    _lib.check(_lib.load().ay2_space_to_depth_x3(img.data_ptr(), dt, B, H, W, float(divisor), out.buf.data_ptr(), out.W, x_offset,
+                                                 _lib.current_stream_ptr()), "ay2_space_to_depth_x3")
+
+
+def sppf_pool_x3(x: ActView, o1: ActView, o2: ActView, o3: ActView, ks: Sequence[int]) -> None:
+    assert x.x3 and x.cstride == o1.cstride == o2.cstride == o3.cstride and x.buf is o1.buf
+    _lib.check(_lib.load().ay2_sppf_pool_x3(x.ptr(), x.B, x.H, x.W, x.c, x.cstride, ks[0], ks[1], ks[2], o1.ptr(), o2.ptr(),
+                                            o3.ptr(), _lib.current_stream_ptr()), "ay2_sppf_pool_x3")
+
+
+def head_decode2(logits: ActView, na: int, no: int, stride_px: float, anchor_wh_px: torch.Tensor, pred: torch.Tensor,
+                 row_offset: int, raw: Optional[torch.Tensor], xyxy: bool = False) -> None:
+    """General head decode: split-precision logits (hi + lo planes, exact sigmoid) and / or x1 y1 x2 y2 boxes."""
+    assert logits.c0 == 0 and pred.dtype == torch.float32 and pred.is_contiguous() and pred.shape[2] == no
+    flags = (1 if xyxy else 0) | (2 if logits.x3 else 0)
+    _lib.check(_lib.load().ay2_head_decode2(logits.ptr(), logits.c if logits.x3 else 0, logits.B, logits.H, logits.W,
+                                            logits.cstride, na, no, float(stride_px), anchor_wh_px.data_ptr(), flags,
+                                            pred.data_ptr(), pred.shape[1], row_offset, _lib.ptr(raw),
+                                            _lib.current_stream_ptr()), "ay2_head_decode2")
 
 
 def head_decode(logits: ActView, na: int, no: int, stride_px: float, anchor_wh_px: torch.Tensor, pred: torch.Tensor,
@@ -448,6 +526,10 @@ def sgd_ema_step(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema
     _lib.check(_lib.load().ay2_sgd_ema_step(param.data_ptr(), grad.data_ptr(), mom.data_ptr(), _lib.ptr(ema), param.numel(),
                                             float(lr), float(momentum), float(weight_decay), int(nesterov), float(ema_decay),
                                             _lib.ptr(inv_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step")
+    # the kernel writes through raw pointers: tell autograd / the compiled-engine cache that these tensors changed
+    for t in (param, mom, ema):
+        if t is not None:
+            torch._C._increment_version(t)
 
 
 def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):

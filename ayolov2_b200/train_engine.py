@@ -477,6 +477,10 @@ class TrainEngine:
             b()
 
     def forward(self, img: torch.Tensor) -> List[torch.Tensor]:
+        # Activations, batch statistics and gradient buffers are ONE static set per engine: a backward is only valid for
+        # the most recent forward. The generation counter lets TrainFunction.backward detect fwd/fwd/bwd/bwd patterns
+        # (two views summed into one loss, KD double passes) instead of silently differentiating the wrong activations.
+        self.generation = getattr(self, "generation", 0) + 1
         self.static_in.copy_(img)
         self._img = self.static_in
         self._run_or_replay("fwd", self._forward_body)
@@ -499,11 +503,22 @@ class TrainFunction(torch.autograd.Function):
         ctx.engine = engine
         ctx.params = params
         outs = engine.forward(x)
+        ctx.generation = engine.generation
+        ctx.consumed = False
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts: torch.Tensor):
         eng: TrainEngine = ctx.engine
+        if ctx.generation != eng.generation:
+            raise RuntimeError(
+                "ayolov2_b200 training forward keeps ONE set of activations per (batch, H, W): this backward belongs to "
+                f"forward #{ctx.generation} but forward #{eng.generation} has overwritten them. Call loss.backward() before "
+                "the next model(x) in train mode (or concatenate the views into one batch).")
+        if ctx.consumed:
+            raise RuntimeError("ayolov2_b200 training forward cannot be back-propagated twice (retain_graph): the static "
+                               "gradient buffers of the first backward have been consumed")
+        ctx.consumed = True
         pg = eng.backward([g if g is not None else torch.zeros_like(o) for g, o in zip(gouts, eng.head_out)])
         grads = tuple(pg.get(id(p)) if p.requires_grad else None for p in ctx.params)
         return (None, None) + grads

@@ -38,6 +38,8 @@ extern "C" {
 
 int ay2_version(void);
 const char* ay2_last_error_string(void);
+/* sha256 (hex) of the sources + compile flags this binary was built from; the Python loader compares it with the tree. */
+const char* ay2_source_hash(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t ay2_launch_count(void);
 
@@ -76,6 +78,12 @@ typedef struct ay2_conv_desc {
                              from `in2` -- torch.cat([a, b], 1) resolved by the consumer when a and b live in different
                              buffers (kindle C3 conv3 after out-of-place fused bottlenecks) */
   int32_t in2_cstride;    /* channel stride of the second input buffer */
+  int32_t x3;             /* 1: split-precision ("bf16x3") verification mode. Every activation tensor is stored as the planes
+                             [hi | lo | hi] (hi = bf16(v), lo = bf16(v - hi)) of each producer's output segment and weights
+                             as [w_hi | w_hi | w_lo] along K, so `cin` counts 3x the logical input channels and the main
+                             loop is unchanged; the epilogue applies the exact SiLU, splits, and writes the three planes of
+                             `cout` channels each at out, out + cout, out + 2 cout (the residual is read as hi + lo from
+                             residual, residual + cout). fp32-equivalent accuracy on the tcgen05 path; ~4x the work. */
   const void* in2;        /* second input (device pointer, same batch / height / width), NULL when cin_split == 0 */
 } ay2_conv_desc;
 
@@ -169,6 +177,21 @@ int ay2_head_decode(const void* logits, int32_t batch, int32_t ny, int32_t nx, i
                     int32_t no, float stride_px, const float* anchor_wh_px /* [na*2] device */, float* pred,
                     int64_t total_rows, int64_t row_offset, float* raw, void* stream);
 
+/* Split-precision ("bf16x3", ay2_conv_desc::x3) forms of the data-movement layers, and the general head decode
+ * (csrc/precise.cu). A tensor of C channels is three planes [hi | lo | hi] of C channels; pointers address plane 0.
+ *   ay2_space_to_depth_x3: out [batch, h/2, out_row_pixels, 48] = planes of the 16-channel pixel; value = pixel / divisor.
+ *   ay2_sppf_pool_x3:      as ay2_sppf_pool on split-precision segments of `c` channels (max of hi + lo, re-split).
+ *   ay2_head_decode2:      ay2_head_decode with lo_offset > 0: logits = plane 0 + the plane lo_offset channels further;
+ *                          flags bit 0: boxes as x1 y1 x2 y2 (YOLOHead.out_xyxy); bit 1: exact fp32 sigmoid.
+ * Upsample needs no special form (a split-precision segment is copied like 3 c ordinary channels). */
+int ay2_space_to_depth_x3(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float divisor, void* out,
+                          int32_t out_row_pixels, int32_t out_x_offset, void* stream);
+int ay2_sppf_pool_x3(const void* in, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t cstride, int32_t k1, int32_t k2,
+                     int32_t k3, void* out1, void* out2, void* out3, void* stream);
+int ay2_head_decode2(const void* logits, int32_t lo_offset, int32_t batch, int32_t ny, int32_t nx, int32_t cstride, int32_t na,
+                     int32_t no, float stride_px, const float* anchor_wh_px, int32_t flags, float* pred, int64_t total_rows,
+                     int64_t row_offset, float* raw, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched NMS: replaces scripts/utils/metrics.py:285-443 non_max_suppression(nms_type="nms") and the
  * torchvision.ops.nms call at :385 for the whole batch in a fixed number of launches.
@@ -237,6 +260,34 @@ int ay2_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, floa
  * Greedy suppression IoU > iou_thres with the reference's fp32 IoU and its comparison against the double threshold. */
 int ay2_nms_boxes(const float* boxes, const int32_t* order, int32_t n, double iou_thres, unsigned long long* mask_ws,
                   int32_t* keep, int32_t* count, void* stream);
+
+/* The non-default suppression rules, batched over images (csrc/nms_variants.cu): replace the per-image host loops and n x n
+ * IoU matrices of scripts/utils/metrics.py:388-431 (nms_type "batched_nms" / "fast_nms" / "matrix_nms" / "merge_nms") and of
+ * scripts/utils/nms.py:63-110 (the same rules on the val2 path).
+ *   ay2_nms_candidate_table: pred fp32 [B, n, no] -> table fp32 [B][cap][8] = {x1, y1, x2, y2, conf, cls, 0, 0} in the
+ *     reference's candidate order (metrics.py:337-368; p->conf_thres / multi_label / max_nms are used), counts int32 [B],
+ *     max_coord fp32 [B] (largest box coordinate among an image's candidates), flags int32 [1]: bit 0 = some image had
+ *     more than `cap` candidates (table truncated), bit 1 = some image had more than p->max_nms (metrics.py:378-379 applies).
+ *   ay2_nms_fast:   survivors = rows no EARLIER row overlaps with IoU >= iou_thres (fp32 compare), table order, first out_cap.
+ *   ay2_nms_matrix: every row, conf scaled by the gaussian (sigma 0.5) matrix-NMS decay; first out_cap rows.
+ *     class_offset: boxes are shifted by cls * class_offset before the IoU (0 = class-agnostic / no separation);
+ *     colmax_ws: fp32 [B][cap] scratch. out_det fp32 [B][out_cap][6], out_count int32 [B].
+ *   ay2_nms_merge: det / det_count hold greedy-NMS survivors in kept order (ay2_nms_batched output, det_cap <= 1024); every
+ *     survivor's box becomes the conf-weighted mean of the candidates overlapping it (IoU > iou_thres) and survivors with
+ *     no second supporter are dropped, for images with n_min_excl < candidates < n_max_excl (metrics.py:420: 1 < n < 3000).
+ *   ay2_nms_batched_scaled: ay2_nms_batched with the class offset of torchvision.ops.boxes.batched_nms: max_coord[b] + 1
+ *     per image (metrics.py:391-394) instead of p->max_wh. */
+int ay2_nms_candidate_table(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, float* table, int32_t cap,
+                            int32_t* counts, float* max_coord, int32_t* flags, void* stream);
+int ay2_nms_fast(const float* table, const int32_t* counts, int32_t batch, int32_t cap, float class_offset, float iou_thres,
+                 float* colmax_ws, float* out_det, int32_t out_cap, int32_t* out_count, void* stream);
+int ay2_nms_matrix(const float* table, const int32_t* counts, int32_t batch, int32_t cap, float class_offset, float* colmax_ws,
+                   float* out_det, int32_t out_cap, int32_t* out_count, void* stream);
+int ay2_nms_merge(const float* table, const int32_t* counts, int32_t batch, int32_t cap, float class_offset, float iou_thres,
+                  int32_t n_min_excl, int32_t n_max_excl, float* det, int32_t det_cap, int32_t* det_count, void* stream);
+int ay2_nms_batched_scaled(const float* pred, const ay2_nms_params* p, const uint8_t* class_mask, const float* max_coord,
+                           void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
+                           void* stream);
 
 /* Validation statistics: replaces the per-image host loop of YoloValidator.statistics_per_image / process_batch
  * (scripts/utils/train_utils.py:294-401) for a whole batch. det / counts: the NMS output ([batch][max_det][6], [batch]);

@@ -101,6 +101,11 @@ def _evb_sigma2(sigma2: float, L: int, M: int, s: np.ndarray, residual: float, x
 
 def evbmf_rank(Y: np.ndarray) -> int:
     """Number of singular values EVBMF keeps (= `diag.shape[0]` at decomposition.py:356-359), sigma2 estimated."""
+    return evbmf_rank_sigma2(Y)[0]
+
+
+def evbmf_rank_sigma2(Y: np.ndarray):
+    """(rank, estimated noise variance) of decomposition.py:81-206 with sigma2 = None, H = None."""
     from scipy.optimize import minimize_scalar
 
     L, M = Y.shape
@@ -116,7 +121,7 @@ def evbmf_rank(Y: np.ndarray) -> int:
     opt = minimize_scalar(_evb_sigma2, args=(L, M, s, residual, xubar), bounds=[lower, upper], method="Bounded")
     sigma2 = opt.x
     threshold = np.sqrt(M * sigma2 * (1 + tauubar) * (1 + alpha / tauubar))
-    return int(np.sum(s > threshold))
+    return int(np.sum(s > threshold)), float(sigma2)
 
 
 def estimate_ranks(weight: torch.Tensor) -> List[int]:

@@ -8,7 +8,7 @@ A plain numpy/torch-CPU restatement of
                                        "matrix_nms", "merge_nms")
   * scripts/utils/metrics.py:138-164   box_iou
   * scripts/utils/general.py:297-321   xywh2xyxy
-  * scripts/utils/nms.py:15-116        batched_nms (val2 path, nms_type "nms")
+  * scripts/utils/nms.py:15-116        batched_nms (val2 path, every nms_type)
   * torchvision.ops.nms (torchvision 0.10.1 pinned by environment.yml:28; 0.26 behaves the same): stable
     descending score sort, greedy suppression with fp32 IoU = inter / (area_i + area_j - inter), strict `>`.
 
@@ -162,11 +162,13 @@ def non_max_suppression(prediction: torch.Tensor, conf_thres: float = 0.25, iou_
 
 
 def batched_nms(prediction: torch.Tensor, conf_thres: float = 0.001, iou_thres: float = 0.65, nms_box: int = 500,
-                agnostic: bool = False) -> List[torch.Tensor]:
-    """nms.py:15-116 restated for nms_type "nms" (note: class offsets are applied only when `agnostic`, :58-62)."""
+                agnostic: bool = False, nms_type: str = "nms") -> List[torch.Tensor]:
+    """nms.py:15-116 restated, every nms_type (note: for "nms" / "merge_nms" class offsets are applied only when
+    `agnostic`, :58-62; "fast_nms" / "matrix_nms" always offset by 4096 * class, :75,84)."""
     pred = prediction.detach().cpu().float().numpy()
     out: List[torch.Tensor] = []
     conf_t = np.float32(conf_thres)
+    thr32 = np.float32(iou_thres)
     for xi in range(pred.shape[0]):
         x = pred[xi]
         idx = np.argsort(-x[:, 4], kind="stable")[:nms_box]  # :41
@@ -177,12 +179,43 @@ def batched_nms(prediction: torch.Tensor, conf_thres: float = 0.001, iou_thres: 
         two = np.float32(2.0)
         box = np.stack((xywh[:, 0] - xywh[:, 2] / two, xywh[:, 1] - xywh[:, 3] / two, xywh[:, 0] + xywh[:, 2] / two,
                         xywh[:, 1] + xywh[:, 3] / two), 1).astype(np.float32)  # :50-54
-        det = np.concatenate((box, confs[j, k, None], k[:, None].astype(np.float32)), 1)
+        det = np.concatenate((box, confs[j, k, None], k[:, None].astype(np.float32)), 1).astype(np.float32)
         if agnostic:  # :58-60 (sic)
-            bboxes = det[:, :4] + det[:, 5:6] * np.float32(4096)
+            bboxes = (det[:, :4] + det[:, 5:6] * np.float32(4096)).astype(np.float32)
         else:
             bboxes = det[:, :4]
-        keep = greedy_nms(bboxes.astype(np.float32), det[:, 4], iou_thres)
+        if nms_type == "nms":  # :64-65
+            keep = greedy_nms(bboxes, det[:, 4], iou_thres)
+        elif nms_type == "batched_nms":  # :68-72 -> torchvision coordinate trick on the un-offset boxes
+            if det.shape[0] == 0:
+                keep = np.zeros((0,), dtype=np.int64)
+            else:
+                off = det[:, 5] * (det[:, :4].max() + np.float32(1))
+                keep = greedy_nms((det[:, :4] + off[:, None]).astype(np.float32), det[:, 4], iou_thres)
+        elif nms_type in ("fast_nms", "matrix_nms"):  # :75-99
+            if det.shape[0] == 0:  # `continue` at :80 / :91 leaves the (empty) candidate rows in place
+                out.append(torch.from_numpy(det))
+                continue
+            sep = (det[:, :4] + det[:, 5:6] * np.float32(4096)).astype(np.float32)
+            iou = np.triu(box_iou(sep, sep), k=1)
+            if nms_type == "fast_nms":
+                keep = np.nonzero(iou.max(0) < thr32)[0]
+            else:
+                m = iou.max(0)[:, None]
+                decay = torch.exp(torch.from_numpy(-(iou ** 2 - m ** 2) / np.float32(0.5))).numpy().min(0)
+                det = det.copy()
+                det[:, 4] *= decay
+                keep = np.arange(det.shape[0])
+        elif nms_type == "merge_nms":  # :101-110
+            keep = greedy_nms(bboxes, det[:, 4], iou_thres)
+            if det.shape[0]:
+                hit = box_iou(bboxes[keep], bboxes) > thr32
+                weights = hit * det[None, :, 4]
+                det = det.copy()
+                det[keep, :4] = (weights @ det[:, :4]).astype(np.float32) / weights.sum(1, keepdims=True)
+                keep = keep[hit.sum(1) > 1]
+        else:
+            raise NotImplementedError(nms_type)
         out.append(torch.from_numpy(det[keep].astype(np.float32)))
     return out
 

@@ -11,6 +11,8 @@ size-independent properties, plus the oracle on a slice the CPU finishes in seco
 import pytest
 import torch
 
+from _parity import errs, record
+
 pytestmark = pytest.mark.gpu
 CONF, IOU = 0.25, 0.45
 
@@ -54,25 +56,34 @@ def test_full_size_batch_properties():
 
 
 def test_full_size_images_against_oracle():
-    """Two of the benchmark's 640 x 640 images: head logits and decoded predictions of the CUDA forward vs the fp32 CPU oracle
-    (bf16 tolerance of the north star, normalised like tests/test_model_gpu.py). Detections themselves are compared at the
-    candidate level only: on this random-weight workload (1,200 heavily overlapping candidates per image) greedy suppression
-    is chaotic under bf16-level perturbations, which is why NMS parity is pinned on IDENTICAL inputs (tests/test_nms_gpu.py)."""
+    """EIGHT of the benchmark's 64 images, full 640 x 640 (BASELINE.json configs[1]): head logits and decoded predictions of
+    the CUDA forward vs the fp32 CPU oracle at the north star's bf16 bound (1e-2, max-norm AND relative L2; measured errors
+    recorded), and candidate-set equality: the rows whose objectness passes conf 0.25 are the same set, except rows whose
+    oracle objectness lies within the MEASURED probability error of the threshold (a band far narrower than the tolerance).
+    Detections themselves are compared at the candidate level only: on this random-weight workload greedy suppression is
+    chaotic under bf16-level perturbations, which is why NMS parity is pinned on IDENTICAL inputs (tests/test_nms_gpu.py)."""
     from oracle import yolo_oracle
 
-    model, imgs, _ = _setup(2)
-    x = imgs[[5, 40]].float() / 255.0
+    model, imgs, _ = _setup(8)
+    pick = [0, 5, 13, 22, 31, 40, 52, 63]
+    x = imgs[pick].float() / 255.0
     got_pred, got_raw = model(x.cuda())
     torch.cuda.synchronize()
     got_pred, got_raw = got_pred.float().cpu(), [r.float().cpu() for r in got_raw]
     want_pred, want_raw = yolo_oracle.forward(model.cpu().float(), x)
-    assert got_pred.shape == want_pred.shape == (2, 25200, 85)
-    for g, w in zip(got_raw, want_raw):
-        assert float((g - w).abs().max() / w.abs().max().clamp_min(1e-6)) < 2e-2
-    assert float((got_pred[..., 4:] - want_pred[..., 4:]).abs().max()) < 2e-2
-    rel_box = (got_pred[..., :4] - want_pred[..., :4]).abs() / (want_pred[..., :4].abs() + 8.0)
-    assert float(rel_box.max()) < 5e-2
-    # candidate sets (objectness > conf): the same rows up to those within the tolerance band of the threshold
+    assert got_pred.shape == want_pred.shape == (8, 25200, 85)
+    for i, (g, w) in enumerate(zip(got_raw, want_raw)):
+        e = errs(g, w)
+        record(f"fullsize_b8_of_64/logits_P{i + 3}", **e)
+        assert e["max_norm"] < 1e-2 and e["rel_l2"] < 1e-2, e
+    eb = errs(got_pred[..., :4], want_pred[..., :4])
+    pabs = float((got_pred[..., 4:] - want_pred[..., 4:]).abs().max())
+    assert eb["max_norm"] < 1e-2 and eb["rel_l2"] < 1e-2 and pabs < 1e-2, (eb, pabs)
+    # candidate sets (objectness > conf)
     go, wo = got_pred[..., 4] > CONF, want_pred[..., 4] > CONF
-    band = (want_pred[..., 4] - CONF).abs() < 2e-2
-    assert int((go != wo)[~band].sum()) == 0 and int(wo.sum()) > 1000
+    band = (want_pred[..., 4] - CONF).abs() <= pabs
+    mism = int((go != wo)[~band].sum())
+    record("fullsize_b8_of_64/decoded", box_max_norm=eb["max_norm"], box_rel_l2=eb["rel_l2"], prob_max_abs=pabs,
+           candidates_oracle=int(wo.sum()), candidates_cuda=int(go.sum()), rows_in_band=int(band.sum()),
+           candidate_mismatches_outside_band=mism)
+    assert mism == 0 and int(wo.sum()) > 4000

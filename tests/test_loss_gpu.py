@@ -133,3 +133,56 @@ def test_loss_duplicate_cells_last_wins():
     t = torch.tensor([[0, 1, 0.52, 0.48, 0.3, 0.25], [0, 2, 0.52, 0.48, 0.3, 0.25], [0, 1, 0.5, 0.5, 0.1, 0.1]])
     hyp = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
     _check(preds, t, hyp, nc)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_loss_half_precision_preds(dtype):
+    """The reference trainer calls ComputeLoss under amp.autocast with a torch head (yolo_trainer.py:318-324): preds arrive in
+    fp16 / bf16. Forward uses the fp32 value of the half logits; the gradient comes back in the predictions' own dtype and
+    equals the fp32 gradient at those logits to half rounding (no out-of-bounds write into half-sized buffers)."""
+    from ayolov2_b200.loss import ComputeLoss
+
+    g = torch.Generator().manual_seed(21)
+    nc, bs, nt = 80, 3, 40
+    preds = [torch.randn(bs, 3, 160 // s, 160 // s, nc + 5, generator=g).to(dtype) for s in (8, 16, 32)]
+    t = torch.zeros(nt, 6)
+    t[:, 0] = torch.randint(0, bs, (nt,), generator=g).float()
+    t[:, 1] = torch.randint(0, nc, (nt,), generator=g).float()
+    t[:, 2:4] = 0.05 + 0.9 * torch.rand(nt, 2, generator=g)
+    t[:, 4:6] = torch.exp(np.log(0.03) + (np.log(0.7) - np.log(0.03)) * torch.rand(nt, 2, generator=g))
+    hyp = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
+    fn = ComputeLoss(_Model(nc, hyp))
+    p_half = [p.clone().cuda().requires_grad_(True) for p in preds]
+    canary = torch.full((4096,), 7.0, device="cuda")  # allocated right after the predictions: a stray fp32-sized write lands here
+    l_half, it_half = fn(p_half, t.cuda())
+    l_half.backward()
+    p_f32 = [p.float().cuda().requires_grad_(True) for p in preds]
+    l_f32, it_f32 = fn(p_f32, t.cuda())
+    l_f32.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(l_half, l_f32) and torch.equal(it_half, it_f32)
+    assert bool((canary == 7.0).all())
+    for a, b in zip(p_half, p_f32):
+        assert a.grad.dtype == dtype and a.grad.shape == a.shape
+        assert torch.equal(a.grad, b.grad.to(dtype))
+
+
+def test_loss_noncontiguous_preds():
+    """Predictions that are permuted views (a torch head's x.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2) without
+    .contiguous()): the gradient must come back laid out for the view, identical to the contiguous case."""
+    from ayolov2_b200.loss import ComputeLoss
+
+    g = torch.Generator().manual_seed(22)
+    nc, bs = 6, 2
+    base = [torch.randn(bs, 3, nc + 5, 64 // s, 64 // s, generator=g).cuda().requires_grad_(True) for s in (8, 16, 32)]
+    t = torch.tensor([[0, 1, 0.52, 0.48, 0.3, 0.25], [1, 2, 0.3, 0.6, 0.2, 0.4]])
+    hyp = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, label_smoothing=0.0)
+    fn = ComputeLoss(_Model(nc, hyp))
+    l1, _ = fn([b.permute(0, 1, 3, 4, 2) for b in base], t.cuda())
+    l1.backward()
+    contig = [b.detach().permute(0, 1, 3, 4, 2).contiguous().requires_grad_(True) for b in base]
+    l2, _ = fn(contig, t.cuda())
+    l2.backward()
+    assert torch.equal(l1, l2)
+    for b, c in zip(base, contig):
+        assert torch.equal(b.grad.permute(0, 1, 3, 4, 2), c.grad)

@@ -1,41 +1,54 @@
 """End-to-end parity of the compiled CUDA forward (ayolov2_b200.engine) with the CPU fp32 oracle
 (oracle/yolo_oracle.py) on seeded random weights shared through the same module tree.
 
-Tolerance (BASELINE.json north_star): bf16 activations -> 1e-2 relative. Errors are normalised by the
-tensor's max magnitude; the head logits additionally by a mean-relative figure."""
+Tolerance (BASELINE.json north_star): bf16 activations -> 1e-2 relative, asserted BOTH as max-norm
+(max|d| / max|ref|) and as relative L2 on the head logits and the decoded boxes; class / objectness probabilities
+additionally within 1e-2 absolute. Every measured error is recorded (tests/_parity.py -> profiles/r02_parity.json;
+round-2 measurements: logits 2.4e-3 .. 3.2e-3 max-norm, 1.8e-3 .. 1.9e-3 rel-L2). The fp32 clause of the north star
+(1e-3) is tested through the split-bf16 engine mode in tests/test_precise_gpu.py."""
 import pytest
 import torch
 
+from _parity import errs, record
+
 pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2  # BASELINE.json north_star: "bf16 within 1e-2"
 
 
 def _norm_err(got, ref):
     return float((got.float().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-6))
 
 
-@pytest.mark.parametrize("name,hw", [("yolov5s", (320, 320)), ("yolov5s", (256, 384)), ("yolov5_v5", (256, 256)), ("yolov5n", (192, 192))])
-def test_forward_matches_oracle(name, hw):
+def _assert_forward_parity(case, got_pred, got_raw, want_pred, want_raw, tol=BF16_TOL):
+    assert got_pred.shape == want_pred.shape
+    for i, (gr, wr) in enumerate(zip(got_raw, want_raw)):
+        assert gr.shape == wr.shape
+        e = errs(gr, wr)
+        record(f"{case}/logits_P{i + 3}", **e)
+        assert e["max_norm"] < tol and e["rel_l2"] < tol, (case, i, e)
+    gp = got_pred.float().cpu()
+    eb = errs(gp[..., :4], want_pred[..., :4])
+    pabs = float((gp[..., 4:] - want_pred[..., 4:]).abs().max())
+    record(f"{case}/decoded", box_max_norm=eb["max_norm"], box_rel_l2=eb["rel_l2"], prob_max_abs=pabs)
+    assert eb["max_norm"] < tol and eb["rel_l2"] < tol, (case, eb)
+    assert pabs < tol, (case, pabs)
+
+
+@pytest.mark.parametrize("name,hw,B", [("yolov5s", (320, 320), 2), ("yolov5s", (256, 384), 2), ("yolov5_v5", (256, 256), 2),
+                                       ("yolov5n", (192, 192), 2), ("yolov5s", (640, 640), 1), ("yolov5m", (320, 320), 1)])
+def test_forward_matches_oracle(name, hw, B):
+    """Includes BASELINE.json configs[0]: yolov5s.yaml forward on a 1 x 3 x 640 x 640 random tensor."""
     from ayolov2_b200 import synth as model_utils
     from oracle import yolo_oracle
 
     model = model_utils.build_model(name, seed=0)
-    B = 2
     g = torch.Generator().manual_seed(5)
     x = torch.rand((B, 3, *hw), generator=g)
     want_pred, want_raw = yolo_oracle.forward(model, x)
     model_cuda = model.cuda()
     got_pred, got_raw = model_cuda(x.cuda())
     torch.cuda.synchronize()
-    assert got_pred.shape == want_pred.shape
-    for gr, wr in zip(got_raw, want_raw):
-        assert gr.shape == wr.shape
-        e = _norm_err(gr, wr)
-        assert e < 2e-2, f"raw logits normalised error {e}"
-    # decoded boxes / scores
-    gp = got_pred.float().cpu()
-    assert float((gp[..., 4:] - want_pred[..., 4:]).abs().max()) < 2e-2  # probabilities
-    rel_box = (gp[..., :4] - want_pred[..., :4]).abs() / (want_pred[..., :4].abs() + 8.0)
-    assert float(rel_box.max()) < 5e-2, float(rel_box.max())
+    _assert_forward_parity(f"forward/{name}_{hw[0]}x{hw[1]}_b{B}", got_pred, got_raw, want_pred, want_raw)
 
 
 def test_uint8_detector_matches_float_path():
@@ -125,8 +138,9 @@ def test_tucker_decomposed_forward_matches_oracle():
     want_pred, want_raw = yolo_oracle.forward(model, x)
     got_pred, got_raw = model.cuda()(x.cuda())
     torch.cuda.synchronize()
-    for g, w in zip(got_raw, want_raw):
-        assert _norm_err(g, w) < 3e-2, _norm_err(g, w)
+    # bf16 storage of the rank-R intermediates: same 1e-2 bound as the dense model (the 1e-3 clause of the north star
+    # for the decomposed model is tested in fp32-equivalent arithmetic, tests/test_precise_gpu.py)
+    _assert_forward_parity("tucker_bf16/yolov5s_256x256_r0.45", got_pred, got_raw, want_pred, want_raw)
 
 
 @pytest.mark.parametrize("name,decomposed", [("yolov5s", False), ("yolov5s", True), ("yolov5m", False)])
@@ -160,9 +174,10 @@ def test_fused_chains_match_separate_launches(name, decomposed):
     p0, r0, n0, s0 = run(False)
     assert n0 == 0 and n1 >= 8, (n0, n1)
     assert s1 < s0
-    for a, b in zip(r1, r0):
-        e = float((a - b).abs().max() / b.abs().max())
-        assert e < 1e-2, e
+    for i, (a, b) in enumerate(zip(r1, r0)):
+        e = errs(a, b)
+        record(f"fused_vs_separate/{name}{'_tucker' if decomposed else ''}/logits_P{i + 3}", **e)
+        assert e["max_norm"] < 1e-2 and e["rel_l2"] < 1e-2, e
 
 
 def test_tta_matches_oracle_views():
@@ -188,6 +203,7 @@ def test_tta_matches_oracle_views():
     got, _ = tta.inference_with_tta(model.cuda(), x.cuda(), s, f)
     got = got.float().cpu()
     assert got.shape == want.shape
-    assert float((got[..., 4:] - want[..., 4:]).abs().max()) < 2e-2
-    rel_box = (got[..., :4] - want[..., :4]).abs() / (want[..., :4].abs() + 8.0)
-    assert float(rel_box.max()) < 5e-2
+    eb = errs(got[..., :4], want[..., :4])
+    pabs = float((got[..., 4:] - want[..., 4:]).abs().max())
+    record("tta/yolov5s_256x320", box_max_norm=eb["max_norm"], box_rel_l2=eb["rel_l2"], prob_max_abs=pabs)
+    assert eb["max_norm"] < BF16_TOL and eb["rel_l2"] < BF16_TOL and pabs < BF16_TOL

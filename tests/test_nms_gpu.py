@@ -185,3 +185,82 @@ def test_nms_boxes_matches_torchvision_semantics():
         got = nms_boxes(boxes.cuda(), scores.cuda(), thr).cpu().numpy()
         assert (want == got).all() and len(want) == len(got)
     assert nms_boxes(boxes[:0].cuda(), scores[:0].cuda(), 0.5).numel() == 0
+
+
+@pytest.mark.parametrize("nms_type", ["batched_nms", "fast_nms", "matrix_nms", "merge_nms"])
+@pytest.mark.parametrize("agnostic", [False, True])
+def test_batched_nms_val2_other_types(nms_type, agnostic):
+    """scripts/utils/nms.py:63-110: the val2 path's non-default nms_type branches on the batched kernels; selection identical
+    to the oracle (pinned to the reference in tests/test_oracle_nms.py), decayed scores / merged boxes to fp32 rounding."""
+    from ayolov2_b200.nms import batched_nms
+    from oracle import nms_oracle
+
+    pred = nms_oracle.synth_predictions(3, n=4000, nc=12, seed=13, cand_frac=0.2)
+    pred[2, :, 4] = 0.0  # an image without candidates
+    kw = dict(conf_thres=0.2, iou_thres=0.6, nms_box=400, agnostic=agnostic, nms_type=nms_type)
+    want = nms_oracle.batched_nms(pred, **kw)
+    got = batched_nms(pred.cuda(), **kw)
+    assert sum(w.shape[0] for w in want) > 50 and want[2].shape[0] == 0
+    for g, w in zip(got, want):
+        assert g.shape == w.shape, (g.shape, w.shape)
+        assert torch.equal(g[:, 5].cpu(), w[:, 5])
+        if nms_type in ("batched_nms", "fast_nms"):
+            assert torch.equal(g.cpu(), w)
+        else:
+            assert torch.allclose(g.cpu(), w, rtol=1e-5, atol=1e-4)
+
+
+def test_batched_nms_val2_more_than_1024_survivors():
+    """The reference has no bound on the survivors of the val2 path (nms.py:63-116); at val2's default conf 0.001 an image
+    can keep more boxes than the batched kernel's 1024-entry kept list. Those images are finished by the unbounded route:
+    nothing is truncated and nothing raises."""
+    from ayolov2_b200.nms import batched_nms
+    from oracle import nms_oracle
+
+    g = torch.Generator().manual_seed(5)
+    n, nc = 3000, 4
+    pred = torch.zeros(2, n, 5 + nc)
+    pred[..., :2] = torch.rand(2, n, 2, generator=g) * 2000      # spread out: almost nothing overlaps
+    pred[..., 2:4] = 4.0 + 4.0 * torch.rand(2, n, 2, generator=g)
+    pred[..., 4] = 0.5 + 0.5 * torch.rand(2, n, generator=g)
+    pred[..., 5:] = torch.rand(2, n, nc, generator=g)
+    pred[1, 200:, 4] = 0.0                                       # the second image stays below the bound
+    for nms_type in ("nms", "merge_nms"):
+        want = nms_oracle.batched_nms(pred, conf_thres=0.3, iou_thres=0.65, nms_box=2000, agnostic=True, nms_type=nms_type)
+        got = batched_nms(pred.cuda(), conf_thres=0.3, iou_thres=0.65, nms_box=2000, agnostic=True, nms_type=nms_type)
+        if nms_type == "nms":
+            assert want[0].shape[0] > 1024 and want[1].shape[0] < 1024
+        for a, b in zip(got, want):
+            assert a.shape == b.shape
+            assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-4) if nms_type == "merge_nms" else torch.equal(a.cpu(), b)
+
+
+def test_other_nms_types_more_than_max_nms_candidates():
+    """metrics.py:378-379: above max_nms (30,000) candidates the rows are re-ranked by confidence and cut before the rule
+    runs. Checks the re-ranked candidate table itself (rows, order, count, coordinate maximum; this also exercises the
+    table-capacity retry, flags bit 0) and one whole rule ("batched_nms", whose class offset is that maximum + 1)."""
+    import numpy as np
+
+    from ayolov2_b200.nms import CandidateTable, non_max_suppression
+    from oracle import nms_oracle
+
+    g = torch.Generator().manual_seed(6)
+    n, nc = 4200, 9
+    pred = torch.zeros(1, n, 5 + nc)
+    pred[..., :2] = torch.rand(1, n, 2, generator=g) * 600
+    pred[..., 2:4] = 20.0 + 60.0 * torch.rand(1, n, 2, generator=g)
+    pred[..., 4] = 0.6 + 0.4 * torch.rand(1, n, generator=g)
+    pred[..., 5:] = 0.5 + 0.5 * torch.rand(1, n, nc, generator=g)   # every (row, class) pair passes: 37,800 candidates
+    tab = CandidateTable(pred.cuda(), 0.25, True, None, max_nms=30000)
+    assert tab.cap < n * nc and tab.settle() and int(tab.counts[0]) == 30000
+    x = pred[0].numpy()
+    conf = x[:, 5:] * x[:, 4:5]
+    i, j = np.nonzero(conf > np.float32(0.25))
+    rows = np.concatenate((nms_oracle.xywh2xyxy(x[i, :4]), conf[i, j, None], j[:, None].astype(np.float32)), 1)
+    rows = rows[np.argsort(-rows[:, 4], kind="stable")[:30000]]
+    assert np.array_equal(tab.rows[0, :30000, :6].cpu().numpy(), rows)
+    assert float(tab.max_coord[0]) == float(rows[:, :4].max())
+    kw = dict(conf_thres=0.25, iou_thres=0.5, multi_label=True, nms_type="batched_nms", max_det=300)
+    want = nms_oracle.non_max_suppression(pred, **kw)
+    got = non_max_suppression(pred.cuda(), **kw)
+    assert want[0].shape[0] > 0 and torch.equal(got[0].cpu(), want[0])

@@ -50,12 +50,35 @@ def test_product_and_oracle_match_reference_golden(g):
 
 
 def test_evbmf_returns_reference_shapes():
-    """EVBMF(Y) -> (U[:, :pos], diag(d), V[:, :pos], post) (decomposition.py:81-206)."""
+    """EVBMF(Y) -> (U[:, :r], diag(d), V[:, :r], info) (decomposition.py:81-206): rank, shapes, a positive noise variance
+    and shrunk singular values below the raw ones; the oracle's EVBMF (a restatement of the reference's) agrees."""
     g = torch.Generator().manual_seed(3)
     Y = torch.randn(24, 5, generator=g) @ torch.randn(5, 200, generator=g) + 0.05 * torch.randn(24, 200, generator=g)
-    U, S, V, post = dec.EVBMF(Y)
+    U, S, V, info = dec.EVBMF(Y)
     assert S.shape == (5, 5) and U.shape == (24, 5) and V.shape == (200, 5)
-    assert set(post) >= {"ma", "mb", "sa2", "sb2", "cacb", "sigma2", "F"} and post["sigma2"] > 0
+    assert info["rank"] == 5 and info["sigma2"] > 0
+    sv = torch.linalg.svdvals(Y.double())[:5].numpy()
+    d = S.diagonal()
+    assert (d > 0).all() and (d < sv).all() and (d > 0.9 * sv).all()
+    ro, so = decomp_oracle.evbmf_rank_sigma2(Y.numpy())
+    assert ro == 5 and abs(so - info["sigma2"]) < 1e-4 * so
+
+
+def test_batched_rank_search_matches_per_matrix():
+    """evb_rank_batch over matrices of different shapes at once == one matrix at a time == the oracle's scipy-bounded search."""
+    g = torch.Generator().manual_seed(8)
+    mats = []
+    for (L, M, r, noise) in [(16, 144, 3, 0.05), (64, 576, 20, 0.02), (32, 288, 1, 0.2), (48, 48, 10, 0.05), (96, 30, 7, 0.03)]:
+        mats.append(torch.randn(L, r, generator=g) @ torch.randn(r, M, generator=g) / r ** 0.5 + noise * torch.randn(L, M, generator=g))
+    svals = [torch.linalg.svdvals(m.double()) for m in mats]
+    shapes = [tuple(m.shape) for m in mats]
+    ranks, sig = dec.evb_rank_batch(svals, shapes)
+    for i, m in enumerate(mats):
+        (r1,), (s1,) = dec.evb_rank_batch([svals[i]], [shapes[i]])
+        assert r1 == ranks[i] and abs(s1 - sig[i]) <= 1e-9 * sig[i]
+        ro, so = decomp_oracle.evbmf_rank_sigma2(m.numpy())  # scipy's bounded Brent search on the same objective
+        assert ro == ranks[i], (i, ro, ranks[i])
+        assert abs(so - sig[i]) < 1e-4 * so, (i, so, sig[i])
 
 
 def test_zero_rank_is_rejected_like_tensorly():

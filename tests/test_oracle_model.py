@@ -82,14 +82,19 @@ def test_cpu_forward_is_refused():
 @pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "tests/res/weights/yolov5s_kindle.pt")), reason="reference fixture absent")
 def test_fixture_checkpoint_detection_pin():
     """fixture weights through the restated operators + NMS on the 99 val images ->
-    608 detections (+-1). Also proves the reference's whole-module pickle loads through the kindle shim."""
+    608 detections (+-1), 411 TP@0.5 (+-2) of 696 GT, mAP50 0.640. Also proves the reference's whole-module pickle loads through the kindle shim."""
     import cv2
     import kindle  # noqa: F401
 
     ck = torch.load(os.path.join(REF, "tests/res/weights/yolov5s_kindle.pt"), map_location="cpu", weights_only=False)
     m = ck["model"].float().eval()
     assert type(m).__name__ == "YOLOModel" and sum(p.numel() for p in m.parameters()) == 7276605
-    ndet = 0
+    import numpy as np
+
+    from oracle import val_oracle
+
+    ndet = ngt = ntp = 0
+    stats = []
     for f in sorted(glob.glob(os.path.join(REF, "tests/res/datasets/coco/images/val2017/*.jpg"))):
         im = cv2.imread(f)
         h, w = im.shape[:2]
@@ -99,5 +104,22 @@ def test_fixture_checkpoint_detection_pin():
         top, left = (640 - nh) // 2, (640 - nw) // 2
         im = cv2.copyMakeBorder(im, top, 640 - nh - top, left, 640 - nw - left, cv2.BORDER_CONSTANT, value=(114, 114, 114))
         x = torch.from_numpy(im[:, :, ::-1].transpose(2, 0, 1).copy()).float()[None] / 255
-        ndet += nms_oracle.non_max_suppression(yolo_oracle.forward(m, x)[0], 0.25, 0.45)[0].shape[0]
+        det = nms_oracle.non_max_suppression(yolo_oracle.forward(m, x)[0], 0.25, 0.45)[0].numpy()
+        ndet += det.shape[0]
+        # the reference-held ground truth of the same image (normalised cls cx cy w h) in the letterboxed 640 x 640 frame
+        lf = f.replace("/images/", "/labels/").rsplit(".", 1)[0] + ".txt"
+        lab = np.loadtxt(lf, ndmin=2).reshape(-1, 5) if os.path.isfile(lf) and os.path.getsize(lf) else np.zeros((0, 5))
+        cx, cy, bw, bh = lab[:, 1] * nw + left, lab[:, 2] * nh + top, lab[:, 3] * nw, lab[:, 4] * nh
+        lab_xyxy = np.stack((lab[:, 0], cx - bw / 2, cy - bh / 2, cx + bw / 2, cy + bh / 2), 1).astype(np.float32)
+        correct = val_oracle.process_batch(det, lab_xyxy)  # train_utils.py:294-333 (class-aware, one detection per label)
+        ngt += lab.shape[0]
+        ntp += int(correct[:, 0].sum())
+        stats.append((correct, det[:, 4], det[:, 5], lab[:, 0]))
+    # 608 detections, 411 TP@IoU0.5 against 696 GT boxes, mAP50 0.640 / mAP50:95 0.475 -- the one
+    # reference-held truth (its own weights, images and labels) that pins the restated operators' semantics
     assert abs(ndet - 608) <= 1, ndet
+    assert ngt == 696, ngt
+    assert abs(ntp - 411) <= 2, ntp
+    tp, conf, pcls, tcls = (np.concatenate(a, 0) for a in zip(*stats))
+    _, _, ap, _, _ = val_oracle.ap_per_class(tp, conf, pcls, tcls)
+    assert abs(float(ap[:, 0].mean()) - 0.640) < 0.01 and abs(float(ap.mean()) - 0.475) < 0.01, (ap[:, 0].mean(), ap.mean())

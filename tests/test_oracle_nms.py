@@ -71,3 +71,23 @@ def test_nms_oracle_matches_reference(kw):
     b = nms_oracle.non_max_suppression(pred.clone(), **kw)
     for x, y in zip(a, b):
         assert x.shape == y.shape and torch.equal(x, y)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("nms_type", ["nms", "batched_nms", "fast_nms", "matrix_nms", "merge_nms"])
+@pytest.mark.parametrize("agnostic", [False, True])
+def test_val2_batched_nms_types_match_reference(nms_type, agnostic):
+    """scripts/utils/nms.py:63-110 (the val2 path): every nms_type of the oracle against the unmodified reference --
+    row selection identical, decayed scores / merged boxes within fp32 rounding."""
+    ref = ref_import.load()
+    pred = nms_oracle.synth_predictions(2, n=1500, nc=6, seed=11)
+    a = ref.batched_nms(pred.clone(), conf_thres=0.2, iou_thres=0.6, nms_box=300, agnostic=agnostic, nms_type=nms_type)
+    b = nms_oracle.batched_nms(pred.clone(), conf_thres=0.2, iou_thres=0.6, nms_box=300, agnostic=agnostic, nms_type=nms_type)
+    for x, y in zip(a, b):
+        x = x.float()
+        assert x.shape == y.shape and x.shape[0] > 0
+        assert torch.equal(x[:, 5], y[:, 5])
+        if nms_type in ("matrix_nms", "merge_nms"):
+            assert torch.allclose(x, y, rtol=1e-5, atol=1e-4)
+        else:
+            assert torch.equal(x, y)
