@@ -441,6 +441,29 @@ __global__ void sgd_ema_kernel(float* __restrict__ p, const float* __restrict__ 
   }
 }
 
+// The same update with the reference's three parameter groups (yolo_trainer.py:149-168: BatchNorm weights, other weights
+// with weight decay, biases) resolved per element: group[i] selects the learning rate / weight decay of element i, so the
+// whole model -- whatever the interleaving of the groups in memory -- is ONE launch, also during warm-up when the bias
+// group follows its own learning-rate ramp (yolo_trainer.py:194-221).
+struct SgdGroups {
+  float lr[4], wd[4];
+};
+__global__ void sgd_ema_groups_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, float* ema,
+                                      const uint8_t* __restrict__ group, long long n, SgdGroups gp, float momentum, int nesterov,
+                                      float ema_decay, float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = group[i] & 3;
+    const float w0 = p[i];
+    float d = g[i] * grad_scale + gp.wd[k] * w0;
+    const float b = momentum * mom[i] + d;
+    mom[i] = b;
+    d = nesterov ? d + momentum * b : b;
+    const float w = w0 - gp.lr[k] * d;
+    p[i] = w;
+    if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * w;
+  }
+}
+
 static int ew_grid(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -598,6 +621,20 @@ extern "C" int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t c
   long long blocks = (npix + lanes - 1) / lanes;
   if (blocks > 148 * 8) blocks = 148 * 8;
   channel_sum_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(g), npix, c, cstride, sum);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_sgd_ema_step_groups(float* param, const float* grad, float* momentum_buf, float* ema, const uint8_t* group,
+                                       int64_t n, const float* lr4, const float* wd4, float momentum, int32_t nesterov,
+                                       float ema_decay, float grad_scale, void* stream) {
+  AY2_REQUIRE(param && grad && momentum_buf && group && lr4 && wd4 && n >= 0, "ay2_sgd_ema_step_groups: bad arguments");
+  if (n == 0) return AY2_OK;
+  SgdGroups gp;
+  for (int k = 0; k < 4; ++k) gp.lr[k] = lr4[k], gp.wd[k] = wd4[k];  // host arrays: they change every warm-up step
+  sgd_ema_groups_kernel<<<ew_grid(n, 256), 256, 0, AY2_ST>>>(param, grad, momentum_buf, ema, group, n, gp, momentum, nesterov,
+                                                             ema_decay, grad_scale);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -23,7 +23,7 @@ class Detector:
     def __init__(self, model: nn.Module, batch: int, height: int = 640, width: int = 640, conf_thres: float = 0.25,
                  iou_thres: float = 0.45, multi_label: bool = False, agnostic: bool = False, max_det: int = 300,
                  in_dtype: torch.dtype = torch.uint8, device: Optional[torch.device] = None, want_raw: bool = False,
-                 dense_pred: bool = False, fuse_candidates: bool = True) -> None:
+                 dense_pred: bool = False, fuse_candidates: bool = True, slots: int = 3) -> None:
         scale = 1.0 / 255.0 if in_dtype == torch.uint8 else 1.0
         self.engine = Engine(model, batch, height, width, in_dtype=in_dtype, scale=scale, want_raw=want_raw,
                              device=device, use_graph=False)
@@ -34,6 +34,7 @@ class Detector:
         self.in_dtype = in_dtype
         pred = self.engine.pred
         nc = pred.shape[2] - 5
+        self._nc = nc
         self.nms_ws = ops.NmsWorkspace(batch, pred.shape[1], pred.shape[2], max_det=max_det,
                                        multi_label=multi_label and nc > 1, device=self.device)
         # fused head: NMS candidates and boxes are decoded straight from the bf16 head logits, the dense
@@ -44,23 +45,38 @@ class Detector:
         # ... and the candidates themselves are scored by the detect convolutions' epilogues, from the output tile they
         # hold in shared memory (ay2_conv_plan_set_head_candidates): the NMS kernel only sorts and suppresses
         self.fused_candidates = fuse_candidates and not dense_pred and all(pl.desc.cout_pad <= 256 for pl in eng.head_plans)
-        if self.fused_candidates:
-            p = self.nms_ws.p
-            p.conf_thres = float(conf_thres)
-            p.multi_label = int(self.multi_label and nc > 1)
-            for pl, off in zip(eng.head_plans, eng.head_row_off):
-                pl.set_head_candidates(self.nms_ws, eng.na, off)
-        # two input / output slots for the host pipeline
-        self.dev_in = [torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) for _ in range(2)]
-        self.host_out = [torch.zeros((batch, max_det, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.host_cnt = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._arm_candidates()
+        # input / output slots of the host pipeline: with `slots` of them, slots - 1 batches can be in flight (the H2D copy
+        # of batch i + 1 and the D2H read of batch i - 1 overlap the kernels of batch i)
+        self.slots = max(2, int(slots))
+        self.dev_in = [torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device) for _ in range(self.slots)]
+        self.host_out = [torch.zeros((batch, max_det, 6), dtype=torch.float32).pin_memory() for _ in range(self.slots)]
+        self.host_cnt = [torch.zeros(batch + 1, dtype=torch.int32).pin_memory() for _ in range(self.slots)]  # [batch] = overflow flag
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
-        self.ev_consumed = [torch.cuda.Event() for _ in range(2)]
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_h2d = [torch.cuda.Event() for _ in range(self.slots)]
+        self.ev_consumed = [torch.cuda.Event() for _ in range(self.slots)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.slots)]
         self._slot = 0
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._warm = False
+
+    def _arm_candidates(self) -> None:
+        if self.fused_candidates:
+            eng, p = self.engine, self.nms_ws.p
+            p.conf_thres = float(self.conf_thres)
+            p.multi_label = int(self.multi_label and self._nc > 1)
+            for pl, off in zip(eng.head_plans, eng.head_row_off):
+                pl.set_head_candidates(self.nms_ws, eng.na, off)
+
+    def _grow_workspace(self) -> None:
+        """Some image had more candidates than the list holds (multi_label at a low conf_thres: up to n * nc): the kernel
+        then kept an arbitrary subset. Re-create the workspace with room for every (row, class) pair, re-arm the detect
+        convolutions and drop the captured graph (it holds the old workspace's addresses)."""
+        n, no = self.engine.pred.shape[1], self.engine.pred.shape[2]
+        self.nms_ws = ops.NmsWorkspace(self.B, n, no, max_det=self.max_det, multi_label=self.multi_label and self._nc > 1,
+                                       max_candidates=n * max(self._nc, 1), device=self.device)
+        self._arm_candidates()
+        self._graph, self._warm = None, False
 
     # ---------------------------------------------------------------------------------------------
     def _body(self) -> None:
@@ -109,7 +125,7 @@ class Detector:
     def submit(self, host_img: torch.Tensor) -> int:
         """Enqueue one batch from HOST memory (pinned for a truly asynchronous copy). Returns the slot id."""
         k = self._slot
-        self._slot ^= 1
+        self._slot = (k + 1) % self.slots
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.ev_consumed[k])  # the s2d kernel that last read this slot has finished
@@ -119,14 +135,23 @@ class Detector:
         det, cnt = self.run_device(self.dev_in[k])
         self.ev_consumed[k].record(cur)
         self.host_out[k].copy_(det, non_blocking=True)
-        self.host_cnt[k].copy_(cnt, non_blocking=True)
+        self.host_cnt[k][:self.B].copy_(cnt, non_blocking=True)
+        self.host_cnt[k][self.B:].copy_(self.nms_ws.overflow, non_blocking=True)
         self.ev_done[k].record(cur)
         return k
 
     def collect(self, k: int) -> List[torch.Tensor]:
         """Wait for slot k and return the reference-style list of (n_i, 6) tensors (host memory)."""
         self.ev_done[k].synchronize()
-        counts = self.host_cnt[k].tolist()
+        if int(self.host_cnt[k][self.B]):
+            # candidate-list overflow: redo this batch (still in its device slot) with a workspace that cannot overflow
+            torch.cuda.synchronize(self.device)
+            self._grow_workspace()
+            det, cnt = self.run_device(self.dev_in[k])
+            self.host_out[k].copy_(det)
+            self.host_cnt[k][:self.B].copy_(cnt)
+            self.host_cnt[k][self.B] = 0
+        counts = self.host_cnt[k][:self.B].tolist()
         out = self.host_out[k]
         return [out[i, :c].clone() for i, c in enumerate(counts)]
 

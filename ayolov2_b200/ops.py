@@ -532,6 +532,22 @@ def sgd_ema_step(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema
             torch._C._increment_version(t)
 
 
+def sgd_ema_step_groups(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema: Optional[torch.Tensor],
+                        group: torch.Tensor, lr: Sequence[float], wd: Sequence[float], momentum: float, nesterov: bool,
+                        ema_decay: float, grad_scale: float = 1.0) -> None:
+    """Fused SGD + EMA over a flat parameter buffer with per-element groups (group: uint8 [n], values 0..3)."""
+    assert param.dtype == grad.dtype == mom.dtype == torch.float32 and group.dtype == torch.uint8
+    assert param.is_contiguous() and grad.is_contiguous() and group.numel() == param.numel()
+    lr4 = (C.c_float * 4)(*(list(lr) + [0.0] * 4)[:4])
+    wd4 = (C.c_float * 4)(*(list(wd) + [0.0] * 4)[:4])
+    _lib.check(_lib.load().ay2_sgd_ema_step_groups(param.data_ptr(), grad.data_ptr(), mom.data_ptr(), _lib.ptr(ema), group.data_ptr(),
+                                                   param.numel(), lr4, wd4, float(momentum), int(nesterov), float(ema_decay),
+                                                   float(grad_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step_groups")
+    for t in (param, mom, ema):
+        if t is not None:
+            torch._C._increment_version(t)
+
+
 def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):
     """[(sub-weight OIHW for the dgrad conv (out = cin, in = cout), kh, kw, pad_h, pad_w, out_sub)]."""
     w = weight.detach().float()

@@ -412,11 +412,13 @@ class TrainEngine:
                 cat_bufs[j] = self.new_act(H, W, Engine._out_channels(layers, j, src_of))
             return cat_bufs[j].slice(off, C_)
 
+        self.layer_bwd_end: List[int] = []  # len(self.bwd) after top-level layer i was built (its closures end there)
         for i, m in enumerate(layers):
             name = type(m).__name__
             srcs = src_of(i)
             if name in ("Conv", "Focus") and srcs[0] < 0:
                 outs[i] = self.stem(m, out_view(i, self.H // 2, self.W // 2, m.conv.out_channels))
+                self.layer_bwd_end.append(len(self.bwd))
                 continue
             xin = [outs[s] for s in srcs]
             if name == "Conv":
@@ -436,6 +438,40 @@ class TrainEngine:
                 self.head(m, xin)
             else:
                 raise NotImplementedError(f"layer {i} ({name}) has no training path")
+            self.layer_bwd_end.append(len(self.bwd))
+
+    # ------------------------------------------------------------------------------------------------ gradient buckets
+    def plan_grad_buckets(self, n_buckets: int) -> List[Tuple[int, int, int, int]]:
+        """Split the backward into `n_buckets` consecutive pieces cut at top-level layer boundaries, of roughly equal
+        parameter bytes: [(first closure, last closure + 1, flat gradient offset lo, hi)] in EXECUTION order (last layers
+        first). Parameters are laid out in model.parameters() order = layer order, so the gradients a piece completes are
+        ONE contiguous range of the flat buffer: it can be all-reduced on a side stream while the next piece still runs
+        (the overlap DDP gets from its bucketed hooks, scripts/train/train_model_builder.py:75-78)."""
+        layers = list(self.model.model)
+        params = list(self.model.parameters())
+        off_of = {id(p): o for p, o in zip(params, self.pg_offsets)}
+        total = int(self.pg_flat.numel())
+        first_off = []  # flat offset where layer i's parameters start (== the next layer's for parameter-free layers)
+        nxt = total
+        for m in reversed(layers):
+            ps = list(m.parameters())
+            if ps:
+                nxt = min(off_of[id(q)] for q in ps)
+            first_off.append(nxt)
+        first_off.reverse()
+        n_buckets = max(1, min(int(n_buckets), len(layers)))
+        cuts, target, hi = [], total / n_buckets, total
+        layer_hi = len(layers)
+        for i in range(len(layers) - 1, -1, -1):
+            lo = first_off[i]
+            if (hi - lo >= target and len(cuts) < n_buckets - 1) or i == 0:
+                b_lo = self.layer_bwd_end[i - 1] if i > 0 else 0
+                cuts.append((b_lo, self.layer_bwd_end[layer_hi - 1], 0 if i == 0 else lo, hi))
+                hi, layer_hi = lo, i
+        self.bwd_chunks = [c for c in cuts if c[1] > c[0]]
+        self.bwd_chunks[-1] = (self.bwd_chunks[-1][0], self.bwd_chunks[-1][1], 0, self.bwd_chunks[-1][3])
+        self._gstate = {k: v for k, v in self._gstate.items() if not k.startswith("bwd")}
+        return self.bwd_chunks
 
     # ------------------------------------------------------------------------------------------------ run
     def _run_or_replay(self, key: str, body: Callable[[], None]) -> None:
@@ -486,11 +522,34 @@ class TrainEngine:
         self._run_or_replay("fwd", self._forward_body)
         return [o.clone() for o in self.head_out]
 
+    def _backward_chunk(self, k: int) -> None:
+        b_lo, b_hi, _, _ = self.bwd_chunks[k]
+        if k == 0:
+            for key, gb in self.grad_of.items():
+                if key not in self.overwritten:
+                    gb.zero_()
+            self.pg_flat.zero_()
+        for b in reversed(self.bwd[b_lo:b_hi]):
+            b()
+
     def backward(self, grads: Sequence[torch.Tensor]) -> Dict[int, torch.Tensor]:
         for gin, g_ in zip(self.head_gin, grads):
             gin.copy_(g_)
-        self._run_or_replay("bwd", self._backward_body)
-        flat = self.pg_flat.clone()  # one copy out of the graph's static buffer; the per-parameter gradients are views of it
+        chunks = getattr(self, "bwd_chunks", None)
+        if chunks and len(chunks) > 1:
+            # bucketed backward: one CUDA graph per piece, `on_grad_bucket(k, lo, hi)` after each (the trainer all-reduces
+            # flat gradients [lo, hi) on a side stream while the next piece runs)
+            cb = getattr(self, "on_grad_bucket", None)
+            for k, (_, _, f_lo, f_hi) in enumerate(chunks):
+                self._run_or_replay(f"bwd{k}", lambda k=k: self._backward_chunk(k))
+                if cb is not None:
+                    cb(k, f_lo, f_hi)
+        else:
+            self._run_or_replay("bwd", self._backward_body)
+        if getattr(self, "static_grads", False):
+            flat = self.pg_flat  # the trainer consumes the static buffer in stream order (no copy)
+        else:
+            flat = self.pg_flat.clone()  # one copy out of the graph's static buffer; the per-parameter gradients are views of it
         self.last_grad_flat = flat
         return {k: flat[v.storage_offset():v.storage_offset() + v.numel()].view(v.shape) for k, v in self.pg.items()}
 
@@ -520,6 +579,10 @@ class TrainFunction(torch.autograd.Function):
                                "gradient buffers of the first backward have been consumed")
         ctx.consumed = True
         pg = eng.backward([g if g is not None else torch.zeros_like(o) for g, o in zip(gouts, eng.head_out)])
+        if getattr(eng, "static_grads", False):
+            # trainer mode (ayolov2_b200.trainer.TrainStep): the optimizer consumes the flat gradient buffer directly;
+            # no per-parameter .grad tensors are materialised (that would be one copy kernel per parameter)
+            return (None, None) + tuple(None for _ in ctx.params)
         grads = tuple(pg.get(id(p)) if p.requires_grad else None for p in ctx.params)
         return (None, None) + grads
 
@@ -531,10 +594,15 @@ def forward_train(model: nn.Module, x: torch.Tensor) -> List[torch.Tensor]:
     B, _, H, W = x.shape
     cache = model.__dict__.setdefault("_train_engine_cache", {})
     key = (B, H, W, x.device.index)
-    eng = cache.get(key)
+    eng = cache.pop(key, None)
     if eng is None:
-        cache.clear()
+        while len(cache) >= int(model.__dict__.get("_train_engine_slots", 1)):  # multi_scale training keeps a few shapes
+            cache.pop(next(iter(cache)))
         eng = TrainEngine(model, B, H, W, device=x.device)
-        cache[key] = eng
+        hook = model.__dict__.get("_train_engine_hook")
+        if hook is not None:
+            hook(eng)
+    cache[key] = eng  # most recently used last
+    model.__dict__["_train_engine_last"] = eng
     params = tuple(model.parameters())
     return list(TrainFunction.apply(eng, x, *params))

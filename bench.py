@@ -9,7 +9,12 @@ uint8 -> /255 -> yolov5s forward (bf16 tensor cores, fp32 accumulate) -> decode 
   value : whole-job images/s with the input batch already resident in HBM (CUDA-event timed, max over ranks)
   e2e   : the same metric through the public host API (Detector.submit/collect): pinned-host uint8 batch ->
           H2D -> kernels -> D2H of the detections, every step, copies inside the timed region
-  roofline : the conv kernel family (60 launches/step) timed live with CUDA events
+  roofline : the conv kernel family: a CUDA graph holding exactly the step's convolution launches, replayed and timed with
+             CUDA events (the in-graph duration, <= ms_per_step), against the measured bf16 peak
+  extras   : the other BASELINE.json configs on the same box -- train_step (configs[2]: yolov5s bs128 global fwd + ComputeLoss
+             + bwd + gradient all-reduce + SGD/EMA, with the all-reduce's exposed time), tucker (configs[3]: decomposed vs
+             dense images/s and the logits error of the fused chain), yolov5l_train (configs[4], 8 GPUs), nms_synthetic
+             (SURVEY 8(d) tensor)
   cpu_baseline : the CPU oracle (fp32 PyTorch restatement + NMS restatement) on this box's host cores
 `--impl reference` times that same CPU path as the reference arm (the reference's operators live in the
 un-vendored `kindle` package, so the restatement in oracle/ is the closest runnable form).
@@ -184,6 +189,186 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process to the CPUs closest to its GPU (NVML affinity) BEFORE any pinned host memory is allocated, so the
+    staging buffers of the end-to-end leg are first-touched on the GPU's NUMA node. Returns a short description."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(cpus & allowed)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"cpus {cpus[0]}-{cpus[-1]} ({len(cpus)}) by NVML affinity"
+        return "NVML affinity empty within the cgroup: not bound"
+    except Exception as e:  # no NVML / not permitted: run unbound
+        return f"not bound ({type(e).__name__})"
+
+
+def time_graph(body, steps: int, warmup: int = 3) -> float:
+    """ms per replay of a CUDA graph capturing `body` (CUDA events on the replay stream)."""
+    import torch
+
+    body()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    for _ in range(warmup):
+        g.replay()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+HYP = dict(box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0, lrf=0.1, momentum=0.937,
+           weight_decay=5e-4, warmup_epochs=3.0, warmup_momentum=0.8, warmup_bias_lr=0.1,
+           optimizer_params=dict(lr=0.01, momentum=0.937, nesterov=True))  # res/configs/cfg/train_config.yaml:29-54
+
+
+def synth_targets(bs: int, seed: int):
+    """n ~ Poisson(7) boxes per image, cls randint(80), xy U(0.05, 0.95), wh LogU(0.02, 0.6) clipped."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(seed)
+    rows = []
+    for b in range(bs):
+        for _ in range(int(rng.poisson(7))):
+            w, h = np.exp(rng.uniform(np.log(0.02), np.log(0.6), 2))
+            x, y = rng.uniform(0.05, 0.95, 2)
+            rows.append([b, rng.integers(0, 80), x, y, min(w, 2 * min(x, 1 - x)), min(h, 2 * min(y, 1 - y))])
+    return torch.tensor(rows, dtype=torch.float32) if rows else torch.zeros((0, 6))
+
+
+def bench_train_step(name: str, global_batch: int, size: int, steps: int, warmup: int, rank: int, world: int, dev, barrier,
+                     max_over_ranks):
+    """One BASELINE train config through ayolov2_b200.trainer.TrainStep (the drop-in of YoloTrainer.training_step): uint8
+    batch on the device -> /255 -> forward (batch-statistics BN) -> ComputeLoss -> backward -> bucketed gradient all-reduce
+    overlapped with the backward -> fused SGD-nesterov + EMA. Returns the extras entry (rank 0) or None."""
+    import torch
+
+    from ayolov2_b200 import synth as model_utils
+    from ayolov2_b200.trainer import TrainStep
+
+    bs = global_batch // world
+    model = model_utils.build_model(name, seed=0)
+    ts = TrainStep(model, HYP, batch_size=global_batch, batches_per_epoch=1000, epochs=300, img_size=size, device=dev)
+    imgs = [torch.randint(0, 256, (bs, 3, size, size), dtype=torch.uint8, device=dev) for _ in range(2)]
+    tgts = [synth_targets(bs, 10 * rank + i).to(dev) for i in range(2)]
+
+    def run(n: int, first: int) -> float:
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            ts.training_step((imgs[i % 2], tgts[i % 2], None, None), first + i, 0)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / n
+
+    run(max(warmup, 4), 0)  # eager pass, graph capture, first replays
+    ms = run(steps, 100)
+    exposed = None
+    if world > 1:  # the same steps without the exchange: what the all-reduce adds to the step (its EXPOSED time)
+        ts.skip_exchange = True
+        ms_local = run(steps, 200)
+        ts.skip_exchange = False
+        exposed = ms - ms_local
+    if rank != 0:
+        return None
+    eng = ts._engine()
+    return {"config": f"{name} {size}x{size} global batch {global_batch} ({bs}/GPU), Poisson(7) targets/img, SGD-nesterov + EMA",
+            "images_per_s": world * bs / (ms / 1000.0), "ms_per_step": ms, "n_gpus": world,
+            "conv_tflops_per_gpu_3x_fwd": 3.0 * eng.flops_fwd / (ms / 1000.0) / 1e12,
+            "allreduce": None if world == 1 else {"bytes": int(eng.pg_flat.numel() * 4), "buckets": len(getattr(eng, "bwd_chunks", [0])),
+                                                  "exposed_ms": exposed, "overlapped_with_backward": len(getattr(eng, "bwd_chunks", [])) > 1},
+            "loss_items_last": [float(v) for v in ts.mloss.tolist()]}
+
+
+def bench_tucker(steps: int, dev):
+    """BASELINE configs[3]: Tucker-2 decomposed yolov5s (fixed ranks ceil(0.5 C)) bs64 640x640 vs dense, one GPU."""
+    import torch
+
+    import ayolov2_b200
+    from ayolov2_b200 import engine as eng_mod, synth as model_utils, tucker
+
+    img = torch.randint(0, 256, (BATCH, 3, H, W), dtype=torch.uint8, device=dev)
+    out = {}
+
+    def run(model, label, fuse=True):
+        eng_mod.Builder.FUSE_CHAINS = fuse
+        try:
+            e = eng_mod.Engine(model, BATCH, H, W, in_dtype=torch.uint8, scale=1 / 255.0, want_raw=False, use_graph=True)
+        finally:
+            eng_mod.Builder.FUSE_CHAINS = True
+        for _ in range(3):
+            e.run(img)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            e.run(img)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out[label] = {"ms_per_step": ms, "images_per_s": BATCH / ms * 1000.0, "launches": len(e.b.steps),
+                      "fused_chain_launches": sum(1 for p in e.b.plans if type(p).__name__ == "ChainPlan"),
+                      "params": sum(p.numel() for p in model.parameters())}
+        return e
+
+    dense = model_utils.build_model("yolov5s", seed=0).to(dev).eval()
+    run(dense, "dense")
+    dec = model_utils.build_model("yolov5s", seed=0)
+    n = len(tucker.decompose_model_fixed(dec, ratio=0.5))
+    dec = dec.to(dev).eval()
+    run(dec, "tucker_fused_chain")
+    run(dec, "tucker_three_launches", fuse=False)
+    # logits of the fused bf16 path against the split-precision (fp32-equivalent) evaluation of the same chains
+    x = torch.rand((2, 3, 320, 320), device=dev)
+    with torch.no_grad():
+        _, raw_b = dec(x)
+        ayolov2_b200.set_precision(dec, "bf16x3")
+        _, raw_p = dec(x)
+        ayolov2_b200.set_precision(dec, "bf16")
+    err = max(float((a - b).norm() / b.norm()) for a, b in zip(raw_b, raw_p))
+    out.update({"decomposed_convs": n, "rank_ratio": 0.5, "fused_vs_dense": out["tucker_fused_chain"]["images_per_s"] / out["dense"]["images_per_s"],
+                "bf16_logits_rel_l2_vs_fp32_equivalent": err,
+                "note": "fp32-equivalent (bf16x3) evaluation vs the nn.Sequential oracle: 3e-6 rel-L2 (tests/test_precise_gpu.py)"})
+    return out
+
+
+def bench_nms_synthetic(dev, steps: int = 20):
+    """NMS alone on the synthetic tensor SURVEY.md 8(d) prescribes (64 x 25200 x 85, ~2,000 clustered candidates / image)."""
+    import torch
+
+    from ayolov2_b200 import synth as model_utils
+    from ayolov2_b200.nms import nms_device
+
+    pred = model_utils.synth_predictions(BATCH, 25200, 80, seed=0, device=dev)
+    ws = nms_device(pred, CONF, IOU)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        nms_device(pred, CONF, IOU, workspace=ws)
+    b.record()
+    torch.cuda.synchronize()
+    return {"ms_dense_3_launches": a.elapsed_time(b) / steps, "candidates": int(ws.ws[:4 * BATCH].view(torch.int32).sum().item()),
+            "detections": int(ws.count.sum().item()),
+            "config": "(64, 25200, 85) fp32, Bernoulli(0.08) x U(0.25, 1) objectness, 200 box clusters / image, conf 0.25 iou 0.45"}
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,6 +376,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the train / Tucker / synthetic-NMS extras")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,6 +394,7 @@ def main() -> None:
 
     args.warmup = max(args.warmup, 3)  # timing rules: at least 3 warm-up steps (the line reports the count actually run)
     args.steps = max(args.steps, 1)
+    numa = bind_to_gpu_numa_node(local_rank)  # before the pinned staging buffers exist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -233,8 +420,8 @@ def main() -> None:
     model_utils.calibrate_head(model, raw)
     model.invalidate_engine()
     det = Detector(model, BATCH, H, W, conf_thres=CONF, iou_thres=IOU, in_dtype=torch.uint8, device=dev)
-    host_imgs = [synth_images(BATCH, 1000 + rank * 10 + i).pin_memory() for i in range(2)]
-    dev_imgs = [h.to(dev) for h in host_imgs]
+    host_imgs = [synth_images(BATCH, 1000 + rank * 10 + i).pin_memory() for i in range(3)]
+    dev_imgs = [h.to(dev) for h in host_imgs[:2]]
 
     # ------------------------------------------------------------------ device-resident throughput (`value`)
     for i in range(args.warmup):
@@ -259,23 +446,24 @@ def main() -> None:
 
     # ------------------------------------------------------------------ end to end through the host API (`e2e`)
     for i in range(args.warmup):
-        det.collect(det.submit(host_imgs[i % 2]))
+        det.collect(det.submit(host_imgs[i % 3]))
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    pending = None
+    pending = []
     for i in range(args.steps):
-        k = det.submit(host_imgs[i % 2])
-        if pending is not None:
-            det.collect(pending)
-        pending = k
-    det.collect(pending)
+        pending.append(det.submit(host_imgs[i % 3]))
+        if len(pending) > det.slots - 1:  # slots - 1 batches in flight: H2D of the next and D2H of the previous overlap the kernels
+            det.collect(pending.pop(0))
+    while pending:
+        det.collect(pending.pop(0))
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
     e2e_value = world * BATCH * args.steps / (e2e_ms / 1000.0)
     h2d = host_imgs[0].numel() * host_imgs[0].element_size()
     d2h = det.host_out[0].numel() * 4 + det.host_cnt[0].numel() * 4
+    n_slots, launches_per_step = det.slots, det.launches_per_step()
 
     # ------------------------------------------------------------------ roofline of the conv kernel family
     peaks = _peaks()
@@ -304,39 +492,51 @@ def main() -> None:
             per_plan.setdefault(id(plan), [plan, 0.0, 0])
             per_plan[id(plan)][1] += a.elapsed_time(b_)
             per_plan[id(plan)][2] += 1
-        conv_ms = sum(v[1] / v[2] for v in per_plan.values())
+        conv_ms_eager = sum(v[1] / v[2] for v in per_plan.values())  # per-launch events: includes the launch gaps a graph hides
+        # The in-step duration of the conv family: a CUDA graph holding EXACTLY the step's convolution launches (the same
+        # plans, in order, plus the memset that re-arms the candidate counters), replayed back to back and timed with CUDA
+        # events on the replay stream. Inter-kernel gaps are the graph's own, so this is <= ms_per_step by construction.
+        conv_steps = [s for s in eng.b.steps if getattr(s, "__self__", None) is not None
+                      and s.__self__.__class__.__name__ in ("ConvPlan", "ChainPlan")]
+
+        def conv_only():
+            if det.fused_candidates:
+                det.nms_ws.begin_candidates()
+            for s in conv_steps:
+                s()
+
+        conv_ms = time_graph(conv_only, 20)
+
+        def nms_only():
+            if det.fused_candidates:
+                det.nms_ws.run_candidates(det.levels, eng.head_logits, det.iou_thres, agnostic=det.agnostic)
+            else:
+                det.nms_ws.run_logits(det.levels, eng.head_logits, det.conf_thres, det.iou_thres, agnostic=det.agnostic)
+
+        det.run_device(dev_imgs[0])  # leave one real step's candidates in the workspace
+        torch.cuda.synchronize()
+        nms_ms = time_graph(nms_only, 20)
         flops = GFLOP_PER_IMG * 1e9 * BATCH
         achieved = flops / (conv_ms / 1000.0) / 1e12
         peak = peaks["tflops_sustained"]
         abytes = ACT_MB_PER_IMG * 1e6 * BATCH
-        traffic = None  # DRAM bytes of the same 52 launches from the committed ncu capture (profiles/*_conv_traffic.json)
+        traffic, traffic_src = None, None  # DRAM bytes of the same launches: from the committed ncu capture of this kernel state
         tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_traffic.json")) \
             if os.path.isdir(os.path.join(ROOT, "profiles")) else []
         if tfiles:
             traffic = json.load(open(os.path.join(ROOT, "profiles", tfiles[-1])))["dram_bytes"]
+            traffic_src = "profiles/" + tfiles[-1] + " (ncu dram__bytes_read.sum + dram__bytes_write.sum over one step's conv launches)"
         n_chain = sum(1 for v in per_plan.values() if v[0].__class__.__name__ == "ChainPlan")
         n_halo = sum(1 for v in per_plan.values() if getattr(v[0], "halo", False))
         roof = {"bound": "tensor",
                 "kernel": f"conv family: {len(per_plan) - n_chain - n_halo} conv_tc_kernel + {n_halo} conv_halo_kernel + {n_chain} "
                           "conv_chain_kernel launches (60 convolutions) = one step", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_src": peaks["src"] + " (sustained)",
-                "conv_ms_per_step": conv_ms, "hbm_view": {"achieved_gbs": abytes / (conv_ms / 1000.0) / 1e9,
-                                                          "peak_gbs": peaks["hbm_gbs"],
-                                                          "frac": abytes / (conv_ms / 1000.0) / 1e9 / peaks["hbm_gbs"]}}
-        # NMS share (north_star: NMS < 2 % of the step): the NMS launch timed alone on the last step's candidates. The
-        # candidates are scored inside the detect convolutions' epilogues (part of conv_ms above); what is left of NMS
-        # is the sort + suppression + output kernel.
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(20):
-            if det.fused_candidates:
-                det.nms_ws.run_candidates(det.levels, eng.head_logits, det.iou_thres, agnostic=det.agnostic)
-            else:
-                det.nms_ws.run_logits(det.levels, eng.head_logits, det.conf_thres, det.iou_thres, agnostic=det.agnostic)
-        b_.record()
-        torch.cuda.synchronize()
-        nms_ms = a.elapsed_time(b_) / 20
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_src": traffic_src,
+                "peak_src": peaks["src"] + " (sustained)", "frac_of_burst_peak": achieved / peaks["tflops_burst"],
+                "conv_ms_per_step": conv_ms, "conv_ms_how": "CUDA-graph replay of the step's conv launches only, CUDA events",
+                "conv_ms_eager_per_launch_events": conv_ms_eager,
+                "hbm_view": {"achieved_gbs": abytes / (conv_ms / 1000.0) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                             "frac": abytes / (conv_ms / 1000.0) / 1e9 / peaks["hbm_gbs"]}}
         roof["nms_ms_per_step"] = nms_ms
         roof["nms_share_of_step"] = nms_ms / ms_per_step
         layers = []
@@ -350,6 +550,33 @@ def main() -> None:
                            "ms": tot / n, "tflops": plan.flops / (tot / n / 1000.0) / 1e12})
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(layers, open(os.path.join(ROOT, "gpurun_out", "conv_layers.json"), "w"), indent=1)
+
+    # ------------------------------------------------------------------ the other BASELINE configs (extras)
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras["train_step"] = bench_train_step("yolov5s", 128, 640, 20, 5, rank, world, dev, barrier, max_over_ranks)
+        except Exception as e:  # an extra must never take the headline line down
+            extras["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+        if world == 8 or os.environ.get("AY2_BENCH_YOLOV5L") == "1":
+            try:
+                extras["yolov5l_train"] = bench_train_step("yolov5l", 32, 640, 10, 4, rank, world, dev, barrier, max_over_ranks)
+            except Exception as e:
+                extras["yolov5l_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                extras["tucker"] = bench_tucker(20, dev)
+            except Exception as e:
+                extras["tucker"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                extras["nms_synthetic"] = bench_nms_synthetic(dev)
+                extras["nms_synthetic"]["share_of_fwd_plus_nms"] = extras["nms_synthetic"]["ms_dense_3_launches"] / (
+                    ms_per_step + extras["nms_synthetic"]["ms_dense_3_launches"])
+            except Exception as e:
+                extras["nms_synthetic"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -370,9 +597,11 @@ def main() -> None:
                        "detections_last_step": ndet, "nms_candidates_last_step": ncand},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": det.launches_per_step() * args.steps,
+                    "ms_per_step": e2e_ms / args.steps, "h2d_gbs_per_rank": h2d / (e2e_ms / args.steps) / 1e6,
+                    "pipeline": f"{n_slots} device input slots, {n_slots - 1} batches in flight; host staging: {numa}"},
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
+            "extras": extras,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

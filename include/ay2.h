@@ -369,6 +369,13 @@ int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t cstride, dou
  * inv_scale: optional device scalar multiplied into the gradient (GradScaler unscale), ema may be NULL */
 int ay2_sgd_ema_step(float* param, const float* grad, float* momentum_buf, float* ema, int64_t n, float lr, float momentum,
                      float weight_decay, int32_t nesterov, float ema_decay, const float* inv_scale, void* stream);
+/* The same fused update with per-element parameter groups: group[i] in 0..3 selects lr4[group] / wd4[group] (HOST arrays of
+ * four floats; the reference's optimizer has three groups -- BatchNorm weights, decayed weights, biases -- whose learning
+ * rates differ during warm-up, scripts/train/yolo_trainer.py:149-168,194-221). grad is multiplied by grad_scale first
+ * (1 / world_size after a sum all-reduce, 1 / loss scale). One launch for the whole flat parameter buffer. */
+int ay2_sgd_ema_step_groups(float* param, const float* grad, float* momentum_buf, float* ema, const uint8_t* group, int64_t n,
+                            const float* lr4, const float* wd4, float momentum, int32_t nesterov, float ema_decay,
+                            float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
