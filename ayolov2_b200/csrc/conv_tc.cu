@@ -131,7 +131,7 @@ __device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok,
   }
 }
 
-constexpr int kHeadDenseMax = 48;  // (pixel, anchor) pairs per tile (of 384) up to which the warp-per-entry walk wins
+constexpr int kHeadDenseMax = 256;  // (pixel, anchor) pairs per tile (of 384) up to which the warp-per-entry walk is used (r02: 8 % of the rows of EVERY level are candidates; the per-thread dense loop costs 80 sigmoids per pixel and anchor whatever the count)
 
 // Two phases per tile. (1) Every epilogue thread owns one pixel and tests the objectness of its group's anchors; passing
 // (pixel, anchor) pairs are appended to a small shared-memory list (warp-aggregated). (2) After a barrier the warps walk

@@ -181,7 +181,7 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
 
 // backward, pass 2: dz = gamma * invstd * (dyh - s1/N - xhat * s2/N)
 __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, const __nv_bfloat16* __restrict__ z,
-                                        int zcs, long long npix, int C, const float* __restrict__ mean,
+                                        int zcs, long long npix, long long npix_norm, int C, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, int act, const double* __restrict__ s1,
                                         const double* __restrict__ s2, __nv_bfloat16* __restrict__ dz, int zdcs) {
@@ -189,7 +189,7 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
   const int lanes = blockDim.x / tpp;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   if (pl >= lanes) return;
-  const float invn = 1.0f / (float)npix;
+  const float invn = 1.0f / (float)npix_norm;  // pixels of the WHOLE (possibly cross-rank, SyncBatchNorm) batch
   float is[8], ms[8], ga[8], be[8], k0[8], k1[8], k2[8];  // dz = k0*dyh - k1 - xhat*k2
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -525,26 +525,46 @@ extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_
   return AY2_OK;
 }
 
-extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
-                              const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
-                              double* s1, double* s2, void* dz, int32_t dz_cstride, void* stream) {
+static int bn_act_bwd_impl(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                           const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
+                           double* s2, void* dz, int32_t dz_cstride, int phases, int64_t npix_norm, void* stream) {
   AY2_REQUIRE(dy && z && mean && invstd && gamma && beta && s1 && s2 && dz, "ay2_bn_act_bwd: null pointer");
   int threads, lanes;
   size_t smem;
   AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_bwd: channels=%d unsupported", c);
-  AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
-  AY2_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * c, AY2_ST));
-  long long blocks = (npix + lanes - 1) / lanes;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_act_bwd_reduce_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
-                                                                  mean, invstd, gamma, beta, act, s1, s2);
-  AY2_CHECK_LAUNCH();
-  bn_act_bwd_apply_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride,
-                                                                           npix, c, mean, invstd, gamma, beta, act, s1, s2,
-                                                                           AY2_BF(dz), dz_cstride);
-  AY2_CHECK_LAUNCH();
-  count_launch(2);
+  if (phases & 1) {
+    AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
+    AY2_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * c, AY2_ST));
+    long long blocks = (npix + lanes - 1) / lanes;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    bn_act_bwd_reduce_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
+                                                                    mean, invstd, gamma, beta, act, s1, s2);
+    AY2_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (phases & 2) {
+    bn_act_bwd_apply_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(
+        AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, npix_norm, c, mean, invstd, gamma, beta, act, s1, s2, AY2_BF(dz),
+        dz_cstride);
+    AY2_CHECK_LAUNCH();
+    count_launch();
+  }
   return AY2_OK;
+}
+
+extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                              const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
+                              double* s1, double* s2, void* dz, int32_t dz_cstride, void* stream) {
+  return bn_act_bwd_impl(dy, dy_cstride, z, z_cstride, npix, c, mean, invstd, gamma, beta, act, s1, s2, dz, dz_cstride, 3, npix, stream);
+}
+
+extern "C" int ay2_bn_act_bwd_phase(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                                    const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
+                                    double* s1, double* s2, void* dz, int32_t dz_cstride, int32_t phase, int64_t npix_total,
+                                    void* stream) {
+  AY2_REQUIRE(phase == 1 || phase == 2, "ay2_bn_act_bwd_phase: phase must be 1 (reduce) or 2 (apply)");
+  return bn_act_bwd_impl(dy, dy_cstride, z, z_cstride, npix, c, mean, invstd, gamma, beta, act, s1, s2, dz, dz_cstride, phase,
+                         npix_total, stream);
 }
 
 extern "C" int ay2_add_slices(const void* src, int32_t src_cstride, void* dst, int32_t dst_cstride, int64_t npix, int32_t c,

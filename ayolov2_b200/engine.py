@@ -22,6 +22,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
+from torch.nn.modules.batchnorm import _BatchNorm
 
 from . import ops
 from .ops import ACT_NONE, ACT_SILU, ActView, ChainPlan, ConvPlan
@@ -37,7 +38,7 @@ def _act_code(m: nn.Module) -> int:
 
 
 def _bn_tuple(bn: Optional[nn.Module]):
-    if isinstance(bn, nn.BatchNorm2d):
+    if isinstance(bn, _BatchNorm):  # BatchNorm2d or SyncBatchNorm (train_model_builder.py:86-91 converts the model)
         return (bn.weight, bn.bias, bn.running_mean, bn.running_var), bn.eps
     return None, 1e-3
 
@@ -656,7 +657,7 @@ def run_single_module(module: nn.Module, x):
     xs = list(x) if isinstance(x, (list, tuple)) else [x]
     if not all(t.is_cuda for t in xs):
         raise RuntimeError(f"ayolov2_b200 {name} runs on CUDA tensors only; there is no CPU fallback")
-    if module.training and any(isinstance(mm, nn.BatchNorm2d) for mm in module.modules()):
+    if module.training and any(isinstance(mm, _BatchNorm) for mm in module.modules()):
         raise NotImplementedError("training-mode module forward is not built yet; call .eval()")
     dev = xs[0].device
     B = xs[0].shape[0]

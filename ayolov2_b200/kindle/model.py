@@ -201,7 +201,7 @@ class YOLOModel(nn.Module):
         """Fold every BatchNorm into its convolution (val.py:331). Parameter count drops by sum(C_bn)... x2
         (gamma, beta) minus the new conv biases (tests/test_tensor_decomposition.py:47: 7,276,605 -> 7,266,973)."""
         for m in self.modules():
-            if isinstance(m, (M.Conv, M.Focus)) and isinstance(m.batch_norm, nn.BatchNorm2d):
+            if isinstance(m, (M.Conv, M.Focus)) and isinstance(m.batch_norm, nn.modules.batchnorm._BatchNorm):
                 fuse_conv_and_bn(m)
         self.invalidate_engine()
         return self

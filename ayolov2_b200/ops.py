@@ -439,15 +439,26 @@ def _npix(v: ActView) -> int:
     return v.B * v.H * v.W
 
 
+def _sync_world(sync: bool) -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size() if (sync and dist.is_available() and dist.is_initialized()) else 1
+
+
 def bn_batch_stats(z: ActView, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
-                   running_var: Optional[torch.Tensor], scratch: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor) -> None:
-    """scratch: double[2*c] (zeroed here); mean / invstd: fp32 [c] outputs; running stats updated in place."""
+                   running_var: Optional[torch.Tensor], scratch: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
+                   sync: bool = False) -> None:
+    """scratch: double[2*c] (zeroed here); mean / invstd: fp32 [c] outputs; running stats updated in place.
+    sync (SyncBatchNorm): the per-channel sums are all-reduced, the statistics are those of the cross-rank batch."""
     lib = _lib.load()
     c = z.c
     scratch.zero_()
     st = _lib.current_stream_ptr()
     _lib.check(lib.ay2_bn_stats(z.ptr(), _npix(z), c, z.cstride, scratch.data_ptr(), scratch.data_ptr() + 8 * c, st), "ay2_bn_stats")
-    _lib.check(lib.ay2_bn_finalize(scratch.data_ptr(), scratch.data_ptr() + 8 * c, _npix(z), c, float(eps), float(momentum),
+    world = _sync_world(sync)
+    if world > 1:
+        torch.distributed.all_reduce(scratch)
+    _lib.check(lib.ay2_bn_finalize(scratch.data_ptr(), scratch.data_ptr() + 8 * c, _npix(z) * world, c, float(eps), float(momentum),
                                    _lib.ptr(running_mean), _lib.ptr(running_var), mean.data_ptr(), invstd.data_ptr(), st),
                "ay2_bn_finalize")
 
@@ -460,9 +471,21 @@ def bn_act_fwd(z: ActView, mean, invstd, gamma, beta, act: int, y: ActView, resi
                "ay2_bn_act_fwd")
 
 
-def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sums: torch.Tensor, dz: ActView) -> None:
-    """sums: double[2*c]; afterwards sums[:c] = d beta, sums[c:] = d gamma."""
+def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sums: torch.Tensor, dz: ActView,
+               sync: bool = False) -> None:
+    """sums: double[2*c]; afterwards sums[:c] = d beta, sums[c:] = d gamma (under `sync` with more than one rank: of the
+    cross-rank batch -- SyncBatchNorm's backward; DDP then averages them like every other gradient, so divide by world)."""
     c = z.c
+    world = _sync_world(sync)
+    if world > 1:
+        lib, st = _lib.load(), _lib.current_stream_ptr()
+        args = (dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                beta.data_ptr(), act, sums.data_ptr(), sums.data_ptr() + 8 * c, dz.ptr(), dz.cstride)
+        _lib.check(lib.ay2_bn_act_bwd_phase(*args, 1, _npix(z) * world, st), "ay2_bn_act_bwd_phase")
+        torch.distributed.all_reduce(sums)
+        _lib.check(lib.ay2_bn_act_bwd_phase(*args, 2, _npix(z) * world, st), "ay2_bn_act_bwd_phase")
+        sums.div_(world)  # this rank's share: the gradient all-reduce (sum, then / world) restores the total
+        return
     _lib.check(_lib.load().ay2_bn_act_bwd(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(), invstd.data_ptr(),
                                           gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(), sums.data_ptr() + 8 * c,
                                           dz.ptr(), dz.cstride, _lib.current_stream_ptr()), "ay2_bn_act_bwd")
@@ -527,9 +550,7 @@ def sgd_ema_step(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema
                                             float(lr), float(momentum), float(weight_decay), int(nesterov), float(ema_decay),
                                             _lib.ptr(inv_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step")
     # the kernel writes through raw pointers: tell autograd / the compiled-engine cache that these tensors changed
-    for t in (param, mom, ema):
-        if t is not None:
-            torch._C._increment_version(t)
+    torch._C._increment_version([t for t in (param, mom, ema) if t is not None])  # takes an ITERABLE of tensors
 
 
 def sgd_ema_step_groups(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tensor, ema: Optional[torch.Tensor],
@@ -543,9 +564,7 @@ def sgd_ema_step_groups(param: torch.Tensor, grad: torch.Tensor, mom: torch.Tens
     _lib.check(_lib.load().ay2_sgd_ema_step_groups(param.data_ptr(), grad.data_ptr(), mom.data_ptr(), _lib.ptr(ema), group.data_ptr(),
                                                    param.numel(), lr4, wd4, float(momentum), int(nesterov), float(ema_decay),
                                                    float(grad_scale), _lib.current_stream_ptr()), "ay2_sgd_ema_step_groups")
-    for t in (param, mom, ema):
-        if t is not None:
-            torch._C._increment_version(t)
+    torch._C._increment_version([t for t in (param, mom, ema) if t is not None])  # takes an ITERABLE of tensors
 
 
 def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):

@@ -34,36 +34,49 @@ def build_model(name: str = "yolov5s", seed: int = 0, randomize_bn: bool = True)
     return m.eval()
 
 
-def calibrate_head(model: nn.Module, raw_levels, cand_frac: float = 0.08, obj_level: float = 0.3, per_level: bool = True) -> None:
+def calibrate_head(model: nn.Module, raw_levels, cand_frac: float = 0.08, conf_thres: float = 0.25, per_level: bool = True) -> None:
     """Random weights give ~0 NMS candidates at conf 0.25, which would make the NMS leg of the
-    benchmark vacuous. Shift the head biases (random-init anyway) so that the load looks like a trained detector's
-    (~2,000 candidates per image over many classes and all pyramid levels):
-      * objectness: per level (per_level=True) or globally, bias += logit(obj_level) - q_{1-cand_frac} of the observed
-        objectness logits, so that ~cand_frac of the rows of EVERY level carry objectness > obj_level;
-      * classes: every (anchor, class) bias is set to minus the mean of its observed logit, so no class wins by its
-        random offset alone and the arg-max classes spread over the whole label set.
+    benchmark vacuous. Shift the head biases (random-init anyway) so that the load looks like the one SURVEY.md §8(d)
+    prescribes -- ~cand_frac of the rows (~2,000 of 25,200 per image) are NMS candidates, spread over every pyramid level
+    and over many classes:
+      * classes: every (anchor, class) bias is set to minus the mean of its observed logit, so no class wins by its random
+        offset alone and the arg-max classes spread over the label set;
+      * objectness: per level (or globally with per_level=False) the bias shift is solved (bisection on the sample) so that
+        exactly cand_frac of the rows pass BOTH tests of metrics.py:313-364: obj > conf_thres and obj * best class > conf_thres.
     `raw_levels`: list of (B, na, ny, nx, no) logits of a sample batch."""
-    import math
-
     head = model.model[-1]
     g = torch.Generator().manual_seed(0)
 
-    def quantile(v: torch.Tensor) -> float:
-        v = v.reshape(-1).float().cpu()
-        if v.numel() > 200000:
-            v = v[torch.randperm(v.numel(), generator=g)[:200000]]
-        return torch.quantile(v, 1.0 - cand_frac).item()
+    def sample(r: torch.Tensor):
+        r = r.reshape(-1, r.shape[-1]).float().cpu()
+        if r.shape[0] > 100000:
+            r = r[torch.randperm(r.shape[0], generator=g)[:100000]]
+        return r
 
-    target = math.log(obj_level / (1.0 - obj_level))
-    q_all = quantile(torch.cat([r[..., 4].reshape(-1).float().cpu() for r in raw_levels]))
+    def solve(obj: torch.Tensor, best_cls: torch.Tensor) -> float:
+        lo, hi = -30.0, 30.0
+        for _ in range(50):
+            mid = 0.5 * (lo + hi)
+            o = torch.sigmoid(obj + mid)
+            frac = float(((o > conf_thres) & (o * best_cls > conf_thres)).float().mean())
+            lo, hi = (mid, hi) if frac < cand_frac else (lo, mid)
+        return 0.5 * (lo + hi)
+
+    samples = []
     with torch.no_grad():
         for conv, r in zip(head.conv, raw_levels):
             b = conv.bias.view(head.na, -1)
-            b[:, 4] += target - (quantile(r[..., 4]) if per_level else q_all)
-            if per_level:
-                b[:, 5:] -= r[..., 5:].float().mean(dim=(0, 2, 3)).to(b.device)
-            else:
-                b[:, 5:] = 0.0
+            mean_c = r[..., 5:].float().mean(dim=(0, 2, 3))                 # (na, nc)
+            b[:, 5:] -= mean_c.to(b.device)
+            rs = sample((r.float() - torch.cat((torch.zeros_like(mean_c[:, :5]), mean_c), 1)[None, :, None, None, :].to(r.device)))
+            samples.append((rs[:, 4], torch.sigmoid(rs[:, 5:]).max(1).values))
+        if per_level:
+            for conv, (o, c) in zip(head.conv, samples):
+                conv.bias.view(head.na, -1)[:, 4] += solve(o, c)
+        else:
+            shift = solve(torch.cat([o for o, _ in samples]), torch.cat([c for _, c in samples]))
+            for conv in head.conv:
+                conv.bias.view(head.na, -1)[:, 4] += shift
 
 
 def synth_predictions(batch: int, n: int = 25200, nc: int = 80, seed: int = 0, cand_frac: float = 0.08, clusters: int = 200,

@@ -24,6 +24,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
+from torch.nn.modules.batchnorm import _BatchNorm
 
 from . import ops
 from .engine import _act_code, _round_up
@@ -109,7 +110,8 @@ class TrainEngine:
         cout, cin = conv.out_channels, conv.in_channels
         assert x.c == cin, (x.c, cin)
         oh, ow = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
-        has_bn = isinstance(bn, nn.BatchNorm2d)
+        has_bn = isinstance(bn, _BatchNorm)
+        sync = isinstance(bn, nn.SyncBatchNorm)  # statistics and their backward sums over the cross-rank batch
         if y is None:
             y = self.new_act(oh, ow, cout)
         z = self.new_act(oh, ow, cout) if has_bn else y
@@ -135,7 +137,7 @@ class TrainEngine:
             self.keep += [mean, invstd, scratch]
 
             def f_bn() -> None:
-                ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd)
+                ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
                 bn.num_batches_tracked += 1
                 ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, residual)
             self.fwd.append(f_bn)
@@ -164,7 +166,7 @@ class TrainEngine:
             if has_bn:
                 if gres is not None:
                     ops.add_slices(gy, gres, accumulate=True)  # shortcut branch: d(residual) += dy
-                ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz)
+                ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz, sync=sync)
                 self._padd(bn.bias, scratch[:cout].float())
                 self._padd(bn.weight, scratch[cout:].float())
             dw.zero_()
@@ -193,7 +195,8 @@ class TrainEngine:
         name = type(m).__name__
         c = m.conv
         bn = getattr(m, "batch_norm", None)
-        assert isinstance(c, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d)
+        assert isinstance(c, nn.Conv2d) and isinstance(bn, _BatchNorm)
+        sync = isinstance(bn, nn.SyncBatchNorm)
         H2, W2 = self.H // 2, self.W // 2
         Wp = W2 + 8
         dev = self.device
@@ -252,7 +255,7 @@ class TrainEngine:
         act = _act_code(m)
 
         def f_bn() -> None:
-            ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd)
+            ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
             bn.num_batches_tracked += 1
             ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, None)
         self.fwd.append(f_bn)
@@ -262,7 +265,7 @@ class TrainEngine:
         x_ptr = s2d.ptr() + 2 * 16  # logical pixel 0 lives at physical column 1
 
         def b() -> None:
-            ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz)
+            ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz, sync=sync)
             self._padd(bn.bias, scratch[:cout].float())
             self._padd(bn.weight, scratch[cout:].float())
             dw.zero_()

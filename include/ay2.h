@@ -347,6 +347,12 @@ int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_cstride, co
 int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
                    const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
                    double* s2, void* dz, int32_t dz_cstride, void* stream);
+/* The same in two phases, for SyncBatchNorm (scripts/train/train_model_builder.py:86-91): phase 1 computes this rank's s1 / s2,
+ * the caller sums them over the ranks (all-reduce of 2 c doubles), phase 2 applies with npix_total = pixels of the whole
+ * cross-rank batch. (The forward is ay2_bn_stats -> all-reduce of sum / sumsq -> ay2_bn_finalize with the total count.) */
+int ay2_bn_act_bwd_phase(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                         const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
+                         double* s2, void* dz, int32_t dz_cstride, int32_t phase, int64_t npix_total, void* stream);
 /* weight gradient of a conv: dw[cout][kh*kw][cin] (fp32, ACCUMULATED) += dz^T (*) x ; tcgen05, split-K */
 int ay2_conv_wgrad(const ay2_conv_desc* desc, const void* x, const void* dz, float* dw, void* stream);
 /* dst (+)= src over a channel slice: residual / concat / fan-out gradient accumulation */

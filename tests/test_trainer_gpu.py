@@ -149,4 +149,6 @@ def test_multi_scale_and_bucket_plan():
     eng._gstate = {k: v for k, v in eng._gstate.items() if not k.startswith("bwd")}
     outs = model(x)
     sum((o * o).sum() for o in outs).backward()
-    assert torch.allclose(eng.last_grad_flat, g_bucketed, rtol=1e-4, atol=1e-6)
+    # (split-K weight gradients accumulate with fp32 atomics: run-to-run order differs, so compare in norm)
+    rel = float((eng.last_grad_flat - g_bucketed).norm() / g_bucketed.norm())
+    assert rel < 1e-3, rel
