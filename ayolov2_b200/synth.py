@@ -34,24 +34,25 @@ def build_model(name: str = "yolov5s", seed: int = 0, randomize_bn: bool = True)
     return m.eval()
 
 
-def calibrate_head(model: nn.Module, raw_levels, cand_frac: float = 0.08, conf_thres: float = 0.25, per_level: bool = True) -> None:
+def calibrate_head(model: nn.Module, run_raw, cand_frac: float = 0.08, conf_thres: float = 0.25, per_level: bool = True) -> None:
     """Random weights give ~0 NMS candidates at conf 0.25, which would make the NMS leg of the
-    benchmark vacuous. Shift the head biases (random-init anyway) so that the load looks like the one SURVEY.md §8(d)
-    prescribes -- ~cand_frac of the rows (~2,000 of 25,200 per image) are NMS candidates, spread over every pyramid level
-    and over many classes:
-      * classes: every (anchor, class) bias is set to minus the mean of its observed logit, so no class wins by its random
-        offset alone and the arg-max classes spread over the label set;
-      * objectness: per level (or globally with per_level=False) the bias shift is solved (bisection on the sample) so that
-        exactly cand_frac of the rows pass BOTH tests of metrics.py:313-364: obj > conf_thres and obj * best class > conf_thres.
-    `raw_levels`: list of (B, na, ny, nx, no) logits of a sample batch."""
+    benchmark vacuous, and their head logits barely vary over the image (objectness: -6.6 +- 0.003 per anchor at stride 8,
+    a tenth of a bf16 step at that magnitude). The detect convolutions (random-init anyway) are therefore re-scaled so that
+    the load looks like the one SURVEY.md §8(d) prescribes -- ~cand_frac of the rows (~2,000 of 25,200 per image) are NMS
+    candidates, on every pyramid level, over many classes:
+      * the objectness / class biases are zeroed and the sample batch is run again, so that the logits are the pure filter
+        responses (small numbers, well resolved in bf16);
+      * objectness and class filters of every anchor are standardised on that sample: logit' = (logit - mean) / std, i.e.
+        weight /= std, bias = -mean / std, so the logits have unit spread (and every class the same);
+      * the objectness bias then gets the shift (bisection on the sample, per level or globally) at which exactly cand_frac
+        of the rows pass BOTH tests of metrics.py:313-364: obj > conf_thres and obj * best class score > conf_thres.
+    `run_raw`: callable returning the list of (B, na, ny, nx, no) logits of a sample batch with the model's CURRENT weights."""
     head = model.model[-1]
     g = torch.Generator().manual_seed(0)
 
-    def sample(r: torch.Tensor):
-        r = r.reshape(-1, r.shape[-1]).float().cpu()
-        if r.shape[0] > 100000:
-            r = r[torch.randperm(r.shape[0], generator=g)[:100000]]
-        return r
+    def refresh():
+        if hasattr(model, "invalidate_engine"):
+            model.invalidate_engine()
 
     def solve(obj: torch.Tensor, best_cls: torch.Tensor) -> float:
         lo, hi = -30.0, 30.0
@@ -64,12 +65,20 @@ def calibrate_head(model: nn.Module, raw_levels, cand_frac: float = 0.08, conf_t
 
     samples = []
     with torch.no_grad():
+        for conv in head.conv:
+            conv.bias.view(head.na, -1)[:, 4:] = 0.0
+        refresh()
+        raw_levels = [r.detach().float() for r in run_raw()]
         for conv, r in zip(head.conv, raw_levels):
-            b = conv.bias.view(head.na, -1)
-            mean_c = r[..., 5:].float().mean(dim=(0, 2, 3))                 # (na, nc)
-            b[:, 5:] -= mean_c.to(b.device)
-            rs = sample((r.float() - torch.cat((torch.zeros_like(mean_c[:, :5]), mean_c), 1)[None, :, None, None, :].to(r.device)))
-            samples.append((rs[:, 4], torch.sigmoid(rs[:, 5:]).max(1).values))
+            mean = r[..., 4:].mean(dim=(0, 2, 3))                        # (na, 1 + nc)
+            std = r[..., 4:].std(dim=(0, 2, 3)).clamp_min(1e-12)
+            w = conv.weight.view(head.na, -1, *conv.weight.shape[1:])    # (na, no, cin, 1, 1)
+            w[:, 4:] /= std.to(w.device)[:, :, None, None, None]
+            conv.bias.view(head.na, -1)[:, 4:] = (-mean / std).to(conv.bias.device)
+            z = ((r[..., 4:] - mean[None, :, None, None, :]) / std[None, :, None, None, :]).reshape(-1, r.shape[-1] - 4).cpu()
+            if z.shape[0] > 100000:
+                z = z[torch.randperm(z.shape[0], generator=g)[:100000]]
+            samples.append((z[:, 0], torch.sigmoid(z[:, 1:]).max(1).values))
         if per_level:
             for conv, (o, c) in zip(head.conv, samples):
                 conv.bias.view(head.na, -1)[:, 4] += solve(o, c)
@@ -77,6 +86,7 @@ def calibrate_head(model: nn.Module, raw_levels, cand_frac: float = 0.08, conf_t
             shift = solve(torch.cat([o for o, _ in samples]), torch.cat([c for _, c in samples]))
             for conv in head.conv:
                 conv.bias.view(head.na, -1)[:, 4] += shift
+    refresh()
 
 
 def synth_predictions(batch: int, n: int = 25200, nc: int = 80, seed: int = 0, cand_frac: float = 0.08, clusters: int = 200,

@@ -414,11 +414,9 @@ def main() -> None:
         return float(t.item())
 
     model = model_utils.build_model("yolov5s", seed=0).to(dev)
-    # make the NMS leg non-vacuous: ~8 % of the rows become candidates (see oracle/model_utils.calibrate_head)
-    with torch.no_grad():
-        _, raw = model(synth_images(4, 7).to(dev).float() / 255.0)
-    model_utils.calibrate_head(model, raw)
-    model.invalidate_engine()
+    # make the NMS leg non-vacuous: ~8 % of the rows of every level become candidates (ayolov2_b200.synth.calibrate_head)
+    sample = synth_images(8, 7).to(dev).float() / 255.0
+    model_utils.calibrate_head(model, lambda: model(sample)[1])
     det = Detector(model, BATCH, H, W, conf_thres=CONF, iou_thres=IOU, in_dtype=torch.uint8, device=dev)
     host_imgs = [synth_images(BATCH, 1000 + rank * 10 + i).pin_memory() for i in range(3)]
     dev_imgs = [h.to(dev) for h in host_imgs[:2]]

@@ -101,10 +101,8 @@ def test_fused_head_nms_equals_dense_path(multi_label, hw):
     model = synth.build_model("yolov5s", seed=2).cuda()
     B, (H, W) = 3, hw
     img = torch.randint(0, 256, (B, 3, H, W), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
-    with torch.no_grad():
-        _, raw = model(img.cuda().float() / 255.0)
-    synth.calibrate_head(model, raw, cand_frac=0.1)
-    model.invalidate_engine()
+    sample = img.cuda().float() / 255.0
+    synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.1)
     kw = dict(conf_thres=0.25, iou_thres=0.45, multi_label=multi_label, in_dtype=torch.uint8)
     fused = Detector(model, B, H, W, **kw)
     logits = Detector(model, B, H, W, fuse_candidates=False, **kw)

@@ -15,10 +15,8 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 torch.manual_seed(0)
 model = synth.build_model("yolov5s", seed=0).cuda()
 img = torch.randint(0, 256, (batch, 3, 640, 640), dtype=torch.uint8, device="cuda")
-with torch.no_grad():
-    _, raw = model(torch.randint(0, 256, (4, 3, 640, 640), dtype=torch.uint8, device="cuda").float() / 255.0)
-synth.calibrate_head(model, raw)
-model.invalidate_engine()
+sample = torch.randint(0, 256, (4, 3, 640, 640), dtype=torch.uint8, device="cuda").float() / 255.0
+synth.calibrate_head(model, lambda: model(sample)[1])
 det = Detector(model, batch, 640, 640, in_dtype=torch.uint8)
 eng = det.engine
 eng._img = img
