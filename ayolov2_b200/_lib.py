@@ -97,6 +97,7 @@ _PROTOS = {
                                        C.POINTER(C.c_void_p)]),
     "ay2_conv_plan_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ay2_conv_plan_destroy": (C.c_int, [C.c_void_p]),
+    "ay2_conv_plan_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ay2_conv_plan_flops": (C.c_double, [C.c_void_p]),
     "ay2_conv_reference_simt": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),

@@ -134,6 +134,55 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of a cluster (ranks 2k, 2k+1 = the two SMs of a TPC) execute ONE tcgen05.mma of
+// M = 256: each CTA holds its own 128 rows of A, HALF of the B tile and its own 128 accumulator lanes; the tensor cores
+// read both halves of B, so every byte of B is fetched (L2 -> SM) and stored once per PAIR instead of once per CTA.
+// The even ("leader") CTA issues the MMA and owns the pipeline barriers; the odd CTA's TMA loads signal the leader's
+// barrier: a shared::cluster address with bit 24 cleared names the same offset in the even CTA of the pair.
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kPairLeaderMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPairLeaderMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPairLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive (release at cluster scope) on the barrier at this offset in the pair's leader CTA
+__device__ __forceinline__ void mbar_arrive_pair_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp of EACH CTA, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[256 x N] (+)= A[256 x 16] B[N x 16]^T: issued by one thread of the leader CTA; descriptors are leader-local addresses
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` once all MMAs issued so far (by this thread) have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: MMA (kind::f16, A and B from shared memory, D in TMEM), commit, TMEM load
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

@@ -69,23 +69,30 @@ constexpr int kSmemPerSm = 227 * 1024;
 // channel planes [hi | lo | hi] and every weight as [w_hi | w_hi | w_lo] along K, so the unchanged main loop accumulates
 // x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32: fp32-equivalent products (the dropped x_lo w_lo term is 2^-16 relative) on
 // the same TMA / tcgen05 pipeline. Only the epilogue differs: exact SiLU, hi/lo split, three plane stores.
-template <int BLOCK_N, int CK, bool X3 = false>
+// PAIR = the CTA-pair form (ay2_ptx.cuh "CTA pair"): a cluster of two CTAs computes two neighbouring M tiles of one N tile
+// with ONE M = 256 tcgen05.mma.cta_group::2 per K step. Each CTA stages its own A tile and HALF of the weight tile, so
+// the weight bytes cross L2 -> SM (and occupy shared memory) once per pair: the stage shrinks from (128 + N) to
+// (128 + N / 2) operand rows and the ring gets deeper. Accumulators, epilogue and stores stay per CTA.
+template <int BLOCK_N, int CK, bool X3 = false, bool PAIR = false>
 struct ConvCfg {
   static constexpr bool kX3 = X3;
+  static constexpr bool kPair = PAIR;
   static constexpr int BN = BLOCK_N;
   static constexpr int SWA = CK * 2;                 // operand row bytes == swizzle span
   static constexpr int A_BYTES = 128 * SWA;
-  static constexpr int B_BYTES = BLOCK_N * SWA;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * SWA;  // per CTA
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OC = BLOCK_N < 64 ? BLOCK_N : 64;  // channels per output slab
   static constexpr int SWO = OC * 2;                       // output slab row bytes == swizzle span
   static constexpr int SLAB_BYTES = 128 * SWO;
   static constexpr int NSLAB = BLOCK_N / OC;
   static constexpr int STAGING_BYTES = 128 * BLOCK_N * 2 * (X3 ? 2 : 1);  // x3: hi slabs, then lo slabs
-  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256 + 1024;  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr + head-candidate list
+  // bias slice + barriers (2 NSTAGES + 4 + 4 <= 24) + tmem ptr (256 B) + head-candidate lists: (pixel, anchor) entries
+  // (768 B), their keys (3072 B) and images (768 B)
+  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 256 + 768 + 3072 + 768 + 256;
   // Small tiles are latency-bound per tile (TMA round trip, TMEM drain, store hand-off): co-residency of
   // several CTAs per SM interleaves independent tile streams. TMEM: CTAS_PER_SM * 2 * BLOCK_N <= 512 columns.
-  static constexpr int CTAS_PER_SM = X3 ? 1 : (BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1));
+  static constexpr int CTAS_PER_SM = (X3 || PAIR) ? 1 : (BLOCK_N <= 64 ? 3 : (BLOCK_N == 128 ? 2 : 1));
   // Epilogue warps: one group of 4 warps covers the 128 TMEM lanes and owns ONE output slab (<= 64 columns): it drains
   // it, stores it with TMA and waits for its own store only -- groups never synchronise with each other, and every
   // scheduler has EPI_GROUPS x CTAS_PER_SM epilogue warps to interleave (the drain is latency-bound per warp).
@@ -99,6 +106,7 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = 1024 + NSTAGES * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 64..512, power of two
   static_assert(NSTAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(!(X3 && PAIR), "the split-precision verification mode runs single CTAs");
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two");
 };
 
@@ -140,7 +148,8 @@ constexpr int kHeadDenseMax = 256;  // (pixel, anchor) pairs per tile (of 384) u
 // mostly failing pixels. Tiles with more than kHeadDenseMax passing pairs fall back to one thread per pixel.
 template <class Cfg>
 __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
-                                                int lane, int ewarp_all, unsigned short* list, int* cnt) {
+                                                int lane, int ewarp_all, unsigned short* list, int* cnt,
+                                                unsigned long long* keys_s, short* img_s) {
   const HeadCandParams& h = p.hc;
   const int box_rows = p.BH * p.BW;
   const int plane = h.out_h * h.out_w;
@@ -253,8 +262,23 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
           bidx = oi;
         }
       }
-      const bool ok = lane == 0 && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
-      head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx), lane);
+      // The key is parked in shared memory; the tile's keys are appended together below. One global atomicAdd per ENTRY
+      // (r02: ~2,000 candidates per image on all levels) serialises in L2 on the image's counter: measured 443 us for the
+      // stride-8 detect convolution instead of 65 us.
+      if (lane == 0) {
+        const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+        keys_s[e] = ok ? ((static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx)) : ~0ull;
+        img_s[e] = static_cast<short>(b);
+      }
+    }
+  }
+  if (!h.multi_label) {
+    // ---- phase 3: append the tile's keys, one atomicAdd per warp and image (a tile rarely spans two images)
+    named_bar_sync(1, Cfg::EPI_THREADS);
+    for (int e0 = ewarp_all * 32; e0 < n; e0 += Cfg::EPI_THREADS) {
+      const int e = e0 + lane;
+      const unsigned long long key = e < n ? keys_s[e] : ~0ull;
+      head_cand_push(h, key != ~0ull, e < n ? img_s[e] : 0, key, lane);
     }
   }
 }
@@ -373,9 +397,9 @@ __device__ __forceinline__ void drain_dispatch(const ConvKernelParams& p, uint32
   }
 }
 
-template <int BLOCK_N, int CK, bool X3>
-__global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLOCK_N, CK, X3>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
-  using Cfg = ConvCfg<BLOCK_N, CK, X3>;
+template <int BLOCK_N, int CK, bool X3, bool PAIR>
+__global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvCfg<BLOCK_N, CK, X3, PAIR>::CTAS_PER_SM) conv_tc_kernel(const __grid_constant__ ConvKernelParams p) {
+  using Cfg = ConvCfg<BLOCK_N, CK, X3, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle patterns repeat every 1024 B and UMMA descriptors assume base_offset 0
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -391,6 +415,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(res_full + 4);
   int* cand_cnt = reinterpret_cast<int*>(tmem_ptr_s + 2);                               // [2], one per tile parity
   unsigned short* cand_list = reinterpret_cast<unsigned short*>(bars) + 128;           // 256 B past the barriers: 128 x 3 entries
+  unsigned long long* cand_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [384]
+  short* cand_img = reinterpret_cast<short*>(reinterpret_cast<uint8_t*>(bars) + 1024 + 3072);                      // [384]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -402,11 +428,13 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
     cand_cnt[0] = cand_cnt[1] = 0;
     for (int i = 0; i < Cfg::NSTAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.csize);  // every CTA sharing the multicast B tile must release the stage
+      // multicast form: every CTA sharing the B tile must release the stage; pair form: the leader's one commit does
+      mbar_init(&empty_bar[i], PAIR ? 1 : p.csize);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
+      // pair form: one arrival per epilogue group of BOTH CTAs, on the leader's barrier
+      mbar_init(&tmem_empty[i], PAIR ? 2 * Cfg::EPI_GROUPS : Cfg::EPI_THREADS);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
@@ -414,7 +442,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmOut);
   }
-  if (warp == 2) tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_ptr_s, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_ptr_s, Cfg::TMEM_COLS);
+  }
   tcgen05_fence_before();
   uint32_t tmem_base = 0;
   if (p.csize > 1) {
@@ -488,6 +519,16 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
               if (elect_one()) {
                 uint8_t* sa = stages + stage * Cfg::STAGE_BYTES;
                 uint8_t* sb = sa + Cfg::A_BYTES;
+                if constexpr (PAIR) {
+                  // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of the two stages
+                  if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    if (j < p.NB)
+                      tma_load_4d_pair(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx, by[j] + dy, bb[j]);
+                  }
+                  tma_load_2d_pair(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0 + crank * (BLOCK_N / 2));
+                } else {
                 mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -502,6 +543,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
                 } else {
                   tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
                 }
+                }
               }
               __syncwarp();
               if (++stage == Cfg::NSTAGES) {
@@ -513,10 +555,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+  } else if (warp == 1 && (!PAIR || crank == 0)) {
+    // =============================== MMA issuer (pair form: the leader CTA only) ===============================
     {  // warp-uniform loop, one elected lane issues (see the producer)
-      constexpr uint32_t idesc = make_idesc_bf16_f32(128, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(PAIR ? 256 : 128, BLOCK_N);
       int stage = 0, phase = 0, it = 0;
       for (int item = item0; item < total_items; item += item_step, ++it) {
         const int acc = it & 1;
@@ -535,11 +577,17 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
             for (int k = 0; k < CK / 16 && !(p.experiment & 1); ++k) {
               const uint64_t adesc = make_smem_desc_kmajor(a_addr + k * 32, Cfg::SWA);
               const uint64_t bdesc = make_smem_desc_kmajor(b_addr + k * 32, Cfg::SWA);
-              umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+              if constexpr (PAIR) umma_f16_ss_pair(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(tmem_d, adesc, bdesc, idesc, (kc | k) != 0 ? 1u : 0u);
             }
+            if constexpr (PAIR) {
+              umma_commit_pair(&empty_bar[stage], 3);                              // the stage is free in both CTAs
+              if (kc == num_k_chunks - 1) umma_commit_pair(&tmem_full[acc], 3);    // both CTAs' accumulators are ready
+            } else {
             if (p.csize > 1) umma_commit_mc(&empty_bar[stage], cmask);  // release the stage in every CTA of the cluster
             else umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
             if (kc == num_k_chunks - 1) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+            }
           }
           __syncwarp();
           if (++stage == Cfg::NSTAGES) {
@@ -607,9 +655,12 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
                           smem_u32(slab), smem_u32(bias_s) + egrp * Cfg::OC * 4, et);
       if (eall == 0 && it == 0) CV_DBG(12);  // first tile drained by this thread
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty[acc]);  // accumulator drained -> back to the MMA warp
+      if constexpr (!PAIR) mbar_arrive(&tmem_empty[acc]);  // accumulator drained -> back to the MMA warp
       fence_proxy_async_smem();       // staging complete -> visible to the TMA store
       named_bar_sync(gbar, 128);
+      if constexpr (PAIR) {  // the group has drained its columns: ONE arrival on the pair leader's barrier
+        if (et == 0) mbar_arrive_pair_leader(&tmem_empty[acc]);
+      }
       if (leader) {
         if (lane < p.NB) {
           tma_store_4d(&p.tmOut, slab + lane * box_rows * Cfg::SWO, nc0, cx, cy, cb);
@@ -627,7 +678,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
         // only read); no group may start rewriting its slab before every group has finished reading
         named_bar_sync(1, Cfg::EPI_THREADS);
         if (eall == 0) cand_cnt[(it + 1) & 1] = 0;  // the other counter was last read before the barrier above
-        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall >> 5, cand_list, &cand_cnt[it & 1]);
+        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall >> 5, cand_list, &cand_cnt[it & 1], cand_keys, cand_img);
         named_bar_sync(1, Cfg::EPI_THREADS);
       }
     }
@@ -646,7 +697,8 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3>::THREADS, ConvCfg<BLO
   }
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -1000,7 +1052,7 @@ using namespace ay2;
 struct ay2_conv_plan {
   ConvKernelParams kp;
   ay2_conv_desc desc;
-  int block_n, ck;
+  int block_n, ck, pair;
   int ctas_per_sm, threads;
   int grid, halo;
   size_t smem;
@@ -1014,12 +1066,12 @@ extern "C" int ay2_conv_block_n(int32_t cout) {
   return 256;
 }
 
-template <int BN, int CK, bool X3>
+template <int BN, int CK, bool X3, bool PAIR = false>
 static void bind_kernel(ay2_conv_plan* pl) {
-  pl->kernel = conv_tc_kernel<BN, CK, X3>;
-  pl->smem = ConvCfg<BN, CK, X3>::SMEM_BYTES;
-  pl->ctas_per_sm = ConvCfg<BN, CK, X3>::CTAS_PER_SM;
-  pl->threads = ConvCfg<BN, CK, X3>::THREADS;
+  pl->kernel = conv_tc_kernel<BN, CK, X3, PAIR>;
+  pl->smem = ConvCfg<BN, CK, X3, PAIR>::SMEM_BYTES;
+  pl->ctas_per_sm = ConvCfg<BN, CK, X3, PAIR>::CTAS_PER_SM;
+  pl->threads = ConvCfg<BN, CK, X3, PAIR>::THREADS;
 }
 
 static int pick_box(int H, int W, int* bh, int* bw) {
@@ -1190,6 +1242,18 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   // neighbouring unicast requests, so multicast saves no LTS bandwidth and only adds lock-step. Off by default.
   static const int env_cluster = getenv("AY2_CONV_CLUSTER") ? atoi(getenv("AY2_CONV_CLUSTER")) : 1;
   kp.csize = (env_cluster == 2 && kp.num_m_tiles >= 2) ? 2 : 1;
+  // CTA-pair form (tcgen05 cta_group::2): for the wide tiles whose operand ingest is dominated by the weight tile -- N tile
+  // of 128 / 256 over whole 64-channel chunks -- when there are enough M tiles to keep every SM pair busy.
+  // AY2_CONV_PAIR: 0 = never, 1 (default) = N >= 128 and K >= 256, 2 = every eligible layer.
+  static const int env_pair = getenv("AY2_CONV_PAIR") ? atoi(getenv("AY2_CONV_PAIR")) : 1;
+  int dev0 = 0, sms0 = 148;
+  cudaGetDevice(&dev0);
+  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+  const int ktot = d->kh * d->kw * d->cin;
+  const bool pair = env_pair > 0 && !d->x3 && (bn == 128 || bn == 256) && ck == 64 && kp.num_m_tiles >= sms0 &&
+                    (env_pair == 2 || ktot >= 256);
+  if (pair) kp.csize = 2;
+  pl->pair = pair ? 1 : 0;
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);
   const int oc = bn < 64 ? bn : 64;
   // output view: pixel stride / row pitch / image pitch (a parity sub-grid doubles the first and keeps the others)
@@ -1220,7 +1284,10 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
     if constexpr (BN * CKV < 256 * 64) {                          \
       if (d->x3) bind_kernel<BN, CKV, true>(pl);                  \
     }                                                             \
-    if (!d->x3) bind_kernel<BN, CKV, false>(pl);                  \
+    if constexpr (BN >= 128 && CKV == 64) {                       \
+      if (pair) bind_kernel<BN, CKV, false, true>(pl);            \
+    }                                                             \
+    if (!d->x3 && !pl->kernel) bind_kernel<BN, CKV, false>(pl);   \
   }
   AY2_BIND(32, 16) AY2_BIND(32, 32) AY2_BIND(32, 64)
   AY2_BIND(64, 16) AY2_BIND(64, 32) AY2_BIND(64, 64)
@@ -1320,6 +1387,13 @@ extern "C" int ay2_conv_plan_set_debug(ay2_conv_plan* pl, unsigned long long* db
   if (info4)
     info4[0] = pl->grid, info4[1] = pl->ctas_per_sm, info4[2] = pl->halo ? -pl->block_n : pl->block_n,
     info4[3] = (pl->halo ? pl->kp.hl_pairs_x * pl->kp.hl_bands_y : 1) * pl->kp.num_m_tiles * pl->kp.num_n_tiles;
+  return AY2_OK;
+}
+
+extern "C" int ay2_conv_plan_info(const ay2_conv_plan* pl, int32_t* out8) {
+  AY2_REQUIRE(pl && out8, "ay2_conv_plan_info: null argument");
+  out8[0] = pl->grid, out8[1] = pl->ctas_per_sm, out8[2] = pl->block_n, out8[3] = pl->ck, out8[4] = pl->halo, out8[5] = pl->pair;
+  out8[6] = pl->kp.csize, out8[7] = (int32_t)pl->smem;
   return AY2_OK;
 }
 

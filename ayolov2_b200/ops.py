@@ -189,6 +189,9 @@ class ConvPlan:
         info = (C.c_int32 * 4)()
         lib.ay2_conv_plan_set_debug(h, None, info)
         self.halo = info[2] < 0  # 3x3 / s1 halo kernel (conv_halo_kernel) instead of conv_tc_kernel
+        info8 = (C.c_int32 * 8)()
+        lib.ay2_conv_plan_info(h, info8)
+        self.pair = bool(info8[5])  # CTA-pair form (tcgen05 cta_group::2)
 
     def run(self, stream: Optional[int] = None) -> None:
         _lib.check(self._lib.ay2_conv_plan_run(self._h, stream if stream is not None else _lib.current_stream_ptr()),

@@ -98,6 +98,9 @@ int ay2_conv_plan_create(const ay2_conv_desc* desc, const void* in, const void* 
                          const void* residual, void* out, ay2_conv_plan** plan);
 int ay2_conv_plan_run(const ay2_conv_plan* plan, void* stream);
 int ay2_conv_plan_destroy(ay2_conv_plan* plan);
+/* How the plan will run: out8 = {grid, CTAs per SM, N tile, K chunk, halo kernel (0/1), CTA-pair form -- tcgen05
+ * cta_group::2, two CTAs of a cluster sharing every weight tile -- (0/1), cluster size, dynamic shared memory bytes}. */
+int ay2_conv_plan_info(const ay2_conv_plan* plan, int32_t* out8);
 /* FLOPs (2*MAC, unpadded) one run of the plan performs — used for roofline accounting. */
 double ay2_conv_plan_flops(const ay2_conv_plan* plan);
 

@@ -34,6 +34,17 @@ CASES = [
 ]
 
 
+# CTA-pair form (tcgen05 cta_group::2): N tile 128 / 256, K >= 256, at least one M tile per SM (>= 148 x 128 output pixels)
+PAIR_CASES = [
+    (2, 112, 112, 256, 256, 1, 1, 0, 1, False, False, False),   # 1x1, 196 M tiles
+    (2, 112, 96, 256, 128, 1, 1, 0, 1, True, True, True),       # N tile 128, residual, channel slices, 168 M tiles
+    (3, 160, 160, 64, 128, 3, 2, 1, 1, False, False, False),    # 3x3 stride 2, K = 576, 150 M tiles
+    (1, 160, 160, 128, 256, 3, 2, 1, 1, False, False, True),    # 3x3 stride 2, 50 M tiles -> too few: single-CTA form
+    (1, 140, 140, 512, 512, 1, 1, 0, 0, False, False, False),   # two N tiles, ODD number of M tiles (154 boxes of 8x16 -> 153.1)
+    (7, 53, 61, 256, 255, 1, 1, 0, 0, False, False, False),     # head-like 255 channels, ragged boxes, batch straddling pairs
+]
+
+
 def _run_case(case, seed=0):
     from ayolov2_b200 import ops
 
@@ -61,6 +72,10 @@ def _run_case(case, seed=0):
     plan.run()
     torch.cuda.synchronize()
     got = y.tensor().float().clone()
+    if seed == 1:  # a second run of the same plan (persistent barriers / TMEM are re-initialised per launch)
+        plan.run()
+        torch.cuda.synchronize()
+        assert torch.equal(got, y.tensor().float())
     untouched = ybuf.clone()
     untouched[..., c0_out:c0_out + Cout] = 7.0
     assert torch.all(untouched == 7.0), "conv wrote outside its channel slice"
@@ -87,11 +102,21 @@ def _run_case(case, seed=0):
     simt = y.tensor().float()
     err2 = (got - simt).abs()
     assert float((err2 - (2.0 ** -7 * simt.abs() + 1e-2)).max()) <= 0, f"case {case}: SIMT mismatch {float(err2.max())}"
+    return plan
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
 def test_conv_parity(case):
     _run_case(case)
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[f"p{i}" for i in range(len(PAIR_CASES))])
+def test_conv_parity_cta_pair(case):
+    """The same parity bar for the cta_group::2 form; the plan reports which form it chose."""
+    plan = _run_case(case, seed=1)
+    out_px = case[0] * ((case[1] + 2 * case[7] - case[5]) // case[6] + 1) * ((case[2] + 2 * case[7] - case[5]) // case[6] + 1)
+    if out_px >= 150 * 128:
+        assert plan.pair, "expected the CTA-pair form"
 
 
 def test_conv_inplace_residual():

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 CONF, IOU = 0.25, 0.45
 
 
-def _setup(batch):
+def _setup(batch, bias_only=False):
     from ayolov2_b200 import synth
     from ayolov2_b200.detector import Detector
 
@@ -25,7 +25,11 @@ def _setup(batch):
     g = torch.Generator().manual_seed(77)
     imgs = torch.randint(0, 256, (64, 3, 640, 640), generator=g, dtype=torch.uint8)
     sample = imgs[:4].cuda().float() / 255.0
-    synth.calibrate_head(model, lambda: model(sample)[1])  # the benchmark's head calibration: a non-vacuous NMS load
+    if bias_only:  # well-conditioned head for the logit comparison against the fp32 oracle
+        with torch.no_grad():
+            synth.calibrate_head_bias_only(model, model(sample)[1])
+    else:          # the benchmark's head calibration: ~2,000 candidates per image over all levels and many classes
+        synth.calibrate_head(model, lambda: model(sample)[1])
     return model, imgs, Detector(model, batch, 640, 640, conf_thres=CONF, iou_thres=IOU, in_dtype=torch.uint8)
 
 
@@ -62,7 +66,7 @@ def test_full_size_images_against_oracle():
     chaotic under bf16-level perturbations, which is why NMS parity is pinned on IDENTICAL inputs (tests/test_nms_gpu.py)."""
     from oracle import yolo_oracle
 
-    model, imgs, _ = _setup(8)
+    model, imgs, _ = _setup(8, bias_only=True)
     pick = [0, 5, 13, 22, 31, 40, 52, 63]
     x = imgs[pick].float() / 255.0
     got_pred, got_raw = model(x.cuda())
