@@ -69,6 +69,12 @@ struct NmsWorkspaceView {
   unsigned long long* keys;  // [batch][key_stride]
   long long key_stride;
   unsigned* rows;            // [batch][n]
+  // class-group split of the suppression kernel (nms.cu): per (image, group) kept lists + the per-image ticket / fallback flag
+  int* done;                 // [batch]
+  int* wide;                 // [batch]
+  unsigned long long* part_keys;  // [batch][groups][max_det]
+  float* part_det;                // [batch][groups][max_det][6]
+  int* part_count;                // [batch][groups]
 };
 NmsWorkspaceView nms_workspace_view(const ay2_nms_params* p, void* workspace);
 

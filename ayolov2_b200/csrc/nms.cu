@@ -316,10 +316,22 @@ __global__ void nms_score_rows_kernel(BoxSource src, ay2_nms_params p, const uin
   stage_flush(st, kb, &counts[b], p.max_candidates, lane);
 }
 
-__global__ void __launch_bounds__(kNmsThreads, 1)
-    nms_sort_scan_kernel(BoxSource src, ay2_nms_params p, unsigned long long* __restrict__ keys, long long key_stride,
-                         const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
-                         int* __restrict__ overflow, long long* __restrict__ trace, const float* __restrict__ wh_scale) {
+// Where one resolved image (or one class group of it) goes: rows [max_det][6], optionally the rows' 64-bit keys (the merge of
+// class groups needs the global order), and the row count.
+struct NmsDst {
+  float* det;
+  unsigned long long* keys;
+  int* count;
+};
+
+// Resolves image b -- or, with ngroups > 1, only its candidates whose class c has c % ngroups == group (classes never
+// suppress each other under per-class offsets, so greedy NMS splits exactly along classes; the caller merges the groups'
+// kept lists by key). Sets *wide_flag when a box leaves the disjoint-class window (the split is then invalid).
+__device__ __noinline__ void nms_image(const BoxSource& src, ay2_nms_params p, unsigned long long* __restrict__ keys,
+                                       long long key_stride, const int* __restrict__ counts, const NmsDst dst,
+                                       int* __restrict__ overflow, long long* __restrict__ trace,
+                                       const float* __restrict__ wh_scale, const int b, const int ngroups, const int group,
+                                       int* __restrict__ wide_flag) {
 #define AY2_NMS_MARK(k)                                                    \
   do {                                                                     \
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); \
@@ -340,12 +352,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   unsigned* mask = reinterpret_cast<unsigned*>(kept_idx + kChunk);                   // [kChunk][kChunkWords]
   __shared__ int s_kept, s_new, s_wide;
 
-  const int b = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int wid = tid >> 5;
   const int nwarp = blockDim.x >> 5;
   const int nc = p.no - 5;
+  __syncthreads();  // a second call in the same CTA (fallback after a failed class split) re-uses the shared arrays
   // per-image class-offset scale (torchvision's batched_nms coordinate trick: max coordinate of the image + 1). A scale
   // that small fails the disjoint-window test below, so such images take the single-segment (exact, all-pairs) route.
   if (wh_scale) p.max_wh = __fadd_rn(wh_scale[b], 1.0f);
@@ -359,7 +371,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     s_wide = 0;
   }
   if (n == 0) {
-    if (tid == 0) out_count[b] = 0;
+    if (tid == 0) *dst.count = 0;
     return;
   }
   // ---------------------------------------------------------------- sort (ascending key == descending score)
@@ -367,7 +379,39 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   while (npow2 < n) npow2 <<= 1;
   unsigned long long* gk = keys + (long long)b * key_stride;
   const unsigned long long* sorted;
-  if (npow2 <= kSortSmemKeys) {
+  if (ngroups > 1) {
+    // class-group filter while loading (the caller guarantees n <= kSortSmemKeys); order is irrelevant before the sort
+    __shared__ int s_take;
+    if (tid == 0) s_take = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+      const int i = i0 + tid;
+      unsigned long long key = 0;
+      bool mine = false;
+      if (i < n) {
+        key = gk[i];
+        mine = static_cast<int>((static_cast<unsigned>(key) % nc) % ngroups) == group;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+      int base = 0;
+      if (lane == 0 && m) base = atomicAdd(&s_take, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (mine) skeys[base + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+    __syncthreads();
+    n = s_take;
+    if (n == 0) {
+      if (tid == 0) *dst.count = 0;
+      return;
+    }
+    npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
+    for (int i = n + tid; i < npow2; i += blockDim.x) skeys[i] = ~0ull;
+    __syncthreads();
+    if (npow2 <= 2 * kNmsThreads) bitonic_sort_regs(skeys, npow2);
+    else bitonic_sort(skeys, npow2);
+    sorted = skeys;
+  } else if (npow2 <= kSortSmemKeys) {
     for (int i = tid; i < npow2; i += blockDim.x) skeys[i] = i < n ? gk[i] : ~0ull;
     __syncthreads();
     if (npow2 <= 2 * kNmsThreads) bitonic_sort_regs(skeys, npow2);
@@ -708,18 +752,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       const unsigned long long key = sorted[i];
       const unsigned idx = static_cast<unsigned>(key);
       const float4 bx = rbox[i];
-      float* o = out_det + ((long long)b * p.max_det + k) * 6;
+      float* o = dst.det + (long long)k * 6;
       o[0] = bx.x;
       o[1] = bx.y;
       o[2] = bx.z;
       o[3] = bx.w;
       o[4] = __uint_as_float(~static_cast<unsigned>(key >> 32));
       o[5] = static_cast<float>(idx % nc);
+      if (dst.keys) dst.keys[k] = key;
       ++k;
     }
     AY2_NMS_MARK(13);
     __syncthreads();
-    if (tid == 0) out_count[b] = min(s_scan[nwarp - 1], p.max_det);
+    if (tid == 0) {
+      *dst.count = min(s_scan[nwarp - 1], p.max_det);
+      if (s_wide && wide_flag) atomicExch(wide_flag, 1);
+    }
     AY2_NMS_MARK(7);
     if (trace && b == 0 && tid == 0) {
       trace[8] = n;
@@ -840,7 +888,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
       kbo[k] = cbo[gi];
       karea[k] = carea[gi];
       kcls[k] = ccls[gi];
-      float* o = out_det + ((long long)b * p.max_det + k) * 6;
+      float* o = dst.det + (long long)k * 6;
+      if (dst.keys) dst.keys[k] = sorted[cs + gi];
       const float4 bx = cbox[gi];
       o[0] = bx.x;
       o[1] = bx.y;
@@ -853,7 +902,84 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
     if (tid == 0) s_kept = kc + nnew;
     __syncthreads();
   }
-  if (tid == 0) out_count[b] = s_kept;
+  if (tid == 0) {
+    *dst.count = s_kept;
+    if (s_wide && wide_flag) atomicExch(wide_flag, 1);
+  }
+}
+
+// One CTA per (image, class group). With one group the CTA resolves the whole image straight into the output. With G > 1
+// (64 images leave more than half of the 148 SMs idle, and a group's sort / scan is a fraction of the image's) each CTA
+// resolves its classes into a partial list; the LAST CTA of an image to finish (ticket counter) merges the partial lists
+// by key -- every row's rank is its own index plus the number of smaller keys in the other lists -- or, if the class
+// split was invalid for this image (a box outside the disjoint-class window, more candidates than the shared-memory
+// sort holds, a max_nms cut), resolves the whole image again by itself. Tickets and flags are left zeroed for the next launch.
+__global__ void __launch_bounds__(kNmsThreads, 1)
+    nms_sort_scan_kernel(BoxSource src, ay2_nms_params p, unsigned long long* __restrict__ keys, long long key_stride,
+                         const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
+                         int* __restrict__ overflow, long long* __restrict__ trace, const float* __restrict__ wh_scale, int G,
+                         float* __restrict__ part_det, unsigned long long* __restrict__ part_keys, int* __restrict__ part_count,
+                         int* __restrict__ done, int* __restrict__ wide) {
+  const int b = blockIdx.x / G, g = blockIdx.x - b * G;
+  const NmsDst whole{out_det + (long long)b * p.max_det * 6, nullptr, out_count + b};
+  if (G == 1) {
+    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr);
+    return;
+  }
+  const int tid = threadIdx.x;
+  const int n_all = counts[b];
+  const bool splittable = n_all <= kSortSmemKeys && n_all <= p.max_nms && n_all <= p.max_candidates;
+  const long long slot = (long long)b * G + g;
+  if (splittable) {
+    const NmsDst part{part_det + slot * p.max_det * 6, part_keys + slot * p.max_det, part_count + slot};
+    nms_image(src, p, keys, key_stride, counts, part, overflow, trace, wh_scale, b, G, g, wide + b);
+  } else if (tid == 0) {
+    atomicExch(wide + b, 1);
+  }
+  __shared__ int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(done + b, 1);
+  __syncthreads();
+  if (s_ticket != G - 1) return;
+  __threadfence();
+  if (*reinterpret_cast<volatile int*>(wide + b)) {
+    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr);
+  } else {
+    int total = 0;
+    for (int h = 0; h < G; ++h) total += *reinterpret_cast<volatile int*>(part_count + (long long)b * G + h);
+    for (int e = tid; e < G * p.max_det; e += blockDim.x) {
+      const int h = e / p.max_det, i = e - h * p.max_det;
+      const int cnt = *reinterpret_cast<volatile int*>(part_count + (long long)b * G + h);
+      if (i >= cnt) continue;
+      const unsigned long long* mine = part_keys + ((long long)b * G + h) * p.max_det;
+      const unsigned long long key = __ldcg(mine + i);
+      int rank = i;
+      for (int o = 0; o < G; ++o) {
+        if (o == h) continue;
+        const unsigned long long* other = part_keys + ((long long)b * G + o) * p.max_det;
+        int lo = 0, hi = *reinterpret_cast<volatile int*>(part_count + (long long)b * G + o);
+        while (lo < hi) {  // number of keys of list o below `key` (keys are unique: score bits, then candidate index)
+          const int mid = (lo + hi) >> 1;
+          if (__ldcg(other + mid) < key) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < p.max_det) {
+        const float* r = part_det + (((long long)b * G + h) * p.max_det + i) * 6;
+        float* o6 = whole.det + (long long)rank * 6;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) o6[q] = __ldcg(r + q);
+      }
+    }
+    if (tid == 0) *whole.count = min(total, p.max_det);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    done[b] = 0;
+    wide[b] = 0;
+  }
 }
 
 constexpr size_t kNmsChunkBytes = sizeof(float4) * (2 * kChunk + kMaxDetCap) + sizeof(float) * (2 * kChunk + kMaxDetCap) +
@@ -877,13 +1003,18 @@ static long long key_stride_for(const ay2_nms_params* p) {
 
 using namespace ay2;
 
-// workspace layout: [counts int32 x B][overflow int32][row_counts int32 x B][pad to 256]
+// workspace layout: [counts int32 x B][overflow int32][row_counts int32 x B][done int32 x B][wide int32 x B][pad to 256]
 //                   [keys u64 x B x key_stride][rows u32 x B x n]
-static size_t nms_head_bytes(const ay2_nms_params* p) { return ((sizeof(int) * (2 * p->batch + 1) + 255) / 256) * 256; }
+//                   [partial keys u64 x B x G x max_det][partial rows f32 x B x G x max_det x 6][partial counts int32 x B x G]
+constexpr int kMaxGroups = 4;  // class groups (CTAs) per image
+static size_t nms_head_ints(const ay2_nms_params* p) { return 4 * (size_t)p->batch + 1; }
+static size_t nms_head_bytes(const ay2_nms_params* p) { return ((sizeof(int) * nms_head_ints(p) + 255) / 256) * 256; }
+static size_t nms_rows_bytes(const ay2_nms_params* p) { return ((sizeof(unsigned) * (size_t)p->batch * (size_t)p->n + 255) / 256) * 256; }
 extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
   if (!p) return 0;
-  return nms_head_bytes(p) + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p) +
-         sizeof(unsigned) * (size_t)p->batch * (size_t)p->n;
+  const size_t parts = (size_t)p->batch * kMaxGroups;
+  return nms_head_bytes(p) + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p) + nms_rows_bytes(p) +
+         parts * p->max_det * (sizeof(unsigned long long) + 6 * sizeof(float)) + parts * sizeof(int);
 }
 
 namespace ay2 {
@@ -892,16 +1023,22 @@ NmsWorkspaceView nms_workspace_view(const ay2_nms_params* p, void* workspace) {
   v.counts = static_cast<int*>(workspace);
   v.overflow = v.counts + p->batch;
   v.row_counts = v.overflow + 1;
+  v.done = v.row_counts + p->batch;
+  v.wide = v.done + p->batch;
   v.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + nms_head_bytes(p));
   v.key_stride = key_stride_for(p);
   v.rows = reinterpret_cast<unsigned*>(v.keys + (size_t)p->batch * v.key_stride);
+  const size_t parts = (size_t)p->batch * kMaxGroups;
+  v.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(v.rows) + nms_rows_bytes(p));
+  v.part_det = reinterpret_cast<float*>(v.part_keys + parts * p->max_det);
+  v.part_count = reinterpret_cast<int*>(v.part_det + parts * p->max_det * 6);
   return v;
 }
 }  // namespace ay2
 
 static int nms_generate_candidates(const BoxSource& src, const ay2_nms_params* p, const uint8_t* class_mask,
                                    const NmsWorkspaceView& v, cudaStream_t st) {
-  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * (2 * p->batch + 1), st));
+  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * nms_head_ints(p), st));
   nms_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, v.rows, v.row_counts);
   AY2_CHECK_LAUNCH();
   nms_score_rows_kernel<<<dim3(16, p->batch), 256, 0, st>>>(src, *p, class_mask, v.rows, v.row_counts, v.keys, v.key_stride,
@@ -936,8 +1073,18 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
     AY2_CHECK_CUDA(cudaMalloc(&trace, 16 * sizeof(long long)));
     AY2_CHECK_CUDA(cudaMemset(trace, 0, 16 * sizeof(long long)));
   }
-  nms_sort_scan_kernel<<<p->batch, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, v.keys, v.key_stride, v.counts, out_det,
-                                                                     out_count, v.overflow, trace, wh_scale);
+  // class groups per image: as many CTAs as the SMs can hold at once (one CTA per SM), at most kMaxGroups; greedy NMS only
+  // splits along classes when classes are separated by offsets (not agnostic) and there is more than one class
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static const int env_groups = getenv("AY2_NMS_GROUPS") ? atoi(getenv("AY2_NMS_GROUPS")) : 0;
+  int G = env_groups > 0 ? env_groups : sms / p->batch;
+  if (G > kMaxGroups) G = kMaxGroups;
+  if (G < 1 || p->agnostic || p->no - 5 < 2 || wh_scale) G = 1;
+  nms_sort_scan_kernel<<<p->batch * G, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, v.keys, v.key_stride, v.counts, out_det, out_count,
+                                                                         v.overflow, trace, wh_scale, G, v.part_det, v.part_keys,
+                                                                         v.part_count, v.done, v.wide);
   AY2_CHECK_LAUNCH();
   if (trace) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1025,7 +1172,7 @@ extern "C" int ay2_nms_candidates_begin(const ay2_nms_params* p, void* workspace
   AY2_REQUIRE(workspace_bytes >= ay2_nms_workspace_bytes(p), "NMS workspace too small (%zu < %zu)", workspace_bytes,
               ay2_nms_workspace_bytes(p));
   const NmsWorkspaceView v = nms_workspace_view(p, workspace);
-  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * (2 * p->batch + 1), static_cast<cudaStream_t>(stream)));
+  AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * nms_head_ints(p), static_cast<cudaStream_t>(stream)));
   return AY2_OK;
 }
 

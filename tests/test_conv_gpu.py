@@ -41,7 +41,7 @@ PAIR_CASES = [
     (3, 160, 160, 64, 128, 3, 2, 1, 1, False, False, False),    # 3x3 stride 2, K = 576, 150 M tiles
     (1, 160, 160, 128, 256, 3, 2, 1, 1, False, False, True),    # 3x3 stride 2, 50 M tiles -> too few: single-CTA form
     (1, 140, 140, 512, 512, 1, 1, 0, 0, False, False, False),   # two N tiles, ODD number of M tiles (154 boxes of 8x16 -> 153.1)
-    (7, 53, 61, 256, 255, 1, 1, 0, 0, False, False, False),     # head-like 255 channels, ragged boxes, batch straddling pairs
+    (7, 53, 61, 256, 248, 1, 1, 0, 0, False, False, False),     # 248 of 256 tile columns, ragged boxes, batch straddling pairs
 ]
 
 
