@@ -139,13 +139,20 @@ __device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok,
   }
 }
 
-constexpr int kHeadDenseMax = 256;  // (pixel, anchor) pairs per tile (of 384) up to which the warp-per-entry walk is used (r02: 8 % of the rows of EVERY level are candidates; the per-thread dense loop costs 80 sigmoids per pixel and anchor whatever the count)
-
 // Two phases per tile. (1) Every epilogue thread owns one pixel and tests the objectness of its group's anchors; passing
-// (pixel, anchor) pairs are appended to a small shared-memory list (warp-aggregated). (2) After a barrier the warps walk
-// that DENSE list: one entry per warp at a time, the 32 lanes split the classes and reduce to the first arg-max -- with
-// sparse candidates (a few % of the rows) this is ~10x less issue work than looping the classes for whole warps of
-// mostly failing pixels. Tiles with more than kHeadDenseMax passing pairs fall back to one thread per pixel.
+// (pixel, anchor) pairs are appended to a shared-memory list (warp-aggregated). (2) After a barrier the warps walk that
+// list: one entry per warp at a time, the 32 lanes split the classes.
+//   Best class (metrics.py:362-364) WITHOUT a sigmoid per class: conf_c = sigmoid(z_c) * obj is non-decreasing in the logit
+//   z_c, so only classes whose logit lies within a small window of the row's largest logit can attain the maximal conf;
+//   the window (1/16 below the maximum, or everything above 11 where fp32 sigmoids saturate into ties) is wide enough that
+//   classes outside it differ from the maximum by > 16 ulps of the sigmoid, far beyond the 2-ulp error of the fast
+//   sigmoid. Exact conf values are computed for the window only (usually one class); first arg-max among them. That makes
+//   a row cost ~3 shared-memory reads and a few shuffles per lane instead of 80 exp + 80 reciprocals: the detect
+//   convolution no longer slows down when most rows pass the objectness test (r02: 429 us -> see profiles/).
+//   multi_label (metrics.py:359-361) needs every conf_c > conf: classes are pre-filtered in logit space by the same
+//   monotonicity (sigmoid(z) * obj > T  =>  z > logit(T / obj) - margin) and evaluated exactly when they may pass.
+// (3) The tile's keys are appended with one global atomicAdd per warp and image (single-label; multi_label appends per
+// class chunk): one atomic per ROW would serialise in L2 on the image's counter.
 template <class Cfg>
 __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
                                                 int lane, int ewarp_all, unsigned short* list, int* cnt,
@@ -170,13 +177,11 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
     const int cc = ch % Cfg::OC;
     return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(px, cc >> 3) + (cc & 7) * 2));
   };
-  // ---- phase 1: objectness test, dense list of passing (pixel, anchor) pairs
+  // ---- phase 1: objectness test, list of passing (pixel, anchor) pairs
   int b0, oy0, ox0;
   const bool inside = locate(et, b0, oy0, ox0);
-  unsigned pass_bits = 0;  // bit a: this thread's pixel passes for anchor a (only this group's anchors)
   for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
     const bool pass = inside && head_sigmoid(logit(et, a * h.no + 4)) > h.conf_thres;
-    pass_bits |= pass ? 1u << a : 0u;
     const unsigned mk = __ballot_sync(0xffffffffu, pass);
     if (mk) {
       int base = 0;
@@ -187,42 +192,6 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
   }
   named_bar_sync(1, Cfg::EPI_THREADS);
   const int n = *reinterpret_cast<volatile int*>(cnt);
-  if (n > kHeadDenseMax) {
-    // dense tile (synthetic / untrained heads): most warps have passing pixels, so every thread scores its own pixel
-    for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
-      const bool pass = (pass_bits >> a) & 1u;
-      if (!__ballot_sync(0xffffffffu, pass)) continue;  // warp-uniform
-      const int c0 = a * h.no;
-      const float obj = pass ? head_sigmoid(logit(et, c0 + 4)) : 0.0f;
-      const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy0 * h.out_w + ox0);
-      if (h.multi_label) {
-        for (int c = 0; c < nc; ++c) {
-          float conf = 0.0f;
-          bool ok = false;
-          if (pass) {
-            conf = __fmul_rn(head_sigmoid(logit(et, c0 + 5 + c)), obj);
-            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
-          }
-          head_cand_push(h, ok, b0, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
-        }
-      } else {
-        float best = -INFINITY;
-        int bidx = 0;
-        if (pass) {
-          for (int c = 0; c < nc; ++c) {  // first arg-max: strict > keeps the lowest index among equal scores
-            const float conf = __fmul_rn(head_sigmoid(logit(et, c0 + 5 + c)), obj);
-            if (conf > best) {
-              best = conf;
-              bidx = c;
-            }
-          }
-        }
-        const bool ok = pass && best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
-        head_cand_push(h, ok, b0, (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx), lane);
-      }
-    }
-    return;
-  }
   // ---- phase 2: one list entry per warp, classes over lanes
   for (int e = ewarp_all; e < n; e += Cfg::EPI_THREADS / 32) {
     const int ent = list[e];
@@ -233,24 +202,56 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
     const float obj = head_sigmoid(logit(px, c0 + 4));
     const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy * h.out_w + ox);
     if (h.multi_label) {
+      // sigmoid(z) * obj > T needs sigmoid(z) > T / obj; in logit space, with a margin far above the fast sigmoid's error
+      const float r = __fdividef(h.conf_thres, obj);
+      const float zmin = r >= 1.0f ? INFINITY : (r <= 0.0f ? -INFINITY : __logf(__fdividef(r, 1.0f - r)) - 0.0625f);
       for (int cb = 0; cb < nc; cb += 32) {  // every class above conf (metrics.py:360-361)
         const int c = cb + lane;
         float conf = 0.0f;
         bool ok = false;
         if (c < nc) {
-          conf = __fmul_rn(head_sigmoid(logit(px, c0 + 5 + c)), obj);
-          ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
+          const float z = logit(px, c0 + 5 + c);
+          if (z >= zmin) {
+            conf = __fmul_rn(head_sigmoid(z), obj);
+            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
+          }
         }
-        head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
+        if (__ballot_sync(0xffffffffu, ok))
+          head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
       }
     } else {
+      float z[4];  // this lane's class logits (nc <= 128; larger heads loop below)
+      float zmax = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = lane + 32 * q;
+        z[q] = c < nc ? logit(px, c0 + 5 + c) : -INFINITY;
+        zmax = fmaxf(zmax, z[q]);
+      }
+      for (int c = lane + 128; c < nc; c += 32) zmax = fmaxf(zmax, logit(px, c0 + 5 + c));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+      const float zwin = fminf(zmax - 0.0625f, 11.0f);
       float best = -INFINITY;
       int bidx = 0x7fffffff;
-      for (int c = lane; c < nc; c += 32) {  // ascending per lane: strict > keeps the lowest index among equal scores
-        const float conf = __fmul_rn(head_sigmoid(logit(px, c0 + 5 + c)), obj);
-        if (conf > best) {
-          best = conf;
-          bidx = c;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // ascending per lane: strict > keeps the lowest index among equal scores
+        if (z[q] >= zwin) {
+          const float conf = __fmul_rn(head_sigmoid(z[q]), obj);
+          if (conf > best) {
+            best = conf;
+            bidx = lane + 32 * q;
+          }
+        }
+      }
+      for (int c = lane + 128; c < nc; c += 32) {
+        const float zc = logit(px, c0 + 5 + c);
+        if (zc >= zwin) {
+          const float conf = __fmul_rn(head_sigmoid(zc), obj);
+          if (conf > best) {
+            best = conf;
+            bidx = c;
+          }
         }
       }
 #pragma unroll
@@ -262,9 +263,6 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
           bidx = oi;
         }
       }
-      // The key is parked in shared memory; the tile's keys are appended together below. One global atomicAdd per ENTRY
-      // (r02: ~2,000 candidates per image on all levels) serialises in L2 on the image's counter: measured 443 us for the
-      // stride-8 detect convolution instead of 65 us.
       if (lane == 0) {
         const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
         keys_s[e] = ok ? ((static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx)) : ~0ull;
@@ -1250,8 +1248,11 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   cudaGetDevice(&dev0);
   cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
   const int ktot = d->kh * d->kw * d->cin;
+  // Measured (r02, bs 64): 3x3 / s2 layers -6 .. -8 us each, 1x1 512 -> 256 -4 us; the HBM-bound 1x1 256 -> 128 layers got
+  // SLOWER (61.6 -> 80.8 us @80x80: the pair form runs one CTA per SM where two co-resident CTAs hid the latency), so
+  // N = 128 tiles pair up only under a spatial kernel.
   const bool pair = env_pair > 0 && !d->x3 && (bn == 128 || bn == 256) && ck == 64 && kp.num_m_tiles >= sms0 &&
-                    (env_pair == 2 || ktot >= 256);
+                    (env_pair == 2 || (ktot >= 256 && (bn == 256 || d->kh * d->kw > 1)));
   if (pair) kp.csize = 2;
   pl->pair = pair ? 1 : 0;
   if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, d->kh * d->kw * d->cin, d->cout_pad, ck, bn / kp.csize);

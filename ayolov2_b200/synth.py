@@ -53,7 +53,8 @@ def calibrate_head_bias_only(model: nn.Module, raw_levels, cand_frac: float = 0.
         model.invalidate_engine()
 
 
-def calibrate_head(model: nn.Module, run_raw, cand_frac: float = 0.08, conf_thres: float = 0.25, per_level: bool = True) -> None:
+def calibrate_head(model: nn.Module, run_raw, cand_frac: float = 0.08, conf_thres: float = 0.25, per_level: bool = True,
+                   cls_gain: float = 4.0) -> None:
     """Random weights give ~0 NMS candidates at conf 0.25, which would make the NMS leg of the
     benchmark vacuous, and their head logits barely vary over the image (objectness: -6.6 +- 0.003 per anchor at stride 8,
     a tenth of a bf16 step at that magnitude). The detect convolutions (random-init anyway) are therefore re-scaled so that
@@ -62,7 +63,10 @@ def calibrate_head(model: nn.Module, run_raw, cand_frac: float = 0.08, conf_thre
       * the objectness / class biases are zeroed and the sample batch is run again, so that the logits are the pure filter
         responses (small numbers, well resolved in bf16);
       * objectness and class filters of every anchor are standardised on that sample: logit' = (logit - mean) / std, i.e.
-        weight /= std, bias = -mean / std, so the logits have unit spread (and every class the same);
+        weight /= std, bias = -mean / std, so the logits have unit spread (and every class the same); the class logits
+        are then stretched by `cls_gain`, so that -- like in a trained detector -- a row's best class score is close to 1
+        and the rows that pass the objectness test are (nearly) the candidates (with unit-spread class logits most rows
+        that pass objectness fail on the class score: 57 % of the stride-8 rows passed objectness for 8.6 % candidates);
       * the objectness bias then gets the shift (bisection on the sample, per level or globally) at which exactly cand_frac
         of the rows pass BOTH tests of metrics.py:313-364: obj > conf_thres and obj * best class score > conf_thres.
     The standardised filters amplify the (tiny) position-dependent part of the random features ~100x, rounding noise
@@ -94,9 +98,12 @@ def calibrate_head(model: nn.Module, run_raw, cand_frac: float = 0.08, conf_thre
             mean = r[..., 4:].mean(dim=(0, 2, 3))                        # (na, 1 + nc)
             std = r[..., 4:].std(dim=(0, 2, 3)).clamp_min(1e-12)
             w = conv.weight.view(head.na, -1, *conv.weight.shape[1:])    # (na, no, cin, 1, 1)
-            w[:, 4:] /= std.to(w.device)[:, :, None, None, None]
-            conv.bias.view(head.na, -1)[:, 4:] = (-mean / std).to(conv.bias.device)
-            z = ((r[..., 4:] - mean[None, :, None, None, :]) / std[None, :, None, None, :]).reshape(-1, r.shape[-1] - 4).cpu()
+            gain = torch.ones_like(std)
+            gain[:, 1:] = cls_gain
+            w[:, 4:] *= (gain / std).to(w.device)[:, :, None, None, None]
+            conv.bias.view(head.na, -1)[:, 4:] = (-mean / std * gain).to(conv.bias.device)
+            z = ((r[..., 4:] - mean[None, :, None, None, :]) / std[None, :, None, None, :] * gain[None, :, None, None, :]
+                 ).reshape(-1, r.shape[-1] - 4).cpu()
             if z.shape[0] > 100000:
                 z = z[torch.randperm(z.shape[0], generator=g)[:100000]]
             samples.append((z[:, 0], torch.sigmoid(z[:, 1:]).max(1).values))

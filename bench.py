@@ -416,7 +416,7 @@ def main() -> None:
     model = model_utils.build_model("yolov5s", seed=0).to(dev)
     # make the NMS leg non-vacuous: ~8 % of the rows of every level become candidates (ayolov2_b200.synth.calibrate_head)
     sample = synth_images(8, 7).to(dev).float() / 255.0
-    model_utils.calibrate_head(model, lambda: model(sample)[1])
+    model_utils.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.12)
     det = Detector(model, BATCH, H, W, conf_thres=CONF, iou_thres=IOU, in_dtype=torch.uint8, device=dev)
     host_imgs = [synth_images(BATCH, 1000 + rank * 10 + i).pin_memory() for i in range(3)]
     dev_imgs = [h.to(dev) for h in host_imgs[:2]]

@@ -16,7 +16,7 @@ torch.manual_seed(0)
 model = synth.build_model("yolov5s", seed=0).cuda()
 img = torch.randint(0, 256, (batch, 3, 640, 640), dtype=torch.uint8, device="cuda")
 sample = torch.randint(0, 256, (4, 3, 640, 640), dtype=torch.uint8, device="cuda").float() / 255.0
-synth.calibrate_head(model, lambda: model(sample)[1])
+synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.12)
 det = Detector(model, batch, 640, 640, in_dtype=torch.uint8)
 eng = det.engine
 eng._img = img
