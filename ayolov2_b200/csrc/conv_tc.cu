@@ -139,47 +139,48 @@ __device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok,
   }
 }
 
-// Two phases per tile. (1) Every epilogue thread owns one pixel and tests the objectness of its group's anchors; passing
-// (pixel, anchor) pairs are appended to a shared-memory list (warp-aggregated). (2) After a barrier the warps walk that
-// list: one entry per warp at a time, the 32 lanes split the classes.
+// Three phases per tile. (1) Every epilogue thread owns one pixel and tests the objectness of its group's anchors; passing
+// (pixel, anchor) pairs are appended to a shared-memory list (warp-aggregated) together with their image and row number.
+// (2) After a barrier the list is walked ONE ENTRY PER THREAD: the thread streams the entry's class logits out of the
+// staged tile with 16-byte shared-memory reads (32 lanes reading 32 different 128-byte rows of a swizzled slab hit every
+// bank group equally: no conflicts beyond the 4 wavefronts 512 bytes need) -- a warp's instruction stream serves 32 rows
+// at once (r02 measurements: a warp per row issued ~3000 clk per row; 80 sigmoids per row before that).
 //   Best class (metrics.py:362-364) WITHOUT a sigmoid per class: conf_c = sigmoid(z_c) * obj is non-decreasing in the logit
 //   z_c, so only classes whose logit lies within a small window of the row's largest logit can attain the maximal conf;
 //   the window (1/16 below the maximum, or everything above 11 where fp32 sigmoids saturate into ties) is wide enough that
 //   classes outside it differ from the maximum by > 16 ulps of the sigmoid, far beyond the 2-ulp error of the fast
-//   sigmoid. Exact conf values are computed for the window only (usually one class); first arg-max among them. That makes
-//   a row cost ~3 shared-memory reads and a few shuffles per lane instead of 80 exp + 80 reciprocals: the detect
-//   convolution no longer slows down when most rows pass the objectness test (r02: 429 us -> see profiles/).
+//   sigmoid. Pass 1 finds the largest logit, pass 2 evaluates exact conf values for the window only (usually one class),
+//   first arg-max among them.
 //   multi_label (metrics.py:359-361) needs every conf_c > conf: classes are pre-filtered in logit space by the same
 //   monotonicity (sigmoid(z) * obj > T  =>  z > logit(T / obj) - margin) and evaluated exactly when they may pass.
 // (3) The tile's keys are appended with one global atomicAdd per warp and image (single-label; multi_label appends per
-// class chunk): one atomic per ROW would serialise in L2 on the image's counter.
+// class step): one atomic per ROW would serialise in L2 on the image's counter.
 template <class Cfg>
 __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
-                                                int lane, int ewarp_all, unsigned short* list, int* cnt,
+                                                int lane, int eall, unsigned short* list, int* cnt,
                                                 unsigned long long* keys_s, short* img_s) {
   const HeadCandParams& h = p.hc;
   const int box_rows = p.BH * p.BW;
   const int plane = h.out_h * h.out_w;
   const int nc = h.no - 5;
-  auto locate = [&](int px, int& b, int& oy, int& ox) -> bool {  // pixel `px` of tile m -> image, row, column
-    const int j = px / box_rows, rr = px - j * box_rows;
-    const int q = m * p.NB + j;
-    b = q / p.boxes_per_img;
-    const int r = q - b * p.boxes_per_img;
-    const int py = r / p.boxes_x;
-    const int ry = rr / p.BW;
-    oy = py * p.BH + ry;
-    ox = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
-    return b < h.batch && oy < h.out_h && ox < h.out_w;
-  };
   auto logit = [&](int px, int ch) -> float {  // channel ch of pixel px in the swizzled staging slabs
     const uint8_t* slab = staging + (ch / Cfg::OC) * Cfg::SLAB_BYTES;
     const int cc = ch % Cfg::OC;
     return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(px, cc >> 3) + (cc & 7) * 2));
   };
-  // ---- phase 1: objectness test, list of passing (pixel, anchor) pairs
+  // ---- phase 1: objectness test, list of passing (pixel, anchor) pairs with their (image, row)
   int b0, oy0, ox0;
-  const bool inside = locate(et, b0, oy0, ox0);
+  {
+    const int j = et / box_rows, rr = et - j * box_rows;
+    const int q = m * p.NB + j;
+    b0 = q / p.boxes_per_img;
+    const int r = q - b0 * p.boxes_per_img;
+    const int py = r / p.boxes_x;
+    const int ry = rr / p.BW;
+    oy0 = py * p.BH + ry;
+    ox0 = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
+  }
+  const bool inside = b0 < h.batch && oy0 < h.out_h && ox0 < h.out_w;
   for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
     const bool pass = inside && head_sigmoid(logit(et, a * h.no + 4)) > h.conf_thres;
     const unsigned mk = __ballot_sync(0xffffffffu, pass);
@@ -187,93 +188,97 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
       int base = 0;
       if (lane == 0) base = atomicAdd(cnt, __popc(mk));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (pass) list[base + __popc(mk & ((1u << lane) - 1u))] = static_cast<unsigned short>(et | (a << 8));
+      if (pass) {
+        const int e = base + __popc(mk & ((1u << lane) - 1u));
+        list[e] = static_cast<unsigned short>(et | (a << 8));
+        img_s[e] = static_cast<short>(b0);
+        keys_s[e] = static_cast<unsigned>(h.row_off + a * plane + oy0 * h.out_w + ox0);  // the row; phase 2 turns it into the key
+      }
     }
   }
   named_bar_sync(1, Cfg::EPI_THREADS);
   const int n = *reinterpret_cast<volatile int*>(cnt);
-  // ---- phase 2: one list entry per warp, classes over lanes
-  for (int e = ewarp_all; e < n; e += Cfg::EPI_THREADS / 32) {
-    const int ent = list[e];
+  // ---- phase 2: one list entry per thread
+  const int rounds = (n + Cfg::EPI_THREADS - 1) / Cfg::EPI_THREADS;
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int e = rd * Cfg::EPI_THREADS + eall;
+    const bool have = e < n;
+    if (!__ballot_sync(0xffffffffu, have)) continue;  // warp-uniform: no entry for this warp in this round
+    const int ent = have ? list[e] : 0;
     const int px = ent & 0xff, a = ent >> 8;
-    int b, oy, ox;
-    locate(px, b, oy, ox);
     const int c0 = a * h.no;
-    const float obj = head_sigmoid(logit(px, c0 + 4));
-    const unsigned row = static_cast<unsigned>(h.row_off + a * plane + oy * h.out_w + ox);
+    const int b = have ? img_s[e] : 0;
+    const unsigned row = have ? static_cast<unsigned>(keys_s[e]) : 0u;
+    const float obj = have ? head_sigmoid(logit(px, c0 + 4)) : 0.0f;
+    const int ch_lo = c0 + 5, ch_hi = c0 + h.no;  // class channels [ch_lo, ch_hi)
+    const int k_lo = ch_lo >> 3, k_hi = (ch_hi + 7) >> 3;
+    auto chunk = [&](int k) -> uint4 {  // channels [8k, 8k + 8) of pixel px
+      const uint8_t* slab = staging + (k / (Cfg::OC / 8)) * Cfg::SLAB_BYTES;
+      return *reinterpret_cast<const uint4*>(slab + swizzled_offset<Cfg::SWO>(px, k % (Cfg::OC / 8)));
+    };
     if (h.multi_label) {
       // sigmoid(z) * obj > T needs sigmoid(z) > T / obj; in logit space, with a margin far above the fast sigmoid's error
-      const float r = __fdividef(h.conf_thres, obj);
+      const float r = have ? __fdividef(h.conf_thres, obj) : 2.0f;
       const float zmin = r >= 1.0f ? INFINITY : (r <= 0.0f ? -INFINITY : __logf(__fdividef(r, 1.0f - r)) - 0.0625f);
-      for (int cb = 0; cb < nc; cb += 32) {  // every class above conf (metrics.py:360-361)
-        const int c = cb + lane;
-        float conf = 0.0f;
-        bool ok = false;
-        if (c < nc) {
-          const float z = logit(px, c0 + 5 + c);
-          if (z >= zmin) {
+      const int k_all = (h.na * h.no + 7) >> 3;
+      for (int k = 0; k < k_all; ++k) {  // warp-uniform trip count (the pushes below are warp-collective); a lane acts on its anchor's chunks
+        const bool live = have && k >= k_lo && k < k_hi;
+        if (!__ballot_sync(0xffffffffu, live)) continue;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (live) v = chunk(k);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ch = 8 * k + i;
+          const float z = __bfloat162float(hv[i]);
+          float conf = 0.0f;
+          bool ok = false;
+          if (live && ch >= ch_lo && ch < ch_hi && z >= zmin) {
             conf = __fmul_rn(head_sigmoid(z), obj);
-            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
+            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[ch - ch_lo]);
           }
+          if (__ballot_sync(0xffffffffu, ok))
+            head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + (ch - ch_lo)), lane);
         }
-        if (__ballot_sync(0xffffffffu, ok))
-          head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
       }
-    } else {
-      float z[4];  // this lane's class logits (nc <= 128; larger heads loop below)
+    } else if (have) {
       float zmax = -INFINITY;
+      for (int k = k_lo; k < k_hi; ++k) {
+        const uint4 v = chunk(k);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = lane + 32 * q;
-        z[q] = c < nc ? logit(px, c0 + 5 + c) : -INFINITY;
-        zmax = fmaxf(zmax, z[q]);
+        for (int i = 0; i < 8; ++i) {
+          const int ch = 8 * k + i;
+          if (ch >= ch_lo && ch < ch_hi) zmax = fmaxf(zmax, __bfloat162float(hv[i]));
+        }
       }
-      for (int c = lane + 128; c < nc; c += 32) zmax = fmaxf(zmax, logit(px, c0 + 5 + c));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
       const float zwin = fminf(zmax - 0.0625f, 11.0f);
       float best = -INFINITY;
-      int bidx = 0x7fffffff;
+      int bidx = 0;
+      for (int k = k_lo; k < k_hi; ++k) {  // ascending class order: strict > keeps the lowest index among equal scores
+        const uint4 v = chunk(k);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {  // ascending per lane: strict > keeps the lowest index among equal scores
-        if (z[q] >= zwin) {
-          const float conf = __fmul_rn(head_sigmoid(z[q]), obj);
-          if (conf > best) {
-            best = conf;
-            bidx = lane + 32 * q;
+        for (int i = 0; i < 8; ++i) {
+          const int ch = 8 * k + i;
+          const float z = __bfloat162float(hv[i]);
+          if (ch >= ch_lo && ch < ch_hi && z >= zwin) {
+            const float conf = __fmul_rn(head_sigmoid(z), obj);
+            if (conf > best) {
+              best = conf;
+              bidx = ch - ch_lo;
+            }
           }
         }
       }
-      for (int c = lane + 128; c < nc; c += 32) {
-        const float zc = logit(px, c0 + 5 + c);
-        if (zc >= zwin) {
-          const float conf = __fmul_rn(head_sigmoid(zc), obj);
-          if (conf > best) {
-            best = conf;
-            bidx = c;
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {  // first arg-max over the warp (metrics.py:363-364): larger score, then lower class
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) {
-          best = ob;
-          bidx = oi;
-        }
-      }
-      if (lane == 0) {
-        const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
-        keys_s[e] = ok ? ((static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx)) : ~0ull;
-        img_s[e] = static_cast<short>(b);
-      }
+      const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+      keys_s[e] = ok ? ((static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx)) : ~0ull;
     }
   }
   if (!h.multi_label) {
     // ---- phase 3: append the tile's keys, one atomicAdd per warp and image (a tile rarely spans two images)
     named_bar_sync(1, Cfg::EPI_THREADS);
-    for (int e0 = ewarp_all * 32; e0 < n; e0 += Cfg::EPI_THREADS) {
+    for (int e0 = (eall >> 5) * 32; e0 < n; e0 += Cfg::EPI_THREADS) {
       const int e = e0 + lane;
       const unsigned long long key = e < n ? keys_s[e] : ~0ull;
       head_cand_push(h, key != ~0ull, e < n ? img_s[e] : 0, key, lane);
@@ -676,7 +681,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
         // only read); no group may start rewriting its slab before every group has finished reading
         named_bar_sync(1, Cfg::EPI_THREADS);
         if (eall == 0) cand_cnt[(it + 1) & 1] = 0;  // the other counter was last read before the barrier above
-        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall >> 5, cand_list, &cand_cnt[it & 1], cand_keys, cand_img);
+        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall, cand_list, &cand_cnt[it & 1], cand_keys, cand_img);
         named_bar_sync(1, Cfg::EPI_THREADS);
       }
     }

@@ -115,7 +115,8 @@ def test_conv_parity_cta_pair(case):
     """The same parity bar for the cta_group::2 form; the plan reports which form it chose."""
     plan = _run_case(case, seed=1)
     out_px = case[0] * ((case[1] + 2 * case[7] - case[5]) // case[6] + 1) * ((case[2] + 2 * case[7] - case[5]) // case[6] + 1)
-    if out_px >= 150 * 128:
+    n_tile, spatial = case[4], case[5] > 1
+    if out_px >= 150 * 128 and (n_tile > 128 or spatial):  # (N tiles of 128 pair up only under a spatial kernel)
         assert plan.pair, "expected the CTA-pair form"
 
 
