@@ -67,6 +67,7 @@ struct NmsWorkspaceView {
   int* overflow;             // [1]
   int* row_counts;           // [batch] rows that passed the objectness test (two-phase generation only)
   unsigned long long* keys;  // [batch][key_stride]
+  unsigned long long* keys2; // [batch][key_stride] compaction scratch of the dense-slot mode (more candidates than the shared-memory sort holds)
   long long key_stride;
   unsigned* rows;            // [batch][n]
   // class-group split of the suppression kernel (nms.cu): per (image, group) kept lists + the per-image ticket / fallback flag
@@ -86,6 +87,12 @@ struct HeadCandParams {
   long long key_stride;
   float conf_thres;
   int max_candidates, na, no, row_off, multi_label, batch, out_h, out_w;
+  // 1: a candidate's key is stored at slot [image][row] of the key array (pre-filled with ~0 by ay2_nms_candidates_begin) --
+  // no counters, no atomics; the suppression kernel compacts the slots while loading. Single-label lists with room for
+  // every row (nms_dense_slots()).
+  int dense_slots;
 };
+// The fused head uses row-indexed key slots (above) when this holds.
+inline bool nms_dense_slots(const ay2_nms_params* p) { return !p->multi_label && p->max_candidates >= p->n; }
 
 }  // namespace ay2

@@ -331,7 +331,8 @@ __device__ __noinline__ void nms_image(const BoxSource& src, ay2_nms_params p, u
                                        long long key_stride, const int* __restrict__ counts, const NmsDst dst,
                                        int* __restrict__ overflow, long long* __restrict__ trace,
                                        const float* __restrict__ wh_scale, const int b, const int ngroups, const int group,
-                                       int* __restrict__ wide_flag) {
+                                       int* __restrict__ wide_flag, const int dense, unsigned long long* __restrict__ keys2,
+                                       int* __restrict__ count_back) {
 #define AY2_NMS_MARK(k)                                                    \
   do {                                                                     \
     if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[k] = clock64(); \
@@ -361,7 +362,8 @@ __device__ __noinline__ void nms_image(const BoxSource& src, ay2_nms_params p, u
   // per-image class-offset scale (torchvision's batched_nms coordinate trick: max coordinate of the image + 1). A scale
   // that small fails the disjoint-window test below, so such images take the single-segment (exact, all-pairs) route.
   if (wh_scale) p.max_wh = __fadd_rn(wh_scale[b], 1.0f);
-  int n = counts[b];
+  // dense-slot mode (fused head): the key array holds one slot per ROW, ~0 where the row is no candidate
+  int n = dense ? p.n : counts[b];
   if (n > p.max_candidates) {
     n = p.max_candidates;
     if (tid == 0) atomicExch(overflow, 1);
@@ -379,9 +381,11 @@ __device__ __noinline__ void nms_image(const BoxSource& src, ay2_nms_params p, u
   while (npow2 < n) npow2 <<= 1;
   unsigned long long* gk = keys + (long long)b * key_stride;
   const unsigned long long* sorted;
-  if (ngroups > 1) {
-    // class-group filter while loading (the caller guarantees n <= kSortSmemKeys); order is irrelevant before the sort
+  if (ngroups > 1 || dense) {
+    // Compacting load: keep the live slots (dense mode) of this CTA's class group; order is irrelevant before the sort.
+    // Up to kSortSmemKeys keys land in shared memory, any excess in the global scratch list.
     __shared__ int s_take;
+    unsigned long long* g2 = keys2 + (long long)b * key_stride;
     if (tid == 0) s_take = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
@@ -390,27 +394,48 @@ __device__ __noinline__ void nms_image(const BoxSource& src, ay2_nms_params p, u
       bool mine = false;
       if (i < n) {
         key = gk[i];
-        mine = static_cast<int>((static_cast<unsigned>(key) % nc) % ngroups) == group;
+        mine = (!dense || key != ~0ull) && (ngroups == 1 || static_cast<int>((static_cast<unsigned>(key) % nc) % ngroups) == group);
       }
       const unsigned m = __ballot_sync(0xffffffffu, mine);
       int base = 0;
       if (lane == 0 && m) base = atomicAdd(&s_take, __popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (mine) skeys[base + __popc(m & ((1u << lane) - 1u))] = key;
+      if (mine) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < kSortSmemKeys) skeys[pos] = key;
+        else if (ngroups == 1) g2[pos] = key;
+      }
     }
     __syncthreads();
     n = s_take;
+    if (count_back && tid == 0 && n) atomicAdd(count_back, n);  // the candidate count, for the callers that report it
     if (n == 0) {
       if (tid == 0) *dst.count = 0;
       return;
     }
     npow2 = 2;
     while (npow2 < n) npow2 <<= 1;
-    for (int i = n + tid; i < npow2; i += blockDim.x) skeys[i] = ~0ull;
-    __syncthreads();
-    if (npow2 <= 2 * kNmsThreads) bitonic_sort_regs(skeys, npow2);
-    else bitonic_sort(skeys, npow2);
-    sorted = skeys;
+    if (n > kSortSmemKeys) {
+      if (ngroups > 1) {  // a class group too large for the shared-memory sort: the whole image takes the single-CTA route
+        if (tid == 0) {
+          *dst.count = 0;
+          if (wide_flag) atomicExch(wide_flag, 1);
+        }
+        return;
+      }
+      for (int i = tid; i < npow2; i += blockDim.x)
+        if (i < kSortSmemKeys) g2[i] = skeys[i];
+        else if (i >= n) g2[i] = ~0ull;
+      __syncthreads();
+      bitonic_sort(g2, npow2);
+      sorted = g2;
+    } else {
+      for (int i = n + tid; i < npow2; i += blockDim.x) skeys[i] = ~0ull;
+      __syncthreads();
+      if (npow2 <= 2 * kNmsThreads) bitonic_sort_regs(skeys, npow2);
+      else bitonic_sort(skeys, npow2);
+      sorted = skeys;
+    }
   } else if (npow2 <= kSortSmemKeys) {
     for (int i = tid; i < npow2; i += blockDim.x) skeys[i] = i < n ? gk[i] : ~0ull;
     __syncthreads();
@@ -919,20 +944,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
                          const int* __restrict__ counts, float* __restrict__ out_det, int* __restrict__ out_count,
                          int* __restrict__ overflow, long long* __restrict__ trace, const float* __restrict__ wh_scale, int G,
                          float* __restrict__ part_det, unsigned long long* __restrict__ part_keys, int* __restrict__ part_count,
-                         int* __restrict__ done, int* __restrict__ wide) {
+                         int* __restrict__ done, int* __restrict__ wide, int dense, unsigned long long* __restrict__ keys2,
+                         int* __restrict__ counts_rw) {
   const int b = blockIdx.x / G, g = blockIdx.x - b * G;
   const NmsDst whole{out_det + (long long)b * p.max_det * 6, nullptr, out_count + b};
+  int* count_back = dense ? counts_rw + b : nullptr;
   if (G == 1) {
-    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr);
+    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr, dense, keys2, count_back);
     return;
   }
   const int tid = threadIdx.x;
-  const int n_all = counts[b];
-  const bool splittable = n_all <= kSortSmemKeys && n_all <= p.max_nms && n_all <= p.max_candidates;
+  const int n_all = dense ? 0 : counts[b];  // (dense mode: unknown before the scan; an oversized group reports itself)
+  const bool splittable = n_all <= kSortSmemKeys && n_all <= p.max_nms && n_all <= p.max_candidates && (!dense || p.n <= p.max_nms);
   const long long slot = (long long)b * G + g;
   if (splittable) {
     const NmsDst part{part_det + slot * p.max_det * 6, part_keys + slot * p.max_det, part_count + slot};
-    nms_image(src, p, keys, key_stride, counts, part, overflow, trace, wh_scale, b, G, g, wide + b);
+    nms_image(src, p, keys, key_stride, counts, part, overflow, trace, wh_scale, b, G, g, wide + b, dense, keys2, count_back);
   } else if (tid == 0) {
     atomicExch(wide + b, 1);
   }
@@ -944,7 +971,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
   if (s_ticket != G - 1) return;
   __threadfence();
   if (*reinterpret_cast<volatile int*>(wide + b)) {
-    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr);
+    nms_image(src, p, keys, key_stride, counts, whole, overflow, trace, wh_scale, b, 1, 0, nullptr, dense, keys2,
+              splittable ? nullptr : count_back);  // (the groups have already reported the candidate count, if they ran)
   } else {
     int total = 0;
     for (int h = 0; h < G; ++h) total += *reinterpret_cast<volatile int*>(part_count + (long long)b * G + h);
@@ -1004,7 +1032,7 @@ static long long key_stride_for(const ay2_nms_params* p) {
 using namespace ay2;
 
 // workspace layout: [counts int32 x B][overflow int32][row_counts int32 x B][done int32 x B][wide int32 x B][pad to 256]
-//                   [keys u64 x B x key_stride][rows u32 x B x n]
+//                   [keys u64 x B x key_stride][keys2 u64 x B x key_stride][rows u32 x B x n]
 //                   [partial keys u64 x B x G x max_det][partial rows f32 x B x G x max_det x 6][partial counts int32 x B x G]
 constexpr int kMaxGroups = 4;  // class groups (CTAs) per image
 static size_t nms_head_ints(const ay2_nms_params* p) { return 4 * (size_t)p->batch + 1; }
@@ -1013,7 +1041,7 @@ static size_t nms_rows_bytes(const ay2_nms_params* p) { return ((sizeof(unsigned
 extern "C" size_t ay2_nms_workspace_bytes(const ay2_nms_params* p) {
   if (!p) return 0;
   const size_t parts = (size_t)p->batch * kMaxGroups;
-  return nms_head_bytes(p) + sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p) + nms_rows_bytes(p) +
+  return nms_head_bytes(p) + 2 * sizeof(unsigned long long) * (size_t)p->batch * (size_t)key_stride_for(p) + nms_rows_bytes(p) +
          parts * p->max_det * (sizeof(unsigned long long) + 6 * sizeof(float)) + parts * sizeof(int);
 }
 
@@ -1027,7 +1055,8 @@ NmsWorkspaceView nms_workspace_view(const ay2_nms_params* p, void* workspace) {
   v.wide = v.done + p->batch;
   v.keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + nms_head_bytes(p));
   v.key_stride = key_stride_for(p);
-  v.rows = reinterpret_cast<unsigned*>(v.keys + (size_t)p->batch * v.key_stride);
+  v.keys2 = v.keys + (size_t)p->batch * v.key_stride;
+  v.rows = reinterpret_cast<unsigned*>(v.keys2 + (size_t)p->batch * v.key_stride);
   const size_t parts = (size_t)p->batch * kMaxGroups;
   v.part_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(v.rows) + nms_rows_bytes(p));
   v.part_det = reinterpret_cast<float*>(v.part_keys + parts * p->max_det);
@@ -1060,7 +1089,8 @@ static int nms_common_checks(const ay2_nms_params* p, const void* workspace, siz
 }
 
 static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, const NmsWorkspaceView& v, float* out_det,
-                                int32_t* out_count, int32_t* overflow_flag, cudaStream_t st, const float* wh_scale = nullptr) {
+                                int32_t* out_count, int32_t* overflow_flag, cudaStream_t st, const float* wh_scale = nullptr,
+                                bool dense = false) {
   // the opt-in to > 48 KB of dynamic shared memory is per (function, device): one flag per device, not per process
   static DeviceOnce once;
   if (once.first())
@@ -1084,7 +1114,7 @@ static int nms_sort_scan_launch(const BoxSource& src, const ay2_nms_params* p, c
   if (G < 1 || p->agnostic || p->no - 5 < 2 || wh_scale) G = 1;
   nms_sort_scan_kernel<<<p->batch * G, kNmsThreads, kNmsSmemBytes, st>>>(src, *p, v.keys, v.key_stride, v.counts, out_det, out_count,
                                                                          v.overflow, trace, wh_scale, G, v.part_det, v.part_keys,
-                                                                         v.part_count, v.done, v.wide);
+                                                                         v.part_count, v.done, v.wide, dense ? 1 : 0, v.keys2, v.counts);
   AY2_CHECK_LAUNCH();
   if (trace) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1173,6 +1203,9 @@ extern "C" int ay2_nms_candidates_begin(const ay2_nms_params* p, void* workspace
               ay2_nms_workspace_bytes(p));
   const NmsWorkspaceView v = nms_workspace_view(p, workspace);
   AY2_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int) * nms_head_ints(p), static_cast<cudaStream_t>(stream)));
+  if (nms_dense_slots(p))  // row-indexed key slots: every slot starts as "no candidate" (~0); only the n used slots per image
+    AY2_CHECK_CUDA(cudaMemset2DAsync(v.keys, sizeof(unsigned long long) * v.key_stride, 0xFF, sizeof(unsigned long long) * p->n,
+                                     p->batch, static_cast<cudaStream_t>(stream)));
   return AY2_OK;
 }
 
@@ -1185,7 +1218,7 @@ extern "C" int ay2_nms_from_candidates(const ay2_head_levels* hl, const ay2_nms_
   rc = box_source_from_levels(hl, p, &src);
   if (rc != AY2_OK) return rc;
   rc = nms_sort_scan_launch(src, p, nms_workspace_view(p, workspace), out_det, out_count, overflow_flag,
-                            static_cast<cudaStream_t>(stream));
+                            static_cast<cudaStream_t>(stream), nullptr, nms_dense_slots(p));
   if (rc != AY2_OK) return rc;
   count_launch(1);
   return AY2_OK;

@@ -487,7 +487,8 @@ class TrainEngine:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(g):
+                # thread-local capture mode: under DDP the NCCL watchdog thread polls its events while this thread captures
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     body()
             except Exception as e:  # capture is an optimisation of the launch path only: keep training, say so loudly
                 import warnings
