@@ -198,12 +198,18 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
   }
   named_bar_sync(1, Cfg::EPI_THREADS);
   const int n = *reinterpret_cast<volatile int*>(cnt);
-  // ---- phase 2: one list entry per thread
-  const int rounds = (n + Cfg::EPI_THREADS - 1) / Cfg::EPI_THREADS;
-  for (int rd = 0; rd < rounds; ++rd) {
-    const int e = rd * Cfg::EPI_THREADS + eall;
+  // ---- phase 2: EIGHT lanes per list entry (four entries per warp and pass). A lane holds at most two 16-byte chunks
+  // (16 logits) of the entry's class range in registers: one shared-memory round trip, a 3-step shuffle for the largest
+  // logit, the exact conf of the window classes from the registers, a 3-step shuffle for the first arg-max. (One thread
+  // per entry made a ~4000-clk dependent chain that three warps walked while thirteen waited at the barrier below;
+  // one warp per entry issued ~3000 clk per row.)
+  constexpr int kWarps = Cfg::EPI_THREADS / 32;
+  const int sub = lane & 7, slot = lane >> 3, wall = eall >> 5;
+  const int passes = (n + 4 * kWarps - 1) / (4 * kWarps);
+  for (int ps = 0; ps < passes; ++ps) {
+    const int e = (ps * kWarps + wall) * 4 + slot;
     const bool have = e < n;
-    if (!__ballot_sync(0xffffffffu, have)) continue;  // warp-uniform: no entry for this warp in this round
+    if (!__ballot_sync(0xffffffffu, have)) continue;  // warp-uniform
     const int ent = have ? list[e] : 0;
     const int px = ent & 0xff, a = ent >> 8;
     const int c0 = a * h.no;
@@ -212,73 +218,79 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
     const float obj = have ? head_sigmoid(logit(px, c0 + 4)) : 0.0f;
     const int ch_lo = c0 + 5, ch_hi = c0 + h.no;  // class channels [ch_lo, ch_hi)
     const int k_lo = ch_lo >> 3, k_hi = (ch_hi + 7) >> 3;
-    auto chunk = [&](int k) -> uint4 {  // channels [8k, 8k + 8) of pixel px
-      const uint8_t* slab = staging + (k / (Cfg::OC / 8)) * Cfg::SLAB_BYTES;
-      return *reinterpret_cast<const uint4*>(slab + swizzled_offset<Cfg::SWO>(px, k % (Cfg::OC / 8)));
-    };
+    float z[16];
+    int chb[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int k = k_lo + sub + 8 * q;
+      chb[q] = 8 * k;
+      uint4 v = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // bf16 -inf
+      if (have && k < k_hi) {
+        const uint8_t* slab = staging + (k / (Cfg::OC / 8)) * Cfg::SLAB_BYTES;
+        v = *reinterpret_cast<const uint4*>(slab + swizzled_offset<Cfg::SWO>(px, k % (Cfg::OC / 8)));
+      }
+      const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ch = chb[q] + i;
+        z[8 * q + i] = (ch >= ch_lo && ch < ch_hi) ? __bfloat162float(hv[i]) : -INFINITY;
+      }
+    }
+    // (a head with more than 16 x 8 = 128 class channels per anchor would need more chunks per lane)
     if (h.multi_label) {
       // sigmoid(z) * obj > T needs sigmoid(z) > T / obj; in logit space, with a margin far above the fast sigmoid's error
       const float r = have ? __fdividef(h.conf_thres, obj) : 2.0f;
       const float zmin = r >= 1.0f ? INFINITY : (r <= 0.0f ? -INFINITY : __logf(__fdividef(r, 1.0f - r)) - 0.0625f);
-      const int k_all = (h.na * h.no + 7) >> 3;
-      for (int k = 0; k < k_all; ++k) {  // warp-uniform trip count (the pushes below are warp-collective); a lane acts on its anchor's chunks
-        const bool live = have && k >= k_lo && k < k_hi;
-        if (!__ballot_sync(0xffffffffu, live)) continue;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (live) v = chunk(k);
-        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ch = 8 * k + i;
-          const float z = __bfloat162float(hv[i]);
-          float conf = 0.0f;
-          bool ok = false;
-          if (live && ch >= ch_lo && ch < ch_hi && z >= zmin) {
-            conf = __fmul_rn(head_sigmoid(z), obj);
-            ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[ch - ch_lo]);
-          }
-          if (__ballot_sync(0xffffffffu, ok))
-            head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + (ch - ch_lo)), lane);
+      for (int i = 0; i < 16; ++i) {
+        const int c = chb[i >> 3] + (i & 7) - ch_lo;
+        float conf = 0.0f;
+        bool ok = false;
+        if (z[i] >= zmin) {  // (-inf for channels outside the class range / lanes without an entry)
+          conf = __fmul_rn(head_sigmoid(z[i]), obj);
+          ok = conf > h.conf_thres && (!h.class_mask || h.class_mask[c]);
         }
+        if (__ballot_sync(0xffffffffu, ok))
+          head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
       }
-    } else if (have) {
-      float zmax = -INFINITY;
-      for (int k = k_lo; k < k_hi; ++k) {
-        const uint4 v = chunk(k);
-        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
+    } else {
+      float zmax = z[0];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ch = 8 * k + i;
-          if (ch >= ch_lo && ch < ch_hi) zmax = fmaxf(zmax, __bfloat162float(hv[i]));
-        }
-      }
+      for (int i = 1; i < 16; ++i) zmax = fmaxf(zmax, z[i]);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
       const float zwin = fminf(zmax - 0.0625f, 11.0f);
       float best = -INFINITY;
-      int bidx = 0;
-      for (int k = k_lo; k < k_hi; ++k) {  // ascending class order: strict > keeps the lowest index among equal scores
-        const uint4 v = chunk(k);
-        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&v);
+      int bidx = 0x7fffffff;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ch = 8 * k + i;
-          const float z = __bfloat162float(hv[i]);
-          if (ch >= ch_lo && ch < ch_hi && z >= zwin) {
-            const float conf = __fmul_rn(head_sigmoid(z), obj);
-            if (conf > best) {
-              best = conf;
-              bidx = ch - ch_lo;
-            }
+      for (int i = 0; i < 16; ++i) {  // ascending class order inside a chunk; the reduction below orders across lanes by index
+        if (z[i] >= zwin) {
+          const float conf = __fmul_rn(head_sigmoid(z[i]), obj);
+          const int c = chb[i >> 3] + (i & 7) - ch_lo;
+          if (conf > best || (conf == best && c < bidx)) {
+            best = conf;
+            bidx = c;
           }
         }
       }
-      const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
-      const unsigned long long key = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx);
-      if (h.dense_slots) {
-        // row-indexed slot: no counter, no atomic, nothing to wait for (r02: with ~2,000 candidates per image on every level the
-        // per-warp atomicAdd on the 64 adjacent image counters queued up in one L2 slice, ~15 ns each: +135 us on the stride-8 level)
-        if (ok) h.keys[(long long)b * h.key_stride + row] = key;
-      } else {
-        keys_s[e] = ok ? key : ~0ull;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {  // first arg-max over the entry's 8 lanes (metrics.py:363-364): larger score, then lower class
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) {
+          best = ob;
+          bidx = oi;
+        }
+      }
+      if (have && sub == 0) {
+        const bool ok = best > h.conf_thres && (!h.class_mask || h.class_mask[bidx]);
+        const unsigned long long key = (static_cast<unsigned long long>(~__float_as_uint(best)) << 32) | (row * nc + bidx);
+        if (h.dense_slots) {
+          // row-indexed slot: no counter, no atomic, nothing to wait for
+          if (ok) h.keys[(long long)b * h.key_stride + row] = key;
+        } else {
+          keys_s[e] = ok ? key : ~0ull;
+        }
       }
     }
   }
@@ -1342,6 +1354,7 @@ extern "C" int ay2_conv_plan_set_head_candidates(ay2_conv_plan* pl, const ay2_nm
   AY2_REQUIRE(pl->kp.num_n_tiles == 1, "head candidates need all %d output channels in one N tile (block_n=%d)", d.cout,
               pl->block_n);
   AY2_REQUIRE(na >= 1 && p->no > 5 && na * p->no <= d.cout, "head layout na=%d no=%d does not fit cout=%d", na, p->no, d.cout);
+  AY2_REQUIRE(p->no - 5 <= 120, "the fused candidate epilogue holds at most 120 classes per anchor in registers (nc=%d)", p->no - 5);
   AY2_REQUIRE(p->batch == d.batch, "NMS batch %d != conv batch %d", p->batch, d.batch);
   AY2_REQUIRE(d.out_pix_stride <= 0, "head candidates are not defined for sub-grid outputs");
   AY2_REQUIRE(row_off >= 0 && row_off + na * d.out_h * d.out_w <= p->n, "level rows [%d, %d) exceed params.n = %d", row_off,

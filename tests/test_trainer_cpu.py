@@ -1,0 +1,78 @@
+"""Host-side logic of ayolov2_b200.trainer (no GPU): the warm-up / epoch schedules and parameter groups of
+scripts/train/yolo_trainer.py:124-221, and -- in two gloo ranks -- that all-reducing a flat gradient buffer in contiguous
+buckets (what TrainStep does on a side stream while the backward still runs) equals one all-reduce of the whole buffer."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+from ayolov2_b200.trainer import NOMINAL_BATCH, lr_function, parameter_groups, warmup_state
+
+HYP = dict(warmup_bias_lr=0.1, warmup_momentum=0.8, momentum=0.937, lrf=0.1)
+
+
+def test_lr_function_matches_reference_formulas():
+    for e in (0, 1, 37, 150, 299):
+        assert lr_function(e, 300, 0.1) == ((1 + math.cos(e * math.pi / 300)) / 2) * 0.9 + 0.1          # yolo_trainer.py:136-138
+        assert lr_function(e, 300, 0.1, linear=True) == (1 - e / 299) * 0.9 + 0.1                         # :130-133
+    assert lr_function(0, 300, 0.1) == 1.0 and abs(lr_function(300, 300, 0.1) - 0.1) < 1e-12
+
+
+@pytest.mark.parametrize("bs", [16, 64, 128])
+def test_warmup_state(bs):
+    nw = 1000.0
+    for ni in (0, 1, 250, 999, 1000):
+        acc, lrs, mom = warmup_state(ni, nw, 0.97, 0.01, HYP, bs)
+        assert acc == max(1, np.interp(ni, [0, nw], [1, NOMINAL_BATCH / bs]).round())                    # :200-204
+        assert lrs[0] == lrs[1] == np.interp(ni, [0, nw], [0.0, 0.01 * 0.97])                            # :206-216
+        assert lrs[2] == np.interp(ni, [0, nw], [0.1, 0.01 * 0.97])
+        assert mom == np.interp(ni, [0, nw], [0.8, 0.937])                                               # :217-221
+    assert warmup_state(1000, nw, 1.0, 0.01, HYP, 16)[0] == 4 and warmup_state(0, nw, 1.0, 0.01, HYP, 16)[0] == 1
+
+
+def test_parameter_groups_follow_the_reference_rule():
+    """yolo_trainer.py:149-160 on this repo's kindle model: every parameter lands in exactly one group, BN weights in 0."""
+    from ayolov2_b200 import synth
+
+    m = synth.build_model("yolov5n", seed=0)
+    g = parameter_groups(m)
+    params = dict(m.named_parameters())
+    assert set(g) == {id(p) for p in params.values()}
+    pg0, pg1, pg2 = [], [], []
+    for _, v in m.named_modules():
+        if hasattr(v, "bias") and isinstance(v.bias, torch.Tensor):
+            pg2.append(v.bias)
+        if isinstance(v, nn.BatchNorm2d):
+            pg0.append(v.weight)
+        elif hasattr(v, "weight") and isinstance(v.weight, torch.Tensor):
+            pg1.append(v.weight)
+    for grp, ps in enumerate((pg0, pg1, pg2)):
+        assert all(g[id(p)] == grp for p in ps)
+    assert len(pg0) + len(pg1) + len(pg2) == len(params)
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(rank)
+    flat = torch.randn(10007, generator=g)
+    whole = flat.clone()
+    dist.all_reduce(whole)
+    cuts = [(7000, 10007), (2048, 7000), (0, 2048)]  # execution order of a backward: last layers first
+    for lo, hi in cuts:
+        dist.all_reduce(flat[lo:hi])
+    ret[rank] = bool(torch.equal(flat, whole))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_whole_buffer_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29650 + os.getpid() % 200
+    mp.spawn(_bucket_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
