@@ -15,6 +15,7 @@
 //
 // Reference: the conv/BN backward that `scaler.scale(loss).backward()` (scripts/train/yolo_trainer.py:329) runs
 // through cuDNN for every kindle Conv.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ay2_common.h"
@@ -31,6 +32,7 @@ struct WgradParams {
   int boxes_x, boxes_per_img, total_chunks;
   int BH, BW, NB;
   int kh, kw, stride, pad;
+  int halo_tile_bytes;  // HALO kernels: bytes of one box's (BH+2) x (BW+2) x XB-channel tile, rounded up to 1024
 };
 
 template <int N_T, int XB>  // N_T: input channels per CTA (multiple of XB), XB: channels per x box (32 or 64)
@@ -43,11 +45,22 @@ struct WgradCfg {
   static constexpr int TAP_BYTES = NXB * XBLK_BYTES;
 };
 
-template <int N_T, int XB, int TAPS>
+// HALO (3x3 / stride 1 / pad 1 only): instead of nine shifted copies of the x tile (one per tap) a chunk loads each box's
+// (BH+2) x (BW+2) halo tile ONCE; tap (kh, kw) is the same tile read from a start address shifted by kh halo lines + kw
+// pixel rows (SWIZZLE_64B/128B are functions of the absolute shared-memory address for the TMA write and the UMMA read
+// alike, as in conv_halo_kernel). A K slice of 16 pixels is two 8-row groups of 8 horizontally adjacent pixels: SBO is
+// 8 rows when the box is >= 16 pixels wide and one halo line when it is 8 wide. The three taps of one filter row are one
+// pixel row apart, i.e. three N blocks at LBO = one row: one N = 3 * N_T instruction per filter row.
+// Per 128-pixel chunk the x side shrinks from 9 * 128 TMA rows to (BH+2) * (BW+2) (180 for an 8 x 16 box): the kernel was
+// bound by exactly that fill (training-step kernels).
+constexpr int kWgradHaloMax = 20 * 1024;  // bytes reserved per stage for the halo tiles of a chunk (one 8 x 16 box: 12 KB; four 4 x 8: 16 KB)
+
+template <int N_T, int XB, int TAPS, bool HALO = false>
 __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<N_T, XB>;
-  constexpr int STAGE_BYTES = Cfg::A_BYTES + TAPS * Cfg::TAP_BYTES;
-  constexpr int NSTAGES = (220 * 1024) / STAGE_BYTES >= 3 ? 3 : 2;
+  static_assert(!HALO || (TAPS == 9 && N_T == XB), "the halo form is the 3x3 kernel with one channel block per CTA");
+  constexpr int STAGE_BYTES = Cfg::A_BYTES + (HALO ? kWgradHaloMax : TAPS * Cfg::TAP_BYTES);
+  constexpr int NSTAGES = (220 * 1024) / STAGE_BYTES >= 4 ? 4 : (220 * 1024) / STAGE_BYTES >= 3 ? 3 : 2;
   static_assert((220 * 1024) / STAGE_BYTES >= 2, "stage too large");
   constexpr int TMEM_COLS_RAW = TAPS * N_T;
   constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128
@@ -94,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     for (int ch = chunk_begin; ch < chunk_end; ++ch) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sa = stages + stage * STAGE_BYTES;
-      mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+      mbar_expect_tx(&full_bar[stage], HALO ? Cfg::A_BYTES + p.NB * (p.BH + 2) * (p.BW + 2) * Cfg::XROW : STAGE_BYTES);
       for (int j = 0; j < p.NB; ++j) {
         const int q = ch * p.NB + j;
         const int b = q / p.boxes_per_img;
@@ -103,6 +116,9 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
         const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
         tma_load_4d(&p.tmDz, &full_bar[stage], sa + j * box_rows * 128, m0, ox, oy, b);
         tma_load_4d(&p.tmDz, &full_bar[stage], sa + Cfg::P * 128 + j * box_rows * 128, m0 + 64, ox, oy, b);
+        if constexpr (HALO) {
+          tma_load_4d(&p.tmX[0], &full_bar[stage], sa + Cfg::A_BYTES + j * p.halo_tile_bytes, c0, ox - 1, oy - 1, b);
+        } else
         for (int t = 0; t < TAPS; ++t) {
           const int kh = t / p.kw, kw = t - kh * p.kw;
           int dy, dx, view = 0;
@@ -145,6 +161,29 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       tcgen05_fence_after();
       const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES);
       const uint32_t x_addr = a_addr + Cfg::A_BYTES;
+      if constexpr (HALO) {
+        constexpr uint32_t idesc_row = make_idesc_bf16_f32(128, 3 * N_T) | (1u << 15) | (1u << 16);
+        const int line = (p.BW + 2) * Cfg::XROW;              // one halo line
+        const uint32_t sbo = p.BW == 8 ? line : 8 * Cfg::XROW;  // distance between the two 8-pixel groups of a K slice
+#pragma unroll 1
+        for (int k = 0; k < Cfg::P / 16; ++k) {
+          const int pix = 16 * k;                              // first pixel (A row) of the slice, box-major order
+          const int j = pix / box_rows, rem = pix - j * box_rows;
+          const int y = rem / p.BW, x0 = rem - y * p.BW;
+          const uint32_t a = a_addr + k * 16 * 128;
+          const uint64_t adesc = static_cast<uint64_t>((a & 0x3FFFF) >> 4) | (static_cast<uint64_t>((Cfg::P * 128) >> 4) << 16) |
+                                 (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+          const uint32_t tile = x_addr + j * p.halo_tile_bytes + (y * (p.BW + 2) + x0) * Cfg::XROW;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const uint32_t bb = tile + kh * line;
+            const uint64_t bdesc = static_cast<uint64_t>((bb & 0x3FFFF) >> 4) | (static_cast<uint64_t>(Cfg::XROW >> 4) << 16) |
+                                   (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) |
+                                   ((Cfg::XROW == 128 ? 2ull : 4ull) << 61);
+            umma_f16_ss(tmem_base + kh * 3 * N_T, adesc, bdesc, idesc_row, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int t = 0; t < TAPS; t += (TAPS - t >= TAPS_PER_MMA ? TAPS_PER_MMA : 1)) {
         const bool big = TAPS - t >= TAPS_PER_MMA;
@@ -237,26 +276,27 @@ static int encode_map4(CUtensorMap* tm, const void* base, int C, int W, int H, i
   return AY2_OK;
 }
 
-template <int N_T, int XB, int TAPS>
+template <int N_T, int XB, int TAPS, bool HALO = false>
 static int launch_wgrad(const WgradParams& kp, int grid, cudaStream_t st) {
   using Cfg = WgradCfg<N_T, XB>;
-  constexpr int STAGE_BYTES = Cfg::A_BYTES + TAPS * Cfg::TAP_BYTES;
-  constexpr int NSTAGES = (220 * 1024) / STAGE_BYTES >= 3 ? 3 : 2;
+  constexpr int STAGE_BYTES = Cfg::A_BYTES + (HALO ? kWgradHaloMax : TAPS * Cfg::TAP_BYTES);
+  constexpr int NSTAGES = (220 * 1024) / STAGE_BYTES >= 4 ? 4 : (220 * 1024) / STAGE_BYTES >= 3 ? 3 : 2;
   constexpr size_t smem = 1024 + (size_t)NSTAGES * STAGE_BYTES + 256;
   static DeviceOnce once;
   if (once.first())
-    AY2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<N_T, XB, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_wgrad_kernel<N_T, XB, TAPS><<<grid, 256, smem, st>>>(kp);
+    AY2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<N_T, XB, TAPS, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_wgrad_kernel<N_T, XB, TAPS, HALO><<<grid, 256, smem, st>>>(kp);
   AY2_CHECK_LAUNCH();
   return AY2_OK;
 }
 
-static void pick_box_w(int H, int W, int* bh, int* bw) {
+static void pick_box_w(int H, int W, int* bh, int* bw, int min_w = 1) {
   static const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {8, 8}, {4, 16}, {16, 4}, {2, 32}, {4, 8}, {8, 4}, {2, 16}, {4, 4}, {2, 8}, {1, 16}};
   double best = 1e30;
   int bi = 0;
   for (int i = 0; i < (int)(sizeof(cand) / sizeof(cand[0])); ++i) {
     const int h = cand[i][0], w = cand[i][1];
+    if (w < min_w) continue;
     const double cover = (double)ceil_div(H, h) * h * (double)ceil_div(W, w) * w;
     const double cost = cover * (1.0 + 0.002 * (128 / (h * w)));
     if (cost < best) {
@@ -288,6 +328,21 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   memset(&kp, 0, sizeof(kp));
   int bh, bw;
   pick_box_w(d->out_h, d->out_w, &bh, &bw);
+  // 3x3 / stride 1 / pad 1: one halo tile per box instead of nine shifted x tiles (boxes at least 8 pixels wide, so that
+  // the 8-row groups of the MN-major operand are horizontally adjacent pixels)
+  static const int env_halo = [] { const char* e = getenv("AY2_WGRAD_HALO"); return e ? atoi(e) : 1; }();
+  bool halo = false;
+  if (env_halo && taps == 9 && d->stride == 1 && d->pad == 1) {
+    int hh, hw;
+    pick_box_w(d->out_h, d->out_w, &hh, &hw, 8);
+    const int tile = ((hh + 2) * (hw + 2) * 64 + 1023) & ~1023;  // XB = 32 channels = 64-byte rows
+    if ((128 / (hh * hw)) * tile <= kWgradHaloMax) {
+      halo = true;
+      bh = hh;
+      bw = hw;
+      kp.halo_tile_bytes = tile;
+    }
+  }
   kp.BH = bh;
   kp.BW = bw;
   kp.NB = 128 / (bh * bw);
@@ -326,7 +381,8 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   if (rc == AY2_OK) {
     if (d->stride == 1) {
       const int64_t rowp = d->in_row_pixels > 0 ? d->in_row_pixels : d->in_w;
-      rc = encode_map4(&kp.tmX[0], x, d->cin, d->in_w, d->in_h, d->batch, cs, cs * rowp, cs * rowp * d->in_h, xb, bw, bh);
+      rc = encode_map4(&kp.tmX[0], x, d->cin, d->in_w, d->in_h, d->batch, cs, cs * rowp, cs * rowp * d->in_h, xb,
+                       halo ? bw + 2 : bw, halo ? bh + 2 : bh);
     } else {
       for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
         for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {
@@ -339,7 +395,8 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   if (rc != AY2_OK) return rc;
   const int grid = kp.num_m_tiles * kp.num_n_tiles * ksplit;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (taps == 9) rc = launch_wgrad<32, 32, 9>(kp, grid, st);
+  if (taps == 9 && halo) rc = launch_wgrad<32, 32, 9, true>(kp, grid, st);
+  else if (taps == 9) rc = launch_wgrad<32, 32, 9>(kp, grid, st);
   else if (n_t == 256) rc = launch_wgrad<256, 64, 1>(kp, grid, st);
   else if (n_t == 128) rc = launch_wgrad<128, 64, 1>(kp, grid, st);
   else if (n_t == 64) rc = launch_wgrad<64, 64, 1>(kp, grid, st);

@@ -28,6 +28,8 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   o.w = pack_bf16x2(f[6], f[7]);
   return o;
 }
+constexpr int kUnroll = 4;  // pixels per thread per loop trip of the streaming kernels below
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 // sigmoid(x) = 0.5 + 0.5 * tanh(x/2): ONE MUFU op (tanh.approx, |rel err| <= 2^-11, below the bf16 storage of every
 // tensor it feeds). exp2 + rcp would be two, and these kernels are MUFU-bound: 2 passes x 5e9 elements per step.
 __device__ __forceinline__ float sigmoid_acc(float x) {
@@ -70,16 +72,37 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long n
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  if (active)
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+  if (active) {
+    // kUnroll independent 16-byte loads per thread in flight: with one, the ~1500 resident threads of an SM hold 24 KB
+    // outstanding, about half of what HBM3e needs to stay busy (bandwidth x latency / 148 SMs ~ 45 KB)
+    const long long step = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + pl;
+    const __nv_bfloat16* zp = z + cg * 8;
+    for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
+      uint4 q[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) q[u] = ld_stream(zp + (p + u * step) * cs);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float f[8];
+        unpack8(q[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += f[j];
+          acc[1][j] += f[j] * f[j];
+        }
+      }
+    }
+    for (; p < npix; p += step) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(z + p * cs + cg * 8), f);
+      unpack8(ld_stream(zp + p * cs), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[0][j] += f[j];
         acc[1][j] += f[j] * f[j];
       }
     }
+  }
   double* dst[2] = {sum, sumsq};
   block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
 }
@@ -120,11 +143,11 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long
     Bc[j] = beta[c] - A[j] * mean[c];
   }
   const long long step = (long long)gridDim.x * lanes;
-  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += step) {
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
-    float r[8];
-    if (res) unpack8(*reinterpret_cast<const uint4*>(res + p * rcs + cg * 8), r);
+  long long p = (long long)blockIdx.x * lanes + pl;
+  auto one = [&](const uint4& qz, const uint4& qr, long long pp) {
+    float f[8], r[8];
+    unpack8(qz, f);
+    if (res) unpack8(qr, r);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float u = fmaf(f[j], A[j], Bc[j]);
@@ -132,8 +155,20 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long
       if (res) u += r[j];
       f[j] = u;
     }
-    *reinterpret_cast<uint4*>(y + p * ycs + cg * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(y + pp * ycs + cg * 8) = pack8(f);
+  };
+  for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
+    uint4 qz[kUnroll], qr[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      qz[u] = ld_stream(z + (p + u * step) * zcs + cg * 8);
+      qr[u] = res ? ld_stream(res + (p + u * step) * rcs + cg * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) one(qz[u], qr[u], p + u * step);
   }
+  for (; p < npix; p += step)
+    one(ld_stream(z + p * zcs + cg * 8), res ? ld_stream(res + p * rcs + cg * 8) : make_uint4(0, 0, 0, 0), p);
 }
 
 // backward, pass 1: s1[c] = sum dyh, s2[c] = sum dyh * xhat, with dyh = dy * act'(u), u = gamma*xhat + beta
@@ -157,11 +192,11 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
     ga[j] = active ? gamma[c] : 0.f;
     be[j] = active ? beta[c] : 0.f;
   }
-  if (active)
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += (long long)gridDim.x * lanes) {
+  if (active) {
+    auto one = [&](const uint4& qg, const uint4& qz) {
       float g[8], f[8];
-      unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cg * 8), g);
-      unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
+      unpack8(qg, g);
+      unpack8(qz, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = fmaf(f[j], is[j], -ms[j]);
@@ -174,7 +209,21 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
         acc[0][j] += d;
         acc[1][j] = fmaf(d, xh, acc[1][j]);
       }
+    };
+    const long long step = (long long)gridDim.x * lanes;
+    long long p = (long long)blockIdx.x * lanes + pl;
+    for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
+      uint4 qg[kUnroll], qz[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        qg[u] = ld_stream(dy + (p + u * step) * dcs + cg * 8);
+        qz[u] = ld_stream(z + (p + u * step) * zcs + cg * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) one(qg[u], qz[u]);
     }
+    for (; p < npix; p += step) one(ld_stream(dy + p * dcs + cg * 8), ld_stream(z + p * zcs + cg * 8));
+  }
   double* dst[2] = {s1, s2};
   block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
 }
@@ -202,11 +251,10 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
     k1[j] = k0[j] * (float)s1[c] * invn;
     k2[j] = k0[j] * (float)s2[c] * invn;
   }
-  const long long step = (long long)gridDim.x * lanes;
-  for (long long p = (long long)blockIdx.x * lanes + pl; p < npix; p += step) {
+  auto one = [&](const uint4& qg, const uint4& qz, long long pp) {
     float g[8], f[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + p * dcs + cg * 8), g);
-    unpack8(*reinterpret_cast<const uint4*>(z + p * zcs + cg * 8), f);
+    unpack8(qg, g);
+    unpack8(qz, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = fmaf(f[j], is[j], -ms[j]);
@@ -218,8 +266,21 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
       }
       g[j] = fmaf(d, k0[j], -fmaf(xh, k2[j], k1[j]));
     }
-    *reinterpret_cast<uint4*>(dz + p * zdcs + cg * 8) = pack8(g);
+    *reinterpret_cast<uint4*>(dz + pp * zdcs + cg * 8) = pack8(g);
+  };
+  const long long step = (long long)gridDim.x * lanes;
+  long long p = (long long)blockIdx.x * lanes + pl;
+  for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
+    uint4 qg[kUnroll], qz[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      qg[u] = ld_stream(dy + (p + u * step) * dcs + cg * 8);
+      qz[u] = ld_stream(z + (p + u * step) * zcs + cg * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) one(qg[u], qz[u], p + u * step);
   }
+  for (; p < npix; p += step) one(ld_stream(dy + p * dcs + cg * 8), ld_stream(z + p * zcs + cg * 8), p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,34 +433,50 @@ __global__ void maxpool_bwd_tile_kernel(const __nv_bfloat16* __restrict__ x, int
 }
 
 // (bs, na, ny, nx, no) fp32 <-> NHWC bf16 [B, ny, nx, cstride] (channel = a*no + o): YOLOHead train layout
-__global__ void head_grad_to_nhwc_kernel(const float* __restrict__ g, int B, int na, int ny, int nx, int no,
+// One warp per pixel: lane l handles the channel pairs (2l + 64j, 2l + 64j + 1), so that the fp32 side is touched in
+// runs of consecutive floats (one anchor's `no` values are contiguous there) and the bf16 NHWC side in 128-byte lines.
+__global__ void head_grad_to_nhwc_kernel(const float* __restrict__ g, int npix, int na, int nynx, int no,
                                          __nv_bfloat16* __restrict__ out, int cs) {
-  const long long total = (long long)B * ny * nx * cs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % cs);
-    const long long pix = i / cs;
-    float v = 0.f;
-    if (ch < na * no) {
-      const int a = ch / no, o = ch - a * no;
-      const int x = (int)(pix % nx), y = (int)((pix / nx) % ny), b = (int)(pix / ((long long)nx * ny));
-      v = g[((((long long)b * na + a) * ny + y) * nx + x) * no + o];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int used = na * no;
+  for (int pix = blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += gridDim.x * wpb) {
+    const int b = pix / nynx, yx = pix - b * nynx;
+    const float* gb = g + (size_t)b * na * nynx * no + (size_t)yx * no;
+    __nv_bfloat16* o = out + (size_t)pix * cs;
+    for (int ch = 2 * lane; ch < cs; ch += 64) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = ch + e;
+        v[e] = 0.f;
+        if (c < used) {
+          const int a = c / no;
+          v[e] = gb[(size_t)a * nynx * no + (c - a * no)];
+        }
+      }
+      *reinterpret_cast<__nv_bfloat162*>(o + ch) = __floats2bfloat162_rn(v[0], v[1]);
     }
-    out[i] = __float2bfloat16_rn(v);
   }
 }
-__global__ void head_logits_to_train_kernel(const __nv_bfloat16* __restrict__ logits, int cs, int B, int na, int ny, int nx,
+__global__ void head_logits_to_train_kernel(const __nv_bfloat16* __restrict__ logits, int cs, int npix, int na, int nynx,
                                             int no, float* __restrict__ out) {
-  const long long total = (long long)B * na * ny * nx * no;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(i % no);
-    long long r = i / no;
-    const int x = (int)(r % nx);
-    r /= nx;
-    const int y = (int)(r % ny);
-    r /= ny;
-    const int a = (int)(r % na);
-    const int b = (int)(r / na);
-    out[i] = __bfloat162float(logits[(((long long)b * ny + y) * nx + x) * cs + a * no + o]);
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int used = na * no;
+  for (int pix = blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += gridDim.x * wpb) {
+    const int b = pix / nynx, yx = pix - b * nynx;
+    float* ob = out + (size_t)b * na * nynx * no + (size_t)yx * no;
+    const __nv_bfloat16* in = logits + (size_t)pix * cs;
+    for (int ch = 2 * lane; ch < used; ch += 64) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(in + ch));
+      const int a0 = ch / no;
+      ob[(size_t)a0 * nynx * no + (ch - a0 * no)] = v.x;
+      if (ch + 1 < used) {
+        const int a1 = (ch + 1) / no;
+        ob[(size_t)a1 * nynx * no + (ch + 1 - a1 * no)] = v.y;
+      }
+    }
   }
 }
 
@@ -616,8 +693,9 @@ extern "C" int ay2_maxpool_bwd(const void* x, int32_t x_cstride, const void* dy,
 extern "C" int ay2_head_grad_to_nhwc(const float* grad, int32_t batch, int32_t na, int32_t ny, int32_t nx, int32_t no,
                                      void* out, int32_t out_cstride, void* stream) {
   AY2_REQUIRE(grad && out && na * no <= out_cstride, "ay2_head_grad_to_nhwc: bad arguments");
-  head_grad_to_nhwc_kernel<<<ew_grid((long long)batch * ny * nx * out_cstride, 256), 256, 0, AY2_ST>>>(
-      grad, batch, na, ny, nx, no, AY2_BF(out), out_cstride);
+  AY2_REQUIRE(out_cstride % 2 == 0 && (long long)batch * ny * nx < (1ll << 31), "ay2_head_grad_to_nhwc: bad layout");
+  head_grad_to_nhwc_kernel<<<ew_grid((long long)batch * ny * nx * 32, 256), 256, 0, AY2_ST>>>(
+      grad, batch * ny * nx, na, ny * nx, no, AY2_BF(out), out_cstride);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;
@@ -626,8 +704,9 @@ extern "C" int ay2_head_grad_to_nhwc(const float* grad, int32_t batch, int32_t n
 extern "C" int ay2_head_logits_to_train(const void* logits, int32_t cstride, int32_t batch, int32_t na, int32_t ny,
                                         int32_t nx, int32_t no, float* out, void* stream) {
   AY2_REQUIRE(logits && out && na * no <= cstride, "ay2_head_logits_to_train: bad arguments");
-  head_logits_to_train_kernel<<<ew_grid((long long)batch * na * ny * nx * no, 256), 256, 0, AY2_ST>>>(
-      AY2_CBF(logits), cstride, batch, na, ny, nx, no, out);
+  AY2_REQUIRE(cstride % 2 == 0 && (long long)batch * ny * nx < (1ll << 31), "ay2_head_logits_to_train: bad layout");
+  head_logits_to_train_kernel<<<ew_grid((long long)batch * ny * nx * 32, 256), 256, 0, AY2_ST>>>(
+      AY2_CBF(logits), cstride, batch * ny * nx, na, ny * nx, no, out);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -333,15 +333,15 @@ class TrainEngine:
             cpad = _round_up(na * no, 16)
             logits = self.new_act(x.H, x.W, cpad)
             out = torch.zeros((self.B, na, x.H, x.W, no), dtype=torch.float32, device=self.device)
-            gin = torch.zeros_like(out)
             self.head_out.append(out)
-            self.head_gin.append(gin)
             gl = self.g(logits)
-            # gradient arrives as (bs, na, ny, nx, no) fp32 -> NHWC bf16 before the conv's backward (executed reversed:
-            # append the conversion AFTER the conv record so that it runs first)
+            # The gradient arrives as (bs, na, ny, nx, no) fp32 and is converted to NHWC bf16 straight from the caller's
+            # tensor, eagerly, before the backward graphs replay (`backward`): staging it in a static buffer first would
+            # be a 1.1 GB read + write per step at bs 128. The conversion writes every channel of `gl`, padding included.
+            self.head_gin.append(gl)
+            self.overwritten.add(id(logits.buf))
             self._head_conv(conv, x, logits, na * no)
             self.fwd.append(lambda l=logits, o=out: ops.head_logits_to_train(l, na, no, o))
-            self.bwd.append(lambda g_=gin, gl_=gl: ops.head_grad_to_nhwc(g_, gl_))
 
     def _head_conv(self, conv: nn.Conv2d, x: ActView, logits: ActView, nch: int) -> None:
         """1x1 conv with bias, Cout = na*no padded to the logits buffer width."""
@@ -524,6 +524,10 @@ class TrainEngine:
         self.static_in.copy_(img)
         self._img = self.static_in
         self._run_or_replay("fwd", self._forward_body)
+        if getattr(self, "static_grads", False):
+            # trainer mode: the loss and its backward run before the next forward (the generation guard enforces it), so
+            # the outputs may alias the graph's static buffers -- fresh tensor objects, no copy
+            return [o.detach() for o in self.head_out]
         return [o.clone() for o in self.head_out]
 
     def _backward_chunk(self, k: int) -> None:
@@ -537,8 +541,11 @@ class TrainEngine:
             b()
 
     def backward(self, grads: Sequence[torch.Tensor]) -> Dict[int, torch.Tensor]:
-        for gin, g_ in zip(self.head_gin, grads):
-            gin.copy_(g_)
+        for gl, g_ in zip(self.head_gin, grads):
+            g_ = g_.detach()
+            if g_.dtype != torch.float32 or not g_.is_contiguous():
+                g_ = g_.float().contiguous()
+            ops.head_grad_to_nhwc(g_, gl)
         chunks = getattr(self, "bwd_chunks", None)
         if chunks and len(chunks) > 1:
             # bucketed backward: one CUDA graph per piece, `on_grad_bucket(k, lo, hi)` after each (the trainer all-reduces

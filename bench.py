@@ -251,6 +251,18 @@ def synth_targets(bs: int, seed: int):
     return torch.tensor(rows, dtype=torch.float32) if rows else torch.zeros((0, 6))
 
 
+def calibrated_model(dev, name: str = "yolov5s"):
+    """The benchmark's model: random-init `name` (seed 0) whose detect head is re-scaled so that the NMS leg is not vacuous:
+    ~8 % of the rows of every pyramid level (~2,000 of 25,200 per image) are candidates at conf 0.25, over
+    many classes (ayolov2_b200.synth.calibrate_head). The profiling tools under tools/ use the same function."""
+    from ayolov2_b200 import synth as model_utils
+
+    model = model_utils.build_model(name, seed=0).to(dev)
+    sample = synth_images(32, 7).to(dev).float() / 255.0
+    model_utils.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.08)
+    return model
+
+
 def bench_train_step(name: str, global_batch: int, size: int, steps: int, warmup: int, rank: int, world: int, dev, barrier,
                      max_over_ranks):
     """One BASELINE train config through ayolov2_b200.trainer.TrainStep (the drop-in of YoloTrainer.training_step): uint8
@@ -413,10 +425,7 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    model = model_utils.build_model("yolov5s", seed=0).to(dev)
-    # make the NMS leg non-vacuous: ~8 % of the rows of every level become candidates (ayolov2_b200.synth.calibrate_head)
-    sample = synth_images(8, 7).to(dev).float() / 255.0
-    model_utils.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.12)
+    model = calibrated_model(dev)
     det = Detector(model, BATCH, H, W, conf_thres=CONF, iou_thres=IOU, in_dtype=torch.uint8, device=dev)
     host_imgs = [synth_images(BATCH, 1000 + rank * 10 + i).pin_memory() for i in range(3)]
     dev_imgs = [h.to(dev) for h in host_imgs[:2]]

@@ -61,6 +61,13 @@ def test_bn_silu_forward_backward(C, cs, c0):
     (4, 20, 20, 512, 256, 1, 1, 0, False),
     (2, 16, 24, 32, 32, 3, 1, 1, False),
     (2, 40, 40, 64, 128, 3, 2, 1, False),
+    # 3x3 / s1: the halo-tile form of the kernel (one (BH+2) x (BW+2) x tile per box, taps = shifted descriptors) with
+    # 8 x 16 boxes (160, 80), two 8 x 8 boxes per chunk (40), four 4 x 8 (20, above), ragged maps and 16 input channels
+    (1, 160, 160, 32, 32, 3, 1, 1, False),
+    (2, 80, 80, 64, 64, 3, 1, 1, True),
+    (2, 40, 40, 128, 128, 3, 1, 1, False),
+    (2, 12, 20, 16, 32, 3, 1, 1, False),
+    (3, 22, 38, 32, 48, 3, 1, 1, False),
 ], ids=lambda c: "x".join(map(str, c)))
 def test_conv_wgrad(case):
     from ayolov2_b200 import ops

@@ -12,9 +12,7 @@ from ayolov2_b200 import synth  # noqa: E402
 from ayolov2_b200.detector import Detector  # noqa: E402
 
 dev = torch.device("cuda:0")
-model = synth.build_model("yolov5s", seed=0).to(dev)
-sample = bench.synth_images(8, 7).to(dev).float() / 255.0
-synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.12)
+model = bench.calibrated_model(torch.device("cuda:0"))
 det = Detector(model, bench.BATCH, bench.H, bench.W, conf_thres=bench.CONF, iou_thres=bench.IOU, in_dtype=torch.uint8, device=dev)
 imgs = bench.synth_images(bench.BATCH, 1000).to(dev)
 det.run_device(imgs)

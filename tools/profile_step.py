@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
+import bench  # noqa: E402
 from ayolov2_b200 import synth  # noqa: E402
 from ayolov2_b200.detector import Detector  # noqa: E402
 from ayolov2_b200.nms import nms_device  # noqa: E402
@@ -13,10 +14,8 @@ from ayolov2_b200.nms import nms_device  # noqa: E402
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 torch.manual_seed(0)
-model = synth.build_model("yolov5s", seed=0).cuda()
+model = bench.calibrated_model(torch.device("cuda:0"))
 img = torch.randint(0, 256, (batch, 3, 640, 640), dtype=torch.uint8, device="cuda")
-sample = torch.randint(0, 256, (4, 3, 640, 640), dtype=torch.uint8, device="cuda").float() / 255.0
-synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.12)
 det = Detector(model, batch, 640, 640, in_dtype=torch.uint8)
 eng = det.engine
 eng._img = img
