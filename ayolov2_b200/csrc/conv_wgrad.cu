@@ -32,7 +32,7 @@ struct WgradParams {
   int boxes_x, boxes_per_img, total_chunks;
   int BH, BW, NB;
   int kh, kw, stride, pad;
-  int halo_tile_bytes;  // HALO kernels: bytes of one box's (BH+2) x (BW+2) x XB-channel tile, rounded up to 1024
+  int halo_tile_bytes;  // HALO kernels: bytes of one image's (BH+2) x (BW+2) x XB-channel tile
 };
 
 template <int N_T, int XB>  // N_T: input channels per CTA (multiple of XB), XB: channels per x box (32 or 64)
@@ -53,7 +53,7 @@ struct WgradCfg {
 // pixel row apart, i.e. three N blocks at LBO = one row: one N = 3 * N_T instruction per filter row.
 // Per 128-pixel chunk the x side shrinks from 9 * 128 TMA rows to (BH+2) * (BW+2) (180 for an 8 x 16 box): the kernel was
 // bound by exactly that fill (training-step kernels).
-constexpr int kWgradHaloMax = 20 * 1024;  // bytes reserved per stage for the halo tiles of a chunk (one 8 x 16 box: 12 KB; four 4 x 8: 16 KB)
+constexpr int kWgradHaloMax = 20 * 1024;  // bytes reserved per stage for the halo tiles of a chunk (one 8 x 16 box: 11.25 KB; eight 2 x 8: 20 KB)
 
 template <int N_T, int XB, int TAPS, bool HALO = false>
 __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -107,20 +107,25 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     for (int ch = chunk_begin; ch < chunk_end; ++ch) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sa = stages + stage * STAGE_BYTES;
-      mbar_expect_tx(&full_bar[stage], HALO ? Cfg::A_BYTES + p.NB * (p.BH + 2) * (p.BW + 2) * Cfg::XROW : STAGE_BYTES);
-      for (int j = 0; j < p.NB; ++j) {
-        const int q = ch * p.NB + j;
-        const int b = q / p.boxes_per_img;
-        const int r = q - b * p.boxes_per_img;
-        const int py = r / p.boxes_x;
-        const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW;
-        tma_load_4d(&p.tmDz, &full_bar[stage], sa + j * box_rows * 128, m0, ox, oy, b);
-        tma_load_4d(&p.tmDz, &full_bar[stage], sa + Cfg::P * 128 + j * box_rows * 128, m0 + 64, ox, oy, b);
-        if constexpr (HALO) {
-          tma_load_4d(&p.tmX[0], &full_bar[stage], sa + Cfg::A_BYTES + j * p.halo_tile_bytes, c0, ox - 1, oy - 1, b);
-        } else
+      // One chunk = one spatial box of NB consecutive images: every operand is ONE TMA box with a batch extent of NB
+      // (rows land image-major, then box row, then pixel -- the same K order for dz and x), so the single producer thread
+      // issues 3 (halo) / 2 + TAPS copies per chunk whatever the map size. Images past the batch are zero-filled.
+      const int ig = ch / p.boxes_per_img;
+      const int r = ch - ig * p.boxes_per_img;
+      const int py = r / p.boxes_x;
+      const int oy = py * p.BH, ox = (r - py * p.boxes_x) * p.BW, b = ig * p.NB;
+      const bool two = m0 + 64 < p.cout;  // the second 64-channel block of dz exists (else its accumulator rows are never read)
+      const uint32_t x_bytes = HALO ? p.NB * p.halo_tile_bytes : STAGE_BYTES - Cfg::A_BYTES;
+      mbar_expect_tx(&full_bar[stage], (two ? Cfg::A_BYTES : Cfg::A_BYTES / 2) + x_bytes);
+      tma_load_4d(&p.tmDz, &full_bar[stage], sa, m0, ox, oy, b);
+      if (two) tma_load_4d(&p.tmDz, &full_bar[stage], sa + Cfg::P * 128, m0 + 64, ox, oy, b);
+      if constexpr (HALO) {
+        tma_load_4d(&p.tmX[0], &full_bar[stage], sa + Cfg::A_BYTES, c0, ox - 1, oy - 1, b);
+      } else {
+        constexpr int KW = TAPS == 9 ? 3 : 1;
+#pragma unroll
         for (int t = 0; t < TAPS; ++t) {
-          const int kh = t / p.kw, kw = t - kh * p.kw;
+          const int kh = t / KW, kw = t - kh * KW;
           int dy, dx, view = 0;
           if (p.stride == 1) {
             dy = kh - p.pad;
@@ -135,8 +140,7 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
           uint8_t* sx = sa + Cfg::A_BYTES + t * Cfg::TAP_BYTES;
 #pragma unroll
           for (int xb = 0; xb < Cfg::NXB; ++xb)
-            tma_load_4d(&p.tmX[view], &full_bar[stage], sx + xb * Cfg::XBLK_BYTES + j * box_rows * Cfg::XROW,
-                        c0 + xb * XB, ox + dx, oy + dy, b);
+            tma_load_4d(&p.tmX[view], &full_bar[stage], sx + xb * Cfg::XBLK_BYTES, c0 + xb * XB, ox + dx, oy + dy, b);
         }
       }
       if (++stage == NSTAGES) {
@@ -155,6 +159,25 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
     constexpr int N_BIG = TAPS_PER_MMA * N_T;
     constexpr uint32_t idesc_big = make_idesc_bf16_f32(128, N_BIG) | (1u << 15) | (1u << 16);
     constexpr uint32_t idesc_one = make_idesc_bf16_f32(128, N_T) | (1u << 15) | (1u << 16);
+    // halo form: the K slices' start offsets inside the chunk's halo tiles do not depend on the chunk -- compute them
+    // once (this thread issues every MMA alone; integer divisions per slice made IT the bottleneck of the kernel)
+    [[maybe_unused]] constexpr uint32_t idesc_row = make_idesc_bf16_f32(128, 3 * N_T) | (1u << 15) | (1u << 16);
+    [[maybe_unused]] uint32_t halo_off[Cfg::P / 16];
+    [[maybe_unused]] uint32_t halo_line = 0;
+    [[maybe_unused]] uint64_t halo_desc_hi = 0;
+    if constexpr (HALO) {
+      halo_line = (p.BW + 2) * Cfg::XROW;                            // one halo line
+      const uint32_t sbo = p.BW == 8 ? halo_line : 8 * Cfg::XROW;    // distance between the two 8-pixel groups of a K slice
+      halo_desc_hi = (static_cast<uint64_t>(Cfg::XROW >> 4) << 16) | (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) |
+                     ((Cfg::XROW == 128 ? 2ull : 4ull) << 61);
+#pragma unroll
+      for (int k = 0; k < Cfg::P / 16; ++k) {
+        const int pix = 16 * k;                                       // first pixel (A row) of the slice, image-major order
+        const int j = pix / box_rows, rem = pix - j * box_rows;
+        const int y = rem / p.BW, x0 = rem - y * p.BW;
+        halo_off[k] = j * p.halo_tile_bytes + (y * (p.BW + 2) + x0) * Cfg::XROW;
+      }
+    }
     int stage = 0, phase = 0;
     for (int i = 0; i < nchunks; ++i) {
       mbar_wait(&full_bar[stage], phase);
@@ -162,24 +185,15 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
       const uint32_t a_addr = smem_u32(stages + stage * STAGE_BYTES);
       const uint32_t x_addr = a_addr + Cfg::A_BYTES;
       if constexpr (HALO) {
-        constexpr uint32_t idesc_row = make_idesc_bf16_f32(128, 3 * N_T) | (1u << 15) | (1u << 16);
-        const int line = (p.BW + 2) * Cfg::XROW;              // one halo line
-        const uint32_t sbo = p.BW == 8 ? line : 8 * Cfg::XROW;  // distance between the two 8-pixel groups of a K slice
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < Cfg::P / 16; ++k) {
-          const int pix = 16 * k;                              // first pixel (A row) of the slice, box-major order
-          const int j = pix / box_rows, rem = pix - j * box_rows;
-          const int y = rem / p.BW, x0 = rem - y * p.BW;
           const uint32_t a = a_addr + k * 16 * 128;
           const uint64_t adesc = static_cast<uint64_t>((a & 0x3FFFF) >> 4) | (static_cast<uint64_t>((Cfg::P * 128) >> 4) << 16) |
                                  (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-          const uint32_t tile = x_addr + j * p.halo_tile_bytes + (y * (p.BW + 2) + x0) * Cfg::XROW;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
-            const uint32_t bb = tile + kh * line;
-            const uint64_t bdesc = static_cast<uint64_t>((bb & 0x3FFFF) >> 4) | (static_cast<uint64_t>(Cfg::XROW >> 4) << 16) |
-                                   (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) |
-                                   ((Cfg::XROW == 128 ? 2ull : 4ull) << 61);
+            const uint32_t bb = x_addr + halo_off[k] + kh * halo_line;
+            const uint64_t bdesc = halo_desc_hi | static_cast<uint64_t>((bb & 0x3FFFF) >> 4);
             umma_f16_ss(tmem_base + kh * 3 * N_T, adesc, bdesc, idesc_row, (i | k) != 0 ? 1u : 0u);
           }
         }
@@ -250,7 +264,7 @@ typedef CUresult (*PFN_encodeTiledW)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int encode_map4(CUtensorMap* tm, const void* base, int C, int W, int H, int B, int64_t sW, int64_t sH, int64_t sB,
-                       int boxc, int bw, int bh) {
+                       int boxc, int bw, int bh, int nb) {
   static PFN_encodeTiledW enc = nullptr;
   if (!enc) {
     void* ptr = nullptr;
@@ -264,7 +278,7 @@ static int encode_map4(CUtensorMap* tm, const void* base, int C, int W, int H, i
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sB * 2};
-  cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUtensorMapSwizzle sw = boxc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -335,7 +349,7 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   if (env_halo && taps == 9 && d->stride == 1 && d->pad == 1) {
     int hh, hw;
     pick_box_w(d->out_h, d->out_w, &hh, &hw, 8);
-    const int tile = ((hh + 2) * (hw + 2) * 64 + 1023) & ~1023;  // XB = 32 channels = 64-byte rows
+    const int tile = (hh + 2) * (hw + 2) * 64;  // XB = 32 channels = 64-byte rows; the NB tiles of a box are contiguous
     if ((128 / (hh * hw)) * tile <= kWgradHaloMax) {
       halo = true;
       bh = hh;
@@ -348,8 +362,7 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   kp.NB = 128 / (bh * bw);
   kp.boxes_x = ceil_div(d->out_w, bw);
   kp.boxes_per_img = kp.boxes_x * ceil_div(d->out_h, bh);
-  const long long total_boxes = (long long)kp.boxes_per_img * d->batch;
-  kp.total_chunks = (int)((total_boxes + kp.NB - 1) / kp.NB);
+  kp.total_chunks = kp.boxes_per_img * ceil_div(d->batch, kp.NB);  // chunk = (group of NB images, spatial box)
   kp.kh = d->kh;
   kp.kw = d->kw;
   kp.stride = d->stride;
@@ -376,19 +389,19 @@ extern "C" int ay2_conv_wgrad(const ay2_conv_desc* d, const void* x, const void*
   if (ksplit > kp.total_chunks) ksplit = kp.total_chunks;
   kp.ksplit = ksplit;
   int rc = encode_map4(&kp.tmDz, dz, d->cout, d->out_w, d->out_h, d->batch, d->out_cstride, (int64_t)d->out_cstride * d->out_w,
-                       (int64_t)d->out_cstride * d->out_w * d->out_h, 64, bw, bh);
+                       (int64_t)d->out_cstride * d->out_w * d->out_h, 64, bw, bh, kp.NB);
   const int64_t cs = d->in_cstride;
   if (rc == AY2_OK) {
     if (d->stride == 1) {
       const int64_t rowp = d->in_row_pixels > 0 ? d->in_row_pixels : d->in_w;
       rc = encode_map4(&kp.tmX[0], x, d->cin, d->in_w, d->in_h, d->batch, cs, cs * rowp, cs * rowp * d->in_h, xb,
-                       halo ? bw + 2 : bw, halo ? bh + 2 : bh);
+                       halo ? bw + 2 : bw, halo ? bh + 2 : bh, kp.NB);
     } else {
       for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
         for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {
           const uint8_t* base = static_cast<const uint8_t*>(x) + ((int64_t)ph * d->in_w + pw) * cs * 2;
           rc = encode_map4(&kp.tmX[ph * 2 + pw], base, d->cin, d->in_w / 2, d->in_h / 2, d->batch, 2 * cs, 2 * cs * d->in_w,
-                           cs * d->in_w * d->in_h, xb, bw, bh);
+                           cs * d->in_w * d->in_h, xb, bw, bh, kp.NB);
         }
     }
   }

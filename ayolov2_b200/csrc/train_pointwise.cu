@@ -60,6 +60,71 @@ __device__ __forceinline__ void block_channel_reduce(float (*acc)[8], int tpp, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed fp32 math (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per instruction). The streaming BatchNorm kernels below
+// were bound by instruction issue, not HBM: ~1e12 elements/s whatever the byte count (tools/prof_trainops.py: the backward
+// reduce pass ran at 3.5 TB/s next to an apply pass at 6.0 TB/s with the same math and 1.5x the bytes). A thread's 8
+// channels are 4 float2 pairs; every per-element multiply/add below is one packed instruction per PAIR.
+// ------------------------------------------------------------------------------------------------
+struct F8 {
+  float2 v[4];
+};
+__device__ __forceinline__ F8 unpack8p(const uint4& q) {
+  F8 r;
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8p(const F8& f) {
+  uint4 o;
+  o.x = pack_bf16x2(f.v[0].x, f.v[0].y);
+  o.y = pack_bf16x2(f.v[1].x, f.v[1].y);
+  o.z = pack_bf16x2(f.v[2].x, f.v[2].y);
+  o.w = pack_bf16x2(f.v[3].x, f.v[3].y);
+  return o;
+}
+// per-channel constants of a thread's 8 channels as 4 pairs (two 16-byte loads)
+__device__ __forceinline__ F8 load8p(const float* __restrict__ p) {
+  F8 r;
+  if (reinterpret_cast<uintptr_t>(p) & 15) {  // a parameter that is a view at an odd offset of a flat buffer
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.v[j] = make_float2(p[2 * j], p[2 * j + 1]);
+    return r;
+  }
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = make_float2(a.x, a.y);
+  r.v[1] = make_float2(a.z, a.w);
+  r.v[2] = make_float2(b.x, b.y);
+  r.v[3] = make_float2(b.z, b.w);
+  return r;
+}
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+// d * silu'(u) for a pair, from h = u / 2: t = tanh(h), sigmoid = 0.5 + 0.5 t, sigmoid (1 - sigmoid) = (1 - t^2) / 4, so
+// silu'(u) = sigmoid + u sigmoid (1 - sigmoid) = sigmoid + 0.5 h (1 - t^2). One MUFU per element, 5 packed instructions per pair.
+__device__ __forceinline__ float2 silu_grad_times(float2 d, float2 h) {
+  const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+  const float2 half2 = make_float2(0.5f, 0.5f), one2 = make_float2(1.0f, 1.0f);
+  const float2 sg = __ffma2_rn(half2, t, half2);
+  const float2 q = __ffma2_rn(make_float2(-t.x, -t.y), t, one2);
+  const float2 w = __fmul2_rn(h, q);
+  return __fmul2_rn(d, __ffma2_rn(half2, w, sg));
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-channel sum / sum of squares of z [npix][cstride] (first C channels)
 // ------------------------------------------------------------------------------------------------
 __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long npix, int C, int cs, double* sum,
@@ -69,39 +134,36 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, long long n
   const int lanes = blockDim.x / tpp;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const bool active = pl < lanes;
-  float acc[2][8];
+  float2 a0[4], a1[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (int j = 0; j < 4; ++j) a0[j] = a1[j] = make_float2(0.f, 0.f);
   if (active) {
-    // kUnroll independent 16-byte loads per thread in flight: with one, the ~1500 resident threads of an SM hold 24 KB
-    // outstanding, about half of what HBM3e needs to stay busy (bandwidth x latency / 148 SMs ~ 45 KB)
+    // kUnroll independent 16-byte loads per thread in flight (bandwidth x latency / 148 SMs ~ 45 KB per SM)
     const long long step = (long long)gridDim.x * lanes;
     long long p = (long long)blockIdx.x * lanes + pl;
     const __nv_bfloat16* zp = z + cg * 8;
+    auto one = [&](const uint4& q) {
+      const F8 f = unpack8p(q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a0[j] = __fadd2_rn(a0[j], f.v[j]);
+        a1[j] = __ffma2_rn(f.v[j], f.v[j], a1[j]);
+      }
+    };
     for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
       uint4 q[kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) q[u] = ld_stream(zp + (p + u * step) * cs);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        float f[8];
-        unpack8(q[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[0][j] += f[j];
-          acc[1][j] += f[j] * f[j];
-        }
-      }
+      for (int u = 0; u < kUnroll; ++u) one(q[u]);
     }
-    for (; p < npix; p += step) {
-      float f[8];
-      unpack8(ld_stream(zp + p * cs), f);
+    for (; p < npix; p += step) one(ld_stream(zp + p * cs));
+  }
+  float acc[2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += f[j];
-        acc[1][j] += f[j] * f[j];
-      }
-    }
+  for (int j = 0; j < 4; ++j) {
+    acc[0][2 * j] = a0[j].x, acc[0][2 * j + 1] = a0[j].y;
+    acc[1][2 * j] = a1[j].x, acc[1][2 * j + 1] = a1[j].y;
   }
   double* dst[2] = {sum, sumsq};
   block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
@@ -135,27 +197,34 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, long long
   const int lanes = blockDim.x / tpp;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   if (pl >= lanes) return;
-  float A[8], Bc[8];
+  F8 A, Bc;
+  {
+    const F8 ga = load8p(gamma + cg * 8), be = load8p(beta + cg * 8), mu = load8p(mean + cg * 8), is = load8p(invstd + cg * 8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    A[j] = gamma[c] * invstd[c];
-    Bc[j] = beta[c] - A[j] * mean[c];
+    for (int j = 0; j < 4; ++j) {
+      A.v[j] = __fmul2_rn(ga.v[j], is.v[j]);
+      Bc.v[j] = make_float2(be.v[j].x - A.v[j].x * mu.v[j].x, be.v[j].y - A.v[j].y * mu.v[j].y);
+    }
   }
+  const bool silu = act == AY2_ACT_SILU;
   const long long step = (long long)gridDim.x * lanes;
   long long p = (long long)blockIdx.x * lanes + pl;
   auto one = [&](const uint4& qz, const uint4& qr, long long pp) {
-    float f[8], r[8];
-    unpack8(qz, f);
-    if (res) unpack8(qr, r);
+    F8 f = unpack8p(qz);
+    const F8 r = unpack8p(qr);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float u = fmaf(f[j], A[j], Bc[j]);
-      if (act == AY2_ACT_SILU) u = u * sigmoid_fwd(u);
-      if (res) u += r[j];
-      f[j] = u;
+    for (int j = 0; j < 4; ++j) {
+      float2 u = __ffma2_rn(f.v[j], A.v[j], Bc.v[j]);
+      if (silu) {
+        // u * sigmoid(u), sigmoid = 1 / (1 + 2^(-u log2 e)): the 2-MUFU form (~2 ulp), see sigmoid_fwd
+        const float2 e2 = __fmul2_rn(u, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+        const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.0f, 1.0f));
+        u = __fmul2_rn(u, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+      }
+      if (res) u = __fadd2_rn(u, r.v[j]);
+      f.v[j] = u;
     }
-    *reinterpret_cast<uint4*>(y + pp * ycs + cg * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(y + pp * ycs + cg * 8) = pack8p(f);
   };
   for (; p + (kUnroll - 1) * step < npix; p += kUnroll * step) {
     uint4 qz[kUnroll], qr[kUnroll];
@@ -181,33 +250,31 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
   const int lanes = blockDim.x / tpp;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const bool active = pl < lanes;
-  float acc[2][8];
-  float is[8], ms[8], ga[8], be[8];  // xhat = z*is - ms ; u = ga*xhat + be
+  float2 a0[4], a1[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc[0][j] = acc[1][j] = 0.f;
-    const int c = cg * 8 + j;
-    is[j] = active ? invstd[c] : 0.f;
-    ms[j] = active ? mean[c] * invstd[c] : 0.f;
-    ga[j] = active ? gamma[c] : 0.f;
-    be[j] = active ? beta[c] : 0.f;
-  }
+  for (int j = 0; j < 4; ++j) a0[j] = a1[j] = make_float2(0.f, 0.f);
   if (active) {
-    auto one = [&](const uint4& qg, const uint4& qz) {
-      float g[8], f[8];
-      unpack8(qg, g);
-      unpack8(qz, f);
+    F8 is, nms, gah, beh;  // xhat = z*is + nms ; h = u/2 = gah*xhat + beh
+    {
+      const F8 ga = load8p(gamma + cg * 8), be = load8p(beta + cg * 8), mu = load8p(mean + cg * 8);
+      is = load8p(invstd + cg * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = fmaf(f[j], is[j], -ms[j]);
-        float d = g[j];
-        if (act == AY2_ACT_SILU) {
-          const float u = fmaf(ga[j], xh, be[j]);
-          const float sg = sigmoid_acc(u);
-          d *= sg * fmaf(u, 1.0f - sg, 1.0f);
-        }
-        acc[0][j] += d;
-        acc[1][j] = fmaf(d, xh, acc[1][j]);
+      for (int j = 0; j < 4; ++j) {
+        nms.v[j] = make_float2(-mu.v[j].x * is.v[j].x, -mu.v[j].y * is.v[j].y);
+        gah.v[j] = make_float2(0.5f * ga.v[j].x, 0.5f * ga.v[j].y);
+        beh.v[j] = make_float2(0.5f * be.v[j].x, 0.5f * be.v[j].y);
+      }
+    }
+    const bool silu = act == AY2_ACT_SILU;
+    auto one = [&](const uint4& qg, const uint4& qz) {
+      const F8 g = unpack8p(qg), f = unpack8p(qz);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xh = __ffma2_rn(f.v[j], is.v[j], nms.v[j]);
+        float2 d = g.v[j];
+        if (silu) d = silu_grad_times(d, __ffma2_rn(gah.v[j], xh, beh.v[j]));
+        a0[j] = __fadd2_rn(a0[j], d);
+        a1[j] = __ffma2_rn(d, xh, a1[j]);
       }
     };
     const long long step = (long long)gridDim.x * lanes;
@@ -224,6 +291,12 @@ __global__ void bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, i
     }
     for (; p < npix; p += step) one(ld_stream(dy + p * dcs + cg * 8), ld_stream(z + p * zcs + cg * 8));
   }
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    acc[0][2 * j] = a0[j].x, acc[0][2 * j + 1] = a0[j].y;
+    acc[1][2 * j] = a1[j].x, acc[1][2 * j + 1] = a1[j].y;
+  }
   double* dst[2] = {s1, s2};
   block_channel_reduce<2>(acc, tpp, lanes, cg, pl, active, sm, dst, C);
 }
@@ -239,34 +312,33 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   if (pl >= lanes) return;
   const float invn = 1.0f / (float)npix_norm;  // pixels of the WHOLE (possibly cross-rank, SyncBatchNorm) batch
-  float is[8], ms[8], ga[8], be[8], k0[8], k1[8], k2[8];  // dz = k0*dyh - k1 - xhat*k2
+  F8 is, nms, gah, beh, k0, nk1, nk2;  // dz = k0*dyh + nk1 + xhat*nk2
+  {
+    const F8 ga = load8p(gamma + cg * 8), be = load8p(beta + cg * 8), mu = load8p(mean + cg * 8);
+    is = load8p(invstd + cg * 8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    is[j] = invstd[c];
-    ms[j] = mean[c] * is[j];
-    ga[j] = gamma[c];
-    be[j] = beta[c];
-    k0[j] = ga[j] * is[j];
-    k1[j] = k0[j] * (float)s1[c] * invn;
-    k2[j] = k0[j] * (float)s2[c] * invn;
-  }
-  auto one = [&](const uint4& qg, const uint4& qz, long long pp) {
-    float g[8], f[8];
-    unpack8(qg, g);
-    unpack8(qz, f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = fmaf(f[j], is[j], -ms[j]);
-      float d = g[j];
-      if (act == AY2_ACT_SILU) {
-        const float u = fmaf(ga[j], xh, be[j]);
-        const float sg = sigmoid_acc(u);
-        d *= sg * fmaf(u, 1.0f - sg, 1.0f);
-      }
-      g[j] = fmaf(d, k0[j], -fmaf(xh, k2[j], k1[j]));
+    for (int j = 0; j < 4; ++j) {
+      const int c = cg * 8 + 2 * j;
+      nms.v[j] = make_float2(-mu.v[j].x * is.v[j].x, -mu.v[j].y * is.v[j].y);
+      gah.v[j] = make_float2(0.5f * ga.v[j].x, 0.5f * ga.v[j].y);
+      beh.v[j] = make_float2(0.5f * be.v[j].x, 0.5f * be.v[j].y);
+      k0.v[j] = __fmul2_rn(ga.v[j], is.v[j]);
+      nk1.v[j] = make_float2(-k0.v[j].x * (float)s1[c] * invn, -k0.v[j].y * (float)s1[c + 1] * invn);
+      nk2.v[j] = make_float2(-k0.v[j].x * (float)s2[c] * invn, -k0.v[j].y * (float)s2[c + 1] * invn);
     }
-    *reinterpret_cast<uint4*>(dz + pp * zdcs + cg * 8) = pack8(g);
+  }
+  const bool silu = act == AY2_ACT_SILU;
+  auto one = [&](const uint4& qg, const uint4& qz, long long pp) {
+    F8 g = unpack8p(qg);
+    const F8 f = unpack8p(qz);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 xh = __ffma2_rn(f.v[j], is.v[j], nms.v[j]);
+      float2 d = g.v[j];
+      if (silu) d = silu_grad_times(d, __ffma2_rn(gah.v[j], xh, beh.v[j]));
+      g.v[j] = __ffma2_rn(d, k0.v[j], __ffma2_rn(xh, nk2.v[j], nk1.v[j]));
+    }
+    *reinterpret_cast<uint4*>(dz + pp * zdcs + cg * 8) = pack8p(g);
   };
   const long long step = (long long)gridDim.x * lanes;
   long long p = (long long)blockIdx.x * lanes + pl;
@@ -555,6 +627,24 @@ using namespace ay2;
 #define AY2_BF(p) static_cast<__nv_bfloat16*>(p)
 #define AY2_CBF(p) static_cast<const __nv_bfloat16*>(p)
 
+// Grid of a grid-stride streaming kernel: ONE wave of resident blocks (occupancy x SMs), never more blocks than pixel
+// groups. Every block pays a prologue (per-channel constants) and, in the reducing kernels, C double-precision atomics:
+// with the former 8-16 blocks per SM the 20x20 / 40x40 layers spent more time there than streaming (26 MB in 35-65 us).
+template <typename K>
+static int wave_grid(K kernel, int threads, size_t smem, long long groups) {
+  static int per_sm = 0, sms = 0;  // one instantiation (and one cache) per kernel type/pointer
+  static const void* cached = nullptr;
+  if (cached != reinterpret_cast<const void*>(kernel)) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cached = reinterpret_cast<const void*>(kernel);
+  }
+  const long long cap = (long long)per_sm * sms;
+  return (int)(groups < 1 ? 1 : (groups < cap ? groups : cap));
+}
+
 static int red_cfg(int c, int* threads, int* lanes, size_t* smem) {
   const int tpp = c / 8;
   if (c % 8 != 0 || tpp < 1 || tpp > 256) return -1;
@@ -569,9 +659,8 @@ extern "C" int ay2_bn_stats(const void* z, int64_t npix, int32_t c, int32_t cstr
   int threads, lanes;
   size_t smem;
   AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_stats: channels=%d unsupported", c);
-  long long blocks = (npix + lanes - 1) / lanes;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_stats_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(z), npix, c, cstride, sum, sumsq);
+  const int blocks = wave_grid(bn_stats_kernel, threads, smem, (npix + lanes - 1) / lanes);
+  bn_stats_kernel<<<blocks, threads, smem, AY2_ST>>>(AY2_CBF(z), npix, c, cstride, sum, sumsq);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;
@@ -594,7 +683,7 @@ extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_
   int threads, lanes;
   size_t smem;
   AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_fwd: channels=%d unsupported", c);
-  bn_act_fwd_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(AY2_CBF(z), npix, c, z_cstride, mean, invstd, gamma,
+  bn_act_fwd_kernel<<<wave_grid(bn_act_fwd_kernel, 256, 0, (npix + lanes - 1) / lanes), 256, 0, AY2_ST>>>(AY2_CBF(z), npix, c, z_cstride, mean, invstd, gamma,
                                                                      beta, act, AY2_BF(y), y_cstride, AY2_CBF(residual),
                                                                      res_cstride);
   AY2_CHECK_LAUNCH();
@@ -610,17 +699,20 @@ static int bn_act_bwd_impl(const void* dy, int32_t dy_cstride, const void* z, in
   size_t smem;
   AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_bwd: channels=%d unsupported", c);
   if (phases & 1) {
-    AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
-    AY2_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * c, AY2_ST));
-    long long blocks = (npix + lanes - 1) / lanes;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    bn_act_bwd_reduce_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
+    if (s2 == s1 + c) {
+      AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * c, AY2_ST));
+    } else {
+      AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
+      AY2_CHECK_CUDA(cudaMemsetAsync(s2, 0, sizeof(double) * c, AY2_ST));
+    }
+    const int blocks = wave_grid(bn_act_bwd_reduce_kernel, threads, smem, (npix + lanes - 1) / lanes);
+    bn_act_bwd_reduce_kernel<<<blocks, threads, smem, AY2_ST>>>(AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, c,
                                                                     mean, invstd, gamma, beta, act, s1, s2);
     AY2_CHECK_LAUNCH();
     count_launch();
   }
   if (phases & 2) {
-    bn_act_bwd_apply_kernel<<<ew_grid((npix + lanes - 1) / lanes * 256, 256), 256, 0, AY2_ST>>>(
+    bn_act_bwd_apply_kernel<<<wave_grid(bn_act_bwd_apply_kernel, 256, 0, (npix + lanes - 1) / lanes), 256, 0, AY2_ST>>>(
         AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, npix_norm, c, mean, invstd, gamma, beta, act, s1, s2, AY2_BF(dz),
         dz_cstride);
     AY2_CHECK_LAUNCH();

@@ -21,7 +21,7 @@ for step in "$@"; do
     parity)  timeout 900 python tools/parity_report.py ${AY2_PARITY_ARGS} > gpurun_out/parity.log 2>&1; echo "parity rc=$?"; tail -30 gpurun_out/parity.log ;;
     launches) timeout 600 ncu $N --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches.csv python tools/profile_step.py 3 > gpurun_out/launches.log 2>&1; echo "launches rc=$?" ;;
     convmetrics) timeout 900 ncu $N --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed -k regex:conv_ --csv --log-file gpurun_out/conv_metrics.csv python tools/profile_step.py 3 > gpurun_out/conv_metrics.log 2>&1; echo "convmetrics rc=$?" ;;
-    prof:*)  rx="${step#prof:}"; timeout 900 ncu $N --set full --import-source on -k "regex:$rx" -c 3 -o "gpurun_out/prof_$rx" -f python tools/profile_step.py 3 > "gpurun_out/prof_$rx.log" 2>&1; echo "prof $rx rc=$?" ;;
+    prof:*)  rx="${step#prof:}"; timeout 900 ncu $N --set full --import-source on -k "regex:$rx" -c ${AY2_PROF_COUNT:-3} -o "gpurun_out/prof_$rx" -f python ${AY2_PROF_SCRIPT:-tools/profile_step.py 3} > "gpurun_out/prof_$rx.log" 2>&1; echo "prof $rx rc=$?" ;;
     py:*)    s="${step#py:}"; b=$(basename "${s%% *}" .py); timeout 1200 python $s > "gpurun_out/$b.log" 2>&1; echo "$b rc=$?"; tail -25 "gpurun_out/$b.log" | cut -c1-400 ;;
     *) echo "unknown step $step" ;;
   esac
