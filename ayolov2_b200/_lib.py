@@ -150,6 +150,7 @@ _PROTOS = {
     "ay2_channel_sum": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ay2_sgd_ema_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float,
                                    C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "ay2_repack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "ay2_sgd_ema_step_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_float,
                                           C.c_float, C.c_void_p]),

@@ -613,6 +613,40 @@ __global__ void sgd_ema_groups_kernel(float* __restrict__ p, const float* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight re-packing for the training engine: every packed bf16 operand (forward [Cout_pad][KH*KW*Cin], the flipped /
+// transposed / parity-split data-gradient weights) is a pure index permutation of its fp32 OIHW parameter, padded with
+// zeros. `ay2_repack_weights` applies ALL of them in one launch from a device table of segments
+// {src parameter, dst operand, int32 gather index per dst element (-1 = zero), first global element}: after an optimizer
+// step the ~1,000 small permute / cast / copy kernels of the per-layer refresh become one.
+// ------------------------------------------------------------------------------------------------
+struct RepackSeg {
+  const float* src;
+  __nv_bfloat16* dst;
+  const int32_t* idx;
+  long long begin;  // first element of this segment in the concatenated destination space (multiple of 8)
+};
+__global__ void repack_weights_kernel(const RepackSeg* __restrict__ segs, int nseg, long long total8) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total8; g += (long long)gridDim.x * blockDim.x) {
+    const long long e = g * 8;
+    int lo = 0, hi = nseg - 1;  // last segment whose begin <= e
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (segs[mid].begin <= e) lo = mid;
+      else hi = mid - 1;
+    }
+    const RepackSeg sg = segs[lo];
+    const long long off = e - sg.begin;
+    const int4 i0 = *reinterpret_cast<const int4*>(sg.idx + off), i1 = *reinterpret_cast<const int4*>(sg.idx + off + 4);
+    const int ix[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ix[j] >= 0 ? sg.src[ix[j]] : 0.f;
+    *reinterpret_cast<uint4*>(sg.dst + off) = pack8(v);
+  }
+}
+
 static int ew_grid(long long total, int threads) {
   long long blocks = (total + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -812,6 +846,14 @@ extern "C" int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t c
   long long blocks = (npix + lanes - 1) / lanes;
   if (blocks > 148 * 8) blocks = 148 * 8;
   channel_sum_kernel<<<(int)blocks, threads, smem, AY2_ST>>>(AY2_CBF(g), npix, c, cstride, sum);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_repack_weights(const void* segments, int32_t nseg, int64_t total, void* stream) {
+  AY2_REQUIRE(segments && nseg > 0 && total > 0 && total % 8 == 0, "ay2_repack_weights: bad arguments");
+  repack_weights_kernel<<<ew_grid(total / 8, 256), 256, 0, AY2_ST>>>(static_cast<const RepackSeg*>(segments), nseg, total / 8);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -594,28 +594,65 @@ def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):
     return specs
 
 
-def make_dgrad_weights(weight: torch.Tensor, stride: int, pad: int, dz_channels: int) -> List[torch.Tensor]:
-    """Packed bf16 weights of the dgrad launches, in the order make_dgrad_plans creates its plans."""
+def conv_weight_layout(w: torch.Tensor) -> torch.Tensor:
+    """OIHW fp32 -> the K-major operand layout [Cout_pad, KH*KW*Cin] in fp32 (pack_conv_weight without the BN fold and the
+    bf16 cast): a pure index permutation + zero padding, so applying it to an index-valued tensor yields the gather table
+    of `repack_weights`."""
+    cout, cin, kh, kw = w.shape
+    bn_tile = conv_block_n(cout)
+    cout_pad = (cout + bn_tile - 1) // bn_tile * bn_tile
+    out = torch.zeros((cout_pad, kh * kw * cin), dtype=torch.float32, device=w.device)
+    out[:cout] = w.float().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    return out
+
+
+def dgrad_weight_layouts(weight: torch.Tensor, stride: int, pad: int, dz_channels: int) -> List[torch.Tensor]:
+    """fp32 operand layouts of the dgrad launches, in the order make_dgrad_plans creates its plans (index permutations of
+    `weight`, zero padded)."""
     out = []
     for wt, *_ in _dgrad_specs(weight, stride, pad):
         if wt.shape[1] < dz_channels:
             wt = torch.cat((wt, torch.zeros((wt.shape[0], dz_channels - wt.shape[1]) + tuple(wt.shape[2:]), device=wt.device)), 1)
-        out.append(pack_conv_weight(wt, None)[0])
+        out.append(conv_weight_layout(wt))
     return out
 
 
-def make_dgrad_plans(dz: ActView, dx: ActView, weight: torch.Tensor, stride: int, pad: int, accumulate: bool) -> List[ConvPlan]:
+def make_dgrad_weights(weight: torch.Tensor, stride: int, pad: int, dz_channels: int) -> List[torch.Tensor]:
+    """Packed bf16 weights of the dgrad launches, in the order make_dgrad_plans creates its plans."""
+    return [w.to(torch.bfloat16) for w in dgrad_weight_layouts(weight, stride, pad, dz_channels)]
+
+
+def gather_index_of(layout_fn, shape, device) -> torch.Tensor:
+    """int32 gather table of a layout function (OIHW fp32 -> operand layout): out.flat[i] = weight.flat[idx[i]], -1 = zero.
+    Built by running the function on a tensor holding 1 + its own flat indices (exact in fp32 below 2^24 elements)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    assert n < (1 << 24), "weight tensor too large for the fp32 index trick"
+    probe = torch.arange(1, n + 1, dtype=torch.float32, device=device).view(*shape)
+    return (layout_fn(probe).round().to(torch.int32) - 1).contiguous()
+
+
+def repack_weights(table: torch.Tensor, nseg: int, total: int) -> None:
+    """table: int64 (nseg, 4) CUDA tensor of (src fp32 ptr, dst bf16 ptr, int32 index ptr, first element); see include/ay2.h."""
+    _lib.check(_lib.load().ay2_repack_weights(table.data_ptr(), nseg, total, _lib.current_stream_ptr()), "ay2_repack_weights")
+
+
+def make_dgrad_plans(dz: ActView, dx: ActView, weight: torch.Tensor, stride: int, pad: int, accumulate: bool,
+                     share: Optional[List["ConvPlan"]] = None) -> List[ConvPlan]:
     """Data gradient of `y = conv(x, weight, stride, pad)` as forward-conv launches of the same tcgen05 kernel:
        stride 1: dx = conv(dz, flip(W)^T, pad = k-1-p);
        stride 2: the four (row, column) parity sub-grids of dx are stride-1 convs of dz with the taps of matching
                  parity (ix = 2*ox + kw - p), written through a strided output view.
-    weight: OIHW fp32 (the forward conv's). accumulate: dx += (fan-out), implemented with the residual input."""
+    weight: OIHW fp32 (the forward conv's). accumulate: dx += (fan-out), implemented with the residual input.
+    share: plans of the other `accumulate` flavour of the same gradient, whose packed weight / bias buffers are reused."""
     cout, cin = weight.shape[0], weight.shape[1]
     assert dz.c >= cout and dx.c == cin, (dz.c, cout, dx.c, cin)
     res = dx if accumulate else None
     plans: List[ConvPlan] = []
-    packed = make_dgrad_weights(weight, stride, pad, dz.c)
-    for (wt, kh, kw, ph, pw, sub), wp in zip(_dgrad_specs(weight, stride, pad), packed):
-        bp = torch.zeros(wp.shape[0], dtype=torch.float32, device=wp.device)
+    specs = _dgrad_specs(weight, stride, pad)
+    packed = [pl.w for pl in share] if share is not None else make_dgrad_weights(weight, stride, pad, dz.c)
+    for i, ((wt, kh, kw, ph, pw, sub), wp) in enumerate(zip(specs, packed)):
+        bp = share[i].b if share is not None else torch.zeros(wp.shape[0], dtype=torch.float32, device=wp.device)
         plans.append(ConvPlan(dz, dx, wp, bp, kh, kw, 1, ph, ACT_NONE, residual=res, pad_w=pw, out_sub=sub))
     return plans

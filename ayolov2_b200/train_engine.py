@@ -45,6 +45,21 @@ class _ConvRec:
         self.stem = False
 
 
+class _GradSite:
+    """One write into a channel slice of a gradient buffer during the backward pass. The launch order of a backward is
+    static, so the first (eager) backward decides once whether this site is the FIRST writer of its slice in a step --
+    then it overwrites (no zero-fill of the buffer, no read of the old value) -- or a later one that accumulates."""
+
+    def __init__(self, eng: "TrainEngine", gv: ActView):
+        self.eng, self.key, self.lo, self.hi = eng, id(gv.buf), gv.c0, gv.c0 + gv.c
+        self.acc: Optional[bool] = None
+
+    def accumulate(self) -> bool:
+        if self.acc is None:
+            self.acc = self.eng._claim(self.key, self.lo, self.hi)
+        return self.acc
+
+
 class TrainEngine:
     def __init__(self, model: nn.Module, batch: int, height: int, width: int, in_dtype: torch.dtype = torch.float32,
                  scale: float = 1.0, device: Optional[torch.device] = None, use_graph: bool = True) -> None:
@@ -60,6 +75,12 @@ class TrainEngine:
         self.keep: List[Any] = []
         self.grad_of: Dict[int, torch.Tensor] = {}   # id(activation buffer) -> gradient buffer
         self.overwritten: set = set()                 # activation buffers whose gradient needs no zero-fill per step
+        self._cover: Dict[int, List[Tuple[int, int]]] = {}  # gradient buffer -> channel intervals written so far (first backward)
+        self._needs_zero: set = set()                 # gradient buffers with partially overlapping writers: zero-filled per step
+        self._gbuf: Dict[int, torch.Tensor] = {}      # id(gradient buffer) -> gradient buffer
+        self._repack: List[Tuple[nn.Parameter, torch.Tensor, torch.Tensor]] = []  # (fp32 parameter, packed bf16 operand, gather index)
+        self._repack_table: Optional[torch.Tensor] = None
+        self._repack_total, self._repack_ptrs = 0, None
         self._img: Optional[torch.Tensor] = None
         self.head_out: List[torch.Tensor] = []
         self.head_gin: List[torch.Tensor] = []
@@ -70,7 +91,7 @@ class TrainEngine:
         self.use_graph = use_graph
         self._gstate: Dict[str, int] = {}
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
-        self.static_in = torch.zeros((batch, 3, height, width), dtype=torch.float32, device=self.device)
+        self.static_in = torch.zeros((batch, 3, height, width), dtype=in_dtype, device=self.device)
         self._build()
         # parameter gradients: views (in model.parameters() order) of ONE flat fp32 buffer, so that a step zeroes, copies,
         # all-reduces and applies them with a handful of launches instead of one per parameter
@@ -97,7 +118,56 @@ class TrainEngine:
         if gb is None:
             gb = torch.zeros_like(v.buf)
             self.grad_of[id(v.buf)] = gb
+            self._gbuf[id(gb)] = gb
         return ActView(gb, v.c0, v.c)
+
+    def _claim(self, key: int, lo: int, hi: int) -> bool:
+        """Resolution of a _GradSite at the first backward: False = first writer of [lo, hi) (overwrite), True = accumulate."""
+        iv = self._cover.setdefault(key, [])
+        hit = sorted((a, b) for a, b in iv if a < hi and b > lo)
+        if not hit:
+            iv.append((lo, hi))
+            return False
+        pos = lo
+        for a, b in hit:
+            if a > pos:
+                break
+            pos = max(pos, b)
+        if pos < hi:  # partly fresh, partly written: accumulate onto a per-step zero-fill (never the case in the YOLOv5 graphs)
+            self._needs_zero.add(key)
+            iv.append((lo, hi))
+        return True
+
+    # ------------------------------------------------------------------------------------------------ weight re-packing
+    def _repack_add(self, param: nn.Parameter, dst: torch.Tensor, layout_fn) -> None:
+        """Register a packed bf16 operand `dst` = layout_fn(param) (an index permutation with zero padding): all of them are
+        refreshed from the current parameter values by ONE gather launch at the start of every forward."""
+        idx = ops.gather_index_of(layout_fn, tuple(param.shape), self.device)
+        assert idx.numel() == dst.numel() and dst.is_contiguous() and dst.numel() % 8 == 0, (idx.shape, dst.shape)
+        self._repack.append((param, dst, idx))
+
+    def _repack_run(self) -> None:
+        if self._repack:
+            ops.repack_weights(self._repack_table, len(self._repack), self._repack_total)
+
+    def _repack_sync_table(self) -> None:
+        """(Re)build the device segment table when a parameter's storage moved (first call; TrainStep re-points the
+        parameters into its flat buffer; `.to()` / `load_state_dict` with assign). Outside the CUDA graphs: the captured
+        gather reads the table at run time."""
+        ptrs = [p.data_ptr() for p, _, _ in self._repack]
+        if ptrs == self._repack_ptrs:
+            return
+        rows, begin = [], 0
+        for p, dst, idx in self._repack:
+            assert p.dtype == torch.float32 and p.is_contiguous()
+            rows.append((p.data_ptr(), dst.data_ptr(), idx.data_ptr(), begin))
+            begin += dst.numel()
+        host = torch.tensor(rows, dtype=torch.int64)
+        if self._repack_table is None:
+            self._repack_table = host.to(self.device)
+        else:
+            self._repack_table.copy_(host)
+        self._repack_total, self._repack_ptrs = begin, ptrs
 
     def _padd(self, p: nn.Parameter, t: torch.Tensor) -> None:
         self.pg[id(p)].add_(t.reshape(p.shape))
@@ -124,11 +194,9 @@ class TrainEngine:
         self.keep += [wp, bp, plan]
         self.flops_fwd += plan.flops
 
-        def refresh() -> None:
-            wp[:cout].copy_(conv.weight.detach().permute(0, 2, 3, 1).reshape(cout, -1))
-            if conv.bias is not None:
-                bp[:cout].copy_(conv.bias.detach())
-        self.refresh.append(refresh)
+        self._repack_add(conv.weight, wp, ops.conv_weight_layout)
+        if conv.bias is not None:
+            self.refresh.append(lambda: bp[:cout].copy_(conv.bias.detach()))
         self.fwd.append(plan.run)
         if has_bn:
             mean = torch.empty(cout, device=dev)
@@ -150,22 +218,21 @@ class TrainEngine:
         gx = self.g(x) if need_dx else None
         dw = torch.zeros((cout, k * k * cin), dtype=torch.float32, device=dev)
         dplans: List[ConvPlan] = []
+        dplans_first: List[ConvPlan] = []
+        dx_site = _GradSite(self, gx) if need_dx else None
         if need_dx:
             dplans = ops.make_dgrad_plans(gz, gx, conv.weight, s, p, accumulate=True)
-            self.keep += dplans
-            wsrc = conv.weight
-
-            def refresh_d() -> None:
-                fresh = ops.make_dgrad_weights(wsrc, s, p, gz.c)
-                for pl, wnew in zip(dplans, fresh):
-                    pl.w.copy_(wnew)
-            self.refresh.append(refresh_d)
+            dplans_first = ops.make_dgrad_plans(gz, gx, conv.weight, s, p, accumulate=False, share=dplans)
+            self.keep += dplans + dplans_first
+            for i, pl in enumerate(dplans):
+                self._repack_add(conv.weight, pl.w, lambda w, i=i: ops.dgrad_weight_layouts(w, s, p, gz.c)[i])
         gres = self.g(residual) if residual is not None else None
+        res_site = _GradSite(self, gres) if gres is not None else None
 
         def b() -> None:
             if has_bn:
                 if gres is not None:
-                    ops.add_slices(gy, gres, accumulate=True)  # shortcut branch: d(residual) += dy
+                    ops.add_slices(gy, gres, accumulate=res_site.accumulate())  # shortcut branch: d(residual) (+)= dy
                 ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz, sync=sync)
                 self._padd(bn.bias, scratch[:cout].float())
                 self._padd(bn.weight, scratch[cout:].float())
@@ -176,8 +243,9 @@ class TrainEngine:
                 bs = torch.zeros(_round_up(cout, 8), dtype=torch.float64, device=dev)
                 ops.channel_sum(ActView(gz.buf, gz.c0, _round_up(cout, 8)), bs)
                 self._padd(conv.bias, bs[:cout].float())
-            for pl in dplans:
-                pl.run()
+            if need_dx:
+                for pl in (dplans if dx_site.accumulate() else dplans_first):
+                    pl.run()
         self.bwd.append(b)
         return y
 
@@ -304,15 +372,17 @@ class TrainEngine:
         self.fwd.append(lambda: ops.sppf_pool(sl[0], sl[1], sl[2], sl[3], ks))
         out = self.kindle_conv(m.conv2, cat, y=y)
         gs = [self.g(s) for s in sl]
+        sites = [_GradSite(self, gs[2]), _GradSite(self, gs[1]), _GradSite(self, gs[0])] if cascade else \
+            [_GradSite(self, gs[0]) for _ in range(3)]
 
         def b() -> None:  # runs after conv2's backward filled d(cat)
             if cascade:  # p3 = pool(p2), p2 = pool(p1), p1 = pool(x1): route through the cascade like the reference
-                ops.maxpool_bwd(sl[2], gs[3], ks[0], gs[2], accumulate=True)
-                ops.maxpool_bwd(sl[1], gs[2], ks[0], gs[1], accumulate=True)
-                ops.maxpool_bwd(sl[0], gs[1], ks[0], gs[0], accumulate=True)
+                ops.maxpool_bwd(sl[2], gs[3], ks[0], gs[2], accumulate=sites[0].accumulate())
+                ops.maxpool_bwd(sl[1], gs[2], ks[0], gs[1], accumulate=sites[1].accumulate())
+                ops.maxpool_bwd(sl[0], gs[1], ks[0], gs[0], accumulate=sites[2].accumulate())
             else:
                 for i in (1, 2, 3):
-                    ops.maxpool_bwd(sl[0], gs[i], ks[i - 1], gs[0], accumulate=True)
+                    ops.maxpool_bwd(sl[0], gs[i], ks[i - 1], gs[0], accumulate=sites[i - 1].accumulate())
         # order: this must run BEFORE conv1's backward and AFTER conv2's: conv2's b() was appended last, so insert
         # the pool backward just before it in list order (lists are executed reversed)
         self.bwd.insert(len(self.bwd) - 1, b)
@@ -324,7 +394,8 @@ class TrainEngine:
             y = self.new_act(2 * x.H, 2 * x.W, x.c)
         self.fwd.append(lambda: ops.upsample2x(x, y))
         gy, gx = self.g(y), self.g(x)
-        self.bwd.append(lambda: ops.upsample2x_bwd(gy, gx, accumulate=True))
+        site = _GradSite(self, gx)
+        self.bwd.append(lambda: ops.upsample2x_bwd(gy, gx, accumulate=site.accumulate()))
         return y
 
     def head(self, m: nn.Module, xs: Sequence[ActView]) -> None:
@@ -364,7 +435,9 @@ class TrainEngine:
         dw = torch.zeros((cpad, cin), dtype=torch.float32, device=dev)
         wfull = torch.zeros((cpad, cin, 1, 1), device=dev)
         dplans = ops.make_dgrad_plans(gl, gx, wfull, 1, 0, accumulate=True)
-        self.keep += dplans
+        dplans_first = ops.make_dgrad_plans(gl, gx, wfull, 1, 0, accumulate=False, share=dplans)
+        dx_site = _GradSite(self, gx)
+        self.keep += dplans + dplans_first
 
         def refresh_d() -> None:
             wfull[:nch].copy_(conv.weight.detach())
@@ -379,7 +452,7 @@ class TrainEngine:
             bs = torch.zeros(cpad, dtype=torch.float64, device=dev)
             ops.channel_sum(gl, bs)
             self._padd(conv.bias, bs[:nch].float())
-            for pl in dplans:
+            for pl in (dplans if dx_site.accumulate() else dplans_first):
                 pl.run()
         self.bwd.append(b)
 
@@ -503,16 +576,22 @@ class TrainEngine:
         self._graphs[key].replay()
 
     def _forward_body(self) -> None:
+        self._repack_run()
         for r in self.refresh:
             r()
         for f in self.fwd:
             f()
 
-    def _backward_body(self) -> None:
-        for key, gb in self.grad_of.items():
-            if key not in self.overwritten:  # pre-BN gradients are written whole by bn_act_bwd, never accumulated
-                gb.zero_()
+    def _zero_grad_buffers(self) -> None:
+        # Activation-gradient buffers are allocated zeroed and every slice is overwritten by its first writer of the step
+        # (_GradSite), so only buffers whose writers overlap partially need a fill -- none in the YOLOv5 graphs; this used
+        # to be ~125 fills / 1.8 ms per step at batch 128. The flat parameter gradient accumulates and is always cleared.
+        for key in self._needs_zero:
+            self._gbuf[key].zero_()
         self.pg_flat.zero_()
+
+    def _backward_body(self) -> None:
+        self._zero_grad_buffers()
         for b in reversed(self.bwd):
             b()
 
@@ -523,6 +602,7 @@ class TrainEngine:
         self.generation = getattr(self, "generation", 0) + 1
         self.static_in.copy_(img)
         self._img = self.static_in
+        self._repack_sync_table()
         self._run_or_replay("fwd", self._forward_body)
         if getattr(self, "static_grads", False):
             # trainer mode: the loss and its backward run before the next forward (the generation guard enforces it), so
@@ -533,10 +613,7 @@ class TrainEngine:
     def _backward_chunk(self, k: int) -> None:
         b_lo, b_hi, _, _ = self.bwd_chunks[k]
         if k == 0:
-            for key, gb in self.grad_of.items():
-                if key not in self.overwritten:
-                    gb.zero_()
-            self.pg_flat.zero_()
+            self._zero_grad_buffers()
         for b in reversed(self.bwd[b_lo:b_hi]):
             b()
 
@@ -598,18 +675,20 @@ class TrainFunction(torch.autograd.Function):
         return (None, None) + grads
 
 
-def forward_train(model: nn.Module, x: torch.Tensor) -> List[torch.Tensor]:
-    """YOLOModel.forward in training mode (returns the list of (bs, na, ny, nx, no) head outputs)."""
-    if x.dtype != torch.float32:
+def forward_train(model: nn.Module, x: torch.Tensor, scale: float = 1.0) -> List[torch.Tensor]:
+    """YOLOModel.forward in training mode (returns the list of (bs, na, ny, nx, no) head outputs) on `x * scale`.
+    A uint8 batch with scale = 1/255 is the reference's `prepare_img` (abstract_trainer.py:252-261) fused into the stem's
+    space-to-depth pass: no fp32 copy of the images is ever materialised (the trainer's path)."""
+    if x.dtype not in (torch.float32, torch.uint8):
         x = x.float()
     B, _, H, W = x.shape
     cache = model.__dict__.setdefault("_train_engine_cache", {})
-    key = (B, H, W, x.device.index)
+    key = (B, H, W, x.device.index, x.dtype, float(scale))
     eng = cache.pop(key, None)
     if eng is None:
         while len(cache) >= int(model.__dict__.get("_train_engine_slots", 1)):  # multi_scale training keeps a few shapes
             cache.pop(next(iter(cache)))
-        eng = TrainEngine(model, B, H, W, device=x.device)
+        eng = TrainEngine(model, B, H, W, in_dtype=x.dtype, scale=scale, device=x.device)
         hook = model.__dict__.get("_train_engine_hook")
         if hook is not None:
             hook(eng)

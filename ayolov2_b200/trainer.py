@@ -35,6 +35,7 @@ import torch.nn.functional as F
 from . import dist_utils as du
 from . import ops
 from .loss import ComputeLoss
+from .train_engine import forward_train
 
 NOMINAL_BATCH = 64  # yolo_trainer.py:88
 
@@ -196,14 +197,18 @@ class TrainStep:
         if ni <= self.num_warmups:
             self.warmup(ni, epoch)
         imgs, labels = train_batch[0], train_batch[1]
-        imgs = self.prepare_img(imgs, self.device) if imgs.dtype == torch.uint8 else imgs.to(self.device).float()
+        fused_u8 = imgs.dtype == torch.uint8 and not self.use_multi_scale and self.model.training
+        if fused_u8:
+            imgs = imgs.to(self.device, non_blocking=True)  # / 255 happens inside the stem's space-to-depth pass
+        else:
+            imgs = self.prepare_img(imgs, self.device) if imgs.dtype == torch.uint8 else imgs.to(self.device).float()
         labels = labels.to(self.device)
         if self.use_multi_scale:
             imgs = self.multi_scale(imgs)
         boundary = ni % self.accumulate == 0
         self._exchange_now = self.world > 1 and boundary and self.accumulate == 1 and self._flat_ready and not self.skip_exchange
         self._bucket_events = []
-        pred = self.model(imgs)
+        pred = forward_train(self.model, imgs, scale=1.0 / 255.0) if fused_u8 else self.model(imgs)
         eng = self._engine()
         if not self._flat_ready:
             self._setup_flat(eng)  # first call: the engine (and the flat layout) exists now; this step exchanges unbucketed

@@ -378,6 +378,13 @@ int ay2_channel_sum(const void* g, int64_t npix, int32_t c, int32_t cstride, dou
  * inv_scale: optional device scalar multiplied into the gradient (GradScaler unscale), ema may be NULL */
 int ay2_sgd_ema_step(float* param, const float* grad, float* momentum_buf, float* ema, int64_t n, float lr, float momentum,
                      float weight_decay, int32_t nesterov, float ema_decay, const float* inv_scale, void* stream);
+/* Re-pack every bf16 convolution operand of the training engine from its fp32 parameter in ONE launch (what the reference
+ * gets for free from cuDNN reading OIHW fp32 weights directly; here the tcgen05 kernels want K-major bf16, and the data
+ * gradient wants flipped / transposed / parity-split copies). `segments`: DEVICE array of nseg records
+ *   { const float* src; bf16* dst; const int32_t* idx; int64_t begin; }   (32 bytes each, sorted by begin)
+ * dst[i] = bf16(src[idx[i]]) (idx[i] < 0: zero) for the `count` = next.begin - begin elements of each record; every begin and
+ * `total` (the end of the last record) are multiples of 8, dst and idx 16-byte aligned. */
+int ay2_repack_weights(const void* segments, int32_t nseg, int64_t total, void* stream);
 /* The same fused update with per-element parameter groups: group[i] in 0..3 selects lr4[group] / wd4[group] (HOST arrays of
  * four floats; the reference's optimizer has three groups -- BatchNorm weights, decayed weights, biases -- whose learning
  * rates differ during warm-up, scripts/train/yolo_trainer.py:149-168,194-221). grad is multiplied by grad_scale first

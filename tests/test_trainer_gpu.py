@@ -152,3 +152,27 @@ def test_multi_scale_and_bucket_plan():
     # (split-K weight gradients accumulate with fp32 atomics: run-to-run order differs, so compare in norm)
     rel = float((eng.last_grad_flat - g_bucketed).norm() / g_bucketed.norm())
     assert rel < 1e-3, rel
+
+
+def test_gradient_buffers_carry_nothing_between_steps():
+    """The activation-gradient buffers are static and never zero-filled: every slice is overwritten by its first writer of
+    the step (train_engine._GradSite). A step's gradient must therefore not depend on what earlier steps left behind --
+    compare the 4th backward of one engine (eager, captured, replayed before it, on a 10x larger input) with the first
+    backward of a fresh engine on the same batch."""
+    from ayolov2_b200 import synth
+
+    def flat_grad(model, xs):
+        model.train()
+        for x in xs:
+            model.zero_grad(set_to_none=True)
+            outs = model(x)
+            sum((o * o).sum() for o in outs).backward()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x_big = 10.0 * torch.rand(2, 3, 96, 128, device="cuda", generator=g)
+    x = torch.rand(2, 3, 96, 128, device="cuda", generator=g)
+    used = flat_grad(synth.build_model("yolov5s", seed=0).cuda(), [x_big, x_big, x_big, x])
+    fresh = flat_grad(synth.build_model("yolov5s", seed=0).cuda(), [x])
+    rel = float((used - fresh).norm() / fresh.norm())
+    assert rel < 2e-3, rel  # split-K weight gradients accumulate with fp32 atomics: run-to-run order differs
