@@ -444,16 +444,20 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, int xcs,
 }
 
 // The same, for planes that fit shared memory (the SPP/SPPF maps: 20x20 at 640 px): one block per (image, group of 8
-// channels) stages x and dy, finds every window's argmax ONCE (k*k reads instead of k^4 per output element), then
-// gathers. Identical tie rule and summation order to the kernel above.
+// channels) stages x and dy, finds every window's argmax ONCE and separably -- a row pass (first maximum of the 2r+1 row
+// neighbours) then a column pass over the row maxima (first row that holds the maximum): 2k reads instead of k*k, and the
+// same element nn.MaxPool2d picks (first maximum in row-major window order) -- and scatters dy to the winner with shared-
+// memory fp32 adds (sums of <= k*k bf16 values are exact in fp32, so the order of the adds does not matter).
 __global__ void maxpool_bwd_tile_kernel(const __nv_bfloat16* __restrict__ x, int xcs, const __nv_bfloat16* __restrict__ dy,
                                         int dcs, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, int gcs,
                                         int accumulate) {
   extern __shared__ __align__(16) uint8_t tile_sm[];
   const int HW = H * W;
-  uint4* xs = reinterpret_cast<uint4*>(tile_sm);                       // [HW] 8 channels of x
-  uint4* ds = xs + HW;                                                 // [HW] 8 channels of dy
-  unsigned short* arg = reinterpret_cast<unsigned short*>(ds + HW);    // [HW][8] flat index of the window argmax
+  uint4* xs = reinterpret_cast<uint4*>(tile_sm);                        // [HW] 8 channels of x
+  uint4* ds = xs + HW;                                                  // [HW] 8 channels of dy
+  uint4* rm = ds + HW;                                                  // [HW] 8 row maxima (bf16)
+  float* acc = reinterpret_cast<float*>(rm + HW);                       // [HW][8] gathered gradient
+  unsigned short* ra = reinterpret_cast<unsigned short*>(acc + HW * 8); // [HW][8] column of the row maximum
   const int groups = C >> 3;
   const int b = blockIdx.x / groups, cg = blockIdx.x - b * groups;
   const long long pix0 = (long long)b * HW;
@@ -461,50 +465,59 @@ __global__ void maxpool_bwd_tile_kernel(const __nv_bfloat16* __restrict__ x, int
     xs[q] = *reinterpret_cast<const uint4*>(x + (pix0 + q) * xcs + cg * 8);
     ds[q] = *reinterpret_cast<const uint4*>(dy + (pix0 + q) * dcs + cg * 8);
   }
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
   const int r = k / 2;
   const __nv_bfloat16* xe = reinterpret_cast<const __nv_bfloat16*>(xs);
   const __nv_bfloat16* de = reinterpret_cast<const __nv_bfloat16*>(ds);
-  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+  __nv_bfloat16* re = reinterpret_cast<__nv_bfloat16*>(rm);
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {  // row pass
     const int j = i & 7, q = i >> 3;
     const int qy = q / W, qx = q - qy * W;
     float best = -INFINITY;
-    int bi = 0xffff;
-    for (int wy = max(qy - r, 0); wy <= min(qy + r, H - 1); ++wy)
-      for (int wx = max(qx - r, 0); wx <= min(qx + r, W - 1); ++wx) {
-        const float v = __bfloat162float(xe[(wy * W + wx) * 8 + j]);
-        if (v > best) {
-          best = v;
-          bi = wy * W + wx;
-        }
+    int bx = 0xffff;
+    for (int wx = max(qx - r, 0); wx <= min(qx + r, W - 1); ++wx) {
+      const float v = __bfloat162float(xe[(qy * W + wx) * 8 + j]);
+      if (v > best) {
+        best = v;
+        bx = wx;
       }
-    arg[i] = static_cast<unsigned short>(bi);
+    }
+    re[i] = __float2bfloat16_rn(best);  // exact: the maximum IS one of the bf16 inputs (-inf if the row is all NaN)
+    ra[i] = static_cast<unsigned short>(bx);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {  // column pass + scatter
+    const int j = i & 7, q = i >> 3;
+    const int qy = q / W, qx = q - qy * W;
+    float best = -INFINITY;
+    int bi = -1;
+    for (int wy = max(qy - r, 0); wy <= min(qy + r, H - 1); ++wy) {
+      const int w = (wy * W + qx) * 8 + j;
+      const float v = __bfloat162float(re[w]);
+      if (v > best) {
+        best = v;
+        bi = wy * W + ra[w];
+      }
+    }
+    if (bi >= 0) atomicAdd(&acc[bi * 8 + j], __bfloat162float(de[i]));
   }
   __syncthreads();
   for (int q = threadIdx.x; q < HW; q += blockDim.x) {
-    const int py = q / W, px = q - py * W;
-    float acc[8];
+    float a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int qy = max(py - r, 0); qy <= min(py + r, H - 1); ++qy)
-      for (int qx = max(px - r, 0); qx <= min(px + r, W - 1); ++qx) {
-        const int w = qy * W + qx;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (arg[w * 8 + j] == q) acc[j] += __bfloat162float(de[w * 8 + j]);
-      }
+    for (int j = 0; j < 8; ++j) a[j] = acc[q * 8 + j];
     __nv_bfloat16* o = dx + (pix0 + q) * gcs + cg * 8;
     if (accumulate) {
       float old[8];
       unpack8(*reinterpret_cast<const uint4*>(o), old);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      for (int j = 0; j < 8; ++j) a[j] += old[j];
     }
-    *reinterpret_cast<uint4*>(o) = pack8(acc);
+    *reinterpret_cast<uint4*>(o) = pack8(a);
   }
 }
 
-// (bs, na, ny, nx, no) fp32 <-> NHWC bf16 [B, ny, nx, cstride] (channel = a*no + o): YOLOHead train layout
 // One warp per pixel: lane l handles the channel pairs (2l + 64j, 2l + 64j + 1), so that the fp32 side is touched in
 // runs of consecutive floats (one anchor's `no` values are contiguous there) and the bf16 NHWC side in 128-byte lines.
 __global__ void head_grad_to_nhwc_kernel(const float* __restrict__ g, int npix, int na, int nynx, int no,
@@ -794,7 +807,7 @@ extern "C" int ay2_maxpool_bwd(const void* x, int32_t x_cstride, const void* dy,
                                int32_t w, int32_t c, int32_t k, void* dx, int32_t dx_cstride, int32_t accumulate,
                                void* stream) {
   AY2_REQUIRE(x && dy && dx && k % 2 == 1, "ay2_maxpool_bwd: bad arguments");
-  const size_t tile_bytes = (size_t)h * w * (16 + 16 + 16);
+  const size_t tile_bytes = (size_t)h * w * (16 + 16 + 16 + 32 + 16);  // x, dy, row maxima, fp32 sums, row argmax
   if (c % 8 == 0 && x_cstride % 8 == 0 && dy_cstride % 8 == 0 && dx_cstride % 8 == 0 && h * w < 0xffff &&
       tile_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(dx) & 15) == 0) {
