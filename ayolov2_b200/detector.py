@@ -9,6 +9,7 @@ PCIe copy of batch i+1 overlaps the kernels of batch i.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -44,6 +45,8 @@ class Detector:
         self.levels = ops.make_head_levels(eng.head_logits, eng.na, eng.head_strides, eng.head_anchors_px)
         # ... and the candidates themselves are scored by the detect convolutions' epilogues, from the output tile they
         # hold in shared memory (ay2_conv_plan_set_head_candidates): the NMS kernel only sorts and suppresses
+        if os.environ.get("AY2_FUSE_CANDIDATES") is not None:  # A/B switch for measurements
+            fuse_candidates = os.environ["AY2_FUSE_CANDIDATES"] != "0"
         self.fused_candidates = fuse_candidates and not dense_pred and all(pl.desc.cout_pad <= 256 for pl in eng.head_plans)
         self._arm_candidates()
         # input / output slots of the host pipeline: with `slots` of them, slots - 1 batches can be in flight (the H2D copy

@@ -1,5 +1,5 @@
-"""Turns the raw ncu outputs of tools/gpu_prof2.sh (gpurun_out/) into the small tracked summaries under profiles/.
-Run in the build container after a profiling gpurun call:  python tools/summarize_profiles.py r01"""
+"""Turns the raw ncu outputs of `tools/gpu.sh launches convmetrics prof:<regex>` (gpurun_out/) into the small tracked summaries
+under profiles/. Run in the build container after a profiling gpurun call:  python tools/summarize_profiles.py r02"""
 import collections
 import csv
 import json
@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 os.makedirs(PROF, exist_ok=True)
 
 
@@ -52,7 +52,9 @@ if os.path.exists(p):
     print(open(os.path.join(PROF, f"{tag}_launches_step.csv")).read())
 
 # 2. per-launch metrics of the 52 conv launches of one step (DRAM traffic for roofline.traffic)
-p = os.path.join(OUT, "conv52.csv")
+p = os.path.join(OUT, "conv_metrics.csv")
+if not os.path.exists(p):
+    p = os.path.join(OUT, "conv52.csv")
 if os.path.exists(p):
     per = collections.OrderedDict()
     for r in rows_of(p):
@@ -83,10 +85,8 @@ if os.path.exists(p):
     print(json.dumps(summary, indent=1))
 
 # 3. full captures -> raw metric CSV (small) for whatever .ncu-rep files exist
-for rep in ("prof_conv3", "prof_chain", "prof_nms"):
-    rp = os.path.join(OUT, rep + ".ncu-rep")
-    if not os.path.exists(rp):
-        continue
+for rp in sorted(__import__("glob").glob(os.path.join(OUT, "prof_*.ncu-rep"))):
+    rep = re.sub(r"[^A-Za-z0-9_]+", "_", os.path.basename(rp)[:-len(".ncu-rep")]).strip("_")
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
