@@ -113,7 +113,7 @@ def yolo_head(m: nn.Module, xs: Sequence[torch.Tensor], training: bool):
         raw.append(t)
         if not training:
             yv, xv = torch.meshgrid(torch.arange(ny), torch.arange(nx), indexing="ij")
-            grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).to(t.dtype)
+            grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).to(t)  # dtype and device (GPU-run checks at full size)
             y = t.sigmoid()
             stride = float(m.stride[i])
             xy = (y[..., 0:2] * 2.0 - 0.5 + grid) * stride

@@ -89,3 +89,36 @@ def test_full_size_images_against_oracle():
            candidates_oracle=int(wo.sum()), candidates_cuda=int(go.sum()), rows_in_band=int(band.sum()),
            candidate_mismatches_outside_band=mism)
     assert mism == 0 and int(wo.sum()) > 4000
+
+
+def test_full_size_all_images_against_gpu_run_oracle():
+    """ALL 64 images of the benchmark batch at 640 x 640: the same comparison as above with the fp32 oracle executed on the
+    GPU (plain torch fp32, TF32 off) as the checker -- the CPU needs minutes for 64 images, the restatement is the same code."""
+    from copy import deepcopy
+
+    from oracle import yolo_oracle
+
+    model, imgs, _ = _setup(16, bias_only=True)
+    ref = deepcopy(model).float().cuda().eval()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    worst = {}
+    try:
+        for s in range(0, 64, 16):
+            x = (imgs[s:s + 16].float() / 255.0).cuda()
+            got_pred, got_raw = model(x)
+            with torch.no_grad():
+                want_pred, want_raw = yolo_oracle.forward(ref, x)
+            for i, (g, w) in enumerate(zip(got_raw, want_raw)):
+                e = errs(g.float(), w)
+                for k, v in e.items():
+                    worst[f"P{i + 3}_{k}"] = max(worst.get(f"P{i + 3}_{k}", 0.0), v)
+                assert e["max_norm"] < 1e-2 and e["rel_l2"] < 1e-2, (s, i, e)
+            eb = errs(got_pred[..., :4].float(), want_pred[..., :4])
+            pabs = float((got_pred[..., 4:].float() - want_pred[..., 4:]).abs().max())
+            worst["box_max_norm"] = max(worst.get("box_max_norm", 0.0), eb["max_norm"])
+            worst["prob_max_abs"] = max(worst.get("prob_max_abs", 0.0), pabs)
+            assert eb["max_norm"] < 1e-2 and pabs < 1e-2, (s, eb, pabs)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    record("fullsize_b64_gpu_run_oracle/worst_of_64", **worst)
