@@ -251,8 +251,17 @@ class TrainEngine:
 
     def kindle_conv(self, m: nn.Module, x: ActView, y: Optional[ActView] = None, residual: Optional[ActView] = None) -> ActView:
         if isinstance(m.conv, nn.Sequential):
-            raise NotImplementedError("training a Tucker-decomposed model is not implemented (the reference fine-tunes "
-                                      "decomposed models rarely; eval-mode execution is supported)")
+            # Tucker-2 chain (scripts/tensor_decomposition/decomposition.py:363-424): 1x1 -> kxk -> 1x1 plain convolutions,
+            # BatchNorm + activation after the last one. Fine-tuning runs the links as separate launches (forward, data and
+            # weight gradients each); the fused chain kernel is an eval-mode kernel.
+            convs = list(m.conv)
+            if not all(isinstance(c, nn.Conv2d) for c in convs) or any(c.out_channels % 8 for c in convs[:-1]):
+                raise NotImplementedError("training a decomposed Conv needs nn.Conv2d links whose ranks are multiples of 8 "
+                                          f"(got {[getattr(c, 'out_channels', type(c).__name__) for c in convs]})")
+            cur = x
+            for c in convs[:-1]:
+                cur = self.conv_bn_act(c, None, ACT_NONE, cur)
+            return self.conv_bn_act(convs[-1], getattr(m, "batch_norm", None), _act_code(m), cur, y, residual)
         return self.conv_bn_act(m.conv, getattr(m, "batch_norm", None), _act_code(m), x, y, residual)
 
     # ------------------------------------------------------------------------------------------------ stem

@@ -101,3 +101,35 @@ def test_chain_rejects_in_place_and_unsupported():
     assert not ops.chain_supported(d)
     d = ops.chain_desc(x, 64, 64, 0, 1, 1, 0, 64, 0, stride=2)
     assert not ops.chain_supported(d)
+
+
+def test_offline_factorisation_on_the_device_feeds_the_fused_chain():
+    """the offline tool's per-layer work (EVB rank estimate + HOOI, decomposition.py:157-424) with the weight
+    resident on the GPU -- torch.linalg on the device, the rank search batched on the host -- gives the same ranks and the
+    same chain (as a function: factor signs are not unique) as on the CPU (the decomposed model's eval-mode execution through
+    the fused chain kernel is covered by tests/test_model_gpu.py)."""
+    import torch.nn as nn
+
+    from ayolov2_b200 import decomposition as dec
+
+    torch.manual_seed(11)
+    # a Tucker-structured signal (ranks 12 out / 10 in) + noise, so that EVB truncates both modes
+    core, u, v = torch.randn(12, 10, 3, 3), torch.randn(64, 12), torch.randn(64, 10)
+    conv = nn.Conv2d(64, 64, 3, padding=1, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_(torch.einsum("abhw,oa,ib->oihw", core, u, v) / 120 ** 0.5 + 0.05 * torch.randn(64, 64, 3, 3))
+    ranks_cpu = dec.estimate_ranks(conv)
+    chain_cpu = dec.tucker_decomposition_conv_layer(conv, ranks_cpu)
+    conv_gpu = nn.Conv2d(64, 64, 3, padding=1, bias=True).cuda()
+    conv_gpu.load_state_dict(conv.state_dict())
+    ranks_gpu = dec.estimate_ranks(conv_gpu)
+    assert ranks_gpu == ranks_cpu and 0 < ranks_cpu[0] < 64 and 0 < ranks_cpu[1] < 64, (ranks_cpu, ranks_gpu)
+    chain_gpu = dec.tucker_decomposition_conv_layer(conv_gpu, ranks_gpu)
+    assert all(p.is_cuda for p in chain_gpu.parameters())
+    x = torch.randn(2, 64, 24, 24)
+    with torch.no_grad():
+        want = chain_cpu(x)
+        got = chain_gpu(x.cuda()).cpu()
+        full = conv(x)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-3
+    assert float((want - full).norm() / full.norm()) < 0.2  # the truncation keeps the signal

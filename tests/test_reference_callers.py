@@ -192,3 +192,51 @@ def test_reference_training_step_drives_the_drop_in_boundary(monkeypatch):
     acc, lrs, mom = warmup_state(5, t.num_warmups, lr_function(0, 3, HYP["lrf"]), 0.01, HYP, 2)
     assert acc == t.accumulate and abs(opt.param_groups[0]["lr"] - lrs[0]) < 1e-12
     assert abs(opt.param_groups[2]["lr"] - lrs[2]) < 1e-12 and abs(opt.param_groups[0]["momentum"] - mom) < 1e-12
+
+
+def test_every_reference_call_site_binds_to_the_product_signatures():
+    """Static half of the boundary check: EVERY call of the drop-in entry points in the reference tree -- validator, trainer,
+    KD trainer (scripts/train/kd_trainer.py:378), val.py / val2.py, TTA -- is parsed with `ast` and bound (number of
+    positional arguments + keyword names) to the signature of the product function of the same name."""
+    import ast
+    import glob
+    import os
+
+    from ayolov2_b200 import loss as ploss
+    from ayolov2_b200 import nms as pnms
+
+    targets = {
+        "non_max_suppression": inspect.signature(pnms.non_max_suppression),
+        "batched_nms": inspect.signature(pnms.batched_nms),
+        "box_iou": inspect.signature(pnms.box_iou),
+        "ComputeLoss": inspect.signature(ploss.ComputeLoss),
+    }
+    root = "/root/reference"
+    files = [f for f in glob.glob(os.path.join(root, "**", "*.py"), recursive=True) if "/tests/" not in f]
+    seen = {k: [] for k in targets}
+    for f in files:
+        try:
+            tree = ast.parse(open(f, encoding="utf-8").read())
+        except SyntaxError:
+            continue
+        defined_here = {n.name for n in ast.walk(tree) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call):
+                continue
+            name = node.func.id if isinstance(node.func, ast.Name) else (node.func.attr if isinstance(node.func, ast.Attribute) else None)
+            if name not in targets or any(isinstance(a, ast.Starred) for a in node.args) or any(k.arg is None for k in node.keywords):
+                continue
+            if isinstance(node.func, ast.Attribute) and not (isinstance(node.func.value, ast.Name) and node.func.value.id in ("nms", "metrics", "losses")):
+                continue  # torchvision.ops.boxes.batched_nms and friends: not the reference's own function
+            if name in defined_here and name == "batched_nms" and f.endswith("scripts/utils/nms.py"):
+                pass  # the definition file also calls torchvision's; those were filtered above
+            args = [object()] * len(node.args)
+            kwargs = {k.arg: object() for k in node.keywords}
+            try:
+                targets[name].bind(*args, **kwargs)
+            except TypeError as e:
+                raise AssertionError(f"{os.path.relpath(f, root)}:{node.lineno}: {name}(...) does not bind: {e}")
+            seen[name].append(f"{os.path.relpath(f, root)}:{node.lineno}")
+    assert any("kd_trainer.py" in s for s in seen["non_max_suppression"]), seen["non_max_suppression"]
+    assert any("train_utils.py" in s for s in seen["non_max_suppression"])
+    assert len(seen["ComputeLoss"]) >= 2 and len(seen["batched_nms"]) >= 1, seen

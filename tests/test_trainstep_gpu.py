@@ -219,3 +219,35 @@ def _full_size_backward(base, x, bs):
 
     record(f"train_fullsize_yolov5s_640_b{bs}/fixed_upstream_gradient", cosine=cos, rounding_noise_floor_cosine=cos0, norm_ratio=ratio)
     assert cos > cos0 and cos > 0.85 and 0.93 < ratio < 1.07, (cos, cos0, ratio, worst)
+
+
+def test_tucker_decomposed_model_trains():
+    """Fine-tuning a Tucker-2 decomposed model (decompose_model.py writes such checkpoints; the reference trains them like
+    any other): every kxk Conv is the nn.Sequential(1x1, kxk, 1x1) of decomposition.py:363-424. Backward for a fixed
+    upstream gradient vs the fp32 oracle's autograd through the same modules."""
+    from ayolov2_b200 import tucker
+    from oracle import yolo_oracle
+
+    base = _build("mini_v6")
+    replaced = tucker.decompose_model_fixed(base, ratio=0.5)
+    assert len(replaced) >= 3
+    bs, hw = 4, (128, 160)
+    x = torch.rand((bs, 3, *hw), generator=torch.Generator().manual_seed(3))
+    ref = deepcopy(base).train()
+    preds_ref = yolo_oracle.forward_with_grad(ref, x)
+    g = torch.Generator().manual_seed(7)
+    G = [torch.randn(p.shape, generator=g) / p.numel() ** 0.5 for p in preds_ref]
+    sum((p * gg).sum() for p, gg in zip(preds_ref, G)).backward()
+    m = deepcopy(base).cuda().train()
+    preds = m(x.cuda())
+    sum((p * gg.cuda()).sum() for p, gg in zip(preds, G)).backward()
+    torch.cuda.synchronize()
+    for a, b in zip(preds, preds_ref):
+        rel = float((a.detach().cpu() - b.detach()).norm() / b.detach().norm())
+        print(f"tucker mini_v6: train-mode logits rel-L2 vs fp32 oracle {rel:.4f}")
+        assert rel < 8e-2, rel
+    names = [n for n, _ in m.named_parameters()]
+    assert any(".conv.0.weight" in n for n in names) and all(p.grad is not None for p in m.parameters())
+    cos, ratio, worst = _grad_stats(m, ref)
+    print(f"tucker mini_v6: fixed-upstream gradient cosine {cos:.5f} vs the exact fp32 oracle, norm ratio {ratio:.4f}, worst {worst}")
+    assert cos > 0.9 and 0.85 < ratio < 1.15, (cos, ratio, worst)
