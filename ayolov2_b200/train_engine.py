@@ -507,10 +507,12 @@ class TrainEngine:
                 continue
             xin = [outs[s] for s in srcs]
             if name == "Conv":
-                c = m.conv
-                k_, s_, p_ = c.kernel_size[0], c.stride[0], c.padding[0]
-                oh, ow = (xin[0].H + 2 * p_ - k_) // s_ + 1, (xin[0].W + 2 * p_ - k_) // s_ + 1
-                outs[i] = self.kindle_conv(m, xin[0], y=out_view(i, oh, ow, c.out_channels))
+                links = list(m.conv) if isinstance(m.conv, nn.Sequential) else [m.conv]  # Tucker chain: the kxk link strides
+                oh, ow = xin[0].H, xin[0].W
+                for c in links:
+                    k_, s_, p_ = c.kernel_size[0], c.stride[0], c.padding[0]
+                    oh, ow = (oh + 2 * p_ - k_) // s_ + 1, (ow + 2 * p_ - k_) // s_ + 1
+                outs[i] = self.kindle_conv(m, xin[0], y=out_view(i, oh, ow, links[-1].out_channels))
             elif name == "C3":
                 outs[i] = self.c3(m, xin[0], out_view(i, xin[0].H, xin[0].W, m.conv3.conv.out_channels))
             elif name in ("SPP", "SPPF"):

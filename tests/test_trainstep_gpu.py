@@ -250,4 +250,4 @@ def test_tucker_decomposed_model_trains():
     assert any(".conv.0.weight" in n for n in names) and all(p.grad is not None for p in m.parameters())
     cos, ratio, worst = _grad_stats(m, ref)
     print(f"tucker mini_v6: fixed-upstream gradient cosine {cos:.5f} vs the exact fp32 oracle, norm ratio {ratio:.4f}, worst {worst}")
-    assert cos > 0.9 and 0.85 < ratio < 1.15, (cos, ratio, worst)
+    assert cos > 0.95 and 0.93 < ratio < 1.07, (cos, ratio, worst)  # measured: 0.977, 1.005
