@@ -746,7 +746,9 @@ struct HaloCfg {
   static constexpr int TH = 16, TW = 8;                   // one half tile
   static constexpr int HH = TH + 2;                       // halo lines
   static constexpr int X_SLOT = (HH * (2 * TW + 2) * SWA + 1023) / 1024 * 1024;  // 18 x 18 pixels x 128 B
-  static constexpr int NX = 2;
+  // input ring: a narrow-N item (the packed stem: one chunk, three taps) finishes its tile long before the next halo
+  // tile's TMA round trip completes, so two slots leave the MMA warp waiting; three fit next to the small weight stages
+  static constexpr int NX = BLOCK_N <= 64 ? 3 : 2;
   static constexpr int W_STAGE = BLOCK_N * SWA;
   static constexpr int OC = BLOCK_N < 64 ? BLOCK_N : 64;
   static constexpr int SWO = OC * 2;
@@ -756,7 +758,7 @@ struct HaloCfg {
   static constexpr int EPI_THREADS = 128 * EPI_GROUPS;
   static constexpr int THREADS = 128 + EPI_THREADS;
   static constexpr int STAGING_BYTES = EPI_GROUPS * SLAB_BYTES;
-  static constexpr int TAIL_BYTES = EPI_GROUPS * OC * 4 + 256;  // per-group bias slice + barriers + tmem ptr
+  static constexpr int TAIL_BYTES = EPI_GROUPS * OC * 4 + 320;  // per-group bias slice + barriers + tmem ptr
   static constexpr int NW_RAW = (kSmemPerSm - 2048 - NX * X_SLOT - STAGING_BYTES - TAIL_BYTES) / W_STAGE;
   static constexpr int NW = NW_RAW > 8 ? 8 : NW_RAW;
   static constexpr int SMEM_BYTES = 1024 + NX * X_SLOT + NW * W_STAGE + STAGING_BYTES + TAIL_BYTES;
@@ -764,9 +766,10 @@ struct HaloCfg {
   static_assert(NW >= 3, "not enough shared memory for the weight ring");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KW = 3>  // KW = 3: 3x3 / pad 1; KW = 1: the 3x1 window form of the packed stem (no halo columns)
 __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel(const __grid_constant__ ConvKernelParams p) {
   using Cfg = HaloCfg<BLOCK_N>;
+  constexpr int NTAPS = 3 * KW, PADW = KW == 3 ? 1 : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xring = smem;
@@ -774,23 +777,25 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
   uint8_t* staging = wring + Cfg::NW * Cfg::W_STAGE;
   float* bias_s = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);  // [EPI_GROUPS][OC]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + Cfg::EPI_GROUPS * Cfg::OC);
-  uint64_t* xfull = bars;                // [2]
-  uint64_t* xempty = bars + 2;           // [2]
-  uint64_t* wfull = bars + 4;            // [8]
-  uint64_t* wempty = bars + 12;          // [8]
-  uint64_t* tmem_full = bars + 20;       // [2]
-  uint64_t* tmem_empty = bars + 22;      // [2]
-  uint64_t* res_full = bars + 24;        // [EPI_GROUPS <= 4]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* xfull = bars;                // [NX <= 4]
+  uint64_t* xempty = bars + 4;           // [NX <= 4]
+  uint64_t* wfull = bars + 8;            // [8]
+  uint64_t* wempty = bars + 16;          // [8]
+  uint64_t* tmem_full = bars + 24;       // [2]
+  uint64_t* tmem_empty = bars + 26;      // [2]
+  uint64_t* res_full = bars + 28;        // [EPI_GROUPS <= 4]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     CV_DBG(0);
     if (p.dbg) p.dbg[(size_t)blockIdx.x * 16 + 9] = clock64();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cfg::NX; ++i) {
       mbar_init(&xfull[i], 1);
       mbar_init(&xempty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], Cfg::EPI_THREADS);
     }
@@ -857,16 +862,16 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
       int n0, b, y0, x0, nh;
       decode(item, n0, b, y0, x0, nh);
       const CUtensorMap* tmX = nh == 2 ? &p.tmA[0] : &p.tmA[1];
-      const uint32_t xbytes = Cfg::HH * (nh * Cfg::TW + 2) * Cfg::SWA;
+      const uint32_t xbytes = Cfg::HH * (nh * Cfg::TW + KW - 1) * Cfg::SWA;  // KW = 3: one halo column each side; KW = 1: none
       for (int c = 0; c < cin_chunks; ++c) {
         mbar_wait(&xempty[xs], xph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&xfull[xs], xbytes);
-          tma_load_4d(tmX, &xfull[xs], xring + xs * Cfg::X_SLOT, c * Cfg::CK, x0 - 1, y0 - 1, b);
+          tma_load_4d(tmX, &xfull[xs], xring + xs * Cfg::X_SLOT, c * Cfg::CK, x0 - PADW, y0 - 1, b);
         }
         __syncwarp();
         if (++xs == Cfg::NX) { xs = 0; xph ^= 1; }
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < NTAPS; ++tap) {
           mbar_wait(&wempty[ws], wph ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&wfull[ws], Cfg::W_STAGE);
@@ -893,13 +898,13 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
       mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
       tcgen05_fence_after();
       const uint32_t d0 = tmem_base + acc * 2 * BLOCK_N;
-      const int hw = nh * Cfg::TW + 2;                       // halo line in pixels == rows
+      const int hw = nh * Cfg::TW + KW - 1;                  // halo line in pixels == rows
       const uint32_t a_hi0 = (static_cast<uint32_t>(hw * Cfg::SWA) >> 4) | (1u << 14) | (2u << 29);
       for (int c = 0; c < cin_chunks; ++c) {
         mbar_wait(&xfull[xs], xph);
         const uint32_t a_slot = x_lo0 + xs * (Cfg::X_SLOT >> 4);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - ky * 3;
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const int ky = tap / KW, kx = tap - ky * KW;
           mbar_wait(&wfull[ws], wph);
           tcgen05_fence_after();
           if (c == 0 && tap == 0 && it == 0 && lane == 0) CV_DBG(2);
@@ -917,8 +922,8 @@ __global__ void __launch_bounds__(HaloCfg<BLOCK_N>::THREADS, 1) conv_halo_kernel
               }
             }
             umma_commit(&wempty[ws]);
-            if (tap == 8) umma_commit(&xempty[xs]);
-            if (tap == 8 && c == cin_chunks - 1) umma_commit(&tmem_full[acc]);
+            if (tap == NTAPS - 1) umma_commit(&xempty[xs]);
+            if (tap == NTAPS - 1 && c == cin_chunks - 1) umma_commit(&tmem_full[acc]);
           }
           __syncwarp();
           if (++ws == Cfg::NW) { ws = 0; wph ^= 1; }
@@ -1165,8 +1170,10 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
     // the MMA rows on this feature-map size, e.g. 20 x 20)
     static const int env_halo = getenv("AY2_CONV_HALO") ? atoi(getenv("AY2_CONV_HALO")) : 1;
     const int bands = ceil_div(d->out_h, 16), halves = ceil_div(d->out_w, 8);
-    const bool shape_ok = !d->x3 && d->kh == 3 && d->kw == 3 && d->stride == 1 && d->pad == 1 && pad_w == 1 && d->cin % 64 == 0 &&
-                          split == 0 && d->in_pix_stride <= 0 && d->in_row_pixels <= 0 && d->out_pix_stride <= 0 &&
+    // (3x3 with pad 1, or the 3x1 window form of the packed stem: kw = 1, pad_w = 0, custom input pixel / row strides)
+    const bool shape_ok = !d->x3 && d->kh == 3 && ((d->kw == 3 && pad_w == 1 && d->in_pix_stride <= 0 && d->in_row_pixels <= 0) ||
+                                                   (d->kw == 1 && pad_w == 0)) &&
+                          d->stride == 1 && d->pad == 1 && d->cin % 64 == 0 && split == 0 && d->out_pix_stride <= 0 &&
                           d->out_row_pixels <= 0;
     const bool fill_ok = (double)bands * 16 * halves * 8 <= 1.3 * d->out_h * d->out_w;
     if (env_halo && shape_ok && (fill_ok || env_halo == 2)) {
@@ -1185,21 +1192,29 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
       kp.has_res = d->res_cstride != 0;
       kp.bias = bias;
       kp.csize = 1;
-      const int64_t cs = d->in_cstride, os = d->out_cstride, rs = d->res_cstride;
+      kp.kw = d->kw;
+      kp.pad_w = pad_w;
+      const int64_t os = d->out_cstride, rs = d->res_cstride;
       const int W = d->in_w, H = d->in_h;
       const int oc = nt < 64 ? nt : 64;
-      int rc = encode_act_map(&kp.tmA[0], in, d->cin, W, H, d->batch, cs, cs * W, cs * W * H, 64, 18, 18);
-      if (rc == AY2_OK) rc = encode_act_map(&kp.tmA[1], in, d->cin, W, H, d->batch, cs, cs * W, cs * W * H, 64, 10, 18);
-      if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, 9 * d->cin, d->cout_pad, 64, nt);
+      const int xw = d->kw - 1;  // halo columns
+      int rc = encode_act_map(&kp.tmA[0], in, d->cin, W, H, d->batch, pix_stride, pix_stride * row_pixels,
+                              pix_stride * row_pixels * H, 64, 16 + xw, 18);
+      if (rc == AY2_OK)
+        rc = encode_act_map(&kp.tmA[1], in, d->cin, W, H, d->batch, pix_stride, pix_stride * row_pixels,
+                            pix_stride * row_pixels * H, 64, 8 + xw, 18);
+      if (rc == AY2_OK) rc = encode_weight_map(&kp.tmB, weight, 3 * d->kw * d->cin, d->cout_pad, 64, nt);
       if (rc == AY2_OK) rc = encode_act_map(&kp.tmOut, out, d->cout, W, H, d->batch, os, os * W, os * W * H, oc, 8, 16);
       if (rc == AY2_OK && kp.has_res) rc = encode_act_map(&kp.tmRes, residual, d->cout, W, H, d->batch, rs, rs * W, rs * W * H, oc, 8, 16);
       if (rc != AY2_OK) {
         delete pl;
         return rc;
       }
-      if (nt == 32) pl->kernel = conv_halo_kernel<32>, pl->smem = HaloCfg<32>::SMEM_BYTES, pl->threads = HaloCfg<32>::THREADS;
-      else if (nt == 64) pl->kernel = conv_halo_kernel<64>, pl->smem = HaloCfg<64>::SMEM_BYTES, pl->threads = HaloCfg<64>::THREADS;
-      else pl->kernel = conv_halo_kernel<128>, pl->smem = HaloCfg<128>::SMEM_BYTES, pl->threads = HaloCfg<128>::THREADS;
+      if (nt == 32) pl->smem = HaloCfg<32>::SMEM_BYTES, pl->threads = HaloCfg<32>::THREADS;
+      else if (nt == 64) pl->smem = HaloCfg<64>::SMEM_BYTES, pl->threads = HaloCfg<64>::THREADS;
+      else pl->smem = HaloCfg<128>::SMEM_BYTES, pl->threads = HaloCfg<128>::THREADS;
+      if (d->kw == 3) pl->kernel = nt == 32 ? conv_halo_kernel<32, 3> : (nt == 64 ? conv_halo_kernel<64, 3> : conv_halo_kernel<128, 3>);
+      else pl->kernel = nt == 32 ? conv_halo_kernel<32, 1> : (nt == 64 ? conv_halo_kernel<64, 1> : conv_halo_kernel<128, 1>);
       pl->ctas_per_sm = 1;
       pl->halo = 1;
       cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem);

@@ -142,13 +142,15 @@ def test_conv_inplace_residual():
     assert torch.equal(buf[..., C_:], before[..., C_:])
 
 
-def test_conv_window_mode_packed_stem():
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 32, 48, 32), (2, 24, 40, 32), (1, 20, 20, 64), (3, 40, 72, 64)])
+def test_conv_window_mode_packed_stem(B, H, W, Cout):
     """16-channel 3x3 conv run as 3x1 taps over overlapping 4-pixel windows (in_pix_stride 16 < cin 64) of a
-    horizontally padded buffer == plain 3x3 conv of the 16-channel tensor."""
+    horizontally padded buffer == plain 3x3 conv of the 16-channel tensor. Since round 2 this form runs in the halo kernel
+    (one 18-line tile per item, the three vertical taps are shifted descriptors): full tiles, a one-half right edge (W = 40,
+    72), partial bands (H = 24, 40) and a map the halo tiles fill badly (20 x 20: generic kernel)."""
     from ayolov2_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(4)
-    B, H, W, Cout = 2, 32, 48, 32
     Wp = W + 8
     buf = torch.zeros((B, H, Wp, 16), device="cuda", dtype=torch.bfloat16)
     x = torch.randn((B, H, W, 16), device="cuda", generator=g).to(torch.bfloat16)
