@@ -1029,10 +1029,12 @@ int encode_act_map(CUtensorMap* tm, const void* base, int C, int W, int H, int B
                           int64_t sB, int boxc, int bw, int bh) {
   // L2 promotion: fetch 256 B only when a pixel's channels are one dense run of >= 256 B that this conv consumes
   // entirely; a channel slice of a wider concat buffer would otherwise drag its neighbour's bytes through HBM.
+  // (a pixel pitch that is not a multiple of 128 B -- the 3-slice C3 buffer at c_ = 32: 192 B -- puts every other row
+  // across two 128-byte lines: promote 64 B there, or the neighbouring slice's bytes come along)
   const bool dense = (int64_t)C == sW && C * 2 >= 256;
   const CUtensorMapL2promotion promo = dense ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                             : (boxc * 2 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
+                                             : (boxc * 2 >= 128 && (sW * 2) % 128 == 0 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                                       : CU_TENSOR_MAP_L2_PROMOTION_L2_64B);
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
