@@ -507,9 +507,15 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
         const int mg = item / p.num_n_tiles;
         const int m = mg * p.csize + crank;
         const int n0 = (item - mg * p.num_n_tiles) * BLOCK_N;
+        // Box origins of the tile, warp-uniform (uniform registers feed the TMA instructions directly). A tile of ONE box
+        // (8 x 16 pixels: every map of 80 x 80 and above) takes the short path: two divisions per tile and one copy per
+        // stage instead of sixteen divisions and an eight-way predicated sequence -- for the K = 32 / one-chunk stages of
+        // the early layers that sequence was the longest chain in the kernel.
+        const bool one_box = p.NB == 1;
         int bx[8], by[8], bb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          if (j > 0 && one_box) break;
           const int q = m * p.NB + j;
           const int b = q / p.boxes_per_img;
           const int r = q - b * p.boxes_per_img;
@@ -544,27 +550,34 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
                 if constexpr (PAIR) {
                   // both CTAs' copies complete on the LEADER's barrier, which expects the bytes of the two stages
                   if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                  if (one_box) {
+                    tma_load_4d_pair(tmA, &full_bar[stage], sa, ccoord, bx[0] + dx, by[0] + dy, bb[0]);
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    if (j < p.NB)
-                      tma_load_4d_pair(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx, by[j] + dy, bb[j]);
+                    for (int j = 0; j < 8; ++j) {
+                      if (j < p.NB)
+                        tma_load_4d_pair(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx, by[j] + dy, bb[j]);
+                    }
                   }
                   tma_load_2d_pair(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0 + crank * (BLOCK_N / 2));
                 } else {
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                  mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                  if (one_box) {
+                    tma_load_4d(tmA, &full_bar[stage], sa, ccoord, bx[0] + dx, by[0] + dy, bb[0]);
+                  } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (j < p.NB)
-                    tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx,
-                                by[j] + dy, bb[j]);
-                }
-                if (p.csize > 1) {
-                  constexpr int HALF_ROWS = BLOCK_N / 2;
-                  tma_load_2d_mc(&p.tmB, &full_bar[stage], sb + crank * HALF_ROWS * Cfg::SWA, kbase + cc * CK,
-                                 n0 + crank * HALF_ROWS, cmask);
-                } else {
-                  tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
-                }
+                    for (int j = 0; j < 8; ++j) {
+                      if (j < p.NB)
+                        tma_load_4d(tmA, &full_bar[stage], sa + j * box_rows * Cfg::SWA, ccoord, bx[j] + dx, by[j] + dy, bb[j]);
+                    }
+                  }
+                  if (p.csize > 1) {
+                    constexpr int HALF_ROWS = BLOCK_N / 2;
+                    tma_load_2d_mc(&p.tmB, &full_bar[stage], sb + crank * HALF_ROWS * Cfg::SWA, kbase + cc * CK,
+                                   n0 + crank * HALF_ROWS, cmask);
+                  } else {
+                    tma_load_2d(&p.tmB, &full_bar[stage], sb, kbase + cc * CK, n0);
+                  }
                 }
               }
               __syncwarp();
