@@ -156,11 +156,10 @@ __device__ __forceinline__ void head_cand_push(const HeadCandParams& h, bool ok,
 // (3) The tile's keys are appended with one global atomicAdd per warp and image (single-label; multi_label appends per
 // class step): one atomic per ROW would serialise in L2 on the image's counter.
 template <class Cfg>
-__device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int m, int et, int egrp,
-                                                int lane, int eall, unsigned short* list, int* cnt,
+__device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const uint8_t* staging, int3 epix, const int* box_s,
+                                                int et, int egrp, int lane, int eall, unsigned short* list, int* cnt,
                                                 unsigned long long* keys_s, short* img_s) {
   const HeadCandParams& h = p.hc;
-  const int box_rows = p.BH * p.BW;
   const int plane = h.out_h * h.out_w;
   const int nc = h.no - 5;
   auto logit = [&](int px, int ch) -> float {  // channel ch of pixel px in the swizzled staging slabs
@@ -169,17 +168,9 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
     return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(slab + swizzled_offset<Cfg::SWO>(px, cc >> 3) + (cc & 7) * 2));
   };
   // ---- phase 1: objectness test, list of passing (pixel, anchor) pairs with their (image, row)
-  int b0, oy0, ox0;
-  {
-    const int j = et / box_rows, rr = et - j * box_rows;
-    const int q = m * p.NB + j;
-    b0 = q / p.boxes_per_img;
-    const int r = q - b0 * p.boxes_per_img;
-    const int py = r / p.boxes_x;
-    const int ry = rr / p.BW;
-    oy0 = py * p.BH + ry;
-    ox0 = (r - py * p.boxes_x) * p.BW + (rr - ry * p.BW);
-  }
+  // (image, origin) of this thread's box come from the group-0 leader's per-tile index arithmetic (box_s); the thread's
+  // place inside its box (epix = box, row, column) does not change from tile to tile: no divisions here
+  const int b0 = box_s[epix.x * 3], oy0 = box_s[epix.x * 3 + 1] + epix.y, ox0 = box_s[epix.x * 3 + 2] + epix.z;
   const bool inside = b0 < h.batch && oy0 < h.out_h && ox0 < h.out_w;
   for (int a = egrp; a < h.na; a += Cfg::EPI_GROUPS) {
     const bool pass = inside && head_sigmoid(logit(et, a * h.no + 4)) > h.conf_thres;
@@ -439,6 +430,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
   unsigned short* cand_list = reinterpret_cast<unsigned short*>(bars) + 128;           // 256 B past the barriers: 128 x 3 entries
   unsigned long long* cand_keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [384]
   short* cand_img = reinterpret_cast<short*>(reinterpret_cast<uint8_t*>(bars) + 1024 + 3072);                      // [384]
+  int* cand_box = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 1024 + 3072 + 768);                     // [8][3] image, y, x of the tile's boxes
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -642,6 +634,10 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
     int it = 0;
     uint32_t res_phase = 0;
     const bool leader = ewarp == 0;  // first warp of the group: lanes < NB own one box each (residual load, store, bulk group)
+    int3 epix;                       // this thread's accumulator row inside the tile: (box, row in box, column in box)
+    epix.x = et / box_rows;
+    epix.y = (et - epix.x * box_rows) / p.BW;
+    epix.z = et - epix.x * box_rows - epix.y * p.BW;
     uint8_t* slab = staging + egrp * Cfg::SLAB_BYTES;
     const int gbar = 2 + egrp;       // named barrier of this group
     // one N tile: the bias slice never changes -> staged once
@@ -667,6 +663,11 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
           const int py = r / p.boxes_x;
           cy = py * p.BH;
           cx = (r - py * p.boxes_x) * p.BW;
+        }
+        if (p.hc.keys && egrp == 0 && lane < 8) {  // for the candidate epilogue below (read after an all-group barrier)
+          cand_box[lane * 3] = cb;
+          cand_box[lane * 3 + 1] = cy;
+          cand_box[lane * 3 + 2] = cx;
         }
         tma_store_wait_read<0>();  // the previous tile's store of this slab has finished reading it
         if (p.has_res) {
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
         // only read); no group may start rewriting its slab before every group has finished reading
         named_bar_sync(1, Cfg::EPI_THREADS);
         if (eall == 0) cand_cnt[(it + 1) & 1] = 0;  // the other counter was last read before the barrier above
-        head_candidates<Cfg>(p, staging, m, et, egrp, lane, eall, cand_list, &cand_cnt[it & 1], cand_keys, cand_img);
+        head_candidates<Cfg>(p, staging, epix, cand_box, et, egrp, lane, eall, cand_list, &cand_cnt[it & 1], cand_keys, cand_img);
         named_bar_sync(1, Cfg::EPI_THREADS);
       }
     }
