@@ -242,10 +242,15 @@ __global__ void __launch_bounds__(256, 1) conv_wgrad_kernel(const __grid_constan
           tmem_ld_32x32b_x32(taddr + t * N_T + cc, v);
           tmem_ld_wait();
           if (n < p.cout) {
+            // 16-byte vector reductions (red.global.add.v4.f32): a thread owns 32 consecutive floats of ITS filter row, so
+            // the lanes of a warp never share a sector -- four floats per L2 operation instead of one (cin % 8 == 0)
             float* dst = p.dw + ((size_t)n * taps + t) * p.cin + c0 + cc;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c0 + cc + i < p.cin) atomicAdd(dst + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; i += 4)
+              if (c0 + cc + i < p.cin)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(v[i])),
+                             "f"(__uint_as_float(v[i + 1])), "f"(__uint_as_float(v[i + 2])), "f"(__uint_as_float(v[i + 3]))
+                             : "memory");
           }
         }
       }
