@@ -312,19 +312,28 @@ class TrainEngine:
         if y is None:
             y = self.new_act(H2, W2, cout)
         z = self.new_act(H2, W2, cout)
-        bn_tile = ops.conv_block_n(cout)
-        wp = torch.zeros((_round_up(cout, bn_tile), 3 * 64), dtype=torch.bfloat16, device=dev)
-        bp = torch.zeros(_round_up(cout, bn_tile), dtype=torch.float32, device=dev)
-        plan = ConvPlan(s2d, z, wp, bp, 3, 1, 1, 1, ACT_NONE, pad_w=0, window=(64, W2, 16, Wp))
+        # pair form (engine.Builder.stem): two horizontally adjacent output pixels share one 4-pixel window, M = pixel pairs,
+        # N = 2 * cout -- the window tile is fetched once per pair and the MMA is twice as wide
+        pair = z.c0 == 0 and z.cstride == cout and W2 % 2 == 0 and Wp % 2 == 0 and 2 * cout <= 256
+        npx = 2 if pair else 1
+        bn_tile = ops.conv_block_n(npx * cout)
+        wp = torch.zeros((_round_up(npx * cout, bn_tile), 3 * 64), dtype=torch.bfloat16, device=dev)
+        bp = torch.zeros(_round_up(npx * cout, bn_tile), dtype=torch.float32, device=dev)
+        if pair:
+            z2 = ActView(z.buf.view(self.B, H2, W2 // 2, 2 * cout), 0, 2 * cout)
+            plan = ConvPlan(s2d, z2, wp, bp, 3, 1, 1, 1, ACT_NONE, pad_w=0, window=(64, W2 // 2, 32, Wp // 2))
+        else:
+            plan = ConvPlan(s2d, z, wp, bp, 3, 1, 1, 1, ACT_NONE, pad_w=0, window=(64, W2, 16, Wp))
         self.keep += [wp, bp, plan]
         self.flops_fwd += 2.0 * self.B * H2 * W2 * cout * 108
 
         def refresh() -> None:
             w2 = to_s2d_weight(c.weight.detach().float())
-            ww = torch.zeros((cout, 3, 64), device=dev)  # [cout][kh][kwp*16 + ch]
-            for kwp in range(3):
-                ww[:, :, kwp * 16:kwp * 16 + 12] = w2[:, :, :, kwp].permute(0, 2, 1)
-            wp[:cout].copy_(ww.reshape(cout, -1))
+            ww = torch.zeros((npx * cout, 3, 64), device=dev)  # [pixel of the pair * cout + o][kh][window pixel * 16 + ch]
+            for px in range(npx):
+                for kwp in range(3):
+                    ww[px * cout:(px + 1) * cout, :, (kwp + px) * 16:(kwp + px) * 16 + 12] = w2[:, :, :, kwp].permute(0, 2, 1)
+            wp[:npx * cout].copy_(ww.reshape(npx * cout, -1))
         self.refresh.append(refresh)
         self.fwd.append(plan.run)
         mean, invstd = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
