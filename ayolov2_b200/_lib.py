@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
         ("cout_pad", C.c_int32), ("pad_w", C.c_int32),
         ("in_pix_stride", C.c_int32), ("in_row_pixels", C.c_int32),
         ("out_pix_stride", C.c_int32), ("out_row_pixels", C.c_int32),
-        ("cin_split", C.c_int32), ("in2_cstride", C.c_int32), ("x3", C.c_int32),
+        ("cin_split", C.c_int32), ("in2_cstride", C.c_int32), ("x3", C.c_int32), ("stride_w", C.c_int32),
         ("in2", C.c_void_p),
     ]
 

@@ -37,7 +37,7 @@ struct ConvKernelParams {
   int num_m_tiles, num_n_tiles;
   int boxes_x, boxes_per_img;
   int BH, BW, NB;
-  int kh, kw, stride, pad, pad_w;
+  int kh, kw, stride, pad, pad_w, stride_w;
   int cin_chunks;  // Cin / CK
   int cin;         // K extent per tap in the packed weights
   int split_chunks;  // > 0: channel chunks >= split_chunks come from the second input view tmA[3] (stride-1 convs only):
@@ -525,9 +525,9 @@ __global__ void __launch_bounds__(ConvCfg<BLOCK_N, CK, X3, PAIR>::THREADS, ConvC
               dx = kw - p.pad_w;
             } else {
               const int uy = kh - p.pad, ux = kw - p.pad_w;
-              const int ph = uy & 1, pw = ux & 1;
+              const int ph = uy & 1, pw = p.stride_w == 1 ? 0 : (ux & 1);  // stride_w 1: row-parity views only
               dy = (uy - ph) >> 1;
-              dx = (ux - pw) >> 1;
+              dx = p.stride_w == 1 ? ux : ((ux - pw) >> 1);
               view = ph * 2 + pw;
             }
             const int kbase = (kh * p.kw + kw) * p.cin;
@@ -1158,12 +1158,15 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   const int64_t row_pixels = d->in_row_pixels > 0 ? d->in_row_pixels : d->in_w;
   AY2_REQUIRE(pix_stride % 8 == 0, "in_pix_stride must be a multiple of 8 elements");
   AY2_REQUIRE(d->stride == 1 || (d->in_pix_stride <= 0 && d->in_row_pixels <= 0), "custom input strides need stride 1");
+  const int stride_w = d->stride_w > 0 ? d->stride_w : d->stride;
+  AY2_REQUIRE(stride_w == d->stride || (d->stride == 2 && stride_w == 1 && d->kw == 2 && pad_w == 1 && !d->x3 && d->cin_split == 0),
+              "stride_w != stride is built for the pixel-pair form only (stride 2, stride_w 1, kw 2, pad_w 1)");
   const int exp_oh = (d->in_h + 2 * d->pad - d->kh) / d->stride + 1;
-  const int exp_ow = (d->in_w + 2 * pad_w - d->kw) / d->stride + 1;
+  const int exp_ow = stride_w != d->stride ? d->in_w : (d->in_w + 2 * pad_w - d->kw) / d->stride + 1;  // pair form: left pad only
   // (sub-grid outputs are the dgrad of a strided conv: asymmetric implicit padding, the caller fixes the size)
   AY2_REQUIRE(d->out_pix_stride > 0 || (exp_oh == d->out_h && exp_ow == d->out_w),
               "conv output size %dx%d does not match %dx%d", d->out_h, d->out_w, exp_oh, exp_ow);
-  if (d->stride == 2) AY2_REQUIRE(d->in_h % 2 == 0 && d->in_w % 2 == 0, "stride-2 conv needs even input size");
+  if (d->stride == 2) AY2_REQUIRE(d->in_h % 2 == 0 && (stride_w == 1 || d->in_w % 2 == 0), "stride-2 conv needs even input size");
   const int bn = ay2_conv_block_n(d->cout);
   AY2_REQUIRE(d->cout_pad >= d->cout && d->cout_pad % bn == 0, "cout_pad=%d must be a multiple of %d", d->cout_pad, bn);
   AY2_REQUIRE(d->res_cstride == 0 || residual, "residual stride given without a residual pointer");
@@ -1268,6 +1271,7 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
   kp.stride = d->stride;
   kp.pad = d->pad;
   kp.pad_w = pad_w;
+  kp.stride_w = stride_w;
   kp.cin = d->cin;
   kp.cin_chunks = d->cin / ck;
   kp.split_chunks = split / ck;
@@ -1285,6 +1289,12 @@ extern "C" int ay2_conv_plan_create(const ay2_conv_desc* d, const void* in, cons
     if (rc == AY2_OK && split)
       rc = encode_act_map(&kp.tmA[3], d->in2, d->cin - split, d->in_w, d->in_h, d->batch, d->in2_cstride,
                           (int64_t)d->in2_cstride * d->in_w, (int64_t)d->in2_cstride * d->in_w * d->in_h, ck, bw, bh);
+  } else if (stride_w == 1) {
+    for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph) {  // row-parity views: every column, every other row
+      const uint8_t* base = static_cast<const uint8_t*>(in) + (int64_t)ph * d->in_w * cs * 2;
+      rc = encode_act_map(&kp.tmA[ph * 2], base, d->cin, d->in_w, d->in_h / 2, d->batch, cs, 2 * cs * d->in_w,
+                          cs * d->in_w * d->in_h, ck, bw, bh);
+    }
   } else {
     for (int ph = 0; ph < 2 && rc == AY2_OK; ++ph)
       for (int pw = 0; pw < 2 && rc == AY2_OK; ++pw) {

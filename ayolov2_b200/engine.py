@@ -111,6 +111,24 @@ class Builder:
                       torch.cat((mu, torch.zeros(padn, device=self.device))), torch.cat((var, torch.ones(padn, device=self.device))))
             if bias is not None:
                 bias = torch.cat((bias, torch.zeros(y.c - cout, device=self.device)))
+        if (self.PIXEL_PAIRS and not self.x3 and (kh, kw, stride, pad) == (3, 3, 2, 1) and xc == 32 and x2 is None and residual is None
+                and x.c0 == 0 and x.cstride == 32 and x.W % 2 == 0 and x.H % 2 == 0):
+            # 3x3 / stride 2 over 32 channels (the layer after the stem): 64-byte operand rows, nine taps of K = 32. Read PAIRS
+            # of pixels as 64-channel rows instead -- the same buffer viewed as [B, H, W/2, 64] -- with a 3x2-tap kernel:
+            # pair ox-1 carries column 2ox-1 in its upper 32 channels (kw = 0), pair ox carries columns 2ox, 2ox+1 (kw = 1, 2).
+            # Stride 2 over rows only: 128-byte rows, six taps (one weight block of zeros).
+            w2 = torch.zeros((w.shape[0], 64, 3, 2), device=self.device)
+            w2[:, 32:, :, 0] = w[:, :, :, 0]
+            w2[:, :32, :, 1] = w[:, :, :, 1]
+            w2[:, 32:, :, 1] = w[:, :, :, 2]
+            wp, bp = ops.pack_conv_weight(w2, bias, bn, eps)
+            xp = ActView(x.buf.view(x.B, x.H, x.W // 2, 64), 0, 64)
+            plan = ConvPlan(xp, y, wp, bp, 3, 2, 2, 1, act, pad_w=1, stride_w=1)
+            self.plans.append(plan)
+            self.steps.append(plan.run)
+            self.flops += 2.0 * self.B * y.H * y.W * cout * kh * kw * cin
+            self.act_bytes += 2.0 * self.B * (x.H * x.W * cin + y.H * y.W * cout)
+            return
         if self.x3:
             segs = self.segments_of(x)
             if x2 is not None:
@@ -128,6 +146,7 @@ class Builder:
     # ---------------------------------------------------------------------------------------------
     # fused chains (csrc/conv_chain.cu): 1x1 -> 3x3 (-> 1x1) in one launch
     FUSE_CHAINS = True      # class-level switch (tests / A-B measurements)
+    PIXEL_PAIRS = os.environ.get("AY2_PIXEL_PAIRS", "1") != "0"  # 3x3/s2 over 32 channels as a 3x2-tap conv over pixel pairs
     # Bottlenecks wider than this stay two launches: measured on B200 (r01, bs 64): c = 32 @160x160 fused 0.165 ms vs
     # 0.240 ms, c = 64 @80x80 0.097 vs 0.084 ms, c = 128 @40x40 0.105 vs 0.066 ms (the serialised stages of the fused
     # kernel lose to two pipelined launches once the 3x3 is tensor-bound). Tucker chains are always fused when supported.

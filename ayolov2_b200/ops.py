@@ -138,12 +138,13 @@ class ConvPlan:
     def __init__(self, x: ActView, y: ActView, w_packed: torch.Tensor, bias: torch.Tensor, kh: int, kw: int,
                  stride: int, pad: int, act: int, residual: Optional[ActView] = None, pad_w: int = -1,
                  window: Optional[Tuple[int, int, int, int]] = None, out_sub: Optional[Tuple[int, int]] = None,
-                 x2: Optional[ActView] = None):
+                 x2: Optional[ActView] = None, stride_w: int = 0):
         """`window` = (cin, in_w, pix_stride, row_pixels): read `x.buf` as overlapping windows of `cin` channels
         starting at every physical pixel (the packed 16-channel stem); otherwise the input is the ActView `x`.
         `out_sub` = (py, px): write (and read the residual from) the (row, column) parity sub-grid of `y` -- the
         output is then y.H/2 x y.W/2 pixels (data gradient of a stride-2 convolution).
-        `x2`: second input view; the conv consumes torch.cat([x, x2], channel) without the concatenation existing."""
+        `x2`: second input view; the conv consumes torch.cat([x, x2], channel) without the concatenation existing.
+        `stride_w`: horizontal stride when it differs from `stride` (the pixel-pair form: stride 2 over rows, 1 over pairs)."""
         lib = _lib.load()
         cout_pad, ktot = w_packed.shape
         cin = window[0] if window else x.pc + (x2.pc if x2 is not None else 0)
@@ -174,6 +175,7 @@ class ConvPlan:
                 assert (residual.H, residual.W) == (y.H, y.W)
                 r_ptr += 2 * (py * residual.W + px) * residual.cstride
         d.kh, d.kw, d.stride, d.pad, d.act = kh, kw, stride, pad, act
+        d.stride_w = stride_w
         d.res_cstride = residual.cstride if residual is not None else 0
         d.cout_pad = cout_pad
         d.x3 = int(x3)

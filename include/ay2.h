@@ -84,6 +84,10 @@ typedef struct ay2_conv_desc {
                              loop is unchanged; the epilogue applies the exact SiLU, splits, and writes the three planes of
                              `cout` channels each at out, out + cout, out + 2 cout (the residual is read as hi + lo from
                              residual, residual + cout). fp32-equivalent accuracy on the tcgen05 path; ~4x the work. */
+  int32_t stride_w;       /* horizontal stride if different from `stride` (0 = same). Only (stride 2, stride_w 1) is built: a
+                             3x3 / stride-2 conv over 32 channels reads PAIRS of pixels as 64-channel rows -- the tensor viewed
+                             as [B, H, W/2, 64] -- as a 3x2-tap conv (left pad 1, no right pad: out_w = in_w) with stride 2 over
+                             rows only; 128-byte operand rows and 6 instead of 9 taps */
   const void* in2;        /* second input (device pointer, same batch / height / width), NULL when cin_split == 0 */
 } ay2_conv_desc;
 

@@ -30,7 +30,7 @@ def test_build_and_symbols():
 def test_struct_layouts_match_header():
     from ayolov2_b200 import _lib
 
-    assert ctypes.sizeof(_lib.ConvDesc) == 104 and _lib.ConvDesc.in2.offset == 96  # 23 int32, 4 bytes padding, pointer
+    assert ctypes.sizeof(_lib.ConvDesc) == 112 and _lib.ConvDesc.in2.offset == 104  # 25 int32, 4 bytes padding, pointer
     assert ctypes.sizeof(_lib.ChainDesc) == 17 * 4
     assert ctypes.sizeof(_lib.NmsParams) == 48
     assert ctypes.sizeof(_lib.LossParams) == 120 and _lib.LossParams.fl_gamma.offset == 112  # 5 + 10 + 5 + 8 + 2 four-byte fields

@@ -172,3 +172,29 @@ def test_conv_window_mode_packed_stem(B, H, W, Cout):
     plan.run_reference_simt()
     torch.cuda.synchronize()
     assert float((y.tensor().float() - got).abs().max()) < 3e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 32, 48, 64), (1, 40, 72, 64), (3, 16, 24, 128)])
+def test_conv_pixel_pair_form_stride2(B, H, W, Cout):
+    """3x3 / stride 2 / pad 1 over 32 channels run as a 3x2-tap conv over PAIRS of pixels (the NHWC buffer viewed as
+    [B, H, W/2, 64]; stride 2 over rows, 1 over pairs; `stride_w` in ay2_conv_desc) == the plain convolution."""
+    from ayolov2_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn((B, H, W, 32), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn((Cout, 32, 3, 3), device="cuda", generator=g) * 0.1
+    bias = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    w2 = torch.zeros((Cout, 64, 3, 2), device="cuda")
+    w2[:, 32:, :, 0] = w[:, :, :, 0]
+    w2[:, :32, :, 1] = w[:, :, :, 1]
+    w2[:, 32:, :, 1] = w[:, :, :, 2]
+    wp, bp = ops.pack_conv_weight(w2, bias)
+    y = ops.new_act(B, H // 2, W // 2, Cout)
+    xp = ops.ActView(x.view(B, H, W // 2, 64), 0, 64)
+    plan = ops.ConvPlan(xp, y, wp, bp, 3, 2, 2, 1, 1, pad_w=1, stride_w=1)
+    plan.run()
+    torch.cuda.synchronize()
+    got = y.tensor().float()
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias, stride=2, padding=1)).permute(0, 2, 3, 1)
+    err = (got - ref).abs()
+    assert float((err - (2.0 ** -7 * ref.abs() + 2e-2)).max()) <= 0, float(err.max())
