@@ -306,11 +306,22 @@ __global__ void bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, in
                                         int zcs, long long npix, long long npix_norm, int C, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, int act, const double* __restrict__ s1,
-                                        const double* __restrict__ s2, __nv_bfloat16* __restrict__ dz, int zdcs) {
+                                        const double* __restrict__ s2, __nv_bfloat16* __restrict__ dz, int zdcs,
+                                        float* __restrict__ dbeta_acc, float* __restrict__ dgamma_acc) {
   const int tpp = C >> 3;
   const int lanes = blockDim.x / tpp;
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   if (pl >= lanes) return;
+  if (dbeta_acc && blockIdx.x == 0 && pl == 0) {
+    // the parameter gradients are the two sums themselves: d beta = s1, d gamma = s2 -- accumulated into the caller's fp32
+    // (flat) gradient here instead of two conversion + two add launches per layer on the host side
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      dbeta_acc[c] += (float)s1[c];
+      dgamma_acc[c] += (float)s2[c];
+    }
+  }
   const float invn = 1.0f / (float)npix_norm;  // pixels of the WHOLE (possibly cross-rank, SyncBatchNorm) batch
   F8 is, nms, gah, beh, k0, nk1, nk2;  // dz = k0*dyh + nk1 + xhat*nk2
   {
@@ -740,7 +751,8 @@ extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_
 
 static int bn_act_bwd_impl(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
-                           double* s2, void* dz, int32_t dz_cstride, int phases, int64_t npix_norm, void* stream) {
+                           double* s2, void* dz, int32_t dz_cstride, int phases, int64_t npix_norm, void* stream,
+                           float* dbeta_acc = nullptr, float* dgamma_acc = nullptr) {
   AY2_REQUIRE(dy && z && mean && invstd && gamma && beta && s1 && s2 && dz, "ay2_bn_act_bwd: null pointer");
   int threads, lanes;
   size_t smem;
@@ -761,7 +773,7 @@ static int bn_act_bwd_impl(const void* dy, int32_t dy_cstride, const void* z, in
   if (phases & 2) {
     bn_act_bwd_apply_kernel<<<wave_grid(bn_act_bwd_apply_kernel, 256, 0, (npix + lanes - 1) / lanes), 256, 0, AY2_ST>>>(
         AY2_CBF(dy), dy_cstride, AY2_CBF(z), z_cstride, npix, npix_norm, c, mean, invstd, gamma, beta, act, s1, s2, AY2_BF(dz),
-        dz_cstride);
+        dz_cstride, dbeta_acc, dgamma_acc);
     AY2_CHECK_LAUNCH();
     count_launch();
   }
@@ -772,6 +784,15 @@ extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z,
                               const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
                               double* s1, double* s2, void* dz, int32_t dz_cstride, void* stream) {
   return bn_act_bwd_impl(dy, dy_cstride, z, z_cstride, npix, c, mean, invstd, gamma, beta, act, s1, s2, dz, dz_cstride, 3, npix, stream);
+}
+
+extern "C" int ay2_bn_act_bwd_grads(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
+                                    const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
+                                    double* s1, double* s2, void* dz, int32_t dz_cstride, float* dbeta_acc, float* dgamma_acc,
+                                    void* stream) {
+  AY2_REQUIRE(dbeta_acc && dgamma_acc, "ay2_bn_act_bwd_grads: null gradient pointer");
+  return bn_act_bwd_impl(dy, dy_cstride, z, z_cstride, npix, c, mean, invstd, gamma, beta, act, s1, s2, dz, dz_cstride, 3, npix, stream,
+                         dbeta_acc, dgamma_acc);
 }
 
 extern "C" int ay2_bn_act_bwd_phase(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,

@@ -477,9 +477,11 @@ def bn_act_fwd(z: ActView, mean, invstd, gamma, beta, act: int, y: ActView, resi
 
 
 def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sums: torch.Tensor, dz: ActView,
-               sync: bool = False) -> None:
+               sync: bool = False, grad_beta: Optional[torch.Tensor] = None, grad_gamma: Optional[torch.Tensor] = None) -> bool:
     """sums: double[2*c]; afterwards sums[:c] = d beta, sums[c:] = d gamma (under `sync` with more than one rank: of the
-    cross-rank batch -- SyncBatchNorm's backward; DDP then averages them like every other gradient, so divide by world)."""
+    cross-rank batch -- SyncBatchNorm's backward; DDP then averages them like every other gradient, so divide by world).
+    grad_beta / grad_gamma: fp32 [c] accumulators (slices of the flat gradient) the kernel adds the two sums to; returns
+    True when it did (single-rank statistics), False when the caller has to add `sums` itself."""
     c = z.c
     world = _sync_world(sync)
     if world > 1:
@@ -490,10 +492,19 @@ def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sum
         torch.distributed.all_reduce(sums)
         _lib.check(lib.ay2_bn_act_bwd_phase(*args, 2, _npix(z) * world, st), "ay2_bn_act_bwd_phase")
         sums.div_(world)  # this rank's share: the gradient all-reduce (sum, then / world) restores the total
-        return
+        return False
+    if grad_beta is not None and grad_gamma is not None:
+        assert grad_beta.dtype == grad_gamma.dtype == torch.float32 and grad_beta.is_contiguous() and grad_gamma.is_contiguous()
+        assert grad_beta.numel() == c and grad_gamma.numel() == c
+        _lib.check(_lib.load().ay2_bn_act_bwd_grads(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(),
+                                                    invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(),
+                                                    sums.data_ptr() + 8 * c, dz.ptr(), dz.cstride, grad_beta.data_ptr(),
+                                                    grad_gamma.data_ptr(), _lib.current_stream_ptr()), "ay2_bn_act_bwd_grads")
+        return True
     _lib.check(_lib.load().ay2_bn_act_bwd(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(), invstd.data_ptr(),
                                           gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(), sums.data_ptr() + 8 * c,
                                           dz.ptr(), dz.cstride, _lib.current_stream_ptr()), "ay2_bn_act_bwd")
+    return False
 
 
 def conv_wgrad(x: ActView, dz: ActView, dw: torch.Tensor, kh: int, kw: int, stride: int, pad: int,

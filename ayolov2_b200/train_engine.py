@@ -81,6 +81,7 @@ class TrainEngine:
         self._repack: List[Tuple[nn.Parameter, torch.Tensor, torch.Tensor]] = []  # (fp32 parameter, packed bf16 operand, gather index)
         self._repack_table: Optional[torch.Tensor] = None
         self._repack_total, self._repack_ptrs = 0, None
+        self._bn_counters: List[torch.Tensor] = []    # num_batches_tracked of every BatchNorm the forward passes through
         self._img: Optional[torch.Tensor] = None
         self.head_out: List[torch.Tensor] = []
         self.head_gin: List[torch.Tensor] = []
@@ -199,6 +200,7 @@ class TrainEngine:
             self.refresh.append(lambda: bp[:cout].copy_(conv.bias.detach()))
         self.fwd.append(plan.run)
         if has_bn:
+            self._bn_counters.append(bn.num_batches_tracked)  # all incremented by one launch at the end of the forward
             mean = torch.empty(cout, device=dev)
             invstd = torch.empty(cout, device=dev)
             scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
@@ -206,7 +208,6 @@ class TrainEngine:
 
             def f_bn() -> None:
                 ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
-                bn.num_batches_tracked += 1
                 ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, residual)
             self.fwd.append(f_bn)
         else:
@@ -233,12 +234,18 @@ class TrainEngine:
             if has_bn:
                 if gres is not None:
                     ops.add_slices(gy, gres, accumulate=res_site.accumulate())  # shortcut branch: d(residual) (+)= dy
-                ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz, sync=sync)
-                self._padd(bn.bias, scratch[:cout].float())
-                self._padd(bn.weight, scratch[cout:].float())
-            dw.zero_()
-            ops.conv_wgrad(x, gz, dw, k, k, s, p)
-            self._padd(conv.weight, dw.view(cout, k, k, cin).permute(0, 3, 1, 2))
+                # (d beta, d gamma go straight into the flat gradient from the apply pass unless SyncBatchNorm has to
+                # all-reduce the sums first)
+                if not ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz,
+                                      sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)]):
+                    self._padd(bn.bias, scratch[:cout].float())
+                    self._padd(bn.weight, scratch[cout:].float())
+            if k == 1:  # [cout][cin] IS the OIHW layout: accumulate straight into the flat gradient (zeroed once per step)
+                ops.conv_wgrad(x, gz, self.pg[id(conv.weight)].view(cout, cin), 1, 1, s, p)
+            else:
+                dw.zero_()
+                ops.conv_wgrad(x, gz, dw, k, k, s, p)
+                self._padd(conv.weight, dw.view(cout, k, k, cin).permute(0, 3, 1, 2))
             if conv.bias is not None:
                 bs = torch.zeros(_round_up(cout, 8), dtype=torch.float64, device=dev)
                 ops.channel_sum(ActView(gz.buf, gz.c0, _round_up(cout, 8)), bs)
@@ -339,10 +346,10 @@ class TrainEngine:
         mean, invstd = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
         scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
         act = _act_code(m)
+        self._bn_counters.append(bn.num_batches_tracked)
 
         def f_bn() -> None:
             ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
-            bn.num_batches_tracked += 1
             ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, None)
         self.fwd.append(f_bn)
         gy, gz = self.g(y), self.g(z)
@@ -351,9 +358,10 @@ class TrainEngine:
         x_ptr = s2d.ptr() + 2 * 16  # logical pixel 0 lives at physical column 1
 
         def b() -> None:
-            ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz, sync=sync)
-            self._padd(bn.bias, scratch[:cout].float())
-            self._padd(bn.weight, scratch[cout:].float())
+            if not ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz,
+                                  sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)]):
+                self._padd(bn.bias, scratch[:cout].float())
+                self._padd(bn.weight, scratch[cout:].float())
             dw.zero_()
             ops.conv_wgrad(s2d, gz, dw, 3, 3, 1, 1, in_row_pixels=Wp, x_ptr=x_ptr, in_w=W2)
             g2 = dw.view(cout, 3, 3, 16)[..., :12].permute(0, 3, 1, 2)  # (cout, 12, 3, 3)
@@ -601,6 +609,8 @@ class TrainEngine:
             r()
         for f in self.fwd:
             f()
+        if self._bn_counters:
+            torch._foreach_add_(self._bn_counters, 1)
 
     def _zero_grad_buffers(self) -> None:
         # Activation-gradient buffers are allocated zeroed and every slice is overwritten by its first writer of the step
