@@ -752,13 +752,15 @@ extern "C" int ay2_bn_act_fwd(const void* z, int64_t npix, int32_t c, int32_t z_
 static int bn_act_bwd_impl(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
                            const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
                            double* s2, void* dz, int32_t dz_cstride, int phases, int64_t npix_norm, void* stream,
-                           float* dbeta_acc = nullptr, float* dgamma_acc = nullptr) {
+                           float* dbeta_acc = nullptr, float* dgamma_acc = nullptr, bool sums_zeroed = false) {
   AY2_REQUIRE(dy && z && mean && invstd && gamma && beta && s1 && s2 && dz, "ay2_bn_act_bwd: null pointer");
   int threads, lanes;
   size_t smem;
   AY2_REQUIRE(red_cfg(c, &threads, &lanes, &smem) == 0, "ay2_bn_act_bwd: channels=%d unsupported", c);
   if (phases & 1) {
-    if (s2 == s1 + c) {
+    if (sums_zeroed) {
+      // the caller cleared every layer's sums with one fill before the backward pass
+    } else if (s2 == s1 + c) {
       AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * c, AY2_ST));
     } else {
       AY2_CHECK_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * c, AY2_ST));
@@ -789,10 +791,10 @@ extern "C" int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z,
 extern "C" int ay2_bn_act_bwd_grads(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
                                     const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
                                     double* s1, double* s2, void* dz, int32_t dz_cstride, float* dbeta_acc, float* dgamma_acc,
-                                    void* stream) {
+                                    int32_t sums_zeroed, void* stream) {
   AY2_REQUIRE(dbeta_acc && dgamma_acc, "ay2_bn_act_bwd_grads: null gradient pointer");
   return bn_act_bwd_impl(dy, dy_cstride, z, z_cstride, npix, c, mean, invstd, gamma, beta, act, s1, s2, dz, dz_cstride, 3, npix, stream,
-                         dbeta_acc, dgamma_acc);
+                         dbeta_acc, dgamma_acc, sums_zeroed != 0);
 }
 
 extern "C" int ay2_bn_act_bwd_phase(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,

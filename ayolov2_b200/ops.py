@@ -452,12 +452,14 @@ def _sync_world(sync: bool) -> int:
 
 def bn_batch_stats(z: ActView, eps: float, momentum: float, running_mean: Optional[torch.Tensor],
                    running_var: Optional[torch.Tensor], scratch: torch.Tensor, mean: torch.Tensor, invstd: torch.Tensor,
-                   sync: bool = False) -> None:
-    """scratch: double[2*c] (zeroed here); mean / invstd: fp32 [c] outputs; running stats updated in place.
-    sync (SyncBatchNorm): the per-channel sums are all-reduced, the statistics are those of the cross-rank batch."""
+                   sync: bool = False, zeroed: bool = False) -> None:
+    """scratch: double[2*c] (zeroed here unless the caller already did: `zeroed`); mean / invstd: fp32 [c] outputs; running
+    stats updated in place. sync (SyncBatchNorm): the per-channel sums are all-reduced, the statistics are those of the
+    cross-rank batch."""
     lib = _lib.load()
     c = z.c
-    scratch.zero_()
+    if not zeroed:
+        scratch.zero_()
     st = _lib.current_stream_ptr()
     _lib.check(lib.ay2_bn_stats(z.ptr(), _npix(z), c, z.cstride, scratch.data_ptr(), scratch.data_ptr() + 8 * c, st), "ay2_bn_stats")
     world = _sync_world(sync)
@@ -477,11 +479,13 @@ def bn_act_fwd(z: ActView, mean, invstd, gamma, beta, act: int, y: ActView, resi
 
 
 def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sums: torch.Tensor, dz: ActView,
-               sync: bool = False, grad_beta: Optional[torch.Tensor] = None, grad_gamma: Optional[torch.Tensor] = None) -> bool:
+               sync: bool = False, grad_beta: Optional[torch.Tensor] = None, grad_gamma: Optional[torch.Tensor] = None,
+               zeroed: bool = False) -> bool:
     """sums: double[2*c]; afterwards sums[:c] = d beta, sums[c:] = d gamma (under `sync` with more than one rank: of the
     cross-rank batch -- SyncBatchNorm's backward; DDP then averages them like every other gradient, so divide by world).
     grad_beta / grad_gamma: fp32 [c] accumulators (slices of the flat gradient) the kernel adds the two sums to; returns
-    True when it did (single-rank statistics), False when the caller has to add `sums` itself."""
+    True when it did (single-rank statistics), False when the caller has to add `sums` itself. zeroed: `sums` is already
+    zero (honoured on the single-rank path only; the SyncBatchNorm path clears it itself)."""
     c = z.c
     world = _sync_world(sync)
     if world > 1:
@@ -499,7 +503,8 @@ def bn_act_bwd(dy: ActView, z: ActView, mean, invstd, gamma, beta, act: int, sum
         _lib.check(_lib.load().ay2_bn_act_bwd_grads(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(),
                                                     invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(),
                                                     sums.data_ptr() + 8 * c, dz.ptr(), dz.cstride, grad_beta.data_ptr(),
-                                                    grad_gamma.data_ptr(), _lib.current_stream_ptr()), "ay2_bn_act_bwd_grads")
+                                                    grad_gamma.data_ptr(), int(zeroed), _lib.current_stream_ptr()),
+                   "ay2_bn_act_bwd_grads")
         return True
     _lib.check(_lib.load().ay2_bn_act_bwd(dy.ptr(), dy.cstride, z.ptr(), z.cstride, _npix(z), c, mean.data_ptr(), invstd.data_ptr(),
                                           gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(), sums.data_ptr() + 8 * c,

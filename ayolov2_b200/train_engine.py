@@ -82,6 +82,10 @@ class TrainEngine:
         self._repack_table: Optional[torch.Tensor] = None
         self._repack_total, self._repack_ptrs = 0, None
         self._bn_counters: List[torch.Tensor] = []    # num_batches_tracked of every BatchNorm the forward passes through
+        # per-layer BatchNorm sums (statistics in the forward, the two backward sums later) are slices of ONE double buffer,
+        # cleared by one fill at the start of each pass instead of one fill / memset per layer
+        self._sums_flat = torch.zeros(1 << 18, dtype=torch.float64, device=self.device)
+        self._sums_used = 0
         self._img: Optional[torch.Tensor] = None
         self.head_out: List[torch.Tensor] = []
         self.head_gin: List[torch.Tensor] = []
@@ -170,6 +174,13 @@ class TrainEngine:
             self._repack_table.copy_(host)
         self._repack_total, self._repack_ptrs = begin, ptrs
 
+    def _sums(self, n: int) -> torch.Tensor:
+        n = _round_up(n, 2)
+        assert self._sums_used + n <= self._sums_flat.numel(), "BatchNorm sum buffer too small for this model"
+        v = self._sums_flat[self._sums_used:self._sums_used + n]
+        self._sums_used += n
+        return v
+
     def _padd(self, p: nn.Parameter, t: torch.Tensor) -> None:
         self.pg[id(p)].add_(t.reshape(p.shape))
 
@@ -203,11 +214,11 @@ class TrainEngine:
             self._bn_counters.append(bn.num_batches_tracked)  # all incremented by one launch at the end of the forward
             mean = torch.empty(cout, device=dev)
             invstd = torch.empty(cout, device=dev)
-            scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
-            self.keep += [mean, invstd, scratch]
+            scratch = self._sums(2 * cout)
+            self.keep += [mean, invstd]
 
             def f_bn() -> None:
-                ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
+                ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync, zeroed=True)
                 ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, residual)
             self.fwd.append(f_bn)
         else:
@@ -237,7 +248,7 @@ class TrainEngine:
                 # (d beta, d gamma go straight into the flat gradient from the apply pass unless SyncBatchNorm has to
                 # all-reduce the sums first)
                 if not ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz,
-                                      sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)]):
+                                      sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)], zeroed=True):
                     self._padd(bn.bias, scratch[:cout].float())
                     self._padd(bn.weight, scratch[cout:].float())
             if k == 1:  # [cout][cin] IS the OIHW layout: accumulate straight into the flat gradient (zeroed once per step)
@@ -344,12 +355,12 @@ class TrainEngine:
         self.refresh.append(refresh)
         self.fwd.append(plan.run)
         mean, invstd = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
-        scratch = torch.empty(2 * cout, dtype=torch.float64, device=dev)
+        scratch = self._sums(2 * cout)
         act = _act_code(m)
         self._bn_counters.append(bn.num_batches_tracked)
 
         def f_bn() -> None:
-            ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync)
+            ops.bn_batch_stats(z, bn.eps, bn.momentum, bn.running_mean, bn.running_var, scratch, mean, invstd, sync=sync, zeroed=True)
             ops.bn_act_fwd(z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, y, None)
         self.fwd.append(f_bn)
         gy, gz = self.g(y), self.g(z)
@@ -359,7 +370,7 @@ class TrainEngine:
 
         def b() -> None:
             if not ops.bn_act_bwd(gy, z, mean, invstd, bn.weight.detach().float(), bn.bias.detach().float(), act, scratch, gz,
-                                  sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)]):
+                                  sync=sync, grad_beta=self.pg[id(bn.bias)], grad_gamma=self.pg[id(bn.weight)], zeroed=True):
                 self._padd(bn.bias, scratch[:cout].float())
                 self._padd(bn.weight, scratch[cout:].float())
             dw.zero_()
@@ -604,6 +615,7 @@ class TrainEngine:
         self._graphs[key].replay()
 
     def _forward_body(self) -> None:
+        self._sums_flat[:self._sums_used].zero_()
         self._repack_run()
         for r in self.refresh:
             r()
@@ -619,6 +631,7 @@ class TrainEngine:
         for key in self._needs_zero:
             self._gbuf[key].zero_()
         self.pg_flat.zero_()
+        self._sums_flat[:self._sums_used].zero_()
 
     def _backward_body(self) -> None:
         self._zero_grad_buffers()

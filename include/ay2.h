@@ -355,10 +355,12 @@ int ay2_bn_act_bwd(const void* dy, int32_t dy_cstride, const void* z, int32_t z_
                    const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act, double* s1,
                    double* s2, void* dz, int32_t dz_cstride, void* stream);
 /* ay2_bn_act_bwd that also ACCUMULATES the parameter gradients (d beta = s1, d gamma = s2) into two fp32 arrays of c
- * elements -- the slices of the trainer's flat gradient buffer -- from inside the apply pass. */
+ * elements -- the slices of the trainer's flat gradient buffer -- from inside the apply pass. sums_zeroed != 0: s1 / s2
+ * are already zero (the caller clears the sums of every layer with one fill per backward pass). */
 int ay2_bn_act_bwd_grads(const void* dy, int32_t dy_cstride, const void* z, int32_t z_cstride, int64_t npix, int32_t c,
                          const float* mean, const float* invstd, const float* gamma, const float* beta, int32_t act,
-                         double* s1, double* s2, void* dz, int32_t dz_cstride, float* dbeta_acc, float* dgamma_acc, void* stream);
+                         double* s1, double* s2, void* dz, int32_t dz_cstride, float* dbeta_acc, float* dgamma_acc,
+                         int32_t sums_zeroed, void* stream);
 /* The same in two phases, for SyncBatchNorm (scripts/train/train_model_builder.py:86-91): phase 1 computes this rank's s1 / s2,
  * the caller sums them over the ranks (all-reduce of 2 c doubles), phase 2 applies with npix_total = pixels of the whole
  * cross-rank batch. (The forward is ay2_bn_stats -> all-reduce of sum / sumsq -> ay2_bn_finalize with the total count.) */
