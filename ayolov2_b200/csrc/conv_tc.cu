@@ -314,10 +314,21 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, uint32_t slab,
       float bb[8], f[8];
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba + g * 32));
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + g * 32 + 16));
+      // two columns per instruction (FADD2 / FMUL2 / FFMA2: each lane rounds exactly like the scalar form, so the result
+      // is bit-identical): the drain is bound by instruction issue on the narrow-N layers (~6 instructions per element)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = __uint_as_float(v[g * 8 + i]) + bb[i];
-        f[i] = SILU ? silu_f(x) : x;
+      for (int i = 0; i < 4; ++i) {
+        float2 x = __fadd2_rn(make_float2(__uint_as_float(v[g * 8 + 2 * i]), __uint_as_float(v[g * 8 + 2 * i + 1])),
+                              make_float2(bb[2 * i], bb[2 * i + 1]));
+        if (SILU) {  // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (silu_f)
+          const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+          float tx, ty;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+          x = __ffma2_rn(h, make_float2(tx, ty), h);
+        }
+        f[2 * i] = x.x;
+        f[2 * i + 1] = x.y;
       }
       const uint32_t dst = slab + swizzled_offset<Cfg::SWO>(et, cc / 8 + g);
       if (RES) {
