@@ -128,7 +128,23 @@ __device__ __forceinline__ unsigned long long ch_now() {
     if (p.dbg && blockIdx.x == 0 && (it) < 16) p.dbg[(it) * 16 + (slot)] = ch_now(); \
   } while (0)
 
-__device__ __forceinline__ float ch_act(float x, int act) { return act == AY2_ACT_SILU ? silu_f(x) : x; }
+// act(v + bias) for 8 consecutive columns, two columns per instruction (FADD2 / FMUL2 / FFMA2 round per lane exactly like
+// the scalar form of silu_f: bit-identical results)
+__device__ __forceinline__ void ch_bias_act8(const uint32_t* v, const float* bb, int act, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 x = __fadd2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), make_float2(bb[2 * i], bb[2 * i + 1]));
+    if (act == AY2_ACT_SILU) {
+      const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+      float tx, ty;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+      x = __ffma2_rn(h, make_float2(tx, ty), h);
+    }
+    f[2 * i] = x.x;
+    f[2 * i + 1] = x.y;
+  }
+}
 
 // 16 accumulator columns of one row: +bias -> act (-> zero) -> bf16 -> two 16-byte stores `plane` bytes apart
 // (no-swizzle core-matrix layout of T / U: 8 channels x 16 B per pixel, one plane per 8 channels).
@@ -140,8 +156,9 @@ __device__ __forceinline__ void ch_store_planes(const uint32_t* v, uint32_t bias
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(bias_addr + g * 32));
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(bias_addr + g * 32 + 16));
     float f[8];
+    ch_bias_act8(v + g * 8, bb, act, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = keep ? ch_act(__uint_as_float(v[g * 8 + i]) + bb[i], act) : 0.0f;
+    for (int i = 0; i < 8; ++i) f[i] = keep ? f[i] : 0.0f;
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + g * plane), "r"(pack_bf16x2(f[0], f[1])),
                  "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
                  : "memory");
@@ -200,8 +217,7 @@ __device__ __forceinline__ void chain_store_tile(const ChainParams& p, uint8_t* 
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(ba));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb[4]), "=f"(bb[5]), "=f"(bb[6]), "=f"(bb[7]) : "r"(ba + 16));
         float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = ch_act(__uint_as_float(v[g * 8 + i]) + bb[i], act);
+        ch_bias_act8(v + g * 8, bb, act, f);
         const uint32_t dst = smem_u32(slab) + swizzled_offset_rt(row, chunk0 + g, swo);
         if (p.has_res) {
           uint32_t src = dst;
