@@ -245,32 +245,58 @@ __device__ __forceinline__ void head_candidates(const ConvKernelParams& p, const
           head_cand_push(h, ok, b, (static_cast<unsigned long long>(~__float_as_uint(conf)) << 32) | (row * nc + c), lane);
       }
     } else {
-      float zmax = z[0];
+      // Arg-max in LOGIT space: the lane's first largest logit (ascending class order inside a lane), then the entry's
+      // over its 8 lanes (larger logit, then lower class). Below 11 two different bf16 logits give different fp32 scores
+      // (their sigmoids differ by >= 1e-6 relative, far above the 2^-22 error of ex2 / rcp and the product's rounding), and
+      // equal logits give equal scores, so this IS the first arg-max of the scores (metrics.py:363-364) and only the
+      // winner's score is ever computed. Above 11 the sigmoid saturates (distinct logits may round to one score, and the
+      // lower class must win): those rows take the window scan below.
+      float zb = z[0];
+      int ib = 0;
 #pragma unroll
-      for (int i = 1; i < 16; ++i) zmax = fmaxf(zmax, z[i]);
+      for (int i = 1; i < 16; ++i)
+        if (z[i] > zb) {
+          zb = z[i];
+          ib = i;
+        }
+      int cb = chb[ib >> 3] + (ib & 7) - ch_lo;
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-      const float zwin = fminf(zmax - 0.0625f, 11.0f);
-      float best = -INFINITY;
-      int bidx = 0x7fffffff;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {  // ascending class order inside a chunk; the reduction below orders across lanes by index
-        if (z[i] >= zwin) {
-          const float conf = __fmul_rn(head_sigmoid(z[i]), obj);
-          const int c = chb[i >> 3] + (i & 7) - ch_lo;
-          if (conf > best || (conf == best && c < bidx)) {
-            best = conf;
-            bidx = c;
-          }
+      for (int o = 4; o > 0; o >>= 1) {
+        const float oz = __shfl_xor_sync(0xffffffffu, zb, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, cb, o);
+        if (oz > zb || (oz == zb && oc < cb)) {
+          zb = oz;
+          cb = oc;
         }
       }
+      float best;
+      int bidx;
+      if (!__ballot_sync(0xffffffffu, zb > 10.9375f)) {  // warp-uniform: no entry of this pass is near saturation
+        best = __fmul_rn(head_sigmoid(zb), obj);
+        bidx = cb;
+      } else {
+        const float zwin = fminf(zb - 0.0625f, 11.0f);  // zb is the entry's largest logit in all of its lanes
+        best = -INFINITY;
+        bidx = 0x7fffffff;
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {  // first arg-max over the entry's 8 lanes (metrics.py:363-364): larger score, then lower class
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) {
-          best = ob;
-          bidx = oi;
+        for (int i = 0; i < 16; ++i) {  // ascending class order inside a chunk; the reduction below orders across lanes by index
+          if (z[i] >= zwin) {
+            const float conf = __fmul_rn(head_sigmoid(z[i]), obj);
+            const int c = chb[i >> 3] + (i & 7) - ch_lo;
+            if (conf > best || (conf == best && c < bidx)) {
+              best = conf;
+              bidx = c;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {  // first arg-max over the entry's 8 lanes: larger score, then lower class
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+          if (ob > best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+          }
         }
       }
       if (have && sub == 0) {
