@@ -76,3 +76,32 @@ def test_bucketed_allreduce_equals_whole_buffer_gloo():
     port = 29650 + os.getpid() % 200
     mp.spawn(_bucket_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_weight_repack_gather_tables_reproduce_the_layout_functions():
+    """train_engine refreshes every packed bf16 conv operand with ONE gather launch (ay2_repack_weights) whose index tables
+    come from running the layout functions on index-valued tensors (ops.gather_index_of). On the CPU: gathering a random
+    weight through each table equals applying the layout function itself -- forward layout, stride-1 and stride-2 dgrad."""
+    import torch
+
+    from ayolov2_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    for cout, cin, k, s, p in [(32, 16, 3, 1, 1), (64, 32, 3, 2, 1), (24, 40, 1, 1, 0), (256, 128, 3, 2, 1)]:
+        w = torch.randn((cout, cin, k, k), generator=g)
+        fns = [ops.conv_weight_layout]
+        n_d = len(ops.dgrad_weight_layouts(w, s, p, _round8(cout)))
+        fns += [lambda t, i=i: ops.dgrad_weight_layouts(t, s, p, _round8(cout))[i] for i in range(n_d)]
+        assert n_d == (1 if s == 1 else 4)
+        for fn in fns:
+            want = fn(w)
+            idx = ops.gather_index_of(fn, tuple(w.shape), "cpu")
+            assert idx.dtype == torch.int32 and idx.shape == want.shape
+            flat = torch.cat((w.reshape(-1), torch.zeros(1)))
+            got = flat[idx.reshape(-1).long().clamp_min(-1)].reshape(want.shape)  # index -1 -> the appended zero
+            assert torch.equal(got, want)
+            assert int((idx < 0).sum()) == int(want.numel() - (want != 0).sum())  # only the padding is -1 (w has no zeros)
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
