@@ -105,3 +105,22 @@ def test_weight_repack_gather_tables_reproduce_the_layout_functions():
 
 def _round8(n):
     return (n + 7) // 8 * 8
+
+
+def test_first_writer_overwrites_rule():
+    """train_engine._GradSite: the first writer of a gradient slice in the (static) backward order overwrites, later ones
+    accumulate; a writer that is partly new, partly old accumulates onto a per-step zero fill of that buffer."""
+    import types
+
+    from ayolov2_b200.train_engine import TrainEngine
+
+    eng = types.SimpleNamespace(_cover={}, _needs_zero=set())
+    claim = lambda lo, hi, key=1: TrainEngine._claim(eng, key, lo, hi)  # noqa: E731
+    assert claim(0, 64) is False          # first writer of [0, 64): overwrite
+    assert claim(0, 32) is True           # inside what was written: accumulate
+    assert claim(64, 128) is False        # fresh slice of the same buffer (concat neighbour): overwrite
+    assert claim(32, 96) is True          # covered by the union of the two
+    assert not eng._needs_zero
+    assert claim(96, 160) is True         # [128, 160) was never written: accumulate, and the buffer needs its zero fill
+    assert eng._needs_zero == {1}
+    assert claim(0, 8, key=2) is False and eng._needs_zero == {1}  # other buffers are independent
