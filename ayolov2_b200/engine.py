@@ -117,11 +117,7 @@ class Builder:
             # of pixels as 64-channel rows instead -- the same buffer viewed as [B, H, W/2, 64] -- with a 3x2-tap kernel:
             # pair ox-1 carries column 2ox-1 in its upper 32 channels (kw = 0), pair ox carries columns 2ox, 2ox+1 (kw = 1, 2).
             # Stride 2 over rows only: 128-byte rows, six taps (one weight block of zeros).
-            w2 = torch.zeros((w.shape[0], 64, 3, 2), device=self.device)
-            w2[:, 32:, :, 0] = w[:, :, :, 0]
-            w2[:, :32, :, 1] = w[:, :, :, 1]
-            w2[:, 32:, :, 1] = w[:, :, :, 2]
-            wp, bp = ops.pack_conv_weight(w2, bias, bn, eps)
+            wp, bp = ops.pack_conv_weight(ops.pixel_pair_weight(w), bias, bn, eps)
             xp = ActView(x.buf.view(x.B, x.H, x.W // 2, 64), 0, 64)
             plan = ConvPlan(xp, y, wp, bp, 3, 2, 2, 1, act, pad_w=1, stride_w=1)
             self.plans.append(plan)

@@ -612,6 +612,19 @@ def _dgrad_specs(weight: torch.Tensor, stride: int, pad: int):
     return specs
 
 
+def pixel_pair_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW weight of a 3x3 / stride-2 / pad-1 conv over 32 channels -> the (cout, 64, 3, 2) weight of the same conv read
+    over PAIRS of pixels ([B, H, W/2, 64]; stride 2 over rows, 1 over pairs; one pair of zero padding on the left only): pair
+    ox - 1 carries input column 2 ox - 1 in its upper 32 channels (kw = 0), pair ox columns 2 ox and 2 ox + 1 (kw = 1, 2)."""
+    cout, cin, kh, kw = w.shape
+    assert (cin, kh, kw) == (32, 3, 3), w.shape
+    w2 = torch.zeros((cout, 64, 3, 2), dtype=w.dtype, device=w.device)
+    w2[:, 32:, :, 0] = w[:, :, :, 0]
+    w2[:, :32, :, 1] = w[:, :, :, 1]
+    w2[:, 32:, :, 1] = w[:, :, :, 2]
+    return w2
+
+
 def conv_weight_layout(w: torch.Tensor) -> torch.Tensor:
     """OIHW fp32 -> the K-major operand layout [Cout_pad, KH*KW*Cin] in fp32 (pack_conv_weight without the BN fold and the
     bf16 cast): a pure index permutation + zero padding, so applying it to an index-valued tensor yields the gather table

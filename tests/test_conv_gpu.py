@@ -184,11 +184,7 @@ def test_conv_pixel_pair_form_stride2(B, H, W, Cout):
     x = torch.randn((B, H, W, 32), device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn((Cout, 32, 3, 3), device="cuda", generator=g) * 0.1
     bias = torch.randn(Cout, device="cuda", generator=g) * 0.1
-    w2 = torch.zeros((Cout, 64, 3, 2), device="cuda")
-    w2[:, 32:, :, 0] = w[:, :, :, 0]
-    w2[:, :32, :, 1] = w[:, :, :, 1]
-    w2[:, 32:, :, 1] = w[:, :, :, 2]
-    wp, bp = ops.pack_conv_weight(w2, bias)
+    wp, bp = ops.pack_conv_weight(ops.pixel_pair_weight(w), bias)
     y = ops.new_act(B, H // 2, W // 2, Cout)
     xp = ops.ActView(x.view(B, H, W // 2, 64), 0, 64)
     plan = ops.ConvPlan(xp, y, wp, bp, 3, 2, 2, 1, 1, pad_w=1, stride_w=1)

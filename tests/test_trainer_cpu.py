@@ -124,3 +124,22 @@ def test_first_writer_overwrites_rule():
     assert claim(96, 160) is True         # [128, 160) was never written: accumulate, and the buffer needs its zero fill
     assert eng._needs_zero == {1}
     assert claim(0, 8, key=2) is False and eng._needs_zero == {1}  # other buffers are independent
+
+
+def test_pixel_pair_weight_is_the_same_convolution():
+    """ops.pixel_pair_weight: a 3x3 / stride-2 / pad-1 conv over 32 channels == a 3x2-tap conv over pairs of pixels (64-channel
+    "pixels"), stride 2 over rows and 1 over pairs, one pair of zero padding on the left only. Checked with torch on the CPU."""
+    import torch
+    import torch.nn.functional as F
+
+    from ayolov2_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn((2, 32, 12, 20), generator=g)
+    w = torch.randn((48, 32, 3, 3), generator=g)
+    want = F.conv2d(x, w, stride=2, padding=1)
+    # NCHW view of the pairs: channel index = (pixel of the pair) * 32 + c, exactly the NHWC buffer viewed as [B, H, W/2, 64]
+    xp = x.view(2, 32, 12, 10, 2).permute(0, 4, 1, 2, 3).reshape(2, 64, 12, 10)
+    xp = F.pad(xp, (1, 0, 1, 1))  # left pair, top / bottom rows
+    got = F.conv2d(xp, ops.pixel_pair_weight(w), stride=(2, 1))
+    assert got.shape == want.shape and torch.allclose(got, want, atol=1e-4, rtol=1e-5)
