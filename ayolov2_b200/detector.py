@@ -112,6 +112,10 @@ class Detector:
         eng = self.engine
         eng._img = img
         eng.b.s2d_step()
+        return self._run_body()
+
+    def _run_body(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The static part of a step (the stem's space-to-depth input has been written)."""
         if not self._warm:
             self._body()  # first call: plain launches (sets function attributes) ...
             torch.cuda.synchronize()
@@ -137,6 +141,48 @@ class Detector:
         cur.wait_event(self.ev_h2d[k])
         det, cnt = self.run_device(self.dev_in[k])
         self.ev_consumed[k].record(cur)
+        self.host_out[k].copy_(det, non_blocking=True)
+        self.host_cnt[k][:self.B].copy_(cnt, non_blocking=True)
+        self.host_cnt[k][self.B:].copy_(self.nms_ws.overflow, non_blocking=True)
+        self.ev_done[k].record(cur)
+        return k
+
+    def submit_packed(self, pb, fused: bool = True) -> int:
+        """Enqueue one batch of LOADED images (`data_loader.pack_batch`: ragged HWC BGR uint8 + geometry table in one host
+        arena). The letterbox / channel flip / collate of scripts/data_loader/data_loader.py:380-393,461-477 runs on the
+        device: one H2D copy of the raw bytes, then one kernel that writes the stem's space-to-depth input directly
+        (`fused`; prepare_img's /255 included) or the uint8 NCHW slot followed by the usual first step. Returns the slot id;
+        `pb.shapes` holds what `scale_coords` needs."""
+        import dataclasses
+
+        assert pb.batch == self.B and tuple(pb.out_shape) == (self.H, self.W) and self.in_dtype == torch.uint8
+        k = self._slot
+        self._slot = (k + 1) % self.slots
+        n = pb.arena.numel()
+        if not hasattr(self, "stage"):
+            self.stage = [None] * self.slots
+        if self.stage[k] is None or self.stage[k].numel() < n:
+            torch.cuda.synchronize(self.device)  # a (rare) growth must not free bytes a running kernel still reads
+            self.stage[k] = torch.empty(max(n, self.B * (3 * self.H * self.W + 64)), dtype=torch.uint8, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_consumed[k])
+            dst = self.stage[k][:n]
+            dst.copy_(pb.arena, non_blocking=True)
+            self.ev_h2d[k].record(self.copy_stream)
+        cur.wait_event(self.ev_h2d[k])
+        dpb = dataclasses.replace(pb, arena=dst)
+        eng = self.engine
+        if fused and not eng.b.x3:
+            dpb.to_space_to_depth(eng.b.s2d_view, eng.b.s2d_scale, x_offset=1)
+            self.ev_consumed[k].record(cur)
+            det, cnt = self._run_body()
+            self._packed_fused_last = True
+        else:
+            dpb.to_device(out=self.dev_in[k])
+            det, cnt = self.run_device(self.dev_in[k])
+            self.ev_consumed[k].record(cur)
+            self._packed_fused_last = False
         self.host_out[k].copy_(det, non_blocking=True)
         self.host_cnt[k][:self.B].copy_(cnt, non_blocking=True)
         self.host_cnt[k][self.B:].copy_(self.nms_ws.overflow, non_blocking=True)

@@ -229,6 +229,7 @@ class Builder:
         Wp = W2 + 8
         s2d = ActView(torch.zeros((self.B, H2, Wp, 48 if self.x3 else 16), dtype=torch.bfloat16, device=self.device), 0, 16, self.x3)
         self.keep.append(s2d.buf)
+        self.s2d_view, self.s2d_scale = s2d, scale  # the fused letterbox kernel (data_loader.PackedBatch) writes it directly
         if self.x3:
             inv = 1.0 / scale
             divisor = float(round(inv)) if abs(inv - round(inv)) < 1e-6 * inv else inv  # 1/255 -> exactly 255

@@ -296,6 +296,35 @@ int ay2_nms_batched_scaled(const float* pred, const ay2_nms_params* p, const uin
                            void* workspace, size_t workspace_bytes, float* out_det, int32_t* out_count, int32_t* overflow_flag,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input side: letterbox + BGR->RGB + HWC->CHW + collate of a whole batch in one launch. Replaces
+ * LoadImages._letterbox (scripts/data_loader/data_loader.py:395-459: cv2.resize INTER_LINEAR to the unpadded size +
+ * cv2.copyMakeBorder), the transpose / channel flip of :388-389 and the torch.stack of collate_fn (:461-477, :905-909);
+ * with AY2_LB_S2D_BF16 also prepare_img + ay2_space_to_depth (the uint8 NCHW batch is never written).
+ *   arena : DEVICE bytes holding the loaded images, HWC BGR uint8 (ragged sizes; rows src_row_bytes apart)
+ *   table : DEVICE array of `batch` records; the geometry is the host's (data_loader.py:428-455 is scalar arithmetic):
+ *           dst_w / dst_h = new_unpad (the size after the resize; == src size: plain copy), top / left = the border
+ *   out   : AY2_LB_NCHW_U8  -> uint8 [batch][3][out_h][out_w] RGB (the reference's collated tensor), bit-exact with cv2
+ *           AY2_LB_S2D_BF16 -> bf16 [batch][out_h/2][out_row_pixels][16] at column offset out_x_offset, value * scale
+ *                              (identical to ay2_space_to_depth of the uint8 tensor)
+ *   color_bgr : border colour, b | g << 8 | r << 16 (the reference: 114, 114, 114). out_h even, out_w % 4 == 0. */
+#define AY2_LB_NCHW_U8 0
+#define AY2_LB_S2D_BF16 1
+typedef struct ay2_letterbox_image {
+  int64_t src_offset;     /* byte offset of the image inside `arena` */
+  int32_t src_h, src_w;   /* the loaded image */
+  int32_t src_row_bytes;  /* >= 3 * src_w */
+  int32_t dst_h, dst_w;   /* new_unpad (h, w) */
+  int32_t top, left;      /* border above / left of the resized image */
+  int32_t reserved;
+} ay2_letterbox_image;    /* 40 bytes */
+int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t out_h, int32_t out_w,
+                          uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels, int32_t out_x_offset,
+                          float scale, void* stream);
+/* LoadImagesAndLabels.collate_fn (data_loader.py:905-909): labels fp32 [total][6] (already concatenated), offsets int32
+ * [batch + 1] (row range of every image, DEVICE): writes the image index into column 0. */
+int ay2_collate_labels(float* labels, const int32_t* offsets, int32_t batch, int32_t total, void* stream);
+
 /* Validation statistics: replaces the per-image host loop of YoloValidator.statistics_per_image / process_batch
  * (scripts/utils/train_utils.py:294-401) for a whole batch. det / counts: the NMS output ([batch][max_det][6], [batch]);
  * labels: fp32 [nt][6] = image, class, box; meta == NULL: boxes are xyxy in the detections' coordinates (the plain

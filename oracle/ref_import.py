@@ -89,3 +89,16 @@ def clamp_compat():
         yield
     finally:
         torch.Tensor.clamp_ = orig
+
+
+def load_data_loader():
+    """The reference's scripts/data_loader/data_loader.py module, unmodified (for LoadImages._letterbox / collate_fn,
+    LoadImagesAndLabels.collate_fn). Needs cv2 (installed in the build container) and one more stub: `p_tqdm`
+    (progress-bar helper of the label cache, not on this path)."""
+    load()
+    pt = _stub("p_tqdm")
+    if not hasattr(pt, "p_map"):
+        pt.p_map = None
+    import scripts.data_loader.data_loader as dl  # type: ignore
+
+    return dl

@@ -1,0 +1,140 @@
+"""GPU input side (csrc/letterbox.cu through the C-ABI, ayolov2_b200/data_loader.py) against the oracle
+(oracle/input_oracle.py, pinned to cv2 and to the unmodified reference's _letterbox / collate_fn) and against the committed
+outputs of the unmodified reference (tests/golden/input_golden.npz). Integer work: the bar is bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = pytest.mark.gpu
+
+from ayolov2_b200 import data_loader as dl  # noqa: E402
+from ayolov2_b200 import ops  # noqa: E402
+from oracle import input_oracle  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "input_golden.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden_input import CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_letterbox_collate_equals_reference_golden(ci):
+    g = np.load(GOLD)
+    new_shape, shapes, kw = CASES[ci]
+    imgs = [g[f"c{ci}_img{k}"] for k in range(len(shapes))]
+    kw = {k: v for k, v in kw.items() if k != "auto"}
+    pb = dl.pack_batch(imgs, new_shape, **kw)
+    out = pb.to_device("cuda")
+    torch.cuda.synchronize()
+    assert out.dtype == torch.uint8 and tuple(out.shape) == g[f"c{ci}_batch"].shape
+    assert np.array_equal(out.cpu().numpy(), g[f"c{ci}_batch"])
+    geo = g[f"c{ci}_geo"]
+    for i in range(len(imgs)):
+        assert pb.ratios[i] == (geo[i, 0], geo[i, 1]) and pb.shapes[i][1][1] == (geo[i, 2], geo[i, 3])
+
+
+@pytest.mark.parametrize("new_shape", [(640, 640), (384, 672), (32, 36)])
+def test_letterbox_collate_equals_oracle_ragged_shapes(new_shape):
+    """Up- and down-scales, the exact 2 x 2 decimation, images already at the output size, one-pixel-wide / one-row images."""
+    rng = np.random.default_rng(hash(new_shape) % 1000)
+    H, W = new_shape
+    shapes = [(H, W), (2 * H, 2 * W), (H, W // 2), (H // 2, W), (1, 7), (9, 1), (H - 1, W - 1), (H + 1, W + 3), (3 * H, 5 * W // 2)]
+    shapes += [(int(rng.integers(2, 3 * H)), int(rng.integers(2, 3 * W))) for _ in range(7)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    for kw in (dict(), dict(scale_up=False), dict(scale_fill=True)):
+        ref, ref_shapes = input_oracle.load_and_collate(imgs, new_shape, auto=False, **kw)
+        pb = dl.pack_batch(imgs, new_shape, **kw)
+        got = pb.to_device("cuda").cpu().numpy()
+        bad = [i for i in range(len(imgs)) if not np.array_equal(got[i], ref[i])]
+        assert not bad, f"images {[(i, shapes[i]) for i in bad]} differ ({kw})"
+        assert pb.shapes == ref_shapes
+
+
+def test_fused_space_to_depth_equals_two_step_path():
+    """AY2_LB_S2D_BF16 == letterbox to uint8 NCHW followed by ay2_space_to_depth (prepare_img's /255 included), bit for bit,
+    and the padding columns of the stem's input stay untouched."""
+    H, W, B = 128, 160, 5
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (int(rng.integers(20, 300)), int(rng.integers(20, 300)), 3), dtype=np.uint8) for _ in range(B)]
+    pb = dl.pack_batch(imgs, (H, W), pin=True)
+    u8 = pb.to_device("cuda")
+    Wp = W // 2 + 8
+    ref = ops.ActView(torch.full((B, H // 2, Wp, 16), 7.0, dtype=torch.bfloat16, device="cuda"), 0, 16)
+    got = ops.ActView(torch.full((B, H // 2, Wp, 16), 7.0, dtype=torch.bfloat16, device="cuda"), 0, 16)
+    ops.space_to_depth(u8, ref, 1.0 / 255.0, x_offset=1)
+    staging = torch.empty(pb.arena.numel() + 64, dtype=torch.uint8, device="cuda")
+    pb.to_space_to_depth(got, 1.0 / 255.0, x_offset=1, staging=staging)
+    torch.cuda.synchronize()
+    assert torch.equal(got.buf.view(torch.int16), ref.buf.view(torch.int16))
+    assert torch.all(got.buf[:, :, 0, :] == 7.0) and torch.all(got.buf[:, :, W // 2 + 1:, :] == 7.0)
+
+
+def test_full_size_batch_properties():
+    """BASELINE-size batch (64 x 3 x 640 x 640): size-independent properties instead of the (slow) oracle -- the border is
+    the constant colour, an image already at the output size passes through unchanged (flipped to RGB planes), and the
+    kernel is idempotent on its own output fed back as an image."""
+    B, H, W = 64, 640, 640
+    rng = np.random.default_rng(11)
+    shapes = [(640, 640) if i % 4 == 0 else (640, int(rng.integers(300, 640))) if i % 4 == 1 else (int(rng.integers(300, 640)), 640)
+              if i % 4 == 2 else (int(rng.integers(100, 400)), int(rng.integers(100, 400))) for i in range(B)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    pb = dl.pack_batch(imgs, (H, W), pin=True)
+    out = pb.to_device("cuda")
+    host = out.cpu().numpy()
+    for i, im in enumerate(imgs):
+        (uw, uh), _, _, (top, bottom, left, right) = dl.letterbox_geometry(im.shape[:2], (H, W), auto=False)
+        mask = np.ones((H, W), bool)
+        mask[top:top + uh, left:left + uw] = False
+        assert np.all(host[i][:, mask] == 114)
+        if im.shape[:2] == (uh, uw):
+            assert np.array_equal(host[i][:, top:top + uh, left:left + uw], im.transpose(2, 0, 1)[::-1])
+    again = dl.pack_batch([np.ascontiguousarray(host[i].transpose(1, 2, 0)[:, :, ::-1]) for i in range(B)], (H, W)).to_device("cuda")
+    assert torch.equal(again, out)
+    sample = [1, 2, 3, 62, 63]  # and five images against the oracle
+    ref, _ = input_oracle.load_and_collate([imgs[i] for i in sample], (H, W))
+    assert np.array_equal(host[sample], ref)
+
+
+def test_collate_labels_equals_golden_and_oracle():
+    g = np.load(GOLD)
+    labels = [torch.from_numpy(g[f"lab_in{i}"]) for i in range(4)]
+    got = dl.collate_labels(labels, "cuda").cpu().numpy()
+    assert np.array_equal(got, g["lab_out"])
+    rng = np.random.default_rng(5)
+    many = [rng.random((int(n), 6)).astype(np.float32) for n in rng.integers(0, 40, 64)]
+    got = dl.collate_labels([torch.from_numpy(m) for m in many], "cuda").cpu().numpy()
+    assert np.array_equal(got, input_oracle.collate_labels(many))
+    assert dl.collate_labels([torch.zeros(0, 6)] * 3, "cuda").shape == (0, 6)
+
+
+def test_detector_from_loaded_images_equals_detector_on_the_reference_batch():
+    """Detector.submit_packed (raw loaded images -> device letterbox, fused into the stem's input or through the uint8 slot)
+    returns exactly the detections of Detector.detect on the batch the reference's Dataset + collate_fn would have built."""
+    from ayolov2_b200 import synth
+    from ayolov2_b200.detector import Detector
+
+    model = synth.build_model("yolov5s", seed=2).cuda()
+    B, H, W = 4, 320, 352
+    imgs = input_oracle.synth_images(21, [(320, 352), (200, 352), (320, 240), (97, 131)])
+    ref_batch, ref_shapes = input_oracle.load_and_collate(imgs, (H, W))
+    host = torch.from_numpy(ref_batch)
+    sample = host.cuda().float() / 255.0
+    synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.1)
+    det = Detector(model, B, H, W, conf_thres=0.25, iou_thres=0.45, in_dtype=torch.uint8)
+    want = det.detect(host.pin_memory())
+    assert sum(x.shape[0] for x in want) > 20
+    pb = dl.pack_batch(imgs, (H, W), pin=True)
+    assert pb.shapes == ref_shapes
+    for fused in (True, False, True):
+        got = det.collect(det.submit_packed(pb, fused=fused))
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    # pipelined: several batches in flight over the slots
+    ks = [det.submit_packed(pb) for _ in range(2)]
+    for k in ks:
+        for a, b in zip(det.collect(k), want):
+            assert torch.equal(a, b)

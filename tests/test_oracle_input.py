@@ -1,0 +1,98 @@
+"""Pins oracle/input_oracle.py (letterbox + collate, data_loader.py:388-477,888-909): against the committed outputs of the
+unmodified reference (tests/golden/input_golden.npz), against the reference itself when /root/reference is present, and
+the restated cv2.resize against cv2 when it is importable. CPU only."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import input_oracle, ref_import  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "input_golden.npz")
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+from make_golden_input import CASES  # noqa: E402
+
+HAVE_CV2 = importlib.util.find_spec("cv2") is not None
+
+
+def golden_case(g, ci):
+    new_shape, shapes, kw = CASES[ci]
+    imgs = [g[f"c{ci}_img{k}"] for k in range(len(shapes))]
+    return new_shape, imgs, kw, g[f"c{ci}_batch"], g[f"c{ci}_geo"]
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_letterbox_collate_matches_golden(ci):
+    g = np.load(GOLD)
+    new_shape, imgs, kw, batch, geo = golden_case(g, ci)
+    for im, (h, w) in zip(imgs, CASES[ci][1]):
+        assert im.shape == (h, w, 3)
+    got, shapes = input_oracle.load_and_collate(imgs, new_shape, **kw)
+    assert got.dtype == np.uint8 and got.shape == batch.shape
+    assert np.array_equal(got, batch)
+    for im, row, shp in zip(imgs, geo, shapes):
+        _, ratio, pad, _ = input_oracle.letterbox_geometry(im.shape[:2], new_shape, **kw)
+        assert tuple(row) == (ratio[0], ratio[1], float(pad[0]), float(pad[1]))
+        assert shp[0] == im.shape[:2] and shp[1][1] == pad
+
+
+def test_synth_images_reproduce_the_fixture_inputs():
+    g = np.load(GOLD)
+    for ci, (_, shapes, _) in enumerate(CASES):
+        for k, im in enumerate(input_oracle.synth_images(100 + ci, shapes)):
+            assert np.array_equal(im, g[f"c{ci}_img{k}"])
+
+
+def test_collate_labels_matches_golden():
+    g = np.load(GOLD)
+    labels = [g[f"lab_in{i}"] for i in range(4)]
+    got = input_oracle.collate_labels(labels)
+    assert np.array_equal(got, g["lab_out"])
+    assert got[:, 0].tolist() == [0, 0, 0, 2, 2, 2, 2, 2, 3]
+    assert input_oracle.collate_labels([]).shape == (0, 6)
+
+
+def test_auto_mode_pads_to_the_stride_multiple():
+    im = input_oracle.synth_images(3, [(100, 60)])[0]
+    out, ratio, (dw, dh) = input_oracle.letterbox(im, (128, 128), auto=True, stride=32)
+    assert out.shape[0] == 128 and out.shape[1] % 32 == 0 and out.shape[1] < 128
+    assert np.all(out[:, 0] == 114) or dw < 1
+
+
+@pytest.mark.skipif(not HAVE_CV2, reason="cv2 not installed")
+def test_resize_restatement_is_bit_exact_against_cv2():
+    import cv2
+
+    rng = np.random.default_rng(0)
+    for t in range(150):
+        h, w = (int(v) for v in rng.integers(2, 300, 2))
+        if t % 7 == 0:
+            dh, dw = max(h // 2, 1), max(w // 2, 1)
+            h, w = 2 * dh, 2 * dw
+        elif t % 7 == 1:
+            dh, dw = h, int(rng.integers(1, 300))
+        else:
+            dh, dw = (int(v) for v in rng.integers(1, 300, 2))
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(ref, input_oracle.resize_linear_u8(img, dw, dh)), ((h, w), (dh, dw))
+
+
+@pytest.mark.skipif(not (ref_import.available() and HAVE_CV2), reason="reference tree / cv2 not present")
+def test_oracle_matches_the_unmodified_reference():
+    dl = ref_import.load_data_loader()
+    fake = types.SimpleNamespace(img_size=160, stride=32)
+    rng = np.random.default_rng(1)
+    for case in range(12):
+        shapes = [(int(rng.integers(20, 260)), int(rng.integers(20, 260))) for _ in range(3)]
+        kw = [dict(auto=False), dict(auto=True), dict(auto=False, scale_up=False), dict(auto=False, scale_fill=True)][case % 4]
+        for im in input_oracle.synth_images(case, shapes):
+            ref, r_ratio, r_pad = dl.LoadImages._letterbox(fake, im, new_shape=(160, 128), **kw)
+            got, ratio, pad = input_oracle.letterbox(im, (160, 128), **kw)
+            assert np.array_equal(ref, got), (im.shape, kw)
+            assert tuple(r_ratio) == tuple(ratio) and tuple(r_pad) == tuple(pad)
