@@ -157,7 +157,7 @@ _PROTOS = {
     "ay2_sgd_ema_step_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_int32, C.c_float,
                                           C.c_float, C.c_void_p]),
-    "ay2_letterbox_collate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32,
+    "ay2_letterbox_collate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32,
                                         C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
     "ay2_collate_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_nms_workspace_bytes": (C.c_size_t, [C.POINTER(NmsParams)]),

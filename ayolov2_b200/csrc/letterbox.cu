@@ -1,4 +1,4 @@
-// Input side of the path on the GPU: letterbox + BGR->RGB + HWC->CHW + collate for a whole batch in ONE launch.
+// Input side of the path on the GPU: letterbox + BGR->RGB + HWC->CHW + collate for a whole batch (one launch per kind of image: plain copy / resize).
 //
 // Replaces, per image on the host in the reference, LoadImages._letterbox (scripts/data_loader/data_loader.py:395-459:
 // cv2.resize(INTER_LINEAR) to the unpadded size + cv2.copyMakeBorder(114)), the `transpose((2, 0, 1))[::-1]` of
@@ -26,14 +26,20 @@ struct LetterboxParams {
   uint8_t color[3];  // BGR like the source
 };
 
+enum { LB_COPY = 0, LB_AREA = 1, LB_LINEAR = 2 };
+__device__ __forceinline__ int image_mode(const ay2_letterbox_image& im) {
+  if (im.dst_h == im.src_h && im.dst_w == im.src_w) return LB_COPY;
+  if (im.src_h == 2 * im.dst_h && im.src_w == 2 * im.dst_w) return LB_AREA;  // cv2 reroutes the exact 2 x 2 decimation
+  return LB_LINEAR;
+}
+
 struct Tap {
   int s0, s1, c0, c1;  // source indices and 11-bit weights
 };
 
-// resize.cpp: fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s  (scale = 1 / (dst / src) in double)
-__device__ __forceinline__ void tap_position(int d, int ssize, int dsize, int& s, float& f) {
-  const double inv = __ddiv_rn((double)dsize, (double)ssize);
-  const double scale = __ddiv_rn(1.0, inv);
+// resize.cpp: fx = (float)((d + 0.5) * scale - 0.5); s = floor(fx); fx -= s, with scale = 1 / (dst / src) in double
+// (the host puts it into the table: two double divisions per tap were a third of the interpolating kernel's instructions)
+__device__ __forceinline__ void tap_position(int d, double scale, int& s, float& f) {
   f = __double2float_rn(__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5));
   const float fl = floorf(f);
   s = (int)fl;
@@ -49,102 +55,36 @@ __device__ __forceinline__ Tap make_tap(float f, int s0, int s1) {
 }
 
 // columns collapse to one tap outside [0, w - 1); rows are clamped instead
-__device__ __forceinline__ Tap column_tap(int d, int ssize, int dsize) {
+__device__ __forceinline__ Tap column_tap(int d, int ssize, double scale) {
   int s;
   float f;
-  tap_position(d, ssize, dsize, s, f);
+  tap_position(d, scale, s, f);
   if (s < 0) f = 0.f, s = 0;
   if (s >= ssize - 1) f = 0.f, s = ssize - 1;
   return make_tap(f, s, min(s + 1, ssize - 1));
 }
 
-__device__ __forceinline__ Tap row_tap(int d, int ssize, int dsize) {
+__device__ __forceinline__ Tap row_tap(int d, int ssize, double scale) {
   int s;
   float f;
-  tap_position(d, ssize, dsize, s, f);
+  tap_position(d, scale, s, f);
   return make_tap(f, min(max(s, 0), ssize - 1), min(max(s + 1, 0), ssize - 1));
 }
 
+// the thread's 4 x 2 pixels (BGR) -> the collated uint8 NCHW RGB tensor, or the stem's space-to-depth bf16 image
 template <int KIND>
-__global__ void __launch_bounds__(256) letterbox_collate_kernel(LetterboxParams p) {
-  const int b = blockIdx.z;
-  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
-  if (x0 >= p.W || y0 >= p.H) return;
-  const ay2_letterbox_image im = p.table[b];
-  const uint8_t* src = p.arena + im.src_offset;
-  const int mode = (im.dst_h == im.src_h && im.dst_w == im.src_w) ? 0 : (im.src_h == 2 * im.dst_h && im.src_w == 2 * im.dst_w) ? 1 : 2;
-
-  uint8_t px[2][4][3];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) px[r][j][c] = p.color[c];
-
-  const int ry = y0 - im.top, rx = x0 - im.left;  // position inside the resized image
-  const bool any_row = ry + 1 >= 0 && ry < im.dst_h;
-  const bool any_col = rx + 3 >= 0 && rx < im.dst_w;
-  if (any_row && any_col) {
-    if (mode == 2) {
-      Tap ct[4], rt[2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ct[j] = column_tap(min(max(rx + j, 0), im.dst_w - 1), im.src_w, im.dst_w);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) rt[r] = row_tap(min(max(ry + r, 0), im.dst_h - 1), im.src_h, im.dst_h);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (ry + r < 0 || ry + r >= im.dst_h) continue;
-        const uint8_t* l0 = src + (size_t)rt[r].s0 * im.src_row_bytes;
-        const uint8_t* l1 = src + (size_t)rt[r].s1 * im.src_row_bytes;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rx + j < 0 || rx + j >= im.dst_w) continue;
-          const int o0 = ct[j].s0 * 3, o1 = ct[j].s1 * 3;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int h0 = (int)__ldg(l0 + o0 + c) * ct[j].c0 + (int)__ldg(l0 + o1 + c) * ct[j].c1;  // horizontal pass
-            const int h1 = (int)__ldg(l1 + o0 + c) * ct[j].c0 + (int)__ldg(l1 + o1 + c) * ct[j].c1;
-            const int v = (((rt[r].c0 * (h0 >> 4)) >> 16) + ((rt[r].c1 * (h1 >> 4)) >> 16) + 2) >> 2;  // vertical pass
-            px[r][j][c] = (uint8_t)min(max(v, 0), 255);
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (ry + r < 0 || ry + r >= im.dst_h) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rx + j < 0 || rx + j >= im.dst_w) continue;
-          if (mode == 0) {
-            const uint8_t* q = src + (size_t)(ry + r) * im.src_row_bytes + (rx + j) * 3;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) px[r][j][c] = __ldg(q + c);
-          } else {  // exact 2 x 2 decimation: area filter
-            const uint8_t* q0 = src + (size_t)(2 * (ry + r)) * im.src_row_bytes + (2 * (rx + j)) * 3;
-            const uint8_t* q1 = q0 + im.src_row_bytes;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              px[r][j][c] = (uint8_t)(((int)__ldg(q0 + c) + (int)__ldg(q0 + 3 + c) + (int)__ldg(q1 + c) + (int)__ldg(q1 + 3 + c) + 2) >> 2);
-          }
-        }
-      }
-    }
-  }
-
+__device__ __forceinline__ void write_block(const LetterboxParams& p, int b, int x0, int y0, const uint8_t (&px)[2][4][3]) {
   if constexpr (KIND == AY2_LB_NCHW_U8) {
     uint8_t* out = static_cast<uint8_t*>(p.out);
 #pragma unroll
     for (int c = 0; c < 3; ++c)  // output channel c (RGB) = source channel 2 - c (BGR)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        uchar4 v = make_uchar4(px[r][0][2 - c], px[r][1][2 - c], px[r][2][2 - c], px[r][3][2 - c]);
+        const uchar4 v = make_uchar4(px[r][0][2 - c], px[r][1][2 - c], px[r][2][2 - c], px[r][3][2 - c]);
         *reinterpret_cast<uchar4*>(out + (((size_t)b * 3 + c) * p.H + y0 + r) * p.W + x0) = v;
       }
   } else {
-    // the stem's space-to-depth image (ay2_space_to_depth): [B, H/2, out_row_pixels, 16] bf16, channel (dy*2+dx)*3 + c
+    // ay2_space_to_depth's layout: [B, H/2, out_row_pixels, 16] bf16, channel (dy*2+dx)*3 + c, 4 zero channels
     uint4* out = static_cast<uint4*>(p.out);
     const size_t opix = ((size_t)b * (p.H >> 1) + (y0 >> 1)) * p.out_row_pixels + (x0 >> 1) + p.out_x_offset;
 #pragma unroll
@@ -165,6 +105,85 @@ __global__ void __launch_bounds__(256) letterbox_collate_kernel(LetterboxParams 
   }
 }
 
+// Two kernels over the same grid, because they want different register budgets: the copy kernel (images that enter at
+// their final size -- the validation set after `_load_image`) is a pure streaming kernel that needs many warps in flight;
+// the interpolating kernel carries six taps per thread. Each exits at once on the other's images.
+template <int KIND, bool RESIZE>
+__global__ void __launch_bounds__(256) letterbox_collate_kernel(LetterboxParams p) {
+  const int b = blockIdx.z;
+  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int y0 = (blockIdx.y * 8 + threadIdx.y) * 2;
+  const ay2_letterbox_image im = p.table[b];
+  const int mode = image_mode(im);
+  if ((mode != LB_COPY) != RESIZE) return;
+  if (x0 >= p.W || y0 >= p.H) return;
+  const uint8_t* src = p.arena + im.src_offset;
+
+  uint8_t px[2][4][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[r][j][c] = p.color[c];
+
+  const int ry = y0 - im.top, rx = x0 - im.left;  // position inside the resized image
+  if (ry + 1 >= 0 && ry < im.dst_h && rx + 3 >= 0 && rx < im.dst_w) {
+    if constexpr (!RESIZE) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (ry + r < 0 || ry + r >= im.dst_h) continue;
+        const uint8_t* q = src + (size_t)(ry + r) * im.src_row_bytes + rx * 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rx + j < 0 || rx + j >= im.dst_w) continue;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) px[r][j][c] = __ldg(q + 3 * j + c);
+        }
+      }
+    } else if (mode == LB_LINEAR) {
+      Tap ct[4], rt[2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ct[j] = column_tap(min(max(rx + j, 0), im.dst_w - 1), im.src_w, im.scale_x);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) rt[r] = row_tap(min(max(ry + r, 0), im.dst_h - 1), im.src_h, im.scale_y);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (ry + r < 0 || ry + r >= im.dst_h) continue;
+        const uint8_t* l0 = src + (size_t)rt[r].s0 * im.src_row_bytes;
+        const uint8_t* l1 = src + (size_t)rt[r].s1 * im.src_row_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rx + j < 0 || rx + j >= im.dst_w) continue;
+          const int o0 = ct[j].s0 * 3, o1 = ct[j].s1 * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int h0 = (int)__ldg(l0 + o0 + c) * ct[j].c0 + (int)__ldg(l0 + o1 + c) * ct[j].c1;  // horizontal pass
+            const int h1 = (int)__ldg(l1 + o0 + c) * ct[j].c0 + (int)__ldg(l1 + o1 + c) * ct[j].c1;
+            const int v = (((rt[r].c0 * (h0 >> 4)) >> 16) + ((rt[r].c1 * (h1 >> 4)) >> 16) + 2) >> 2;  // vertical pass
+            px[r][j][c] = (uint8_t)min(max(v, 0), 255);
+          }
+        }
+      }
+    } else {  // LB_AREA
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (ry + r < 0 || ry + r >= im.dst_h) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rx + j < 0 || rx + j >= im.dst_w) continue;
+          const uint8_t* q0 = src + (size_t)(2 * (ry + r)) * im.src_row_bytes + (2 * (rx + j)) * 3;
+          const uint8_t* q1 = q0 + im.src_row_bytes;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            px[r][j][c] = (uint8_t)(((int)__ldg(q0 + c) + (int)__ldg(q0 + 3 + c) + (int)__ldg(q1 + c) + (int)__ldg(q1 + 3 + c) + 2) >> 2);
+        }
+      }
+    }
+  }
+  write_block<KIND>(p, b, x0, y0, px);
+}
+
 // LoadImagesAndLabels.collate_fn (data_loader.py:905-907): label column 0 = index of the image the row belongs to
 __global__ void collate_labels_kernel(float* labels, const int* offsets, int batch, int total) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,9 +200,9 @@ __global__ void collate_labels_kernel(float* labels, const int* offsets, int bat
 
 using namespace ay2;
 
-extern "C" int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t out_h,
-                                     int32_t out_w, uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels,
-                                     int32_t out_x_offset, float scale, void* stream) {
+extern "C" int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t kinds,
+                                     int32_t out_h, int32_t out_w, uint32_t color_bgr, int32_t out_kind, void* out,
+                                     int32_t out_row_pixels, int32_t out_x_offset, float scale, void* stream) {
   AY2_REQUIRE(arena && table && out && batch >= 0, "ay2_letterbox_collate: bad arguments");
   AY2_REQUIRE(out_h > 0 && out_w > 0 && out_h % 2 == 0 && out_w % 4 == 0,
               "ay2_letterbox_collate: the network input must have an even height and a width that is a multiple of 4 (got %dx%d)", out_h, out_w);
@@ -192,18 +211,26 @@ extern "C" int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_i
     AY2_REQUIRE(out_x_offset >= 0 && out_row_pixels >= out_w / 2 + out_x_offset, "ay2_letterbox_collate: output row too short");
   AY2_REQUIRE(batch <= 65535, "ay2_letterbox_collate: batch %d too large", batch);
   if (batch == 0) return AY2_OK;
+  if ((kinds & (AY2_LB_HAS_COPY | AY2_LB_HAS_RESIZE)) == 0) kinds = AY2_LB_HAS_COPY | AY2_LB_HAS_RESIZE;  // unknown: run both
   LetterboxParams p;
   p.arena = arena, p.table = table, p.out = out, p.H = out_h, p.W = out_w;
   p.out_row_pixels = out_row_pixels, p.out_x_offset = out_x_offset, p.scale = scale;
   p.color[0] = color_bgr & 255u, p.color[1] = (color_bgr >> 8) & 255u, p.color[2] = (color_bgr >> 16) & 255u;
   const dim3 block(32, 8), grid(ceil_div(out_w, 128), ceil_div(out_h, 16), batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (out_kind == AY2_LB_NCHW_U8)
-    letterbox_collate_kernel<AY2_LB_NCHW_U8><<<grid, block, 0, st>>>(p);
-  else
-    letterbox_collate_kernel<AY2_LB_S2D_BF16><<<grid, block, 0, st>>>(p);
-  AY2_CHECK_LAUNCH();
-  count_launch();
+  const bool u8 = out_kind == AY2_LB_NCHW_U8;
+  if (kinds & AY2_LB_HAS_COPY) {
+    if (u8) letterbox_collate_kernel<AY2_LB_NCHW_U8, false><<<grid, block, 0, st>>>(p);
+    else letterbox_collate_kernel<AY2_LB_S2D_BF16, false><<<grid, block, 0, st>>>(p);
+    AY2_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (kinds & AY2_LB_HAS_RESIZE) {
+    if (u8) letterbox_collate_kernel<AY2_LB_NCHW_U8, true><<<grid, block, 0, st>>>(p);
+    else letterbox_collate_kernel<AY2_LB_S2D_BF16, true><<<grid, block, 0, st>>>(p);
+    AY2_CHECK_LAUNCH();
+    count_launch();
+  }
   return AY2_OK;
 }
 

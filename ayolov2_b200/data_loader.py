@@ -1,4 +1,4 @@
-"""Input side of the path on the GPU: letterbox + BGR->RGB + HWC->CHW + collate in one launch.
+"""Input side of the path on the GPU: letterbox + BGR->RGB + HWC->CHW + collate of a whole batch.
 
 The reference does this per image on the host, inside the Dataset (scripts/data_loader/data_loader.py):
   `LoadImages.__getitem__` (:373-393)  -> `_letterbox` (:395-459, cv2.resize + cv2.copyMakeBorder) -> transpose + channel
@@ -9,7 +9,8 @@ Here the Dataset hands over the LOADED images as they are (ragged HWC BGR uint8)
     byte arena (pinned on request). It computes the per-image geometry (`letterbox_geometry`: the scalar arithmetic of
     :428-455) and the reference's `shapes` tuples. Usable as a DataLoader `collate_fn` (pure CPU, picklable result).
   * `PackedBatch.to_device(...)` -- ONE host->device copy of the arena (the raw pixels are fewer bytes than the padded
-    batch) and ONE kernel (`ay2_letterbox_collate`, csrc/letterbox.cu) that resizes (cv2's 8-bit INTER_LINEAR, bit-exact),
+    batch) and one call (`ay2_letterbox_collate`, csrc/letterbox.cu: a launch for the images that
+    enter at their final size, one for those that are resized) that resizes (cv2's 8-bit INTER_LINEAR, bit-exact),
     pads, flips the channels and writes either the reference's collated uint8 NCHW tensor or directly the bf16
     space-to-depth image the stem convolution reads (then `prepare_img`'s /255 and `ay2_space_to_depth` are fused in).
 
@@ -28,9 +29,10 @@ import torch
 from . import _lib
 
 LB_NCHW_U8, LB_S2D_BF16 = 0, 1
-_REC = np.dtype([("src_offset", "<i8"), ("src_h", "<i4"), ("src_w", "<i4"), ("src_row_bytes", "<i4"), ("dst_h", "<i4"),
+LB_HAS_COPY, LB_HAS_RESIZE = 1, 2
+_REC = np.dtype([("src_offset", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("src_h", "<i4"), ("src_w", "<i4"), ("src_row_bytes", "<i4"), ("dst_h", "<i4"),
                  ("dst_w", "<i4"), ("top", "<i4"), ("left", "<i4"), ("reserved", "<i4")])  # ay2_letterbox_image
-assert _REC.itemsize == 40
+assert _REC.itemsize == 56
 
 
 def letterbox_geometry(shape: Sequence[int], new_shape: Sequence[int], auto: bool = True, scale_fill: bool = False,
@@ -67,6 +69,7 @@ class PackedBatch:
     ratios: tuple                # per image (ratio_w, ratio_h) returned by _letterbox
     color: Tuple[int, int, int] = (114, 114, 114)
     paths: tuple = ()
+    kinds: int = 0               # LB_HAS_COPY | LB_HAS_RESIZE: which kernels the batch needs
 
     @property
     def table_bytes(self) -> int:
@@ -113,7 +116,7 @@ def _launch(pb: PackedBatch, dev_arena: torch.Tensor, kind: int, out_ptr: int, r
     H, W = pb.out_shape
     base = dev_arena.data_ptr()
     color = pb.color[0] | (pb.color[1] << 8) | (pb.color[2] << 16)
-    _lib.check(_lib.load().ay2_letterbox_collate(base + pb.table_bytes, base, pb.batch, H, W, C.c_uint32(color), kind, out_ptr,
+    _lib.check(_lib.load().ay2_letterbox_collate(base + pb.table_bytes, base, pb.batch, pb.kinds, H, W, C.c_uint32(color), kind, out_ptr,
                                                  row_pixels, x_offset, float(scale), _lib.current_stream_ptr()),
                "ay2_letterbox_collate")
 
@@ -132,7 +135,7 @@ def pack_batch(images: Sequence[np.ndarray], new_shape: Sequence[int], auto: boo
     B = len(images)
     rec = np.zeros(B, dtype=_REC)
     off = (B * _REC.itemsize + 15) & ~15
-    shapes, ratios = [], []
+    shapes, ratios, kinds = [], [], 0
     for i, im in enumerate(images):
         if not (isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3):
             raise TypeError(f"pack_batch: image {i} must be a uint8 HWC array with 3 channels")
@@ -140,7 +143,10 @@ def pack_batch(images: Sequence[np.ndarray], new_shape: Sequence[int], auto: boo
         (uw, uh), ratio, (dw, dh), (top, bottom, left, right) = letterbox_geometry((h, w), (H, W), False, scale_fill, scale_up, stride)
         if (uh + top + bottom, uw + left + right) != (H, W):
             raise ValueError(f"pack_batch: image {i} ({h}x{w}) letterboxes to {uh + top + bottom}x{uw + left + right}, not {H}x{W}")
-        rec[i] = (off - B * _REC.itemsize, h, w, 3 * w, uh, uw, top, left, 0)
+        # cv2's step per destination pixel, in its own precision and order (resize.cpp: scale = 1. / inv_scale, both double)
+        sx, sy = 1.0 / (float(uw) / float(w)), 1.0 / (float(uh) / float(h))
+        rec[i] = (off - B * _REC.itemsize, sx, sy, h, w, 3 * w, uh, uw, top, left, 0)
+        kinds |= LB_HAS_COPY if (uh, uw) == (h, w) else LB_HAS_RESIZE
         off = (off + 3 * h * w + 15) & ~15
         h0, w0 = orig_shapes[i] if orig_shapes is not None else (h, w)
         shapes.append(((h0, w0), ((h / h0, w / w0), (dw, dh))))
@@ -155,7 +161,7 @@ def pack_batch(images: Sequence[np.ndarray], new_shape: Sequence[int], auto: boo
     for i, im in enumerate(images):
         start = B * _REC.itemsize + int(rec[i]["src_offset"])
         host[start:start + im.size] = np.ascontiguousarray(im).reshape(-1)
-    return PackedBatch(arena, B, (H, W), tuple(shapes), tuple(ratios), tuple(int(c) for c in color), tuple(paths))
+    return PackedBatch(arena, B, (H, W), tuple(shapes), tuple(ratios), tuple(int(c) for c in color), tuple(paths), kinds)
 
 
 def collate_fn(batch: List[tuple], new_shape: Sequence[int] = (640, 640), **kw):

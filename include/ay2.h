@@ -307,20 +307,26 @@ int ay2_nms_batched_scaled(const float* pred, const ay2_nms_params* p, const uin
  *   out   : AY2_LB_NCHW_U8  -> uint8 [batch][3][out_h][out_w] RGB (the reference's collated tensor), bit-exact with cv2
  *           AY2_LB_S2D_BF16 -> bf16 [batch][out_h/2][out_row_pixels][16] at column offset out_x_offset, value * scale
  *                              (identical to ay2_space_to_depth of the uint8 tensor)
- *   color_bgr : border colour, b | g << 8 | r << 16 (the reference: 114, 114, 114). out_h even, out_w % 4 == 0. */
+ *   color_bgr : border colour, b | g << 8 | r << 16 (the reference: 114, 114, 114). out_h even, out_w % 4 == 0.
+ *   kinds : which kinds of image the table holds (AY2_LB_HAS_*; 0 = unknown). Images that enter at their final size and
+ *           images that are resized run in separate launches over the same grid (different register budgets). */
 #define AY2_LB_NCHW_U8 0
 #define AY2_LB_S2D_BF16 1
+#define AY2_LB_HAS_COPY 1
+#define AY2_LB_HAS_RESIZE 2
 typedef struct ay2_letterbox_image {
   int64_t src_offset;     /* byte offset of the image inside `arena` */
+  double scale_x;         /* 1.0 / ((double)dst_w / src_w): cv2's source step per destination pixel */
+  double scale_y;         /* 1.0 / ((double)dst_h / src_h) */
   int32_t src_h, src_w;   /* the loaded image */
   int32_t src_row_bytes;  /* >= 3 * src_w */
   int32_t dst_h, dst_w;   /* new_unpad (h, w) */
   int32_t top, left;      /* border above / left of the resized image */
   int32_t reserved;
-} ay2_letterbox_image;    /* 40 bytes */
-int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t out_h, int32_t out_w,
-                          uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels, int32_t out_x_offset,
-                          float scale, void* stream);
+} ay2_letterbox_image;    /* 56 bytes */
+int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t kinds, int32_t out_h,
+                          int32_t out_w, uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels,
+                          int32_t out_x_offset, float scale, void* stream);
 /* LoadImagesAndLabels.collate_fn (data_loader.py:905-909): labels fp32 [total][6] (already concatenated), offsets int32
  * [batch + 1] (row range of every image, DEVICE): writes the image index into column 0. */
 int ay2_collate_labels(float* labels, const int32_t* offsets, int32_t batch, int32_t total, void* stream);

@@ -52,6 +52,9 @@ def test_letterbox_collate_equals_oracle_ragged_shapes(new_shape):
         bad = [i for i in range(len(imgs)) if not np.array_equal(got[i], ref[i])]
         assert not bad, f"images {[(i, shapes[i]) for i in bad]} differ ({kw})"
         assert pb.shapes == ref_shapes
+        import dataclasses
+        unknown = dataclasses.replace(pb, kinds=0)  # a C caller that does not classify its images: both kernels run
+        assert np.array_equal(unknown.to_device("cuda").cpu().numpy(), ref)
 
 
 def test_fused_space_to_depth_equals_two_step_path():
