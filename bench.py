@@ -381,6 +381,75 @@ def bench_nms_synthetic(dev, steps: int = 20):
             "config": "(64, 25200, 85) fp32, Bernoulli(0.08) x U(0.25, 1) objectness, 200 box clusters / image, conf 0.25 iou 0.45"}
 
 
+def bench_input_side(det, dev, steps: int = 20):
+    """the loader's letterbox + channel flip + collate (scripts/data_loader/data_loader.py:380-393,
+    461-477) on the GPU. (1) the kernel alone, fused into the stem's space-to-depth input, against the HBM roofline;
+    (2) end to end through Detector.submit_packed from LOADED images in pinned host memory (ragged HWC BGR uint8, long side
+    640 like `_load_image` leaves them), next to the CPU oracle's letterbox + collate of the same images."""
+    import dataclasses
+
+    import numpy as np
+    import torch
+
+    from ayolov2_b200 import data_loader as dl
+    from ayolov2_b200 import ops
+    from oracle import input_oracle
+
+    rng = np.random.default_rng(0)
+    out = {}
+    # validation-like mix: long side 640 (3:4, 4:3, 2:3 aspect ratios and squares), a quarter smaller images that are up-scaled
+    def shapes_of(kind):
+        res = []
+        for i in range(BATCH):
+            if kind == "copy" or (kind == "val" and i % 4):
+                res.append([(640, 480), (480, 640), (640, 428), (428, 640), (640, 640)][i % 5])
+            else:
+                res.append((int(rng.integers(240, 500)), int(rng.integers(240, 600))))
+        return res
+    peak = _peaks().get("hbm_gbs") or 6532.2
+    s2d = [ops.ActView(torch.zeros_like(det.engine.b.s2d_view.buf), 0, 16) for _ in range(2)]
+    for kind in ("copy", "resize", "val"):
+        shp = shapes_of(kind)
+        imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shp]
+        pbs = [dl.pack_batch(imgs[k:] + imgs[:k], (H, W), pin=True) for k in (0, 1)]
+        dpb = [dataclasses.replace(pb, arena=pb.arena.to(dev)) for pb in pbs]
+        reps = 10
+
+        def body():
+            for i in range(reps):  # two input / output sets alternate; one launch moves > 126 MB (L2)
+                dpb[i & 1].to_space_to_depth(s2d[i & 1], 1.0 / 255.0, x_offset=1)
+        ms = time_graph(body, steps) / reps
+        src = sum(3 * h * w for h, w in shp)
+        wr = BATCH * H * W * 8
+        out[f"kernel_{kind}"] = {"ms": ms, "algorithmic_bytes": src + wr, "achieved_gbs": (src + wr) / ms / 1e6,
+                                 "frac_of_hbm_peak": (src + wr) / ms / 1e6 / peak}
+        if kind != "val":
+            continue
+        # end to end from loaded images
+        for i in range(3):
+            det.collect(det.submit_packed(pbs[i & 1]))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pending = []
+        for i in range(steps):
+            pending.append(det.submit_packed(pbs[i & 1]))
+            if len(pending) > det.slots - 1:
+                det.collect(pending.pop(0))
+        while pending:
+            det.collect(pending.pop(0))
+        dt = time.perf_counter() - t0
+        out["e2e_from_loaded_images"] = {"images_per_s": BATCH * steps / dt, "ms_per_step": dt * 1000 / steps,
+                                         "h2d_bytes_per_step": int(pbs[0].arena.numel()),
+                                         "padded_batch_bytes": BATCH * 3 * H * W}
+        t0 = time.perf_counter()
+        n = 16
+        input_oracle.load_and_collate(imgs[:n], (H, W))
+        dt = time.perf_counter() - t0
+        out["cpu_oracle"] = {"images_per_s": n / dt, "cores": 1, "kind": "port", "sample": f"{n} images of the same mix, numpy restatement of _letterbox + collate_fn"}
+    out["config"] = f"{BATCH} loaded images -> ({BATCH}, 3, {H}, {W}); 'val': long side 640 mixed aspect ratios, one in four up-scaled; fused into the stem's space-to-depth input (bf16, /255)"
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -577,6 +646,10 @@ def main() -> None:
                 extras["tucker"] = bench_tucker(20, dev)
             except Exception as e:
                 extras["tucker"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            try:
+                extras["input_side"] = bench_input_side(det, dev)
+            except Exception as e:
+                extras["input_side"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
                 extras["nms_synthetic"] = bench_nms_synthetic(dev)
                 extras["nms_synthetic"]["share_of_fwd_plus_nms"] = extras["nms_synthetic"]["ms_dense_3_launches"] / (
