@@ -16,7 +16,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libay2.so"
 HASH_MARK = b"AY2_SOURCE_HASH="
 
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "precise.cu", "train_pointwise.cu", "nms.cu", "nms_variants.cu", "loss.cu", "val_match.cu", "letterbox.cu"]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_chain.cu", "conv_wgrad.cu", "pointwise.cu", "precise.cu", "train_pointwise.cu", "nms.cu", "nms_variants.cu", "loss.cu", "val_match.cu", "letterbox.cu", "pseudo_labels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

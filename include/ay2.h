@@ -331,6 +331,15 @@ int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table
  * [batch + 1] (row range of every image, DEVICE): writes the image index into column 0. */
 int ay2_collate_labels(float* labels, const int32_t* offsets, int32_t batch, int32_t total, void* stream);
 
+/* Knowledge-distillation pseudo-labels (the KD caller of the NMS kernels): replaces
+ * SoftTeacherTrainer.prepare_labels_for_augmention / filter_invalid and the label assembly of get_pseudo_labeled_batch
+ * (scripts/train/kd_trainer.py:385-397,436-487) + xyxy2xywh with its validity correction (scripts/utils/general.py:250-295).
+ * det / counts: the NMS output ([batch][max_det][6] xyxy conf cls, [batch]). Keeps score > score_thr and (use_min_size)
+ * width, height > min_size; labels: fp32 [batch * max_det][6] = image, class, x, y, w, h (normalised by width / height), rows in
+ * image order then detection order; out_counts: int32 [batch + 1] = labels per image, then the total. */
+int ay2_pseudo_labels(const float* det, const int32_t* counts, int32_t batch, int32_t max_det, float score_thr, float min_size,
+                      int32_t use_min_size, float width, float height, float* labels, int32_t* out_counts, void* stream);
+
 /* Validation statistics: replaces the per-image host loop of YoloValidator.statistics_per_image / process_batch
  * (scripts/utils/train_utils.py:294-401) for a whole batch. det / counts: the NMS output ([batch][max_det][6], [batch]);
  * labels: fp32 [nt][6] = image, class, box; meta == NULL: boxes are xyxy in the detections' coordinates (the plain

@@ -102,3 +102,25 @@ def load_data_loader():
     import scripts.data_loader.data_loader as dl  # type: ignore
 
     return dl
+
+
+class _AnyAttr(types.ModuleType):
+    """A stub module whose every attribute is an empty class (for `from albumentations import DualTransform` etc.)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {})
+
+
+def load_kd_trainer():
+    """The reference's scripts/train/kd_trainer.py, unmodified (SoftTeacherTrainer.prepare_labels_for_augmention / filter_invalid
+    are plain functions of their arguments). Two more absent packages are stubbed: `albumentations` (strong augmentation, not
+    on this path) and `wandb`."""
+    load_data_loader()
+    for name in ("albumentations", "wandb"):
+        if name not in sys.modules:
+            sys.modules[name] = _AnyAttr(name)
+    import scripts.train.kd_trainer as kd  # type: ignore
+
+    return kd
