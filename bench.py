@@ -381,7 +381,7 @@ def bench_nms_synthetic(dev, steps: int = 20):
             "config": "(64, 25200, 85) fp32, Bernoulli(0.08) x U(0.25, 1) objectness, 200 box clusters / image, conf 0.25 iou 0.45"}
 
 
-def bench_input_side(det, dev, steps: int = 20):
+def bench_input_side(det, dev, rank: int, world: int, barrier, max_over_ranks, steps: int = 30):
     """the loader's letterbox + channel flip + collate (scripts/data_loader/data_loader.py:380-393,
     461-477) on the GPU. (1) the kernel alone, fused into the stem's space-to-depth input, against the HBM roofline;
     (2) end to end through Detector.submit_packed from LOADED images in pinned host memory (ragged HWC BGR uint8, long side
@@ -425,22 +425,39 @@ def bench_input_side(det, dev, steps: int = 20):
                                  "frac_of_hbm_peak": (src + wr) / ms / 1e6 / peak}
         if kind != "val":
             continue
-        # end to end from loaded images
-        for i in range(3):
-            det.collect(det.submit_packed(pbs[i & 1]))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pending = []
-        for i in range(steps):
-            pending.append(det.submit_packed(pbs[i & 1]))
-            if len(pending) > det.slots - 1:
-                det.collect(pending.pop(0))
-        while pending:
-            det.collect(pending.pop(0))
-        dt = time.perf_counter() - t0
-        out["e2e_from_loaded_images"] = {"images_per_s": BATCH * steps / dt, "ms_per_step": dt * 1000 / steps,
-                                         "h2d_bytes_per_step": int(pbs[0].arena.numel()),
-                                         "padded_batch_bytes": BATCH * 3 * H * W}
+        # end to end from loaded images. The two collectives below run exactly once on every rank whatever happens locally
+        # (a rank that failed reports an infinite time instead of leaving the others in a barrier)
+        err, dt_local = None, float("inf")
+        try:
+            for i in range(3):
+                det.collect(det.submit_packed(pbs[i & 1]))
+            torch.cuda.synchronize()
+        except Exception as e:
+            err = e
+        barrier()  # every rank stages its own batches at the same time (the host -> device link is the shared resource)
+        if err is None:
+            try:
+                t0 = time.perf_counter()
+                pending = []
+                for i in range(steps):
+                    pending.append(det.submit_packed(pbs[i & 1]))
+                    if len(pending) > det.slots - 1:
+                        det.collect(pending.pop(0))
+                while pending:
+                    det.collect(pending.pop(0))
+                dt_local = time.perf_counter() - t0
+            except Exception as e:
+                err = e
+        dt = max_over_ranks(dt_local * 1000.0) / 1000.0
+        if err is not None or dt == float("inf"):
+            out["e2e_from_loaded_images"] = {"error": f"{type(err).__name__}: {err}"[:200] if err else "another rank failed"}
+        else:
+            out["e2e_from_loaded_images"] = {"images_per_s": world * BATCH * steps / dt, "ms_per_step": dt * 1000 / steps, "n_gpus": world,
+                                             "h2d_bytes_per_step": int(pbs[0].arena.numel()),
+                                             "padded_batch_bytes": BATCH * 3 * H * W,
+                                             "h2d_gbs_per_rank": int(pbs[0].arena.numel()) / (dt / steps) / 1e9}
+        if rank != 0:
+            continue
         t0 = time.perf_counter()
         n = 16
         input_oracle.load_and_collate(imgs[:n], (H, W))
@@ -641,15 +658,15 @@ def main() -> None:
             except Exception as e:
                 extras["yolov5l_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
+        try:  # all ranks: the end-to-end part measures the shared host -> device path
+            extras["input_side"] = bench_input_side(det, dev, rank, world, barrier, max_over_ranks)
+        except Exception as e:
+            extras["input_side"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if rank == 0:
             try:
                 extras["tucker"] = bench_tucker(20, dev)
             except Exception as e:
                 extras["tucker"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-            try:
-                extras["input_side"] = bench_input_side(det, dev)
-            except Exception as e:
-                extras["input_side"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
                 extras["nms_synthetic"] = bench_nms_synthetic(dev)
                 extras["nms_synthetic"]["share_of_fwd_plus_nms"] = extras["nms_synthetic"]["ms_dense_3_launches"] / (
