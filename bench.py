@@ -646,33 +646,31 @@ def main() -> None:
 
     # ------------------------------------------------------------------ the other BASELINE configs (extras)
     extras = {}
-    if not args.no_extras:
+    only = [x for x in os.environ.get("AY2_BENCH_EXTRAS", "").split(",") if x]  # e.g. AY2_BENCH_EXTRAS=input_side (same on every rank)
+    want = lambda name: not only or name in only  # noqa: E731
+    def extra(name, fn, ranks_all=True):
+        """Run one extra; an extra must never take the headline line down."""
+        if args.no_extras or not want(name) or (not ranks_all and rank != 0):
+            return
         try:
-            extras["train_step"] = bench_train_step("yolov5s", 128, 640, 20, 5, rank, world, dev, barrier, max_over_ranks)
-        except Exception as e:  # an extra must never take the headline line down
-            extras["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        torch.cuda.empty_cache()
-        if world == 8 or os.environ.get("AY2_BENCH_YOLOV5L") == "1":
-            try:
-                extras["yolov5l_train"] = bench_train_step("yolov5l", 32, 640, 10, 4, rank, world, dev, barrier, max_over_ranks)
-            except Exception as e:
-                extras["yolov5l_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-            torch.cuda.empty_cache()
-        try:  # all ranks: the end-to-end part measures the shared host -> device path
-            extras["input_side"] = bench_input_side(det, dev, rank, world, barrier, max_over_ranks)
+            extras[name] = fn()
         except Exception as e:
-            extras["input_side"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        if rank == 0:
-            try:
-                extras["tucker"] = bench_tucker(20, dev)
-            except Exception as e:
-                extras["tucker"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-            try:
-                extras["nms_synthetic"] = bench_nms_synthetic(dev)
-                extras["nms_synthetic"]["share_of_fwd_plus_nms"] = extras["nms_synthetic"]["ms_dense_3_launches"] / (
-                    ms_per_step + extras["nms_synthetic"]["ms_dense_3_launches"])
-            except Exception as e:
-                extras["nms_synthetic"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    extra("train_step", lambda: bench_train_step("yolov5s", 128, 640, 20, 5, rank, world, dev, barrier, max_over_ranks))
+    if world == 8 or os.environ.get("AY2_BENCH_YOLOV5L") == "1":
+        extra("yolov5l_train", lambda: bench_train_step("yolov5l", 32, 640, 10, 4, rank, world, dev, barrier, max_over_ranks))
+    # all ranks: the end-to-end part measures the shared host -> device path
+    extra("input_side", lambda: bench_input_side(det, dev, rank, world, barrier, max_over_ranks))
+    extra("tucker", lambda: bench_tucker(20, dev), ranks_all=False)
+
+    def nms_synth():
+        r = bench_nms_synthetic(dev)
+        r["share_of_fwd_plus_nms"] = r["ms_dense_3_launches"] / (ms_per_step + r["ms_dense_3_launches"])
+        return r
+    extra("nms_synthetic", nms_synth, ranks_all=False)
+    if not args.no_extras:
         barrier()
 
     cpu = None
