@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 from ayolov2_b200 import data_loader as dl  # noqa: E402
 from ayolov2_b200 import ops  # noqa: E402
 from oracle import input_oracle  # noqa: E402
+from _parity import record  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "input_golden.npz")
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
@@ -31,6 +32,9 @@ def test_letterbox_collate_equals_reference_golden(ci):
     out = pb.to_device("cuda")
     torch.cuda.synchronize()
     assert out.dtype == torch.uint8 and tuple(out.shape) == g[f"c{ci}_batch"].shape
+    diff = np.abs(out.cpu().numpy().astype(np.int32) - g[f"c{ci}_batch"].astype(np.int32))
+    record(f"input/letterbox_collate_vs_reference_golden_c{ci}", max_abs_diff=int(diff.max()), mismatching_bytes=int((diff > 0).sum()),
+           bytes=int(diff.size))
     assert np.array_equal(out.cpu().numpy(), g[f"c{ci}_batch"])
     geo = g[f"c{ci}_geo"]
     for i in range(len(imgs)):
@@ -50,6 +54,8 @@ def test_letterbox_collate_equals_oracle_ragged_shapes(new_shape):
         pb = dl.pack_batch(imgs, new_shape, **kw)
         got = pb.to_device("cuda").cpu().numpy()
         bad = [i for i in range(len(imgs)) if not np.array_equal(got[i], ref[i])]
+        record(f"input/letterbox_vs_oracle_{new_shape[0]}x{new_shape[1]}_{'_'.join(kw) or 'default'}", images=len(imgs),
+               mismatching_bytes=int((got != ref).sum()), bytes=int(ref.size))
         assert not bad, f"images {[(i, shapes[i]) for i in bad]} differ ({kw})"
         assert pb.shapes == ref_shapes
         import dataclasses

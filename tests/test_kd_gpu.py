@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 from make_golden_kd import CASES  # noqa: E402
 from ayolov2_b200 import kd  # noqa: E402
 from oracle import kd_oracle  # noqa: E402
+from _parity import record  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "kd_golden.npz")
 
@@ -44,7 +45,10 @@ def test_full_size_buffer_equals_oracle():
     for thr, ms in ((0.25, 2.0), (0.0, None), (0.999, 0.0)):
         labels, per_image = kd.pseudo_labels_from_detections(det.cuda(), counts.cuda(), (640, 640), thr, ms)
         want = kd_oracle.pseudo_labels(preds, (640, 640), thr, ms)
-        assert labels.shape == want.shape and np.array_equal(labels.cpu().numpy(), want)
+        assert labels.shape == want.shape
+        record(f"kd/pseudo_labels_64x300_thr{thr}_min{ms}", labels=int(len(want)),
+               max_abs_diff=float(np.abs(labels.cpu().numpy() - want).max()) if len(want) else 0.0)
+        assert np.array_equal(labels.cpu().numpy(), want)
         assert per_image.tolist() == [int((want[:, 0] == i).sum()) for i in range(B)]
 
 
