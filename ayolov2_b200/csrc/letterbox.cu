@@ -184,6 +184,29 @@ __global__ void __launch_bounds__(256) letterbox_collate_kernel(LetterboxParams 
   write_block<KIND>(p, b, x0, y0, px);
 }
 
+// YoloTrainer.multi_scale (scripts/train/yolo_trainer.py:223-248) with prepare_img (abstract_trainer.py:252-261) fused in:
+// out = F.interpolate(in * pre, size, mode="bilinear", align_corners=False) as fp32 NCHW, in the operation order of
+// torch's own kernel (source index = max(ratio * (dst + 0.5) - 0.5, 0), ratio = in / out in fp32; lambda = frac;
+// value = l0h * (l0w * v00 + l1w * v01) + l1h * (l0w * v10 + l1w * v11)). A thread owns one output pixel, three channels.
+template <typename T>
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const T* __restrict__ in, int H, int W, float* __restrict__ out,
+                                                              int H2, int W2, float pre, float rh, float rw, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int x2 = (int)(idx % W2), y2 = (int)((idx / W2) % H2), b = (int)(idx / ((long long)W2 * H2));
+    const float h1r = fmaxf(rh * ((float)y2 + 0.5f) - 0.5f, 0.0f), w1r = fmaxf(rw * ((float)x2 + 0.5f) - 0.5f, 0.0f);
+    const int h1 = (int)h1r, w1 = (int)w1r;
+    const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
+    const float h1l = h1r - (float)h1, h0l = 1.0f - h1l, w1l = w1r - (float)w1, w0l = 1.0f - w1l;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* p = in + (((size_t)b * 3 + c) * H + h1) * W + w1;
+      const float v00 = (float)p[0] * pre, v01 = (float)p[w1p] * pre;
+      const float v10 = (float)p[(size_t)h1p * W] * pre, v11 = (float)p[(size_t)h1p * W + w1p] * pre;
+      out[(((size_t)b * 3 + c) * H2 + y2) * W2 + x2] = h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11);
+    }
+  }
+}
+
 // LoadImagesAndLabels.collate_fn (data_loader.py:905-907): label column 0 = index of the image the row belongs to
 __global__ void collate_labels_kernel(float* labels, const int* offsets, int batch, int total) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,6 +261,26 @@ extern "C" int ay2_collate_labels(float* labels, const int32_t* offsets, int32_t
   AY2_REQUIRE(batch >= 0 && total >= 0 && (total == 0 || (labels && offsets && batch > 0)), "ay2_collate_labels: bad arguments");
   if (total == 0) return AY2_OK;
   collate_labels_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(labels, offsets, batch, total);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_resize_bilinear(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float pre_scale, float* out,
+                                   int32_t out_h, int32_t out_w, void* stream) {
+  AY2_REQUIRE(img && out && batch >= 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0, "ay2_resize_bilinear: bad arguments");
+  AY2_REQUIRE(dtype == AY2_DT_U8 || dtype == AY2_DT_F32, "ay2_resize_bilinear: dtype %d unsupported", dtype);
+  const long long total = (long long)batch * out_h * out_w;
+  if (total == 0) return AY2_OK;
+  const float rh = (float)h / (float)out_h, rw = (float)w / (float)out_w;  // area_pixel_compute_scale, align_corners = false
+  const int threads = 256;
+  const long long want = (total + threads - 1) / threads;
+  const int blocks = (int)(want < 148ll * 32 ? want : 148ll * 32);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == AY2_DT_U8)
+    resize_bilinear_kernel<uint8_t><<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(img), h, w, out, out_h, out_w, pre_scale, rh, rw, total);
+  else
+    resize_bilinear_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(img), h, w, out, out_h, out_w, pre_scale, rh, rw, total);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -313,6 +313,17 @@ def space_to_depth(img: torch.Tensor, out: ActView, scale: float, x_offset: int 
                                               _lib.current_stream_ptr()), "ay2_space_to_depth")
 
 
+def resize_bilinear(img: torch.Tensor, out: torch.Tensor, pre_scale: float = 1.0) -> None:
+    """out (fp32 NCHW, any size) = F.interpolate(img * pre_scale, out.shape[2:], mode="bilinear", align_corners=False);
+    img NCHW uint8 / fp32. `YoloTrainer.multi_scale` + `prepare_img` in one pass (yolo_trainer.py:223-248)."""
+    assert img.is_cuda and out.is_cuda and img.is_contiguous() and out.is_contiguous() and out.dtype == torch.float32
+    assert img.dim() == 4 and img.shape[1] == 3 and out.shape[:2] == img.shape[:2]
+    dt = {torch.uint8: _lib.DT_U8, torch.float32: _lib.DT_F32}[img.dtype]
+    _lib.check(_lib.load().ay2_resize_bilinear(img.data_ptr(), dt, img.shape[0], img.shape[2], img.shape[3], float(pre_scale),
+                                               out.data_ptr(), out.shape[2], out.shape[3], _lib.current_stream_ptr()),
+               "ay2_resize_bilinear")
+
+
 def sppf_pool(x: ActView, o1: ActView, o2: ActView, o3: ActView, ks: Sequence[int]) -> None:
     assert x.cstride == o1.cstride == o2.cstride == o3.cstride and x.buf is o1.buf
     _lib.check(_lib.load().ay2_sppf_pool(x.ptr(), x.B, x.H, x.W, x.c, x.cstride, ks[0], ks[1], ks[2], o1.ptr(),

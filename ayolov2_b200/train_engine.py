@@ -643,7 +643,11 @@ class TrainEngine:
         # the most recent forward. The generation counter lets TrainFunction.backward detect fwd/fwd/bwd/bwd patterns
         # (two views summed into one loss, KD double passes) instead of silently differentiating the wrong activations.
         self.generation = getattr(self, "generation", 0) + 1
-        self.static_in.copy_(img)
+        if isinstance(img, ResizedInput):
+            # multi_scale: the bilinear resize (and prepare_img's / 255) writes the graph's static input directly
+            ops.resize_bilinear(img.src, self.static_in, img.pre_scale)
+        else:
+            self.static_in.copy_(img)
         self._img = self.static_in
         self._repack_sync_table()
         self._run_or_replay("fwd", self._forward_body)
@@ -718,6 +722,40 @@ class TrainFunction(torch.autograd.Function):
         return (None, None) + grads
 
 
+class ResizedInput:
+    """A training batch that still has to be resized: `src` NCHW uint8 / fp32 on the device, multiplied by `pre_scale` and
+    bilinearly resized to `size` (H, W) while it is written into the engine's input (YoloTrainer.multi_scale,
+    scripts/train/yolo_trainer.py:223-248, with prepare_img fused in)."""
+
+    def __init__(self, src: torch.Tensor, size: Sequence[int], pre_scale: float = 1.0) -> None:
+        assert src.is_cuda and src.dim() == 4 and src.shape[1] == 3 and src.dtype in (torch.uint8, torch.float32)
+        self.src, self.size, self.pre_scale = src.contiguous(), (int(size[0]), int(size[1])), float(pre_scale)
+
+
+def forward_train_resized(model: nn.Module, x: torch.Tensor, size: Sequence[int], pre_scale: float = 1.0) -> List[torch.Tensor]:
+    """forward_train(model, F.interpolate(x * pre_scale, size, mode="bilinear", align_corners=False)) without the three
+    intermediate fp32 images (scaled copy, interpolated copy, copy into the engine's static input)."""
+    inp = ResizedInput(x, size, pre_scale)
+    eng = _engine_for(model, x.shape[0], inp.size[0], inp.size[1], x.device, torch.float32, 1.0)
+    return list(TrainFunction.apply(eng, inp, *tuple(model.parameters())))
+
+
+def _engine_for(model: nn.Module, B: int, H: int, W: int, device: torch.device, dtype: torch.dtype, scale: float) -> "TrainEngine":
+    cache = model.__dict__.setdefault("_train_engine_cache", {})
+    key = (B, H, W, device.index, dtype, float(scale))
+    eng = cache.pop(key, None)
+    if eng is None:
+        while len(cache) >= int(model.__dict__.get("_train_engine_slots", 1)):  # multi_scale training keeps a few shapes
+            cache.pop(next(iter(cache)))
+        eng = TrainEngine(model, B, H, W, in_dtype=dtype, scale=scale, device=device)
+        hook = model.__dict__.get("_train_engine_hook")
+        if hook is not None:
+            hook(eng)
+    cache[key] = eng  # most recently used last
+    model.__dict__["_train_engine_last"] = eng
+    return eng
+
+
 def forward_train(model: nn.Module, x: torch.Tensor, scale: float = 1.0) -> List[torch.Tensor]:
     """YOLOModel.forward in training mode (returns the list of (bs, na, ny, nx, no) head outputs) on `x * scale`.
     A uint8 batch with scale = 1/255 is the reference's `prepare_img` (abstract_trainer.py:252-261) fused into the stem's
@@ -725,17 +763,6 @@ def forward_train(model: nn.Module, x: torch.Tensor, scale: float = 1.0) -> List
     if x.dtype not in (torch.float32, torch.uint8):
         x = x.float()
     B, _, H, W = x.shape
-    cache = model.__dict__.setdefault("_train_engine_cache", {})
-    key = (B, H, W, x.device.index, x.dtype, float(scale))
-    eng = cache.pop(key, None)
-    if eng is None:
-        while len(cache) >= int(model.__dict__.get("_train_engine_slots", 1)):  # multi_scale training keeps a few shapes
-            cache.pop(next(iter(cache)))
-        eng = TrainEngine(model, B, H, W, in_dtype=x.dtype, scale=scale, device=x.device)
-        hook = model.__dict__.get("_train_engine_hook")
-        if hook is not None:
-            hook(eng)
-    cache[key] = eng  # most recently used last
-    model.__dict__["_train_engine_last"] = eng
+    eng = _engine_for(model, B, H, W, x.device, x.dtype, scale)
     params = tuple(model.parameters())
     return list(TrainFunction.apply(eng, x, *params))

@@ -35,7 +35,7 @@ import torch.nn.functional as F
 from . import dist_utils as du
 from . import ops
 from .loss import ComputeLoss
-from .train_engine import forward_train
+from .train_engine import forward_train, forward_train_resized
 
 NOMINAL_BATCH = 64  # yolo_trainer.py:88
 
@@ -164,12 +164,19 @@ class TrainStep:
         self.lrs = [self.lr0 * f] * 3
         self.momentum = float(self.hyp["momentum"])
 
-    def multi_scale(self, imgs: torch.Tensor) -> torch.Tensor:
+    def multi_scale_shape(self, hw: Sequence[int]) -> Optional[List[int]]:
+        """The random target size of `multi_scale` (:233-245; one draw from `random` per step, like the reference), or None
+        when the batch keeps its size."""
         g = self.grid_size
         sz = random.randrange(int(self.img_size * 0.5), int(self.img_size * 1.5 + g)) // g * g
-        sf = sz / max(imgs.shape[2:])
-        if sf != 1:
-            new_shape = [math.ceil(x * sf / g) * g for x in imgs.shape[2:]]
+        sf = sz / max(hw)
+        return [math.ceil(x * sf / g) * g for x in hw] if sf != 1 else None
+
+    def multi_scale(self, imgs: torch.Tensor) -> torch.Tensor:
+        """Reference form on a prepared float batch (kept for callers that hold one; the step itself resizes while it fills
+        the engine's input, `forward_train_resized`)."""
+        new_shape = self.multi_scale_shape(imgs.shape[2:])
+        if new_shape is not None:
             imgs = F.interpolate(imgs, size=new_shape, mode="bilinear", align_corners=False)
         return imgs
 
@@ -197,18 +204,26 @@ class TrainStep:
         if ni <= self.num_warmups:
             self.warmup(ni, epoch)
         imgs, labels = train_batch[0], train_batch[1]
-        fused_u8 = imgs.dtype == torch.uint8 and not self.use_multi_scale and self.model.training
-        if fused_u8:
-            imgs = imgs.to(self.device, non_blocking=True)  # / 255 happens inside the stem's space-to-depth pass
+        u8 = imgs.dtype == torch.uint8 and self.model.training
+        new_shape = self.multi_scale_shape(imgs.shape[2:]) if self.use_multi_scale else None
+        fused_u8 = u8 and new_shape is None
+        if u8:
+            imgs = imgs.to(self.device, non_blocking=True)  # / 255 happens inside the stem's space-to-depth / the resize pass
         else:
             imgs = self.prepare_img(imgs, self.device) if imgs.dtype == torch.uint8 else imgs.to(self.device).float()
         labels = labels.to(self.device)
-        if self.use_multi_scale:
-            imgs = self.multi_scale(imgs)
         boundary = ni % self.accumulate == 0
         self._exchange_now = self.world > 1 and boundary and self.accumulate == 1 and self._flat_ready and not self.skip_exchange
         self._bucket_events = []
-        pred = forward_train(self.model, imgs, scale=1.0 / 255.0) if fused_u8 else self.model(imgs)
+        if fused_u8:
+            pred = forward_train(self.model, imgs, scale=1.0 / 255.0)
+        elif new_shape is not None and self.model.training:
+            # multi_scale (:223-248): prepare_img's / 255, the bilinear resize and the copy into the engine's input are one pass
+            pred = forward_train_resized(self.model, imgs, new_shape, pre_scale=1.0 / 255.0 if u8 else 1.0)
+        else:
+            if new_shape is not None:
+                imgs = F.interpolate(imgs, size=new_shape, mode="bilinear", align_corners=False)
+            pred = self.model(imgs)
         eng = self._engine()
         if not self._flat_ready:
             self._setup_flat(eng)  # first call: the engine (and the flat layout) exists now; this step exchanges unbucketed

@@ -327,6 +327,12 @@ typedef struct ay2_letterbox_image {
 int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t kinds, int32_t out_h,
                           int32_t out_w, uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels,
                           int32_t out_x_offset, float scale, void* stream);
+/* YoloTrainer.multi_scale (scripts/train/yolo_trainer.py:223-248) with prepare_img (scripts/train/abstract_trainer.py:252-261)
+ * fused in: out fp32 [batch][3][out_h][out_w] = F.interpolate(img * pre_scale, (out_h, out_w), mode="bilinear",
+ * align_corners=False); img NCHW uint8 (AY2_DT_U8) or fp32 (AY2_DT_F32). Replaces the .float() / 255 pass, the ATen
+ * interpolation and the copy into the training engine's static input (the engine passes its input buffer as `out`). */
+int ay2_resize_bilinear(const void* img, int32_t dtype, int32_t batch, int32_t h, int32_t w, float pre_scale, float* out,
+                        int32_t out_h, int32_t out_w, void* stream);
 /* LoadImagesAndLabels.collate_fn (data_loader.py:905-909): labels fp32 [total][6] (already concatenated), offsets int32
  * [batch + 1] (row range of every image, DEVICE): writes the image index into column 0. */
 int ay2_collate_labels(float* labels, const int32_t* offsets, int32_t batch, int32_t total, void* stream);

@@ -147,3 +147,55 @@ def test_detector_from_loaded_images_equals_detector_on_the_reference_batch():
     for k in ks:
         for a, b in zip(det.collect(k), want):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("shape,size", [((2, 3, 128, 128), (96, 96)), ((3, 3, 64, 96), (160, 224)), ((1, 3, 640, 640), (352, 352)),
+                                        ((2, 3, 33, 47), (64, 32))])
+def test_resize_bilinear_matches_torch_interpolate(dtype, shape, size):
+    """ay2_resize_bilinear == F.interpolate(prepare_img(x), size, bilinear, align_corners=False) (yolo_trainer.py:223-248 after
+    abstract_trainer.py:252-261). Floating point: same formula and operation order as torch's kernel; asserted to 2e-6 absolute
+    on values in [0, 1] (a few fp32 ulps; north_star's fp32 tolerance is 1e-3), measured error recorded."""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(sum(shape) + size[0])
+    if dtype == torch.uint8:
+        x = torch.randint(0, 256, shape, generator=g, dtype=torch.uint8).cuda()
+        ref = F.interpolate(x.float() / 255.0, size=size, mode="bilinear", align_corners=False)
+        pre = 1.0 / 255.0
+    else:
+        x = torch.rand(shape, generator=g).cuda()
+        ref = F.interpolate(x, size=size, mode="bilinear", align_corners=False)
+        pre = 1.0
+    out = torch.empty((shape[0], 3, *size), dtype=torch.float32, device="cuda")
+    ops.resize_bilinear(x, out, pre)
+    err = float((out - ref).abs().max())
+    record(f"input/resize_bilinear_{'u8' if dtype == torch.uint8 else 'f32'}_{shape[2]}x{shape[3]}_to_{size[0]}x{size[1]}", max_abs=err,
+           exact_fraction=float((out == ref).float().mean()))
+    assert err <= 2e-6, err
+
+
+def test_multi_scale_step_fills_the_engine_input_in_one_pass():
+    """forward_train_resized(model, uint8 batch, size, 1/255) == model(F.interpolate(batch.float() / 255, size)) in train
+    mode: same engine, same static input up to the resize's fp32 rounding, so the head outputs agree to bf16 noise."""
+    import torch.nn.functional as F
+
+    from ayolov2_b200 import synth
+    from ayolov2_b200.train_engine import forward_train_resized
+
+    model = synth.build_model("yolov5n", seed=0).cuda().train()
+    x = torch.randint(0, 256, (4, 3, 128, 128), generator=torch.Generator().manual_seed(3), dtype=torch.uint8).cuda()
+    size = (96, 160)
+    want_in = F.interpolate(x.float() / 255.0, size=size, mode="bilinear", align_corners=False)
+    with torch.no_grad():
+        ref = [o.clone() for o in model(want_in)]
+        eng = model.__dict__["_train_engine_last"]
+        got = [o.clone() for o in forward_train_resized(model, x, size, 1.0 / 255.0)]
+    assert model.__dict__["_train_engine_last"] is eng, "the resized route must reuse the engine of that shape"
+    assert float((eng.static_in - want_in).abs().max()) <= 2e-6
+    for a, b in zip(got, ref):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 2e-2 * float(b.abs().max())
+    # and it trains: the gradient flows through the one autograd node
+    outs = forward_train_resized(model, x, size, 1.0 / 255.0)
+    sum((o * o).mean() for o in outs).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters() if p.requires_grad)
