@@ -60,6 +60,8 @@ class Detector:
         self.ev_consumed = [torch.cuda.Event() for _ in range(self.slots)]
         self.ev_done = [torch.cuda.Event() for _ in range(self.slots)]
         self._slot = 0
+        self._slot_packed: dict = {}  # slot -> (device PackedBatch, fused) for batches submitted through submit_packed
+        self.stage: List[Optional[torch.Tensor]] = [None] * self.slots  # raw-image arenas of submit_packed
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._warm = False
 
@@ -139,6 +141,7 @@ class Detector:
             self.dev_in[k].copy_(host_img, non_blocking=True)
             self.ev_h2d[k].record(self.copy_stream)
         cur.wait_event(self.ev_h2d[k])
+        self._slot_packed.pop(k, None)
         det, cnt = self.run_device(self.dev_in[k])
         self.ev_consumed[k].record(cur)
         self.host_out[k].copy_(det, non_blocking=True)
@@ -159,8 +162,6 @@ class Detector:
         k = self._slot
         self._slot = (k + 1) % self.slots
         n = pb.arena.numel()
-        if not hasattr(self, "stage"):
-            self.stage = [None] * self.slots
         if self.stage[k] is None or self.stage[k].numel() < n:
             torch.cuda.synchronize(self.device)  # a (rare) growth must not free bytes a running kernel still reads
             self.stage[k] = torch.empty(max(n, self.B * (3 * self.H * self.W + 64)), dtype=torch.uint8, device=self.device)
@@ -173,21 +174,23 @@ class Detector:
         cur.wait_event(self.ev_h2d[k])
         dpb = dataclasses.replace(pb, arena=dst)
         eng = self.engine
-        if fused and not eng.b.x3:
-            dpb.to_space_to_depth(eng.b.s2d_view, eng.b.s2d_scale, x_offset=1)
-            self.ev_consumed[k].record(cur)
-            det, cnt = self._run_body()
-            self._packed_fused_last = True
-        else:
-            dpb.to_device(out=self.dev_in[k])
-            det, cnt = self.run_device(self.dev_in[k])
-            self.ev_consumed[k].record(cur)
-            self._packed_fused_last = False
+        fused = fused and not eng.b.x3
+        self._slot_packed[k] = (dpb, fused)  # the slot's input, should collect() have to redo the batch (candidate overflow)
+        det, cnt = self._run_packed(dpb, fused, k)
+        self.ev_consumed[k].record(cur)
         self.host_out[k].copy_(det, non_blocking=True)
         self.host_cnt[k][:self.B].copy_(cnt, non_blocking=True)
         self.host_cnt[k][self.B:].copy_(self.nms_ws.overflow, non_blocking=True)
         self.ev_done[k].record(cur)
         return k
+
+    def _run_packed(self, dpb, fused: bool, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        eng = self.engine
+        if fused:
+            dpb.to_space_to_depth(eng.b.s2d_view, eng.b.s2d_scale, x_offset=1)
+            return self._run_body()
+        dpb.to_device(out=self.dev_in[k])
+        return self.run_device(self.dev_in[k])
 
     def collect(self, k: int) -> List[torch.Tensor]:
         """Wait for slot k and return the reference-style list of (n_i, 6) tensors (host memory)."""
@@ -196,7 +199,8 @@ class Detector:
             # candidate-list overflow: redo this batch (still in its device slot) with a workspace that cannot overflow
             torch.cuda.synchronize(self.device)
             self._grow_workspace()
-            det, cnt = self.run_device(self.dev_in[k])
+            packed = self._slot_packed.get(k)
+            det, cnt = self._run_packed(packed[0], packed[1], k) if packed else self.run_device(self.dev_in[k])
             self.host_out[k].copy_(det)
             self.host_cnt[k][:self.B].copy_(cnt)
             self.host_cnt[k][self.B] = 0

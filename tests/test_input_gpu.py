@@ -199,3 +199,32 @@ def test_multi_scale_step_fills_the_engine_input_in_one_pass():
     outs = forward_train_resized(model, x, size, 1.0 / 255.0)
     sum((o * o).mean() for o in outs).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters() if p.requires_grad)
+
+
+def test_candidate_overflow_redo_keeps_the_packed_input():
+    """collect() redoes a batch whose candidate list overflowed (multi_label at a low conf_thres). For a batch submitted as
+    loaded images the redo must start again from the raw-image arena of the slot (the uint8 slot holds nothing for it)."""
+    from ayolov2_b200 import synth
+    from ayolov2_b200.detector import Detector
+
+    model = synth.build_model("yolov5s", seed=2).cuda()
+    B, H, W = 2, 256, 256
+    imgs = input_oracle.synth_images(31, [(256, 200), (120, 256)])
+    ref_batch, _ = input_oracle.load_and_collate(imgs, (H, W))
+    host = torch.from_numpy(ref_batch)
+    sample = host.cuda().float() / 255.0
+    synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.1)
+    kw = dict(conf_thres=0.05, iou_thres=0.45, multi_label=True, in_dtype=torch.uint8)
+    want = Detector(model, B, H, W, **kw).detect(host.pin_memory())
+    assert sum(x.shape[0] for x in want) > 20
+    small = Detector(model, B, H, W, **kw)
+    n, no = small.engine.pred.shape[1], small.engine.pred.shape[2]
+    pb = dl.pack_batch(imgs, (H, W), pin=True)
+    for fused in (True, False):
+        small.nms_ws = ops.NmsWorkspace(B, n, no, max_det=300, multi_label=True, max_candidates=64, device=small.device)
+        small._arm_candidates()
+        small._graph, small._warm = None, False
+        got = small.collect(small.submit_packed(pb, fused=fused))
+        assert small.nms_ws.p.max_candidates > 64, "the overflow must have been detected and the workspace grown"
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
