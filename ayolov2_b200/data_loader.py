@@ -158,9 +158,13 @@ def pack_batch(images: Sequence[np.ndarray], new_shape: Sequence[int], auto: boo
         arena = arena[:off]
     host = arena.numpy()
     host[:B * _REC.itemsize] = rec.view(np.uint8)
+    end = B * _REC.itemsize
     for i, im in enumerate(images):
         start = B * _REC.itemsize + int(rec[i]["src_offset"])
+        host[end:start] = 0  # alignment gap (the arena is uninitialised memory: keep the packed bytes deterministic)
         host[start:start + im.size] = np.ascontiguousarray(im).reshape(-1)
+        end = start + im.size
+    host[end:off] = 0
     return PackedBatch(arena, B, (H, W), tuple(shapes), tuple(ratios), tuple(int(c) for c in color), tuple(paths), kinds)
 
 

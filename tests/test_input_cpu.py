@@ -65,3 +65,35 @@ def test_no_cpu_fallback():
     pb = dl.pack_batch(imgs, (96, 128))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pb.to_device(torch.device("cpu"))
+
+
+class _LoadedImages(torch.utils.data.Dataset):
+    """What the reference's LoadImages would return if __getitem__ stopped right after _load_image (data_loader.py:373)."""
+
+    def __init__(self):
+        self.shapes = [(96, 128), (72, 128), (96, 100), (33, 47), (95, 127)]
+        self.imgs = input_oracle.synth_images(8, self.shapes)
+
+    def __len__(self):
+        return len(self.imgs)
+
+    def __getitem__(self, i):
+        return self.imgs[i], f"img{i}.jpg", self.imgs[i].shape[:2]
+
+
+def test_collate_fn_runs_inside_dataloader_workers():
+    """The host half is pure CPU and its result pickles: it can be the DataLoader's collate_fn in worker processes, like the
+    reference's (data_loader.py:461-477); the device half runs in the consumer."""
+    import functools
+
+    ds = _LoadedImages()
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, shuffle=False, num_workers=1, drop_last=False,
+                                         collate_fn=functools.partial(dl.collate_fn, new_shape=(96, 128)))
+    seen = 0
+    for pb, paths, shapes in loader:
+        assert isinstance(pb, dl.PackedBatch) and pb.batch == len(paths) == len(shapes) and not pb.arena.is_cuda
+        want = dl.pack_batch(ds.imgs[seen:seen + pb.batch], (96, 128))
+        assert torch.equal(pb.arena, want.arena) and pb.shapes == want.shapes and pb.kinds == want.kinds
+        assert paths == tuple(f"img{i}.jpg" for i in range(seen, seen + pb.batch))
+        seen += pb.batch
+    assert seen == len(ds)
