@@ -463,6 +463,25 @@ def bench_input_side(det, dev, rank: int, world: int, barrier, max_over_ranks, s
         input_oracle.load_and_collate(imgs[:n], (H, W))
         dt = time.perf_counter() - t0
         out["cpu_oracle"] = {"images_per_s": n / dt, "cores": 1, "kind": "port", "sample": f"{n} images of the same mix, numpy restatement of _letterbox + collate_fn"}
+        try:  # the reference's own dependency for this step, when the box has it: cv2.resize + copyMakeBorder + transpose + stack
+            import cv2
+
+            def cv2_letterbox(im):
+                (uw, uh), _, _, (top, bottom, left, right) = dl.letterbox_geometry(im.shape[:2], (H, W), auto=False)
+                if (uh, uw) != im.shape[:2]:
+                    im = cv2.resize(im, (uw, uh), interpolation=cv2.INTER_LINEAR)
+                im = cv2.copyMakeBorder(im, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+                return np.ascontiguousarray(im.transpose((2, 0, 1))[::-1])
+            cv2.setNumThreads(1)
+            t0 = time.perf_counter()
+            reps = 4
+            for _ in range(reps):
+                np.stack([cv2_letterbox(im) for im in imgs], 0)
+            dt = time.perf_counter() - t0
+            out["cpu_cv2"] = {"images_per_s": reps * len(imgs) / dt, "cores": 1, "kind": "reference dependency (opencv " + cv2.__version__ + ")",
+                              "sample": f"{reps} x {len(imgs)} images of the same mix: cv2.resize + copyMakeBorder + transpose + np.stack"}
+        except ImportError:
+            pass
     out["config"] = f"{BATCH} loaded images -> ({BATCH}, 3, {H}, {W}); 'val': long side 640 mixed aspect ratios, one in four up-scaled; fused into the stem's space-to-depth input (bf16, /255)"
     return out
 
