@@ -480,8 +480,8 @@ def bench_input_side(det, dev, rank: int, world: int, barrier, max_over_ranks, s
             dt = time.perf_counter() - t0
             out["cpu_cv2"] = {"images_per_s": reps * len(imgs) / dt, "cores": 1, "kind": "reference dependency (opencv " + cv2.__version__ + ")",
                               "sample": f"{reps} x {len(imgs)} images of the same mix: cv2.resize + copyMakeBorder + transpose + np.stack"}
-        except ImportError:
-            pass
+        except Exception as e:  # no cv2 on the box (or anything else): the entry is optional
+            out["cpu_cv2"] = {"unavailable": f"{type(e).__name__}: {e}"[:120]}
     out["config"] = f"{BATCH} loaded images -> ({BATCH}, 3, {H}, {W}); 'val': long side 640 mixed aspect ratios, one in four up-scaled; fused into the stem's space-to-depth input (bf16, /255)"
     return out
 
