@@ -164,6 +164,7 @@ _PROTOS = {
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ay2_resize_bilinear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p]),
+    "ay2_load_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "ay2_nms_workspace_bytes": (C.c_size_t, [C.POINTER(NmsParams)]),
     "ay2_nms_from_logits": (C.c_int, [C.POINTER(HeadLevels), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

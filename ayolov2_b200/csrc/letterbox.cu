@@ -184,6 +184,112 @@ __global__ void __launch_bounds__(256) letterbox_collate_kernel(LetterboxParams 
   write_block<KIND>(p, b, x0, y0, px);
 }
 
+// ------------------------------------------------------------------------------------------------
+// LoadImages._load_image after the decode (scripts/data_loader/data_loader.py:320-329): long side -> img_size with
+// cv2.resize INTER_AREA (shrinking, no augmentation) or INTER_LINEAR, ragged images -> ragged images in the same arena.
+// A thread owns one output pixel. INTER_AREA as OpenCV computes it for 8-bit images (oracle/input_oracle.py):
+//   integer ratios: integer cell sum, (a + b + c + d + 2) >> 2 for 2 x 2, else round_half_even(sum * fp32(1 / area));
+//   other ratios:   per source line the fp32 sum of its cells in source order (buf += S * alpha; partial left cell, full
+//                   cells, partial right cell, weights from double arithmetic rounded once to fp32), then the fp32 sum of
+//                   the lines (sum += beta * buf) -- separate multiplies and adds (the CPU build has no FMA), half-even.
+struct AreaCells {
+  int s1, s2;          // full cells [s1, s2)
+  bool left, right;    // partial cells at s1 - 1 / s2
+  float wl, wm, wr;    // their weights
+};
+__device__ __forceinline__ AreaCells area_cells(int d, int ssize, double scale) {
+  AreaCells a;
+  const double fs1 = __dmul_rn((double)d, scale), fs2 = __dadd_rn(fs1, scale);
+  const double cell = fmin(scale, __dsub_rn((double)ssize, fs1));
+  int s1 = (int)ceil(fs1), s2 = (int)floor(fs2);
+  s2 = min(s2, ssize - 1);
+  s1 = min(s1, s2);
+  a.s1 = s1, a.s2 = s2;
+  const double dl = __dsub_rn((double)s1, fs1), dr = __dsub_rn(fs2, (double)s2);
+  a.left = dl > 1e-3;
+  a.right = dr > 1e-3;
+  a.wl = __double2float_rn(__ddiv_rn(dl, cell));
+  a.wm = __double2float_rn(__ddiv_rn(1.0, cell));
+  a.wr = __double2float_rn(__ddiv_rn(fmin(fmin(dr, 1.0), cell), cell));
+  return a;
+}
+
+__device__ __forceinline__ void area_line(const uint8_t* line, const AreaCells& x, float beta, float (&sum)[3]) {
+  float buf[3] = {0.f, 0.f, 0.f};
+  if (x.left) {
+    const uint8_t* q = line + (x.s1 - 1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)__ldg(q + c), x.wl));
+  }
+  for (int sx = x.s1; sx < x.s2; ++sx) {
+    const uint8_t* q = line + sx * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)__ldg(q + c), x.wm));
+  }
+  if (x.right) {
+    const uint8_t* q = line + x.s2 * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)__ldg(q + c), x.wr));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sum[c] = __fadd_rn(sum[c], __fmul_rn(beta, buf[c]));
+}
+
+__device__ __forceinline__ uint8_t round_u8(float v) { return (uint8_t)min(max(__float2int_rn(v), 0), 255); }
+
+__global__ void __launch_bounds__(256) load_resize_kernel(uint8_t* arena, const ay2_load_resize_image* table) {
+  const ay2_load_resize_image im = table[blockIdx.z];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= im.dst_h * im.dst_w) return;
+  const int dy = idx / im.dst_w, dx = idx - dy * im.dst_w;
+  const uint8_t* src = arena + im.src_offset;
+  uint8_t* out = arena + im.dst_offset + (size_t)dy * im.dst_row_bytes + dx * 3;
+  const bool half = im.src_h == 2 * im.dst_h && im.src_w == 2 * im.dst_w;
+  if (half) {  // both interpolations run the 2 x 2 area filter on an exact decimation
+    const uint8_t* q0 = src + (size_t)(2 * dy) * im.src_row_bytes + (2 * dx) * 3;
+    const uint8_t* q1 = q0 + im.src_row_bytes;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = (uint8_t)(((int)__ldg(q0 + c) + (int)__ldg(q0 + 3 + c) + (int)__ldg(q1 + c) + (int)__ldg(q1 + 3 + c) + 2) >> 2);
+    return;
+  }
+  if (im.mode == AY2_LR_LINEAR) {
+    const Tap ct = column_tap(dx, im.src_w, im.scale_x), rt = row_tap(dy, im.src_h, im.scale_y);
+    const uint8_t* l0 = src + (size_t)rt.s0 * im.src_row_bytes;
+    const uint8_t* l1 = src + (size_t)rt.s1 * im.src_row_bytes;
+    const int o0 = ct.s0 * 3, o1 = ct.s1 * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = (int)__ldg(l0 + o0 + c) * ct.c0 + (int)__ldg(l0 + o1 + c) * ct.c1;
+      const int h1 = (int)__ldg(l1 + o0 + c) * ct.c0 + (int)__ldg(l1 + o1 + c) * ct.c1;
+      out[c] = (uint8_t)min(max((((rt.c0 * (h0 >> 4)) >> 16) + ((rt.c1 * (h1 >> 4)) >> 16) + 2) >> 2, 0), 255);
+    }
+    return;
+  }
+  // INTER_AREA
+  const int isx = __double2int_rn(im.scale_x), isy = __double2int_rn(im.scale_y);
+  const double eps = 2.220446049250313e-16;  // DBL_EPSILON
+  if (fabs(im.scale_x - (double)isx) < eps && fabs(im.scale_y - (double)isy) < eps) {
+    int total[3] = {0, 0, 0};
+    for (int ky = 0; ky < isy; ++ky) {
+      const uint8_t* q = src + (size_t)(dy * isy + ky) * im.src_row_bytes + (dx * isx) * 3;
+      for (int kx = 0; kx < isx; ++kx)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) total[c] += (int)__ldg(q + kx * 3 + c);
+    }
+    const float inv = __fdiv_rn(1.0f, (float)(isx * isy));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] = round_u8(__fmul_rn((float)total[c], inv));
+    return;
+  }
+  const AreaCells x = area_cells(dx, im.src_w, im.scale_x), y = area_cells(dy, im.src_h, im.scale_y);
+  float sum[3] = {0.f, 0.f, 0.f};
+  if (y.left) area_line(src + (size_t)(y.s1 - 1) * im.src_row_bytes, x, y.wl, sum);
+  for (int sy = y.s1; sy < y.s2; ++sy) area_line(src + (size_t)sy * im.src_row_bytes, x, y.wm, sum);
+  if (y.right) area_line(src + (size_t)y.s2 * im.src_row_bytes, x, y.wr, sum);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[c] = round_u8(sum[c]);
+}
+
 // YoloTrainer.multi_scale (scripts/train/yolo_trainer.py:223-248) with prepare_img (abstract_trainer.py:252-261) fused in:
 // out = F.interpolate(in * pre, size, mode="bilinear", align_corners=False) as fp32 NCHW, in the operation order of
 // torch's own kernel (source index = max(ratio * (dst + 0.5) - 0.5, 0), ratio = in / out in fp32; lambda = frac;
@@ -281,6 +387,16 @@ extern "C" int ay2_resize_bilinear(const void* img, int32_t dtype, int32_t batch
     resize_bilinear_kernel<uint8_t><<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(img), h, w, out, out_h, out_w, pre_scale, rh, rw, total);
   else
     resize_bilinear_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(img), h, w, out, out_h, out_w, pre_scale, rh, rw, total);
+  AY2_CHECK_LAUNCH();
+  count_launch();
+  return AY2_OK;
+}
+
+extern "C" int ay2_load_resize(uint8_t* arena, const ay2_load_resize_image* table, int32_t count, int32_t max_dst_pixels, void* stream) {
+  AY2_REQUIRE(count >= 0 && max_dst_pixels >= 0 && (count == 0 || (arena && table)), "ay2_load_resize: bad arguments");
+  AY2_REQUIRE(count <= 65535, "ay2_load_resize: %d images in one call", count);
+  if (count == 0 || max_dst_pixels == 0) return AY2_OK;
+  load_resize_kernel<<<dim3(ceil_div(max_dst_pixels, 256), 1, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(arena, table);
   AY2_CHECK_LAUNCH();
   count_launch();
   return AY2_OK;

@@ -33,6 +33,11 @@ LB_HAS_COPY, LB_HAS_RESIZE = 1, 2
 _REC = np.dtype([("src_offset", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("src_h", "<i4"), ("src_w", "<i4"), ("src_row_bytes", "<i4"), ("dst_h", "<i4"),
                  ("dst_w", "<i4"), ("top", "<i4"), ("left", "<i4"), ("reserved", "<i4")])  # ay2_letterbox_image
 assert _REC.itemsize == 56
+LR_LINEAR, LR_AREA = 0, 1
+_LOAD_REC = np.dtype([("src_offset", "<i8"), ("dst_offset", "<i8"), ("scale_x", "<f8"), ("scale_y", "<f8"), ("src_h", "<i4"),
+                      ("src_w", "<i4"), ("src_row_bytes", "<i4"), ("dst_h", "<i4"), ("dst_w", "<i4"), ("dst_row_bytes", "<i4"),
+                      ("mode", "<i4"), ("reserved", "<i4")])  # ay2_load_resize_image
+assert _LOAD_REC.itemsize == 64
 
 
 def letterbox_geometry(shape: Sequence[int], new_shape: Sequence[int], auto: bool = True, scale_fill: bool = False,
@@ -70,6 +75,13 @@ class PackedBatch:
     color: Tuple[int, int, int] = (114, 114, 114)
     paths: tuple = ()
     kinds: int = 0               # LB_HAS_COPY | LB_HAS_RESIZE: which kernels the batch needs
+    # decode-side resize (`_load_image`, data_loader.py:320-329) of `n_load` images: its table sits inside the arena, the
+    # resized images are written to `scratch_bytes` of DEVICE memory right behind the uploaded bytes
+    host_bytes: int = 0
+    n_load: int = 0
+    load_table_offset: int = 0   # relative to the first byte after the letterbox table
+    scratch_bytes: int = 0
+    max_dst_pixels: int = 0
 
     @property
     def table_bytes(self) -> int:
@@ -105,16 +117,23 @@ def _arena_to_device(pb: PackedBatch, device, staging: Optional[torch.Tensor]) -
         raise RuntimeError("PackedBatch.to_device: the letterbox / collate kernel runs on a CUDA device only (no CPU fallback)")
     n = pb.arena.numel()
     if staging is None:
-        return pb.arena.to(device, non_blocking=True)
-    assert staging.is_cuda and staging.dtype == torch.uint8 and staging.numel() >= n
-    dst = staging[:n]
-    dst.copy_(pb.arena, non_blocking=True)
+        if not pb.scratch_bytes:
+            return pb.arena.to(device, non_blocking=True)
+        staging = torch.empty(n + pb.scratch_bytes, dtype=torch.uint8, device=device)
+    assert staging.is_cuda and staging.dtype == torch.uint8 and staging.numel() >= n + pb.scratch_bytes
+    dst = staging[:n + pb.scratch_bytes]
+    dst[:n].copy_(pb.arena, non_blocking=True)
     return dst
 
 
 def _launch(pb: PackedBatch, dev_arena: torch.Tensor, kind: int, out_ptr: int, row_pixels: int, x_offset: int, scale: float) -> None:
     H, W = pb.out_shape
     base = dev_arena.data_ptr()
+    assert dev_arena.numel() >= pb.host_bytes + pb.scratch_bytes, "the device arena lacks the scratch space of the decode-side resize"
+    if pb.n_load:
+        img_base = base + pb.table_bytes
+        _lib.check(_lib.load().ay2_load_resize(img_base, img_base + pb.load_table_offset, pb.n_load, pb.max_dst_pixels,
+                                               _lib.current_stream_ptr()), "ay2_load_resize")
     color = pb.color[0] | (pb.color[1] << 8) | (pb.color[2] << 16)
     _lib.check(_lib.load().ay2_letterbox_collate(base + pb.table_bytes, base, pb.batch, pb.kinds, H, W, C.c_uint32(color), kind, out_ptr,
                                                  row_pixels, x_offset, float(scale), _lib.current_stream_ptr()),
@@ -124,48 +143,87 @@ def _launch(pb: PackedBatch, dev_arena: torch.Tensor, kind: int, out_ptr: int, r
 def pack_batch(images: Sequence[np.ndarray], new_shape: Sequence[int], auto: bool = False, scale_fill: bool = False,
                scale_up: bool = True, stride: int = 32, color: Sequence[int] = (114, 114, 114), pin: bool = False,
                paths: Sequence[str] = (), orig_shapes: Optional[Sequence[Tuple[int, int]]] = None,
-               arena: Optional[torch.Tensor] = None) -> PackedBatch:
-    """Host half. images: loaded HWC BGR uint8 arrays (what `_load_image` returns, data_loader.py:294-350); `orig_shapes`:
-    their (h0, w0) before `_load_image`'s resize when it differs (only enters the `shapes` tuples). The reference calls
-    `_letterbox(img, new_shape=shape, auto=False)` (:380); `auto=True` is rejected here because a batch needs one shape."""
+               arena: Optional[torch.Tensor] = None, img_size: Optional[int] = None, augmentation: bool = False) -> PackedBatch:
+    """Host half. images: HWC BGR uint8 arrays. With `img_size=None` they are LOADED images (what `_load_image` returns,
+    data_loader.py:294-350) and `orig_shapes` their (h0, w0) before that function's resize when it differs (only enters the
+    `shapes` tuples). With `img_size` they are DECODED images (`cv2.imread`) and `_load_image`'s resize (:320-329: long side ->
+    img_size, INTER_AREA when shrinking and `augmentation` is off, INTER_LINEAR otherwise) runs on the device too, into
+    scratch space behind the uploaded bytes. The reference calls `_letterbox(img, new_shape=shape, auto=False)` (:380);
+    `auto=True` is rejected here because a batch needs one shape."""
     if auto:
         raise ValueError("pack_batch: auto=True gives every image its own output shape; the collated batch needs one (the "
                          "reference's __getitem__ passes auto=False, data_loader.py:380)")
     H, W = int(new_shape[0]), int(new_shape[1])
     B = len(images)
+    head = B * _REC.itemsize
     rec = np.zeros(B, dtype=_REC)
-    off = (B * _REC.itemsize + 15) & ~15
-    shapes, ratios, kinds = [], [], 0
+    loaded = []  # per image: (h1, w1) after the decode-side resize, or None
     for i, im in enumerate(images):
         if not (isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3):
             raise TypeError(f"pack_batch: image {i} must be a uint8 HWC array with 3 channels")
-        h, w = im.shape[:2]
+        h0, w0 = im.shape[:2]
+        r = img_size / max(h0, w0) if img_size is not None else 1
+        loaded.append((int(h0 * r), int(w0 * r)) if r != 1 else None)
+        if loaded[-1] is not None and min(loaded[-1]) < 1:
+            raise ValueError(f"pack_batch: image {i} ({h0}x{w0}) vanishes at img_size {img_size}")
+    n_load = sum(x is not None for x in loaded)
+    load_rec = np.zeros(n_load, dtype=_LOAD_REC)
+    off = (head + 15) & ~15
+    load_table_offset = off - head
+    off = (off + n_load * _LOAD_REC.itemsize + 15) & ~15
+    src_off = []
+    for im in images:
+        src_off.append(off - head)
+        off = (off + im.size + 15) & ~15
+    host_bytes = off
+    shapes, ratios, kinds, k, max_dst = [], [], 0, 0, 0
+    for i, im in enumerate(images):
+        h0, w0 = im.shape[:2]
+        if loaded[i] is None:
+            h, w, image_off = h0, w0, src_off[i]
+        else:
+            h, w = loaded[i]
+            image_off = off - head  # in the device-only scratch space
+            off = (off + 3 * h * w + 15) & ~15
+            shrink = h <= h0 and w <= w0 and (h, w) != (h0, w0)
+            mode = LR_AREA if shrink and not augmentation else LR_LINEAR
+            load_rec[k] = (src_off[i], image_off, 1.0 / (float(w) / float(w0)), 1.0 / (float(h) / float(h0)), h0, w0, 3 * w0,
+                           h, w, 3 * w, mode, 0)
+            k += 1
+            max_dst = max(max_dst, h * w)
         (uw, uh), ratio, (dw, dh), (top, bottom, left, right) = letterbox_geometry((h, w), (H, W), False, scale_fill, scale_up, stride)
         if (uh + top + bottom, uw + left + right) != (H, W):
             raise ValueError(f"pack_batch: image {i} ({h}x{w}) letterboxes to {uh + top + bottom}x{uw + left + right}, not {H}x{W}")
         # cv2's step per destination pixel, in its own precision and order (resize.cpp: scale = 1. / inv_scale, both double)
         sx, sy = 1.0 / (float(uw) / float(w)), 1.0 / (float(uh) / float(h))
-        rec[i] = (off - B * _REC.itemsize, sx, sy, h, w, 3 * w, uh, uw, top, left, 0)
+        rec[i] = (image_off, sx, sy, h, w, 3 * w, uh, uw, top, left, 0)
         kinds |= LB_HAS_COPY if (uh, uw) == (h, w) else LB_HAS_RESIZE
-        off = (off + 3 * h * w + 15) & ~15
-        h0, w0 = orig_shapes[i] if orig_shapes is not None else (h, w)
+        if orig_shapes is not None and img_size is None:
+            h0, w0 = orig_shapes[i]
         shapes.append(((h0, w0), ((h / h0, w / w0), (dw, dh))))
         ratios.append(ratio)
+    scratch_bytes = off - host_bytes
     if arena is None:
-        arena = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
+        arena = torch.empty(host_bytes, dtype=torch.uint8, pin_memory=pin)
     else:
-        assert arena.dtype == torch.uint8 and not arena.is_cuda and arena.numel() >= off
-        arena = arena[:off]
+        assert arena.dtype == torch.uint8 and not arena.is_cuda and arena.numel() >= host_bytes
+        arena = arena[:host_bytes]
     host = arena.numpy()
-    host[:B * _REC.itemsize] = rec.view(np.uint8)
-    end = B * _REC.itemsize
+    host[:head] = rec.view(np.uint8)
+    end = head
+    if n_load:
+        start = head + load_table_offset
+        host[end:start] = 0
+        host[start:start + load_rec.nbytes] = load_rec.view(np.uint8)
+        end = start + load_rec.nbytes
     for i, im in enumerate(images):
-        start = B * _REC.itemsize + int(rec[i]["src_offset"])
+        start = head + src_off[i]
         host[end:start] = 0  # alignment gap (the arena is uninitialised memory: keep the packed bytes deterministic)
         host[start:start + im.size] = np.ascontiguousarray(im).reshape(-1)
         end = start + im.size
-    host[end:off] = 0
-    return PackedBatch(arena, B, (H, W), tuple(shapes), tuple(ratios), tuple(int(c) for c in color), tuple(paths), kinds)
+    host[end:host_bytes] = 0
+    return PackedBatch(arena, B, (H, W), tuple(shapes), tuple(ratios), tuple(int(c) for c in color), tuple(paths), kinds,
+                       host_bytes, n_load, load_table_offset, scratch_bytes, max_dst)
 
 
 def collate_fn(batch: List[tuple], new_shape: Sequence[int] = (640, 640), **kw):

@@ -161,15 +161,15 @@ class Detector:
         assert pb.batch == self.B and tuple(pb.out_shape) == (self.H, self.W) and self.in_dtype == torch.uint8
         k = self._slot
         self._slot = (k + 1) % self.slots
-        n = pb.arena.numel()
-        if self.stage[k] is None or self.stage[k].numel() < n:
+        n, need = pb.arena.numel(), pb.arena.numel() + pb.scratch_bytes  # + device scratch of the decode-side resize
+        if self.stage[k] is None or self.stage[k].numel() < need:
             torch.cuda.synchronize(self.device)  # a (rare) growth must not free bytes a running kernel still reads
-            self.stage[k] = torch.empty(max(n, self.B * (3 * self.H * self.W + 64)), dtype=torch.uint8, device=self.device)
+            self.stage[k] = torch.empty(max(need, self.B * (3 * self.H * self.W + 64)), dtype=torch.uint8, device=self.device)
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.ev_consumed[k])
-            dst = self.stage[k][:n]
-            dst.copy_(pb.arena, non_blocking=True)
+            dst = self.stage[k][:need]
+            dst[:n].copy_(pb.arena, non_blocking=True)
             self.ev_h2d[k].record(self.copy_stream)
         cur.wait_event(self.ev_h2d[k])
         dpb = dataclasses.replace(pb, arena=dst)

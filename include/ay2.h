@@ -327,6 +327,22 @@ typedef struct ay2_letterbox_image {
 int ay2_letterbox_collate(const uint8_t* arena, const ay2_letterbox_image* table, int32_t batch, int32_t kinds, int32_t out_h,
                           int32_t out_w, uint32_t color_bgr, int32_t out_kind, void* out, int32_t out_row_pixels,
                           int32_t out_x_offset, float scale, void* stream);
+/* LoadImages._load_image after the decode (scripts/data_loader/data_loader.py:320-329): every image of the table is resized
+ * inside `arena` (DEVICE bytes; src and dst are byte offsets, HWC BGR uint8) with cv2's INTER_AREA (AY2_LR_AREA: the image
+ * shrinks in both directions) or INTER_LINEAR (AY2_LR_LINEAR) arithmetic, bit-exact. scale_x / scale_y as in
+ * ay2_letterbox_image. max_dst_pixels = the largest dst_h * dst_w of the table (grid sizing). The resized images are then
+ * ordinary inputs of ay2_letterbox_collate (its src_offset = this dst_offset). */
+#define AY2_LR_LINEAR 0
+#define AY2_LR_AREA 1
+typedef struct ay2_load_resize_image {
+  int64_t src_offset, dst_offset;
+  double scale_x, scale_y;      /* 1.0 / ((double)dst / src) */
+  int32_t src_h, src_w, src_row_bytes;
+  int32_t dst_h, dst_w, dst_row_bytes;
+  int32_t mode, reserved;
+} ay2_load_resize_image;        /* 64 bytes */
+int ay2_load_resize(uint8_t* arena, const ay2_load_resize_image* table, int32_t count, int32_t max_dst_pixels, void* stream);
+
 /* YoloTrainer.multi_scale (scripts/train/yolo_trainer.py:223-248) with prepare_img (scripts/train/abstract_trainer.py:252-261)
  * fused in: out fp32 [batch][3][out_h][out_w] = F.interpolate(img * pre_scale, (out_h, out_w), mode="bilinear",
  * align_corners=False); img NCHW uint8 (AY2_DT_U8) or fp32 (AY2_DT_F32). Replaces the .float() / 255 pass, the ATen

@@ -1,6 +1,7 @@
 """CPU oracle for the input side of the path. TEST INFRASTRUCTURE ONLY (see oracle/nms_oracle.py for the import rule).
 
 numpy restatement of
+  * scripts/data_loader/data_loader.py:320-329   LoadImages._load_image after the decode (long side -> img_size)
   * scripts/data_loader/data_loader.py:395-459   LoadImages._letterbox (resize to the unpadded size, constant border)
   * scripts/data_loader/data_loader.py:388-389   HWC BGR -> CHW RGB (`img.transpose((2, 0, 1))[::-1]`)
   * scripts/data_loader/data_loader.py:461-477   LoadImages.collate_fn (torch.stack of the images)
@@ -15,6 +16,7 @@ here in integer arithmetic:
     horizontal pass keeps 32-bit integers, the vertical pass is
     (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
     an exact 2x2 down-scale is rerouted to the area filter (a + b + c + d + 2) >> 2.
+  * cv2.resize(..., INTER_AREA) on 8-bit images that shrink: see resize_area_u8.
   * cv2.copyMakeBorder(..., BORDER_CONSTANT, value=color).
 Pinned bit-exact against cv2 itself on 400 random shape pairs, against the UNMODIFIED reference `_letterbox` /
 `collate_fn` imported from /root/reference (tests/test_oracle_input.py, build container) and against the committed
@@ -69,6 +71,81 @@ def resize_linear_u8(img: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+def _area_tab(ssize: int, dsize: int, scale: float):
+    """resize.cpp computeResizeAreaTab: for every destination index the (source index, fp32 weight) entries, in order."""
+    tabs = []
+    for d in range(dsize):
+        fs1 = np.float64(d) * scale
+        fs2 = fs1 + scale
+        cell = min(scale, np.float64(ssize) - fs1)
+        s1, s2 = int(np.ceil(fs1)), int(np.floor(fs2))
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        e = []
+        if s1 - fs1 > 1e-3:
+            e.append((s1 - 1, np.float32((s1 - fs1) / cell)))
+        for sidx in range(s1, s2):
+            e.append((sidx, np.float32(1.0 / cell)))
+        if fs2 - s2 > 1e-3:
+            e.append((s2, np.float32(min(min(fs2 - s2, 1.0), cell) / cell)))
+        tabs.append(e)
+    width = max(len(e) for e in tabs)
+    si = np.zeros((dsize, width), np.int64)
+    al = np.zeros((dsize, width), np.float32)  # padding entries carry weight 0: x + 0 == x
+    for d, e in enumerate(tabs):
+        for t, (sidx, a) in enumerate(e):
+            si[d, t], al[d, t] = sidx, a
+    return si, al
+
+
+def resize_area_u8(img: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_AREA) for uint8 HWC images that shrink in both directions,
+    bit-exact. Integer ratios (resizeAreaFast_): integer cell sums, (a + b + c + d + 2) >> 2 for 2 x 2, otherwise
+    round_half_even(sum * fp32(1 / area)); other ratios (resizeArea_): per source line the weighted fp32 sum of its cells in
+    source order (buf += S * alpha), then the weighted fp32 sum of the lines (sum += beta * buf), rounded half to even."""
+    assert img.dtype == np.uint8 and img.ndim == 3
+    h, w, c = img.shape
+    assert dst_w <= w and dst_h <= h
+    f32 = np.float32
+    scale_x, scale_y = 1.0 / (np.float64(dst_w) / w), 1.0 / (np.float64(dst_h) / h)
+    isx, isy = int(np.rint(scale_x)), int(np.rint(scale_y))
+    eps = np.finfo(np.float64).eps
+    if abs(scale_x - isx) < eps and abs(scale_y - isy) < eps:
+        a = img.astype(np.int64)
+        if isx == 2 and isy == 2:
+            return ((a[0:2 * dst_h:2, 0:2 * dst_w:2] + a[0:2 * dst_h:2, 1:2 * dst_w:2] + a[1:2 * dst_h:2, 0:2 * dst_w:2]
+                     + a[1:2 * dst_h:2, 1:2 * dst_w:2] + 2) >> 2).astype(np.uint8)
+        total = np.zeros((dst_h, dst_w, c), np.int64)
+        for ky in range(isy):
+            for kx in range(isx):
+                total += a[ky:ky + dst_h * isy:isy, kx:kx + dst_w * isx:isx]
+        v = (total.astype(f32) * (f32(1.0) / f32(isx * isy))).astype(f32)
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    xs, xa = _area_tab(w, dst_w, scale_x)
+    ys, ya = _area_tab(h, dst_h, scale_y)
+    src = img.astype(f32)
+    buf = np.zeros((h, dst_w, c), f32)
+    for t in range(xs.shape[1]):
+        buf = (buf + (src[:, xs[:, t], :] * xa[None, :, t, None]).astype(f32)).astype(f32)
+    out = np.zeros((dst_h, dst_w, c), f32)
+    for t in range(ys.shape[1]):
+        out = (out + (ya[:, t, None, None] * buf[ys[:, t]]).astype(f32)).astype(f32)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def load_image_resize(im: np.ndarray, img_size: int, augmentation: bool = False) -> np.ndarray:
+    """data_loader.py:320-329 (`_load_image` after the decode): long side -> img_size; INTER_AREA when shrinking without
+    augmentation, INTER_LINEAR otherwise; untouched when the long side already matches."""
+    h0, w0 = im.shape[:2]
+    r = img_size / max(h0, w0)
+    if r == 1:
+        return im
+    dst_w, dst_h = int(w0 * r), int(h0 * r)
+    if r < 1 and not augmentation:
+        return resize_area_u8(im, dst_w, dst_h)
+    return resize_linear_u8(im, dst_w, dst_h)
+
+
 def letterbox_geometry(shape: Sequence[int], new_shape: Sequence[int], auto: bool = True, scale_fill: bool = False,
                        scale_up: bool = True, stride: int = 32):
     """data_loader.py:428-455 without the pixels: (new_unpad (w, h), ratio (w, h), (dw, dh), (top, bottom, left, right))."""
@@ -112,16 +189,20 @@ def to_chw_rgb(im: np.ndarray) -> np.ndarray:
 
 
 def load_and_collate(images: List[np.ndarray], new_shape: Sequence[int], auto: bool = False, scale_fill: bool = False,
-                     scale_up: bool = True, stride: int = 32, color: Sequence[int] = (114, 114, 114)):
+                     scale_up: bool = True, stride: int = 32, color: Sequence[int] = (114, 114, 114),
+                     img_size: Optional[int] = None, augmentation: bool = False):
     """LoadImages.__getitem__ from the letterbox on (data_loader.py:380-393) for every image + collate_fn (:461-477):
-    (uint8 [B, 3, H, W], shapes) with shapes[i] = ((h0, w0), ((h / h0, w / w0), (dw, dh))) for images that enter at their
-    loaded size (h0, w0) == (h, w)."""
+    (uint8 [B, 3, H, W], shapes) with shapes[i] = ((h0, w0), ((h / h0, w / w0), (dw, dh))); images enter at their loaded
+    size ((h0, w0) == (h, w)) or, with `img_size`, as decoded and go through `_load_image`'s resize first."""
     out, shapes = [], []
     for im in images:
+        h0, w0 = im.shape[:2]
+        if img_size is not None:  # decoded image: `_load_image`'s resize first (data_loader.py:320-329)
+            im = load_image_resize(im, img_size, augmentation)
         lb, _, pad = letterbox(im, new_shape, color=color, auto=auto, scale_fill=scale_fill, scale_up=scale_up, stride=stride)
         out.append(to_chw_rgb(lb))
         h, w = im.shape[:2]
-        shapes.append(((h, w), ((1.0, 1.0), pad)))
+        shapes.append(((h0, w0), ((h / h0, w / w0), pad)))
     return np.stack(out, 0), tuple(shapes)
 
 

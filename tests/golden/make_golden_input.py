@@ -24,10 +24,36 @@ CASES = [
 ]
 
 
+# decoded image shapes and img_size for the `_load_image` fixture (data_loader.py:294-350): INTER_AREA for the general, the
+# integer (3 x 3, 2 x 1 -> general in y) and the 2 x 2 ratios, INTER_LINEAR for the up-scale and under augmentation
+LOAD_CASES = [((150, 97), 64, False), ((97, 150), 64, False), ((192, 96), 64, False), ((128, 128), 64, False),
+              ((40, 31), 64, False), ((150, 97), 64, True), ((64, 50), 64, False), ((131, 200), 100, False)]
+
+
+def reference_load_image(dl, im, img_size, augmentation, tmpdir):
+    """The unmodified LoadImages._load_image on a PNG (lossless) of `im`."""
+    import cv2
+
+    path = os.path.join(tmpdir, "im.png")
+    cv2.imwrite(path, im)
+    fake = types.SimpleNamespace(imgs=[None], img_npy=[None], img_files=[path], img_size=img_size,
+                                 augmentation=(lambda x: x) if augmentation else None, cache_images=None)
+    out, hw0, hw = dl.LoadImages._load_image(fake, 0)
+    return out, hw0, hw
+
+
 def main():
+    import tempfile
+
     dl = ref_import.load_data_loader()
     fake = types.SimpleNamespace(img_size=128, stride=32)
     out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for li, ((h, w), size, aug) in enumerate(LOAD_CASES):
+            im = input_oracle.synth_images(300 + li, [(h, w)])[0]
+            res, hw0, hw = reference_load_image(dl, im, size, aug, tmp)
+            assert tuple(hw0) == (h, w) and tuple(hw) == res.shape[:2]
+            out[f"load{li}_in"], out[f"load{li}_out"] = im, res
     for ci, (new_shape, shapes, kw) in enumerate(CASES):
         imgs = input_oracle.synth_images(100 + ci, shapes)
         items, geo = [], []

@@ -97,3 +97,39 @@ def test_collate_fn_runs_inside_dataloader_workers():
         assert paths == tuple(f"img{i}.jpg" for i in range(seen, seen + pb.batch))
         seen += pb.batch
     assert seen == len(ds)
+
+
+def test_pack_batch_with_decode_side_resize():
+    """img_size: `_load_image`'s resize is planned by the host (data_loader.py:320-329) -- table of the resize kernel, scratch
+    space behind the uploaded bytes, letterbox records that read the resized images, the reference's shapes tuples."""
+    shapes = [(150, 97), (64, 50), (40, 31), (128, 128), (97, 150)]
+    imgs = input_oracle.synth_images(6, shapes)
+    pb = dl.pack_batch(imgs, (64, 64), img_size=64)
+    raw = pb.arena.numpy()
+    assert pb.host_bytes == raw.size and pb.n_load == 4 and pb.scratch_bytes > 0
+    rec = raw[:pb.table_bytes].view(dl._REC)
+    lstart = pb.table_bytes + pb.load_table_offset
+    lrec = raw[lstart:lstart + pb.n_load * dl._LOAD_REC.itemsize].view(dl._LOAD_REC)
+    _, ref_shapes = input_oracle.load_and_collate(imgs, (64, 64), img_size=64)
+    assert pb.shapes == ref_shapes
+    k = 0
+    for i, im in enumerate(imgs):
+        h0, w0 = im.shape[:2]
+        want = input_oracle.load_image_resize(im, 64)
+        assert (rec[i]["src_h"], rec[i]["src_w"]) == want.shape[:2]
+        if want is im:
+            assert rec[i]["src_offset"] + pb.table_bytes < pb.host_bytes
+            continue
+        r = lrec[k]
+        k += 1
+        assert (r["src_h"], r["src_w"], r["dst_h"], r["dst_w"]) == (h0, w0, want.shape[0], want.shape[1])
+        assert r["mode"] == (dl.LR_AREA if want.shape[0] < h0 else dl.LR_LINEAR)
+        assert r["dst_offset"] == rec[i]["src_offset"] and r["dst_offset"] + pb.table_bytes >= pb.host_bytes  # in the scratch space
+        assert r["dst_offset"] + pb.table_bytes + 3 * want.shape[0] * want.shape[1] <= pb.host_bytes + pb.scratch_bytes
+        start = pb.table_bytes + int(r["src_offset"])
+        assert np.array_equal(raw[start:start + im.size].reshape(im.shape), im)
+        assert r["scale_x"] == 1.0 / (want.shape[1] / w0) and r["scale_y"] == 1.0 / (want.shape[0] / h0)
+    assert k == pb.n_load and pb.max_dst_pixels == max(64 * 41, 64 * 49, 64 * 64, 41 * 64)
+    aug = dl.pack_batch(imgs[:1], (64, 64), img_size=64, augmentation=True)
+    l2 = aug.arena.numpy()[aug.table_bytes + aug.load_table_offset:][:64].view(dl._LOAD_REC)
+    assert l2[0]["mode"] == dl.LR_LINEAR

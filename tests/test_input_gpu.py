@@ -228,3 +228,80 @@ def test_candidate_overflow_redo_keeps_the_packed_input():
         assert small.nms_ws.p.max_candidates > 64, "the overflow must have been detected and the workspace grown"
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+from make_golden_input import LOAD_CASES  # noqa: E402
+
+
+def _resized_on_device(pb, staging):
+    """The images the resize kernel wrote into the scratch space, in table order."""
+    raw = pb.arena.numpy()
+    lstart = pb.table_bytes + pb.load_table_offset
+    lrec = raw[lstart:lstart + pb.n_load * dl._LOAD_REC.itemsize].view(dl._LOAD_REC)
+    dev = staging.cpu().numpy()
+    out = []
+    for r in lrec:
+        start = pb.table_bytes + int(r["dst_offset"])
+        out.append(dev[start:start + 3 * int(r["dst_h"]) * int(r["dst_w"])].reshape(int(r["dst_h"]), int(r["dst_w"]), 3))
+    return out
+
+
+def test_load_resize_equals_reference_golden():
+    """`_load_image`'s resize on the device (ay2_load_resize: INTER_AREA general / integer / 2 x 2, INTER_LINEAR) == the outputs
+    of the unmodified reference (PNG -> LoadImages._load_image), and the collated batch == the oracle's composition."""
+    g = np.load(GOLD)
+    for li, ((h, w), size, aug) in enumerate(LOAD_CASES):
+        im = g[f"load{li}_in"]
+        pb = dl.pack_batch([im], (size, size), img_size=size, augmentation=aug)
+        staging = torch.zeros(pb.host_bytes + pb.scratch_bytes, dtype=torch.uint8, device="cuda")
+        out = pb.to_device(staging=staging)
+        torch.cuda.synchronize()
+        want = g[f"load{li}_out"]
+        if pb.n_load:
+            got = _resized_on_device(pb, staging)[0]
+            diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            record(f"input/load_resize_vs_reference_golden_{li}", max_abs_diff=int(diff.max()), mismatching_bytes=int((diff > 0).sum()),
+                   bytes=int(diff.size))
+            assert np.array_equal(got, want), (li, (h, w), size, aug)
+        ref, ref_shapes = input_oracle.load_and_collate([im], (size, size), img_size=size, augmentation=aug)
+        assert np.array_equal(out.cpu().numpy(), ref) and pb.shapes == ref_shapes
+
+
+@pytest.mark.parametrize("img_size,aug", [(640, False), (96, False), (96, True)])
+def test_decoded_batch_equals_oracle(img_size, aug):
+    """Ragged decoded images -> collated batch: strong and weak shrinks, integer ratios (2, 3, 4), exact halves, up-scales,
+    images already at the size; against the oracle (pinned to cv2 and the reference)."""
+    rng = np.random.default_rng(img_size + aug)
+    S = img_size
+    shapes = [(S, S), (2 * S, 2 * S), (3 * S, 3 * S // 2), (4 * S, 4 * S), (2 * S, S), (S // 2, S // 3), (S + 1, S - 7), (5 * S // 2, 7 * S // 3),
+              (S, S // 2), (S - 1, S - 1)]
+    shapes += [(int(rng.integers(8, 3 * S)), int(rng.integers(8, 3 * S))) for _ in range(6)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    ref, ref_shapes = input_oracle.load_and_collate(imgs, (S, S), img_size=S, augmentation=aug)
+    pb = dl.pack_batch(imgs, (S, S), img_size=S, augmentation=aug, pin=True)
+    got = pb.to_device("cuda").cpu().numpy()
+    bad = [(i, shapes[i]) for i in range(len(imgs)) if not np.array_equal(got[i], ref[i])]
+    record(f"input/decoded_batch_vs_oracle_{S}_{'aug' if aug else 'val'}", images=len(imgs), mismatching_bytes=int((got != ref).sum()),
+           bytes=int(ref.size))
+    assert not bad, bad
+    assert pb.shapes == ref_shapes
+
+
+def test_detector_from_decoded_images():
+    from ayolov2_b200 import synth
+    from ayolov2_b200.detector import Detector
+
+    model = synth.build_model("yolov5s", seed=2).cuda()
+    B, S = 3, 256
+    imgs = input_oracle.synth_images(41, [(512, 384), (300, 411), (256, 256)])
+    ref_batch, ref_shapes = input_oracle.load_and_collate(imgs, (S, S), img_size=S)
+    host = torch.from_numpy(ref_batch)
+    sample = host.cuda().float() / 255.0
+    synth.calibrate_head(model, lambda: model(sample)[1], cand_frac=0.1)
+    det = Detector(model, B, S, S, conf_thres=0.25, iou_thres=0.45, in_dtype=torch.uint8)
+    want = det.detect(host.pin_memory())
+    pb = dl.pack_batch(imgs, (S, S), img_size=S, pin=True)
+    assert pb.shapes == ref_shapes and pb.n_load == 2
+    for fused in (True, False):
+        for a, b in zip(det.collect(det.submit_packed(pb, fused=fused)), want):
+            assert torch.equal(a, b)

@@ -96,3 +96,58 @@ def test_oracle_matches_the_unmodified_reference():
             got, ratio, pad = input_oracle.letterbox(im, (160, 128), **kw)
             assert np.array_equal(ref, got), (im.shape, kw)
             assert tuple(r_ratio) == tuple(ratio) and tuple(r_pad) == tuple(pad)
+
+
+from make_golden_input import LOAD_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("li", range(len(LOAD_CASES)))
+def test_load_image_resize_matches_reference_golden(li):
+    """`_load_image` after the decode (data_loader.py:320-329): outputs of the unmodified reference on PNG files."""
+    g = np.load(GOLD)
+    (h, w), size, aug = LOAD_CASES[li]
+    im = g[f"load{li}_in"]
+    assert im.shape == (h, w, 3)
+    got = input_oracle.load_image_resize(im, size, aug)
+    assert got.shape == g[f"load{li}_out"].shape and np.array_equal(got, g[f"load{li}_out"])
+
+
+@pytest.mark.skipif(not HAVE_CV2, reason="cv2 not installed")
+def test_area_restatement_is_bit_exact_against_cv2():
+    import cv2
+
+    rng = np.random.default_rng(2)
+    for t in range(120):
+        h, w = (int(v) for v in rng.integers(8, 260, 2))
+        if t % 5 == 0:  # integer ratios, equal and unequal
+            ky, kx = [(2, 2), (3, 3), (2, 3), (4, 2), (1, 2), (5, 5)][(t // 5) % 6]
+            dh, dw = max(h // ky, 1), max(w // kx, 1)
+            h, w = dh * ky, dw * kx
+        elif t % 5 == 1:  # what _load_image asks for
+            r = 64 / max(h, w)
+            if r >= 1:
+                continue
+            dw, dh = int(w * r), int(h * r)
+        else:
+            dh, dw = int(rng.integers(1, h + 1)), int(rng.integers(1, w + 1))
+        if (dh, dw) == (h, w) or dh < 1 or dw < 1:
+            continue
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(ref, input_oracle.resize_area_u8(img, dw, dh)), ((h, w), (dh, dw))
+
+
+@pytest.mark.skipif(not (ref_import.available() and HAVE_CV2), reason="reference tree / cv2 not present")
+def test_load_image_oracle_matches_the_unmodified_reference(tmp_path):
+    from make_golden_input import reference_load_image
+
+    dl = ref_import.load_data_loader()
+    rng = np.random.default_rng(3)
+    for case in range(10):
+        h, w = (int(v) for v in rng.integers(20, 300, 2))
+        size = int(rng.choice([64, 96, 160]))
+        aug = case % 3 == 2
+        im = input_oracle.synth_images(400 + case, [(h, w)])[0]
+        ref, _, _ = reference_load_image(dl, im, size, aug, str(tmp_path))
+        got = input_oracle.load_image_resize(im, size, aug)
+        assert ref.shape == got.shape and np.array_equal(ref, got), ((h, w), size, aug)
