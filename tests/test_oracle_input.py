@@ -151,3 +151,53 @@ def test_load_image_oracle_matches_the_unmodified_reference(tmp_path):
         ref, _, _ = reference_load_image(dl, im, size, aug, str(tmp_path))
         got = input_oracle.load_image_resize(im, size, aug)
         assert ref.shape == got.shape and np.array_equal(ref, got), ((h, w), size, aug)
+
+
+def _area_cells(d, ssize, scale):
+    """Per-pixel form of computeResizeAreaTab, as csrc/letterbox.cu (area_cells) evaluates it on the device."""
+    import math
+
+    fs1 = np.float64(d) * np.float64(scale)
+    fs2 = fs1 + np.float64(scale)
+    cell = min(np.float64(scale), np.float64(ssize) - fs1)
+    s1, s2 = int(math.ceil(fs1)), int(math.floor(fs2))
+    s2 = min(s2, ssize - 1)
+    s1 = min(s1, s2)
+    dl, dr = np.float64(s1) - fs1, fs2 - np.float64(s2)
+    f32 = np.float32
+    return s1, s2, dl > 1e-3, dr > 1e-3, f32(dl / cell), f32(np.float64(1.0) / cell), f32(min(min(dr, 1.0), cell) / cell)
+
+
+def _area_pixel(img, dx, dy, sx, sy):
+    """One output pixel of load_resize_kernel's general INTER_AREA branch: lines in order, cells in order, separate fp32
+    multiplies and adds."""
+    f32 = np.float32
+    h, w, _ = img.shape
+    x1, x2, xl, xr, xwl, xwm, xwr = _area_cells(dx, w, sx)
+    y1, y2, yl, yr, ywl, ywm, ywr = _area_cells(dy, h, sy)
+    cols = ([(x1 - 1, xwl)] if xl else []) + [(c, xwm) for c in range(x1, x2)] + ([(x2, xwr)] if xr else [])
+    rows = ([(y1 - 1, ywl)] if yl else []) + [(r, ywm) for r in range(y1, y2)] + ([(y2, ywr)] if yr else [])
+    total = np.zeros(3, f32)
+    for r, beta in rows:
+        buf = np.zeros(3, f32)
+        for c, alpha in cols:
+            buf = (buf + (img[r, c].astype(f32) * alpha).astype(f32)).astype(f32)
+        total = (total + (beta * buf).astype(f32)).astype(f32)
+    return np.clip(np.rint(total), 0, 255).astype(np.uint8)
+
+
+def test_per_pixel_area_formulation_equals_the_table_formulation():
+    """The device computes every output pixel on its own (cells and weights from the pixel index) while OpenCV and the oracle
+    build tables first: both must give the same bytes (this pins the kernel's algorithm on the CPU; the kernel itself is
+    compared with the oracle in tests/test_input_gpu.py)."""
+    rng = np.random.default_rng(0)
+    cases = [((30, 23), (13, 10)), ((31, 47), (30, 20)), ((17, 9), (17, 4)), ((50, 33), (7, 5)), ((40, 40), (39, 39)), ((9, 40), (3, 13))]
+    cases += [((int(h), int(w)), (int(rng.integers(1, h + 1)), int(rng.integers(1, w + 1)))) for h, w in rng.integers(4, 40, (8, 2))]
+    for (h, w), (dh, dw) in cases:
+        sx, sy = 1.0 / (float(dw) / float(w)), 1.0 / (float(dh) / float(h))
+        if (dh, dw) == (h, w) or (abs(sx - round(sx)) < 2.3e-16 and abs(sy - round(sy)) < 2.3e-16):
+            continue  # integer ratios take the cell-sum path
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = input_oracle.resize_area_u8(img, dw, dh)
+        got = np.stack([np.stack([_area_pixel(img, dx, dy, sx, sy) for dx in range(dw)], 0) for dy in range(dh)], 0)
+        assert np.array_equal(got, want), ((h, w), (dh, dw))
