@@ -50,3 +50,40 @@ def test_sass_uses_blackwell_tensor_path():
     for mnem in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
         assert mnem in sass, mnem
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_input_side_records_match_the_c_structs(tmp_path):
+    """The host writes ay2_letterbox_image / ay2_load_resize_image records as numpy structured arrays: their field offsets and
+    sizes must be what a C compiler makes of include/ay2.h (compiled here with gcc; plain C, no CUDA needed)."""
+    import shutil
+    import subprocess
+
+    import pytest
+
+    from ayolov2_b200 import data_loader as dl
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"ay2_letterbox_image": dl._REC, "ay2_load_resize_image": dl._LOAD_REC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ay2.h"', "int main(void) {"]
+    for name, dt in structs.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for field in dt.names:
+            lines.append(f'  printf("{name} {field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        name, field, value = line.split()
+        dt = structs[name]
+        if field == "size":
+            assert dt.itemsize == int(value), (name, dt.itemsize, value)
+        else:
+            assert dt.fields[field][1] == int(value), (name, field, dt.fields[field][1], value)
+        seen += 1
+    assert seen == sum(len(dt.names) + 1 for dt in structs.values())
